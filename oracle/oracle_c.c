@@ -1,0 +1,583 @@
+/* CPU oracle (plain C) for the integer/bit-exact parts of the DreamWaltz-G SDS hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Never linked into the product.
+ * Build: oracle/Makefile  (gcc -O2 -ffp-contract=off -fopenmp; contraction OFF is part of
+ * the specification: every fp32 +,-,*,/,sqrt below is a single IEEE-754 operation, and the
+ * CUDA kernels reproduce the same operation sequence so that radii, tile rectangles, sort
+ * keys, tile ranges and n_contrib are bit-exact).
+ *
+ * PARITY UNPINNED for both algorithms restated here:
+ *  (1) multi-resolution grid encoder  -- reference core/nerf/gridencoder/src/gridencoder.cu
+ *      (get_grid_index :66-84, kernel_grid :87-242, kernel_grid_backward :245-337,
+ *      kernel_input_backward :340-366).  The reference kernel is CUDA-only and cannot be
+ *      executed in the build container (no GPU), so this is a restatement.
+ *  (2) tile-based EWA Gaussian rasteriser fwd+bwd -- third-party
+ *      ashawkey/diff-gaussian-rasterization @ git HEAD (reference scripts/install.sh:30),
+ *      NOT vendored under /root/reference; restated from the published algorithm
+ *      (SURVEY.md appendix B), anchored on the reference call site
+ *      core/gaussian/gaussian_renderer.py:186-195.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------ */
+/* (1) grid encoder                                                                      */
+/* ------------------------------------------------------------------------------------ */
+static inline uint32_t grid_index(int gridtype, int align_corners, uint32_t hashmap_size,
+                                  uint32_t resolution, const uint32_t pg[3]) {
+    /* gridencoder.cu:66-84 (D=3): accumulate while stride <= hashmap_size, then modulo;
+       hash (primes) only when gridtype==0 and the dense index would overflow the level. */
+    uint32_t stride = 1, index = 0;
+    for (int d = 0; d < 3 && stride <= hashmap_size; d++) {
+        index += pg[d] * stride;
+        stride *= align_corners ? resolution : (resolution + 1);
+    }
+    if (gridtype == 0 && stride > hashmap_size) {
+        index = (pg[0] * 1u) ^ (pg[1] * 2654435761u) ^ (pg[2] * 805459861u);
+    }
+    return index % hashmap_size;
+}
+
+/* x01: inputs already mapped to [0,1] ([B,3]); table [rows,C]; level_scale/level_res are
+   the host-computed per-level constants (scale = exp2f(l*S)*H - 1, res = ceil(scale)+1).
+   out [B, L*C] (final layout of grid.py:61); dy_dx [B, L*3*C] or NULL (grid.py:54). */
+void orc_grid_forward(const float* x01, const float* table, const int* offsets,
+                      const float* level_scale, const uint32_t* level_res,
+                      int B, int L, int C, int gridtype, int align_corners, int interp,
+                      float* out, float* dy_dx, uint32_t* corner_index /* [B,L,8] or NULL */) {
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; b++) {
+        const float* x = x01 + (size_t)b * 3;
+        int oob = 0;
+        for (int d = 0; d < 3; d++) if (x[d] < 0 || x[d] > 1) oob = 1;
+        for (int l = 0; l < L; l++) {
+            float* o = out + (size_t)b * L * C + (size_t)l * C;
+            float* dd = dy_dx ? dy_dx + (size_t)b * L * 3 * C + (size_t)l * 3 * C : NULL;
+            if (oob) {
+                for (int c = 0; c < C; c++) o[c] = 0;
+                if (dd) for (int k = 0; k < 3 * C; k++) dd[k] = 0;
+                if (corner_index) for (int k = 0; k < 8; k++) corner_index[((size_t)b * L + l) * 8 + k] = 0xffffffffu;
+                continue;
+            }
+            const float* g = table + (size_t)offsets[l] * C;
+            uint32_t hs = (uint32_t)(offsets[l + 1] - offsets[l]);
+            float scale = level_scale[l];
+            uint32_t res = level_res[l];
+            float pos[3], pderiv[3] = {1.f, 1.f, 1.f};
+            uint32_t pg[3];
+            for (int d = 0; d < 3; d++) {
+                pos[d] = fmaf(x[d], scale, align_corners ? 0.0f : 0.5f);
+                float fl = floorf(pos[d]);
+                pg[d] = (uint32_t)fl;
+                pos[d] -= fl;
+                if (interp == 1) {
+                    float v = pos[d];
+                    pderiv[d] = 6 * v * (1.0f - v);
+                    pos[d] = v * v * (3.0f - 2.0f * v);
+                }
+            }
+            float r[8] = {0};
+            for (int idx = 0; idx < 8; idx++) {
+                float w = 1; uint32_t pl[3];
+                for (int d = 0; d < 3; d++) {
+                    if ((idx & (1 << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+                    else { w *= pos[d]; pl[d] = pg[d] + 1; }
+                }
+                uint32_t gi = grid_index(gridtype, align_corners, hs, res, pl);
+                if (corner_index) corner_index[((size_t)b * L + l) * 8 + idx] = (uint32_t)offsets[l] + gi;
+                for (int c = 0; c < C; c++) r[c] += w * g[(size_t)gi * C + c];
+            }
+            for (int c = 0; c < C; c++) o[c] = r[c];
+            if (dd) {
+                for (int gd = 0; gd < 3; gd++) {
+                    float rg[8] = {0};
+                    for (int idx = 0; idx < 4; idx++) {
+                        float w = scale; uint32_t pl[3];
+                        for (int nd = 0; nd < 2; nd++) {
+                            int d = (nd >= gd) ? nd + 1 : nd;
+                            if ((idx & (1 << nd)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+                            else { w *= pos[d]; pl[d] = pg[d] + 1; }
+                        }
+                        pl[gd] = pg[gd];
+                        uint32_t il = grid_index(gridtype, align_corners, hs, res, pl);
+                        pl[gd] = pg[gd] + 1;
+                        uint32_t ir = grid_index(gridtype, align_corners, hs, res, pl);
+                        for (int c = 0; c < C; c++)
+                            rg[c] += w * (g[(size_t)ir * C + c] - g[(size_t)il * C + c]) * pderiv[gd];
+                    }
+                    for (int c = 0; c < C; c++) dd[gd * C + c] = rg[c];
+                }
+            }
+        }
+    }
+}
+
+/* grad [B, L*C]; grad_table must be zero-initialised (accumulated in double then the caller
+   casts); grad_x [B,3] or NULL uses dy_dx (kernel_input_backward). */
+void orc_grid_backward(const float* grad, const float* x01, const int* offsets,
+                       const float* level_scale, const uint32_t* level_res,
+                       int B, int L, int C, int gridtype, int align_corners, int interp,
+                       double* grad_table, const float* dy_dx, float* grad_x) {
+    for (int b = 0; b < B; b++) {            /* serial: deterministic accumulation order */
+        const float* x = x01 + (size_t)b * 3;
+        int oob = 0;
+        for (int d = 0; d < 3; d++) if (x[d] < 0 || x[d] > 1) oob = 1;
+        if (oob) continue;
+        for (int l = 0; l < L; l++) {
+            uint32_t hs = (uint32_t)(offsets[l + 1] - offsets[l]);
+            float scale = level_scale[l];
+            uint32_t res = level_res[l];
+            float pos[3]; uint32_t pg[3];
+            for (int d = 0; d < 3; d++) {
+                pos[d] = fmaf(x[d], scale, align_corners ? 0.0f : 0.5f);
+                float fl = floorf(pos[d]);
+                pg[d] = (uint32_t)fl;
+                pos[d] -= fl;
+                if (interp == 1) { float v = pos[d]; pos[d] = v * v * (3.0f - 2.0f * v); }
+            }
+            const float* gr = grad + (size_t)b * L * C + (size_t)l * C;
+            for (int idx = 0; idx < 8; idx++) {
+                float w = 1; uint32_t pl[3];
+                for (int d = 0; d < 3; d++) {
+                    if ((idx & (1 << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+                    else { w *= pos[d]; pl[d] = pg[d] + 1; }
+                }
+                uint32_t gi = grid_index(gridtype, align_corners, hs, res, pl);
+                for (int c = 0; c < C; c++)
+                    grad_table[((size_t)offsets[l] + gi) * C + c] += (double)(w * gr[c]);
+            }
+        }
+    }
+    if (grad_x && dy_dx) {
+        for (int b = 0; b < B; b++)
+            for (int d = 0; d < 3; d++) {
+                float r = 0;
+                for (int l = 0; l < L; l++)
+                    for (int c = 0; c < C; c++)
+                        r += grad[(size_t)b * L * C + l * C + c] * dy_dx[(size_t)b * L * 3 * C + l * 3 * C + d * C + c];
+                grad_x[(size_t)b * 3 + d] = r;
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* (2) Gaussian rasteriser                                                               */
+/* ------------------------------------------------------------------------------------ */
+#define TILE 16
+
+/* exp(x) for x <= 0, specified operation-by-operation so that CPU and GPU agree bit for bit:
+   n = rint(x*log2e); r = x - n*ln2 (two-step, fma); e^r = 1 + r + r^2*P5(r) (Horner, fma);
+   result = e^r * 2^n (exponent built from bits).  ~1 ulp. */
+static inline float spec_expf(float x) {
+    if (x < -87.0f) return 0.0f;
+    float t = x * 1.44269504088896341f;
+    float n = rintf(t);
+    float r = fmaf(n, -0.693145751953125f, x);
+    r = fmaf(n, -1.42860682030941723e-6f, r);
+    float p = 1.9875691500e-4f;
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    float z = r * r;
+    float y = fmaf(p, z, r);
+    y = y + 1.0f;
+    int32_t bits = ((int32_t)n + 127) << 23;
+    float s; memcpy(&s, &bits, 4);
+    return y * s;
+}
+float orc_spec_expf(float x) { return spec_expf(x); }
+
+typedef struct {
+    int H, W;
+    float tanfovx, tanfovy;
+    float view[16];   /* row-vector convention, row-major flat: p_view_k = sum_i p_i view[i*4+k] */
+    float proj[16];
+    float bg[3];
+    float scale_modifier;
+} OrcCamera;
+
+static inline void xform4x3(const float* p, const float* m, float* o) {
+    o[0] = m[0] * p[0] + m[4] * p[1] + m[8] * p[2] + m[12];
+    o[1] = m[1] * p[0] + m[5] * p[1] + m[9] * p[2] + m[13];
+    o[2] = m[2] * p[0] + m[6] * p[1] + m[10] * p[2] + m[14];
+}
+static inline void xform4x4(const float* p, const float* m, float* o) {
+    o[0] = m[0] * p[0] + m[4] * p[1] + m[8] * p[2] + m[12];
+    o[1] = m[1] * p[0] + m[5] * p[1] + m[9] * p[2] + m[13];
+    o[2] = m[2] * p[0] + m[6] * p[1] + m[10] * p[2] + m[14];
+    o[3] = m[3] * p[0] + m[7] * p[1] + m[11] * p[2] + m[15];
+}
+
+/* Sigma = R diag(s)^2 R^T, R from the (unnormalised) real-first quaternion; 6 unique terms. */
+static inline void cov3d_from_scale_rot(const float* s3, float mod, const float* q, float* c6) {
+    float r = q[0], x = q[1], y = q[2], z = q[3];
+    float R[3][3] = {
+        {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+        {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+        {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+    float s[3] = {mod * s3[0], mod * s3[1], mod * s3[2]};
+    float M[3][3];                       /* M = R * diag(s):  M[i][k] = R[i][k]*s[k] */
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) M[i][k] = R[i][k] * s[k];
+    /* Sigma[i][j] = sum_k M[i][k]*M[j][k], summed k = 0,1,2 left to right */
+    int t = 0;
+    for (int i = 0; i < 3; i++) for (int j = i; j < 3; j++)
+        c6[t++] = M[i][0] * M[j][0] + M[i][1] * M[j][1] + M[i][2] * M[j][2];
+}
+
+/* EWA: cov2D = (J W) Sigma (J W)^T with the 1.3*tanfov clamp; returns (a,b,c) incl. +0.3. */
+static inline void cov2d(const float* tview, float fx, float fy, float tanfovx, float tanfovy,
+                         const float* c6, const float* view, float* abc, float* Tm /* 2x3 */) {
+    float tx = tview[0], ty = tview[1], tz = tview[2];
+    float limx = 1.3f * tanfovx, limy = 1.3f * tanfovy;
+    float txtz = tx / tz, tytz = ty / tz;
+    tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+    ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+    float J00 = fx / tz, J02 = -(fx * tx) / (tz * tz);
+    float J11 = fy / tz, J12 = -(fy * ty) / (tz * tz);
+    /* W[r][c] = view[c*4 + r] (rotation part of world->view, column-vector form) */
+    float T[2][3];
+    for (int c = 0; c < 3; c++) {
+        T[0][c] = J00 * view[c * 4 + 0] + J02 * view[c * 4 + 2];
+        T[1][c] = J11 * view[c * 4 + 1] + J12 * view[c * 4 + 2];
+    }
+    float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+    float TS[2][3];
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 3; j++)
+        TS[i][j] = T[i][0] * S[0][j] + T[i][1] * S[1][j] + T[i][2] * S[2][j];
+    abc[0] = TS[0][0] * T[0][0] + TS[0][1] * T[0][1] + TS[0][2] * T[0][2] + 0.3f;
+    abc[1] = TS[0][0] * T[1][0] + TS[0][1] * T[1][1] + TS[0][2] * T[1][2];
+    abc[2] = TS[1][0] * T[1][0] + TS[1][1] * T[1][1] + TS[1][2] * T[1][2] + 0.3f;
+    if (Tm) memcpy(Tm, T, sizeof(T));
+}
+
+/* Per-Gaussian preprocess.  Outputs (all length N unless noted): radii i32, xy [N,2],
+   depth, cov3D [N,6], conic_opacity [N,4], rect [N,4] = (xmin,ymin,xmax,ymax) in tiles,
+   tiles_touched u32.  Returns total P = sum tiles_touched. */
+int64_t orc_raster_preprocess(int N, const float* means3D, const float* scales, const float* rots,
+                              const float* opacities, const OrcCamera* cam,
+                              int32_t* radii, float* xy, float* depth, float* cov3D,
+                              float* conic_opacity, int32_t* rect, uint32_t* tiles_touched) {
+    const int H = cam->H, W = cam->W;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const float fx = W / (2.0f * cam->tanfovx), fy = H / (2.0f * cam->tanfovy);
+    int64_t P = 0;
+#pragma omp parallel for schedule(static) reduction(+ : P)
+    for (int i = 0; i < N; i++) {
+        radii[i] = 0; tiles_touched[i] = 0;
+        xy[2 * i] = xy[2 * i + 1] = 0; depth[i] = 0;
+        for (int k = 0; k < 4; k++) { conic_opacity[4 * i + k] = 0; rect[4 * i + k] = 0; }
+        for (int k = 0; k < 6; k++) cov3D[6 * i + k] = 0;
+        const float* p = means3D + 3 * (size_t)i;
+        float pv[3]; xform4x3(p, cam->view, pv);
+        if (pv[2] <= 0.2f) continue;
+        float ph[4]; xform4x4(p, cam->proj, ph);
+        float pw = 1.0f / (ph[3] + 0.0000001f);
+        float pp[2] = {ph[0] * pw, ph[1] * pw};
+        float c6[6]; cov3d_from_scale_rot(scales + 3 * (size_t)i, cam->scale_modifier, rots + 4 * (size_t)i, c6);
+        memcpy(cov3D + 6 * (size_t)i, c6, sizeof(c6));
+        float abc[3]; cov2d(pv, fx, fy, cam->tanfovx, cam->tanfovy, c6, cam->view, abc, NULL);
+        float det = abc[0] * abc[2] - abc[1] * abc[1];
+        if (det == 0.0f) continue;
+        float det_inv = 1.f / det;
+        float conic[3] = {abc[2] * det_inv, -abc[1] * det_inv, abc[0] * det_inv};
+        float mid = 0.5f * (abc[0] + abc[2]);
+        float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+        float l1 = mid + sq, l2 = mid - sq;
+        float my_radius = ceilf(3.f * sqrtf(fmaxf(l1, l2)));
+        /* ndc2Pix is evaluated in double upstream (double literals) */
+        float px = (float)((((double)pp[0] + 1.0) * (double)W - 1.0) * 0.5);
+        float py = (float)((((double)pp[1] + 1.0) * (double)H - 1.0) * 0.5);
+        int r = (int)my_radius;
+        int x0 = (int)((px - r) / TILE), y0 = (int)((py - r) / TILE);
+        int x1 = (int)((px + r + TILE - 1) / TILE), y1 = (int)((py + r + TILE - 1) / TILE);
+        x0 = x0 < 0 ? 0 : (x0 > gx ? gx : x0); y0 = y0 < 0 ? 0 : (y0 > gy ? gy : y0);
+        x1 = x1 < 0 ? 0 : (x1 > gx ? gx : x1); y1 = y1 < 0 ? 0 : (y1 > gy ? gy : y1);
+        if ((x1 - x0) * (y1 - y0) == 0) continue;
+        depth[i] = pv[2]; radii[i] = r; xy[2 * i] = px; xy[2 * i + 1] = py;
+        conic_opacity[4 * i + 0] = conic[0]; conic_opacity[4 * i + 1] = conic[1];
+        conic_opacity[4 * i + 2] = conic[2]; conic_opacity[4 * i + 3] = opacities[i];
+        rect[4 * i + 0] = x0; rect[4 * i + 1] = y0; rect[4 * i + 2] = x1; rect[4 * i + 3] = y1;
+        tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
+        P += tiles_touched[i];
+    }
+    return P;
+}
+
+typedef struct { uint64_t k; uint32_t v; } KV;
+static int kv_cmp(const void* a, const void* b) {
+    const KV* x = (const KV*)a; const KV* y = (const KV*)b;
+    if (x->k != y->k) return x->k < y->k ? -1 : 1;
+    return x->v < y->v ? -1 : (x->v > y->v);       /* stable radix == ascending emit order == idx */
+}
+
+/* Emit (tile<<32 | depth bits, idx), sort, find per-tile ranges [start,end). */
+void orc_raster_bin(int N, const OrcCamera* cam, const float* depth, const int32_t* rect,
+                    const uint32_t* tiles_touched, int64_t P, uint64_t* keys, uint32_t* vals,
+                    uint32_t* ranges /* [tiles,2] */) {
+    const int gx = (cam->W + TILE - 1) / TILE, gy = (cam->H + TILE - 1) / TILE;
+    KV* kv = (KV*)malloc(sizeof(KV) * (size_t)(P > 0 ? P : 1));
+    int64_t off = 0;
+    for (int i = 0; i < N; i++) {
+        if (!tiles_touched[i]) continue;
+        uint32_t db; memcpy(&db, depth + i, 4);
+        for (int y = rect[4 * i + 1]; y < rect[4 * i + 3]; y++)
+            for (int x = rect[4 * i + 0]; x < rect[4 * i + 2]; x++) {
+                kv[off].k = ((uint64_t)(y * gx + x) << 32) | db;
+                kv[off].v = (uint32_t)i;
+                off++;
+            }
+    }
+    qsort(kv, (size_t)P, sizeof(KV), kv_cmp);
+    memset(ranges, 0, sizeof(uint32_t) * 2 * (size_t)gx * gy);
+    for (int64_t j = 0; j < P; j++) {
+        keys[j] = kv[j].k; vals[j] = kv[j].v;
+        uint32_t t = (uint32_t)(kv[j].k >> 32);
+        if (j == 0) ranges[2 * t] = 0;
+        else {
+            uint32_t tp = (uint32_t)(kv[j - 1].k >> 32);
+            if (t != tp) { ranges[2 * tp + 1] = (uint32_t)j; ranges[2 * t] = (uint32_t)j; }
+        }
+        if (j == P - 1) ranges[2 * t + 1] = (uint32_t)P;
+    }
+    free(kv);
+}
+
+/* alpha of Gaussian g at pixel (px,py); returns 0 if skipped. */
+static inline int eval_alpha(const float* xy, const float* co, float pxf, float pyf, float* alpha, float* G,
+                             float* dx, float* dy) {
+    float ddx = xy[0] - pxf, ddy = xy[1] - pyf;
+    float power = -0.5f * (co[0] * ddx * ddx + co[2] * ddy * ddy) - co[1] * ddx * ddy;
+    if (power > 0.0f) return 0;
+    float g = spec_expf(power);
+    float a = fminf(0.99f, co[3] * g);
+    if (a < 1.0f / 255.0f) return 0;
+    *alpha = a; *G = g; *dx = ddx; *dy = ddy;
+    return 1;
+}
+
+void orc_raster_render(const OrcCamera* cam, const uint32_t* ranges, const uint32_t* vals,
+                       const float* xy, const float* conic_opacity, const float* colors /* [N,3] */,
+                       const float* depth, float* out_color /* [3,H,W] */, float* out_depth, float* out_alpha,
+                       float* final_T, uint32_t* n_contrib) {
+    const int H = cam->H, W = cam->W;
+    const int gx = (W + TILE - 1) / TILE;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int pix = 0; pix < H * W; pix++) {
+        int py = pix / W, px = pix % W;
+        int tile = (py / TILE) * gx + (px / TILE);
+        uint32_t s = ranges[2 * tile], e = ranges[2 * tile + 1];
+        float T = 1.0f, C[3] = {0, 0, 0}, D = 0, A = 0;
+        uint32_t contributor = 0, last = 0;
+        for (uint32_t j = s; j < e; j++) {
+            contributor++;
+            uint32_t g = vals[j];
+            float alpha, G, dx, dy;
+            if (!eval_alpha(xy + 2 * (size_t)g, conic_opacity + 4 * (size_t)g, (float)px, (float)py, &alpha, &G, &dx, &dy))
+                continue;
+            float test_T = T * (1 - alpha);
+            if (test_T < 0.0001f) break;
+            float w = alpha * T;
+            for (int c = 0; c < 3; c++) C[c] += colors[3 * (size_t)g + c] * w;
+            D += depth[g] * w;
+            A += w;
+            T = test_T;
+            last = contributor;
+        }
+        final_T[pix] = T; n_contrib[pix] = last;
+        for (int c = 0; c < 3; c++) out_color[(size_t)c * H * W + pix] = C[c] + T * cam->bg[c];
+        out_depth[pix] = D; out_alpha[pix] = A;
+    }
+}
+
+/* Backward of the blend (per pixel, back to front) accumulated serially in double so the
+   oracle is deterministic; outputs are per-Gaussian: dL_dmean2D [N,2], dL_dconic [N,3]
+   (xx, xy, yy as accumulated upstream: .y holds the single off-diagonal term),
+   dL_dopacity [N], dL_dcolor [N,3], dL_ddepth [N]. */
+void orc_raster_render_backward(const OrcCamera* cam, const uint32_t* ranges, const uint32_t* vals,
+                                const float* xy, const float* conic_opacity, const float* colors,
+                                const float* depth, const float* final_T, const uint32_t* n_contrib,
+                                const float* dL_dcolor_pix /* [3,H,W] */, const float* dL_ddepth_pix,
+                                const float* dL_dalpha_pix, int N,
+                                double* g_mean2D, double* g_conic, double* g_opacity, double* g_color,
+                                double* g_depth) {
+    const int H = cam->H, W = cam->W;
+    const int gx = (W + TILE - 1) / TILE;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    for (int pix = 0; pix < H * W; pix++) {
+        int py = pix / W, px = pix % W;
+        int tile = (py / TILE) * gx + (px / TILE);
+        uint32_t s = ranges[2 * tile];
+        const float T_final = final_T[pix];
+        float T = T_final;
+        uint32_t last_contributor = n_contrib[pix];
+        float dLp[3] = {dL_dcolor_pix[pix], dL_dcolor_pix[(size_t)H * W + pix], dL_dcolor_pix[2 * (size_t)H * W + pix]};
+        float dLd = dL_ddepth_pix ? dL_ddepth_pix[pix] : 0.f;
+        float dLa = dL_dalpha_pix ? dL_dalpha_pix[pix] : 0.f;
+        float accum_rec[3] = {0, 0, 0}, accum_d = 0, accum_a = 0;
+        float last_alpha = 0, last_color[3] = {0, 0, 0}, last_depth = 0;
+        float bg_dot = cam->bg[0] * dLp[0] + cam->bg[1] * dLp[1] + cam->bg[2] * dLp[2];
+        for (int64_t k = (int64_t)last_contributor - 1; k >= 0; k--) {
+            uint32_t g = vals[s + k];
+            const float* co = conic_opacity + 4 * (size_t)g;
+            float alpha, G, dx, dy;
+            if (!eval_alpha(xy + 2 * (size_t)g, co, (float)px, (float)py, &alpha, &G, &dx, &dy)) continue;
+            T = T / (1.f - alpha);
+            const float dchannel_dcolor = alpha * T;
+            float dL_dalpha = 0.f;
+            for (int c = 0; c < 3; c++) {
+                float col = colors[3 * (size_t)g + c];
+                accum_rec[c] = last_alpha * last_color[c] + (1.f - last_alpha) * accum_rec[c];
+                last_color[c] = col;
+                dL_dalpha += (col - accum_rec[c]) * dLp[c];
+                g_color[3 * (size_t)g + c] += (double)(dchannel_dcolor * dLp[c]);
+            }
+            float dep = depth[g];
+            accum_d = last_alpha * last_depth + (1.f - last_alpha) * accum_d;
+            last_depth = dep;
+            dL_dalpha += (dep - accum_d) * dLd;
+            g_depth[g] += (double)(dchannel_dcolor * dLd);
+            accum_a = last_alpha + (1.f - last_alpha) * accum_a;
+            dL_dalpha += (1.f - accum_a) * dLa;
+            dL_dalpha *= T;
+            last_alpha = alpha;
+            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+            const float dL_dG = co[3] * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            const float dG_ddelx = -gdx * co[0] - gdy * co[1];
+            const float dG_ddely = -gdy * co[2] - gdx * co[1];
+            g_mean2D[2 * (size_t)g + 0] += (double)(dL_dG * dG_ddelx * ddelx_dx);
+            g_mean2D[2 * (size_t)g + 1] += (double)(dL_dG * dG_ddely * ddely_dy);
+            g_conic[3 * (size_t)g + 0] += (double)(-0.5f * gdx * dx * dL_dG);
+            g_conic[3 * (size_t)g + 1] += (double)(-0.5f * gdx * dy * dL_dG);
+            g_conic[3 * (size_t)g + 2] += (double)(-0.5f * gdy * dy * dL_dG);
+            g_opacity[g] += (double)(G * dL_dalpha);
+        }
+    }
+    (void)N;
+}
+
+/* Backward of preprocess: (dL_dmean2D, dL_dconic, dL_ddepth) -> dL_dmeans3D [N,3],
+   dL_dscales [N,3], dL_drots [N,4].  Follows the published computeCov2D / preprocess /
+   computeCov3D backward (float arithmetic, tolerance-compared). */
+void orc_raster_preprocess_backward(int N, const float* means3D, const float* scales, const float* rots,
+                                    const OrcCamera* cam, const int32_t* radii, const float* cov3D,
+                                    const float* g_mean2D /* [N,2] */, const float* g_conic /* [N,3] */,
+                                    const float* g_depth /* [N] */,
+                                    float* g_means3D, float* g_scales, float* g_rots) {
+    const int H = cam->H, W = cam->W;
+    const float fx = W / (2.0f * cam->tanfovx), fy = H / (2.0f * cam->tanfovy);
+    const float* view = cam->view; const float* proj = cam->proj;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        for (int k = 0; k < 3; k++) { g_means3D[3 * i + k] = 0; g_scales[3 * i + k] = 0; }
+        for (int k = 0; k < 4; k++) g_rots[4 * i + k] = 0;
+        if (radii[i] <= 0) continue;
+        const float* p = means3D + 3 * (size_t)i;
+        const float* c6 = cov3D + 6 * (size_t)i;
+        /* ---- cov2D backward ---- */
+        float t[3]; xform4x3(p, view, t);
+        const float limx = 1.3f * cam->tanfovx, limy = 1.3f * cam->tanfovy;
+        const float txtz = t[0] / t[2], tytz = t[1] / t[2];
+        t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
+        t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
+        const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+        const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+        float J00 = fx / t[2], J02 = -(fx * t[0]) / (t[2] * t[2]);
+        float J11 = fy / t[2], J12 = -(fy * t[1]) / (t[2] * t[2]);
+        float T[2][3];
+        for (int c = 0; c < 3; c++) {
+            T[0][c] = J00 * view[c * 4 + 0] + J02 * view[c * 4 + 2];
+            T[1][c] = J11 * view[c * 4 + 1] + J12 * view[c * 4 + 2];
+        }
+        float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+        float TS[2][3];
+        for (int r = 0; r < 2; r++) for (int j = 0; j < 3; j++)
+            TS[r][j] = T[r][0] * S[0][j] + T[r][1] * S[1][j] + T[r][2] * S[2][j];
+        float a = TS[0][0] * T[0][0] + TS[0][1] * T[0][1] + TS[0][2] * T[0][2] + 0.3f;
+        float b = TS[0][0] * T[1][0] + TS[0][1] * T[1][1] + TS[0][2] * T[1][2];
+        float c = TS[1][0] * T[1][0] + TS[1][1] * T[1][1] + TS[1][2] * T[1][2] + 0.3f;
+        float denom = a * c - b * b;
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        float dcx = g_conic[3 * i + 0], dcy = g_conic[3 * i + 1], dcz = g_conic[3 * i + 2];
+        float dL_dcov[6] = {0, 0, 0, 0, 0, 0};
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-c * c * dcx + 2 * b * c * dcy + (denom - a * c) * dcz);
+            dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c) * dcx);
+            dL_db = denom2inv * 2 * (b * c * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
+            /* cov2D = T Sigma T^T : dL/dSigma_jk (symmetric, off-diagonals counted twice) */
+            dL_dcov[0] = T[0][0] * T[0][0] * dL_da + T[0][0] * T[1][0] * dL_db + T[1][0] * T[1][0] * dL_dc;
+            dL_dcov[3] = T[0][1] * T[0][1] * dL_da + T[0][1] * T[1][1] * dL_db + T[1][1] * T[1][1] * dL_dc;
+            dL_dcov[5] = T[0][2] * T[0][2] * dL_da + T[0][2] * T[1][2] * dL_db + T[1][2] * T[1][2] * dL_dc;
+            dL_dcov[1] = 2 * T[0][0] * T[0][1] * dL_da + (T[0][0] * T[1][1] + T[0][1] * T[1][0]) * dL_db + 2 * T[1][0] * T[1][1] * dL_dc;
+            dL_dcov[2] = 2 * T[0][0] * T[0][2] * dL_da + (T[0][0] * T[1][2] + T[0][2] * T[1][0]) * dL_db + 2 * T[1][0] * T[1][2] * dL_dc;
+            dL_dcov[4] = 2 * T[0][2] * T[0][1] * dL_da + (T[0][1] * T[1][2] + T[0][2] * T[1][1]) * dL_db + 2 * T[1][1] * T[1][2] * dL_dc;
+        }
+        /* dL/dT (2x3) */
+        float dL_dT[2][3];
+        for (int j = 0; j < 3; j++) {
+            dL_dT[0][j] = 2 * (T[0][0] * S[j][0] + T[0][1] * S[j][1] + T[0][2] * S[j][2]) * dL_da
+                        + (T[1][0] * S[j][0] + T[1][1] * S[j][1] + T[1][2] * S[j][2]) * dL_db;
+            dL_dT[1][j] = 2 * (T[1][0] * S[j][0] + T[1][1] * S[j][1] + T[1][2] * S[j][2]) * dL_dc
+                        + (T[0][0] * S[j][0] + T[0][1] * S[j][1] + T[0][2] * S[j][2]) * dL_db;
+        }
+        /* T[0][c] = J00*Wr0c + J02*Wr2c, with Wrkc = view[c*4+k] */
+        float dL_dJ00 = 0, dL_dJ02 = 0, dL_dJ11 = 0, dL_dJ12 = 0;
+        for (int cc = 0; cc < 3; cc++) {
+            dL_dJ00 += view[cc * 4 + 0] * dL_dT[0][cc];
+            dL_dJ02 += view[cc * 4 + 2] * dL_dT[0][cc];
+            dL_dJ11 += view[cc * 4 + 1] * dL_dT[1][cc];
+            dL_dJ12 += view[cc * 4 + 2] * dL_dT[1][cc];
+        }
+        float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
+        float dL_dtx = x_grad_mul * -fx * tz2 * dL_dJ02;
+        float dL_dty = y_grad_mul * -fy * tz2 * dL_dJ12;
+        float dL_dtz = -fx * tz2 * dL_dJ00 - fy * tz2 * dL_dJ11 + (2 * fx * t[0]) * tz3 * dL_dJ02 + (2 * fy * t[1]) * tz3 * dL_dJ12;
+        /* t = W p + trans : dL/dp = W^T dL/dt ; W^T[k][r] = view[k*4+r] */
+        float gm[3];
+        for (int k = 0; k < 3; k++)
+            gm[k] = view[k * 4 + 0] * dL_dtx + view[k * 4 + 1] * dL_dty + view[k * 4 + 2] * dL_dtz;
+        /* ---- mean2D -> mean3D through the perspective divide ---- */
+        float m_hom[4]; xform4x4(p, proj, m_hom);
+        float m_w = 1.0f / (m_hom[3] + 0.0000001f);
+        float mul1 = (proj[0] * p[0] + proj[4] * p[1] + proj[8] * p[2] + proj[12]) * m_w * m_w;
+        float mul2 = (proj[1] * p[0] + proj[5] * p[1] + proj[9] * p[2] + proj[13]) * m_w * m_w;
+        float d2x = g_mean2D[2 * i + 0], d2y = g_mean2D[2 * i + 1];
+        gm[0] += (proj[0] * m_w - proj[3] * mul1) * d2x + (proj[1] * m_w - proj[3] * mul2) * d2y;
+        gm[1] += (proj[4] * m_w - proj[7] * mul1) * d2x + (proj[5] * m_w - proj[7] * mul2) * d2y;
+        gm[2] += (proj[8] * m_w - proj[11] * mul1) * d2x + (proj[9] * m_w - proj[11] * mul2) * d2y;
+        /* ---- depth -> mean3D through the view z row ---- */
+        float gd = g_depth ? g_depth[i] : 0.f;
+        gm[0] += view[2] * gd; gm[1] += view[6] * gd; gm[2] += view[10] * gd;
+        for (int k = 0; k < 3; k++) g_means3D[3 * i + k] = gm[k];
+        /* ---- cov3D -> scale, rotation ---- */
+        const float* q = rots + 4 * (size_t)i;
+        float r = q[0], x = q[1], y = q[2], z = q[3];
+        float R[3][3] = {
+            {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+            {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+            {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+        float s[3] = {cam->scale_modifier * scales[3 * i], cam->scale_modifier * scales[3 * i + 1], cam->scale_modifier * scales[3 * i + 2]};
+        /* Sigma = M M^T with M = R diag(s).  dL/dSigma full symmetric matrix (off-diag halves) */
+        float dS[3][3] = {{dL_dcov[0], 0.5f * dL_dcov[1], 0.5f * dL_dcov[2]},
+                          {0.5f * dL_dcov[1], dL_dcov[3], 0.5f * dL_dcov[4]},
+                          {0.5f * dL_dcov[2], 0.5f * dL_dcov[4], dL_dcov[5]}};
+        float M[3][3], dM[3][3];
+        for (int a_ = 0; a_ < 3; a_++) for (int k = 0; k < 3; k++) M[a_][k] = R[a_][k] * s[k];
+        for (int a_ = 0; a_ < 3; a_++) for (int k = 0; k < 3; k++)
+            dM[a_][k] = 2.f * (dS[a_][0] * M[0][k] + dS[a_][1] * M[1][k] + dS[a_][2] * M[2][k]);
+        float dR[3][3];
+        for (int k = 0; k < 3; k++) {
+            g_scales[3 * i + k] = cam->scale_modifier * (R[0][k] * dM[0][k] + R[1][k] * dM[1][k] + R[2][k] * dM[2][k]);
+            for (int a_ = 0; a_ < 3; a_++) dR[a_][k] = dM[a_][k] * s[k];
+        }
+        g_rots[4 * i + 0] = 2 * z * (dR[1][0] - dR[0][1]) + 2 * y * (dR[0][2] - dR[2][0]) + 2 * x * (dR[2][1] - dR[1][2]);
+        g_rots[4 * i + 1] = 2 * y * (dR[0][1] + dR[1][0]) + 2 * z * (dR[0][2] + dR[2][0]) + 2 * r * (dR[2][1] - dR[1][2]) - 4 * x * (dR[2][2] + dR[1][1]);
+        g_rots[4 * i + 2] = 2 * x * (dR[0][1] + dR[1][0]) + 2 * r * (dR[0][2] - dR[2][0]) + 2 * z * (dR[2][1] + dR[1][2]) - 4 * y * (dR[2][2] + dR[0][0]);
+        g_rots[4 * i + 3] = 2 * r * (dR[1][0] - dR[0][1]) + 2 * x * (dR[0][2] + dR[2][0]) + 2 * y * (dR[2][1] + dR[1][2]) - 4 * z * (dR[1][1] + dR[0][0]);
+    }
+}
