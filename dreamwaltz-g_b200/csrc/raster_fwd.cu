@@ -1,0 +1,156 @@
+// Rasteriser stage 3 (R12/R13): per-tile front-to-back alpha blending, and the C-ABI forward.
+//
+// One 256-thread CTA per 16x16 tile, one pixel per thread (the per-pixel transmittance chain is
+// evaluated sequentially in source order so that final_T and n_contrib are bit-exact with the
+// oracle).  The tile's depth-sorted 48-byte instance records are contiguous in HBM; they are
+// staged into shared memory by 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx),
+// double-buffered so the copy of chunk c+1 overlaps the blend of chunk c.  All threads read the
+// same record at the same time (shared-memory broadcast); warps vote to leave early.
+#include "raster_common.cuh"
+
+namespace dwg {
+namespace raster {
+
+int launch_pre(const DwgRasterCamera& cam, int64_t N, const float* means3D, const float* opacities,
+               const float* scales, const float* rots, GeomView g, BinView b, int T, int64_t P_cap,
+               int32_t* radii, int32_t* status, cudaStream_t st);
+int launch_sort(int T, BinView b, GeomView g, const float* colors, int write_keys, cudaStream_t st);
+
+__global__ void __launch_bounds__(TILE_PIX)
+render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
+                  float bg0, float bg1, float bg2,
+                  float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+    __shared__ __align__(128) Rec s_rec[2][CHUNK];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int px = blockIdx.x * TILE + (threadIdx.x & (TILE - 1));
+    const int py = blockIdx.y * TILE + (threadIdx.x >> 4);
+    const bool inside = px < W && py < H;
+    const float pxf = (float)px, pyf = (float)py;
+    const uint2 rg = ranges[tile];
+    const int n = (int)(rg.y - rg.x);
+    const int rounds = (n + CHUNK - 1) / CHUNK;
+    const Rec* src = recs + rg.x;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && rounds > 0) {
+        const uint32_t bytes = (uint32_t)(min(CHUNK, n) * sizeof(Rec));
+        mbar_expect_tx(&s_bar[0], bytes);
+        tma_bulk_g2s(&s_rec[0][0], src, bytes, &s_bar[0]);
+    }
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, A = 0.f;
+    uint32_t contributor = 0, last = 0;
+    for (int c = 0; c < rounds; c++) {
+        const int buf = c & 1;
+        // every thread has finished reading buffer buf^1 (chunk c-1): safe to refill it with chunk c+1
+        const int n_done = __syncthreads_count(done);
+        if (n_done == TILE_PIX) {
+            mbar_wait(&s_bar[buf], (uint32_t)((c >> 1) & 1));   // never exit with a bulk copy in flight
+            break;
+        }
+        if (threadIdx.x == 0 && c + 1 < rounds) {
+            const int cnt = min(CHUNK, n - (c + 1) * CHUNK);
+            const uint32_t bytes = (uint32_t)(cnt * sizeof(Rec));
+            mbar_expect_tx(&s_bar[buf ^ 1], bytes);
+            tma_bulk_g2s(&s_rec[buf ^ 1][0], src + (size_t)(c + 1) * CHUNK, bytes, &s_bar[buf ^ 1]);
+        }
+        mbar_wait(&s_bar[buf], (uint32_t)((c >> 1) & 1));
+        const int cnt = min(CHUNK, n - c * CHUNK);
+        if (!done) {
+            for (int j = 0; j < cnt; j++) {
+                contributor++;
+                const Rec rc = s_rec[buf][j];
+                float alpha, G, dx, dy;
+                if (!eval_alpha(rc, pxf, pyf, alpha, G, dx, dy)) continue;
+                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                if (test_T < 0.0001f) { done = true; break; }
+                const float w = __fmul_rn(alpha, T);
+                C0 = __fadd_rn(C0, __fmul_rn(rc.r, w));
+                C1 = __fadd_rn(C1, __fmul_rn(rc.g, w));
+                C2 = __fadd_rn(C2, __fmul_rn(rc.b, w));
+                D = __fadd_rn(D, __fmul_rn(rc.depth, w));
+                A = __fadd_rn(A, w);
+                T = test_T;
+                last = contributor;
+            }
+        }
+    }
+    if (inside) {
+        const size_t pix = (size_t)py * W + px;
+        const size_t HW = (size_t)H * W;
+        final_T[pix] = T;
+        n_contrib[pix] = last;
+        out_color[pix] = __fadd_rn(C0, __fmul_rn(T, bg0));
+        out_color[HW + pix] = __fadd_rn(C1, __fmul_rn(T, bg1));
+        out_color[2 * HW + pix] = __fadd_rn(C2, __fmul_rn(T, bg2));
+        out_depth[pix] = D;
+        out_alpha[pix] = A;
+    }
+}
+
+}  // namespace raster
+}  // namespace dwg
+
+using namespace dwg;
+using namespace dwg::raster;
+
+extern "C" int64_t dwg_raster_geom_bytes(int64_t N) { return (int64_t)GeomView::bytes(N > 0 ? N : 1); }
+extern "C" int64_t dwg_raster_bin_bytes(int64_t P_cap, int H, int W) {
+    const int T = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    return (int64_t)BinView::bytes(P_cap > 0 ? P_cap : 1, T);
+}
+extern "C" int64_t dwg_raster_img_bytes(int H, int W) { return (int64_t)ImgView::bytes(H, W); }
+
+extern "C" int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N, const float* means3D,
+                                  const float* colors_precomp, const float* opacities, const float* scales,
+                                  const float* rotations, float* out_color, float* out_depth, float* out_alpha,
+                                  int32_t* radii, void* geom, void* bin, int64_t P_cap, void* img,
+                                  int32_t* status, void* stream) {
+    DWG_REQUIRE(cam && out_color && out_depth && out_alpha && geom && bin && img && status, "null pointer");
+    DWG_REQUIRE(N == 0 || (means3D && colors_precomp && opacities && scales && rotations && radii), "null input");
+    DWG_REQUIRE(cam->image_height > 0 && cam->image_width > 0, "bad image size");
+    DWG_REQUIRE(P_cap > 0 && P_cap < (1ll << 31), "P_cap must be in (0, 2^31)");
+    const int H = cam->image_height, W = cam->image_width;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const int T = gx * gy;
+    DWG_REQUIRE(T <= 65535 * 16, "image too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    GeomView g(geom, N > 0 ? N : 1);
+    BinView b(bin, P_cap, T);
+    ImgView im(img, H, W);
+    int rc = launch_pre(*cam, N, means3D, opacities, scales, rotations, g, b, T, P_cap, radii, status, st);
+    if (rc != DWG_OK) return rc;
+    rc = launch_sort(T, b, g, colors_precomp, 1, st);
+    if (rc != DWG_OK) return rc;
+    render_fwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2],
+                                                        out_color, out_depth, out_alpha, im.final_T, im.n_contrib);
+    return check_launch("dwg_raster_forward");
+}
+
+extern "C" void* dwg_raster_view(int which, void* geom, void* bin, void* img, int64_t N, int64_t P_cap, int H, int W) {
+    const int T = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    GeomView g(geom, N > 0 ? N : 1);
+    BinView b(bin, P_cap > 0 ? P_cap : 1, T);
+    ImgView im(img, H, W);
+    switch (which) {
+        case 0: return g.xy;
+        case 1: return g.depth;
+        case 2: return g.cov3D;
+        case 3: return g.conic_opacity;
+        case 4: return g.rect;
+        case 5: return g.tiles_touched;
+        case 6: return b.ranges;
+        case 7: return b.keys_out;
+        case 8: return b.vals_out;
+        case 9: return im.final_T;
+        case 10: return im.n_contrib;
+        case 11: return b.recs;
+        default: return nullptr;
+    }
+}

@@ -1,0 +1,90 @@
+"""ctypes binding of libdwg_sm100.so (the C ABI declared in include/dwg.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised (the
+reference trainer's ``except RuntimeError`` checkpoint-and-exit path, core/trainer.py:919-923,
+keeps working).  torch is used only for device memory and the current stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO_PATH = os.path.join(_PKG, 'libdwg_sm100.so')
+_lib = None
+
+c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+
+class DwgRasterCamera(ctypes.Structure):
+    _fields_ = [('image_height', ctypes.c_int32), ('image_width', ctypes.c_int32),
+                ('tanfovx', c_float), ('tanfovy', c_float),
+                ('viewmatrix', c_float * 16), ('projmatrix', c_float * 16),
+                ('bg', c_float * 3), ('scale_modifier', c_float)]
+
+
+# name -> (restype, argtypes); this table is also what tests use to check the exported symbols
+SIGNATURES = {
+    'dwg_last_error': (ctypes.c_char_p, []),
+    'dwg_version': (c_int, []),
+    'dwg_device_cc': (c_int, []),
+    'dwg_lbs_skin_fwd': (c_int, [c_void_p] * 6 + [c_int64, c_int, c_void_p]),
+    'dwg_lbs_skin_bwd': (c_int, [c_void_p] * 10 + [c_int64, c_int, c_void_p]),
+    'dwg_sh_eval_fwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'dwg_sh_eval_bwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int64, c_void_p]),
+    'dwg_grid_encode_fwd': (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                    c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    'dwg_grid_encode_bwd': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    'dwg_raster_geom_bytes': (c_int64, [c_int64]),
+    'dwg_raster_bin_bytes': (c_int64, [c_int64, c_int, c_int]),
+    'dwg_raster_img_bytes': (c_int64, [c_int, c_int]),
+    'dwg_raster_bwd_scratch_bytes': (c_int64, [c_int64]),
+    'dwg_raster_forward': (c_int, [ctypes.POINTER(DwgRasterCamera), c_int64] + [c_void_p] * 9 +
+                           [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'dwg_raster_backward': (c_int, [ctypes.POINTER(DwgRasterCamera), c_int64] + [c_void_p] * 5 +
+                            [c_void_p, c_void_p, c_int64, c_void_p] + [c_void_p] * 3 + [c_void_p] * 6 +
+                            [c_void_p, c_void_p]),
+    'dwg_raster_view': (c_void_p, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int]),
+}
+
+
+def lib():
+    """Load libdwg_sm100.so (raises RuntimeError if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f'{SO_PATH} not found: build it with `python -m dwg.build` '
+                               '(__graft_entry__.build()); there is no CPU or PyTorch fallback')
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().dwg_last_error().decode(errors='replace')
+        raise RuntimeError(f'libdwg {what} failed ({rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'libdwg needs contiguous CUDA tensors'
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32c(t):
+    """float32 + contiguous view/copy of a tensor (no-op when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,254 @@
+"""torch.autograd wrappers over the C ABI (include/dwg.h).  Thin: allocate outputs/workspaces,
+pass raw pointers + the current stream, convert error codes to RuntimeError."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, f32c, lib, ptr, stream
+
+
+# ------------------------------------------------------------------------------ LBS skinning
+class _LbsSkin(torch.autograd.Function):
+    """x' , q' = skin(W, A, x, q)  (dwg_lbs_skin_fwd/bwd)."""
+
+    @staticmethod
+    def forward(ctx, W, A, x, q):
+        W, A, x = f32c(W), f32c(A), f32c(x)
+        q = None if q is None else f32c(q)
+        N, J = W.shape
+        assert A.shape == (J, 4, 4) and x.shape == (N, 3)
+        x_out = torch.empty_like(x)
+        q_out = None if q is None else torch.empty_like(q)
+        check(lib().dwg_lbs_skin_fwd(ptr(W), ptr(A), ptr(x), ptr(q), ptr(x_out), ptr(q_out), N, J, stream()),
+              'dwg_lbs_skin_fwd')
+        ctx.save_for_backward(W, A, x, q)
+        ctx.has_q = q is not None
+        if q is None:
+            return x_out
+        return x_out, q_out
+
+    @staticmethod
+    def backward(ctx, g_x_out, g_q_out=None):
+        W, A, x, q = ctx.saved_tensors
+        N, J = W.shape
+        need_W, need_A = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_x_out = f32c(g_x_out) if g_x_out is not None else torch.zeros_like(x)
+        if ctx.has_q:
+            g_q_out = f32c(g_q_out) if g_q_out is not None else torch.zeros_like(q)
+        g_x = torch.empty_like(x)
+        g_q = torch.empty_like(q) if ctx.has_q else None
+        g_W = torch.empty_like(W) if need_W else None
+        g_A = torch.zeros_like(A) if need_A else None
+        check(lib().dwg_lbs_skin_bwd(ptr(W), ptr(A), ptr(x), ptr(q), ptr(g_x_out), ptr(g_q_out if ctx.has_q else None),
+                                     ptr(g_x), ptr(g_q), ptr(g_W), ptr(g_A), N, J, stream()), 'dwg_lbs_skin_bwd')
+        return g_W, g_A, g_x, g_q
+
+
+def lbs_skin(W, A, x, q=None):
+    """Fused linear-blend skinning: W [N,J], A [J,4,4], x [N,3], q [N,4] or None."""
+    return _LbsSkin.apply(W, A, x, q)
+
+
+# ------------------------------------------------------------------------------ SH colour
+class _ShEval(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh, pos, campos, deg):
+        sh, pos, campos = f32c(sh), f32c(pos), f32c(campos).reshape(3)
+        N, stride = sh.shape[0], sh.shape[1]
+        assert sh.shape[2] == 3 and pos.shape == (N, 3)
+        rgb = torch.empty(N, 3, device=sh.device, dtype=torch.float32)
+        clamped = torch.empty(N, device=sh.device, dtype=torch.uint8)
+        check(lib().dwg_sh_eval_fwd(ptr(sh), stride, deg, ptr(pos), ptr(campos), ptr(rgb), ptr(clamped), N, stream()),
+              'dwg_sh_eval_fwd')
+        ctx.save_for_backward(sh, pos, campos, clamped)
+        ctx.deg = deg
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        sh, pos, campos, clamped = ctx.saved_tensors
+        N, stride = sh.shape[0], sh.shape[1]
+        g_sh = torch.empty_like(sh)
+        g_pos = torch.empty_like(pos) if ctx.needs_input_grad[1] else None
+        check(lib().dwg_sh_eval_bwd(ptr(sh), stride, ctx.deg, ptr(pos), ptr(campos), ptr(clamped), ptr(f32c(g_rgb)),
+                                    ptr(g_sh), ptr(g_pos), N, stream()), 'dwg_sh_eval_bwd')
+        return g_sh, g_pos, None, None
+
+
+def sh_colors(sh_features, positions, campos, sh_levels):
+    """rgb = clamp_min(eval_sh(sh_levels-1, sh, normalize(pos - campos)) + 0.5, 0); sh [N,K,3]."""
+    return _ShEval.apply(sh_features, positions, campos, int(sh_levels) - 1)
+
+
+# ------------------------------------------------------------------------------ grid encoder
+def grid_level_table(num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                     desired_resolution=4096, per_level_scale=None, input_dim=3, align_corners=False):
+    """GridEncoder.__init__ (core/nerf/gridencoder/grid.py:104-133) + the per-level kernel
+    constants of gridencoder.cu:138-139, evaluated once on the host in float32."""
+    if desired_resolution is not None:
+        per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
+    offsets, offset = [], 0
+    max_params = 2 ** log2_hashmap_size
+    for i in range(num_levels):
+        resolution = int(np.ceil(base_resolution * per_level_scale ** i))
+        params = min(max_params, (resolution if align_corners else resolution + 1) ** input_dim)
+        params = int(np.ceil(params / 8) * 8)
+        offsets.append(offset)
+        offset += params
+    offsets.append(offset)
+    S = np.float32(np.log2(per_level_scale))
+    lv = np.arange(num_levels, dtype=np.float32)
+    scale = (np.exp2(lv * S).astype(np.float32) * np.float32(base_resolution) - np.float32(1.0)).astype(np.float32)
+    res = (np.ceil(scale).astype(np.uint32) + np.uint32(1)).astype(np.uint32)
+    return np.array(offsets, np.int32), float(per_level_scale), scale, res
+
+
+class GridSpec:
+    """Device-resident level table of one grid encoder."""
+
+    def __init__(self, device, bound=2.0, gridtype='tiled', align_corners=False, interpolation='smoothstep', **kw):
+        offsets, pls, scale, res = grid_level_table(align_corners=align_corners, **kw)
+        self.num_levels = len(scale)
+        self.n_rows = int(offsets[-1])
+        self.per_level_scale = pls
+        self.bound = float(bound)
+        self.gridtype = {'hash': 0, 'tiled': 1}[gridtype]
+        self.interp = {'linear': 0, 'smoothstep': 1}[interpolation]
+        self.align_corners = bool(align_corners)
+        self.offsets_np, self.scale_np, self.res_np = offsets, scale, res
+        self.offsets = torch.from_numpy(offsets).to(device)
+        self.level_scale = torch.from_numpy(scale).to(device)
+        self.level_res = torch.from_numpy(res.astype(np.int32)).to(device)       # bit pattern of uint32
+
+
+class _GridEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, spec):
+        x, table = f32c(x), f32c(table)
+        B, L = x.shape[0], spec.num_levels
+        assert x.shape[1] == 3 and table.shape == (spec.n_rows, 2)
+        out = torch.empty(B, L * 2, device=x.device, dtype=torch.float32)
+        check(lib().dwg_grid_encode_fwd(ptr(x), spec.bound, ptr(table), ptr(spec.offsets), ptr(spec.level_scale),
+                                        ptr(spec.level_res), ptr(out), L * 2, 2, None, B, L, spec.gridtype,
+                                        int(spec.align_corners), spec.interp, stream()), 'dwg_grid_encode_fwd')
+        ctx.save_for_backward(x, table)
+        ctx.spec = spec
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, table = ctx.saved_tensors
+        spec = ctx.spec
+        B, L = x.shape[0], spec.num_levels
+        grad = f32c(grad)
+        g_table = torch.zeros_like(table)
+        g_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        check(lib().dwg_grid_encode_bwd(ptr(grad), L * 2, 2, ptr(x), spec.bound, ptr(table), ptr(spec.offsets),
+                                        ptr(spec.level_scale), ptr(spec.level_res), ptr(g_table), ptr(g_x), B, L,
+                                        spec.gridtype, int(spec.align_corners), spec.interp, stream()),
+              'dwg_grid_encode_bwd')
+        return g_x, g_table, None
+
+
+def grid_encode(x, table, spec):
+    """Multi-resolution grid encoding of world positions x [B,3] -> [B, 2L] (GridEncoder.forward)."""
+    return _GridEncode.apply(x, table, spec)
+
+
+# ------------------------------------------------------------------------------ rasteriser
+def _camera_struct(H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier):
+    cam = _lib.DwgRasterCamera()
+    cam.image_height, cam.image_width = int(H), int(W)
+    cam.tanfovx, cam.tanfovy = float(tanfovx), float(tanfovy)
+    v = viewmatrix.detach().float().reshape(16).cpu().tolist()
+    p = projmatrix.detach().float().reshape(16).cpu().tolist()
+    b = bg.detach().float().reshape(3).cpu().tolist()
+    for i in range(16):
+        cam.viewmatrix[i], cam.projmatrix[i] = v[i], p[i]
+    for i in range(3):
+        cam.bg[i] = b[i]
+    cam.scale_modifier = float(scale_modifier)
+    return cam
+
+
+class RasterState:
+    """Workspaces kept between forward and backward (and inspected by the parity tests)."""
+    __slots__ = ('cam', 'N', 'H', 'W', 'P_cap', 'geom', 'bin', 'img', 'status', 'radii')
+
+    def view(self, which, dtype, shape):
+        """Typed torch view of an internal buffer (dwg_raster_view)."""
+        L = lib()
+        p = L.dwg_raster_view(which, ptr(self.geom), ptr(self.bin), ptr(self.img), self.N, self.P_cap, self.H, self.W)
+        base = {0: self.geom, 1: self.geom, 2: self.geom, 3: self.geom, 4: self.geom, 5: self.geom}.get(which)
+        if base is None:
+            base = self.img if which in (9, 10) else self.bin
+        off = p - base.data_ptr()
+        n = int(np.prod(shape))
+        isz = torch.empty(0, dtype=dtype).element_size()
+        return base[off:off + n * isz].view(dtype).reshape(shape)
+
+
+def default_instance_capacity(N):
+    return int(max(4 * N, 1 << 20))
+
+
+class _Rasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, colors, opacities, scales, rotations, cam_args, state_out):
+        H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier, P_cap = cam_args
+        dev = means3D.device
+        means3D, colors, scales, rotations = f32c(means3D), f32c(colors), f32c(scales), f32c(rotations)
+        opac = f32c(opacities).reshape(-1)
+        N = means3D.shape[0]
+        L = lib()
+        cam = _camera_struct(H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier)
+        P_cap = int(P_cap or default_instance_capacity(N))
+        st = RasterState()
+        st.cam, st.N, st.H, st.W, st.P_cap = cam, N, H, W, P_cap
+        u8 = lambda n: torch.empty(int(n), device=dev, dtype=torch.uint8)
+        st.geom = u8(L.dwg_raster_geom_bytes(N))
+        st.bin = u8(L.dwg_raster_bin_bytes(P_cap, H, W))
+        st.img = u8(L.dwg_raster_img_bytes(H, W))
+        st.status = torch.zeros(4, device=dev, dtype=torch.int32)
+        st.radii = torch.zeros(N, device=dev, dtype=torch.int32)
+        color = torch.empty(3, H, W, device=dev, dtype=torch.float32)
+        depth = torch.empty(1, H, W, device=dev, dtype=torch.float32)
+        alpha = torch.empty(1, H, W, device=dev, dtype=torch.float32)
+        check(L.dwg_raster_forward(ctypes.byref(cam), N, ptr(means3D), ptr(colors), ptr(opac), ptr(scales),
+                                   ptr(rotations), ptr(color), ptr(depth), ptr(alpha), ptr(st.radii), ptr(st.geom),
+                                   ptr(st.bin), P_cap, ptr(st.img), ptr(st.status), stream()), 'dwg_raster_forward')
+        ctx.save_for_backward(means3D, colors, opac, scales, rotations)
+        ctx.st = st
+        ctx.opac_shape = opacities.shape
+        if state_out is not None:
+            state_out.append(st)
+        ctx.mark_non_differentiable(st.radii)
+        return color, st.radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_color, _g_radii, g_depth, g_alpha):
+        means3D, colors, opac, scales, rotations = ctx.saved_tensors
+        st = ctx.st
+        N, dev = st.N, means3D.device
+        L = lib()
+        g_color = f32c(g_color) if g_color is not None else torch.zeros(3, st.H, st.W, device=dev)
+        g_depth = f32c(g_depth) if g_depth is not None else None
+        g_alpha = f32c(g_alpha) if g_alpha is not None else None
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        g_m3, g_m2, g_c, g_o, g_s, g_r = e(N, 3), e(N, 3), e(N, 3), e(N), e(N, 3), e(N, 4)
+        scratch = torch.empty(int(L.dwg_raster_bwd_scratch_bytes(N)), device=dev, dtype=torch.uint8)
+        check(L.dwg_raster_backward(ctypes.byref(st.cam), N, ptr(means3D), ptr(colors), ptr(opac), ptr(scales),
+                                    ptr(rotations), ptr(st.geom), ptr(st.bin), st.P_cap, ptr(st.img), ptr(g_color),
+                                    ptr(g_depth), ptr(g_alpha), ptr(g_m3), ptr(g_m2), ptr(g_c), ptr(g_o), ptr(g_s),
+                                    ptr(g_r), ptr(scratch), stream()), 'dwg_raster_backward')
+        return g_m3, g_m2, g_c, g_o.reshape(ctx.opac_shape), g_s, g_r, None, None
+
+
+def rasterize(means3D, means2D, colors, opacities, scales, rotations, *, image_height, image_width, tanfovx,
+              tanfovy, viewmatrix, projmatrix, bg, scale_modifier=1.0, instance_capacity=None, state_out=None):
+    """Differentiable tile rasteriser -> (color [3,H,W], radii i32 [N], depth [1,H,W], alpha [1,H,W])."""
+    cam_args = (int(image_height), int(image_width), float(tanfovx), float(tanfovy), viewmatrix, projmatrix, bg,
+                float(scale_modifier), instance_capacity)
+    return _Rasterize.apply(means3D, means2D, colors, opacities, scales, rotations, cam_args, state_out)

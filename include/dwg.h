@@ -1,0 +1,145 @@
+/* dwg.h -- C ABI of libdwg_sm100.so: the B200-native DreamWaltz-G SDS hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only: device pointers, int/int64_t sizes, float scalars; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or
+ *     freed by the library except the opaque handles created by dwg_*_create();
+ *   - all tensors are dense row-major fp32 unless stated; "i32"/"u32"/"u64" = integer types;
+ *   - return value 0 = success, negative = error (dwg_last_error() gives the message);
+ *     kernels are launched asynchronously on `stream`, errors of the launch itself are
+ *     reported, execution errors surface at the caller's next synchronisation;
+ *   - re-entrant per stream; no global mutable state besides the last-error string.
+ *
+ * Each function cites the reference interface it replaces (paths into the reference repo).
+ */
+#ifndef DWG_H_
+#define DWG_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWG_OK 0
+#define DWG_ERR_INVALID -1      /* bad argument (shape / null / unsupported option)  */
+#define DWG_ERR_CUDA -2         /* CUDA runtime error at launch                       */
+#define DWG_ERR_CAPACITY -3     /* caller-provided workspace too small                */
+
+const char* dwg_last_error(void);
+int dwg_version(void);
+/* device sanity: returns compute capability major*10+minor of the current device, <0 on error */
+int dwg_device_cc(void);
+
+/* ------------------------------------------------------------------------------------------
+ * R2/R3  Linear-blend skinning of Gaussians.
+ * Replaces RigidTransform.transform_points(weights=W) + transform_quaternions(weights=W,
+ * flip_rotation_axis=True)  (core/human/inverse_lbs.py:190-242) as called from
+ * DreamWaltzG.lbs_transform (core/system/avatar.py:1446-1460).
+ *   W  [N,J]   blend weights (already row-normalised, avatar.py:914-917)
+ *   A  [J,4,4] joint SE3 (J_pose_rigid composed with G_transl_offset); rows 0..2 are used
+ *   x  [N,3]   positions           q  [N,4] real-first quaternions or NULL (positions only)
+ *   x_out [N,3], q_out [N,4] (NULL iff q NULL)
+ * M_n = sum_j W[n,j] A[j,:3,:];  x' = M[:,:3] x + M[:,3];
+ * q' = mat2quat(F (M[:,:3] (F quat2mat(q))))  with F = diag(1,-1,-1)   (pytorch3d 0.7.5 maths).
+ */
+int dwg_lbs_skin_fwd(const float* W, const float* A, const float* x, const float* q,
+                     float* x_out, float* q_out, int64_t N, int J, void* stream);
+/* Backward.  g_x_out [N,3], g_q_out [N,4] or NULL  ->  g_x [N,3], g_q [N,4] (NULL iff q NULL),
+ * optional g_W [N,J] (written) and g_A [J,4,4] (ACCUMULATED with atomics; caller zeroes). */
+int dwg_lbs_skin_bwd(const float* W, const float* A, const float* x, const float* q,
+                     const float* g_x_out, const float* g_q_out,
+                     float* g_x, float* g_q, float* g_W, float* g_A,
+                     int64_t N, int J, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R10  Spherical-harmonic colour.  Replaces eval_sh + get_colors + compute_colors
+ * (core/gaussian/spherical_harmonics.py:117-172, gaussian_utils.py:12-17,
+ * gaussian_renderer.py:72-105):  dirs = normalize(pos - campos), rgb = max(sum_k Y_k sh_k + 0.5, 0).
+ *   sh [N, sh_stride, 3] (first (deg+1)^2 coefficients used), pos [N,3], campos [3] (device)
+ *   rgb [N,3]; clamped [N] u8 bit c set when channel c was clamped (needed by the backward).
+ */
+int dwg_sh_eval_fwd(const float* sh, int sh_stride, int deg, const float* pos, const float* campos,
+                    float* rgb, uint8_t* clamped, int64_t N, void* stream);
+/* g_rgb [N,3] -> g_sh [N, sh_stride, 3] (first (deg+1)^2 rows written, rest zeroed), g_pos [N,3] or NULL */
+int dwg_sh_eval_bwd(const float* sh, int sh_stride, int deg, const float* pos, const float* campos,
+                    const uint8_t* clamped, const float* g_rgb, float* g_sh, float* g_pos,
+                    int64_t N, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R6  Multi-resolution grid encoder.  Replaces _gridencoder.grid_encode_forward/backward
+ * (core/nerf/gridencoder/src/gridencoder.h:12-15, gridencoder.cu:87-500) incl. the
+ * (x+bound)/(2*bound) mapping of GridEncoder.forward (grid.py:153).  D = 3, C = 2.
+ *   x [B,3] world positions (bound > 0) or inputs already mapped to [0,1] (bound <= 0); table [rows,2]; offsets i32 [L+1]; level_scale f32 [L] and
+ *   level_res u32 [L] = host-evaluated exp2f(l*S)*H-1 and ceil(scale)+1 (gridencoder.cu:138-139);
+ *   out: element (b, l, c) at out[b*out_stride_b + l*out_stride_l + c]  (so both the final
+ *   [B, L*C] layout and the reference's [L,B,C] staging layout are expressible);
+ *   dy_dx [B, L*3*C] or NULL (derivative w.r.t. the [0,1]-mapped input, as the reference).
+ *   gridtype 0 hash / 1 tiled; interp 0 linear / 1 smoothstep.
+ */
+int dwg_grid_encode_fwd(const float* x, float bound, const float* table, const int32_t* offsets,
+                        const float* level_scale, const uint32_t* level_res,
+                        float* out, int64_t out_stride_b, int64_t out_stride_l, float* dy_dx,
+                        int64_t B, int L, int gridtype, int align_corners, int interp, void* stream);
+/* grad: element (b,l,c) at grad[b*g_stride_b + l*g_stride_l + c].  g_table [rows,2] is
+ * ACCUMULATED (atomics; caller zeroes, grid.py:81).  g_x [B,3] or NULL: gradient w.r.t. the
+ * WORLD position (includes the 1/(2*bound) factor); recomputed from the table, no dy_dx buffer. */
+int dwg_grid_encode_bwd(const float* grad, int64_t g_stride_b, int64_t g_stride_l,
+                        const float* x, float bound, const float* table, const int32_t* offsets,
+                        const float* level_scale, const uint32_t* level_res,
+                        float* g_table, float* g_x,
+                        int64_t B, int L, int gridtype, int align_corners, int interp, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R11-R13  Differentiable tile rasteriser.  Replaces diff_gaussian_rasterization._C
+ * rasterize_gaussians / rasterize_gaussians_backward (third party, ashawkey fork; call site
+ * core/gaussian/gaussian_renderer.py:186-195).  16x16 tiles.
+ */
+typedef struct {
+    int32_t image_height, image_width;
+    float tanfovx, tanfovy;
+    float viewmatrix[16];     /* GaussianRasterizationSettings.viewmatrix, row-major flat */
+    float projmatrix[16];     /* GaussianRasterizationSettings.projmatrix, row-major flat */
+    float bg[3];
+    float scale_modifier;
+} DwgRasterCamera;
+
+/* Workspace sizing.  P_cap = capacity (in (tile,Gaussian) instances) the caller grants the
+ * binning buffers; the true count P is data dependent and stays on the device (no host sync).
+ * If P > P_cap the forward sets status word bit 0 and renders nothing beyond capacity. */
+int64_t dwg_raster_geom_bytes(int64_t N);                       /* per-Gaussian state     */
+int64_t dwg_raster_bin_bytes(int64_t P_cap, int H, int W);      /* instances + tile table */
+int64_t dwg_raster_img_bytes(int H, int W);                     /* final_T, n_contrib     */
+
+/* Forward.  colors_precomp [N,3]; opacities [N]; scales [N,3]; rotations [N,4] (w,x,y,z, used
+ * unnormalised); outputs out_color [3,H,W], out_depth [H,W], out_alpha [H,W], radii i32 [N].
+ * geom/bin/img are caller workspaces of the sizes above (kept for the backward).
+ * status: i32[4] device words {overflow flag, P (num_rendered), max tile load, reserved}. */
+int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N,
+                       const float* means3D, const float* colors_precomp, const float* opacities,
+                       const float* scales, const float* rotations,
+                       float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
+                       void* geom, void* bin, int64_t P_cap, void* img, int32_t* status, void* stream);
+/* Backward.  dL_dcolor [3,H,W], dL_ddepth [H,W] or NULL, dL_dalpha [H,W] or NULL ->
+ * g_means3D [N,3], g_means2D [N,3] (z = 0), g_colors [N,3], g_opacities [N], g_scales [N,3],
+ * g_rotations [N,4].  All outputs are fully written (no pre-zeroing needed); `scratch` must
+ * hold dwg_raster_bwd_scratch_bytes(N) bytes. */
+int64_t dwg_raster_bwd_scratch_bytes(int64_t N);
+int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N,
+                        const float* means3D, const float* colors_precomp, const float* opacities,
+                        const float* scales, const float* rotations,
+                        const void* geom, const void* bin, int64_t P_cap, const void* img,
+                        const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                        float* g_means3D, float* g_means2D, float* g_colors, float* g_opacities,
+                        float* g_scales, float* g_rotations, void* scratch, void* stream);
+/* Debug / parity views into the workspaces (device pointers into geom / bin / img):
+ * which = 0 xy f32[N,2] | 1 depth f32[N] | 2 cov3D f32[N,6] | 3 conic_opacity f32[N,4]
+ *       | 4 rect i32[N,4] | 5 tiles_touched u32[N] | 6 tile ranges u32[tiles,2]
+ *       | 7 sorted keys u64[P_cap] | 8 sorted values u32[P_cap] | 9 final_T f32[H,W]
+ *       | 10 n_contrib u32[H,W] */
+void* dwg_raster_view(int which, void* geom, void* bin, void* img, int64_t N, int64_t P_cap, int H, int W);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWG_H_ */

@@ -1,0 +1,285 @@
+"""GPU parity: the CUDA path (through the C ABI of libdwg_sm100.so) against the CPU oracle on
+the same seeded inputs and against the committed golden vectors.  Bit-exact for integer /
+index work; stated tolerances for floating point."""
+import numpy as np
+import pytest
+import torch
+
+from dwg import camera, ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _t(a):
+    return torch.as_tensor(np.asarray(a)).to(DEV)
+
+
+# ------------------------------------------------------------------------------------ LBS
+def _lbs_case(N, J=55, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    W = torch.rand(N, J, generator=g) ** 6
+    W = W / W.sum(1, keepdim=True)
+    A = torch.eye(4).repeat(J, 1, 1)
+    A[:, :3, :] += torch.randn(J, 3, 4, generator=g) * 0.3
+    x = torch.randn(N, 3, generator=g) * 0.5
+    q = torch.randn(N, 4, generator=g)
+    return W, A, x, q
+
+
+@pytest.mark.parametrize('N', [1, 127, 128, 1000, 4097])
+def test_lbs_skin_forward_backward_vs_oracle(N):
+    from oracle import lbs as olbs
+    W, A, x, q = _lbs_case(N)
+    xo_ref, qo_ref = olbs.skin(W, A, x, q)
+    xo, qo = ops.lbs_skin(W.to(DEV), A.to(DEV), x.to(DEV), q.to(DEV))
+    torch.testing.assert_close(xo.cpu(), xo_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(qo.cpu(), qo_ref, rtol=1e-4, atol=1e-5)
+    xo1 = ops.lbs_skin(W.to(DEV), A.to(DEV), x.to(DEV))
+    torch.testing.assert_close(xo1.cpu(), xo_ref, rtol=1e-5, atol=1e-5)
+    # backward against torch autograd of the oracle (double precision)
+    Wd, Ad, xd, qd = (t.double().requires_grad_(True) for t in (W, A, x, q))
+    xr, qr = olbs.skin(Wd, Ad, xd, qd)
+    gx, gq = torch.randn_like(xr), torch.randn_like(qr)
+    ((xr * gx).sum() + (qr * gq).sum()).backward()
+    Wg, Ag, xg, qg = (t.to(DEV).requires_grad_(True) for t in (W, A, x, q))
+    xo, qo = ops.lbs_skin(Wg, Ag, xg, qg)
+    ((xo * gx.float().to(DEV)).sum() + (qo * gq.float().to(DEV)).sum()).backward()
+    for got, ref, name in ((xg.grad, xd.grad, 'x'), (qg.grad, qd.grad, 'q'), (Wg.grad, Wd.grad, 'W'), (Ag.grad, Ad.grad, 'A')):
+        ref = ref.float()
+        err = (got.cpu() - ref).abs().max() / (ref.abs().max() + 1e-12)
+        assert err < 2e-4, (name, float(err))
+
+
+def test_lbs_skin_matches_reference_golden(golden):
+    g = golden('lbs_small')
+    xo, qo = ops.lbs_skin(_t(g['W']), _t(g['A']), _t(g['x']), _t(g['q']))
+    np.testing.assert_allclose(xo.cpu().numpy(), g['x_out'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(qo.cpu().numpy(), g['q_out'], rtol=1e-4, atol=1e-5)
+
+
+def test_lbs_identity_pose_is_identity():
+    N, J = 777, 55
+    W, _, x, q = _lbs_case(N)
+    A = torch.eye(4).repeat(J, 1, 1)
+    xo, qo = ops.lbs_skin(W.to(DEV), A.to(DEV), x.to(DEV), q.to(DEV))
+    torch.testing.assert_close(xo.cpu(), x, rtol=1e-6, atol=1e-6)
+    qn = q / q.norm(dim=-1, keepdim=True)
+    same = torch.minimum((qo.cpu() - qn).abs().max(1).values, (qo.cpu() + qn).abs().max(1).values)
+    assert same.max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------ SH
+@pytest.mark.parametrize('levels', [1, 2, 3, 4, 5])
+def test_sh_matches_reference_golden_and_grad(golden, levels):
+    from oracle import sh as osh
+    g = golden('sh')
+    sh, pos, campos = _t(g['sh']), _t(g['pos']), _t(g['campos'])
+    rgb = ops.sh_colors(sh, pos, campos, levels)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g[f'colors_l{levels}'], rtol=1e-5, atol=2e-6)
+    shd = torch.tensor(g['sh']).double().requires_grad_(True)
+    posd = torch.tensor(g['pos']).double().requires_grad_(True)
+    ref = osh.sh_colors(shd, posd, torch.tensor(g['campos']).double(), levels)
+    go = torch.randn_like(ref)
+    (ref * go).sum().backward()
+    shg, posg = sh.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    (ops.sh_colors(shg, posg, campos, levels) * go.float().to(DEV)).sum().backward()
+    torch.testing.assert_close(shg.grad.cpu(), shd.grad.float(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(posg.grad.cpu(), posd.grad.float(), rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------ grid
+def _grid_case(B, seed=0, gridtype='tiled', interp='smoothstep'):
+    from oracle import grid as ogrid
+    offsets, pls, S, scale, res = ogrid.level_table()
+    rng = np.random.default_rng(seed)
+    table = rng.uniform(-1e-1, 1e-1, size=(int(offsets[-1]), 2)).astype(np.float32)
+    x = rng.uniform(-2.0, 2.0, size=(B, 3)).astype(np.float32)
+    x[:5] = [[2.0, 2.0, 2.0], [-2.0, -2.0, -2.0], [2.01, 0, 0], [0, -2.5, 0], [0.0, 0.0, 0.0]]     # edges + OOB
+    spec = ops.GridSpec(DEV, bound=2.0, gridtype=gridtype, interpolation=interp)
+    assert np.array_equal(spec.offsets_np, offsets) and np.array_equal(spec.scale_np, scale) and np.array_equal(spec.res_np, res)
+    return x, table, (offsets, scale, res), spec
+
+
+@pytest.mark.parametrize('gridtype,interp', [('tiled', 'smoothstep'), ('hash', 'linear')])
+def test_grid_encode_forward_backward_vs_oracle(gridtype, interp):
+    from oracle import grid as ogrid
+    B = 3000
+    x, table, (offsets, scale, res), spec = _grid_case(B, 1, gridtype, interp)
+    gt, it = {'hash': 0, 'tiled': 1}[gridtype], {'linear': 0, 'smoothstep': 1}[interp]
+    enc_ref, dy_ref, _ = ogrid.forward(x, table, offsets, scale, res, bound=2.0, gridtype=gt, interp=it)
+    xt, tt = _t(x).requires_grad_(True), _t(table).requires_grad_(True)
+    enc = ops.grid_encode(xt, tt, spec)
+    # identical corner indices + identical fp32 weights => values agree to fp32 rounding of 8-term sums
+    np.testing.assert_allclose(enc.detach().cpu().numpy(), enc_ref, rtol=1e-5, atol=1e-7)
+    assert np.all(enc.detach().cpu().numpy()[2:4] == 0)                      # out-of-bound rows are zero
+    g = np.random.default_rng(2).normal(size=enc_ref.shape).astype(np.float32)
+    (enc * _t(g)).sum().backward()
+    gt_ref, gx_ref = ogrid.backward(g, x, table.shape, offsets, scale, res, dy_dx=dy_ref, bound=2.0, gridtype=gt, interp=it)
+    np.testing.assert_allclose(tt.grad.cpu().numpy(), gt_ref.astype(np.float32), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), gx_ref, rtol=1e-3, atol=1e-5 * np.abs(gx_ref).max())
+
+
+def test_gridencoder_dropin_module_layout():
+    """The reference-facing `_gridencoder` functions: [L,B,C] outputs, dy_dx buffer, in-place grads."""
+    import _gridencoder as ge
+    from oracle import grid as ogrid
+    B = 500
+    x, table, (offsets, scale, res), spec = _grid_case(B, 3)
+    x01 = ((x + np.float32(2.0)) / np.float32(4.0)).astype(np.float32)
+    L, C, D = 16, 2, 3
+    S = float(np.log2(spec.per_level_scale))
+    out = torch.empty(L, B, C, device=DEV)
+    dy = torch.empty(B, L * D * C, device=DEV)
+    ge.grid_encode_forward(_t(x01), _t(table), _t(offsets), out, B, D, C, L, S, 16, dy, 1, False, 1)
+    enc_ref, dy_ref, _ = ogrid.forward(x, table, offsets, scale, res, bound=2.0)
+    np.testing.assert_allclose(out.permute(1, 0, 2).reshape(B, L * C).cpu().numpy(), enc_ref, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(dy.cpu().numpy(), dy_ref, rtol=1e-4, atol=1e-5)
+    g = np.random.default_rng(5).normal(size=(B, L * C)).astype(np.float32)
+    gl = _t(g).view(B, L, C).permute(1, 0, 2).contiguous()
+    ge_t = torch.zeros(table.shape, device=DEV)
+    gi = torch.zeros(B, D, device=DEV)
+    ge.grid_encode_backward(gl, _t(x01), _t(table), _t(offsets), ge_t, B, D, C, L, S, 16, dy, gi, 1, False, 1)
+    gt_ref, gx_ref = ogrid.backward(g, x, table.shape, offsets, scale, res, dy_dx=dy_ref, bound=2.0)
+    np.testing.assert_allclose(ge_t.cpu().numpy(), gt_ref.astype(np.float32), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gi.cpu().numpy(), gx_ref * 4.0, rtol=1e-3, atol=1e-4 * np.abs(gx_ref).max())
+
+
+# ------------------------------------------------------------------------------------ raster
+def _raster_case(n, H, W, seed=0, radius=2.2, fov=45.0, scale_range=(0.01, 0.06), bg=(0.1, 0.2, 0.3)):
+    from oracle import raster as orast
+    g = synth.random_gaussians(n, seed=seed, extent=0.45, scale_range=scale_range)
+    d = camera.make_camera(radius, 35.0, 75.0, fov, H, W)
+    view, proj, campos, tfx, tfy = camera.raster_matrices(d)
+    cam = orast.make_camera(H, W, tfx, tfy, view.numpy(), proj.numpy(), bg)
+    kw = dict(image_height=H, image_width=W, tanfovx=tfx, tanfovy=tfy, viewmatrix=view, projmatrix=proj,
+              bg=torch.tensor(bg))
+    return g, cam, kw
+
+
+def _run_gpu(g, kw, grads=None, cap=None):
+    t = {k: v.to(DEV).requires_grad_(True) for k, v in g.items()}
+    m2 = torch.zeros(t['positions'].shape[0], 3, device=DEV, requires_grad=True)
+    states = []
+    color, radii, depth, alpha = ops.rasterize(t['positions'], m2, t['colors'], t['opacities'], t['scales'],
+                                               t['quaternions'], state_out=states, instance_capacity=cap, **kw)
+    if grads is not None:
+        dc, dd, da = grads
+        ((color * _t(dc)).sum() + (depth[0] * _t(dd)).sum() + (alpha[0] * _t(da)).sum()).backward()
+    return color, radii, depth, alpha, states[0], t, m2
+
+
+@pytest.mark.parametrize('n,H,W,seed', [(400, 48, 64, 1), (5000, 128, 128, 2), (20000, 256, 256, 3), (3, 33, 17, 4)])
+def test_raster_forward_bit_exact_binning_and_image(n, H, W, seed):
+    from oracle import raster as orast
+    g, cam, kw = _raster_case(n, H, W, seed)
+    o = orast.forward(cam, g['positions'], g['scales'], g['quaternions'], g['opacities'], g['colors'])
+    color, radii, depth, alpha, st, _, _ = _run_gpu(g, kw)
+    N, P = n, o['P']
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    status = st.status.cpu().numpy()
+    assert status[0] == 0 and status[1] == P
+    # ---- bit-exact integer / index state ----
+    assert np.array_equal(radii.cpu().numpy(), o['radii'])
+    assert np.array_equal(st.view(4, torch.int32, (N, 4)).cpu().numpy(), o['rect'])
+    assert np.array_equal(st.view(5, torch.int32, (N,)).cpu().numpy().view(np.uint32), o['tiles_touched'])
+    assert np.array_equal(st.view(1, torch.float32, (N,)).cpu().numpy().view(np.uint32), o['depth'].view(np.uint32))
+    assert np.array_equal(st.view(0, torch.float32, (N, 2)).cpu().numpy().view(np.uint32), o['xy'].view(np.uint32))
+    assert np.array_equal(st.view(3, torch.float32, (N, 4)).cpu().numpy().view(np.uint32), o['conic_opacity'].view(np.uint32))
+    assert np.array_equal(st.view(2, torch.float32, (N, 6)).cpu().numpy().view(np.uint32), o['cov3D'].view(np.uint32))
+    assert np.array_equal(st.view(6, torch.int32, (T, 2)).cpu().numpy().view(np.uint32), o['ranges'])
+    keys = st.view(7, torch.int64, (st.P_cap,)).cpu().numpy().view(np.uint64)[:P]
+    vals = st.view(8, torch.int32, (st.P_cap,)).cpu().numpy().view(np.uint32)[:P]
+    assert np.array_equal(keys, o['keys']) and np.array_equal(vals, o['vals'])
+    assert np.array_equal(st.view(10, torch.int32, (H, W)).cpu().numpy().view(np.uint32), o['n_contrib'])
+    # ---- images: same operation order => bit-exact; PSNR reported as the contractual bound ----
+    assert np.array_equal(st.view(9, torch.float32, (H, W)).cpu().numpy().view(np.uint32), o['final_T'].view(np.uint32))
+    for got, ref in ((color.cpu().numpy(), o['color']), (depth[0].cpu().numpy(), o['out_depth']), (alpha[0].cpu().numpy(), o['out_alpha'])):
+        mse = float(np.mean((got - ref) ** 2))
+        psnr = 99.0 if mse == 0 else 10 * np.log10(1.0 / mse)
+        assert psnr >= 40.0
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('n,H,W,seed', [(400, 48, 64, 1), (5000, 128, 128, 2)])
+def test_raster_backward_vs_oracle(n, H, W, seed):
+    from oracle import raster as orast
+    g, cam, kw = _raster_case(n, H, W, seed)
+    o = orast.forward(cam, g['positions'], g['scales'], g['quaternions'], g['opacities'], g['colors'])
+    rng = np.random.default_rng(seed)
+    dc = rng.normal(size=(3, H, W)).astype(np.float32)
+    dd = rng.normal(size=(H, W)).astype(np.float32)
+    da = rng.normal(size=(H, W)).astype(np.float32)
+    b = orast.backward(cam, o, dc, dd, da)
+    _, _, _, _, _, t, m2 = _run_gpu(g, kw, grads=(dc, dd, da))
+    pairs = (('means3D', t['positions'].grad), ('means2D', m2.grad), ('colors', t['colors'].grad),
+             ('opacities', t['opacities'].grad), ('scales', t['scales'].grad), ('rots', t['quaternions'].grad))
+    for name, got in pairs:
+        ref = b[name]
+        got = got.cpu().numpy().reshape(ref.shape)
+        err = np.abs(got - ref).max() / (np.abs(ref).max() + 1e-20)
+        assert err < 1e-4, (name, float(err))         # fp32 atomics reorder the sums
+
+
+def test_raster_large_tile_merge_path_and_capacity_overflow():
+    """> SORT_CHUNK instances in one tile exercises the merge passes; a too-small instance
+    capacity is reported through the status word instead of corrupting memory."""
+    from oracle import raster as orast
+    n, H, W = 6000, 32, 32
+    g, cam, kw = _raster_case(n, H, W, seed=7, radius=3.5, fov=30.0, scale_range=(0.002, 0.01))
+    g['positions'] = g['positions'] * 0.15
+    o = orast.forward(cam, g['positions'], g['scales'], g['quaternions'], g['opacities'], g['colors'])
+    assert (o['ranges'][:, 1] - o['ranges'][:, 0]).max() > 2048
+    color, radii, depth, alpha, st, _, _ = _run_gpu(g, kw)
+    P = o['P']
+    keys = st.view(7, torch.int64, (st.P_cap,)).cpu().numpy().view(np.uint64)[:P]
+    assert np.array_equal(keys, o['keys'])
+    assert np.array_equal(st.view(10, torch.int32, (H, W)).cpu().numpy().view(np.uint32), o['n_contrib'])
+    np.testing.assert_allclose(color.cpu().numpy(), o['color'], rtol=0, atol=1e-6)
+    # overflow: capacity below P
+    color2, _, _, _, st2, _, _ = _run_gpu(g, kw, cap=max(P // 2, 1))
+    s2 = st2.status.cpu().numpy()
+    assert s2[0] == 1 and s2[1] == P
+    assert torch.isfinite(color2).all()
+
+
+def test_raster_empty_and_all_culled():
+    H = W = 32
+    g, cam, kw = _raster_case(10, H, W, seed=9)
+    g['positions'][:, :] = torch.tensor([0.0, 50.0, 0.0])          # far outside / behind
+    color, radii, depth, alpha, st, _, _ = _run_gpu(g, kw)
+    bg = torch.tensor([0.1, 0.2, 0.3]).view(3, 1, 1)
+    assert int(st.status[1]) == 0 and int(radii.abs().sum()) == 0
+    torch.testing.assert_close(color.cpu(), bg.expand(3, H, W).contiguous())
+    assert float(alpha.abs().max()) == 0.0
+
+
+def test_dropin_rasterizer_module_signature():
+    """Surface 1: diff_gaussian_rasterization.{GaussianRasterizationSettings, GaussianRasterizer}."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from oracle import raster as orast
+    from oracle import sh as osh
+    n, H, W = 300, 64, 64
+    g, cam, kw = _raster_case(n, H, W, seed=11)
+    settings = GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=kw['tanfovx'], tanfovy=kw['tanfovy'],
+                                             bg=kw['bg'].to(DEV), scale_modifier=1.0, viewmatrix=kw['viewmatrix'].to(DEV),
+                                             projmatrix=kw['projmatrix'].to(DEV), sh_degree=2,
+                                             campos=torch.tensor([0.0, 0.0, 0.0], device=DEV), prefiltered=False, debug=False)
+    rast = GaussianRasterizer(raster_settings=settings)
+    t = {k: v.to(DEV) for k, v in g.items()}
+    m2 = torch.zeros(n, 3, device=DEV, requires_grad=True)
+    color, radii, depth, alpha = rast(means3D=t['positions'], means2D=m2, shs=None, colors_precomp=t['colors'],
+                                      opacities=t['opacities'], scales=t['scales'], rotations=t['quaternions'],
+                                      cov3D_precomp=None)
+    o = orast.forward(cam, g['positions'], g['scales'], g['quaternions'], g['opacities'], g['colors'])
+    assert color.shape == (3, H, W) and depth.shape == (1, H, W) and alpha.shape == (1, H, W) and radii.dtype == torch.int32
+    np.testing.assert_allclose(color.cpu().numpy(), o['color'], atol=1e-6)
+    with pytest.raises(Exception):
+        rast(means3D=t['positions'], means2D=m2, opacities=t['opacities'], scales=t['scales'], rotations=t['quaternions'])
+    # SH path == SH oracle colours fed to the raster oracle
+    sh = torch.randn(n, 16, 3) * 0.3
+    c_sh, _, _, _ = rast(means3D=t['positions'], means2D=m2, shs=sh.to(DEV), opacities=t['opacities'],
+                         scales=t['scales'], rotations=t['quaternions'])
+    cols = osh.sh_colors(sh, g['positions'], torch.zeros(3), 3)
+    o2 = orast.forward(cam, g['positions'], g['scales'], g['quaternions'], g['opacities'], cols)
+    np.testing.assert_allclose(c_sh.cpu().numpy(), o2['color'], atol=2e-5)
