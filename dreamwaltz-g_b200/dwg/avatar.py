@@ -1,0 +1,236 @@
+"""R4-R9: the per-step avatar path (DreamWaltzG.animate and what it calls) on the device.
+
+Mirrors reference core/system/avatar.py:1097-1635 for the shipped configuration of
+scripts/train_wo_expr.sh (use_non_rigid_offsets/scales, learn_scale=False,
+use_non_rigid_rotations=False, learn_quaternions=True, frozen LBS weights, mesh-bound hands).
+State-dict key names follow the reference so that checkpoints map 1:1:
+  _positions, _scales, _quaternions, _lbs_weights, nerf_encoder.embeddings,
+  nerf_opacity_and_color_net.net.{i}.{weight,bias},
+  nerf_scale_and_quaternion_net.{layers.{i},gaussian_warp,gaussian_rotation,gaussian_scaling}.{weight,bias},
+  mesh_binding_gaussians.hands.{_bary_coords,_vertex_coords,_scales}
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import lbs as dlbs
+from . import ops
+
+
+@dataclass
+class GaussianOutput:
+    """Field names of reference core/gaussian/gaussian_utils.py:20-33."""
+    positions: Optional[torch.Tensor] = None
+    sh_features: Optional[torch.Tensor] = None
+    opacities: Optional[torch.Tensor] = None
+    quaternions: Optional[torch.Tensor] = None
+    scales: Optional[torch.Tensor] = None
+    colors: Optional[torch.Tensor] = None
+    cov3D: Optional[torch.Tensor] = None
+    offsets: Optional[torch.Tensor] = None
+    lbs_weights: Optional[torch.Tensor] = None
+
+
+class MLP(nn.Module):
+    """core/nerf/nerf_model.py:12-33."""
+
+    def __init__(self, dim_in, dim_out, dim_hidden, num_layers, bias=True):
+        super().__init__()
+        self.num_layers = num_layers
+        self.net = nn.ModuleList([nn.Linear(dim_in if l == 0 else dim_hidden,
+                                            dim_out if l == num_layers - 1 else dim_hidden, bias=bias)
+                                  for l in range(num_layers)])
+
+    def forward(self, x):
+        for l in range(self.num_layers):
+            x = self.net[l](x)
+            if l != self.num_layers - 1:
+                x = F.relu(x)
+        return x
+
+
+class DeformNetwork(nn.Module):
+    """core/deformation/deform_model.py:61-143 (D=4, W=64, no skip, is_6dof=False)."""
+
+    def __init__(self, xyz_input_ch=32, pose_input_ch=63, D=4, W=64):
+        super().__init__()
+        self.layers = nn.ModuleList([nn.Linear(xyz_input_ch + pose_input_ch, W)] + [nn.Linear(W, W) for _ in range(D - 1)])
+        self.gaussian_warp = nn.Linear(W, 3)
+        self.gaussian_rotation = nn.Linear(W, 4)
+        self.gaussian_scaling = nn.Linear(W, 3)
+
+    def forward(self, x, body_pose):
+        h = torch.cat([x, body_pose.expand(x.shape[0], -1)], dim=-1)
+        for lin in self.layers:
+            h = F.leaky_relu(lin(h))
+        return self.gaussian_warp(h), self.gaussian_scaling(h), self.gaussian_rotation(h)
+
+
+class GridEncoder(nn.Module):
+    """core/nerf/gridencoder/grid.py:99-166 (tiled grid, smoothstep) on the dwg kernel."""
+
+    def __init__(self, device='cuda', bound=2.0, **kw):
+        super().__init__()
+        self.spec = ops.GridSpec(device, bound=bound, **kw)
+        self.embeddings = nn.Parameter(torch.empty(self.spec.n_rows, 2, device=device).uniform_(-1e-4, 1e-4))
+        self.output_dim = self.spec.num_levels * 2
+
+    def forward(self, inputs, bound=None):
+        return ops.grid_encode(inputs.reshape(-1, 3), self.embeddings, self.spec).view(*inputs.shape[:-1], self.output_dim)
+
+
+class MeshBindingGaussianModel(nn.Module):
+    """core/system/avatar.py:921-1094."""
+
+    def __init__(self, mesh: dict, n_per_triangle=6, device='cuda'):
+        super().__init__()
+        self.n_per_triangle = n_per_triangle
+        self.register_buffer('predefined_vertex_indices', mesh['predefined_vertex_indices'].to(device))
+        self.register_buffer('triangles', mesh['triangles'].to(device))
+        Fn = self.triangles.shape[0]
+        p2t = torch.arange(Fn, device=device)[..., None].expand(-1, n_per_triangle).reshape(-1)
+        self.register_buffer('points_to_vertices', self.triangles[p2t])
+        self._bary_coords = nn.Parameter(mesh['_bary_coords'].clone().to(device))
+        self._vertex_coords = nn.Parameter(mesh['_vertex_coords'].clone().to(device), requires_grad=False)
+        self._scales = nn.Parameter(mesh['_scales'].clone().to(device))
+
+    def get_positions(self, vertex_coords):
+        bary = self._bary_coords / self._bary_coords.sum(dim=-1, keepdim=True)
+        return torch.einsum('fnv,fvc->fnc', bary, vertex_coords[self.triangles]).reshape(-1, 3)
+
+    def get_scales_and_quaternions(self, vertex_coords, positions, eps=1e-9):
+        dot = lambda a, b: (a * b).sum(-1, keepdim=True)
+        nrm = lambda v: torch.linalg.vector_norm(v, dim=-1, keepdim=True)
+        pv = vertex_coords[self.points_to_vertices]
+        p0, p1, p2, p3 = positions, pv[:, 0], pv[:, 1], pv[:, 2]
+        # vertex normals (utils/mesh.py:34-97)
+        i0, i1, i2 = self.triangles[:, 0], self.triangles[:, 1], self.triangles[:, 2]
+        fn = torch.cross(vertex_coords[i1] - vertex_coords[i0], vertex_coords[i2] - vertex_coords[i0], dim=-1)
+        fn = fn / torch.sqrt(torch.clamp((fn * fn).sum(-1, keepdim=True), min=1e-20))
+        vn = torch.zeros_like(vertex_coords).index_add(0, i0, fn).index_add(0, i1, fn).index_add(0, i2, fn)
+        vn = torch.where(dot(vn, vn) > 1e-20, vn, torch.tensor([0.0, 0.0, 1.0], device=vn.device))
+        vn = vn / torch.sqrt(torch.clamp(dot(vn, vn), min=1e-20))
+        pn = (vn[self.points_to_vertices] * self._bary_coords.reshape(-1, 3)[:, :, None]).sum(dim=1)
+        v0 = pn / (nrm(pn) + eps)
+        ref = torch.tensor((1.0, 0.0, 0.0), device=p0.device).expand_as(p0)
+        v1 = torch.cross(v0, ref, dim=1)
+        v1 = v1 / (nrm(v1) + eps)
+        v2 = torch.cross(v0, v1, dim=1)
+        v2 = v2 / (nrm(v2) + eps)
+        R = torch.stack((v0, v1, v2), dim=2) * torch.tensor([1.0, -1.0, -1.0], device=p0.device).view(1, 3, 1)
+        s1 = (dot(p1 - p0, v1).abs() + dot(p2 - p0, v1).abs() + dot(p3 - p0, v1).abs()) / self.n_per_triangle
+        s2 = (dot(p1 - p0, v2).abs() + dot(p2 - p0, v2).abs() + dot(p3 - p0, v2).abs()) / self.n_per_triangle
+        s1 = s1 * torch.clamp(self._scales[:, 1:2], min=0.5, max=2.0)
+        s2 = s2 * torch.clamp(self._scales[:, 2:3], min=0.5, max=2.0)
+        scales = torch.cat((torch.zeros_like(s1), s1, s2), dim=1)
+        return scales, dlbs.standardize_quaternion(dlbs.matrix_to_quaternion(R))
+
+
+class DreamWaltzGAvatar(nn.Module):
+    """The animate() path of reference DreamWaltzG (avatar.py:1500-1588) on dwg kernels."""
+
+    def __init__(self, body_model: dict, avatar: dict, device='cuda', nerf_bound=2.0,
+                 init_offset=0.01, init_scale=1e-3, max_scale=0.01):
+        super().__init__()
+        self.device = device
+        self.lbs_model = dlbs.GeneralLinearBlendSkinning(body_model, device=device)
+        self._positions = nn.Parameter(avatar['_positions'].clone().to(device))
+        self._scales = nn.Parameter(avatar['_scales'].clone().to(device))
+        self._quaternions = nn.Parameter(avatar['_quaternions'].clone().to(device))
+        self._lbs_weights = nn.Parameter(avatar['_lbs_weights'].clone().to(device), requires_grad=False)
+        self.nerf_bound = nerf_bound
+        self.nerf_encoder = GridEncoder(device=device, bound=nerf_bound)
+        self.nerf_opacity_and_color_net = MLP(32, 4, 64, 3).to(device)
+        self.nerf_scale_and_quaternion_net = DeformNetwork(32, 63, 4, 64).to(device)
+        self.mesh_binding_gaussians = nn.ModuleDict()
+        if avatar.get('mesh') is not None:
+            self.mesh_binding_gaussians['hands'] = MeshBindingGaussianModel(avatar['mesh'], device=device)
+        self.init_offset, self.init_scale, self.max_scale = init_offset, init_scale, max_scale
+        self.smpl_canonical_inputs = {}
+        self._canonical_cache = None
+
+    def get_lbs_weights(self):
+        return self._lbs_weights / self._lbs_weights.sum(dim=-1, keepdim=True)          # avatar.py:914-917
+
+    def _joint_pose_transform(self, transforms):
+        return dlbs.RigidTransform.compose(transforms['J_pose_rigid'], transforms['G_transl_offset']).squeeze(0)
+
+    def static_mlp_forward(self, enc, fix_opacities=False):
+        o = self.nerf_opacity_and_color_net(enc)
+        colors = torch.sigmoid(o[:, 1:])
+        opac = torch.ones_like(o[:, :1]) if fix_opacities else torch.sigmoid(o[:, :1])
+        return colors, opac
+
+    def animate(self, smpl_observed_inputs: Optional[dict] = None) -> GaussianOutput:
+        if smpl_observed_inputs is None:
+            smpl_observed_inputs = self.smpl_canonical_inputs
+        # canonical LBS: constant while the shape is frozen -> evaluated once and cached
+        # (the reference recomputes it every step, avatar.py:1508)
+        if self._canonical_cache is None:
+            with torch.no_grad():
+                _, cV, ctr = self.lbs_model.forward(**self.smpl_canonical_inputs)
+            self._canonical_cache = (cV, ctr)
+        cnl_V, cnl_tr = self._canonical_cache
+        with torch.no_grad():
+            _, obs_V, obs_tr = self.lbs_model.forward(**smpl_observed_inputs)
+        positions = self._positions
+        W = self.get_lbs_weights()
+        cnl_jt = self._joint_pose_transform(cnl_tr)
+        obs_jt = self._joint_pose_transform(obs_tr)
+        canonical_positions = cnl_jt.transform_points(positions, weights=W)
+        enc = self.nerf_encoder(canonical_positions, bound=self.nerf_bound)
+        colors, opacities = self.static_mlp_forward(enc)
+        body_pose = smpl_observed_inputs.get('body_pose', torch.zeros(1, 63, device=self.device))
+        offsets, d_scales, _ = self.nerf_scale_and_quaternion_net(enc, body_pose)
+        # non_rigid_transform (avatar.py:1464-1498, shipped flags)
+        pos = positions + offsets * self.init_offset
+        scales = (torch.exp(d_scales) * self.init_scale).clamp_max(self.max_scale)
+        quats = F.normalize(self._quaternions)
+        pos, quats = obs_jt.transform_points_and_quaternions(pos, quats, W)
+        out = GaussianOutput(positions=pos, opacities=opacities, colors=colors, quaternions=quats, scales=scales)
+        parts = [out]
+        for _, gm in self.mesh_binding_gaussians.items():
+            cnl_T, obs_T = cnl_V.squeeze(0) if cnl_V.SE3.dim() == 4 else cnl_V, obs_V.squeeze(0) if obs_V.SE3.dim() == 4 else obs_V
+            vidx = gm.predefined_vertex_indices
+            cnl_vc = cnl_T.transform_points(gm._vertex_coords, indices=vidx)
+            m_enc = self.nerf_encoder(gm.get_positions(cnl_vc), bound=self.nerf_bound)
+            m_col, m_op = self.static_mlp_forward(m_enc, fix_opacities=True)
+            obs_vc = obs_T.transform_points(gm._vertex_coords, indices=vidx)
+            m_pos = gm.get_positions(obs_vc)
+            m_sc, m_q = gm.get_scales_and_quaternions(obs_vc, m_pos)
+            parts.append(GaussianOutput(positions=m_pos, opacities=m_op, colors=m_col, quaternions=m_q, scales=m_sc))
+        if len(parts) == 1:
+            return out
+        cat = lambda k: torch.cat([getattr(p, k) for p in parts], dim=0)
+        return GaussianOutput(positions=cat('positions'), opacities=cat('opacities'), colors=cat('colors'),
+                              quaternions=cat('quaternions'), scales=cat('scales'))
+
+
+class GaussianRenderer:
+    """core/gaussian/gaussian_renderer.py:9-224 (the wrapper around the rasteriser)."""
+
+    def __init__(self, sh_levels=4, bg_color=(0.0, 0.0, 0.0)):
+        self.sh_levels = sh_levels
+        self.bg_color = torch.tensor(bg_color)
+
+    def render(self, data: dict, gaussians: GaussianOutput, return_2d_radii: bool = False) -> dict:
+        from .camera import raster_matrices
+        view, proj, campos, tanfovx, tanfovy = raster_matrices(data)         # host tensors: no device sync
+        means3D = gaussians.positions
+        screenspace_points = torch.zeros(means3D.shape[0], 3, dtype=means3D.dtype, requires_grad=True, device=means3D.device)
+        colors = gaussians.colors
+        if colors is None:
+            colors = ops.sh_colors(gaussians.sh_features, means3D, campos.to(means3D.device), self.sh_levels)
+        img, radii, depth, alpha = ops.rasterize(
+            means3D, screenspace_points, colors, gaussians.opacities, gaussians.scales, gaussians.quaternions,
+            image_height=data['image_height'], image_width=data['image_width'], tanfovx=tanfovx, tanfovy=tanfovy,
+            viewmatrix=view, projmatrix=proj, bg=self.bg_color)
+        out = {'image': img.permute(1, 2, 0).unsqueeze(0), 'depth': depth.permute(1, 2, 0).unsqueeze(0),
+               'alpha': alpha.permute(1, 2, 0).unsqueeze(0), 'image_chw': img}
+        if return_2d_radii:
+            out['radii'] = radii
+            out['viewspace_points'] = screenspace_points
+        return out
