@@ -75,6 +75,8 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     const float bg_dot = bg0 * dLp0 + bg1 * dLp1 + bg2 * dLp2;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     const int lane = threadIdx.x & 31;
+    const float sx0 = (float)(blockIdx.x * TILE), sx1 = sx0 + (float)(TILE - 1);
+    const float sy0 = (float)(blockIdx.y * TILE + ((threadIdx.x >> 5) << 1)), sy1 = sy0 + 1.0f;
     for (int it = 0; it < rounds; it++) {
         const int c = rounds - 1 - it;
         const int buf = it & 1;
@@ -91,6 +93,8 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
             const uint32_t k = (uint32_t)(c * CHUNK + j);
             float v[NG];
             bool contrib = false;
+            const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][j]);
+            if (!strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1)) continue;   // warp-uniform
             if (k < last_contributor) {
                 const Rec rc = s_rec[buf][j];
                 float alpha, G, dx, dy;

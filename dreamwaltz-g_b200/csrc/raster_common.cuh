@@ -1,5 +1,7 @@
 // Shared definitions for the tile rasteriser (R11-R13).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dwg {
@@ -10,16 +12,18 @@ constexpr int TILE_PIX = TILE * TILE;
 constexpr int CHUNK = 256;               // instances staged per TMA bulk copy in the blend loops
 constexpr int SORT_CHUNK = 2048;         // keys sorted in shared memory at a time
 
-// One (tile, Gaussian) instance in depth order, gathered once by the sort kernel and then
+// One (tile, Gaussian) instance in depth order, gathered once by the pack kernel and then
 // streamed (contiguously, 48 B, 16-byte aligned) by the forward and backward blend kernels.
+// The first 16 bytes carry everything a warp needs to decide that none of its pixels can be
+// touched (conservative screen-space extent of the alpha >= 1/255 ellipse, as two halves).
 struct __align__(16) Rec {
     float x, y;              // pixel-space mean
+    uint32_t ext;            // half2: (ext_x, ext_y), rounded up, conservative
+    uint32_t idx;            // Gaussian index
     float cx, cy, cz;        // conic
     float op;                // opacity
     float r, g, b;           // colour
     float depth;             // view-space z
-    uint32_t idx;            // Gaussian index
-    uint32_t pad;
 };
 static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
 
@@ -47,16 +51,21 @@ struct BinView {
     uint32_t* tile_fill;     // [T]   scatter cursors
     uint32_t* tile_start;    // [T+1] exclusive scan
     uint2* ranges;           // [T]   [start,end) per tile (upstream identifyTileRanges)
+    uint32_t* n_runs;        // [4]   {number of sort runs, ...}
+    uint2* runs;             // [R]   (first instance, count) of each <= SORT_CHUNK run
     uint64_t* inst_key;      // [P]   (depth bits << 32 | idx), unsorted then sorted per tile
     uint64_t* inst_tmp;      // [P]   merge ping-pong buffer (tiles with > SORT_CHUNK instances)
+    uint32_t* inst_tile;     // [P]   tile of each instance slot
     uint64_t* keys_out;      // [P]   (tile << 32 | depth bits)  == upstream sorted keys
     uint32_t* vals_out;      // [P]   Gaussian idx               == upstream sorted values
     Rec* recs;               // [P]
+    __host__ __device__ static int64_t run_cap(int64_t P, int T) { return T + P / SORT_CHUNK + 1; }
     __host__ __device__ static size_t header_bytes(int T) {
-        return align256(sizeof(uint32_t) * T) * 2 + align256(sizeof(uint32_t) * (T + 1)) + align256(sizeof(uint2) * T);
+        return align256(sizeof(uint32_t) * T) * 2 + align256(sizeof(uint32_t) * (T + 1)) + align256(sizeof(uint2) * T) + 256;
     }
     __host__ __device__ static size_t bytes(int64_t P, int T) {
-        return header_bytes(T) + align256(sizeof(uint64_t) * P) * 3 + align256(sizeof(uint32_t) * P) + align256(sizeof(Rec) * P);
+        return header_bytes(T) + align256(sizeof(uint2) * run_cap(P, T)) + align256(sizeof(uint64_t) * P) * 3 +
+               align256(sizeof(uint32_t) * P) * 2 + align256(sizeof(Rec) * P);
     }
     __host__ __device__ BinView(void* base, int64_t P, int T) {
         char* p = (char*)base;
@@ -64,13 +73,24 @@ struct BinView {
         tile_fill = (uint32_t*)p; p += align256(sizeof(uint32_t) * T);
         tile_start = (uint32_t*)p; p += align256(sizeof(uint32_t) * (T + 1));
         ranges = (uint2*)p; p += align256(sizeof(uint2) * T);
+        n_runs = (uint32_t*)p; p += 256;
+        runs = (uint2*)p; p += align256(sizeof(uint2) * run_cap(P, T));
         inst_key = (uint64_t*)p; p += align256(sizeof(uint64_t) * P);
         inst_tmp = (uint64_t*)p; p += align256(sizeof(uint64_t) * P);
+        inst_tile = (uint32_t*)p; p += align256(sizeof(uint32_t) * P);
         keys_out = (uint64_t*)p; p += align256(sizeof(uint64_t) * P);
         vals_out = (uint32_t*)p; p += align256(sizeof(uint32_t) * P);
         recs = (Rec*)p;
     }
 };
+
+// number of pairwise merge passes a tile segment of n instances needs after the run sort
+__host__ __device__ inline int merge_passes(uint32_t n) {
+    int p = 0;
+    for (uint32_t len = SORT_CHUNK; len < n; len <<= 1) p++;
+    return p;
+}
+constexpr int MAX_MERGE_PASSES = 6;      // tiles up to SORT_CHUNK * 64 = 131072 instances
 
 struct ImgView {
     float* final_T; uint32_t* n_contrib;
@@ -104,6 +124,9 @@ __device__ __forceinline__ float spec_expf(float x) {
 
 // alpha of one instance at pixel (pxf,pyf); false when the instance is skipped (power > 0 or
 // alpha < 1/255).  Operation order is part of the spec (see oracle eval_alpha).
+// power < -5.6 implies exp(power) < 0.0037 < 1/255 even with a few ulp of error, hence
+// alpha = min(0.99, op*G) <= G < 1/255 for any op <= 1: rejecting early is exactly equivalent
+// (for op > 1 the early test is skipped).
 __device__ __forceinline__ bool eval_alpha(const Rec& rc, float pxf, float pyf, float& alpha, float& G, float& dx, float& dy) {
     dx = __fsub_rn(rc.x, pxf);
     dy = __fsub_rn(rc.y, pyf);
@@ -112,9 +135,16 @@ __device__ __forceinline__ bool eval_alpha(const Rec& rc, float pxf, float pyf, 
     const float c = __fmul_rn(__fmul_rn(rc.cy, dx), dy);
     const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(a, b)), c);
     if (power > 0.0f) return false;
+    if (power < -5.6f && rc.op <= 1.0f) return false;
     G = spec_expf(power);
     alpha = fminf(0.99f, __fmul_rn(rc.op, G));
     return !(alpha < 1.0f / 255.0f);
+}
+
+// Conservative test: can ANY pixel of the strip [x0,x1] x [y0,y1] get alpha >= 1/255 ?
+__device__ __forceinline__ bool strip_may_touch(float rx, float ry, uint32_t ext, float x0, float x1, float y0, float y1) {
+    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&ext));
+    return !(rx + e.x < x0 || rx - e.x > x1 || ry + e.y < y0 || ry - e.y > y1);
 }
 
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk) helpers ----

@@ -14,7 +14,8 @@ namespace raster {
 int launch_pre(const DwgRasterCamera& cam, int64_t N, const float* means3D, const float* opacities,
                const float* scales, const float* rots, GeomView g, BinView b, int T, int64_t P_cap,
                int32_t* radii, int32_t* status, cudaStream_t st);
-int launch_sort(int T, BinView b, GeomView g, const float* colors, int write_keys, cudaStream_t st);
+int launch_sort(int T, BinView b, GeomView g, const float* colors, const int32_t* status, int64_t P_cap,
+                int write_keys, cudaStream_t st);
 
 __global__ void __launch_bounds__(TILE_PIX)
 render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
@@ -45,7 +46,10 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     }
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, A = 0.f;
-    uint32_t contributor = 0, last = 0;
+    uint32_t last = 0;
+    // this warp's pixel strip (16 x 2)
+    const float sx0 = (float)(blockIdx.x * TILE), sx1 = sx0 + (float)(TILE - 1);
+    const float sy0 = (float)(blockIdx.y * TILE + ((threadIdx.x >> 5) << 1)), sy1 = sy0 + 1.0f;
     for (int c = 0; c < rounds; c++) {
         const int buf = c & 1;
         // every thread has finished reading buffer buf^1 (chunk c-1): safe to refill it with chunk c+1
@@ -62,14 +66,19 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
         }
         mbar_wait(&s_bar[buf], (uint32_t)((c >> 1) & 1));
         const int cnt = min(CHUNK, n - c * CHUNK);
-        if (!done) {
+        // Warp-uniform loop: the first 16 bytes of a record decide whether ANY pixel of this warp's
+        // 16x2 strip can be touched; most instances of a tile are rejected here for most warps.
+        const bool warp_live = __any_sync(0xffffffffu, !done);
+        if (warp_live) {
             for (int j = 0; j < cnt; j++) {
-                contributor++;
+                const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][j]);
+                if (!strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1)) continue;
+                if (done) continue;
                 const Rec rc = s_rec[buf][j];
                 float alpha, G, dx, dy;
                 if (!eval_alpha(rc, pxf, pyf, alpha, G, dx, dy)) continue;
                 const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                if (test_T < 0.0001f) { done = true; break; }
+                if (test_T < 0.0001f) { done = true; continue; }
                 const float w = __fmul_rn(alpha, T);
                 C0 = __fadd_rn(C0, __fmul_rn(rc.r, w));
                 C1 = __fadd_rn(C1, __fmul_rn(rc.g, w));
@@ -77,7 +86,7 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                 D = __fadd_rn(D, __fmul_rn(rc.depth, w));
                 A = __fadd_rn(A, w);
                 T = test_T;
-                last = contributor;
+                last = (uint32_t)(c * CHUNK + j + 1);
             }
         }
     }
@@ -126,7 +135,7 @@ extern "C" int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N, const f
     ImgView im(img, H, W);
     int rc = launch_pre(*cam, N, means3D, opacities, scales, rotations, g, b, T, P_cap, radii, status, st);
     if (rc != DWG_OK) return rc;
-    rc = launch_sort(T, b, g, colors_precomp, 1, st);
+    rc = launch_sort(T, b, g, colors_precomp, status, P_cap, 1, st);
     if (rc != DWG_OK) return rc;
     render_fwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2],
                                                         out_color, out_depth, out_alpha, im.final_T, im.n_contrib);

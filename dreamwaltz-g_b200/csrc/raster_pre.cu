@@ -183,7 +183,44 @@ tile_scan_kernel(int T, BinView b, int64_t P_cap, int32_t* __restrict__ status) 
         status[1] = (int32_t)P;
         status[2] = (int32_t)m;
         status[3] = 0;
+        s_carry = 0;
     }
+    __syncthreads();
+    // ---- sort-run table: every tile segment is cut into runs of <= SORT_CHUNK instances ----
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + threadIdx.x;
+        uint2 rg = make_uint2(0u, 0u);
+        if (t < T) rg = b.ranges[t];
+        const uint32_t n = rg.y - rg.x;
+        const uint32_t v = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+        uint32_t incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, off);
+            if ((threadIdx.x & 31) >= off) incl += nb;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t nb = __shfl_up_sync(0xffffffffu, w, off);
+                if (threadIdx.x >= off) w += nb;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u;
+        const uint32_t carry = s_carry;
+        uint32_t r0 = carry + warp_off + incl - v;
+        for (uint32_t k = 0; k < v; k++)
+            b.runs[r0 + k] = make_uint2(rg.x + k * SORT_CHUNK, min((uint32_t)SORT_CHUNK, n - k * SORT_CHUNK));
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + warp_off + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) b.n_runs[0] = s_carry;
 }
 
 __global__ void __launch_bounds__(256)
@@ -197,7 +234,7 @@ scatter_kernel(int64_t N, int gx, GeomView g, BinView b, int64_t P_cap) {
         for (int x = rc.x; x < rc.z; x++) {
             const int t = y * gx + x;
             const uint32_t slot = b.tile_start[t] + atomicAdd(&b.tile_fill[t], 1u);
-            if ((int64_t)slot < P_cap) b.inst_key[slot] = key;
+            if ((int64_t)slot < P_cap) { b.inst_key[slot] = key; b.inst_tile[slot] = (uint32_t)t; }
         }
 }
 

@@ -46,6 +46,11 @@ SIGNATURES = {
     'dwg_raster_backward': (c_int, [ctypes.POINTER(DwgRasterCamera), c_int64] + [c_void_p] * 5 +
                             [c_void_p, c_void_p, c_int64, c_void_p] + [c_void_p] * 3 + [c_void_p] * 6 +
                             [c_void_p, c_void_p]),
+    'dwg_gemm_bf16': (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                              c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_float, c_int, c_void_p]),
+    'dwg_conv2d_nhwc_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 11 +
+                             [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'dwg_raster_view': (c_void_p, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int]),
 }
 

@@ -252,3 +252,75 @@ def rasterize(means3D, means2D, colors, opacities, scales, rotations, *, image_h
     cam_args = (int(image_height), int(image_width), float(tanfovx), float(tanfovy), viewmatrix, projmatrix, bg,
                 float(scale_modifier), instance_capacity)
     return _Rasterize.apply(means3D, means2D, colors, opacities, scales, rotations, cam_args, state_out)
+
+
+# ------------------------------------------------------------------------------ tensor-core GEMM / conv
+ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2}
+
+
+def _chk_bf16(t):
+    assert t.is_cuda and t.dtype == torch.bfloat16, 'tcgen05 layers take bf16 CUDA tensors'
+    return t
+
+
+def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=1.0, act=None, out_dtype=torch.bfloat16,
+         out=None):
+    """C[..., M, N] = act(alpha * A[..., M, K] @ B[..., N, K]^T + bias + bias2) + residual  (dwg_gemm_bf16).
+    a: [M,K] / [b1,M,K] / [b2,b1,M,K] bf16, last dim contiguous (any strides that are multiples of 8);
+    b: same rank with N rows."""
+    _chk_bf16(a), _chk_bf16(b)
+    assert a.stride(-1) == 1 and b.stride(-1) == 1 and a.dim() == b.dim() and 2 <= a.dim() <= 4
+    lead = (1,) * (4 - a.dim())
+    a4 = a.as_strided(lead + tuple(a.shape), tuple(a.stride(0) * a.shape[0] for _ in lead) + tuple(a.stride()))
+    b4 = b.as_strided(lead + tuple(b.shape), tuple(b.stride(0) * b.shape[0] for _ in lead) + tuple(b.stride()))
+    nb2, nb1, M, K = a4.shape
+    N = b4.shape[2]
+    assert b4.shape[3] == K and b4.shape[0] == nb2 and b4.shape[1] == nb1
+    if out is None:
+        out = torch.empty(nb2, nb1, M, N, device=a.device, dtype=out_dtype)
+        c4 = out
+        out = out.reshape(tuple(a.shape[:-1]) + (N,))
+    else:
+        c4 = out.as_strided((1,) * (4 - out.dim()) + tuple(out.shape), (0,) * (4 - out.dim()) + tuple(out.stride())) if out.dim() < 4 else out
+        assert c4.stride(-1) == 1
+    r4 = None
+    if residual is not None:
+        _chk_bf16(residual)
+        r4 = residual.as_strided((1,) * (4 - residual.dim()) + tuple(residual.shape), (0,) * (4 - residual.dim()) + tuple(residual.stride())) if residual.dim() < 4 else residual
+        assert r4.stride(-1) == 1
+    bias = None if bias is None else f32c(bias)
+    bias2 = None if bias2 is None else f32c(bias2)
+    check(lib().dwg_gemm_bf16(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
+                              b4.data_ptr(), b4.stride(2), b4.stride(1), b4.stride(0),
+                              c4.data_ptr(), c4.stride(2), c4.stride(1), c4.stride(0), int(c4.dtype == torch.bfloat16),
+                              M, N, K, nb1, nb2, ptr(bias), ptr(bias2), int(bias2_rows_per),
+                              None if r4 is None else r4.data_ptr(), 0 if r4 is None else r4.stride(2),
+                              0 if r4 is None else r4.stride(1), 0 if r4 is None else r4.stride(0),
+                              float(alpha), ACT[act], stream()), 'dwg_gemm_bf16')
+    return out
+
+
+def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding=1, out_hw=None, act=None,
+                out_dtype=torch.bfloat16):
+    """NHWC implicit-GEMM convolution (dwg_conv2d_nhwc_bf16).  x [N,H,W,Cin], w [Cout,k,k,Cin] bf16.
+    padding: int (symmetric) or (top, left) with out_hw=(Ho, Wo) for asymmetric cases."""
+    _chk_bf16(x), _chk_bf16(w)
+    assert x.is_contiguous() and w.is_contiguous()
+    Nimg, H, W, Cin = x.shape
+    Cout, k, k2, Cin2 = w.shape
+    assert k == k2 and Cin2 == Cin
+    ph, pw = (padding, padding) if isinstance(padding, int) else padding
+    if out_hw is None:
+        Ho, Wo = (H + 2 * ph - k) // stride + 1, (W + 2 * pw - k) // stride + 1
+    else:
+        Ho, Wo = out_hw
+    y = torch.empty(Nimg, Ho, Wo, Cout, device=x.device, dtype=out_dtype)
+    if residual is not None:
+        _chk_bf16(residual)
+        assert residual.shape == y.shape and residual.is_contiguous()
+    bias = None if bias is None else f32c(bias)
+    bias2 = None if bias2 is None else f32c(bias2)
+    check(lib().dwg_conv2d_nhwc_bf16(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.bfloat16), Nimg, H, W, Cin, Cout, k,
+                                     stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], stream()),
+          'dwg_conv2d_nhwc_bf16')
+    return y

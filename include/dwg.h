@@ -139,6 +139,36 @@ int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N,
  *       | 10 n_contrib u32[H,W] */
 void* dwg_raster_view(int which, void* geom, void* bin, void* img, int64_t N, int64_t P_cap, int H, int W);
 
+/* ------------------------------------------------------------------------------------------
+ * R14/R15  Dense layers of the UNet / ControlNet / VAE encoder on the 5th-gen tensor cores
+ * (tcgen05.mma, accumulators in TMEM, operands staged by TMA).  Replaces the cuBLAS / cuDNN
+ * calls diffusers makes for nn.Linear / nn.Conv2d / attention matmuls inside
+ * UNet2DConditionModel, ControlNetModel and AutoencoderKL (third party; call sites
+ * core/guidance/controlnet.py:98-114, core/guidance/vae.py:34-40).
+ *
+ * dwg_gemm_bf16:  C[b2][b1][M,N] = act(alpha * A[b2][b1][M,K] . B[b2][b1][N,K]^T + bias[N]
+ *                                      + bias2[row / bias2_rows_per][N]) + residual
+ *   A, B bf16 with K contiguous; strides in ELEMENTS and multiples of 8; C bf16 (out_bf16=1) or
+ *   fp32; residual bf16 with its own strides; act 0 none / 1 SiLU / 2 GELU(erf).
+ */
+int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
+                  const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
+                  void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_bf16,
+                  int M, int N, int K, int nb1, int nb2,
+                  const float* bias, const float* bias2, int bias2_rows_per,
+                  const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
+                  float alpha, int act, void* stream);
+/* dwg_conv2d_nhwc_bf16: implicit-GEMM convolution, no im2col buffer.
+ *   x [Nimg,H,W,Cin] bf16 (Cin % 8 == 0), w [Cout,k,k,Cin] bf16, y [Nimg,Ho,Wo,Cout] bf16/fp32,
+ *   ksize 1|3, stride 1|2, zero padding pad_h/pad_w on the top/left (bottom/right implied by
+ *   Ho/Wo: covers the VAE's asymmetric (0,1,0,1) padding); bias [Cout], bias2_per_image
+ *   [Nimg,Cout] (time embedding), residual [Nimg,Ho,Wo,Cout] bf16. */
+int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int out_bf16,
+                         int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
+                         int pad_h, int pad_w, int Ho, int Wo,
+                         const float* bias, const float* bias2_per_image,
+                         const void* residual, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

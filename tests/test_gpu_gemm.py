@@ -1,0 +1,90 @@
+"""GPU: tcgen05 GEMM / implicit-GEMM conv against a plain PyTorch fp32 reference of the same op
+(inputs rounded to bf16 first, so the only difference is fp32 accumulation order and the bf16
+rounding of the output).  Tolerance: |err| <= 2e-2 * max|ref| for bf16 outputs, 2e-3 for fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dwg import ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _rel(got, ref):
+    return float((got.float() - ref).abs().max() / (ref.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 128, 128), (8192, 320, 320), (300, 77, 40), (4096, 1280, 2560),
+                                   (130, 250, 72), (2, 1280, 320)])
+def test_gemm_plain(M, N, K):
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = torch.randn(N, K, device=DEV).bfloat16()
+    ref = a.float() @ b.float().t()
+    c = ops.gemm(a, b, out_dtype=torch.float32)
+    assert _rel(c, ref) < 2e-3
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV).bfloat16()
+    c2 = ops.gemm(a, b, bias=bias, residual=res, alpha=0.5, act='silu')
+    ref2 = F.silu(0.5 * ref + bias) + res.float()
+    assert c2.dtype == torch.bfloat16 and _rel(c2, ref2) < 2e-2
+    c3 = ops.gemm(a, b, bias=bias, act='gelu', out_dtype=torch.float32)
+    assert _rel(c3, F.gelu(ref + bias)) < 2e-3
+
+
+def test_gemm_strided_batched_attention_shapes():
+    """QK^T and PV for 8 heads x 2 samples with head dim 40, straight from [B, T, heads*hd] tensors."""
+    torch.manual_seed(1)
+    B, T, Hh, hd, Tk = 2, 1024, 8, 40, 77
+    q = torch.randn(B, T, Hh * hd, device=DEV).bfloat16()
+    k = torch.randn(B, Tk, Hh * hd, device=DEV).bfloat16()
+    q4 = q.view(B, T, Hh, hd).permute(0, 2, 1, 3)          # [B, heads, T, hd] strided view
+    k4 = k.view(B, Tk, Hh, hd).permute(0, 2, 1, 3)
+    s = ops.gemm(q4, k4, alpha=hd ** -0.5, out_dtype=torch.float32)
+    ref = torch.einsum('bhtd,bhsd->bhts', q4.float(), k4.float()) * hd ** -0.5
+    assert s.shape == (B, Hh, T, Tk) and _rel(s, ref) < 2e-3
+    # PV with V^T [B, heads, hd, Tk] (K = Tk = 80 after padding to a multiple of 8)
+    p = torch.softmax(ref, -1)
+    Tkp = 80
+    pp = torch.zeros(B, Hh, T, Tkp, device=DEV, dtype=torch.bfloat16)
+    pp[..., :Tk] = p.bfloat16()
+    vt = torch.zeros(B, Hh, hd, Tkp, device=DEV, dtype=torch.bfloat16)
+    vt[..., :Tk] = torch.randn(B, Hh, hd, Tk, device=DEV).bfloat16()
+    out = torch.empty(B, T, Hh * hd, device=DEV, dtype=torch.bfloat16)
+    o4 = out.view(B, T, Hh, hd).permute(0, 2, 1, 3)
+    ops.gemm(pp, vt, out=o4)
+    ref_o = torch.einsum('bhts,bhds->bhtd', pp.float(), vt.float())
+    assert _rel(o4, ref_o) < 2e-2
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k,stride', [
+    (2, 64, 64, 320, 320, 3, 1), (2, 32, 32, 640, 640, 3, 1), (2, 16, 16, 1280, 1280, 3, 1), (2, 8, 8, 1280, 1280, 3, 1),
+    (2, 64, 64, 320, 320, 3, 2), (2, 64, 64, 8, 320, 3, 1), (2, 64, 64, 320, 8, 3, 1), (2, 32, 32, 640, 320, 1, 1),
+    (1, 128, 128, 128, 128, 3, 1), (1, 256, 256, 16, 32, 3, 2), (3, 8, 8, 64, 96, 3, 1), (1, 24, 40, 64, 64, 3, 1)])
+def test_conv2d_nhwc_vs_torch(N, H, W, Cin, Cout, k, stride):
+    torch.manual_seed(2)
+    x = torch.randn(N, H, W, Cin, device=DEV).bfloat16()
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device=DEV)
+    pad = k // 2
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    y = ops.conv2d_nhwc(x, w, bias=bias, stride=stride, padding=pad, out_dtype=torch.float32)
+    assert y.shape == ref.shape and _rel(y, ref) < 2e-3
+    temb = torch.randn(N, Cout, device=DEV)
+    res = torch.randn_like(ref).bfloat16()
+    y2 = ops.conv2d_nhwc(x, w, bias=bias, bias2=temb, residual=res, stride=stride, padding=pad)
+    ref2 = ref + temb[:, None, None, :] + res.float()
+    assert _rel(y2, ref2) < 2e-2
+
+
+def test_conv2d_asymmetric_padding_downsample():
+    """VAE encoder downsample: F.pad(x, (0,1,0,1)) then 3x3 stride-2 conv with padding 0."""
+    torch.manual_seed(3)
+    N, H, W, C = 1, 64, 64, 128
+    x = torch.randn(N, H, W, C, device=DEV).bfloat16()
+    w = (torch.randn(C, 3, 3, C, device=DEV) / (9 * C) ** 0.5).bfloat16()
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xp, w.float().permute(0, 3, 1, 2), None, stride=2, padding=0).permute(0, 2, 3, 1)
+    y = ops.conv2d_nhwc(x, w, stride=2, padding=(0, 0), out_hw=(H // 2, W // 2), out_dtype=torch.float32)
+    assert _rel(y, ref) < 2e-3

@@ -195,7 +195,7 @@ def test_raster_forward_bit_exact_binning_and_image(n, H, W, seed):
     assert np.array_equal(st.view(10, torch.int32, (H, W)).cpu().numpy().view(np.uint32), o['n_contrib'])
     # ---- images: same operation order => bit-exact; PSNR reported as the contractual bound ----
     assert np.array_equal(st.view(9, torch.float32, (H, W)).cpu().numpy().view(np.uint32), o['final_T'].view(np.uint32))
-    for got, ref in ((color.cpu().numpy(), o['color']), (depth[0].cpu().numpy(), o['out_depth']), (alpha[0].cpu().numpy(), o['out_alpha'])):
+    for got, ref in ((color.detach().cpu().numpy(), o['color']), (depth[0].detach().cpu().numpy(), o['out_depth']), (alpha[0].detach().cpu().numpy(), o['out_alpha'])):
         mse = float(np.mean((got - ref) ** 2))
         psnr = 99.0 if mse == 0 else 10 * np.log10(1.0 / mse)
         assert psnr >= 40.0
@@ -236,12 +236,12 @@ def test_raster_large_tile_merge_path_and_capacity_overflow():
     keys = st.view(7, torch.int64, (st.P_cap,)).cpu().numpy().view(np.uint64)[:P]
     assert np.array_equal(keys, o['keys'])
     assert np.array_equal(st.view(10, torch.int32, (H, W)).cpu().numpy().view(np.uint32), o['n_contrib'])
-    np.testing.assert_allclose(color.cpu().numpy(), o['color'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(color.detach().cpu().numpy(), o['color'], rtol=0, atol=1e-6)
     # overflow: capacity below P
     color2, _, _, _, st2, _, _ = _run_gpu(g, kw, cap=max(P // 2, 1))
     s2 = st2.status.cpu().numpy()
     assert s2[0] == 1 and s2[1] == P
-    assert torch.isfinite(color2).all()
+    assert torch.isfinite(color2.detach()).all()
 
 
 def test_raster_empty_and_all_culled():
@@ -251,8 +251,8 @@ def test_raster_empty_and_all_culled():
     color, radii, depth, alpha, st, _, _ = _run_gpu(g, kw)
     bg = torch.tensor([0.1, 0.2, 0.3]).view(3, 1, 1)
     assert int(st.status[1]) == 0 and int(radii.abs().sum()) == 0
-    torch.testing.assert_close(color.cpu(), bg.expand(3, H, W).contiguous())
-    assert float(alpha.abs().max()) == 0.0
+    torch.testing.assert_close(color.detach().cpu(), bg.expand(3, H, W).contiguous())
+    assert float(alpha.detach().abs().max()) == 0.0
 
 
 def test_dropin_rasterizer_module_signature():
@@ -274,7 +274,7 @@ def test_dropin_rasterizer_module_signature():
                                       cov3D_precomp=None)
     o = orast.forward(cam, g['positions'], g['scales'], g['quaternions'], g['opacities'], g['colors'])
     assert color.shape == (3, H, W) and depth.shape == (1, H, W) and alpha.shape == (1, H, W) and radii.dtype == torch.int32
-    np.testing.assert_allclose(color.cpu().numpy(), o['color'], atol=1e-6)
+    np.testing.assert_allclose(color.detach().cpu().numpy(), o['color'], atol=1e-6)
     with pytest.raises(Exception):
         rast(means3D=t['positions'], means2D=m2, opacities=t['opacities'], scales=t['scales'], rotations=t['quaternions'])
     # SH path == SH oracle colours fed to the raster oracle
@@ -283,7 +283,7 @@ def test_dropin_rasterizer_module_signature():
                          scales=t['scales'], rotations=t['quaternions'])
     cols = osh.sh_colors(sh, g['positions'], torch.zeros(3), 3)
     o2 = orast.forward(cam, g['positions'], g['scales'], g['quaternions'], g['opacities'], cols)
-    np.testing.assert_allclose(c_sh.cpu().numpy(), o2['color'], atol=2e-5)
+    np.testing.assert_allclose(c_sh.detach().cpu().numpy(), o2['color'], atol=2e-5)
 
 
 # ------------------------------------------------------------------------------------ animate (R1-R9)
