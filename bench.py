@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- SDS steps/s of the DreamWaltz-G per-step hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one full SDS step on one random view of the cfg2 workload (150k-Gaussian SMPL-X
+avatar, 512x512 render, SD1.5 + ControlNet-openpose shapes, synthetic weights / poses / cameras /
+prompt embeddings): animate (LBS + grid + MLPs + mesh-bound hands) -> tile rasteriser forward ->
+VAE encode -> ControlNet + UNet (CFG batch 2) -> SDS gradient -> backward through the VAE encoder,
+the rasteriser and the avatar to every trainable parameter (optimiser excluded).
+With N > 1 every rank takes its own view per step and the parameter gradients are summed with ONE
+NCCL all-reduce (weak scaling: 1 view per GPU per step); value = views (SDS steps) per second of
+the whole job.  `--impl reference` times the CPU oracle (the reference has no CPU path and
+cannot be installed here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'dreamwaltz-g_b200')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_UNCONSTRAINED, N_MESH_TRI, IMG = 135000, 2500, 512
+WORKLOAD = 'cfg2: 150k-Gaussian SMPL-X avatar SDS step @512^2, SD1.5 + ControlNet-openpose shapes (synthetic weights/data)'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)), 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
+
+
+def poses():
+    rows = np.load(os.path.join(ROOT, 'tests', 'golden', 'poses.npz'))['rows']
+    return rows
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- dwg arm
+class Scene:
+    """Everything one rank needs: avatar, renderer, guidance, per-step inputs."""
+
+    def __init__(self, device, rank, n_unc=N_UNCONSTRAINED, n_tri=N_MESH_TRI, img=IMG, tiny=False):
+        from dwg import avatar as dav, synth
+        from dwg.diffusion import guidance as G, weights as W
+        self.dev, self.rank, self.img = device, rank, img
+        model = synth.make_body_model(0)
+        av = synth.make_avatar(model, n_unc, n_tri, seed=0)
+        self.avatar = dav.DreamWaltzGAvatar(model, av, device=device)
+        with torch.no_grad():
+            g = torch.Generator(device='cpu').manual_seed(1)
+            self.avatar.nerf_encoder.embeddings.copy_((torch.rand(self.avatar.nerf_encoder.embeddings.shape, generator=g) - 0.5).to(device))
+        self.renderer = dav.GaussianRenderer()
+        cfg, vcfg = (W.TINY, W.TINY_VAE) if tiny else (W.SD15, W.VAE15)
+        self.guidance = G.ControlNetScoreDistillation(W.make_unet(cfg), W.make_controlnet(cfg), W.make_vae_encoder(vcfg), cfg, vcfg, device,
+                                                      seed=1000 + rank)
+        self.ctx_dim = cfg['ctx_dim']
+        self.rng = np.random.default_rng(1000 + rank)
+        self.pose_rows = poses()
+        g = torch.Generator().manual_seed(7)
+        # host-side (pinned) per-step inputs of the e2e arm
+        self.h_embeds = {'neg': torch.randn(1, 77, self.ctx_dim, generator=g).pin_memory(), 'text': torch.randn(1, 77, self.ctx_dim, generator=g).pin_memory()}
+        cond = (torch.rand(1, 3, img, img, generator=g) > 0.97).float()          # sparse skeleton-like image
+        self.h_cond = cond.pin_memory()
+        self.d_embeds = {k: v.to(device) for k, v in self.h_embeds.items()}
+        self.d_cond = self.h_cond.to(device)
+        self.params = [p for p in self.avatar.parameters() if p.requires_grad]
+        self.step_i = 0
+
+    def next_view(self):
+        from dwg import camera, synth
+        row = self.pose_rows[self.step_i % len(self.pose_rows)]
+        self.step_i += 1
+        pose = synth.pose_from_row(row)
+        data = camera.random_camera(self.rng, self.img, self.img)
+        return pose, data
+
+    def step(self, pose_dev, data, embeds, cond):
+        for p in self.params:
+            p.grad = None
+        gs = self.avatar.animate(pose_dev)
+        out = self.renderer.render(data, gs)
+        res = self.guidance(out['image_chw'].unsqueeze(0), embeds, cond_inputs=cond)
+        res['diffusion_loss'].backward()
+        return res
+
+
+def flat_grads(params):
+    return torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+
+
+def run_dwg(args):
+    import torch.distributed as dist
+    from dwg import _lib, ops
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(local_rank)
+    dev = f'cuda:{local_rank}'
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    pk, pk_src = peaks()
+    sc = Scene(dev, rank, tiny=args.tiny, n_unc=args.n_unconstrained, img=args.image)
+    if not args.no_graphs:
+        sc.guidance.enable_graphs((args.image, args.image))
+    L = _lib.lib()
+
+    def one_step(e2e):
+        pose, data = sc.next_view()
+        if e2e:
+            # per-step host -> device copies of that step's inputs (pinned memory, async)
+            pose_dev = {k: v.pin_memory().to(dev, non_blocking=True) for k, v in pose.items()}
+            embeds = {k: v.to(dev, non_blocking=True) for k, v in sc.h_embeds.items()}
+            cond = sc.h_cond.to(dev, non_blocking=True)
+        else:
+            pose_dev = {k: v.to(dev) for k, v in pose.items()}
+            embeds, cond = sc.d_embeds, sc.d_cond
+        res = sc.step(pose_dev, data, embeds, cond)
+        if world > 1:
+            fg = flat_grads(sc.params)
+            dist.all_reduce(fg)                      # ONE NCCL all-reduce of every parameter gradient
+        if e2e:
+            # device -> host read of the step's result
+            return float(res['gradients'].abs().mean()), int(res['timestep'][0])
+        return None
+
+    def timed(steps, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.launches
+        e0.record()
+        for _ in range(steps):
+            one_step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, (L.launches - n0) / steps
+
+    for _ in range(args.warmup):
+        one_step(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches = timed(args.steps, False)
+    for _ in range(min(2, args.warmup)):
+        one_step(True)
+    ms_e2e, _ = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): one instrumented,
+    # un-graphed guidance pass with CUDA events around every tensor-core launch; the GPU is kept
+    # busy ahead of the CPU (torch.cuda._sleep) so the events bracket pure execution time.
+    roof = None
+    if rank == 0:
+        g = sc.guidance
+        saved = getattr(g, '_g', None)
+        g._g = None
+        ops.PROFILE = []
+        img = torch.rand(1, 3, args.image, args.image, device=dev, requires_grad=True)
+        torch.cuda._sleep(int(3e8))
+        res = g(img, sc.d_embeds, cond_inputs=sc.d_cond)
+        res['diffusion_loss'].backward()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        g._g = saved
+        tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
+        tot_fl = sum(f for _, _, f, _ in prof)
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12
+        peak = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
+        roof = {'bound': 'tensor', 'kernel': 'dwg::gemm::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv)', 'achieved': round(ach, 1),
+                'peak': peak, 'unit': 'TFLOP/s', 'frac': round(ach / peak, 4), 'traffic': None, 'launches': len(prof),
+                'algorithmic_tflop_per_step': round(tot_fl / 1e12, 3), 'kernel_ms_per_step': round(tot_ms, 3),
+                'peak_source': pk_src + ' bf16_tflops_sustained (kernel timed inside a long step)'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * 1000.0 / ms_step
+    e2e_v = world * 1000.0 / ms_e2e
+    h2d = sc.h_cond.numel() * 4 + sum(v.numel() * 4 for v in sc.h_embeds.values()) + 265 * 4
+    out = {
+        'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)', 'value': round(value, 3), 'unit': 'steps/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_step, 3), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16 tensor-core GEMMs (fp32 accumulate); fp32 geometry/raster', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD if not args.tiny else 'TINY smoke configuration (not the benchmark workload)',
+                   'gaussians': int(sc.avatar._positions.shape[0] + sum(m._scales.shape[0] for m in sc.avatar.mesh_binding_gaussians.values())),
+                   'image': args.image, 'views_per_step': world, 'parallelism': f'view-dp{world} + 1 NCCL all-reduce' if world > 1 else 'single GPU',
+                   'cache': 'inputs larger than L2 (2.6 GB of bf16 weights streamed every step; 126 MB L2)',
+                   'cuda_graphs': not args.no_graphs},
+        'e2e': {'value': round(e2e_v, 3), 'unit': 'steps/s', 'ms_per_step': round(ms_e2e, 3), 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 12},
+        'gpu_launches': int(round(launches)), 'clocks': clocks, 'roofline': roof,
+    }
+    if not args.skip_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline(sample_only=True)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+class OracleScene:
+    """The same workload on the CPU oracle (torch CPU fp32 + the C raster / grid oracle)."""
+
+    def __init__(self, tiny=False, n_unc=N_UNCONSTRAINED, img=IMG):
+        from dwg import synth
+        from dwg.diffusion import weights as W
+        from oracle import grid as ogrid
+        torch.set_num_threads(os.cpu_count())
+        self.img = img
+        self.model = synth.make_body_model(0)
+        self.av = synth.make_avatar(self.model, n_unc, N_MESH_TRI, seed=0)
+        self.cfg, self.vcfg = (W.TINY, W.TINY_VAE) if tiny else (W.SD15, W.VAE15)
+        self.unet, self.cn, self.vae = W.make_unet(self.cfg), W.make_controlnet(self.cfg), W.make_vae_encoder(self.vcfg)
+        self.offsets, _, _, self.scale, self.res = ogrid.level_table()
+        g = torch.Generator().manual_seed(1)
+        self.table = (torch.rand(int(self.offsets[-1]), 2, generator=g) - 0.5)
+        gw = torch.Generator().manual_seed(5)
+        rnd = lambda *s: torch.randn(*s, generator=gw) * 0.3
+        self.nets = {'sigma_w': [rnd(64, 32), rnd(64, 64), rnd(4, 64)], 'sigma_b': [rnd(64), rnd(64), rnd(4)],
+                     'deform': {**{f'layers.{i}.weight': rnd(64, 95 if i == 0 else 64) for i in range(4)}, **{f'layers.{i}.bias': rnd(64) for i in range(4)},
+                                'gaussian_warp.weight': rnd(3, 64), 'gaussian_warp.bias': rnd(3), 'gaussian_rotation.weight': rnd(4, 64),
+                                'gaussian_rotation.bias': rnd(4), 'gaussian_scaling.weight': rnd(3, 64), 'gaussian_scaling.bias': rnd(3)}}
+        g2 = torch.Generator().manual_seed(7)
+        self.emb = {'neg': torch.randn(1, 77, self.cfg['ctx_dim'], generator=g2), 'text': torch.randn(1, 77, self.cfg['ctx_dim'], generator=g2)}
+        self.cond = (torch.rand(1, 3, img, img, generator=g2) > 0.97).float()
+        self.rng = np.random.default_rng(1000)
+        self.rows = poses()
+        self.i = 0
+
+    def step(self):
+        from dwg import camera, synth
+        from oracle import avatar as oav, diffusion as od, grid as ogrid, raster as orast
+        row = self.rows[self.i % len(self.rows)]
+        self.i += 1
+        obs = synth.pose_from_row(row)
+        data = camera.random_camera(self.rng, self.img, self.img)
+        view, proj, campos, tfx, tfy = camera.raster_matrices(data)
+        pos = self.av['_positions'].clone().requires_grad_(True)
+        av = dict(self.av)
+        av['_positions'] = pos
+        av['_quaternions'] = self.av['_quaternions'].clone().requires_grad_(True)
+        table = self.table
+
+        class Enc(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x):
+                out, dy, _ = ogrid.forward(x.detach().numpy(), table.numpy(), self.offsets, self.scale, self.res, bound=2.0)
+                ctx.save_for_backward(x)
+                ctx.dy = dy
+                return torch.from_numpy(out)
+
+            @staticmethod
+            def backward(ctx, g):
+                x, = ctx.saved_tensors
+                _, gx = ogrid.backward(g.numpy(), x.detach().numpy(), tuple(table.shape), self.offsets, self.scale, self.res, dy_dx=ctx.dy, bound=2.0)
+                return torch.from_numpy(gx)
+        gs = oav.animate(self.model, av, self.nets, Enc.apply, {}, obs)
+        cam = orast.make_camera(self.img, self.img, tfx, tfy, view.numpy(), proj.numpy(), (0, 0, 0))
+        o = orast.forward(cam, gs['positions'].detach().numpy(), gs['scales'].detach().numpy(), gs['quaternions'].detach().numpy(),
+                          gs['opacities'].detach().numpy(), gs['colors'].detach().numpy())
+        img = torch.from_numpy(o['color']).unsqueeze(0).requires_grad_(True)
+        veps = torch.randn(1, 4, self.img // 8, self.img // 8)
+        lat = od.vae_encode_latents(self.vae, self.vcfg, img, veps)
+        t = torch.tensor([int(self.rng.integers(20, 981))])
+        noise = torch.randn_like(lat)
+        with torch.no_grad():
+            ln = od.add_noise(lat.detach(), noise, t)
+            grad, _ = od.sds_gradient(self.unet, self.cn, self.cfg, ln, noise, t, self.emb['neg'], self.emb['text'], self.cond, 50.0)
+        (lat * grad).sum().backward()
+        b = orast.backward(cam, o, img.grad[0].numpy())
+        torch.autograd.backward([gs['positions'], gs['colors'], gs['opacities'], gs['scales'], gs['quaternions']],
+                                [torch.from_numpy(b['means3D']), torch.from_numpy(b['colors']), torch.from_numpy(b['opacities']),
+                                 torch.from_numpy(b['scales']), torch.from_numpy(b['rots'])])
+        return float(grad.abs().mean())
+
+
+def cpu_baseline(sample_only=True, tiny=False):
+    """The oracle timed on the host cores on a bounded sample: ONE full SDS step of the same workload."""
+    t0 = time.time()
+    sc = OracleScene(tiny=tiny)
+    t1 = time.time()
+    sc.step()
+    dt = time.time() - t1
+    return {'value': round(1.0 / dt, 5), 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': f'1 full SDS step of the same workload on the CPU oracle ({dt:.1f} s; setup {t1 - t0:.0f} s not counted)'}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    budget_s = 240.0
+    sc = OracleScene(tiny=args.tiny)
+    times = []
+    for _ in range(min(args.warmup, 1)):
+        sc.step()
+    t_begin = time.time()
+    for _ in range(args.steps):
+        t0 = time.time()
+        sc.step()
+        times.append(time.time() - t0)
+        if time.time() - t_begin + times[-1] > budget_s:
+            break
+    ms = 1000.0 * float(np.mean(times))
+    v = 1000.0 / ms
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)', 'value': round(v, 5), 'unit': 'steps/s',
+        'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': len(times), 'warmup': min(args.warmup, 1), 'ms_per_step': round(ms, 1),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'note': 'reference has no CPU path and is not installable here (diffusers, smplx, pytorch3d, '
+                   'diff_gaussian_rasterization absent, no network): this arm times the CPU oracle restatement of the same step'},
+        'cpu_baseline': {'value': round(v, 5), 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': f'{len(times)} full SDS steps of the same workload'},
+        'e2e': {'value': round(v, 5), 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='dwg', choices=['dwg', 'reference'])
+    ap.add_argument('--tiny', action='store_true', help='reduced-width smoke configuration (NOT the benchmark workload)')
+    ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--n-unconstrained', type=int, default=N_UNCONSTRAINED)
+    ap.add_argument('--image', type=int, default=IMG)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_dwg(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -36,6 +36,7 @@ struct Params {
     int M, N, K;                    // per batch entry (conv: M = N_img*Ho*Wo, K = Cin per tap)
     int taps_w, taps_h;             // 1,1 for plain GEMM
     int k_chunks;                   // ceil(K / 64)
+    uint32_t a_bytes;               // bytes one A-tile TMA delivers (the box may hold < 128 rows for tiny images)
     // batching (plain GEMM): z = blockIdx.z -> (z % nb1, z / nb1)
     int nb1;
     // conv geometry (taps > 1 or conv_mode)
@@ -178,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
-                mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                mbar_expect_tx(&full[s], p.a_bytes + B_BYTES);
                 const int kc = it % p.k_chunks;
                 const int tap = it / p.k_chunks;
                 if (p.conv_mode) {
@@ -383,6 +384,7 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     }
     Params p = {};
     p.M = M; p.N = N; p.K = K; p.taps_w = 1; p.taps_h = 1; p.k_chunks = (K + BK - 1) / BK; p.nb1 = nb1; p.conv_mode = 0;
+    p.a_bytes = BM * BK * 2;
     p.C = C; p.out_bf16 = out_bf16; p.ldc = ldc; p.c_b1 = c_b1; p.c_b2 = c_b2;
     p.bias = bias; p.bias2 = bias2; p.bias2_rows_per = bias2_rows_per;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.r_b1 = r_b1; p.r_b2 = r_b2;
@@ -432,6 +434,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     }
     Params p = {};
     p.M = Nimg * Ho * Wo; p.N = Cout; p.K = Cin; p.taps_w = ksize; p.taps_h = ksize; p.k_chunks = (Cin + BK - 1) / BK;
+    p.a_bytes = (uint32_t)(BW * BH * BNI * BK * 2);
     p.nb1 = 1; p.conv_mode = 1; p.Ho = Ho; p.Wo = Wo; p.BH = BH; p.BW = BW; p.BNI = BNI; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
     p.stride = stride; p.pad_h = pad_h; p.pad_w = pad_w;
     p.C = y; p.out_bf16 = out_bf16; p.ldc = Cout;

@@ -1,0 +1,448 @@
+// Normalisation / activation / softmax kernels of the diffusion blocks (R14/R15), NHWC bf16.
+// All are HBM-bound streaming kernels: 128-bit loads (8 bf16), fp32 math, 128-bit stores.
+//   groupnorm (+SiLU) forward: stats pass (per-(image,group) sum / sumsq via block reduction and
+//   a few atomics) + apply pass; backward (VAE encoder input-gradient) the same two-pass shape;
+//   layernorm over channels (one warp per token); row softmax (bf16 in place); GEGLU; SiLU;
+//   the fused CFG + SDS-gradient epilogue (core/guidance/basic.py:595-603,642).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dwg {
+namespace nn {
+
+struct bf8 { __nv_bfloat162 v[4]; };
+static_assert(sizeof(bf8) == 16, "bf8");
+
+__device__ __forceinline__ void unpack8(const bf8& p, float f[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(p.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ bf8 pack8(const float f[8]) {
+    bf8 p;
+#pragma unroll
+    for (int i = 0; i < 4; i++) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return p;
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad(float x) { const float s = 1.0f / (1.0f + __expf(-x)); return s * (1.0f + x * (1.0f - s)); }
+
+// ---------------------------------------------------------------------------- GroupNorm
+// x [N, HW, C] bf16, C % 8 == 0, (C/G) % 8 == 0 or 8 % (C/G) == 0 handled generically via smem bins.
+// stats[n][g] = (sum, sumsq) accumulated with atomics (caller zeroes).
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, int HW, int C, int G, int rows_per_cta) {
+    extern __shared__ float s_bins[];        // [G][2]
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_bins[i] = 0.f;
+    __syncthreads();
+    const int c8 = C / 8;                    // 16-byte vectors per row
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(HW, row0 + rows_per_cta);
+    const bf8* xp = reinterpret_cast<const bf8*>(x + (size_t)n * HW * C);
+    // thread -> (row lane, fixed vector column): per-thread register accumulation over rows, a
+    // handful of shared-memory atomics at the end
+    const int rp = c8 <= 256 ? 256 / c8 : 1;
+    const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
+    for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
+        float s[8], ss[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { s[i] = 0.f; ss[i] = 0.f; }
+        for (int r = row0 + rl; r < row1; r += rp) {
+            float f[8];
+            unpack8(xp[(size_t)r * c8 + cv], f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+        }
+        if (cpg >= 8) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a += s[i]; b += ss[i]; }
+            const int g = (cv * 8) / cpg;
+            atomicAdd(&s_bins[2 * g], a);
+            atomicAdd(&s_bins[2 * g + 1], b);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int g = (cv * 8 + i) / cpg;
+                atomicAdd(&s_bins[2 * g], s[i]);
+                atomicAdd(&s_bins[2 * g + 1], ss[i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(size_t)n * 2 * G + i], s_bins[i]);
+}
+
+// y = (x - mean) * rstd * gamma + beta, optional SiLU
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int HW, int C, int G, float eps, int do_silu,
+                int64_t total_vec) {
+    const int c8 = C / 8, cpg = C / G;
+    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(v % c8);
+        const int n = (int)(v / ((int64_t)HW * c8));
+        float f[8];
+        unpack8(reinterpret_cast<const bf8*>(x)[v], f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int c = cv * 8 + i;
+            const int g = c / cpg;
+            const float mean = stats[((size_t)n * G + g) * 2] * inv_cnt;
+            const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
+            float o = (f[i] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
+            if (do_silu) o = silu(o);
+            f[i] = o;
+        }
+        reinterpret_cast<bf8*>(y)[v] = pack8(f);
+    }
+}
+
+// Backward of y = act(GN(x)).  Pass 1: per-(n,g) sums of (gamma*dz) and (gamma*dz*xhat), dz = dy * act'(z).
+__global__ void __launch_bounds__(256)
+gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ bstats,
+                    int HW, int C, int G, float eps, int do_silu, int rows_per_cta) {
+    extern __shared__ float s_bins[];
+    const int n = blockIdx.y;
+    const int cpg = C / G, c8 = C / 8;
+    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_bins[i] = 0.f;
+    __syncthreads();
+    const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
+    const bf8* xp = reinterpret_cast<const bf8*>(x + (size_t)n * HW * C);
+    const bf8* dp = reinterpret_cast<const bf8*>(dy + (size_t)n * HW * C);
+    const int rp = c8 <= 256 ? 256 / c8 : 1;
+    const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
+    for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
+        float s1[8], s2[8], mean[8], rstd[8], gm[8], bt[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int c = cv * 8 + i, g = c / cpg;
+            s1[i] = 0.f; s2[i] = 0.f;
+            mean[i] = stats[((size_t)n * G + g) * 2] * inv_cnt;
+            const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean[i] * mean[i], 0.f);
+            rstd[i] = rsqrtf(var + eps);
+            gm[i] = gamma[c]; bt[i] = beta[c];
+        }
+        for (int r = row0 + rl; r < row1; r += rp) {
+            float f[8], d[8];
+            unpack8(xp[(size_t)r * c8 + cv], f);
+            unpack8(dp[(size_t)r * c8 + cv], d);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float xh = (f[i] - mean[i]) * rstd[i];
+                float dz = d[i];
+                if (do_silu) dz *= silu_grad(xh * gm[i] + bt[i]);
+                const float gd = gm[i] * dz;
+                s1[i] += gd; s2[i] += gd * xh;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int g = (cv * 8 + i) / cpg;
+            atomicAdd(&s_bins[2 * g], s1[i]);
+            atomicAdd(&s_bins[2 * g + 1], s2[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&bstats[(size_t)n * 2 * G + i], s_bins[i]);
+}
+
+// Pass 2: dx = rstd * (gamma*dz - mean(gamma*dz) - xhat * mean(gamma*dz*xhat)); optional += dx_add
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
+                    const float* __restrict__ bstats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const __nv_bfloat16* __restrict__ dx_add, __nv_bfloat16* __restrict__ dx, int HW, int C, int G, float eps,
+                    int do_silu, int64_t total_vec) {
+    const int c8 = C / 8, cpg = C / G;
+    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(v % c8);
+        const int n = (int)(v / ((int64_t)HW * c8));
+        float f[8], d[8], a[8];
+        unpack8(reinterpret_cast<const bf8*>(x)[v], f);
+        unpack8(reinterpret_cast<const bf8*>(dy)[v], d);
+        if (dx_add) unpack8(reinterpret_cast<const bf8*>(dx_add)[v], a);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int c = cv * 8 + i, g = c / cpg;
+            const float mean = stats[((size_t)n * G + g) * 2] * inv_cnt;
+            const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + eps);
+            const float xh = (f[i] - mean) * rstd;
+            float dz = d[i];
+            if (do_silu) dz *= silu_grad(xh * gamma[c] + beta[c]);
+            const float m1 = bstats[((size_t)n * G + g) * 2] * inv_cnt, m2 = bstats[((size_t)n * G + g) * 2 + 1] * inv_cnt;
+            float o = rstd * (gamma[c] * dz - m1 - xh * m2);
+            if (dx_add) o += a[i];
+            f[i] = o;
+        }
+        reinterpret_cast<bf8*>(dx)[v] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------- LayerNorm (one warp per row)
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, c8 = C / 8;
+    const bf8* xp = reinterpret_cast<const bf8*>(x + row * C);
+    float s = 0.f, ss = 0.f;
+    for (int v = lane; v < c8; v += 32) {
+        float f[8];
+        unpack8(xp[v], f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { s += f[i]; ss += f[i] * f[i]; }
+    }
+    for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
+    const float mean = s / C, rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
+    bf8* yp = reinterpret_cast<bf8*>(y + row * C);
+    for (int v = lane; v < c8; v += 32) {
+        float f[8];
+        unpack8(xp[v], f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) f[i] = (f[i] - mean) * rstd * gamma[v * 8 + i] + beta[v * 8 + i];
+        yp[v] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------- row softmax (bf16, in place)
+// rows x cols_pad (cols valid, the padding columns are written as 0); one CTA per row.
+__global__ void __launch_bounds__(256)
+softmax_kernel(__nv_bfloat16* __restrict__ s, int cols, int cols_pad) {
+    __shared__ float red[8];
+    __nv_bfloat16* row = s + (size_t)blockIdx.x * cols_pad;
+    const int c8 = cols_pad / 8;
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < c8; v += blockDim.x) {
+        float f[8];
+        unpack8(reinterpret_cast<const bf8*>(row)[v], f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (v * 8 + i < cols) mx = fmaxf(mx, f[i]);
+    }
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < c8; v += blockDim.x) {
+        float f[8];
+        unpack8(reinterpret_cast<const bf8*>(row)[v], f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (v * 8 + i < cols) sum += __expf(f[i] - mx);
+    }
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sum += red[w];
+    const float inv = 1.0f / sum;
+    for (int v = threadIdx.x; v < c8; v += blockDim.x) {
+        float f[8];
+        unpack8(reinterpret_cast<const bf8*>(row)[v], f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) f[i] = (v * 8 + i < cols) ? __expf(f[i] - mx) * inv : 0.f;
+        reinterpret_cast<bf8*>(row)[v] = pack8(f);
+    }
+}
+
+// short rows (cols_pad <= 256): one warp per row, 8 rows per CTA
+__global__ void __launch_bounds__(256)
+softmax_warp_kernel(__nv_bfloat16* __restrict__ s, int64_t rows, int cols, int cols_pad) {
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    __nv_bfloat16* row = s + (size_t)r * cols_pad;
+    const int c8 = cols_pad / 8;
+    float f[8];
+    const bool act = lane < c8;
+    if (act) unpack8(reinterpret_cast<const bf8*>(row)[lane], f);
+    float mx = -INFINITY;
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (lane * 8 + i < cols) mx = fmaxf(mx, f[i]);
+    }
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { f[i] = (lane * 8 + i < cols) ? __expf(f[i] - mx) : 0.f; sum += f[i]; }
+    }
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (act) {
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int i = 0; i < 8; i++) f[i] *= inv;
+        reinterpret_cast<bf8*>(row)[lane] = pack8(f);
+    }
+}
+
+// softmax backward in place on dP -> dS:  dS = P * (dP - sum(dP*P))      (VAE mid attention)
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ dp, int cols_pad) {
+    __shared__ float red[8];
+    const __nv_bfloat16* pr = p + (size_t)blockIdx.x * cols_pad;
+    __nv_bfloat16* dr = dp + (size_t)blockIdx.x * cols_pad;
+    const int c8 = cols_pad / 8;
+    float dot = 0.f;
+    for (int v = threadIdx.x; v < c8; v += blockDim.x) {
+        float a[8], b[8];
+        unpack8(reinterpret_cast<const bf8*>(pr)[v], a);
+        unpack8(reinterpret_cast<const bf8*>(dr)[v], b);
+#pragma unroll
+        for (int i = 0; i < 8; i++) dot += a[i] * b[i];
+    }
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    dot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) dot += red[w];
+    for (int v = threadIdx.x; v < c8; v += blockDim.x) {
+        float a[8], b[8];
+        unpack8(reinterpret_cast<const bf8*>(pr)[v], a);
+        unpack8(reinterpret_cast<const bf8*>(dr)[v], b);
+#pragma unroll
+        for (int i = 0; i < 8; i++) b[i] = a[i] * (b[i] - dot);
+        reinterpret_cast<bf8*>(dr)[v] = pack8(b);
+    }
+}
+
+// ---------------------------------------------------------------------------- GEGLU: y = a * gelu(b), x = [rows, 2*inner]
+__global__ void __launch_bounds__(256)
+geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t rows, int inner) {
+    const int i8 = inner / 8;
+    const int64_t total = rows * i8;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = v / i8;
+        const int cv = (int)(v % i8);
+        float a[8], b[8];
+        unpack8(reinterpret_cast<const bf8*>(x + r * 2 * inner)[cv], a);
+        unpack8(reinterpret_cast<const bf8*>(x + r * 2 * inner + inner)[cv], b);
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] *= 0.5f * b[i] * (1.0f + erff(b[i] * 0.70710678118654752f));
+        reinterpret_cast<bf8*>(y + r * inner)[cv] = pack8(a);
+    }
+}
+
+// ---------------------------------------------------------------------------- elementwise helpers
+// mode 0: y = silu(x); mode 1: y = x + a; mode 2: dy * silu'(x)
+__global__ void __launch_bounds__(256)
+eltwise_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ y,
+               int64_t n8, int mode) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
+        float f[8], g[8];
+        unpack8(reinterpret_cast<const bf8*>(x)[v], f);
+        if (mode != 0) unpack8(reinterpret_cast<const bf8*>(a)[v], g);
+#pragma unroll
+        for (int i = 0; i < 8; i++) f[i] = mode == 0 ? silu(f[i]) : (mode == 1 ? f[i] + g[i] : g[i] * silu_grad(f[i]));
+        reinterpret_cast<bf8*>(y)[v] = pack8(f);
+    }
+}
+
+// CFG + SDS gradient: grad = w * (eps_u + s (eps_c - eps_u) - noise)      (basic.py:595-603,642)
+__global__ void __launch_bounds__(256)
+sds_grad_kernel(const float* __restrict__ eps_uncond, const float* __restrict__ eps_cond, const float* __restrict__ noise,
+                float* __restrict__ grad, float* __restrict__ noise_pred, float guidance_scale, float weight, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float np = eps_uncond[i] + guidance_scale * (eps_cond[i] - eps_uncond[i]);
+        if (noise_pred) noise_pred[i] = np;
+        grad[i] = weight * (np - noise[i]);
+    }
+}
+
+static inline unsigned grid_for(int64_t work, int threads) {
+    const int64_t g = (work + threads - 1) / threads;
+    return (unsigned)(g < 8 * kNumSMs ? (g > 0 ? g : 1) : 8 * kNumSMs);
+}
+
+}  // namespace nn
+}  // namespace dwg
+
+using namespace dwg;
+using namespace dwg::nn;
+typedef __nv_bfloat16 bf16;
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
+                                 int N, int HW, int C, int G, float eps, int do_silu, void* stream) {
+    DWG_REQUIRE(x && gamma && beta && y && stats, "null pointer");
+    DWG_REQUIRE(C % 8 == 0 && C % G == 0 && al16(x) && al16(y), "C must be a multiple of 8 and of G; 16-byte aligned tensors");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, st);
+    int rows_per_cta = (int)((int64_t)8192 * 8 / C);           // ~64K elements per CTA
+    if (rows_per_cta < 1) rows_per_cta = 1;
+    dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
+    gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * G, st>>>((const bf16*)x, stats, HW, C, G, rows_per_cta);
+    const int64_t total = (int64_t)N * HW * (C / 8);
+    gn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G, eps, do_silu, total);
+    return check_launch("dwg_groupnorm_fwd");
+}
+
+extern "C" int dwg_groupnorm_bwd(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta,
+                                 const void* dx_add, void* dx, float* bstats, int N, int HW, int C, int G, float eps,
+                                 int do_silu, void* stream) {
+    DWG_REQUIRE(x && dy && stats && gamma && beta && dx && bstats, "null pointer");
+    DWG_REQUIRE(C % 8 == 0 && C % G == 0, "C must be a multiple of 8 and of G");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * N * G, st);
+    int rows_per_cta = (int)((int64_t)4096 * 8 / C);
+    if (rows_per_cta < 1) rows_per_cta = 1;
+    dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
+    gn_bwd_stats_kernel<<<grid, 256, sizeof(float) * 2 * G, st>>>((const bf16*)x, (const bf16*)dy, stats, gamma, beta, bstats, HW, C, G, eps, do_silu, rows_per_cta);
+    const int64_t total = (int64_t)N * HW * (C / 8);
+    gn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, stats, bstats, gamma, beta, (const bf16*)dx_add,
+                                                              (bf16*)dx, HW, C, G, eps, do_silu, total);
+    return check_launch("dwg_groupnorm_bwd");
+}
+
+extern "C" int dwg_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps, void* stream) {
+    DWG_REQUIRE(x && gamma && beta && y && C % 8 == 0, "bad arguments");
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y, rows, C, eps);
+    return check_launch("dwg_layernorm_fwd");
+}
+
+extern "C" int dwg_softmax_rows(void* s, int64_t rows, int cols, int cols_pad, void* stream) {
+    DWG_REQUIRE(s && cols > 0 && cols_pad >= cols && cols_pad % 8 == 0 && rows < (1ll << 31), "bad arguments");
+    if (cols_pad <= 256)
+        softmax_warp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((bf16*)s, rows, cols, cols_pad);
+    else
+        softmax_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((bf16*)s, cols, cols_pad);
+    return check_launch("dwg_softmax_rows");
+}
+
+extern "C" int dwg_softmax_rows_bwd(const void* p, void* dp, int64_t rows, int cols_pad, void* stream) {
+    DWG_REQUIRE(p && dp && cols_pad % 8 == 0 && rows < (1ll << 31), "bad arguments");
+    softmax_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)p, (bf16*)dp, cols_pad);
+    return check_launch("dwg_softmax_rows_bwd");
+}
+
+extern "C" int dwg_geglu(const void* x, void* y, int64_t rows, int inner, void* stream) {
+    DWG_REQUIRE(x && y && inner % 8 == 0, "bad arguments");
+    geglu_kernel<<<grid_for(rows * (inner / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rows, inner);
+    return check_launch("dwg_geglu");
+}
+
+extern "C" int dwg_eltwise_bf16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream) {
+    DWG_REQUIRE(x && y && n % 8 == 0 && mode >= 0 && mode <= 2 && (mode == 0 || a), "bad arguments");
+    eltwise_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)a, (bf16*)y, n / 8, mode);
+    return check_launch("dwg_eltwise_bf16");
+}
+
+extern "C" int dwg_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float* grad, float* noise_pred,
+                            float guidance_scale, float weight, int64_t n, void* stream) {
+    DWG_REQUIRE(eps_uncond && eps_cond && noise && grad, "null pointer");
+    sds_grad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(eps_uncond, eps_cond, noise, grad, noise_pred, guidance_scale, weight, n);
+    return check_launch("dwg_sds_grad");
+}

@@ -51,6 +51,14 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_float, c_int, c_void_p]),
     'dwg_conv2d_nhwc_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 11 +
                              [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'dwg_groupnorm_fwd': (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    'dwg_groupnorm_bwd': (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    'dwg_layernorm_fwd': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),
+    'dwg_softmax_rows': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p]),
+    'dwg_softmax_rows_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'dwg_geglu': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'dwg_eltwise_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'dwg_sds_grad': (c_int, [c_void_p] * 5 + [c_float, c_float, c_int64, c_void_p]),
     'dwg_raster_view': (c_void_p, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int]),
 }
 
@@ -66,8 +74,39 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        _lib = L
+        _lib = _Counting(L)
     return _lib
+
+
+# kernels launched by one call of each entry point (memsets not counted)
+KERNELS_PER_CALL = {
+    'dwg_lbs_skin_fwd': 1, 'dwg_lbs_skin_bwd': 1, 'dwg_sh_eval_fwd': 1, 'dwg_sh_eval_bwd': 1,
+    'dwg_grid_encode_fwd': 1, 'dwg_grid_encode_bwd': 1, 'dwg_raster_forward': 12, 'dwg_raster_backward': 2,
+    'dwg_gemm_bf16': 1, 'dwg_conv2d_nhwc_bf16': 1, 'dwg_groupnorm_fwd': 2, 'dwg_groupnorm_bwd': 2,
+    'dwg_layernorm_fwd': 1, 'dwg_softmax_rows': 1, 'dwg_softmax_rows_bwd': 1, 'dwg_geglu': 1,
+    'dwg_eltwise_bf16': 1, 'dwg_sds_grad': 1,
+}
+
+
+class _Counting:
+    """Thin proxy over the CDLL that counts kernel launches issued through the C ABI (bench.py's
+    ``gpu_launches``)."""
+
+    def __init__(self, cdll):
+        object.__setattr__(self, '_cdll', cdll)
+        object.__setattr__(self, 'launches', 0)
+        object.__setattr__(self, 'flops', 0.0)
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        k = KERNELS_PER_CALL.get(name, 0)
+        if k == 0:
+            return fn
+
+        def wrapped(*a):
+            object.__setattr__(self, 'launches', self.launches + k)
+            return fn(*a)
+        return wrapped
 
 
 def check(rc, what=''):

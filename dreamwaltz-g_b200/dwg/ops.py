@@ -256,6 +256,22 @@ def rasterize(means3D, means2D, colors, opacities, scales, rotations, *, image_h
 
 # ------------------------------------------------------------------------------ tensor-core GEMM / conv
 ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2}
+PROFILE = None        # set to a list to record (start_event, end_event, flops, kind) per tensor-core launch
+
+
+class _prof:
+    def __init__(self, flops, kind):
+        self.flops, self.kind = flops, kind
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.e0, self.e1, self.flops, self.kind))
 
 
 def _chk_bf16(t):
@@ -290,13 +306,14 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
         assert r4.stride(-1) == 1
     bias = None if bias is None else f32c(bias)
     bias2 = None if bias2 is None else f32c(bias2)
-    check(lib().dwg_gemm_bf16(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
-                              b4.data_ptr(), b4.stride(2), b4.stride(1), b4.stride(0),
-                              c4.data_ptr(), c4.stride(2), c4.stride(1), c4.stride(0), int(c4.dtype == torch.bfloat16),
-                              M, N, K, nb1, nb2, ptr(bias), ptr(bias2), int(bias2_rows_per),
-                              None if r4 is None else r4.data_ptr(), 0 if r4 is None else r4.stride(2),
-                              0 if r4 is None else r4.stride(1), 0 if r4 is None else r4.stride(0),
-                              float(alpha), ACT[act], stream()), 'dwg_gemm_bf16')
+    with _prof(2.0 * M * N * K * nb1 * nb2, 'gemm'):
+        check(lib().dwg_gemm_bf16(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
+                                  b4.data_ptr(), b4.stride(2), b4.stride(1), b4.stride(0),
+                                  c4.data_ptr(), c4.stride(2), c4.stride(1), c4.stride(0), int(c4.dtype == torch.bfloat16),
+                                  M, N, K, nb1, nb2, ptr(bias), ptr(bias2), int(bias2_rows_per),
+                                  None if r4 is None else r4.data_ptr(), 0 if r4 is None else r4.stride(2),
+                                  0 if r4 is None else r4.stride(1), 0 if r4 is None else r4.stride(0),
+                                  float(alpha), ACT[act], stream()), 'dwg_gemm_bf16')
     return out
 
 
@@ -320,7 +337,92 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
         assert residual.shape == y.shape and residual.is_contiguous()
     bias = None if bias is None else f32c(bias)
     bias2 = None if bias2 is None else f32c(bias2)
-    check(lib().dwg_conv2d_nhwc_bf16(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.bfloat16), Nimg, H, W, Cin, Cout, k,
-                                     stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], stream()),
-          'dwg_conv2d_nhwc_bf16')
+    with _prof(2.0 * Nimg * Ho * Wo * Cout * Cin * k * k, 'conv'):
+        check(lib().dwg_conv2d_nhwc_bf16(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.bfloat16), Nimg, H, W, Cin, Cout, k,
+                                         stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], stream()),
+              'dwg_conv2d_nhwc_bf16')
     return y
+
+
+# ------------------------------------------------------------------------------ norm / activation kernels (bf16 NHWC)
+def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, return_stats=False):
+    """x [N, ..., C] bf16 channels-last -> [SiLU](GroupNorm(x)) (dwg_groupnorm_fwd)."""
+    _chk_bf16(x)
+    assert x.is_contiguous()
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    y = torch.empty_like(x)
+    stats = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
+    check(lib().dwg_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), N, HW, C, groups, float(eps), int(silu),
+                                  stream()), 'dwg_groupnorm_fwd')
+    return (y, stats) if return_stats else y
+
+
+def group_norm_bwd(x, dy, stats, gamma, beta, groups=32, eps=1e-5, silu=False, dx_add=None):
+    _chk_bf16(x), _chk_bf16(dy)
+    assert x.is_contiguous() and dy.is_contiguous()
+    N, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (N * C)
+    dx = torch.empty_like(x)
+    bstats = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
+    check(lib().dwg_groupnorm_bwd(ptr(x), ptr(dy), ptr(stats), ptr(gamma), ptr(beta), ptr(dx_add), ptr(dx), ptr(bstats), N, HW, C,
+                                  groups, float(eps), int(silu), stream()), 'dwg_groupnorm_bwd')
+    return dx
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    _chk_bf16(x)
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    check(lib().dwg_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), x.numel() // C, C, float(eps), stream()), 'dwg_layernorm_fwd')
+    return y
+
+
+def softmax_rows_(s, cols):
+    """In-place softmax over the last dim of bf16 scores [..., cols_pad]; columns >= cols become 0."""
+    _chk_bf16(s)
+    assert s.is_contiguous()
+    cp = s.shape[-1]
+    check(lib().dwg_softmax_rows(ptr(s), s.numel() // cp, int(cols), cp, stream()), 'dwg_softmax_rows')
+    return s
+
+
+def softmax_rows_bwd_(p, dp):
+    _chk_bf16(p), _chk_bf16(dp)
+    assert p.is_contiguous() and dp.is_contiguous()
+    cp = p.shape[-1]
+    check(lib().dwg_softmax_rows_bwd(ptr(p), ptr(dp), p.numel() // cp, cp, stream()), 'dwg_softmax_rows_bwd')
+    return dp
+
+
+def geglu(x):
+    _chk_bf16(x)
+    assert x.is_contiguous()
+    inner = x.shape[-1] // 2
+    y = torch.empty(x.shape[:-1] + (inner,), device=x.device, dtype=torch.bfloat16)
+    check(lib().dwg_geglu(ptr(x), ptr(y), x.numel() // x.shape[-1], inner, stream()), 'dwg_geglu')
+    return y
+
+
+def silu(x):
+    _chk_bf16(x)
+    y = torch.empty_like(x)
+    check(lib().dwg_eltwise_bf16(ptr(x.contiguous()), None, ptr(y), x.numel(), 0, stream()), 'dwg_eltwise_bf16')
+    return y
+
+
+def add(x, a):
+    _chk_bf16(x), _chk_bf16(a)
+    y = torch.empty_like(x)
+    check(lib().dwg_eltwise_bf16(ptr(x.contiguous()), ptr(a.contiguous()), ptr(y), x.numel(), 1, stream()), 'dwg_eltwise_bf16')
+    return y
+
+
+def sds_grad(eps_uncond, eps_cond, noise, guidance_scale, weight=1.0):
+    """(grad, noise_pred) of basic.py:595-603,642 in fp32."""
+    eu, ec, nz = f32c(eps_uncond), f32c(eps_cond), f32c(noise)
+    grad, npred = torch.empty_like(nz), torch.empty_like(nz)
+    check(lib().dwg_sds_grad(ptr(eu), ptr(ec), ptr(nz), ptr(grad), ptr(npred), float(guidance_scale), float(weight), nz.numel(),
+                             stream()), 'dwg_sds_grad')
+    return grad, npred

@@ -169,6 +169,31 @@ int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int out_bf16,
                          const float* bias, const float* bias2_per_image,
                          const void* residual, int act, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * R14/R15  Normalisation / activation / softmax kernels of the diffusion blocks (NHWC bf16).
+ * Replace torch.nn.GroupNorm / LayerNorm / softmax / GEGLU / SiLU calls inside the diffusers
+ * modules, and the CFG + SDS-gradient arithmetic of core/guidance/basic.py:595-603,642.
+ */
+/* y = [SiLU](GroupNorm_G(x));  x,y [N,HW,C] bf16; stats [N,G,2] fp32 workspace (sum, sumsq), kept for bwd */
+int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
+                      int N, int HW, int C, int G, float eps, int do_silu, void* stream);
+/* dx = d/dx [SiLU](GroupNorm(x)) . dy  (+ dx_add if given);  bstats [N,G,2] fp32 workspace */
+int dwg_groupnorm_bwd(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta,
+                      const void* dx_add, void* dx, float* bstats, int N, int HW, int C, int G, float eps,
+                      int do_silu, void* stream);
+int dwg_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps, void* stream);
+/* in-place row softmax of bf16 scores [rows, cols_pad] (columns >= cols are written as 0) */
+int dwg_softmax_rows(void* s, int64_t rows, int cols, int cols_pad, void* stream);
+/* in place: dP -> dS = P * (dP - sum(dP * P)) */
+int dwg_softmax_rows_bwd(const void* p, void* dp, int64_t rows, int cols_pad, void* stream);
+/* y[rows, inner] = x[:, :inner] * gelu(x[:, inner:]) */
+int dwg_geglu(const void* x, void* y, int64_t rows, int inner, void* stream);
+/* mode 0: y = silu(x); 1: y = x + a; 2: y = a * silu'(x)   (n bf16 elements, n % 8 == 0) */
+int dwg_eltwise_bf16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream);
+/* noise_pred = eps_u + s (eps_c - eps_u);  grad = weight * (noise_pred - noise)   (fp32) */
+int dwg_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float* grad, float* noise_pred,
+                 float guidance_scale, float weight, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

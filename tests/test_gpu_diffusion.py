@@ -1,0 +1,126 @@
+"""GPU: the diffusion blocks (UNet, ControlNet, VAE encoder fwd + input-gradient bwd, SDS algebra)
+on dwg kernels against the fp32 CPU oracle, on a reduced-width model with the full topology
+(tests run in seconds; bench.py runs the SD1.5 sizes).  bf16 tensor-core arithmetic vs an fp32
+oracle: stated tolerance rel-L2 <= 2e-2 on eps / latents, <= 5e-2 on the VAE input gradient."""
+import numpy as np
+import pytest
+import torch
+
+from dwg import ops
+from dwg.diffusion import guidance as G, model as M, weights as W
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def rel_l2(got, ref):
+    return float((got.float().cpu() - ref).norm() / (ref.norm() + 1e-12))
+
+
+def test_norm_kernels_vs_torch():
+    torch.manual_seed(0)
+    x = torch.randn(2, 16, 16, 320, device=DEV).bfloat16()
+    g, b = torch.rand(320, device=DEV) + 0.5, torch.randn(320, device=DEV) * 0.1
+    ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, g, b, 1e-5)
+    y = ops.group_norm(x, g, b, 32, 1e-5, silu=False)
+    assert rel_l2(y.permute(0, 3, 1, 2), ref.cpu()) < 1e-2
+    y2 = ops.group_norm(x, g, b, 32, 1e-5, silu=True)
+    assert rel_l2(y2.permute(0, 3, 1, 2), torch.nn.functional.silu(ref).cpu()) < 1e-2
+    # backward
+    xr = x.float().requires_grad_(True)
+    out = torch.nn.functional.silu(torch.nn.functional.group_norm(xr.permute(0, 3, 1, 2), 32, g, b, 1e-5)).permute(0, 2, 3, 1)
+    dy = torch.randn_like(out).bfloat16()
+    out.backward(dy.float())
+    _, st = ops.group_norm(x, g, b, 32, 1e-5, silu=True, return_stats=True)
+    dx = ops.group_norm_bwd(x, dy, st, g, b, 32, 1e-5, True)
+    assert rel_l2(dx, xr.grad.cpu()) < 2e-2
+    # layernorm / softmax / geglu
+    t = torch.randn(50, 640, device=DEV).bfloat16()
+    assert rel_l2(ops.layer_norm(t, g.repeat(2), b.repeat(2)), torch.nn.functional.layer_norm(t.float(), (640,), g.repeat(2), b.repeat(2)).cpu()) < 1e-2
+    for cols, pad in ((77, 80), (4096, 4096), (300, 304)):
+        s = torch.randn(33, pad, device=DEV).bfloat16()
+        ref = torch.softmax(s.float()[:, :cols], -1)
+        ops.softmax_rows_(s, cols)
+        assert rel_l2(s[:, :cols], ref.cpu()) < 1e-2 and float(s[:, cols:].abs().sum()) == 0
+    gg = torch.randn(64, 2560, device=DEV).bfloat16()
+    a, bb = gg.float().chunk(2, -1)
+    assert rel_l2(ops.geglu(gg), (a * torch.nn.functional.gelu(bb)).cpu()) < 1e-2
+
+
+def _tiny():
+    cfg = W.TINY
+    return cfg, W.make_unet(cfg), W.make_controlnet(cfg), W.make_vae_encoder(W.TINY_VAE)
+
+
+def test_unet_and_controlnet_match_oracle():
+    from oracle import diffusion as od
+    cfg, u_sd, c_sd, _ = _tiny()
+    torch.manual_seed(1)
+    x = torch.randn(2, 4, 16, 16)
+    t = torch.tensor([487])
+    ctx = torch.randn(2, 77, cfg['ctx_dim'])
+    cond = torch.rand(2, 3, 128, 128)
+    with torch.no_grad():
+        down_r, mid_r = od.controlnet_forward(c_sd, cfg, x, t, ctx, cond)
+        eps_r = od.unet_forward(u_sd, cfg, x, t, ctx, down_r, mid_r)
+        eps_plain = od.unet_forward(u_sd, cfg, x, t, ctx)
+    cn, un = M.ControlNet(c_sd, cfg, DEV), M.UNet(u_sd, cfg, DEV)
+    down, mid = cn.forward(x.to(DEV), t.to(DEV), ctx.to(DEV), cond.to(DEV))
+    for i, (d, r) in enumerate(zip(down, down_r)):
+        assert rel_l2(d.permute(0, 3, 1, 2), r) < 2e-2, i
+    assert rel_l2(mid.permute(0, 3, 1, 2), mid_r) < 2e-2
+    eps = un.forward(x.to(DEV), t.to(DEV), ctx.to(DEV), down, mid)
+    assert eps.shape == eps_r.shape and rel_l2(eps, eps_r) < 2e-2
+    assert rel_l2(un.forward(x.to(DEV), t.to(DEV), ctx.to(DEV)), eps_plain) < 2e-2
+
+
+def test_vae_encode_forward_and_input_gradient_match_oracle():
+    from oracle import diffusion as od
+    _, _, _, v_sd = _tiny()
+    vcfg = W.TINY_VAE
+    torch.manual_seed(2)
+    img = torch.rand(1, 3, 64, 64)
+    eps = torch.randn(1, 4, 8, 8)
+    img_r = img.clone().requires_grad_(True)
+    lat_r = od.vae_encode_latents(v_sd, vcfg, img_r, eps)
+    gl = torch.randn_like(lat_r)
+    (lat_r * gl).sum().backward()
+    enc = M.VAEEncoder(v_sd, vcfg, DEV)
+    img_g = img.to(DEV).requires_grad_(True)
+    lat = M.vae_encode(enc, img_g, eps.to(DEV))
+    assert rel_l2(lat, lat_r.detach()) < 2e-2
+    (lat * gl.to(DEV)).sum().backward()
+    assert rel_l2(img_g.grad, img_r.grad) < 5e-2
+
+
+def test_sds_step_matches_oracle_and_specify_gradient():
+    from oracle import diffusion as od
+    cfg, u_sd, c_sd, v_sd = _tiny()
+    torch.manual_seed(3)
+    g = G.ControlNetScoreDistillation(u_sd, c_sd, v_sd, cfg, W.TINY_VAE, DEV, guidance_scale=7.5)
+    img = torch.rand(1, 3, 128, 128)
+    cond = torch.rand(1, 3, 128, 128)
+    emb = {'neg': torch.randn(1, 77, cfg['ctx_dim']), 'text': torch.randn(1, 77, cfg['ctx_dim'])}
+    t = torch.tensor([600])
+    noise, veps = torch.randn(1, 4, 16, 16), torch.randn(1, 4, 16, 16)
+    img_g = img.to(DEV).requires_grad_(True)
+    out = g(img_g, {k: v.to(DEV) for k, v in emb.items()}, cond_inputs=cond.to(DEV), timestep=t.to(DEV), noise=noise.to(DEV),
+            vae_eps=veps.to(DEV))
+    # oracle
+    img_r = img.clone().requires_grad_(True)
+    lat_r = od.vae_encode_latents(v_sd, W.TINY_VAE, img_r, veps)
+    with torch.no_grad():
+        ln = od.add_noise(lat_r.detach(), noise, t)
+        grad_r, np_r = od.sds_gradient(u_sd, c_sd, cfg, ln, noise, t, emb['neg'], emb['text'], cond, guidance_scale=7.5)
+    assert rel_l2(out['latents'], lat_r.detach()) < 2e-2
+    assert rel_l2(out['noise_pred'], np_r) < 3e-2
+    assert rel_l2(out['gradients'], grad_r) < 3e-2
+    assert out['diffusion_loss'].shape == (1,) and float(out['diffusion_loss']) == 1.0
+    out['diffusion_loss'].backward()
+    (lat_r * grad_r).sum().backward()
+    assert rel_l2(img_g.grad, img_r.grad) < 8e-2
+    # CFG/SDS algebra alone (fp32 kernel): exact formula
+    eu, ec, nz = torch.randn(3, 1, 4, 8, 8, device=DEV)
+    gr, npd = ops.sds_grad(eu, ec, nz, 50.0, 1.0)
+    torch.testing.assert_close(npd, eu + 50.0 * (ec - eu), rtol=1e-6, atol=1e-5)
+    torch.testing.assert_close(gr, npd - nz, rtol=1e-6, atol=1e-5)
