@@ -55,7 +55,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, 
 #pragma unroll
             for (int i = 0; i < 8; i++) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
         }
-        if (cpg >= 8) {
+        if (cpg % 8 == 0) {
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; i++) { a += s[i]; b += ss[i]; }
