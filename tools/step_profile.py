@@ -68,6 +68,12 @@ def main():
     for kind, (ms, fl, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
         print(f'{kind:44s} n={n:3d} ms={ms:8.3f} ({100 * ms / tot:4.1f}%) TFLOPs={fl / (ms * 1e-3) / 1e12:7.1f}')
     print(f'total tensor-core ms {tot:.3f}, flops {sum(v[1] for v in agg.values()) / 1e12:.3f} T')
+    # ---- every kernel by CUDA time (CUPTI), one more step
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as pr:
+        sc.step(pose_dev, data, sc.d_embeds, sc.d_cond)
+        torch.cuda.synchronize()
+    print(pr.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=70))
 
 
 if __name__ == '__main__':
