@@ -59,6 +59,8 @@ SIGNATURES = {
     'dwg_geglu': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'dwg_eltwise_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'dwg_sds_grad': (c_int, [c_void_p] * 5 + [c_float, c_float, c_int64, c_void_p]),
+    'dwg_attention_fwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_float, c_void_p]),
     'dwg_raster_view': (c_void_p, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int]),
 }
 
@@ -84,7 +86,7 @@ KERNELS_PER_CALL = {
     'dwg_grid_encode_fwd': 1, 'dwg_grid_encode_bwd': 1, 'dwg_raster_forward': 12, 'dwg_raster_backward': 2,
     'dwg_gemm_bf16': 1, 'dwg_conv2d_nhwc_bf16': 1, 'dwg_groupnorm_fwd': 2, 'dwg_groupnorm_bwd': 2,
     'dwg_layernorm_fwd': 1, 'dwg_softmax_rows': 1, 'dwg_softmax_rows_bwd': 1, 'dwg_geglu': 1,
-    'dwg_eltwise_bf16': 1, 'dwg_sds_grad': 1,
+    'dwg_eltwise_bf16': 1, 'dwg_sds_grad': 1, 'dwg_attention_fwd': 1,
 }
 
 

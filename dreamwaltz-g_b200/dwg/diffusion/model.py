@@ -89,18 +89,22 @@ def attention(W, p, x, ctx, heads, residual):
     Tk = ctx.shape[1]
     hd = C // heads
     Tkp = (Tk + 7) // 8 * 8
-    q = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_q'], bias=W.b.get(p + '.to_q')).view(B, T, heads, hd).permute(0, 2, 1, 3)
-    k = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, heads, hd).permute(0, 2, 1, 3)
+    q3 = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_q'], bias=W.b.get(p + '.to_q')).view(B, T, C)
+    k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
     vT = torch.zeros(B, C, Tkp, device=x.device, dtype=BF) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=BF)
     for b in range(B):
         ops.gemm(W.w[p + '.to_v'], ctx[b], out=vT[b][:, :Tk] if Tkp != Tk else vT[b])
     if (p + '.to_v') in W.b:
         vT += W.b[p + '.to_v'].to(BF)[None, :, None]
-    S = torch.empty(B, heads, T, Tkp, device=x.device, dtype=BF)
-    ops.gemm(q, k, alpha=hd ** -0.5, out=S[..., :Tk] if Tkp != Tk else S)
-    ops.softmax_rows_(S, Tk)
-    o = torch.empty(B, T, C, device=x.device, dtype=BF)
-    ops.gemm(S, vT.view(B, heads, hd, Tkp), out=o.view(B, T, heads, hd).permute(0, 2, 1, 3))
+    if hd <= 128:
+        o = ops.attention(q3, k3, vT, heads, Tk)                       # fused: scores never reach HBM
+    else:
+        q, k = q3.view(B, T, heads, hd).permute(0, 2, 1, 3), k3.view(B, Tk, heads, hd).permute(0, 2, 1, 3)
+        S = torch.empty(B, heads, T, Tkp, device=x.device, dtype=BF)
+        ops.gemm(q, k, alpha=hd ** -0.5, out=S[..., :Tk] if Tkp != Tk else S)
+        ops.softmax_rows_(S, Tk)
+        o = torch.empty(B, T, C, device=x.device, dtype=BF)
+        ops.gemm(S, vT.view(B, heads, hd, Tkp), out=o.view(B, T, heads, hd).permute(0, 2, 1, 3))
     return linear(W, p + '.to_out.0', o.reshape(B * T, C), residual=residual.reshape(B * T, C)).view(B, T, C)
 
 

@@ -426,3 +426,19 @@ def sds_grad(eps_uncond, eps_cond, noise, guidance_scale, weight=1.0):
     check(lib().dwg_sds_grad(ptr(eu), ptr(ec), ptr(nz), ptr(grad), ptr(npred), float(guidance_scale), float(weight), nz.numel(),
                              stream()), 'dwg_sds_grad')
     return grad, npred
+
+
+def attention(q, k, vt, heads, Tk, scale=None):
+    """Fused attention forward (dwg_attention_fwd).  q [B,T,C], k [B,Tk,C] bf16 (last dim contiguous),
+    vt [B,C,Tkp] = V transposed.  Returns [B,T,C] bf16."""
+    _chk_bf16(q), _chk_bf16(k), _chk_bf16(vt)
+    B, T, C = q.shape
+    hd = C // heads
+    assert q.stride(2) == 1 and k.stride(2) == 1 and vt.is_contiguous() and q.stride(0) == T * q.stride(1) and k.stride(0) == Tk * k.stride(1)
+    out = torch.empty(B, T, C, device=q.device, dtype=torch.bfloat16)
+    scale = hd ** -0.5 if scale is None else scale
+    fl = 4.0 * B * heads * T * Tk * hd
+    with _prof(fl, f'attention B{B} h{heads} T{T} Tk{Tk} d{hd}'):
+        check(lib().dwg_attention_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), k.stride(1), ptr(vt), vt.shape[2], ptr(out), B, heads, T, Tk,
+                                      hd, float(scale), stream()), 'dwg_attention_fwd')
+    return out

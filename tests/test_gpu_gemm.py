@@ -88,3 +88,20 @@ def test_conv2d_asymmetric_padding_downsample():
     ref = F.conv2d(xp, w.float().permute(0, 3, 1, 2), None, stride=2, padding=0).permute(0, 2, 3, 1)
     y = ops.conv2d_nhwc(x, w, stride=2, padding=(0, 0), out_hw=(H // 2, W // 2), out_dtype=torch.float32)
     assert _rel(y, ref) < 2e-3
+
+
+@pytest.mark.parametrize('B,heads,T,Tk,hd', [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80),
+                                            (1, 4, 256, 200, 64), (2, 8, 256, 256, 8), (1, 2, 100, 300, 128), (2, 8, 64, 77, 32)])
+def test_fused_attention_vs_sdpa(B, heads, T, Tk, hd):
+    torch.manual_seed(5)
+    C = heads * hd
+    q = torch.randn(B, T, C, device=DEV).bfloat16()
+    k = torch.randn(B, Tk, C, device=DEV).bfloat16()
+    v = torch.randn(B, Tk, C, device=DEV).bfloat16()
+    Tkp = (Tk + 7) // 8 * 8
+    vt = torch.zeros(B, C, Tkp, device=DEV, dtype=torch.bfloat16)
+    vt[:, :, :Tk] = v.transpose(1, 2)
+    out = ops.attention(q, k, vt, heads, Tk)
+    sp = lambda t: t.float().view(B, -1, heads, hd).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B, T, C)
+    assert _rel(out, ref) < 2e-2
