@@ -56,6 +56,9 @@ struct Params {
     int64_t ldr, r_b1, r_b2;
     float alpha;                    // scale applied to the accumulator before bias
     int act;
+    // persistent tile scheduler
+    int m_tiles, n_tiles, nz, ksplit, total_tiles;
+    float* workspace;               // [nz][M][N] fp32 partial sums when ksplit > 1 (zero-initialised)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,6 +67,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -123,22 +129,35 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     return x;
 }
 
+struct TileCoord { int m_tile, n_tile, z, ks; };
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
+    TileCoord c;
+    c.m_tile = t % p.m_tiles; t /= p.m_tiles;          // m fastest: CTAs running together share the B (weight) tile in L2
+    c.n_tile = t % p.n_tiles; t /= p.n_tiles;
+    c.ks = t % p.ksplit; t /= p.ksplit;
+    c.z = t;
+    return c;
+}
+
+// Persistent, warp-specialised: the CTA walks tiles blockIdx.x, +gridDim.x, ...; the smem ring and
+// the two TMEM accumulator stages let the TMA / MMA of tile i+1 overlap the epilogue of tile i.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y, z = blockIdx.z;
-    const int iters = p.taps_h * p.taps_w * p.k_chunks;
+    const int iters_total = p.taps_h * p.taps_w * p.k_chunks;
 
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
@@ -146,11 +165,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -158,132 +177,164 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile origin
-    int a_c1, a_c2, a_c3;            // A coordinates of tap (0,0) (conv) or (m0, b1, b2) (gemm)
-    int b1 = 0, b2 = 0;
-    if (p.conv_mode) {
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int tn = m_tile / (p.tiles_w * p.tiles_h);
-        a_c1 = tw * p.BW * p.stride - p.pad_w;
-        a_c2 = th * p.BH * p.stride - p.pad_h;
-        a_c3 = tn * p.BNI;
-    } else {
-        b1 = z % p.nb1; b2 = z / p.nb1;
-        a_c1 = m_tile * BM; a_c2 = b1; a_c3 = b2;
-    }
+    // k-iteration range of a split
+    auto it_range = [&](int ks, int& it0, int& it1) {
+        it0 = (int)(((int64_t)iters_total * ks) / p.ksplit);
+        it1 = (int)(((int64_t)iters_total * (ks + 1)) / p.ksplit);
+    };
 
     if (warp == 0) {
         if (elect_one()) {
-            for (int it = 0; it < iters; it++) {
-                const int s = it % STAGES;
-                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                mbar_expect_tx(&full[s], p.a_bytes + B_BYTES);
-                const int kc = it % p.k_chunks;
-                const int tap = it / p.k_chunks;
+            uint32_t ring = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(p, t);
+                int a_c1, a_c2, a_c3, b1 = 0, b2 = 0;
                 if (p.conv_mode) {
-                    const int kw = tap % p.taps_w, kh = tap / p.taps_w;
-                    tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1 + kw, a_c2 + kh, a_c3);
-                    tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, n_tile * BN, 0);
+                    const int tw = tc.m_tile % p.tiles_w;
+                    const int th = (tc.m_tile / p.tiles_w) % p.tiles_h;
+                    const int tn = tc.m_tile / (p.tiles_w * p.tiles_h);
+                    a_c1 = tw * p.BW * p.stride - p.pad_w;
+                    a_c2 = th * p.BH * p.stride - p.pad_h;
+                    a_c3 = tn * p.BNI;
                 } else {
-                    tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1, a_c2, a_c3);
-                    tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, n_tile * BN, b1, b2);
+                    b1 = tc.z % p.nb1; b2 = tc.z / p.nb1;
+                    a_c1 = tc.m_tile * BM; a_c2 = b1; a_c3 = b2;
+                }
+                int it0, it1;
+                it_range(tc.ks, it0, it1);
+                for (int it = it0; it < it1; it++, ring++) {
+                    const int s = ring % STAGES;
+                    const uint32_t ph = (ring / STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full[s], p.a_bytes + B_BYTES);
+                    const int kc = it % p.k_chunks;
+                    const int tap = it / p.k_chunks;
+                    if (p.conv_mode) {
+                        const int kw = tap % p.taps_w, kh = tap / p.taps_w;
+                        tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1 + kw, a_c2 + kh, a_c3);
+                        tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, tc.n_tile * BN, 0);
+                    } else {
+                        tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1, a_c2, a_c3);
+                        tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tc.n_tile * BN, b1, b2);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int it = 0; it < iters; it++) {
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            mbar_wait(&full[s], ph);
+        uint32_t ring = 0, tl = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, tl++) {
+            const TileCoord tc = decode_tile(p, t);
+            int it0, it1;
+            it_range(tc.ks, it0, it1);
+            const uint32_t as = tl & 1u;
+            mbar_wait(&tmem_empty[as], ((tl >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator stage
             tc_fence_after();
-            if (elect_one()) {
-                const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES));
-                const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES));
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int it = it0; it < it1; it++, ring++) {
+                const int s = ring % STAGES;
+                const uint32_t ph = (ring / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES));
+                    const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; k++) {
-                    // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
-                    tc_mma(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; k++)
+                        tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
+                    tc_commit(&empty[s]);
+                    if (it == it1 - 1) tc_commit(&tmem_full[as]);
                 }
-                tc_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
-                if (it == iters - 1) tc_commit(tmem_full);  // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        const int q = warp & 3;
         const int lane = threadIdx.x & 31;
-        const int r = q * 32 + lane;                         // row of the tile owned by this thread
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        // output row address
-        int64_t c_off, r_off = 0;
-        bool row_ok;
-        int64_t b2row = 0;
-        if (p.conv_mode) {
-            const int tw = m_tile % p.tiles_w;
-            const int th = (m_tile / p.tiles_w) % p.tiles_h;
-            const int tn = m_tile / (p.tiles_w * p.tiles_h);
-            const int w = tw * p.BW + (r % p.BW);
-            const int h = th * p.BH + (r / p.BW) % p.BH;
-            const int n = tn * p.BNI + r / (p.BW * p.BH);
-            row_ok = (w < p.Wo) && (h < p.Ho) && ((int64_t)n * p.Ho * p.Wo < (int64_t)p.M);
-            const int64_t pix = ((int64_t)n * p.Ho + h) * p.Wo + w;
-            c_off = pix * p.ldc;
-            r_off = pix * p.ldr;
-            b2row = p.bias2_rows_per > 0 ? pix / p.bias2_rows_per : 0;
-        } else {
-            const int64_t m = (int64_t)m_tile * BM + r;
-            row_ok = m < p.M;
-            c_off = (int64_t)b1 * p.c_b1 + (int64_t)b2 * p.c_b2 + m * p.ldc;
-            r_off = (int64_t)b1 * p.r_b1 + (int64_t)b2 * p.r_b2 + m * p.ldr;
-            b2row = p.bias2_rows_per > 0 ? m / p.bias2_rows_per : 0;
-        }
-        const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tc_ld32(taddr_row + (uint32_t)c0, v);
-            const int ncol0 = n_tile * BN + c0;
-            if (!row_ok || ncol0 >= p.N) continue;
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                float x = __uint_as_float(v[j]) * p.alpha;
-                const int n = ncol0 + j;
-                if (n < p.N) {
-                    if (p.bias) x += p.bias[n];
-                    if (p.bias2) x += p.bias2[b2row * p.N + n];
-                    x = apply_act(x, p.act);
-                    if (p.residual) x += __bfloat162float(p.residual[r_off + n]);
-                }
-                f[j] = x;
+        const int r = q * 32 + lane;
+        uint32_t tl = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, tl++) {
+            const TileCoord tc = decode_tile(p, t);
+            const uint32_t as = tl & 1u;
+            mbar_wait(&tmem_full[as], (tl >> 1) & 1u);
+            tc_fence_after();
+            int64_t c_off, r_off = 0, b2row = 0, ws_off = 0;
+            bool row_ok;
+            if (p.conv_mode) {
+                const int tw = tc.m_tile % p.tiles_w;
+                const int th = (tc.m_tile / p.tiles_w) % p.tiles_h;
+                const int tn = tc.m_tile / (p.tiles_w * p.tiles_h);
+                const int w = tw * p.BW + (r % p.BW);
+                const int h = th * p.BH + (r / p.BW) % p.BH;
+                const int n = tn * p.BNI + r / (p.BW * p.BH);
+                row_ok = (w < p.Wo) && (h < p.Ho) && ((int64_t)n * p.Ho * p.Wo < (int64_t)p.M) && (r < p.BW * p.BH * p.BNI);
+                const int64_t pix = ((int64_t)n * p.Ho + h) * p.Wo + w;
+                c_off = pix * p.ldc;
+                r_off = pix * p.ldr;
+                ws_off = pix * p.N;
+                b2row = p.bias2_rows_per > 0 ? pix / p.bias2_rows_per : 0;
+            } else {
+                const int b1 = tc.z % p.nb1, b2 = tc.z / p.nb1;
+                const int64_t m = (int64_t)tc.m_tile * BM + r;
+                row_ok = m < p.M;
+                c_off = (int64_t)b1 * p.c_b1 + (int64_t)b2 * p.c_b2 + m * p.ldc;
+                r_off = (int64_t)b1 * p.r_b1 + (int64_t)b2 * p.r_b2 + m * p.ldr;
+                ws_off = ((int64_t)tc.z * p.M + m) * p.N;
+                b2row = p.bias2_rows_per > 0 ? m / p.bias2_rows_per : 0;
             }
-            const int nvalid = min(32, p.N - ncol0);
-            if (p.out_bf16) {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + ncol0;
-                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            const uint32_t taddr_row = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(taddr_row + (uint32_t)c0, v);
+                if (c0 + 32 >= BN) {                       // last TMEM read of this tile: release the accumulator stage
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[as]);
+                }
+                const int ncol0 = tc.n_tile * BN + c0;
+                if (!row_ok || ncol0 >= p.N) continue;
+                const int nvalid = min(32, p.N - ncol0);
+                if (p.ksplit > 1) {
+                    float* ws = p.workspace + ws_off + ncol0;
+                    for (int j = 0; j < nvalid; j++) atomicAdd(ws + j, __uint_as_float(v[j]));
+                    continue;
+                }
+                float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 pk;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(dst + j) = pk;
+                for (int j = 0; j < 32; j++) {
+                    float x = __uint_as_float(v[j]) * p.alpha;
+                    const int n = ncol0 + j;
+                    if (n < p.N) {
+                        if (p.bias) x += p.bias[n];
+                        if (p.bias2) x += p.bias2[b2row * p.N + n];
+                        x = apply_act(x, p.act);
+                        if (p.residual) x += __bfloat162float(p.residual[r_off + n]);
+                    }
+                    f[j] = x;
+                }
+                if (p.out_bf16) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + ncol0;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(dst + j) = pk;
+                        }
+                    } else {
+                        for (int j = 0; j < nvalid; j++) dst[j] = __float2bfloat16(f[j]);
                     }
                 } else {
-                    for (int j = 0; j < nvalid; j++) dst[j] = __float2bfloat16(f[j]);
-                }
-            } else {
-                float* dst = reinterpret_cast<float*>(p.C) + c_off + ncol0;
-                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    float* dst = reinterpret_cast<float*>(p.C) + c_off + ncol0;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                } else {
-                    for (int j = 0; j < nvalid; j++) dst[j] = f[j];
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+                        for (int j = 0; j < nvalid; j++) dst[j] = f[j];
+                    }
                 }
             }
         }
@@ -292,7 +343,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// split-K finalize: out = act(alpha * ws + bias + bias2) + residual
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(const Params p, int64_t rows_total) {
+    const int64_t total = rows_total * p.N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / p.N;
+        const int n = (int)(i - row * p.N);
+        int64_t c_off, r_off, b2row;
+        if (p.conv_mode) {
+            c_off = row * p.ldc; r_off = row * p.ldr;
+            b2row = p.bias2_rows_per > 0 ? row / p.bias2_rows_per : 0;
+        } else {
+            const int64_t z = row / p.M, m = row - z * p.M;
+            const int b1 = (int)(z % p.nb1), b2 = (int)(z / p.nb1);
+            c_off = (int64_t)b1 * p.c_b1 + (int64_t)b2 * p.c_b2 + m * p.ldc;
+            r_off = (int64_t)b1 * p.r_b1 + (int64_t)b2 * p.r_b2 + m * p.ldr;
+            b2row = p.bias2_rows_per > 0 ? m / p.bias2_rows_per : 0;
+        }
+        float x = p.workspace[i] * p.alpha;
+        if (p.bias) x += p.bias[n];
+        if (p.bias2) x += p.bias2[b2row * p.N + n];
+        x = apply_act(x, p.act);
+        if (p.residual) x += __bfloat162float(p.residual[r_off + n]);
+        if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[c_off + n] = __float2bfloat16(x);
+        else reinterpret_cast<float*>(p.C)[c_off + n] = x;
     }
 }
 
@@ -332,18 +411,62 @@ static int make_map(CUtensorMap* m, const void* base, const uint64_t dims[4], co
     return DWG_OK;
 }
 
-constexpr int BN_ = 128;
-constexpr int STAGES_ = 5;
+static int g_num_sms = 0;
+static float* g_ws = nullptr;            // split-K workspace (grown on demand, never shrunk)
+static size_t g_ws_bytes = 0;
 
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, dim3 grid, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)STAGES_ * (BM * BK * 2 + BN_ * BK * 2) + (2 * STAGES_ + 1) * 8 + 16;
+template <int BN, int STAGES>
+static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, int64_t rows_total, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_kernel<BN_, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    gemm_kernel<BN_, STAGES_><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = kNumSMs;
+    }
+    p.n_tiles = (p.N + BN - 1) / BN;
+    const int iters = p.taps_h * p.taps_w * p.k_chunks;
+    const int64_t base_tiles = (int64_t)p.m_tiles * p.n_tiles * p.nz;
+    // split-K when the tile count cannot fill the machine and the K loop is long
+    int ks = 1;
+    if (base_tiles * 2 <= g_num_sms && iters >= 8) {
+        ks = (int)(g_num_sms / base_tiles);
+        if (ks > iters / 4) ks = iters / 4;
+        if (ks < 1) ks = 1;
+    }
+    p.ksplit = ks;
+    p.total_tiles = (int)(base_tiles * ks);
+    if (ks > 1) {
+        const size_t need = sizeof(float) * (size_t)rows_total * p.N;
+        if (need > g_ws_bytes) {
+            // NOTE: grows outside of stream capture only (warm-up pass sizes it); see DESIGN.md
+            if (g_ws) cudaFree(g_ws);
+            if (cudaMalloc(&g_ws, need) != cudaSuccess) { g_ws = nullptr; g_ws_bytes = 0; set_error("split-K workspace allocation failed"); return DWG_ERR_CUDA; }
+            g_ws_bytes = need;
+        }
+        p.workspace = g_ws;
+        cudaMemsetAsync(g_ws, 0, need, st);
+    }
+    const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+    gemm_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    if (ks > 1) {
+        const int64_t total = rows_total * p.N;
+        int64_t g = (total + 255) / 256;
+        if (g > 4 * g_num_sms) g = 4 * g_num_sms;
+        splitk_finalize_kernel<<<(unsigned)g, 256, 0, st>>>(p, rows_total);
+    }
     return check_launch("tcgen05 gemm");
+}
+
+static int pick_bn(int N) {
+    if (N <= 64) return 64;
+    if (N % 256 == 0 || N >= 1024) return 256;
+    return 128;
 }
 
 }  // namespace gemm
@@ -368,6 +491,7 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     DWG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "A/B must be 16-byte aligned");
     CUtensorMap tmA, tmB;
     const uint32_t ones[4] = {1, 1, 1, 1};
+    const int bn = pick_bn(N);
     {
         const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)nb1, (uint64_t)nb2};
         const uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)(nb1 > 1 ? a_b1 : lda * (int64_t)M) * 2, (uint64_t)(nb2 > 1 ? a_b2 : lda * (int64_t)M) * 2};
@@ -378,7 +502,7 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     {
         const uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)nb1, (uint64_t)nb2};
         const uint64_t str[3] = {(uint64_t)ldb * 2, (uint64_t)(nb1 > 1 ? b_b1 : ldb * (int64_t)N) * 2, (uint64_t)(nb2 > 1 ? b_b2 : ldb * (int64_t)N) * 2};
-        const uint32_t box[4] = {BK, BN_, 1, 1};
+        const uint32_t box[4] = {BK, (uint32_t)bn, 1, 1};
         int rc = make_map(&tmB, B, dims, str, box, ones);
         if (rc) return rc;
     }
@@ -389,8 +513,12 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     p.bias = bias; p.bias2 = bias2; p.bias2_rows_per = bias2_rows_per;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.r_b1 = r_b1; p.r_b2 = r_b2;
     p.alpha = alpha; p.act = act;
-    dim3 grid((M + BM - 1) / BM, (N + BN_ - 1) / BN_, nb1 * nb2);
-    return launch(tmA, tmB, p, grid, (cudaStream_t)stream);
+    p.m_tiles = (M + BM - 1) / BM; p.nz = nb1 * nb2;
+    const int64_t rows_total = (int64_t)M * nb1 * nb2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 64) return launch_t<64, 6>(tmA, tmB, p, rows_total, st);
+    if (bn == 256) return launch_t<256, 4>(tmA, tmB, p, rows_total, st);
+    return launch_t<128, 5>(tmA, tmB, p, rows_total, st);
 }
 
 // NHWC convolution as implicit GEMM.  x [Nimg,H,W,Cin] bf16 (Cin % 8 == 0), w [Cout,kh,kw,Cin] bf16,
@@ -415,6 +543,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     if (BNI > Nimg) BNI = 1 << (31 - __builtin_clz(Nimg));         // largest power of two <= Nimg
     const int tiles_w = (Wo + BW - 1) / BW, tiles_h = (Ho + BH - 1) / BH, tiles_n = (Nimg + BNI - 1) / BNI;
     CUtensorMap tmA, tmB;
+    const int bn = pick_bn(Cout);
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
@@ -427,7 +556,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
         const int taps = ksize * ksize;
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout, 1};
         const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2, (uint64_t)Cout * taps * Cin * 2};
-        const uint32_t box[4] = {BK, 1, BN_, 1};
+        const uint32_t box[4] = {BK, 1, (uint32_t)bn, 1};
         const uint32_t ones[4] = {1, 1, 1, 1};
         int rc = make_map(&tmB, w, dims, str, box, ones);
         if (rc) return rc;
@@ -442,6 +571,10 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
     p.alpha = 1.0f; p.act = act;
     // rows of a tile with n >= Nimg are masked in the epilogue through M
-    dim3 grid(tiles_w * tiles_h * tiles_n, (Cout + BN_ - 1) / BN_, 1);
-    return launch(tmA, tmB, p, grid, (cudaStream_t)stream);
+    p.m_tiles = tiles_w * tiles_h * tiles_n; p.nz = 1;
+    const int64_t rows_total = (int64_t)Nimg * Ho * Wo;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 64) return launch_t<64, 6>(tmA, tmB, p, rows_total, st);
+    if (bn == 256) return launch_t<256, 4>(tmA, tmB, p, rows_total, st);
+    return launch_t<128, 5>(tmA, tmB, p, rows_total, st);
 }

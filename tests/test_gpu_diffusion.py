@@ -30,7 +30,7 @@ def test_norm_kernels_vs_torch():
     # backward
     xr = x.float().requires_grad_(True)
     out = torch.nn.functional.silu(torch.nn.functional.group_norm(xr.permute(0, 3, 1, 2), 32, g, b, 1e-5)).permute(0, 2, 3, 1)
-    dy = torch.randn_like(out).bfloat16()
+    dy = torch.randn(out.shape, device=DEV).bfloat16()
     out.backward(dy.float())
     _, st = ops.group_norm(x, g, b, 32, 1e-5, silu=True, return_stats=True)
     dx = ops.group_norm_bwd(x, dy, st, g, b, 32, 1e-5, True)
