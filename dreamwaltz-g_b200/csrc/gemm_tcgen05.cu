@@ -155,6 +155,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* tmem_full = empty + STAGES;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [BN]
 
     const int warp = threadIdx.x >> 5;
     const int iters_total = p.taps_h * p.taps_w * p.k_chunks;
@@ -252,12 +253,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int q = warp & 3;
         const int lane = threadIdx.x & 31;
         const int r = q * 32 + lane;
+        const int et = threadIdx.x - 128;                   // 0..127 among the epilogue threads
         uint32_t tl = 0;
+        // vector fast path: 16-byte aligned rows for the residual / output
+        const bool res_vec = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && (p.ldr % 8 == 0) &&
+                             (p.r_b1 % 8 == 0) && (p.r_b2 % 8 == 0);
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, tl++) {
             const TileCoord tc = decode_tile(p, t);
             const uint32_t as = tl & 1u;
-            mbar_wait(&tmem_full[as], (tl >> 1) & 1u);
-            tc_fence_after();
             int64_t c_off, r_off = 0, b2row = 0, ws_off = 0;
             bool row_ok;
             if (p.conv_mode) {
@@ -282,8 +285,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 ws_off = ((int64_t)tc.z * p.M + m) * p.N;
                 b2row = p.bias2_rows_per > 0 ? m / p.bias2_rows_per : 0;
             }
+            const int ntile0 = tc.n_tile * BN;
+            // ---- stage the bias slice of this tile in shared memory; prefetch the whole residual
+            // row into registers BEFORE waiting for the accumulator (overlaps the MMA main loop)
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // previous tile's readers are done
+            for (int c = et; c < BN; c += 128) {
+                const int n = ntile0 + c;
+                s_bias[c] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+            }
+            uint4 rr[BN / 8];
+            const bool use_res_vec = res_vec && row_ok && p.ksplit == 1;
+            if (use_res_vec) {
+#pragma unroll
+                for (int i = 0; i < BN / 8; i++) {
+                    const int n = ntile0 + i * 8;
+                    rr[i] = (n + 8 <= p.N) ? *reinterpret_cast<const uint4*>(p.residual + r_off + n) : make_uint4(0, 0, 0, 0);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tmem_full[as], (tl >> 1) & 1u);
+            tc_fence_after();
             const uint32_t taddr_row = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tc_ld32(taddr_row + (uint32_t)c0, v);
@@ -291,7 +314,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[as]);
                 }
-                const int ncol0 = tc.n_tile * BN + c0;
+                const int ncol0 = ntile0 + c0;
                 if (!row_ok || ncol0 >= p.N) continue;
                 const int nvalid = min(32, p.N - ncol0);
                 if (p.ksplit > 1) {
@@ -301,16 +324,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    float x = __uint_as_float(v[j]) * p.alpha;
-                    const int n = ncol0 + j;
-                    if (n < p.N) {
-                        if (p.bias) x += p.bias[n];
-                        if (p.bias2) x += p.bias2[b2row * p.N + n];
-                        x = apply_act(x, p.act);
-                        if (p.residual) x += __bfloat162float(p.residual[r_off + n]);
+                for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) * p.alpha + s_bias[c0 + j];
+                if (p.bias2) {
+                    const float* b2p = p.bias2 + b2row * p.N + ncol0;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(b2p) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(b2p + j));
+                            f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+                        }
+                    } else {
+                        for (int j = 0; j < nvalid; j++) f[j] += b2p[j];
                     }
-                    f[j] = x;
+                }
+                if (p.act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) f[j] = apply_act(f[j], p.act);
+                }
+                if (p.residual) {
+                    if (use_res_vec && nvalid == 32) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint4 u = rr[c0 / 8 + i];
+                            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+                                f[i * 8 + 2 * k] += t2.x; f[i * 8 + 2 * k + 1] += t2.y;
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < nvalid; j++) f[j] += __bfloat162float(p.residual[r_off + ncol0 + j]);
+                    }
                 }
                 if (p.out_bf16) {
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + ncol0;
@@ -417,7 +462,7 @@ static size_t g_ws_bytes = 0;
 
 template <int BN, int STAGES>
 static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, int64_t rows_total, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16;
+    const size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
