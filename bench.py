@@ -106,7 +106,7 @@ class Scene:
         self.guidance = G.ControlNetScoreDistillation(W.make_unet(cfg), W.make_controlnet(cfg), W.make_vae_encoder(vcfg), cfg, vcfg, device,
                                                       seed=1000 + rank)
         self.ctx_dim = cfg['ctx_dim']
-        self.rng = np.random.default_rng(1000 + rank)
+        self.rng = np.random.default_rng(1000 + rank)          # dwg.parallel.rank_seed(1000, rank)
         self.pose_rows = poses()
         g = torch.Generator().manual_seed(7)
         # host-side (pinned) per-step inputs of the e2e arm
@@ -142,7 +142,7 @@ def flat_grads(params):
 
 def run_dwg(args):
     import torch.distributed as dist
-    from dwg import _lib, ops
+    from dwg import _lib, ops, parallel
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -168,8 +168,7 @@ def run_dwg(args):
             embeds, cond = sc.d_embeds, sc.d_cond
         res = sc.step(pose_dev, data, embeds, cond)
         if world > 1:
-            fg = flat_grads(sc.params)
-            dist.all_reduce(fg)                      # ONE NCCL all-reduce of every parameter gradient
+            parallel.allreduce_grads(sc.params)      # ONE NCCL all-reduce of every parameter gradient
         if e2e:
             # device -> host read of the step's result
             return float(res['gradients'].abs().mean()), int(res['timestep'][0])

@@ -89,12 +89,21 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
         }
         mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
         const int cnt = chunk_cnt(c);
-        for (int j = cnt - 1; j >= 0; j--) {
+        for (int j0 = ((cnt - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
+          const int jl = j0 + lane;
+          bool touch = false;
+          if (jl < cnt) {
+              const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][jl]);
+              touch = strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1);
+          }
+          unsigned tmask = __ballot_sync(0xffffffffu, touch);
+          while (tmask) {
+            const int bit = 31 - __clz(tmask);
+            tmask &= ~(1u << bit);
+            const int j = j0 + bit;
             const uint32_t k = (uint32_t)(c * CHUNK + j);
             float v[NG];
             bool contrib = false;
-            const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][j]);
-            if (!strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1)) continue;   // warp-uniform
             if (k < last_contributor) {
                 const Rec rc = s_rec[buf][j];
                 float alpha, G, dx, dy;
@@ -150,6 +159,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
 #pragma unroll
                 for (int q = 0; q < NG; q++) atomicAdd(&s_acc[j][q], v[q]);
             }
+          }
         }
         __syncthreads();            // chunk finished by every warp: flush, and release buffer `buf`
         if ((int)threadIdx.x < cnt) {

@@ -47,6 +47,7 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, A = 0.f;
     uint32_t last = 0;
+    const int lane = threadIdx.x & 31;
     // this warp's pixel strip (16 x 2)
     const float sx0 = (float)(blockIdx.x * TILE), sx1 = sx0 + (float)(TILE - 1);
     const float sy0 = (float)(blockIdx.y * TILE + ((threadIdx.x >> 5) << 1)), sy1 = sy0 + 1.0f;
@@ -70,23 +71,35 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
         // 16x2 strip can be touched; most instances of a tile are rejected here for most warps.
         const bool warp_live = __any_sync(0xffffffffu, !done);
         if (warp_live) {
-            for (int j = 0; j < cnt; j++) {
-                const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][j]);
-                if (!strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1)) continue;
-                if (done) continue;
-                const Rec rc = s_rec[buf][j];
-                float alpha, G, dx, dy;
-                if (!eval_alpha(rc, pxf, pyf, alpha, G, dx, dy)) continue;
-                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                if (test_T < 0.0001f) { done = true; continue; }
-                const float w = __fmul_rn(alpha, T);
-                C0 = __fadd_rn(C0, __fmul_rn(rc.r, w));
-                C1 = __fadd_rn(C1, __fmul_rn(rc.g, w));
-                C2 = __fadd_rn(C2, __fmul_rn(rc.b, w));
-                D = __fadd_rn(D, __fmul_rn(rc.depth, w));
-                A = __fadd_rn(A, w);
-                T = test_T;
-                last = (uint32_t)(c * CHUNK + j + 1);
+            // Warp-cooperative culling: each lane tests ONE instance header against this warp's
+            // 16x2 pixel strip; only the touched instances (ballot bits, ascending order) are
+            // visited by the whole warp.  32x fewer serial iterations for the typical small splat.
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                const int jl = j0 + lane;
+                bool touch = false;
+                if (jl < cnt) {
+                    const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][jl]);
+                    touch = strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1);
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, touch);
+                while (mask) {
+                    const int j = j0 + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (done) continue;
+                    const Rec rc = s_rec[buf][j];
+                    float alpha, G, dx, dy;
+                    if (!eval_alpha(rc, pxf, pyf, alpha, G, dx, dy)) continue;
+                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                    if (test_T < 0.0001f) { done = true; continue; }
+                    const float w = __fmul_rn(alpha, T);
+                    C0 = __fadd_rn(C0, __fmul_rn(rc.r, w));
+                    C1 = __fadd_rn(C1, __fmul_rn(rc.g, w));
+                    C2 = __fadd_rn(C2, __fmul_rn(rc.b, w));
+                    D = __fadd_rn(D, __fmul_rn(rc.depth, w));
+                    A = __fadd_rn(A, w);
+                    T = test_T;
+                    last = (uint32_t)(c * CHUNK + j + 1);
+                }
             }
         }
     }
