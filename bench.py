@@ -148,6 +148,8 @@ def run_dwg(args):
     world = int(os.environ.get('WORLD_SIZE', 1))
     torch.cuda.set_device(local_rank)
     dev = f'cuda:{local_rank}'
+    # the avatar MLPs are still torch nn.Linear: run them on the TF32 tensor-core path
+    torch.backends.cuda.matmul.allow_tf32 = True
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(dev))
     pk, pk_src = peaks()

@@ -303,12 +303,12 @@ using namespace dwg;
 using namespace dwg::attn;
 
 // q [B,T,heads*hd] (row stride q_ld), k [B,Tk,heads*hd] (row stride k_ld), vt [B, heads*hd, Tkp] (V transposed,
-// columns >= Tk must be finite), out [B,T,heads*hd].  All bf16.  hd in {40, 64, 80, 128} (multiple of 8, <= 128).
+// batch stride vt_batch_stride elements, columns >= Tk must be finite), out [B,T,heads*hd].  All bf16.  hd in {40, 64, 80, 128} (multiple of 8, <= 128).
 extern "C" int dwg_attention_fwd(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* vt, int64_t Tkp,
-                                 void* out, int B, int heads, int T, int Tk, int hd, float scale, void* stream) {
+                                 int64_t vt_batch_stride, void* out, int B, int heads, int T, int Tk, int hd, float scale, void* stream) {
     DWG_REQUIRE(q && k && vt && out, "null pointer");
     DWG_REQUIRE(hd % 8 == 0 && hd >= 8 && hd <= 128, "head dim must be a multiple of 8 and <= 128");
-    DWG_REQUIRE(q_ld % 8 == 0 && k_ld % 8 == 0 && Tkp % 8 == 0 && Tkp >= Tk, "strides must be multiples of 8 elements");
+    DWG_REQUIRE(q_ld % 8 == 0 && k_ld % 8 == 0 && Tkp % 8 == 0 && Tkp >= Tk && vt_batch_stride % 8 == 0, "strides must be multiples of 8 elements");
     const int C = heads * hd;
     CUtensorMap tq, tk, tv;
     {
@@ -326,7 +326,7 @@ extern "C" int dwg_attention_fwd(const void* q, int64_t q_ld, const void* k, int
     const int npv = (hd + 15) / 16 * 16;
     {
         const uint64_t d[4] = {(uint64_t)Tkp, (uint64_t)hd, (uint64_t)heads, (uint64_t)B};
-        const uint64_t s[3] = {(uint64_t)Tkp * 2, (uint64_t)hd * Tkp * 2, (uint64_t)C * Tkp * 2};
+        const uint64_t s[3] = {(uint64_t)Tkp * 2, (uint64_t)hd * Tkp * 2, (uint64_t)vt_batch_stride * 2};
         const uint32_t box[4] = {64, (uint32_t)npv, 1, 1};
         int rc = make_map(&tv, vt, d, s, box); if (rc) return rc;
     }

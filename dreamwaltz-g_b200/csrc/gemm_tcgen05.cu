@@ -58,7 +58,8 @@ struct Params {
     int act;
     // persistent tile scheduler
     int m_tiles, n_tiles, nz, ksplit, total_tiles;
-    float* workspace;               // [nz][M][N] fp32 partial sums when ksplit > 1 (zero-initialised)
+    float* workspace;               // [ksplit][rows_total][N] fp32 partial sums when ksplit > 1
+    int64_t ws_slice;               // rows_total * N
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -318,8 +319,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (!row_ok || ncol0 >= p.N) continue;
                 const int nvalid = min(32, p.N - ncol0);
                 if (p.ksplit > 1) {
-                    float* ws = p.workspace + ws_off + ncol0;
-                    for (int j = 0; j < nvalid; j++) atomicAdd(ws + j, __uint_as_float(v[j]));
+                    // partial sums go to their own slice (no atomics, no memset); splitk_finalize adds the slices
+                    float* ws = p.workspace + (int64_t)tc.ks * p.ws_slice + ws_off + ncol0;
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(ws) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(ws + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    } else {
+                        for (int j = 0; j < nvalid; j++) ws[j] = __uint_as_float(v[j]);
+                    }
                     continue;
                 }
                 float f[32];
@@ -410,7 +418,9 @@ splitk_finalize_kernel(const Params p, int64_t rows_total) {
             r_off = (int64_t)b1 * p.r_b1 + (int64_t)b2 * p.r_b2 + m * p.ldr;
             b2row = p.bias2_rows_per > 0 ? m / p.bias2_rows_per : 0;
         }
-        float x = p.workspace[i] * p.alpha;
+        float acc = 0.f;
+        for (int k = 0; k < p.ksplit; k++) acc += p.workspace[(int64_t)k * p.ws_slice + i];
+        float x = acc * p.alpha;
         if (p.bias) x += p.bias[n];
         if (p.bias2) x += p.bias2[b2row * p.N + n];
         x = apply_act(x, p.act);
@@ -487,7 +497,8 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, i
     p.ksplit = ks;
     p.total_tiles = (int)(base_tiles * ks);
     if (ks > 1) {
-        const size_t need = sizeof(float) * (size_t)rows_total * p.N;
+        const size_t need = sizeof(float) * (size_t)rows_total * p.N * ks;
+        p.ws_slice = rows_total * (int64_t)p.N;
         if (need > g_ws_bytes) {
             // NOTE: grows outside of stream capture only (warm-up pass sizes it); see DESIGN.md
             if (g_ws) cudaFree(g_ws);
@@ -495,7 +506,6 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, i
             g_ws_bytes = need;
         }
         p.workspace = g_ws;
-        cudaMemsetAsync(g_ws, 0, need, st);
     }
     const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
     gemm_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(tmA, tmB, p);

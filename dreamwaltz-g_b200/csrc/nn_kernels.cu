@@ -75,29 +75,41 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, 
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(size_t)n * 2 * G + i], s_bins[i]);
 }
 
-// y = (x - mean) * rstd * gamma + beta, optional SiLU
+// y = (x - mean) * rstd * gamma + beta, optional SiLU.  grid (row chunks, N); thread -> (row lane,
+// fixed 8-channel column): scale/shift are computed once per thread, then one 16-byte load, 8 FMAs
+// and one 16-byte store per row.
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int HW, int C, int G, float eps, int do_silu,
-                int64_t total_vec) {
+                int rows_per_cta) {
+    const int n = blockIdx.y;
     const int c8 = C / 8, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(v % c8);
-        const int n = (int)(v / ((int64_t)HW * c8));
-        float f[8];
-        unpack8(reinterpret_cast<const bf8*>(x)[v], f);
+    const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
+    const bf8* xp = reinterpret_cast<const bf8*>(x + (size_t)n * HW * C);
+    bf8* yp = reinterpret_cast<bf8*>(y + (size_t)n * HW * C);
+    const int rp = c8 <= 256 ? 256 / c8 : 1;
+    const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
+    for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
+        float a[8], b[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const int c = cv * 8 + i;
-            const int g = c / cpg;
+            const int c = cv * 8 + i, g = c / cpg;
             const float mean = stats[((size_t)n * G + g) * 2] * inv_cnt;
             const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
-            float o = (f[i] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
-            if (do_silu) o = silu(o);
-            f[i] = o;
+            a[i] = rsqrtf(var + eps) * gamma[c];
+            b[i] = beta[c] - mean * a[i];
         }
-        reinterpret_cast<bf8*>(y)[v] = pack8(f);
+        for (int r = row0 + rl; r < row1; r += rp) {
+            float f[8];
+            unpack8(xp[(size_t)r * c8 + cv], f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float o = fmaf(f[i], a[i], b[i]);
+                f[i] = do_silu ? silu(o) : o;
+            }
+            yp[(size_t)r * c8 + cv] = pack8(f);
+        }
     }
 }
 
@@ -381,12 +393,14 @@ extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float*
     DWG_REQUIRE(C % 8 == 0 && C % G == 0 && al16(x) && al16(y), "C must be a multiple of 8 and of G; 16-byte aligned tensors");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, st);
-    int rows_per_cta = (int)((int64_t)8192 * 8 / C);           // ~64K elements per CTA
+    int rows_per_cta = (int)((int64_t)2048 * 8 / C);           // ~16K elements per CTA
     if (rows_per_cta < 1) rows_per_cta = 1;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
     gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * G, st>>>((const bf16*)x, stats, HW, C, G, rows_per_cta);
-    const int64_t total = (int64_t)N * HW * (C / 8);
-    gn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G, eps, do_silu, total);
+    int rows_apply = (int)((int64_t)2048 * 8 / C);             // ~16K elements per CTA: enough CTAs to fill the machine
+    if (rows_apply < 1) rows_apply = 1;
+    dim3 grid2((HW + rows_apply - 1) / rows_apply, N);
+    gn_apply_kernel<<<grid2, 256, 0, st>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G, eps, do_silu, rows_apply);
     return check_launch("dwg_groupnorm_fwd");
 }
 

@@ -59,7 +59,7 @@ SIGNATURES = {
     'dwg_geglu': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'dwg_eltwise_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'dwg_sds_grad': (c_int, [c_void_p] * 5 + [c_float, c_float, c_int64, c_void_p]),
-    'dwg_attention_fwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
+    'dwg_attention_fwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_void_p]),
     'dwg_raster_view': (c_void_p, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int]),
 }

@@ -81,21 +81,25 @@ def timestep_embedding(t, dim):
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
-def attention(W, p, x, ctx, heads, residual):
+def attention(W, p, x, ctx, heads, residual, kv=None):
     """x [B,T,C] bf16 (queries), ctx [B,Tk,Ck] bf16.  Returns to_out(softmax(QK^T/sqrt(d)) V) + residual.
     V is produced transposed ([B,C,Tk], the K-major operand of the PV matmul) by swapping the
-    operands of its projection GEMM, so no transpose pass exists."""
+    operands of its projection GEMM, so no transpose pass exists.  ``kv`` = precomputed (K, V^T)
+    slices of the batched cross-attention projection (DiffusionNet.project_context)."""
     B, T, C = x.shape
     Tk = ctx.shape[1]
     hd = C // heads
     Tkp = (Tk + 7) // 8 * 8
     q3 = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_q'], bias=W.b.get(p + '.to_q')).view(B, T, C)
-    k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
-    vT = torch.zeros(B, C, Tkp, device=x.device, dtype=BF) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=BF)
-    for b in range(B):
-        ops.gemm(W.w[p + '.to_v'], ctx[b], out=vT[b][:, :Tk] if Tkp != Tk else vT[b])
-    if (p + '.to_v') in W.b:
-        vT += W.b[p + '.to_v'].to(BF)[None, :, None]
+    if kv is not None:
+        k3, vT = kv
+    else:
+        k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
+        vT = torch.zeros(B, C, Tkp, device=x.device, dtype=BF) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=BF)
+        for b in range(B):
+            ops.gemm(W.w[p + '.to_v'], ctx[b], out=vT[b][:, :Tk] if Tkp != Tk else vT[b])
+        if (p + '.to_v') in W.b:
+            vT += W.b[p + '.to_v'].to(BF)[None, :, None]
     if hd <= 128:
         o = ops.attention(q3, k3, vT, heads, Tk)                       # fused: scores never reach HBM
     else:
@@ -104,7 +108,7 @@ def attention(W, p, x, ctx, heads, residual):
         ops.gemm(q, k, alpha=hd ** -0.5, out=S[..., :Tk] if Tkp != Tk else S)
         ops.softmax_rows_(S, Tk)
         o = torch.empty(B, T, C, device=x.device, dtype=BF)
-        ops.gemm(S, vT.view(B, heads, hd, Tkp), out=o.view(B, T, heads, hd).permute(0, 2, 1, 3))
+        ops.gemm(S, vT.unflatten(1, (heads, hd)), out=o.view(B, T, heads, hd).permute(0, 2, 1, 3))
     return linear(W, p + '.to_out.0', o.reshape(B * T, C), residual=residual.reshape(B * T, C)).view(B, T, C)
 
 
@@ -115,6 +119,7 @@ class DiffusionNet:
         self.cfg, self.dev = cfg, device
         self.W = Weights(sd, device)
         self.G = cfg['groups']
+        self._ctx_kv = None
         # all time_emb_proj layers batched into ONE GEMM per step
         names = sorted(n[:-len('.time_emb_proj')] for n in self.W.w if n.endswith('.time_emb_proj'))
         self._tproj_names = names
@@ -126,6 +131,27 @@ class DiffusionNet:
             offs[n] = (o, o + c)
             o += c
         self._tproj_off = offs
+        # all cross-attention K / V projections of the text context batched into 1 + B GEMMs per step
+        xn = sorted(n[:-len('.to_k')] for n in self.W.w if n.endswith('.attn2.to_k'))
+        self._xattn_wk = torch.cat([self.W.w[n + '.to_k'] for n in xn], dim=0).contiguous()
+        self._xattn_wv = torch.cat([self.W.w[n + '.to_v'] for n in xn], dim=0).contiguous()
+        offs, o = {}, 0
+        for n in xn:
+            c = self.W.w[n + '.to_k'].shape[0]
+            offs[n] = (o, o + c)
+            o += c
+        self._xattn_off, self._xattn_total = offs, o
+
+    def project_context(self, ctx):
+        """ctx [B,Tk,Ck] -> {attn2 prefix: (K [B,Tk,C] view, V^T [B,C,Tkp] view)}."""
+        B, Tk, Ck = ctx.shape
+        Tkp = (Tk + 7) // 8 * 8
+        S = self._xattn_total
+        K_all = ops.gemm(ctx.reshape(B * Tk, Ck), self._xattn_wk).view(B, Tk, S)
+        vT_all = torch.zeros(B, S, Tkp, device=ctx.device, dtype=BF)
+        for b in range(B):
+            ops.gemm(self._xattn_wv, ctx[b], out=vT_all[b][:, :Tk])
+        return {n: (K_all[:, :, a:c], vT_all[:, a:c, :]) for n, (a, c) in self._xattn_off.items()}
 
     def heads_at(self, level):
         h = self.cfg['heads']
@@ -156,7 +182,7 @@ class DiffusionNet:
         n = ops.layer_norm(h, W.w[b + '.norm1'], W.b[b + '.norm1'])
         h = attention(W, b + '.attn1', n, n, heads, h)
         n = ops.layer_norm(h, W.w[b + '.norm2'], W.b[b + '.norm2'])
-        h = attention(W, b + '.attn2', n, ctx, heads, h)
+        h = attention(W, b + '.attn2', n, ctx, heads, h, kv=self._ctx_kv.get(b + '.attn2') if self._ctx_kv else None)
         n = ops.layer_norm(h, W.w[b + '.norm3'], W.b[b + '.norm3'])
         g = ops.geglu(linear(W, b + '.ff.net.0.proj', n.reshape(B * H * Wd, C)))
         h = linear(W, b + '.ff.net.2', g, residual=h.reshape(B * H * Wd, C)).view(B, H, Wd, C)
@@ -194,6 +220,7 @@ class ControlNet(DiffusionNet):
         B = sample_nchw.shape[0]
         tproj = self.time_embed(t, B)
         ctx = ctx.to(BF).contiguous()
+        self._ctx_kv = self.project_context(ctx)
         h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
         c = ops.silu(conv(W, 'controlnet_cond_embedding.conv_in', to_nhwc_bf16(cond_nchw01)))
         nblk = 2 * (len(self.cfg['cond_embed']) - 1)
@@ -219,6 +246,7 @@ class UNet(DiffusionNet):
         B = sample_nchw.shape[0]
         tproj = self.time_embed(t, B)
         ctx = ctx.to(BF).contiguous()
+        self._ctx_kv = self.project_context(ctx)
         h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
         h, skips = self.down_path(h, tproj, ctx)
         if down_residuals is not None:

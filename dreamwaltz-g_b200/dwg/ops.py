@@ -434,11 +434,12 @@ def attention(q, k, vt, heads, Tk, scale=None):
     _chk_bf16(q), _chk_bf16(k), _chk_bf16(vt)
     B, T, C = q.shape
     hd = C // heads
-    assert q.stride(2) == 1 and k.stride(2) == 1 and vt.is_contiguous() and q.stride(0) == T * q.stride(1) and k.stride(0) == Tk * k.stride(1)
+    assert q.stride(2) == 1 and k.stride(2) == 1 and vt.stride(2) == 1 and vt.stride(1) == vt.shape[2]
+    assert q.stride(0) == T * q.stride(1) and k.stride(0) == Tk * k.stride(1)
     out = torch.empty(B, T, C, device=q.device, dtype=torch.bfloat16)
     scale = hd ** -0.5 if scale is None else scale
     fl = 4.0 * B * heads * T * Tk * hd
     with _prof(fl, f'attention B{B} h{heads} T{T} Tk{Tk} d{hd}'):
-        check(lib().dwg_attention_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), k.stride(1), ptr(vt), vt.shape[2], ptr(out), B, heads, T, Tk,
+        check(lib().dwg_attention_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), k.stride(1), vt.data_ptr(), vt.shape[2], vt.stride(0), ptr(out), B, heads, T, Tk,
                                       hd, float(scale), stream()), 'dwg_attention_fwd')
     return out

@@ -198,10 +198,11 @@ int dwg_sds_grad(const float* eps_uncond, const float* eps_cond, const float* no
  * leave the SM (tcgen05 QK^T -> TMEM -> online softmax -> tcgen05 PV).  Replaces diffusers'
  * attention processor (F.scaled_dot_product_attention) inside every BasicTransformerBlock.
  *   q [B,T,heads*hd] bf16 (row stride q_ld), k [B,Tk,heads*hd] (row stride k_ld),
- *   vt [B, heads*hd, Tkp] = V transposed (key index contiguous; columns >= Tk finite),
+ *   vt [B, heads*hd, Tkp] = V transposed (key index contiguous; batch stride vt_batch_stride
+ *   elements; columns >= Tk finite),
  *   out [B,T,heads*hd] bf16.  hd multiple of 8, <= 128. */
 int dwg_attention_fwd(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* vt, int64_t Tkp,
-                      void* out, int B, int heads, int T, int Tk, int hd, float scale, void* stream);
+                      int64_t vt_batch_stride, void* out, int B, int heads, int T, int Tk, int hd, float scale, void* stream);
 
 #ifdef __cplusplus
 }
