@@ -88,7 +88,7 @@ __device__ __forceinline__ uint32_t make_idesc(int N) {
 }
 
 template <int CH /* ceil(hd/64) */, int NPV /* round16(hd) */>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(160, (CH == 1 && NPV <= 64) ? 2 : 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -187,7 +187,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const int kv_valid = min(BKV, p.Tk - j * BKV);
             // pass 1: row maximum
             float mx = -INFINITY;
-#pragma unroll
+#pragma unroll 2
             for (int c0 = 0; c0 < BKV; c0 += 16) {
                 uint32_t v[16];
                 tc_ld16(tmem_S + lane_base + (uint32_t)c0, v);
@@ -198,7 +198,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const float alpha = exp2f(m - m_new);               // 0 on the first block (m = -inf)
             float lsum = 0.f;
             // pass 2: P = exp2(s - m_new) -> bf16 -> swizzled smem tile
-#pragma unroll
+#pragma unroll 2
             for (int c0 = 0; c0 < BKV; c0 += 16) {
                 uint32_t v[16];
                 tc_ld16(tmem_S + lane_base + (uint32_t)c0, v);
