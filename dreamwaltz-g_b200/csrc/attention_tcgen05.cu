@@ -127,6 +127,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_S = *tmem_slot, tmem_O = tmem_S + 128;
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == 4) {
         if (elect_one()) {
@@ -292,7 +294,7 @@ template <int CH, int NPV>
 static int launch(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const Params& p, dim3 grid, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)CH * 16384 + 2 * CH * 16384 + 4 * NPV * 128 + 2 * 16384 + 128;
     cudaFuncSetAttribute(fa_fwd_kernel<CH, NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    fa_fwd_kernel<CH, NPV><<<grid, 160, smem, st>>>(q, k, v, p);
+    launch_pdl(fa_fwd_kernel<CH, NPV>, grid, dim3(160), smem, st, q, k, v, p);
     return check_launch("dwg_attention_fwd");
 }
 

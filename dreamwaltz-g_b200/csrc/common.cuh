@@ -68,4 +68,23 @@ __device__ __forceinline__ void cta_store_floats(float* dst, const float* src, i
     }
 }
 
+
+// ---- Programmatic Dependent Launch (PDL): a kernel launched with launch_pdl() may start (barrier
+// init, TMEM allocation, descriptor prefetch, weight-independent setup) while its stream
+// predecessor is still draining; it must call pdl_wait() before touching anything the predecessor
+// wrote, and pdl_trigger() lets ITS successor start early.  Works inside CUDA-graph capture.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace dwg

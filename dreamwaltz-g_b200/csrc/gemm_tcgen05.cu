@@ -178,6 +178,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // everything above overlapped the predecessor's tail; its outputs are visible from here on
+    pdl_trigger();
 
     // k-iteration range of a split
     auto it_range = [&](int ks, int& it0, int& it1) {
@@ -508,7 +510,7 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, i
         p.workspace = g_ws;
     }
     const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-    gemm_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    launch_pdl(gemm_kernel<BN, STAGES>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB, p);
     if (ks > 1) {
         const int64_t total = rows_total * p.N;
         int64_t g = (total + 255) / 256;

@@ -32,6 +32,8 @@ __device__ __forceinline__ float silu_grad(float x) { const float s = 1.0f / (1.
 // stats[n][g] = (sum, sumsq) accumulated with atomics (caller zeroes).
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, int HW, int C, int G, int rows_per_cta) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float s_bins[];        // [G][2]
     const int n = blockIdx.y;
     const int cpg = C / G;
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int HW, int C, int G, float eps, int do_silu,
                 int rows_per_cta) {
+    pdl_wait();
+    pdl_trigger();
     const int n = blockIdx.y;
     const int c8 = C / 8, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
@@ -118,6 +122,8 @@ __global__ void __launch_bounds__(256)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ bstats,
                     int HW, int C, int G, float eps, int do_silu, int rows_per_cta) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float s_bins[];
     const int n = blockIdx.y;
     const int cpg = C / G, c8 = C / 8;
@@ -170,6 +176,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
                     const float* __restrict__ bstats, const float* __restrict__ gamma, const float* __restrict__ beta,
                     const __nv_bfloat16* __restrict__ dx_add, __nv_bfloat16* __restrict__ dx, int HW, int C, int G, float eps,
                     int do_silu, int64_t total_vec) {
+    pdl_wait();
+    pdl_trigger();
     const int c8 = C / 8, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
@@ -201,6 +209,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, c8 = C / 8;
@@ -228,6 +238,8 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 // rows x cols_pad (cols valid, the padding columns are written as 0); one CTA per row.
 __global__ void __launch_bounds__(256)
 softmax_kernel(__nv_bfloat16* __restrict__ s, int cols, int cols_pad) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[8];
     __nv_bfloat16* row = s + (size_t)blockIdx.x * cols_pad;
     const int c8 = cols_pad / 8;
@@ -271,6 +283,8 @@ softmax_kernel(__nv_bfloat16* __restrict__ s, int cols, int cols_pad) {
 // short rows (cols_pad <= 256): one warp per row, 8 rows per CTA
 __global__ void __launch_bounds__(256)
 softmax_warp_kernel(__nv_bfloat16* __restrict__ s, int64_t rows, int cols, int cols_pad) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -302,6 +316,8 @@ softmax_warp_kernel(__nv_bfloat16* __restrict__ s, int64_t rows, int cols, int c
 // softmax backward in place on dP -> dS:  dS = P * (dP - sum(dP*P))      (VAE mid attention)
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ dp, int cols_pad) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[8];
     const __nv_bfloat16* pr = p + (size_t)blockIdx.x * cols_pad;
     __nv_bfloat16* dr = dp + (size_t)blockIdx.x * cols_pad;
@@ -333,6 +349,8 @@ softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restric
 // ---------------------------------------------------------------------------- GEGLU: y = a * gelu(b), x = [rows, 2*inner]
 __global__ void __launch_bounds__(256)
 geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t rows, int inner) {
+    pdl_wait();
+    pdl_trigger();
     const int i8 = inner / 8;
     const int64_t total = rows * i8;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
@@ -352,6 +370,8 @@ geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
 __global__ void __launch_bounds__(256)
 eltwise_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ y,
                int64_t n8, int mode) {
+    pdl_wait();
+    pdl_trigger();
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
         float f[8], g[8];
         unpack8(reinterpret_cast<const bf8*>(x)[v], f);
@@ -396,11 +416,11 @@ extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float*
     int rows_per_cta = (int)((int64_t)2048 * 8 / C);           // ~16K elements per CTA
     if (rows_per_cta < 1) rows_per_cta = 1;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
-    gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * G, st>>>((const bf16*)x, stats, HW, C, G, rows_per_cta);
+    launch_pdl(gn_stats_kernel, grid, dim3(256), sizeof(float) * 2 * G, st, (const bf16*)x, stats, HW, C, G, rows_per_cta);
     int rows_apply = (int)((int64_t)2048 * 8 / C);             // ~16K elements per CTA: enough CTAs to fill the machine
     if (rows_apply < 1) rows_apply = 1;
     dim3 grid2((HW + rows_apply - 1) / rows_apply, N);
-    gn_apply_kernel<<<grid2, 256, 0, st>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G, eps, do_silu, rows_apply);
+    launch_pdl(gn_apply_kernel, grid2, dim3(256), 0, st, (const bf16*)x, (const float*)stats, gamma, beta, (bf16*)y, HW, C, G, eps, do_silu, rows_apply);
     return check_launch("dwg_groupnorm_fwd");
 }
 
@@ -423,7 +443,7 @@ extern "C" int dwg_groupnorm_bwd(const void* x, const void* dy, const float* sta
 
 extern "C" int dwg_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps, void* stream) {
     DWG_REQUIRE(x && gamma && beta && y && C % 8 == 0, "bad arguments");
-    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y, rows, C, eps);
+    launch_pdl(layernorm_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, gamma, beta, (bf16*)y, rows, C, eps);
     return check_launch("dwg_layernorm_fwd");
 }
 
@@ -444,13 +464,13 @@ extern "C" int dwg_softmax_rows_bwd(const void* p, void* dp, int64_t rows, int c
 
 extern "C" int dwg_geglu(const void* x, void* y, int64_t rows, int inner, void* stream) {
     DWG_REQUIRE(x && y && inner % 8 == 0, "bad arguments");
-    geglu_kernel<<<grid_for(rows * (inner / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rows, inner);
+    launch_pdl(geglu_kernel, dim3(grid_for(rows * (inner / 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, rows, inner);
     return check_launch("dwg_geglu");
 }
 
 extern "C" int dwg_eltwise_bf16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream) {
     DWG_REQUIRE(x && y && n % 8 == 0 && mode >= 0 && mode <= 2 && (mode == 0 || a), "bad arguments");
-    eltwise_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)a, (bf16*)y, n / 8, mode);
+    launch_pdl(eltwise_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)a, (bf16*)y, n / 8, mode);
     return check_launch("dwg_eltwise_bf16");
 }
 
