@@ -196,6 +196,14 @@ def run_dwg(args):
 
     for _ in range(args.warmup):
         one_step(False)
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as pr:
+            for _ in range(3):
+                one_step(False)
+            torch.cuda.synchronize()
+        print(pr.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=90), file=sys.stderr)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -382,6 +390,7 @@ def main():
     ap.add_argument('--impl', default='dwg', choices=['dwg', 'reference'])
     ap.add_argument('--tiny', action='store_true', help='reduced-width smoke configuration (NOT the benchmark workload)')
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='print a CUPTI kernel table of 3 steps to stderr')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--n-unconstrained', type=int, default=N_UNCONSTRAINED)
     ap.add_argument('--image', type=int, default=IMG)
