@@ -53,6 +53,33 @@ def geom_part():
     torch.cuda.synchronize()
 
 
+def nn_part():
+    x = torch.randn(2, 64, 64, 320, device=DEV).bfloat16()
+    g, b = torch.ones(320, device=DEV), torch.zeros(320, device=DEV)
+    for _ in range(2):
+        ops.group_norm(x, g, b, 32, 1e-5, True)
+    t = torch.randn(8192, 320, device=DEV).bfloat16()
+    for _ in range(2):
+        ops.layer_norm(t, g, b)
+    gg = torch.randn(8192, 2560, device=DEV).bfloat16()
+    for _ in range(2):
+        ops.geglu(gg)
+    for _ in range(2):
+        ops.add(x, x)
+    xv = torch.randn(1, 512, 512, 128, device=DEV).bfloat16()
+    gv, bv = torch.ones(128, device=DEV), torch.zeros(128, device=DEV)
+    y, st = ops.group_norm(xv, gv, bv, 32, 1e-6, True, return_stats=True)
+    ops.group_norm_bwd(xv, y, st, gv, bv, 32, 1e-6, True)
+    a = torch.randn(128, 1280, device=DEV).bfloat16(); w = torch.randn(1280, 1280, device=DEV).bfloat16()
+    for _ in range(2):
+        ops.gemm(a, w)                      # split-K + finalize
+    a2 = torch.randn(2, 320, device=DEV).bfloat16(); w2 = torch.randn(1280, 320, device=DEV).bfloat16()
+    for _ in range(2):
+        ops.gemm(a2, w2, act='silu')
+
+
+if what in ('nn',):
+    nn_part()
 if what in ('all', 'gemm'):
     gemm_part()
 if what in ('all', 'geom'):
