@@ -29,7 +29,7 @@ constexpr int BK = 64;              // 64 bf16 = 128 bytes = one swizzle-128B ro
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 256;
 
-enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2 };
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };   // GEGLU: columns are (value, gate) pairs -> N/2 outputs
 
 struct Params {
     // problem
@@ -347,6 +347,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < nvalid; j++) f[j] += b2p[j];
                     }
                 }
+                if (p.act == ACT_GEGLU) {
+                    // fused GEGLU (diffusers GEGLU: hidden * gelu(gate)); weight rows were interleaved at load time
+                    float gl[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) gl[j] = f[2 * j] * apply_act(f[2 * j + 1], ACT_GELU);
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + (ncol0 >> 1);
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(gl[j], gl[j + 1]), h1 = __floats2bfloat162_rn(gl[j + 2], gl[j + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(gl[j + 4], gl[j + 5]), h3 = __floats2bfloat162_rn(gl[j + 6], gl[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(dst + j) = pk;
+                        }
+                    } else {
+                        for (int j = 0; j < nvalid / 2; j++) dst[j] = __float2bfloat16(gl[j]);
+                    }
+                    continue;
+                }
                 if (p.act != ACT_NONE) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) f[j] = apply_act(f[j], p.act);
@@ -491,9 +512,10 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, i
     const int64_t base_tiles = (int64_t)p.m_tiles * p.n_tiles * p.nz;
     // split-K when the tile count cannot fill the machine and the K loop is long
     int ks = 1;
-    if (base_tiles * 2 <= g_num_sms && iters >= 8) {
+    if (base_tiles * 2 <= g_num_sms && iters >= 8 && p.act != ACT_GEGLU) {
         ks = (int)(g_num_sms / base_tiles);
-        if (ks > iters / 4) ks = iters / 4;
+        if (ks > iters / 2) ks = iters / 2;
+        if (ks > 16) ks = 16;
         if (ks < 1) ks = 1;
     }
     p.ksplit = ks;
@@ -546,6 +568,7 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     DWG_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && (a_b1 % 8) == 0 && (a_b2 % 8) == 0 && (b_b1 % 8) == 0 && (b_b2 % 8) == 0,
                 "A/B strides must be multiples of 8 elements (16 bytes) for TMA");
     DWG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "A/B must be 16-byte aligned");
+    DWG_REQUIRE(act != ACT_GEGLU || (N % 2 == 0 && out_bf16 && !residual), "GEGLU epilogue: even N, bf16 output, no residual");
     CUtensorMap tmA, tmB;
     const uint32_t ones[4] = {1, 1, 1, 1};
     const int bn = pick_bn(N);

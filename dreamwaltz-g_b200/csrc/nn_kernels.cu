@@ -51,7 +51,25 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, 
         float s[8], ss[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) { s[i] = 0.f; ss[i] = 0.f; }
-        for (int r = row0 + rl; r < row1; r += rp) {
+        int r = row0 + rl;
+        for (; r + 3 * rp < row1; r += 4 * rp) {          // 4 independent 16-byte loads in flight
+            bf8 v0 = xp[(size_t)r * c8 + cv], v1 = xp[(size_t)(r + rp) * c8 + cv];
+            bf8 v2 = xp[(size_t)(r + 2 * rp) * c8 + cv], v3 = xp[(size_t)(r + 3 * rp) * c8 + cv];
+            float f[8];
+            unpack8(v0, f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+            unpack8(v1, f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+            unpack8(v2, f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+            unpack8(v3, f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+        }
+        for (; r < row1; r += rp) {
             float f[8];
             unpack8(xp[(size_t)r * c8 + cv], f);
 #pragma unroll
@@ -104,7 +122,24 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
             a[i] = rsqrtf(var + eps) * gamma[c];
             b[i] = beta[c] - mean * a[i];
         }
-        for (int r = row0 + rl; r < row1; r += rp) {
+        int r = row0 + rl;
+        for (; r + 3 * rp < row1; r += 4 * rp) {          // 4 independent 16-byte loads in flight
+            bf8 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = xp[(size_t)(r + u * rp) * c8 + cv];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float o = fmaf(f[i], a[i], b[i]);
+                    f[i] = do_silu ? silu(o) : o;
+                }
+                yp[(size_t)(r + u * rp) * c8 + cv] = pack8(f);
+            }
+        }
+        for (; r < row1; r += rp) {
             float f[8];
             unpack8(xp[(size_t)r * c8 + cv], f);
 #pragma unroll
@@ -215,6 +250,40 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, c8 = C / 8;
     const bf8* xp = reinterpret_cast<const bf8*>(x + row * C);
+    bf8* yp = reinterpret_cast<bf8*>(y + row * C);
+    constexpr int MAXV = 5;                            // C <= 1280 stays in registers (all loads issued up front)
+    if (c8 <= MAXV * 32) {
+        bf8 v[MAXV];
+#pragma unroll
+        for (int u = 0; u < MAXV; u++) if (lane + u * 32 < c8) v[u] = xp[lane + u * 32];
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int u = 0; u < MAXV; u++) {
+            if (lane + u * 32 < c8) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; i++) { s += f[i]; ss += f[i] * f[i]; }
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
+        const float mean = s / C, rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
+#pragma unroll
+        for (int u = 0; u < MAXV; u++) {
+            const int vv = lane + u * 32;
+            if (vv < c8) {
+                float f[8];
+                unpack8(v[u], f);
+                const float4 g0 = *reinterpret_cast<const float4*>(gamma + vv * 8), g1 = *reinterpret_cast<const float4*>(gamma + vv * 8 + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(beta + vv * 8), b1 = *reinterpret_cast<const float4*>(beta + vv * 8 + 4);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) f[i] = (f[i] - mean) * rstd * gg[i] + bb[i];
+                yp[vv] = pack8(f);
+            }
+        }
+        return;
+    }
     float s = 0.f, ss = 0.f;
     for (int v = lane; v < c8; v += 32) {
         float f[8];
@@ -224,7 +293,6 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
     }
     for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); ss += __shfl_xor_sync(0xffffffffu, ss, off); }
     const float mean = s / C, rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
-    bf8* yp = reinterpret_cast<bf8*>(y + row * C);
     for (int v = lane; v < c8; v += 32) {
         float f[8];
         unpack8(xp[v], f);
@@ -413,12 +481,13 @@ extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float*
     DWG_REQUIRE(C % 8 == 0 && C % G == 0 && al16(x) && al16(y), "C must be a multiple of 8 and of G; 16-byte aligned tensors");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, st);
-    int rows_per_cta = (int)((int64_t)2048 * 8 / C);           // ~16K elements per CTA
-    if (rows_per_cta < 1) rows_per_cta = 1;
+    const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;        // row lanes per CTA
+    int rows_per_cta = (int)(((int64_t)N * HW + 4 * kNumSMs - 1) / (4 * kNumSMs));      // ~4 CTAs per SM
+    if (rows_per_cta < 4 * rp_) rows_per_cta = 4 * rp_;
+    if (rows_per_cta > 64 * rp_) rows_per_cta = 64 * rp_;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
     launch_pdl(gn_stats_kernel, grid, dim3(256), sizeof(float) * 2 * G, st, (const bf16*)x, stats, HW, C, G, rows_per_cta);
-    int rows_apply = (int)((int64_t)2048 * 8 / C);             // ~16K elements per CTA: enough CTAs to fill the machine
-    if (rows_apply < 1) rows_apply = 1;
+    int rows_apply = rows_per_cta;
     dim3 grid2((HW + rows_apply - 1) / rows_apply, N);
     launch_pdl(gn_apply_kernel, grid2, dim3(256), 0, st, (const bf16*)x, (const float*)stats, gamma, beta, (bf16*)y, HW, C, G, eps, do_silu, rows_apply);
     return check_launch("dwg_groupnorm_fwd");

@@ -255,7 +255,7 @@ def rasterize(means3D, means2D, colors, opacities, scales, rotations, *, image_h
 
 
 # ------------------------------------------------------------------------------ tensor-core GEMM / conv
-ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2}
+ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3}
 PROFILE = None        # set to a list to record (start_event, end_event, flops, kind) per tensor-core launch
 
 
@@ -292,10 +292,11 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
     nb2, nb1, M, K = a4.shape
     N = b4.shape[2]
     assert b4.shape[3] == K and b4.shape[0] == nb2 and b4.shape[1] == nb1
+    No = N // 2 if act == 'geglu' else N                  # fused GEGLU halves the output width
     if out is None:
-        out = torch.empty(nb2, nb1, M, N, device=a.device, dtype=out_dtype)
+        out = torch.empty(nb2, nb1, M, No, device=a.device, dtype=out_dtype)
         c4 = out
-        out = out.reshape(tuple(a.shape[:-1]) + (N,))
+        out = out.reshape(tuple(a.shape[:-1]) + (No,))
     else:
         c4 = out.as_strided((1,) * (4 - out.dim()) + tuple(out.shape), (0,) * (4 - out.dim()) + tuple(out.stride())) if out.dim() < 4 else out
         assert c4.stride(-1) == 1

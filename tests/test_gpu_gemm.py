@@ -105,3 +105,27 @@ def test_fused_attention_vs_sdpa(B, heads, T, Tk, hd):
     sp = lambda t: t.float().view(B, -1, heads, hd).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B, T, C)
     assert _rel(out, ref) < 2e-2
+
+
+def test_gemm_fused_geglu_epilogue():
+    torch.manual_seed(7)
+    M, K, inner = 2048, 640, 2560
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(2 * inner, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(2 * inner, device=DEV) * 0.1
+    full = a.float() @ w.float().t() + bias
+    ref = full[:, :inner] * F.gelu(full[:, inner:])
+    wi = torch.stack([w[:inner], w[inner:]], dim=1).reshape(2 * inner, K).contiguous()
+    bi = torch.stack([bias[:inner], bias[inner:]], dim=1).reshape(2 * inner).contiguous()
+    out = ops.gemm(a, wi, bias=bi, act='geglu')
+    assert out.shape == (M, inner) and _rel(out, ref) < 2e-2
+
+
+def test_gemm_tiny_m_and_deep_split_k():
+    torch.manual_seed(8)
+    for (M, N, K) in ((2, 1280, 320), (128, 1280, 5120), (128, 1280, 1280), (512, 1280, 1280)):
+        a = torch.randn(M, K, device=DEV).bfloat16()
+        b = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+        res = torch.randn(M, N, device=DEV).bfloat16()
+        c = ops.gemm(a, b, residual=res, out_dtype=torch.float32)
+        assert _rel(c, a.float() @ b.float().t() + res.float()) < 2e-3
