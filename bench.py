@@ -176,6 +176,8 @@ def run_dwg(args):
             return float(res['gradients'].abs().mean()), int(res['timestep'][0])
         return None
 
+    cpu_ms = [0.0]
+
     def timed(steps, e2e):
         if world > 1:
             dist.barrier()
@@ -183,8 +185,10 @@ def run_dwg(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = L.launches
         e0.record()
+        t_cpu = time.perf_counter()
         for _ in range(steps):
             one_step(e2e)
+        cpu_ms[0] = (time.perf_counter() - t_cpu) * 1000.0 / steps        # host enqueue time (no sync inside)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -208,6 +212,7 @@ def run_dwg(args):
     if rank == 0:
         sampler.start()
     ms_step, launches = timed(args.steps, False)
+    cpu_enqueue_ms = cpu_ms[0]
     for _ in range(min(2, args.warmup)):
         one_step(True)
     ms_e2e, _ = timed(args.steps, True)
@@ -255,7 +260,7 @@ def run_dwg(args):
                    'cache': 'inputs larger than L2 (2.6 GB of bf16 weights streamed every step; 126 MB L2)',
                    'cuda_graphs': not args.no_graphs},
         'e2e': {'value': round(e2e_v, 3), 'unit': 'steps/s', 'ms_per_step': round(ms_e2e, 3), 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 12},
-        'gpu_launches': int(round(launches)), 'clocks': clocks, 'roofline': roof,
+        'gpu_launches': int(round(launches)), 'host_enqueue_ms_per_step': round(cpu_enqueue_ms, 3), 'clocks': clocks, 'roofline': roof,
     }
     if not args.skip_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(sample_only=True)
