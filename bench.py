@@ -136,6 +136,65 @@ class Scene:
         return res
 
 
+class StepGraph:
+    """The WHOLE SDS step (animate -> raster -> VAE -> ControlNet+UNet -> SDS -> backward to every
+    avatar parameter) captured as ONE CUDA graph.  Per-step inputs live in static device buffers
+    (pose, device-resident camera struct, prompt embeddings, condition image); noise / timestep are
+    drawn inside the graph from torch's graph-safe default generator."""
+
+    def __init__(self, sc):
+        from dwg import ops
+        self.sc, dev = sc, sc.dev
+        g = sc.guidance
+        g._g = None
+        g.use_default_generator = True
+        pose, data = sc.next_view()
+        self.data = data                                   # image size / template; matrices come from cam_dev
+        self.pose = {k: v.to(dev).clone() for k, v in pose.items()}
+        self.cam = torch.zeros(ops.CAMERA_WORDS, device=dev)
+        self.embeds = {k: v.clone() for k, v in sc.d_embeds.items()}
+        self.cond = sc.d_cond.clone()
+        self.set_camera(data)
+
+        def body():
+            for p in sc.params:
+                p.grad = None
+            gs = sc.avatar.animate(self.pose)
+            out = sc.renderer.render(self.data, gs, cam_dev=self.cam)
+            res = sc.guidance(out['image_chw'].unsqueeze(0), self.embeds, cond_inputs=self.cond)
+            res['diffusion_loss'].backward()
+            return res['gradients'].abs().mean(), res['timestep']
+        from dwg._lib import lib
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = lib().launches
+        with torch.cuda.graph(self.graph):
+            self.out = body()
+        self.launches = lib().launches - n0
+        torch.cuda.synchronize()
+
+    def pack_camera(self, data, out=None):
+        from dwg import camera, ops
+        view, proj, campos, tfx, tfy = camera.raster_matrices(data)
+        return ops.pack_camera(data['image_height'], data['image_width'], tfx, tfy, view, proj, self.sc.renderer.bg_color, 1.0, out=out)
+
+    def set_camera(self, data):
+        self.cam.copy_(self.pack_camera(data))
+
+    def replay(self):
+        from dwg._lib import lib
+        self.graph.replay()
+        L = lib()
+        object.__setattr__(L, 'launches', L.launches + self.launches)
+        return self.out
+
+
 def flat_grads(params):
     return torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
 
@@ -154,12 +213,42 @@ def run_dwg(args):
         dist.init_process_group('nccl', device_id=torch.device(dev))
     pk, pk_src = peaks()
     sc = Scene(dev, rank, tiny=args.tiny, n_unc=args.n_unconstrained, img=args.image)
-    if not args.no_graphs:
+    sg = None
+    if not args.no_graphs and not args.no_step_graph:
+        try:
+            sg = StepGraph(sc)
+        except Exception as e:                       # fall back to sub-graphs (reported in config)
+            print(f'[bench] whole-step graph capture failed ({type(e).__name__}: {e}); using sub-graphs', file=sys.stderr)
+            sg = None
+            torch.cuda.synchronize()
+    if sg is None and not args.no_graphs:
+        sc.guidance.use_default_generator = False
         sc.guidance.enable_graphs((args.image, args.image))
     L = _lib.lib()
+    pin = lambda t: t.pin_memory()
+    h_cam = pin(torch.zeros(ops.CAMERA_WORDS))
 
     def one_step(e2e):
         pose, data = sc.next_view()
+        if sg is not None:
+            # static-buffer updates + ONE graph replay
+            sg.pack_camera(data, out=h_cam)
+            if e2e:
+                for k, v in pose.items():
+                    sg.pose[k].copy_(pin(v), non_blocking=True)
+                for k, v in sc.h_embeds.items():
+                    sg.embeds[k].copy_(v, non_blocking=True)
+                sg.cond.copy_(sc.h_cond, non_blocking=True)
+            else:
+                for k, v in pose.items():
+                    sg.pose[k].copy_(v, non_blocking=True)
+            sg.cam.copy_(h_cam, non_blocking=True)
+            metric, tstep = sg.replay()
+            if world > 1:
+                parallel.allreduce_grads(sc.params)
+            if e2e:
+                return float(metric), int(tstep[0])
+            return None
         if e2e:
             # per-step host -> device copies of that step's inputs (pinned memory, async)
             pose_dev = {k: v.pin_memory().to(dev, non_blocking=True) for k, v in pose.items()}
@@ -258,7 +347,7 @@ def run_dwg(args):
                    'gaussians': int(sc.avatar._positions.shape[0] + sum(m._scales.shape[0] for m in sc.avatar.mesh_binding_gaussians.values())),
                    'image': args.image, 'views_per_step': world, 'parallelism': f'view-dp{world} + 1 NCCL all-reduce' if world > 1 else 'single GPU',
                    'cache': 'inputs larger than L2 (2.6 GB of bf16 weights streamed every step; 126 MB L2)',
-                   'cuda_graphs': not args.no_graphs},
+                   'cuda_graphs': ('whole step' if sg is not None else ('sub-graphs' if not args.no_graphs else False))},
         'e2e': {'value': round(e2e_v, 3), 'unit': 'steps/s', 'ms_per_step': round(ms_e2e, 3), 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 12},
         'gpu_launches': int(round(launches)), 'host_enqueue_ms_per_step': round(cpu_enqueue_ms, 3), 'clocks': clocks, 'roofline': roof,
     }
@@ -395,6 +484,7 @@ def main():
     ap.add_argument('--impl', default='dwg', choices=['dwg', 'reference'])
     ap.add_argument('--tiny', action='store_true', help='reduced-width smoke configuration (NOT the benchmark workload)')
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--no-step-graph', action='store_true', help='capture only the diffusion sub-graphs')
     ap.add_argument('--profile', action='store_true', help='print a CUPTI kernel table of 3 steps to stderr')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--n-unconstrained', type=int, default=N_UNCONSTRAINED)

@@ -17,7 +17,7 @@ constexpr int NG = 10;      // mean2D.xy, conic.xyz, opacity, colour.rgb, depth
 
 __global__ void __launch_bounds__(TILE_PIX)
 render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
-                  float bg0, float bg1, float bg2,
+                  float bg0, float bg1, float bg2, const float* __restrict__ bg_dev,
                   const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                   const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
                   const float* __restrict__ dL_dalpha,
@@ -27,6 +27,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     __shared__ float s_acc[CHUNK][NG + 1];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_max[TILE_PIX / 32];
+    if (bg_dev) { bg0 = bg_dev[0]; bg1 = bg_dev[1]; bg2 = bg_dev[2]; }
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int px = blockIdx.x * TILE + (threadIdx.x & (TILE - 1));
     const int py = blockIdx.y * TILE + (threadIdx.x >> 4);
@@ -186,13 +187,14 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
 
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(int64_t N, const float* __restrict__ means3D, const float* __restrict__ scales,
-                      const float* __restrict__ rots, DwgRasterCamera cam, GeomView g,
+                      const float* __restrict__ rots, const DwgRasterCamera cam_val, const DwgRasterCamera* __restrict__ cam_dev, GeomView g,
                       const float* __restrict__ g_mean2D /* [N,3] */, const float4* __restrict__ g_conic_depth,
                       float* __restrict__ g_means3D, float* __restrict__ g_scales, float* __restrict__ g_rots) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
     if (g.tiles_touched[i] > 0) {
+        const DwgRasterCamera cam = cam_dev ? *cam_dev : cam_val;
         const int H = cam.image_height, W = cam.image_width;
         const float fx = W / (2.0f * cam.tanfovx), fy = H / (2.0f * cam.tanfovy);
         const float* view = cam.viewmatrix;
@@ -327,7 +329,7 @@ extern "C" int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N, const 
                                    const void* img, const float* dL_dcolor, const float* dL_ddepth,
                                    const float* dL_dalpha, float* g_means3D, float* g_means2D, float* g_colors,
                                    float* g_opacities, float* g_scales, float* g_rotations, void* scratch,
-                                   void* stream) {
+                                   const void* cam_dev, void* stream) {
     (void)colors_precomp; (void)opacities;
     DWG_REQUIRE(cam && geom && bin && img && dL_dcolor && scratch, "null pointer");
     DWG_REQUIRE(N == 0 || (means3D && scales && rotations && g_means3D && g_means2D && g_colors && g_opacities && g_scales && g_rotations),
@@ -341,14 +343,15 @@ extern "C" int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N, const 
     BinView b(const_cast<void*>(bin), P_cap, T);
     ImgView im(const_cast<void*>(img), H, W);
     float4* gcd = reinterpret_cast<float4*>(scratch);
+    const DwgRasterCamera* cd = reinterpret_cast<const DwgRasterCamera*>(cam_dev);
     cudaMemsetAsync(g_means2D, 0, sizeof(float) * 3 * N, st);
     cudaMemsetAsync(g_colors, 0, sizeof(float) * 3 * N, st);
     cudaMemsetAsync(g_opacities, 0, sizeof(float) * N, st);
     cudaMemsetAsync(gcd, 0, sizeof(float4) * N, st);
-    render_bwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2],
+    render_bwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2], cd ? cd->bg : nullptr,
                                                         im.final_T, im.n_contrib, dL_dcolor, dL_ddepth, dL_dalpha,
                                                         g_means2D, gcd, g_opacities, g_colors);
-    preprocess_bwd_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, means3D, scales, rotations, *cam, g, g_means2D, gcd,
+    preprocess_bwd_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, means3D, scales, rotations, *cam, cd, g, g_means2D, gcd,
                                                                      g_means3D, g_scales, g_rotations);
     return check_launch("dwg_raster_backward");
 }

@@ -11,7 +11,7 @@
 namespace dwg {
 namespace raster {
 
-int launch_pre(const DwgRasterCamera& cam, int64_t N, const float* means3D, const float* opacities,
+int launch_pre(const DwgRasterCamera& cam, const DwgRasterCamera* cam_dev, int64_t N, const float* means3D, const float* opacities,
                const float* scales, const float* rots, GeomView g, BinView b, int T, int64_t P_cap,
                int32_t* radii, int32_t* status, cudaStream_t st);
 int launch_sort(int T, BinView b, GeomView g, const float* colors, const int32_t* status, int64_t P_cap,
@@ -19,11 +19,12 @@ int launch_sort(int T, BinView b, GeomView g, const float* colors, const int32_t
 
 __global__ void __launch_bounds__(TILE_PIX)
 render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
-                  float bg0, float bg1, float bg2,
+                  float bg0, float bg1, float bg2, const float* __restrict__ bg_dev,
                   float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
                   float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
     __shared__ __align__(128) Rec s_rec[2][CHUNK];
     __shared__ __align__(8) uint64_t s_bar[2];
+    if (bg_dev) { bg0 = bg_dev[0]; bg1 = bg_dev[1]; bg2 = bg_dev[2]; }
     const int tile = blockIdx.y * gx + blockIdx.x;
     const int px = blockIdx.x * TILE + (threadIdx.x & (TILE - 1));
     const int py = blockIdx.y * TILE + (threadIdx.x >> 4);
@@ -133,7 +134,7 @@ extern "C" int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N, const f
                                   const float* colors_precomp, const float* opacities, const float* scales,
                                   const float* rotations, float* out_color, float* out_depth, float* out_alpha,
                                   int32_t* radii, void* geom, void* bin, int64_t P_cap, void* img,
-                                  int32_t* status, void* stream) {
+                                  int32_t* status, const void* cam_dev, void* stream) {
     DWG_REQUIRE(cam && out_color && out_depth && out_alpha && geom && bin && img && status, "null pointer");
     DWG_REQUIRE(N == 0 || (means3D && colors_precomp && opacities && scales && rotations && radii), "null input");
     DWG_REQUIRE(cam->image_height > 0 && cam->image_width > 0, "bad image size");
@@ -146,11 +147,12 @@ extern "C" int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N, const f
     GeomView g(geom, N > 0 ? N : 1);
     BinView b(bin, P_cap, T);
     ImgView im(img, H, W);
-    int rc = launch_pre(*cam, N, means3D, opacities, scales, rotations, g, b, T, P_cap, radii, status, st);
+    const DwgRasterCamera* cd = reinterpret_cast<const DwgRasterCamera*>(cam_dev);
+    int rc = launch_pre(*cam, cd, N, means3D, opacities, scales, rotations, g, b, T, P_cap, radii, status, st);
     if (rc != DWG_OK) return rc;
     rc = launch_sort(T, b, g, colors_precomp, status, P_cap, 1, st);
     if (rc != DWG_OK) return rc;
-    render_fwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2],
+    render_fwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2], cd ? cd->bg : nullptr,
                                                         out_color, out_depth, out_alpha, im.final_T, im.n_contrib);
     return check_launch("dwg_raster_forward");
 }

@@ -18,9 +18,12 @@ namespace raster {
 __global__ void __launch_bounds__(256)
 preprocess_kernel(int64_t N, const float* __restrict__ means3D, const float* __restrict__ scales,
                   const float* __restrict__ rots, const float* __restrict__ opacities,
-                  DwgRasterCamera cam, GeomView g, int32_t* __restrict__ radii, uint32_t* __restrict__ tile_count) {
+                  const DwgRasterCamera cam_val, const DwgRasterCamera* __restrict__ cam_dev, GeomView g,
+                  int32_t* __restrict__ radii, uint32_t* __restrict__ tile_count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    // a device-resident camera (updated between CUDA-graph replays) overrides the by-value copy
+    const DwgRasterCamera cam = cam_dev ? *cam_dev : cam_val;
     const int H = cam.image_height, W = cam.image_width;
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
     const float* view = cam.viewmatrix;
@@ -238,12 +241,12 @@ scatter_kernel(int64_t N, int gx, GeomView g, BinView b, int64_t P_cap) {
         }
 }
 
-int launch_pre(const DwgRasterCamera& cam, int64_t N, const float* means3D, const float* opacities,
+int launch_pre(const DwgRasterCamera& cam, const DwgRasterCamera* cam_dev, int64_t N, const float* means3D, const float* opacities,
                const float* scales, const float* rots, GeomView g, BinView b, int T, int64_t P_cap,
                int32_t* radii, int32_t* status, cudaStream_t st) {
     const int gx = (cam.image_width + TILE - 1) / TILE;
     cudaMemsetAsync(b.tile_count, 0, BinView::header_bytes(T), st);      // counts, cursors, starts, ranges
-    if (N > 0) preprocess_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, means3D, scales, rots, opacities, cam, g, radii, b.tile_count);
+    if (N > 0) preprocess_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, means3D, scales, rots, opacities, cam, cam_dev, g, radii, b.tile_count);
     tile_scan_kernel<<<1, 1024, 0, st>>>(T, b, P_cap, status);
     if (N > 0) scatter_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, gx, g, b, P_cap);
     return check_launch("raster preprocess/scan/scatter");

@@ -96,6 +96,10 @@ class MeshBindingGaussianModel(nn.Module):
         self._bary_coords = nn.Parameter(mesh['_bary_coords'].clone().to(device))
         self._vertex_coords = nn.Parameter(mesh['_vertex_coords'].clone().to(device), requires_grad=False)
         self._scales = nn.Parameter(mesh['_scales'].clone().to(device))
+        # constants as device buffers (no per-step host->device copies; CUDA-graph capturable)
+        self.register_buffer('_zaxis', torch.tensor([0.0, 0.0, 1.0], device=device))
+        self.register_buffer('_xaxis', torch.tensor([1.0, 0.0, 0.0], device=device))
+        self.register_buffer('_flip', torch.tensor([1.0, -1.0, -1.0], device=device).view(1, 3, 1))
 
     def get_positions(self, vertex_coords):
         bary = self._bary_coords / self._bary_coords.sum(dim=-1, keepdim=True)
@@ -111,16 +115,16 @@ class MeshBindingGaussianModel(nn.Module):
         fn = torch.cross(vertex_coords[i1] - vertex_coords[i0], vertex_coords[i2] - vertex_coords[i0], dim=-1)
         fn = fn / torch.sqrt(torch.clamp((fn * fn).sum(-1, keepdim=True), min=1e-20))
         vn = torch.zeros_like(vertex_coords).index_add(0, i0, fn).index_add(0, i1, fn).index_add(0, i2, fn)
-        vn = torch.where(dot(vn, vn) > 1e-20, vn, torch.tensor([0.0, 0.0, 1.0], device=vn.device))
+        vn = torch.where(dot(vn, vn) > 1e-20, vn, self._zaxis)
         vn = vn / torch.sqrt(torch.clamp(dot(vn, vn), min=1e-20))
         pn = (vn[self.points_to_vertices] * self._bary_coords.reshape(-1, 3)[:, :, None]).sum(dim=1)
         v0 = pn / (nrm(pn) + eps)
-        ref = torch.tensor((1.0, 0.0, 0.0), device=p0.device).expand_as(p0)
+        ref = self._xaxis.expand_as(p0)
         v1 = torch.cross(v0, ref, dim=1)
         v1 = v1 / (nrm(v1) + eps)
         v2 = torch.cross(v0, v1, dim=1)
         v2 = v2 / (nrm(v2) + eps)
-        R = torch.stack((v0, v1, v2), dim=2) * torch.tensor([1.0, -1.0, -1.0], device=p0.device).view(1, 3, 1)
+        R = torch.stack((v0, v1, v2), dim=2) * self._flip
         s1 = (dot(p1 - p0, v1).abs() + dot(p2 - p0, v1).abs() + dot(p3 - p0, v1).abs()) / self.n_per_triangle
         s2 = (dot(p1 - p0, v2).abs() + dot(p2 - p0, v2).abs() + dot(p3 - p0, v2).abs()) / self.n_per_triangle
         s1 = s1 * torch.clamp(self._scales[:, 1:2], min=0.5, max=2.0)
@@ -216,7 +220,7 @@ class GaussianRenderer:
         self.sh_levels = sh_levels
         self.bg_color = torch.tensor(bg_color)
 
-    def render(self, data: dict, gaussians: GaussianOutput, return_2d_radii: bool = False) -> dict:
+    def render(self, data: dict, gaussians: GaussianOutput, return_2d_radii: bool = False, cam_dev=None) -> dict:
         from .camera import raster_matrices
         view, proj, campos, tanfovx, tanfovy = raster_matrices(data)         # host tensors: no device sync
         means3D = gaussians.positions
@@ -227,7 +231,7 @@ class GaussianRenderer:
         img, radii, depth, alpha = ops.rasterize(
             means3D, screenspace_points, colors, gaussians.opacities, gaussians.scales, gaussians.quaternions,
             image_height=data['image_height'], image_width=data['image_width'], tanfovx=tanfovx, tanfovy=tanfovy,
-            viewmatrix=view, projmatrix=proj, bg=self.bg_color)
+            viewmatrix=view, projmatrix=proj, bg=self.bg_color, cam_dev=cam_dev)
         out = {'image': img.permute(1, 2, 0).unsqueeze(0), 'depth': depth.permute(1, 2, 0).unsqueeze(0),
                'alpha': alpha.permute(1, 2, 0).unsqueeze(0), 'image_chw': img}
         if return_2d_radii:

@@ -49,6 +49,7 @@ class ControlNetScoreDistillation:
         self.vae_scale_factor = 8
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(seed)
+        self.use_default_generator = False      # True inside whole-step CUDA-graph capture (graph-safe philox state)
         self.timestep = None
 
     # ---- CUDA graphs: the diffusion blocks have static shapes; one capture each for
@@ -112,7 +113,7 @@ class ControlNetScoreDistillation:
     def encode_images(self, images01, eps=None):
         if eps is None:
             eps = torch.randn(images01.shape[0], self.vae.cfg['latent'], images01.shape[2] // 8, images01.shape[3] // 8,
-                              device=images01.device, generator=self.gen)
+                              device=images01.device, generator=None if self.use_default_generator else self.gen)
         if getattr(self, '_g', None):
             return _GraphedVaeEncode.apply(images01, eps, self)
         return M.vae_encode(self.vae, images01, eps)
@@ -131,7 +132,8 @@ class ControlNetScoreDistillation:
         return self.unet.forward(latents_model_input, self.timestep, text_embeddings, down, mid)
 
     def get_timestep(self, batch_size):
-        return torch.randint(self.t_lo, self.t_hi + 1, (batch_size,), device=self.device, generator=self.gen)
+        return torch.randint(self.t_lo, self.t_hi + 1, (batch_size,), device=self.device,
+                             generator=None if self.use_default_generator else self.gen)
 
     def add_noise(self, latents, noise, t):
         a = self.acp[t].reshape(-1, 1, 1, 1)
@@ -146,7 +148,7 @@ class ControlNetScoreDistillation:
         self.timestep = timestep if timestep is not None else self.get_timestep(inputs.shape[0])
         with torch.no_grad():
             if noise is None:
-                noise = torch.randn(latents.shape, device=latents.device, generator=self.gen)
+                noise = torch.randn(latents.shape, device=latents.device, generator=None if self.use_default_generator else self.gen)
             latents_noisy = self.add_noise(latents.detach(), noise, self.timestep)
             neg = text_embeds_dict['neg' if use_negative_text else 'null']
             ctx = torch.cat([neg, text_embeds_dict['text']], dim=0)

@@ -187,19 +187,28 @@ def _kinematic_levels(parents):
     return levels
 
 
+def device_levels(parents, device):
+    """Kinematic levels as device index tensors (built once: no host->device copies per step, which
+    also keeps the chain capturable in a CUDA graph)."""
+    return {'par': torch.as_tensor(parents[1:], device=device),
+            'levels': [(torch.as_tensor(i, device=device), torch.as_tensor(p, device=device)) for i, p in _kinematic_levels(parents)]}
+
+
 def batch_rigid_transform(rot_mats, joints, parents, levels=None):
     """smplx.lbs.batch_rigid_transform; the chain is evaluated level by level (tree depth 10)
     instead of 54 sequential products."""
     B, J = joints.shape[:2]
     rel = joints.clone()
-    par = torch.as_tensor(parents[1:], device=joints.device)
+    if levels is None:
+        levels = device_levels(parents, joints.device)
+    par = levels['par']
     rel[:, 1:] = joints[:, 1:] - joints[:, par]
     M = torch.zeros(B, J, 4, 4, dtype=joints.dtype, device=joints.device)
     M[..., :3, :3] = rot_mats
     M[..., :3, 3] = rel
     M[..., 3, 3] = 1.0
     chain = M.clone()
-    for idx, pidx in (levels or _kinematic_levels(parents)):
+    for idx, pidx in levels['levels']:
         chain[:, idx] = chain[:, pidx] @ M[:, idx]
     posed = chain[..., :3, 3]
     A = chain.clone()
@@ -217,7 +226,7 @@ class GeneralLinearBlendSkinning(nn.Module):
         super().__init__()
         p = lambda k: nn.Parameter(model[k].detach().clone().to(device), requires_grad=False)
         self.parents = list(model['parents'])
-        self._levels = _kinematic_levels(self.parents)
+        self._levels = device_levels(self.parents, device)
         for k in ('betas', 'v_template', 'shapedirs', 'posedirs', 'J_regressor', 'lbs_weights', 'pose_mean',
                   'expr_dirs', 'expression'):
             setattr(self, k, p(k))

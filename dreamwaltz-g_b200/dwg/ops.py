@@ -173,9 +173,26 @@ def _camera_struct(H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_mod
     return cam
 
 
+CAMERA_WORDS = 40          # sizeof(DwgRasterCamera) / 4
+
+
+def pack_camera(H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier=1.0, out=None):
+    """Host-side image of DwgRasterCamera as a float32[40] tensor (int fields bit-cast), for the
+    device-resident camera used by CUDA-graph replays: ``cam_dev.copy_(pack_camera(...))``."""
+    t = torch.empty(CAMERA_WORDS, dtype=torch.float32) if out is None else out
+    ti = t.view(torch.int32)
+    ti[0], ti[1] = int(H), int(W)
+    t[2], t[3] = float(tanfovx), float(tanfovy)
+    t[4:20] = viewmatrix.detach().float().reshape(16).cpu()
+    t[20:36] = projmatrix.detach().float().reshape(16).cpu()
+    t[36:39] = bg.detach().float().reshape(3).cpu()
+    t[39] = float(scale_modifier)
+    return t
+
+
 class RasterState:
     """Workspaces kept between forward and backward (and inspected by the parity tests)."""
-    __slots__ = ('cam', 'N', 'H', 'W', 'P_cap', 'geom', 'bin', 'img', 'status', 'radii')
+    __slots__ = ('cam', 'N', 'H', 'W', 'P_cap', 'geom', 'bin', 'img', 'status', 'radii', 'cam_dev')
 
     def view(self, which, dtype, shape):
         """Typed torch view of an internal buffer (dwg_raster_view)."""
@@ -197,7 +214,7 @@ def default_instance_capacity(N):
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, colors, opacities, scales, rotations, cam_args, state_out):
-        H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier, P_cap = cam_args
+        H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier, P_cap, cam_dev = cam_args
         dev = means3D.device
         means3D, colors, scales, rotations = f32c(means3D), f32c(colors), f32c(scales), f32c(rotations)
         opac = f32c(opacities).reshape(-1)
@@ -207,6 +224,7 @@ class _Rasterize(torch.autograd.Function):
         P_cap = int(P_cap or default_instance_capacity(N))
         st = RasterState()
         st.cam, st.N, st.H, st.W, st.P_cap = cam, N, H, W, P_cap
+        st.cam_dev = cam_dev
         u8 = lambda n: torch.empty(int(n), device=dev, dtype=torch.uint8)
         st.geom = u8(L.dwg_raster_geom_bytes(N))
         st.bin = u8(L.dwg_raster_bin_bytes(P_cap, H, W))
@@ -218,7 +236,7 @@ class _Rasterize(torch.autograd.Function):
         alpha = torch.empty(1, H, W, device=dev, dtype=torch.float32)
         check(L.dwg_raster_forward(ctypes.byref(cam), N, ptr(means3D), ptr(colors), ptr(opac), ptr(scales),
                                    ptr(rotations), ptr(color), ptr(depth), ptr(alpha), ptr(st.radii), ptr(st.geom),
-                                   ptr(st.bin), P_cap, ptr(st.img), ptr(st.status), stream()), 'dwg_raster_forward')
+                                   ptr(st.bin), P_cap, ptr(st.img), ptr(st.status), ptr(cam_dev), stream()), 'dwg_raster_forward')
         ctx.save_for_backward(means3D, colors, opac, scales, rotations)
         ctx.st = st
         ctx.opac_shape = opacities.shape
@@ -242,15 +260,15 @@ class _Rasterize(torch.autograd.Function):
         check(L.dwg_raster_backward(ctypes.byref(st.cam), N, ptr(means3D), ptr(colors), ptr(opac), ptr(scales),
                                     ptr(rotations), ptr(st.geom), ptr(st.bin), st.P_cap, ptr(st.img), ptr(g_color),
                                     ptr(g_depth), ptr(g_alpha), ptr(g_m3), ptr(g_m2), ptr(g_c), ptr(g_o), ptr(g_s),
-                                    ptr(g_r), ptr(scratch), stream()), 'dwg_raster_backward')
+                                    ptr(g_r), ptr(scratch), ptr(st.cam_dev), stream()), 'dwg_raster_backward')
         return g_m3, g_m2, g_c, g_o.reshape(ctx.opac_shape), g_s, g_r, None, None
 
 
 def rasterize(means3D, means2D, colors, opacities, scales, rotations, *, image_height, image_width, tanfovx,
-              tanfovy, viewmatrix, projmatrix, bg, scale_modifier=1.0, instance_capacity=None, state_out=None):
+              tanfovy, viewmatrix, projmatrix, bg, scale_modifier=1.0, instance_capacity=None, state_out=None, cam_dev=None):
     """Differentiable tile rasteriser -> (color [3,H,W], radii i32 [N], depth [1,H,W], alpha [1,H,W])."""
     cam_args = (int(image_height), int(image_width), float(tanfovx), float(tanfovy), viewmatrix, projmatrix, bg,
-                float(scale_modifier), instance_capacity)
+                float(scale_modifier), instance_capacity, cam_dev)
     return _Rasterize.apply(means3D, means2D, colors, opacities, scales, rotations, cam_args, state_out)
 
 

@@ -114,12 +114,15 @@ int64_t dwg_raster_img_bytes(int H, int W);                     /* final_T, n_co
 /* Forward.  colors_precomp [N,3]; opacities [N]; scales [N,3]; rotations [N,4] (w,x,y,z, used
  * unnormalised); outputs out_color [3,H,W], out_depth [H,W], out_alpha [H,W], radii i32 [N].
  * geom/bin/img are caller workspaces of the sizes above (kept for the backward).
- * status: i32[4] device words {overflow flag, P (num_rendered), max tile load, reserved}. */
+ * status: i32[4] device words {overflow flag, P (num_rendered), max tile load, reserved}.
+ * cam_dev: NULL, or a DEVICE copy of the camera struct that overrides the matrices / tanfov / bg of
+ * `cam` (same image size): lets a captured CUDA graph be replayed with a new camera. */
 int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N,
                        const float* means3D, const float* colors_precomp, const float* opacities,
                        const float* scales, const float* rotations,
                        float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
-                       void* geom, void* bin, int64_t P_cap, void* img, int32_t* status, void* stream);
+                       void* geom, void* bin, int64_t P_cap, void* img, int32_t* status,
+                       const void* cam_dev, void* stream);
 /* Backward.  dL_dcolor [3,H,W], dL_ddepth [H,W] or NULL, dL_dalpha [H,W] or NULL ->
  * g_means3D [N,3], g_means2D [N,3] (z = 0), g_colors [N,3], g_opacities [N], g_scales [N,3],
  * g_rotations [N,4].  All outputs are fully written (no pre-zeroing needed); `scratch` must
@@ -131,7 +134,7 @@ int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N,
                         const void* geom, const void* bin, int64_t P_cap, const void* img,
                         const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                         float* g_means3D, float* g_means2D, float* g_colors, float* g_opacities,
-                        float* g_scales, float* g_rotations, void* scratch, void* stream);
+                        float* g_scales, float* g_rotations, void* scratch, const void* cam_dev, void* stream);
 /* Debug / parity views into the workspaces (device pointers into geom / bin / img):
  * which = 0 xy f32[N,2] | 1 depth f32[N] | 2 cov3D f32[N,6] | 3 conic_opacity f32[N,4]
  *       | 4 rect i32[N,4] | 5 tiles_touched u32[N] | 6 tile ranges u32[tiles,2]
