@@ -8,14 +8,21 @@
 //     for every filter tap the A tile is fetched by a 4-D TMA box at the shifted pixel
 //     coordinates; TMA zero-fills out-of-bounds pixels (= padding) and channels (= K tail), and
 //     its element strides implement stride-2 convolutions.
-// Structure (Blackwell-native, see blackwell_cuda_programming.md "Anatomy"):
-//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
-//   warp 1   : MMA issuer     (one elected lane: tcgen05.mma.cta_group::1.kind::f16, M=128,
-//                              N=BN, K=16 per instruction; tcgen05.commit frees smem stages)
-//   warp 2   : TMEM allocator (BN fp32 accumulator columns)
-//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> bias / time-embedding /
-//                              residual / activation / scale -> bf16 or fp32 global stores)
-// fp32 accumulators never touch registers during the main loop.
+// Structure (v3):
+//   warp 0    : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1    : MMA issuer     (one elected lane: tcgen05.mma.cta_group::1.kind::f16, M=128,
+//                               N = BN (run-time, any multiple of 32 up to 256), K=16)
+//   warp 2    : TMEM allocator (2 accumulator stages x 256 fp32 columns)
+//   warps 4-11: epilogue       two warps per TMEM lane quadrant, alternating 32-column chunks:
+//                               tcgen05.ld -> bias / time-embedding / activation / GEGLU ->
+//                               (+ residual chunk fetched by TMA into smem) -> swizzled smem
+//                               staging -> TMA store (cp.async.bulk.tensor ... global.shared).
+//                               TMA clips the M / N tails, so the fast path has no masks.
+//   split-K   : the CTAs of one output tile write fp32 partial tiles (coalesced, tile-private
+//               layout) and bump a per-tile counter; the LAST arriver adds the other partials to
+//               its own TMEM accumulator and runs the normal epilogue -- no finalize kernel.
+// The epilogue body is deliberately compact (no unrolling over chunks, one instantiation per
+// output kind): v2's 265 KB of SASS made short kernels instruction-fetch bound (ncu: stall_no_inst).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -27,9 +34,14 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;              // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kMaxStages = 8;
+constexpr uint32_t A_BYTES = BM * BK * 2;
+constexpr int TMEM_STAGE_COLS = 256;
 
 enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };   // GEGLU: columns are (value, gate) pairs -> N/2 outputs
+enum Epi { EPI_BF16 = 0, EPI_F32 = 1, EPI_GEGLU = 2 };
 
 struct Params {
     // problem
@@ -37,29 +49,29 @@ struct Params {
     int taps_w, taps_h;             // 1,1 for plain GEMM
     int k_chunks;                   // ceil(K / 64)
     uint32_t a_bytes;               // bytes one A-tile TMA delivers (the box may hold < 128 rows for tiny images)
-    // batching (plain GEMM): z = blockIdx.z -> (z % nb1, z / nb1)
-    int nb1;
-    // conv geometry (taps > 1 or conv_mode)
+    int nb1;                        // batching (plain GEMM): z -> (z % nb1, z / nb1)
+    // conv geometry
     int conv_mode;
-    int Ho, Wo, BH, BW, BNI;        // output size and the pixel box of one 128-row tile
-    int tiles_w, tiles_h;           // tiles along w / h per image group
+    int Ho, Wo, BH, BW, BNI, Nimg;  // output size and the pixel box of one 128-row tile
+    int tiles_w, tiles_h;
     int stride, pad_h, pad_w;
-    // output
-    void* C;
-    int out_bf16;
-    int64_t ldc, c_b1, c_b2;        // element strides of C (row, batch dims)
+    int ebw, ebh;                   // pixel box (w, h extent) of ONE epilogue warp's 32 rows
     // epilogue
     const float* bias;              // [N] or null
     const float* bias2;             // [rows_b2][N] per-image bias (time embedding) or null
-    int bias2_rows_per;             // rows (pixels) per bias2 row
-    const __nv_bfloat16* residual;  // same layout as C (bf16) or null
-    int64_t ldr, r_b1, r_b2;
-    float alpha;                    // scale applied to the accumulator before bias
+    int bias2_rows_per;
+    int has_res;                    // residual fetched through tmR (bf16, same geometry as C)
+    float alpha;
     int act;
-    // persistent tile scheduler
+    // slow path (unaligned output / residual strides): direct per-thread stores
+    int direct;
+    void* C; int64_t ldc, c_b1, c_b2;
+    const __nv_bfloat16* residual; int64_t ldr, r_b1, r_b2;
+    // tiling
+    int BN, stages;
     int m_tiles, n_tiles, nz, ksplit, total_tiles;
-    float* workspace;               // [ksplit][rows_total][N] fp32 partial sums when ksplit > 1
-    int64_t ws_slice;               // rows_total * N
+    float* workspace;               // split-K partial tiles
+    int* counters;                  // one per output tile, self-resetting
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,6 +102,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -100,16 +121,19 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
                  "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
 }
 
 // K-major, 128B-swizzled operand tile [rows][64 bf16]: 8-row groups are 1024 B apart (SBO),
@@ -124,10 +148,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-    if (act == ACT_SILU) return x / (1.0f + __expf(-x));
-    if (act == ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
-    return x;
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// exact-erf GELU (diffusers GEGLU / F.gelu default) with erf from Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, far below the bf16 output rounding): one rcp + one ex2 instead of erff's
+// ~40-instruction branchy expansion.
+__device__ __forceinline__ float gelu_f(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
 struct TileCoord { int m_tile, n_tile, z, ks; };
@@ -140,23 +173,34 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
     return c;
 }
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // Persistent, warp-specialised: the CTA walks tiles blockIdx.x, +gridDim.x, ...; the smem ring and
 // the two TMEM accumulator stages let the TMA / MMA of tile i+1 overlap the epilogue of tile i.
-template <int BN, int STAGES>
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+            const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-    constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    constexpr int ACC_PER_CHUNK = (EPI == EPI_GEGLU) ? 64 : 32;        // accumulator columns per epilogue chunk (-> 32 outputs)
+    constexpr uint32_t STG_BYTES = (EPI == EPI_F32) ? 4096 : 2048;     // 32 rows x 32 outputs
+    const uint32_t B_BYTES = (uint32_t)p.BN * (BK * 2);
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;          // [2]
-    uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [BN]
+    uint8_t* sB = sA + p.stages * A_BYTES;
+    uint8_t* sStage = sB + p.stages * B_BYTES;                         // [kEpiWarps][2][STG_BYTES]
+    uint8_t* sRes = sStage + kEpiWarps * 2 * STG_BYTES;                // [kEpiWarps][2][2048] (only when has_res)
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.has_res ? kEpiWarps * 2 * 2048 : 0));
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tmem_full = empty + kMaxStages;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;              // [2]
+    uint64_t* res_bar = tmem_empty + 2;                // [kEpiWarps][2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+    volatile int* s_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5;
     const int iters_total = p.taps_h * p.taps_w * p.k_chunks;
@@ -164,14 +208,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmC) : "memory");
+        if (p.has_res) asm volatile("prefetch.tensormap [%0];" :: "l"(&tmR) : "memory");
     }
     if (warp == 1 && elect_one()) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
+        for (int i = 0; i < 2 * kEpiWarps; i++) mbar_init(&res_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(2 * TMEM_STAGE_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -189,7 +236,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (warp == 0) {
         if (elect_one()) {
-            uint32_t ring = 0;
+            uint32_t s = 0, ph = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(p, t);
                 int a_c1, a_c2, a_c3, b1 = 0, b2 = 0;
@@ -206,27 +253,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 int it0, it1;
                 it_range(tc.ks, it0, it1);
-                for (int it = it0; it < it1; it++, ring++) {
-                    const int s = ring % STAGES;
-                    const uint32_t ph = (ring / STAGES) & 1u;
+                int kc = it0 % p.k_chunks, tap = it0 / p.k_chunks;
+                for (int it = it0; it < it1; it++) {
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_expect_tx(&full[s], p.a_bytes + B_BYTES);
-                    const int kc = it % p.k_chunks;
-                    const int tap = it / p.k_chunks;
                     if (p.conv_mode) {
                         const int kw = tap % p.taps_w, kh = tap / p.taps_w;
                         tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1 + kw, a_c2 + kh, a_c3);
-                        tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, tc.n_tile * BN, 0);
+                        tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, tc.n_tile * p.BN, 0);
                     } else {
                         tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1, a_c2, a_c3);
-                        tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tc.n_tile * BN, b1, b2);
+                        tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tc.n_tile * p.BN, b1, b2);
                     }
+                    if (++kc == p.k_chunks) { kc = 0; tap++; }
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        uint32_t ring = 0, tl = 0;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        uint32_t s = 0, ph = 0, tl = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, tl++) {
             const TileCoord tc = decode_tile(p, t);
             int it0, it1;
@@ -234,10 +280,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t as = tl & 1u;
             mbar_wait(&tmem_empty[as], ((tl >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator stage
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * BN;
-            for (int it = it0; it < it1; it++, ring++) {
-                const int s = ring % STAGES;
-                const uint32_t ph = (ring / STAGES) & 1u;
+            const uint32_t tmem_d = tmem_base + as * TMEM_STAGE_COLS;
+            for (int it = it0; it < it1; it++) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 if (elect_one()) {
@@ -250,206 +294,253 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (it == it1 - 1) tc_commit(&tmem_full[as]);
                 }
                 __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;
+        const int e = warp - 4;                             // 0..7
+        const int q = warp & 3;                             // TMEM lane quadrant this warp may read
+        const int half = e >> 2;                            // which chunks of the tile (even / odd)
         const int lane = threadIdx.x & 31;
-        const int r = q * 32 + lane;
-        const int et = threadIdx.x - 128;                   // 0..127 among the epilogue threads
-        uint32_t tl = 0;
-        // vector fast path: 16-byte aligned rows for the residual / output
-        const bool res_vec = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && (p.ldr % 8 == 0) &&
-                             (p.r_b1 % 8 == 0) && (p.r_b2 % 8 == 0);
+        uint8_t* stg = sStage + e * 2 * STG_BYTES;
+        uint8_t* rsm = sRes + e * 2 * 2048;
+        uint64_t* rbar = res_bar + e * 2;
+        const int nchunks = p.BN / ACC_PER_CHUNK;
+        uint32_t tl = 0, slot = 0, rph = 0;                 // slot: running chunk counter (buffer = slot & 1); rph: phase bits of rbar[0..1]
+        // swizzled 16-byte-chunk offsets of this thread's staging row
+        const uint32_t row_off = (EPI == EPI_F32) ? (uint32_t)lane * 128u : (uint32_t)lane * 64u;
+        const uint32_t sw = (EPI == EPI_F32) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+        const uint32_t rsw = (uint32_t)((lane >> 1) & 3);   // residual rows are always bf16 (64 B, SWIZZLE_64B)
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, tl++) {
             const TileCoord tc = decode_tile(p, t);
             const uint32_t as = tl & 1u;
-            int64_t c_off, r_off = 0, b2row = 0, ws_off = 0;
-            bool row_ok;
+            const int r0 = q * 32;
+            int c1, c2, c3;
+            bool box_ok;
+            int64_t b2row = 0, d_row = 0, d_res = 0;       // bias2 row; direct-path row offsets
+            bool row_ok = true;
             if (p.conv_mode) {
                 const int tw = tc.m_tile % p.tiles_w;
                 const int th = (tc.m_tile / p.tiles_w) % p.tiles_h;
                 const int tn = tc.m_tile / (p.tiles_w * p.tiles_h);
-                const int w = tw * p.BW + (r % p.BW);
-                const int h = th * p.BH + (r / p.BW) % p.BH;
-                const int n = tn * p.BNI + r / (p.BW * p.BH);
-                row_ok = (w < p.Wo) && (h < p.Ho) && ((int64_t)n * p.Ho * p.Wo < (int64_t)p.M) && (r < p.BW * p.BH * p.BNI);
+                c1 = tw * p.BW + (r0 % p.BW);
+                c2 = th * p.BH + (r0 / p.BW) % p.BH;
+                c3 = tn * p.BNI + r0 / (p.BW * p.BH);
+                box_ok = (c1 < p.Wo) && (c2 < p.Ho) && (c3 < p.Nimg) && (r0 < p.BW * p.BH * p.BNI);
+                const int w = c1 + lane % p.ebw, h = c2 + (lane / p.ebw) % p.ebh, n = c3 + lane / (p.ebw * p.ebh);
+                row_ok = box_ok && (w < p.Wo) && (h < p.Ho) && (n < p.Nimg);
                 const int64_t pix = ((int64_t)n * p.Ho + h) * p.Wo + w;
-                c_off = pix * p.ldc;
-                r_off = pix * p.ldr;
-                ws_off = pix * p.N;
-                b2row = p.bias2_rows_per > 0 ? pix / p.bias2_rows_per : 0;
+                b2row = n;
+                d_row = pix * p.ldc; d_res = pix * p.ldr;
             } else {
-                const int b1 = tc.z % p.nb1, b2 = tc.z / p.nb1;
-                const int64_t m = (int64_t)tc.m_tile * BM + r;
+                c1 = tc.m_tile * BM + r0; c2 = tc.z % p.nb1; c3 = tc.z / p.nb1;
+                box_ok = c1 < p.M;
+                const int64_t m = c1 + lane;
                 row_ok = m < p.M;
-                c_off = (int64_t)b1 * p.c_b1 + (int64_t)b2 * p.c_b2 + m * p.ldc;
-                r_off = (int64_t)b1 * p.r_b1 + (int64_t)b2 * p.r_b2 + m * p.ldr;
-                ws_off = ((int64_t)tc.z * p.M + m) * p.N;
                 b2row = p.bias2_rows_per > 0 ? m / p.bias2_rows_per : 0;
+                d_row = (int64_t)c2 * p.c_b1 + (int64_t)c3 * p.c_b2 + m * p.ldc;
+                d_res = (int64_t)c2 * p.r_b1 + (int64_t)c3 * p.r_b2 + m * p.ldr;
             }
-            const int ntile0 = tc.n_tile * BN;
-            // ---- stage the bias slice of this tile in shared memory; prefetch the whole residual
-            // row into registers BEFORE waiting for the accumulator (overlaps the MMA main loop)
-            asm volatile("bar.sync 1, 128;" ::: "memory");           // previous tile's readers are done
-            for (int c = et; c < BN; c += 128) {
-                const int n = ntile0 + c;
-                s_bias[c] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+            const int ntile0 = tc.n_tile * p.BN;
+            const int otile0 = (EPI == EPI_GEGLU) ? (ntile0 >> 1) : ntile0;      // first OUTPUT column of the tile
+            const bool use_res = p.has_res && box_ok && !p.direct;
+            // residual chunk of this warp's first chunk: in flight while the MMA main loop runs
+            if (use_res && half < nchunks && lane == 0 && (p.ksplit == 1)) {
+                const uint32_t b = slot & 1u;
+                mbar_expect_tx(&rbar[b], 2048);
+                tma_load_4d(rsm + b * 2048, &tmR, &rbar[b], otile0 + half * 32, c1, c2, c3);
             }
-            uint4 rr[BN / 8];
-            const bool use_res_vec = res_vec && row_ok && p.ksplit == 1;
-            if (use_res_vec) {
-#pragma unroll
-                for (int i = 0; i < BN / 8; i++) {
-                    const int n = ntile0 + i * 8;
-                    rr[i] = (n + 8 <= p.N) ? *reinterpret_cast<const uint4*>(p.residual + r_off + n) : make_uint4(0, 0, 0, 0);
-                }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tmem_full[as], (tl >> 1) & 1u);
             tc_fence_after();
-            const uint32_t taddr_row = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr_row = tmem_base + as * TMEM_STAGE_COLS + ((uint32_t)(q * 32) << 16);
+
+            bool released = false;
+            if (p.ksplit > 1) {
+                // ---- split-K: publish this CTA's partial tile, find out whether we are the last arriver
+                const int out_tile = (tc.z * p.n_tiles + tc.n_tile) * p.m_tiles + tc.m_tile;
+                const int acc_chunks = p.BN / 32;
+                float4* wsp = reinterpret_cast<float4*>(p.workspace) + ((int64_t)out_tile * p.ksplit + tc.ks) * acc_chunks * (8 * 128);
+#pragma unroll 1
+                for (int c = half; c < acc_chunks; c += 2) {
+                    float v[32];
+                    tc_ld32(taddr_row + (uint32_t)(c * 32), v);
+                    float4* dst = wsp + (int64_t)c * (8 * 128) + r0 + lane;
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tc_ld32(taddr_row + (uint32_t)c0, v);
-                if (c0 + 32 >= BN) {                       // last TMEM read of this tile: release the accumulator stage
+                    for (int j = 0; j < 8; j++) dst[j * 128] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");
+                if (e == 0 && lane == 0) {
+                    const int old = atomicAdd(&p.counters[out_tile], 1);
+                    const int last = (old == p.ksplit - 1);
+                    if (last) p.counters[out_tile] = 0;             // self-reset for the next launch
+                    __threadfence();
+                    *s_flag = last;
+                }
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");
+                const int last = *s_flag;
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");      // everyone has read the flag before the next tile rewrites it
+                if (!last) {
                     tc_fence_before();
-                    mbar_arrive(&tmem_empty[as]);
-                }
-                const int ncol0 = ntile0 + c0;
-                if (!row_ok || ncol0 >= p.N) continue;
-                const int nvalid = min(32, p.N - ncol0);
-                if (p.ksplit > 1) {
-                    // partial sums go to their own slice (no atomics, no memset); splitk_finalize adds the slices
-                    float* ws = p.workspace + (int64_t)tc.ks * p.ws_slice + ws_off + ncol0;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(ws) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(ws + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                    } else {
-                        for (int j = 0; j < nvalid; j++) ws[j] = __uint_as_float(v[j]);
-                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[as]);
                     continue;
                 }
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) * p.alpha + s_bias[c0 + j];
-                if (p.bias2) {
-                    const float* b2p = p.bias2 + b2row * p.N + ncol0;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(b2p) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(b2p + j));
-                            f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
-                        }
-                    } else {
-                        for (int j = 0; j < nvalid; j++) f[j] += b2p[j];
-                    }
-                }
-                if (p.act == ACT_GEGLU) {
-                    // fused GEGLU (diffusers GEGLU: hidden * gelu(gate)); weight rows were interleaved at load time
-                    float gl[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) gl[j] = f[2 * j] * apply_act(f[2 * j + 1], ACT_GELU);
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + (ncol0 >> 1);
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(gl[j], gl[j + 1]), h1 = __floats2bfloat162_rn(gl[j + 2], gl[j + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(gl[j + 4], gl[j + 5]), h3 = __floats2bfloat162_rn(gl[j + 6], gl[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(dst + j) = pk;
-                        }
-                    } else {
-                        for (int j = 0; j < nvalid / 2; j++) dst[j] = __float2bfloat16(gl[j]);
-                    }
-                    continue;
-                }
-                if (p.act != ACT_NONE) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) f[j] = apply_act(f[j], p.act);
-                }
-                if (p.residual) {
-                    if (use_res_vec && nvalid == 32) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const uint4 u = rr[c0 / 8 + i];
-                            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
-                                f[i * 8 + 2 * k] += t2.x; f[i * 8 + 2 * k + 1] += t2.y;
-                            }
-                        }
-                    } else {
-                        for (int j = 0; j < nvalid; j++) f[j] += __bfloat162float(p.residual[r_off + ncol0 + j]);
-                    }
-                }
-                if (p.out_bf16) {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + ncol0;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(dst + j) = pk;
-                        }
-                    } else {
-                        for (int j = 0; j < nvalid; j++) dst[j] = __float2bfloat16(f[j]);
-                    }
-                } else {
-                    float* dst = reinterpret_cast<float*>(p.C) + c_off + ncol0;
-                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-                        for (int j = 0; j < nvalid; j++) dst[j] = f[j];
-                    }
+                if (use_res && half < nchunks && lane == 0) {
+                    const uint32_t b = slot & 1u;
+                    mbar_expect_tx(&rbar[b], 2048);
+                    tma_load_4d(rsm + b * 2048, &tmR, &rbar[b], otile0 + half * 32, c1, c2, c3);
                 }
             }
+
+#pragma unroll 1
+            for (int c = half; c < nchunks; c += 2, slot++) {
+                const uint32_t b = slot & 1u;
+                // prefetch the residual of this warp's NEXT chunk of the tile (its buffer was consumed one chunk ago)
+                if (use_res && c + 2 < nchunks && lane == 0) {
+                    const uint32_t nb = b ^ 1u;
+                    mbar_expect_tx(&rbar[nb], 2048);
+                    tma_load_4d(rsm + nb * 2048, &tmR, &rbar[nb], otile0 + (c + 2) * 32, c1, c2, c3);
+                }
+                float f[32];
+                const int acol0 = c * ACC_PER_CHUNK;                    // accumulator column of the chunk inside the tile
+                const int ocol0 = otile0 + c * 32;                      // output column
+                if (EPI == EPI_GEGLU) {
+                    float v[32], g[32];
+                    tc_ld32(taddr_row + (uint32_t)acol0, v);
+                    tc_ld32(taddr_row + (uint32_t)(acol0 + 32), g);
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + ntile0 + acol0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (p.bias) { b0 = __ldg(bp + j); b1 = __ldg(bp + 8 + j); }
+                        // (value, gate) pairs are interleaved along N
+                        f[2 * j] = fmaf(v[4 * j], p.alpha, b0.x) * gelu_f(fmaf(v[4 * j + 1], p.alpha, b0.y));
+                        f[2 * j + 1] = fmaf(v[4 * j + 2], p.alpha, b0.z) * gelu_f(fmaf(v[4 * j + 3], p.alpha, b0.w));
+                        f[16 + 2 * j] = fmaf(g[4 * j], p.alpha, b1.x) * gelu_f(fmaf(g[4 * j + 1], p.alpha, b1.y));
+                        f[16 + 2 * j + 1] = fmaf(g[4 * j + 2], p.alpha, b1.z) * gelu_f(fmaf(g[4 * j + 3], p.alpha, b1.w));
+                    }
+                } else {
+                    tc_ld32(taddr_row + (uint32_t)acol0, f);
+                    if (p.ksplit > 1) {
+                        // last arriver: add the other splits' partial tiles (L2-resident, written by other SMs -> ld.cg)
+                        const int out_tile = (tc.z * p.n_tiles + tc.n_tile) * p.m_tiles + tc.m_tile;
+                        const int acc_chunks = p.BN / 32;
+                        for (int k = 0; k < p.ksplit; k++) {
+                            if (k == tc.ks) continue;
+                            const float4* src = reinterpret_cast<const float4*>(p.workspace) +
+                                                (((int64_t)out_tile * p.ksplit + k) * acc_chunks + c) * (8 * 128) + r0 + lane;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float4 u = __ldcg(src + j * 128);
+                                f[4 * j] += u.x; f[4 * j + 1] += u.y; f[4 * j + 2] += u.z; f[4 * j + 3] += u.w;
+                            }
+                        }
+                    }
+                    const bool full_chunk = (ocol0 + 32 <= p.N) && !p.direct;
+                    if (full_chunk) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + ocol0);
+                        const float4* b2p = reinterpret_cast<const float4*>(p.bias2 + b2row * p.N + ocol0);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias) bb = __ldg(bp + j);
+                            if (p.bias2) { const float4 t2 = __ldg(b2p + j); bb.x += t2.x; bb.y += t2.y; bb.z += t2.z; bb.w += t2.w; }
+                            f[4 * j] = fmaf(f[4 * j], p.alpha, bb.x); f[4 * j + 1] = fmaf(f[4 * j + 1], p.alpha, bb.y);
+                            f[4 * j + 2] = fmaf(f[4 * j + 2], p.alpha, bb.z); f[4 * j + 3] = fmaf(f[4 * j + 3], p.alpha, bb.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int n = ocol0 + j;
+                            float bb = 0.f;
+                            if (n < p.N) {
+                                if (p.bias) bb = p.bias[n];
+                                if (p.bias2) bb += p.bias2[b2row * p.N + n];
+                            }
+                            f[j] = fmaf(f[j], p.alpha, bb);
+                        }
+                    }
+                    if (p.act == ACT_SILU) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = silu_f(f[j]);
+                    } else if (p.act == ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = gelu_f(f[j]);
+                    }
+                }
+                if (c + 2 >= nchunks && !released) {       // last TMEM read of this warp for the tile: release the accumulator stage
+                    released = true;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                }
+                if (p.direct) {
+                    // ---- slow path: unaligned strides; masked per-thread stores
+                    if (row_ok) {
+                        const int nvalid = min(32, ((EPI == EPI_GEGLU) ? (p.N >> 1) : p.N) - ocol0);
+                        for (int j = 0; j < nvalid; j++) {
+                            float x = f[j];
+                            if (p.residual) x += __bfloat162float(p.residual[d_res + ocol0 + j]);
+                            if (EPI == EPI_F32) reinterpret_cast<float*>(p.C)[d_row + ocol0 + j] = x;
+                            else reinterpret_cast<__nv_bfloat16*>(p.C)[d_row + ocol0 + j] = __float2bfloat16(x);
+                        }
+                    }
+                    continue;
+                }
+                if (!box_ok) continue;
+                if (use_res) {
+                    mbar_wait(&rbar[b], (rph >> b) & 1u);
+                    rph ^= (1u << b);
+                    const uint8_t* rrow = rsm + b * 2048 + lane * 64;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((j ^ rsw) << 4));
+                        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+                            f[8 * j + 2 * k] += t2.x; f[8 * j + 2 * k + 1] += t2.y;
+                        }
+                    }
+                }
+                // staging buffer b was last read by the TMA store issued two chunks ago
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+                uint8_t* srow = stg + b * STG_BYTES + row_off;
+                if (EPI == EPI_F32) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<float4*>(srow + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint4 pk;
+                        pk.x = pack_bf16(f[8 * j], f[8 * j + 1]); pk.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+                        pk.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]); pk.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = pk;
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&tmC, stg + b * STG_BYTES, ocol0, c1, c2, c3);
+                    bulk_commit();
+                }
+            }
+            if (!released) {                                 // warps with no chunk in this tile (BN == 32, half == 1)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            }
         }
+        if (lane == 0) bulk_wait_all();                      // smem must stay valid until the last TMA store has read it
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TMEM_COLS));
-    }
-}
-
-// split-K finalize: out = act(alpha * ws + bias + bias2) + residual
-__global__ void __launch_bounds__(256)
-splitk_finalize_kernel(const Params p, int64_t rows_total) {
-    const int64_t total = rows_total * p.N;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / p.N;
-        const int n = (int)(i - row * p.N);
-        int64_t c_off, r_off, b2row;
-        if (p.conv_mode) {
-            c_off = row * p.ldc; r_off = row * p.ldr;
-            b2row = p.bias2_rows_per > 0 ? row / p.bias2_rows_per : 0;
-        } else {
-            const int64_t z = row / p.M, m = row - z * p.M;
-            const int b1 = (int)(z % p.nb1), b2 = (int)(z / p.nb1);
-            c_off = (int64_t)b1 * p.c_b1 + (int64_t)b2 * p.c_b2 + m * p.ldc;
-            r_off = (int64_t)b1 * p.r_b1 + (int64_t)b2 * p.r_b2 + m * p.ldr;
-            b2row = p.bias2_rows_per > 0 ? m / p.bias2_rows_per : 0;
-        }
-        float acc = 0.f;
-        for (int k = 0; k < p.ksplit; k++) acc += p.workspace[(int64_t)k * p.ws_slice + i];
-        float x = acc * p.alpha;
-        if (p.bias) x += p.bias[n];
-        if (p.bias2) x += p.bias2[b2row * p.N + n];
-        x = apply_act(x, p.act);
-        if (p.residual) x += __bfloat162float(p.residual[r_off + n]);
-        if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[c_off + n] = __float2bfloat16(x);
-        else reinterpret_cast<float*>(p.C)[c_off + n] = x;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * TMEM_STAGE_COLS));
     }
 }
 
@@ -469,17 +560,17 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 4-D bf16 tensor map: dims (innermost first), byte strides for dims 1..3, box, element strides
-static int make_map(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                    const uint32_t box[4], const uint32_t estr[4]) {
+// 4-D tensor map: dims (innermost first), byte strides for dims 1..3, box, element strides
+static int make_map(CUtensorMap* m, CUtensorMapDataType dt, CUtensorMapSwizzle swz, const void* base, const uint64_t dims[4],
+                    const uint64_t strides_bytes[3], const uint32_t box[4], const uint32_t estr[4]) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return DWG_ERR_CUDA; }
     cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
     cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
     cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
     cuuint32_t e[4] = {estr[0], estr[1], estr[2], estr[3]};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, dt, 4, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u,%u,%u)", (int)r,
                   (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)d[2], (unsigned long long)d[3],
@@ -488,64 +579,99 @@ static int make_map(CUtensorMap* m, const void* base, const uint64_t dims[4], co
     }
     return DWG_OK;
 }
+static int make_map_bf16(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                         const uint32_t box[4], const uint32_t estr[4]) {
+    return make_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, base, dims, strides_bytes, box, estr);
+}
 
 static int g_num_sms = 0;
-static float* g_ws = nullptr;            // split-K workspace (grown on demand, never shrunk)
+static float* g_ws = nullptr;            // split-K partial tiles (grown on demand, never shrunk)
 static size_t g_ws_bytes = 0;
+static int* g_counters = nullptr;        // split-K arrival counters (zero when idle)
+constexpr int kMaxCounters = 1 << 16;
+constexpr size_t kSmemBudget = 232448 - 1024;       // opt-in maximum minus the 1024-byte alignment slack
 
-template <int BN, int STAGES>
-static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, Params& p, int64_t rows_total, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+static size_t smem_fixed(int epi, int has_res) {
+    const size_t stg = (epi == EPI_F32) ? 4096 : 2048;
+    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + (2 * kMaxStages + 4 + 2 * kEpiWarps) * 8 + 64;
+}
+
+// Tile / split selection: a small analytic model of one CTA's critical path, in SM cycles.
+//   k-iteration = max(tensor pipe 2*BN, smem operand read 128 + BN, L2->SM feed of the CTAs running together)
+//   tile        = k-iterations + epilogue (TMEM drain + math + staging, two warps per lane quadrant)
+struct Plan { int BN, ks, stages; };
+static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats) {
+    const int gran = (epi == EPI_GEGLU) ? 64 : 32;
+    Plan best = {gran, 1, 2};
+    double best_t = 1e30;
+    const size_t fixed = smem_fixed(epi, has_res);
+    for (int BN = gran; BN <= 256; BN += gran) {
+        const int n_tiles = (N + BN - 1) / BN;
+        const size_t stage_bytes = A_BYTES + (size_t)BN * 128;
+        int stages = (int)((kSmemBudget - fixed) / stage_bytes);
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages < 2) continue;
+        const int64_t tiles = (int64_t)m_tiles * n_tiles * nz;
+        for (int ks = 1; ks <= 16; ks++) {
+            if (ks > 1 && (epi == EPI_GEGLU || iters / ks < 2 || tiles * ks > 2 * g_num_sms)) break;
+            if (ks > 1 && (tiles > kMaxCounters || tiles * ks * 128 * (int64_t)BN > ws_cap_floats)) break;
+            const int64_t ctas = tiles * ks;
+            const double active = (double)(ctas < g_num_sms ? ctas : g_num_sms);
+            const double feed = (double)stage_bytes * active / 6000.0;          // ~6.3 KB/cycle chip-wide TMA throughput
+            double t_iter = 2.0 * BN;
+            if (128.0 + BN > t_iter) t_iter = 128.0 + BN;
+            if (feed > t_iter) t_iter = feed;
+            const double k_iters = (double)((iters + ks - 1) / ks);
+            const double t_main = k_iters * t_iter;
+            const double epi_cols = (epi == EPI_GEGLU) ? 14.0 : 7.0;            // cycles per accumulator column per warp pair
+            const double t_epi = 300.0 + BN * epi_cols + (has_res ? 200.0 : 0.0);
+            const double waves = (double)((ctas + g_num_sms - 1) / g_num_sms);
+            double t_tile = t_main > t_epi ? t_main : t_epi;                    // steady state of a persistent CTA
+            double t = 2500.0 + 1500.0 /* first TMA */ + (waves - 1.0) * t_tile + t_main + t_epi;
+            if (ks > 1) t += 1200.0 + (ks - 1) * BN * 6.0;                      // partial write + counter + reading the other partials
+            if (t < best_t) { best_t = t; best = {BN, ks, stages}; }
+        }
     }
+    return best;
+}
+
+template <int EPI>
+static void set_smem_attr() {
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024));
+        done = true;
+    }
+}
+
+static int ensure_globals() {
     if (!g_num_sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms <= 0) g_num_sms = kNumSMs;
     }
-    p.n_tiles = (p.N + BN - 1) / BN;
-    const int iters = p.taps_h * p.taps_w * p.k_chunks;
-    const int64_t base_tiles = (int64_t)p.m_tiles * p.n_tiles * p.nz;
-    // split-K when the tile count cannot fill the machine and the K loop is long
-    int ks = 1;
-    if (base_tiles * 2 <= g_num_sms && iters >= 8 && p.act != ACT_GEGLU) {
-        ks = (int)(g_num_sms / base_tiles);
-        if (ks > iters / 2) ks = iters / 2;
-        if (ks > 16) ks = 16;
-        if (ks < 1) ks = 1;
+    if (!g_counters) {
+        // NOTE: allocated outside of stream capture (the first, un-captured warm-up call creates it)
+        if (cudaMalloc(&g_counters, sizeof(int) * kMaxCounters) != cudaSuccess) { g_counters = nullptr; set_error("split-K counter allocation failed"); return DWG_ERR_CUDA; }
+        cudaMemset(g_counters, 0, sizeof(int) * kMaxCounters);
+        g_ws_bytes = (size_t)64 << 20;
+        if (cudaMalloc(&g_ws, g_ws_bytes) != cudaSuccess) { g_ws = nullptr; g_ws_bytes = 0; set_error("split-K workspace allocation failed"); return DWG_ERR_CUDA; }
     }
-    p.ksplit = ks;
-    p.total_tiles = (int)(base_tiles * ks);
-    if (ks > 1) {
-        const size_t need = sizeof(float) * (size_t)rows_total * p.N * ks;
-        p.ws_slice = rows_total * (int64_t)p.N;
-        if (need > g_ws_bytes) {
-            // NOTE: grows outside of stream capture only (warm-up pass sizes it); see DESIGN.md
-            if (g_ws) cudaFree(g_ws);
-            if (cudaMalloc(&g_ws, need) != cudaSuccess) { g_ws = nullptr; g_ws_bytes = 0; set_error("split-K workspace allocation failed"); return DWG_ERR_CUDA; }
-            g_ws_bytes = need;
-        }
-        p.workspace = g_ws;
-    }
+    return DWG_OK;
+}
+
+static int launch(const CUtensorMap& tmA, CUtensorMap& tmB_out, const CUtensorMap& tmC, const CUtensorMap& tmR, Params& p, int epi, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)p.stages * (A_BYTES + (size_t)p.BN * 128) + smem_fixed(epi, p.has_res);
     const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-    launch_pdl(gemm_kernel<BN, STAGES>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB, p);
-    if (ks > 1) {
-        const int64_t total = rows_total * p.N;
-        int64_t g = (total + 255) / 256;
-        if (g > 4 * g_num_sms) g = 4 * g_num_sms;
-        splitk_finalize_kernel<<<(unsigned)g, 256, 0, st>>>(p, rows_total);
-    }
+    if (epi == EPI_BF16) { set_smem_attr<EPI_BF16>(); launch_pdl(gemm_kernel<EPI_BF16>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB_out, tmC, tmR, p); }
+    else if (epi == EPI_F32) { set_smem_attr<EPI_F32>(); launch_pdl(gemm_kernel<EPI_F32>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB_out, tmC, tmR, p); }
+    else { set_smem_attr<EPI_GEGLU>(); launch_pdl(gemm_kernel<EPI_GEGLU>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB_out, tmC, tmR, p); }
     return check_launch("tcgen05 gemm");
 }
 
-static int pick_bn(int N) {
-    if (N <= 64) return 64;
-    if (N % 256 == 0 || N >= 1024) return 256;
-    return 128;
+static bool aligned16(const void* ptr, int64_t esz, int64_t s0, int64_t s1, int64_t s2) {
+    return ((uintptr_t)ptr & 15) == 0 && (s0 * esz) % 16 == 0 && (s1 * esz) % 16 == 0 && (s2 * esz) % 16 == 0;
 }
 
 }  // namespace gemm
@@ -569,36 +695,65 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
                 "A/B strides must be multiples of 8 elements (16 bytes) for TMA");
     DWG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "A/B must be 16-byte aligned");
     DWG_REQUIRE(act != ACT_GEGLU || (N % 2 == 0 && out_bf16 && !residual), "GEGLU epilogue: even N, bf16 output, no residual");
-    CUtensorMap tmA, tmB;
+    DWG_REQUIRE(act != ACT_GEGLU || !bias || ((uintptr_t)bias & 15) == 0, "GEGLU bias must be 16-byte aligned");
+    int rc = ensure_globals();
+    if (rc) return rc;
+    const int epi = act == ACT_GEGLU ? EPI_GEGLU : (out_bf16 ? EPI_BF16 : EPI_F32);
+    const int64_t esz = out_bf16 ? 2 : 4;
+    if (nb1 == 1) c_b1 = ldc * (int64_t)M;
+    if (nb2 == 1) c_b2 = c_b1 * nb1;
+    if (residual && nb1 == 1) r_b1 = ldr * (int64_t)M;
+    if (residual && nb2 == 1) r_b2 = r_b1 * nb1;
+    Params p = {};
+    p.direct = !aligned16(C, esz, ldc, c_b1, c_b2) || (residual && !aligned16(residual, 2, ldr, r_b1, r_b2)) ||
+               (bias && ((uintptr_t)bias & 15)) || (bias2 && (((uintptr_t)bias2 & 15) || (N % 4))) || (act == ACT_GEGLU && (N % 64));
+    DWG_REQUIRE(!(p.direct && act == ACT_GEGLU), "GEGLU epilogue needs 16-byte aligned output rows and N % 64 == 0");
+    p.has_res = (residual && !p.direct) ? 1 : 0;
+    p.M = M; p.N = N; p.K = K; p.taps_w = 1; p.taps_h = 1; p.k_chunks = (K + BK - 1) / BK; p.nb1 = nb1; p.conv_mode = 0;
+    p.a_bytes = A_BYTES;
+    p.C = C; p.ldc = ldc; p.c_b1 = c_b1; p.c_b2 = c_b2;
+    p.bias = bias; p.bias2 = bias2; p.bias2_rows_per = bias2_rows_per;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.r_b1 = r_b1; p.r_b2 = r_b2;
+    p.alpha = alpha; p.act = act;
+    p.m_tiles = (M + BM - 1) / BM; p.nz = nb1 * nb2;
+    const Plan pl = plan_tiles(p.m_tiles, p.nz, N, p.k_chunks, epi, p.has_res, (int64_t)(g_ws_bytes / 4));
+    p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
+    p.n_tiles = (N + p.BN - 1) / p.BN;
+    p.total_tiles = p.m_tiles * p.n_tiles * p.nz * p.ksplit;
+    p.workspace = g_ws; p.counters = g_counters;
+
+    CUtensorMap tmA, tmB, tmC, tmR;
     const uint32_t ones[4] = {1, 1, 1, 1};
-    const int bn = pick_bn(N);
     {
         const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)nb1, (uint64_t)nb2};
         const uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)(nb1 > 1 ? a_b1 : lda * (int64_t)M) * 2, (uint64_t)(nb2 > 1 ? a_b2 : lda * (int64_t)M) * 2};
         const uint32_t box[4] = {BK, BM, 1, 1};
-        int rc = make_map(&tmA, A, dims, str, box, ones);
+        rc = make_map_bf16(&tmA, A, dims, str, box, ones);
         if (rc) return rc;
     }
     {
         const uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)nb1, (uint64_t)nb2};
         const uint64_t str[3] = {(uint64_t)ldb * 2, (uint64_t)(nb1 > 1 ? b_b1 : ldb * (int64_t)N) * 2, (uint64_t)(nb2 > 1 ? b_b2 : ldb * (int64_t)N) * 2};
-        const uint32_t box[4] = {BK, (uint32_t)bn, 1, 1};
-        int rc = make_map(&tmB, B, dims, str, box, ones);
+        const uint32_t box[4] = {BK, (uint32_t)p.BN, 1, 1};
+        rc = make_map_bf16(&tmB, B, dims, str, box, ones);
         if (rc) return rc;
     }
-    Params p = {};
-    p.M = M; p.N = N; p.K = K; p.taps_w = 1; p.taps_h = 1; p.k_chunks = (K + BK - 1) / BK; p.nb1 = nb1; p.conv_mode = 0;
-    p.a_bytes = BM * BK * 2;
-    p.C = C; p.out_bf16 = out_bf16; p.ldc = ldc; p.c_b1 = c_b1; p.c_b2 = c_b2;
-    p.bias = bias; p.bias2 = bias2; p.bias2_rows_per = bias2_rows_per;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.r_b1 = r_b1; p.r_b2 = r_b2;
-    p.alpha = alpha; p.act = act;
-    p.m_tiles = (M + BM - 1) / BM; p.nz = nb1 * nb2;
-    const int64_t rows_total = (int64_t)M * nb1 * nb2;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64) return launch_t<64, 6>(tmA, tmB, p, rows_total, st);
-    if (bn == 256) return launch_t<256, 4>(tmA, tmB, p, rows_total, st);
-    return launch_t<128, 5>(tmA, tmB, p, rows_total, st);
+    tmC = tmA; tmR = tmA;                                   // placeholders on the direct path (never dereferenced)
+    if (!p.direct) {
+        const uint64_t No = (uint64_t)(act == ACT_GEGLU ? N / 2 : N);
+        const uint64_t dims[4] = {No, (uint64_t)M, (uint64_t)nb1, (uint64_t)nb2};
+        const uint64_t str[3] = {(uint64_t)(ldc * esz), (uint64_t)(c_b1 * esz), (uint64_t)(c_b2 * esz)};
+        const uint32_t box[4] = {32, 32, 1, 1};
+        rc = make_map(&tmC, out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, C, dims, str, box, ones);
+        if (rc) return rc;
+        if (p.has_res) {
+            const uint64_t rstr[3] = {(uint64_t)ldr * 2, (uint64_t)r_b1 * 2, (uint64_t)r_b2 * 2};
+            rc = make_map(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, residual, dims, rstr, box, ones);
+            if (rc) return rc;
+        }
+    }
+    return launch(tmA, tmB, tmC, tmR, p, epi, (cudaStream_t)stream);
 }
 
 // NHWC convolution as implicit GEMM.  x [Nimg,H,W,Cin] bf16 (Cin % 8 == 0), w [Cout,kh,kw,Cin] bf16,
@@ -613,6 +768,9 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     DWG_REQUIRE(Cin % 8 == 0, "Cin must be a multiple of 8 (pad the channels)");
     DWG_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
     DWG_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
+    DWG_REQUIRE(act != ACT_GEGLU, "GEGLU is a linear-layer epilogue");
+    int rc = ensure_globals();
+    if (rc) return rc;
     // pixel box of one 128-row tile
     int BW = 1;
     while (BW * 2 <= Wo && BW * 2 <= BM) BW *= 2;
@@ -622,39 +780,63 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     int BNI = BM / (BW * BH);
     if (BNI > Nimg) BNI = 1 << (31 - __builtin_clz(Nimg));         // largest power of two <= Nimg
     const int tiles_w = (Wo + BW - 1) / BW, tiles_h = (Ho + BH - 1) / BH, tiles_n = (Nimg + BNI - 1) / BNI;
-    CUtensorMap tmA, tmB;
-    const int bn = pick_bn(Cout);
+    const int epi = out_bf16 ? EPI_BF16 : EPI_F32;
+    const int64_t esz = out_bf16 ? 2 : 4;
+    Params p = {};
+    p.direct = (((uintptr_t)y & 15) || (Cout * esz) % 16 || (residual && (((uintptr_t)residual & 15) || (Cout * 2) % 16)) ||
+                (bias && ((uintptr_t)bias & 15)) || (bias2_per_image && (((uintptr_t)bias2_per_image & 15) || (Cout % 4)))) ? 1 : 0;
+    if (BW * BH * BNI < 32 && tiles_n > 1) p.direct = 1;       // a warp's 32-row store box would reach into the next image group
+    p.has_res = (residual && !p.direct) ? 1 : 0;
+    p.M = Nimg * Ho * Wo; p.N = Cout; p.K = Cin; p.taps_w = ksize; p.taps_h = ksize; p.k_chunks = (Cin + BK - 1) / BK;
+    p.a_bytes = (uint32_t)(BW * BH * BNI * BK * 2);
+    p.nb1 = 1; p.conv_mode = 1; p.Ho = Ho; p.Wo = Wo; p.BH = BH; p.BW = BW; p.BNI = BNI; p.Nimg = Nimg; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+    p.stride = stride; p.pad_h = pad_h; p.pad_w = pad_w;
+    p.ebw = BW < 32 ? BW : 32;
+    p.ebh = (32 / p.ebw) < BH ? (32 / p.ebw) : BH;
+    const int ebn = 32 / (p.ebw * p.ebh);
+    p.C = y; p.ldc = Cout;
+    p.bias = bias; p.bias2 = bias2_per_image; p.bias2_rows_per = bias2_per_image ? Ho * Wo : 0;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
+    p.alpha = 1.0f; p.act = act;
+    p.m_tiles = tiles_w * tiles_h * tiles_n; p.nz = 1;
+    const int iters = ksize * ksize * p.k_chunks;
+    const Plan pl = plan_tiles(p.m_tiles, 1, Cout, iters, epi, p.has_res, (int64_t)(g_ws_bytes / 4));
+    p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
+    p.n_tiles = (Cout + p.BN - 1) / p.BN;
+    p.total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+    p.workspace = g_ws; p.counters = g_counters;
+
+    CUtensorMap tmA, tmB, tmC, tmR;
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
         const uint32_t box[4] = {BK, (uint32_t)((BW - 1) * stride + 1), (uint32_t)((BH - 1) * stride + 1), (uint32_t)BNI};
         const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-        int rc = make_map(&tmA, x, dims, str, box, es);
+        rc = make_map_bf16(&tmA, x, dims, str, box, es);
         if (rc) return rc;
     }
+    const uint32_t ones[4] = {1, 1, 1, 1};
     {
         const int taps = ksize * ksize;
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout, 1};
         const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2, (uint64_t)Cout * taps * Cin * 2};
-        const uint32_t box[4] = {BK, 1, (uint32_t)bn, 1};
-        const uint32_t ones[4] = {1, 1, 1, 1};
-        int rc = make_map(&tmB, w, dims, str, box, ones);
+        const uint32_t box[4] = {BK, 1, (uint32_t)p.BN, 1};
+        rc = make_map_bf16(&tmB, w, dims, str, box, ones);
         if (rc) return rc;
     }
-    Params p = {};
-    p.M = Nimg * Ho * Wo; p.N = Cout; p.K = Cin; p.taps_w = ksize; p.taps_h = ksize; p.k_chunks = (Cin + BK - 1) / BK;
-    p.a_bytes = (uint32_t)(BW * BH * BNI * BK * 2);
-    p.nb1 = 1; p.conv_mode = 1; p.Ho = Ho; p.Wo = Wo; p.BH = BH; p.BW = BW; p.BNI = BNI; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
-    p.stride = stride; p.pad_h = pad_h; p.pad_w = pad_w;
-    p.C = y; p.out_bf16 = out_bf16; p.ldc = Cout;
-    p.bias = bias; p.bias2 = bias2_per_image; p.bias2_rows_per = bias2_per_image ? Ho * Wo : 0;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
-    p.alpha = 1.0f; p.act = act;
-    // rows of a tile with n >= Nimg are masked in the epilogue through M
-    p.m_tiles = tiles_w * tiles_h * tiles_n; p.nz = 1;
-    const int64_t rows_total = (int64_t)Nimg * Ho * Wo;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 64) return launch_t<64, 6>(tmA, tmB, p, rows_total, st);
-    if (bn == 256) return launch_t<256, 4>(tmA, tmB, p, rows_total, st);
-    return launch_t<128, 5>(tmA, tmB, p, rows_total, st);
+    tmC = tmA; tmR = tmA;
+    if (!p.direct) {
+        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)Nimg};
+        const uint64_t str[3] = {(uint64_t)(Cout * esz), (uint64_t)((int64_t)Wo * Cout * esz), (uint64_t)((int64_t)Ho * Wo * Cout * esz)};
+        const uint32_t box[4] = {32, (uint32_t)p.ebw, (uint32_t)p.ebh, (uint32_t)ebn};
+        rc = make_map(&tmC, out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, y, dims, str, box, ones);
+        if (rc) return rc;
+        if (p.has_res) {
+            const uint64_t rstr[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+            rc = make_map(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, residual, dims, rstr, box, ones);
+            if (rc) return rc;
+        }
+    }
+    return launch(tmA, tmB, tmC, tmR, p, epi, (cudaStream_t)stream);
 }
