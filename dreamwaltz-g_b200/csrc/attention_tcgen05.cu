@@ -2,13 +2,17 @@
 // ControlNet transformer blocks).  O = softmax(Q K^T / sqrt(d)) V without ever writing the
 // [T, Tk] score matrix to HBM (the unfused path moved ~2 GB per 64x64-resolution layer).
 //
-// One CTA = 128 query rows of one (batch, head).  Per 128-key block:
+// One CTA = 128 query rows of one (batch, head); two CTAs share an SM.  Per 128-key block j:
 //   warp 4 (one elected lane): TMA loads of K / V^T (double-buffered, 128B-swizzled), then
-//       S = Q K^T        tcgen05.mma  M=128 N=128 K=64*chunks   -> TMEM columns [0,128)
-//   warps 0-3 (thread == query row, TMEM lane == row): online softmax straight out of TMEM
-//       (tcgen05.ld), P written as bf16 into a swizzled shared-memory A-operand tile
-//   warp 4:  O_blk = P V  tcgen05.mma  M=128 N=round16(d) K=128 -> TMEM columns [128, 128+N)
-//   warps 0-3: O = alpha * O + O_blk in registers (fp32); final O / l -> bf16 -> HBM.
+//       S(j+1) = Q K^T   tcgen05.mma  M=128 N=128 K=64*chunks   -> TMEM columns [0,128)
+//         issued as soon as the softmax warps have pulled S(j) into registers (s_free), so the
+//         tensor pipe works on the next block while the SIMT pipes do this block's exponentials;
+//       O += P(j) V(j)   tcgen05.mma  M=128 N=round16(d) K=128 -> TMEM columns [128, 128+N)
+//   warps 0-3 (thread == query row, TMEM lane == row): ONE pass over S: tcgen05.ld of the whole
+//       128-column row into registers, row max, p = exp2(s*scale - m_ref), P written as bf16 into a
+//       swizzled shared-memory A-operand tile.  O stays in TMEM for the whole key loop; the running
+//       maximum is LAZY (FA4-style): m_ref only moves when the block maximum exceeds it by more than
+//       2^8, and only then is the O row rescaled in TMEM (tcgen05.ld / tcgen05.st).
 // V is consumed as V^T ([d, Tk], key index contiguous = K-major B operand), which the projection
 // GEMM produces for free by swapping its operands (see dwg/diffusion/model.py).
 #include <cuda.h>
@@ -74,6 +78,26 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 32 consecutive fp32 columns of this thread's TMEM lane, WITHOUT the wait (batch several, then tc_wait_ld)
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -101,8 +125,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     uint8_t* sP = sV + 2 * 2 * VT;                           // 2 key-chunks x TILE
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE);
     uint64_t* q_full = bars; uint64_t* kv_full = bars + 1; uint64_t* kv_empty = bars + 3;
-    uint64_t* s_full = bars + 5; uint64_t* p_full = bars + 6; uint64_t* o_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* s_full = bars + 5; uint64_t* p_full = bars + 6; uint64_t* o_full = bars + 7; uint64_t* s_free = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * BQ, head = blockIdx.y, b = blockIdx.z;
@@ -116,7 +140,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             mbar_init(q_full, 1);
             mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
             mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
-            mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+            mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(s_free, 128);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -145,15 +169,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             for (int c = 0; c < CH; c++) tma_load_4d(sQ + c * TILE, &tmQ, q_full, c * 64, q0, head, b);
             load_kv(0, 0);
             const uint32_t idS = make_idesc(128), idO = make_idesc(NPV);
-            for (int j = 0; j < nblk; j++) {
-                const int s = j & 1;
-                if (j + 1 < nblk) {
-                    mbar_wait(&kv_empty[s ^ 1], (uint32_t)(((j + 1) >> 1) & 1) ^ 1u);
-                    load_kv(j + 1, s ^ 1);
-                }
-                if (j == 0) mbar_wait(q_full, 0);
-                mbar_wait(&kv_full[s], (uint32_t)((j >> 1) & 1));
-                tc_fence_after();
+            auto issue_S = [&](int s) {
 #pragma unroll
                 for (int c = 0; c < CH; c++) {
                     const uint64_t dq = make_desc(smem_u32(sQ + c * TILE));
@@ -162,14 +178,30 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     for (int k = 0; k < 4; k++) tc_mma(tmem_S, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idS, (c | k) != 0 ? 1u : 0u);
                 }
                 tc_commit(s_full);
-                mbar_wait(p_full, (uint32_t)(j & 1));          // P is in shared memory, S has been consumed
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_S(0);
+            for (int j = 0; j < nblk; j++) {
+                const int s = j & 1;
+                if (j + 1 < nblk) {
+                    // stage s^1 was last read by PV(j-1)
+                    mbar_wait(&kv_empty[s ^ 1], (uint32_t)(((j + 1) >> 1) & 1) ^ 1u);
+                    load_kv(j + 1, s ^ 1);
+                    mbar_wait(&kv_full[s ^ 1], (uint32_t)(((j + 1) >> 1) & 1));
+                    mbar_wait(s_free, (uint32_t)(j & 1));           // S(j) is in the softmax warps' registers
+                    tc_fence_after();
+                    issue_S(s ^ 1);                                  // S(j+1) overlaps the exponentials of block j
+                }
+                mbar_wait(p_full, (uint32_t)(j & 1));               // P(j) is in shared memory, O has been rescaled if needed
                 tc_fence_after();
 #pragma unroll
                 for (int kc = 0; kc < 2; kc++) {
                     const uint64_t dp = make_desc(smem_u32(sP + kc * TILE));
                     const uint64_t dv = make_desc(smem_u32(sV + (s * 2 + kc) * VT));
 #pragma unroll
-                    for (int k = 0; k < 4; k++) tc_mma(tmem_O, dp + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idO, (kc | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; k++) tc_mma(tmem_O, dp + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), idO, (j | kc | k) != 0 ? 1u : 0u);
                 }
                 tc_commit(o_full);
                 tc_commit(&kv_empty[s]);
@@ -179,40 +211,58 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     } else {
         const int r = threadIdx.x;                            // query row of the tile == TMEM lane
         const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
-        float m = -INFINITY, l = 0.f;
-        float O[NPV];
-#pragma unroll
-        for (int c = 0; c < NPV; c++) O[c] = 0.f;
+        float m_ref = -INFINITY, l = 0.f;
         for (int j = 0; j < nblk; j++) {
             mbar_wait(s_full, (uint32_t)(j & 1));
             tc_fence_after();
-            const int kv_valid = min(BKV, p.Tk - j * BKV);
-            // pass 1: row maximum
-            float mx = -INFINITY;
-#pragma unroll 2
-            for (int c0 = 0; c0 < BKV; c0 += 16) {
-                uint32_t v[16];
-                tc_ld16(tmem_S + lane_base + (uint32_t)c0, v);
+            float sv[BKV];
 #pragma unroll
-                for (int i = 0; i < 16; i++) if (c0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int c0 = 0; c0 < BKV; c0 += 32) tc_ld32_nowait(tmem_S + lane_base + (uint32_t)c0, sv + c0);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(s_free);                                // the tensor pipe may overwrite S with block j+1
+            if (j == nblk - 1) {
+                const int kv_valid = p.Tk - j * BKV;
+#pragma unroll
+                for (int i = 0; i < BKV; i++) if (i >= kv_valid) sv[i] = -INFINITY;
             }
-            const float m_new = fmaxf(m, mx * p.scale_log2);
-            const float alpha = exp2f(m - m_new);               // 0 on the first block (m = -inf)
-            float lsum = 0.f;
-            // pass 2: P = exp2(s - m_new) -> bf16 -> swizzled smem tile
-#pragma unroll 2
+            float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
+#pragma unroll
+            for (int i = 4; i < BKV; i += 4) {
+                mx0 = fmaxf(mx0, sv[i]); mx1 = fmaxf(mx1, sv[i + 1]); mx2 = fmaxf(mx2, sv[i + 2]); mx3 = fmaxf(mx3, sv[i + 3]);
+            }
+            const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+            // lazy running maximum: move the reference only when the block exceeds it by > 2^8
+            const bool move = m_blk > m_ref + 8.0f;
+            const float m_new = move ? m_blk : m_ref;
+            const float alpha = move ? exp2f(m_ref - m_new) : 1.0f;      // 0 on the first block (m_ref = -inf)
+            if (j > 0) {
+                mbar_wait(o_full, (uint32_t)((j - 1) & 1));     // PV(j-1) done: O is stable and sP may be rewritten
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, move)) {
+#pragma unroll
+                    for (int c0 = 0; c0 < NPV; c0 += 16) {
+                        uint32_t v[16];
+                        tc_ld16(tmem_O + lane_base + (uint32_t)c0, v);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tc_st16(tmem_O + lane_base + (uint32_t)c0, v);
+                    }
+                    tc_wait_st();
+                }
+            }
+            l *= alpha;
+            m_ref = m_new;
+            float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
             for (int c0 = 0; c0 < BKV; c0 += 16) {
-                uint32_t v[16];
-                tc_ld16(tmem_S + lane_base + (uint32_t)c0, v);
                 uint32_t pk[8];
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const float p0 = (c0 + i < kv_valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
-                    const float p1 = (c0 + i + 1 < kv_valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
+                    const float p0 = exp2f(fmaf(sv[c0 + i], p.scale_log2, -m_new));
+                    const float p1 = exp2f(fmaf(sv[c0 + i + 1], p.scale_log2, -m_new));
+                    ls0 += p0; ls1 += p1;
                     const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-                    // accumulate the ROUNDED probabilities so that l matches what the PV matmul sees
-                    const float2 hf = __bfloat1622float2(h);
-                    lsum += hf.x + hf.y;
                     pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
                 }
                 // 16 columns = two 16-byte chunks of the 128-byte row; chunk index XOR (row & 7)
@@ -222,39 +272,35 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 *reinterpret_cast<uint4*>(rowp + (((ch) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
-            l = l * alpha + lsum;
-            m = m_new;
+            l += ls0 + ls1;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy (MMA)
             tc_fence_before();
             mbar_arrive(p_full);
-            // O = alpha * O + P V
-            mbar_wait(o_full, (uint32_t)(j & 1));
-            tc_fence_after();
-#pragma unroll
-            for (int c0 = 0; c0 < NPV; c0 += 16) {
-                uint32_t v[16];
-                tc_ld16(tmem_O + lane_base + (uint32_t)c0, v);
-#pragma unroll
-                for (int i = 0; i < 16; i++) O[c0 + i] = O[c0 + i] * alpha + __uint_as_float(v[i]);
-            }
-            tc_fence_before();
         }
+        mbar_wait(o_full, (uint32_t)((nblk - 1) & 1));
+        tc_fence_after();
         const int t = q0 + r;
-        if (t < p.T) {
-            const float inv = 1.0f / l;
-            __nv_bfloat16* dst = p.out + ((int64_t)b * p.T + t) * p.out_row_stride + (int64_t)head * p.hd;
+        const float inv = 1.0f / l;
+        __nv_bfloat16* dst = p.out + ((int64_t)b * p.T + t) * p.out_row_stride + (int64_t)head * p.hd;
 #pragma unroll
-            for (int c0 = 0; c0 < NPV; c0 += 8) {
-                if (c0 < p.hd) {
+        for (int c0 = 0; c0 < NPV; c0 += 16) {
+            uint32_t v[16];
+            tc_ld16(tmem_O + lane_base + (uint32_t)c0, v);
+#pragma unroll
+            for (int h8 = 0; h8 < 16; h8 += 8) {
+                if (t < p.T && c0 + h8 < p.hd) {
                     uint4 pk;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(O[c0] * inv, O[c0 + 1] * inv), h1 = __floats2bfloat162_rn(O[c0 + 2] * inv, O[c0 + 3] * inv);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(O[c0 + 4] * inv, O[c0 + 5] * inv), h3 = __floats2bfloat162_rn(O[c0 + 6] * inv, O[c0 + 7] * inv);
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[h8]) * inv, __uint_as_float(v[h8 + 1]) * inv);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[h8 + 2]) * inv, __uint_as_float(v[h8 + 3]) * inv);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[h8 + 4]) * inv, __uint_as_float(v[h8 + 5]) * inv);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[h8 + 6]) * inv, __uint_as_float(v[h8 + 7]) * inv);
                     pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
                     pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                    *reinterpret_cast<uint4*>(dst + c0) = pk;
+                    *reinterpret_cast<uint4*>(dst + c0 + h8) = pk;
                 }
             }
         }
+        tc_fence_before();
     }
     tc_fence_before();
     __syncthreads();

@@ -80,6 +80,20 @@ def main():
         fl = 2.0 * Ni * H * W * Ci * Co * k * k
         print(f'{f"conv{k}x{k} {Ni}x{H}x{W} {Ci}->{Co}":40s} {t:8.1f} {fl / t / 1e6:8.1f} {tc:9.1f} {t / max(tc, 1e-9):6.2f}', flush=True)
 
+    if not ncu:
+        for B, h, T, Tk, hd in ((2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 4096, 77, 40), (2, 8, 256, 256, 160 // 1 if False else 128)):
+            C = h * hd
+            q = torch.randn(B, T, C, device=dev).bfloat16()
+            k = torch.randn(B, Tk, C, device=dev).bfloat16()
+            Tkp = (Tk + 7) // 8 * 8
+            vt = torch.randn(B, C, Tkp, device=dev).bfloat16()
+            t = timeit(lambda: ops.attention(q, k, vt, h, Tk), iters)
+            sp = lambda x: x.view(B, -1, h, hd).transpose(1, 2)
+            v = vt[:, :, :Tk].transpose(1, 2).contiguous()
+            tc = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(sp(q), sp(k), sp(v)), iters)
+            fl = 4.0 * B * h * T * Tk * hd
+            print(f'{f"attention B{B} h{h} T{T} Tk{Tk} d{hd}":40s} {t:8.1f} {fl / t / 1e6:8.1f} {tc:9.1f} {t / max(tc, 1e-9):6.2f}', flush=True)
+
 
 if __name__ == '__main__':
     main()
