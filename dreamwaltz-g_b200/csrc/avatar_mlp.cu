@@ -1,0 +1,573 @@
+// R7 / R8 / R9: the two per-Gaussian MLPs of DreamWaltzG.animate and their activations, fused.
+//
+//   nerf_opacity_and_color_net   MLP 32 -> 64 -> 64 -> 4, ReLU            (core/nerf/nerf_model.py:12-33,
+//                                out[:,0] -> sigmoid opacity, out[:,1:4] -> sigmoid colour,
+//                                core/system/avatar.py:1283-1290)
+//   nerf_scale_and_quaternion_net DeformNetwork [enc(32) | body_pose(63)] -> 4 x (64, leaky_relu 0.01)
+//                                -> heads warp(3) / scaling(3)            (core/deformation/deform_model.py:102-143;
+//                                the rotation head is not consumed with use_non_rigid_rotations=False)
+//   non_rigid_transform          pos = positions + 0.01 * warp, scales = clamp_max(exp(scaling) * 1e-3, 0.01)
+//                                (core/system/avatar.py:1464-1498, shipped flags)
+//
+// The reference runs these as ~40 eager kernels forward (Linear = cuBLAS SGEMM + elementwise) and as
+// many again in autograd, moving every [N,64] activation through HBM several times.  Here one
+// forward and one backward kernel do all of it in plain fp32 FMA arithmetic -- exactly the
+// reference's numeric type (the hidden width is 64: the work is 21 kMAC per Gaussian, 5.7 GFLOP per
+// pass, far too small to be tensor-bound, and fp32 keeps parity with the reference tight):
+//   * the 63 pose inputs are identical for every Gaussian: folded into the first-layer bias once
+//     per CTA (their weight gradient is the outer product bias-gradient x pose);
+//   * weights live in shared memory for the whole kernel (86 KB); a thread owns one Gaussian and
+//     walks the layer chain with its activation column in shared memory (layout [feature][point],
+//     conflict-free), weights arriving as broadcast 128-bit shared loads: 64 FMAs per 17 loads;
+//   * forward saves the six hidden activations (fp32, [layer][feature][point], coalesced);
+//   * backward: per 256-point tile and layer, dL/dW is a register-tiled 64x64xP product over the
+//     tile (4x4 block per thread, accumulated in registers across ALL tiles of the CTA, written as
+//     per-CTA partials and summed by a second tiny kernel: deterministic, no atomics), dL/dx is
+//     again thread-per-point and in place.
+#include "common.cuh"
+
+namespace dwg {
+namespace mlp {
+
+constexpr int P = 256;            // points per tile == threads per CTA
+constexpr int S = P + 4;          // backward smem row stride in words: 16-byte aligned rows, 4 banks apart
+constexpr int HID = 64, ENC = 32, POSE = 63;
+
+// flat fp32 parameter vector (also the layout of the gradient vector)
+constexpr int S1W = 0, S1B = 2048, S2W = 2112, S2B = 6208, S3W = 6272, S3B = 6528;
+constexpr int D0W = 6532, D0B = 8580, D1W = 8644, D1B = 12740, D2W = 12804, D2B = 16900, D3W = 16964, D3B = 21060;
+constexpr int WPW = 21124, WPB = 21316, SCW = 21319, SCB = 21511, NPARAM = 21514;
+
+struct FwdArgs {
+    const float* enc;         // [N,32]
+    const float* positions;   // [Nu,3]
+    const float* params;      // [NPARAM]
+    const float* w_pose;      // [64,63]  (layers.0.weight[:, 32:95])
+    const float* pose;        // [63]
+    float* colors;            // [N,3]
+    float* opac;              // [N]
+    float* pos_out;           // [Nu,3]
+    float* scales;            // [Nu,3]
+    float* acts_s;            // [2][64][Np]   or null
+    float* acts_d;            // [4][64][Nup]  or null
+    int64_t N, Nu, Np, Nup;
+    float init_offset, init_scale, max_scale;
+};
+
+struct BwdArgs {
+    const float* enc; const float* params;
+    const float* colors; const float* opac; const float* scales;
+    const float* acts_s; const float* acts_d;
+    const float* g_colors; const float* g_opac; const float* g_pos; const float* g_scales;   // any may be null (= zero)
+    float* g_enc;             // [N,32]
+    float* partial;           // [gridDim.x][NPARAM]
+    int64_t N, Nu, Np, Nup;
+    float init_offset, max_scale;
+};
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+
+__device__ __forceinline__ float act_fn(float x, int act) {
+    if (act == ACT_RELU) return fmaxf(x, 0.f);
+    if (act == ACT_LRELU) return x > 0.f ? x : 0.01f * x;
+    return x;
+}
+__device__ __forceinline__ float act_grad(float a, int act) {      // from the POST-activation value (same sign as the input)
+    if (act == ACT_RELU) return a > 0.f ? 1.f : 0.f;
+    if (act == ACT_LRELU) return a > 0.f ? 1.f : 0.01f;
+    return 1.f;
+}
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// thread-per-point layer: out[o] = act(b[o] + sum_k Wt[k][o] * col[k*stride]);  Wt = [K][O] in smem
+template <int K, int O, int ACT>
+__device__ __forceinline__ void layer_fwd(const float* __restrict__ Wt, const float* __restrict__ b, float* col, int stride,
+                                          float (&out)[O]) {
+#pragma unroll
+    for (int o = 0; o < O; o++) out[o] = b[o];
+#pragma unroll 2
+    for (int k = 0; k < K; k++) {
+        const float a = col[k * stride];
+        const float4* w = reinterpret_cast<const float4*>(Wt + k * O);
+#pragma unroll
+        for (int o4 = 0; o4 < O / 4; o4++) {
+            const float4 ww = w[o4];
+            out[4 * o4] = fmaf(a, ww.x, out[4 * o4]); out[4 * o4 + 1] = fmaf(a, ww.y, out[4 * o4 + 1]);
+            out[4 * o4 + 2] = fmaf(a, ww.z, out[4 * o4 + 2]); out[4 * o4 + 3] = fmaf(a, ww.w, out[4 * o4 + 3]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < O; o++) out[o] = act_fn(out[o], ACT);
+}
+
+// hidden layer in place on the thread's activation column (+ optional save to global [O][Np])
+template <int K, int ACT>
+__device__ __forceinline__ void hidden_fwd(const float* __restrict__ Wt, const float* __restrict__ b, float* col, float* gsave, int64_t Np, bool valid) {
+    float h[HID];
+    layer_fwd<K, HID, ACT>(Wt, b, col, P, h);
+#pragma unroll
+    for (int o = 0; o < HID; o++) col[o * P] = h[o];
+    if (gsave && valid) {
+#pragma unroll
+        for (int o = 0; o < HID; o++) gsave[o * Np] = h[o];
+    }
+}
+
+__device__ __forceinline__ void load_transposed(float* dst, const float* __restrict__ src, int O, int K) {     // dst[k][o] = src[o][k]
+    for (int i = threadIdx.x; i < O * K; i += blockDim.x) {
+        const int o = i / K, k = i - o * K;
+        dst[k * O + o] = src[i];
+    }
+}
+
+__device__ __forceinline__ void load_enc_column(const float* __restrict__ enc, int64_t p, bool valid, float* col, int stride) {
+    if (valid) {
+        const float4* e = reinterpret_cast<const float4*>(enc + p * ENC);
+#pragma unroll
+        for (int j = 0; j < ENC / 4; j++) {
+            const float4 v = __ldg(e + j);
+            col[(4 * j) * stride] = v.x; col[(4 * j + 1) * stride] = v.y; col[(4 * j + 2) * stride] = v.z; col[(4 * j + 3) * stride] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ENC; k++) col[k * stride] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(P, 1)
+mlp_fwd_kernel(const FwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* Ws1 = sm;                       // [32][64]
+    float* Ws2 = Ws1 + ENC * HID;          // [64][64]
+    float* Ws3 = Ws2 + HID * HID;          // [64][4]
+    float* Wd0 = Ws3 + HID * 4;            // [32][64]
+    float* Wd1 = Wd0 + ENC * HID;
+    float* Wd2 = Wd1 + HID * HID;
+    float* Wd3 = Wd2 + HID * HID;
+    float* Wdh = Wd3 + HID * HID;          // [64][8]: warp xyz, scaling xyz, 0, 0
+    float* bs1 = Wdh + HID * 8;
+    float* bs2 = bs1 + HID;
+    float* bs3 = bs2 + HID;                // [4]
+    float* bd0 = bs3 + 4;                  // effective: bias + W_pose @ pose
+    float* bd1 = bd0 + HID;
+    float* bd2 = bd1 + HID;
+    float* bd3 = bd2 + HID;
+    float* bdh = bd3 + HID;                // [8]
+    float* act = bdh + 8;                  // [64][P]
+    const int tid = threadIdx.x;
+    const float* W = a.params;
+    load_transposed(Ws1, W + S1W, HID, ENC);
+    load_transposed(Ws2, W + S2W, HID, HID);
+    load_transposed(Ws3, W + S3W, 4, HID);
+    load_transposed(Wd0, W + D0W, HID, ENC);
+    load_transposed(Wd1, W + D1W, HID, HID);
+    load_transposed(Wd2, W + D2W, HID, HID);
+    load_transposed(Wd3, W + D3W, HID, HID);
+    for (int i = tid; i < HID * 8; i += P) {
+        const int k = i >> 3, o = i & 7;
+        Wdh[i] = o < 3 ? W[WPW + o * HID + k] : (o < 6 ? W[SCW + (o - 3) * HID + k] : 0.f);
+    }
+    if (tid < HID) {
+        bs1[tid] = W[S1B + tid]; bs2[tid] = W[S2B + tid];
+        bd1[tid] = W[D1B + tid]; bd2[tid] = W[D2B + tid]; bd3[tid] = W[D3B + tid];
+        float b = W[D0B + tid];
+        for (int j = 0; j < POSE; j++) b = fmaf(a.w_pose[tid * POSE + j], a.pose[j], b);
+        bd0[tid] = b;
+    }
+    if (tid < 4) bs3[tid] = W[S3B + tid];
+    if (tid < 8) bdh[tid] = tid < 3 ? W[WPB + tid] : (tid < 6 ? W[SCB + tid - 3] : 0.f);
+    __syncthreads();
+
+    float* col = act + tid;
+    const int64_t ntiles = (a.N + P - 1) / P;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t p = tile * P + tid;
+        const bool valid = p < a.N;
+        // ---- opacity / colour net
+        load_enc_column(a.enc, p, valid, col, P);
+        hidden_fwd<ENC, ACT_RELU>(Ws1, bs1, col, a.acts_s ? a.acts_s + p : nullptr, a.Np, valid);
+        hidden_fwd<HID, ACT_RELU>(Ws2, bs2, col, a.acts_s ? a.acts_s + HID * a.Np + p : nullptr, a.Np, valid);
+        float o4[4];
+        layer_fwd<HID, 4, ACT_NONE>(Ws3, bs3, col, P, o4);
+        if (valid) {
+            a.opac[p] = p < a.Nu ? sigmoidf(o4[0]) : 1.0f;           // mesh-bound Gaussians: opacity fixed to 1 (avatar.py:1287-1288)
+            a.colors[p * 3] = sigmoidf(o4[1]); a.colors[p * 3 + 1] = sigmoidf(o4[2]); a.colors[p * 3 + 2] = sigmoidf(o4[3]);
+        }
+        // ---- deformation net (unconstrained Gaussians only)
+        if (tile * P < a.Nu) {
+            const bool vu = p < a.Nu;
+            load_enc_column(a.enc, p, vu, col, P);
+            hidden_fwd<ENC, ACT_LRELU>(Wd0, bd0, col, a.acts_d ? a.acts_d + p : nullptr, a.Nup, vu);
+            hidden_fwd<HID, ACT_LRELU>(Wd1, bd1, col, a.acts_d ? a.acts_d + 1 * HID * a.Nup + p : nullptr, a.Nup, vu);
+            hidden_fwd<HID, ACT_LRELU>(Wd2, bd2, col, a.acts_d ? a.acts_d + 2 * HID * a.Nup + p : nullptr, a.Nup, vu);
+            hidden_fwd<HID, ACT_LRELU>(Wd3, bd3, col, a.acts_d ? a.acts_d + 3 * HID * a.Nup + p : nullptr, a.Nup, vu);
+            float h8[8];
+            layer_fwd<HID, 8, ACT_NONE>(Wdh, bdh, col, P, h8);
+            if (vu) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    a.pos_out[p * 3 + c] = a.positions[p * 3 + c] + h8[c] * a.init_offset;
+                    a.scales[p * 3 + c] = fminf(expf(h8[3 + c]) * a.init_scale, a.max_scale);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- backward
+// cooperative load of a saved activation tile [rows][P] (global row stride Nrow) into A[rows][S]; points >= Nvalid -> 0
+__device__ __forceinline__ void load_act_tile(float* A, const float* __restrict__ g, int rows, int64_t Nrow, int64_t p0, int64_t Nvalid) {
+    for (int i = threadIdx.x; i < rows * (P / 4); i += P) {
+        const int k = i / (P / 4), j = i - k * (P / 4);
+        const int64_t p = p0 + 4 * j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p + 3 < Nvalid) v = __ldg(reinterpret_cast<const float4*>(g + k * Nrow + p));
+        else if (p < Nvalid) {
+            v.x = g[k * Nrow + p];
+            if (p + 1 < Nvalid) v.y = g[k * Nrow + p + 1];
+            if (p + 2 < Nvalid) v.z = g[k * Nrow + p + 2];
+        }
+        *reinterpret_cast<float4*>(A + k * S + 4 * j) = v;
+    }
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+
+// dW[o][i] += sum_p G[o][p] * A[i][p]   (O = 64 rows of G, KIN rows of A); thread (ty, tx) owns o = ty + 16a, i = tx + 16b
+template <int KIN>
+__device__ __forceinline__ void wgrad_tile(const float* __restrict__ G, const float* __restrict__ A, float (&acc)[4 * (KIN / 16)]) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    constexpr int NB = KIN / 16;
+#pragma unroll 2
+    for (int p4 = 0; p4 < P / 4; p4++) {
+        float4 g[4], x[NB];
+#pragma unroll
+        for (int q = 0; q < 4; q++) g[q] = *reinterpret_cast<const float4*>(G + (ty + 16 * q) * S + 4 * p4);
+#pragma unroll
+        for (int b = 0; b < NB; b++) x[b] = *reinterpret_cast<const float4*>(A + (tx + 16 * b) * S + 4 * p4);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) acc[q * NB + b] += dot4(g[q], x[b]);
+    }
+}
+
+// sum over the tile of row `row` of G
+__device__ __forceinline__ float row_sum(const float* __restrict__ G, int row) {
+    float s0 = 0.f, s1 = 0.f;
+    const float4* r = reinterpret_cast<const float4*>(G + row * S);
+#pragma unroll 4
+    for (int j = 0; j < P / 4; j += 2) {
+        const float4 u = r[j], v = r[j + 1];
+        s0 += (u.x + u.y) + (u.z + u.w);
+        s1 += (v.x + v.y) + (v.z + v.w);
+    }
+    return s0 + s1;
+}
+
+// thread-per-point input gradient, in place: G[i][p] <- (sum_{o<O} W[o][i] * G[o][p]) * act'(A[i][p]);  W = [O][KIN] row-major in smem
+template <int O, int KIN, int ACT, bool W_ALIGNED>
+__device__ __forceinline__ void dgrad_tile(const float* __restrict__ W, float* Gcol, const float* Acol, float (&gin)[KIN]) {
+#pragma unroll
+    for (int i = 0; i < KIN; i++) gin[i] = 0.f;
+#pragma unroll 2
+    for (int o = 0; o < O; o++) {
+        const float g = Gcol[o * S];
+        if (W_ALIGNED) {
+            const float4* w = reinterpret_cast<const float4*>(W + o * KIN);
+#pragma unroll
+            for (int i4 = 0; i4 < KIN / 4; i4++) {
+                const float4 ww = w[i4];
+                gin[4 * i4] = fmaf(g, ww.x, gin[4 * i4]); gin[4 * i4 + 1] = fmaf(g, ww.y, gin[4 * i4 + 1]);
+                gin[4 * i4 + 2] = fmaf(g, ww.z, gin[4 * i4 + 2]); gin[4 * i4 + 3] = fmaf(g, ww.w, gin[4 * i4 + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < KIN; i++) gin[i] = fmaf(g, W[o * KIN + i], gin[i]);
+        }
+    }
+    if (ACT != ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < KIN; i++) gin[i] *= act_grad(Acol[i * S], ACT);
+    }
+}
+
+__global__ void __launch_bounds__(P, 1)
+mlp_bwd_kernel(const BwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* Wsm = sm;                                   // flat parameter vector (original [out][in] layouts)
+    float* G = Wsm + ((NPARAM + 3) & ~3);              // [64][S]
+    float* A = G + HID * S;                            // [64][S]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NPARAM; i += P) Wsm[i] = a.params[i];
+    __syncthreads();
+
+    // register-resident weight-gradient accumulators (whole CTA lifetime)
+    float dWs1[8] = {}, dWs2[16] = {}, dWs3 = 0.f, dWd0[8] = {}, dWd1[16] = {}, dWd2[16] = {}, dWd3[16] = {}, dWdh0 = 0.f, dWdh1 = 0.f;
+    float dbs1 = 0.f, dbs2 = 0.f, dbs3 = 0.f, dbd0 = 0.f, dbd1 = 0.f, dbd2 = 0.f, dbd3 = 0.f, dbdh = 0.f;
+
+    float* Gcol = G + tid;
+    float* Acol = A + tid;
+    const int64_t ntiles = (a.N + P - 1) / P;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t p0 = tile * P, p = p0 + tid;
+        const bool valid = p < a.N;
+        // =============================================================== opacity / colour net
+        {
+            float go[4] = {0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                if (a.g_opac && p < a.Nu) { const float o = a.opac[p]; go[0] = a.g_opac[p] * o * (1.f - o); }
+                if (a.g_colors) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { const float v = a.colors[p * 3 + c]; go[1 + c] = a.g_colors[p * 3 + c] * v * (1.f - v); }
+                }
+            }
+            __syncthreads();                                       // previous tile is done with G / A
+#pragma unroll
+            for (int o = 0; o < 4; o++) Gcol[o * S] = go[o];
+            load_act_tile(A, a.acts_s + HID * a.Np, HID, a.Np, p0, a.N);          // h2
+            __syncthreads();
+            {   // head weight gradient: 4 x 64 entries, one per thread
+                const int o = tid >> 6, i = tid & 63;
+                const float4* gr = reinterpret_cast<const float4*>(G + o * S);
+                const float4* ar = reinterpret_cast<const float4*>(A + i * S);
+                float s = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < P / 4; j++) s += dot4(gr[j], ar[j]);
+                dWs3 += s;
+                if (tid < 4) dbs3 += row_sum(G, tid);
+            }
+            __syncthreads();
+            float gin[HID];
+            dgrad_tile<4, HID, ACT_RELU, true>(Wsm + S3W, Gcol, Acol, gin);
+#pragma unroll
+            for (int i = 0; i < HID; i++) Gcol[i * S] = gin[i];
+            __syncthreads();
+            load_act_tile(A, a.acts_s, HID, a.Np, p0, a.N);                        // h1
+            __syncthreads();
+            wgrad_tile<HID>(G, A, dWs2);
+            if (tid < HID) dbs2 += row_sum(G, tid);
+            __syncthreads();
+            dgrad_tile<HID, HID, ACT_RELU, true>(Wsm + S2W, Gcol, Acol, gin);
+#pragma unroll
+            for (int i = 0; i < HID; i++) Gcol[i * S] = gin[i];
+            __syncthreads();                                       // every thread is done with A (h1) before the columns are rewritten
+            load_enc_column(a.enc, p, valid, Acol, S);
+            __syncthreads();
+            wgrad_tile<ENC>(G, A, dWs1);
+            if (tid < HID) dbs1 += row_sum(G, tid);
+            __syncthreads();
+            float ge[ENC];
+            dgrad_tile<HID, ENC, ACT_NONE, true>(Wsm + S1W, Gcol, Acol, ge);
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(a.g_enc + p * ENC);
+#pragma unroll
+                for (int j = 0; j < ENC / 4; j++) dst[j] = make_float4(ge[4 * j], ge[4 * j + 1], ge[4 * j + 2], ge[4 * j + 3]);
+            }
+        }
+        // =============================================================== deformation net
+        if (p0 < a.Nu) {
+            const bool vu = p < a.Nu;
+            float gh[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (vu) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (a.g_pos) gh[c] = a.g_pos[p * 3 + c] * a.init_offset;
+                    if (a.g_scales) { const float s = a.scales[p * 3 + c]; gh[3 + c] = s < a.max_scale ? a.g_scales[p * 3 + c] * s : 0.f; }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int o = 0; o < 6; o++) Gcol[o * S] = gh[o];
+            load_act_tile(A, a.acts_d + 3 * HID * a.Nup, HID, a.Nup, p0, a.Nu);     // d4
+            __syncthreads();
+            {   // head weight gradients: 6 x 64 entries: e = tid (o = tid/64 < 4) and e = tid + 256 (o = 4 + tid/64, tid < 128)
+                const int i = tid & 63;
+                const float4* ar = reinterpret_cast<const float4*>(A + i * S);
+                const float4* g0 = reinterpret_cast<const float4*>(G + (tid >> 6) * S);
+                const float4* g1 = reinterpret_cast<const float4*>(G + (4 + ((tid >> 6) & 1)) * S);
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < P / 4; j++) { const float4 x = ar[j]; s0 += dot4(g0[j], x); s1 += dot4(g1[j], x); }
+                dWdh0 += s0;
+                if (tid < 128) dWdh1 += s1;
+                if (tid < 6) dbdh += row_sum(G, tid);
+            }
+            __syncthreads();
+            float gin[HID];
+            {   // heads -> d4: rows of the two head matrices (SCW is not 16-byte aligned: scalar loads)
+#pragma unroll
+                for (int i = 0; i < HID; i++) gin[i] = 0.f;
+#pragma unroll
+                for (int o = 0; o < 6; o++) {
+                    const float g = Gcol[o * S];
+                    const float* w = o < 3 ? Wsm + WPW + o * HID : Wsm + SCW + (o - 3) * HID;
+#pragma unroll
+                    for (int i = 0; i < HID; i++) gin[i] = fmaf(g, w[i], gin[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < HID; i++) gin[i] *= act_grad(Acol[i * S], ACT_LRELU);
+            }
+#pragma unroll
+            for (int i = 0; i < HID; i++) Gcol[i * S] = gin[i];
+#pragma unroll 1
+            for (int l = 3; l >= 1; l--) {
+                __syncthreads();
+                load_act_tile(A, a.acts_d + (l - 1) * HID * a.Nup, HID, a.Nup, p0, a.Nu);
+                __syncthreads();
+                if (l == 3) { wgrad_tile<HID>(G, A, dWd3); if (tid < HID) dbd3 += row_sum(G, tid); }
+                else if (l == 2) { wgrad_tile<HID>(G, A, dWd2); if (tid < HID) dbd2 += row_sum(G, tid); }
+                else { wgrad_tile<HID>(G, A, dWd1); if (tid < HID) dbd1 += row_sum(G, tid); }
+                __syncthreads();
+                dgrad_tile<HID, HID, ACT_LRELU, true>(Wsm + (l == 3 ? D3W : (l == 2 ? D2W : D1W)), Gcol, Acol, gin);
+#pragma unroll
+                for (int i = 0; i < HID; i++) Gcol[i * S] = gin[i];
+            }
+            __syncthreads();
+            load_enc_column(a.enc, p, vu, Acol, S);
+            __syncthreads();
+            wgrad_tile<ENC>(G, A, dWd0);
+            if (tid < HID) dbd0 += row_sum(G, tid);
+            __syncthreads();
+            float ge[ENC];
+            dgrad_tile<HID, ENC, ACT_NONE, true>(Wsm + D0W, Gcol, Acol, ge);
+            if (vu) {
+                float4* dst = reinterpret_cast<float4*>(a.g_enc + p * ENC);
+#pragma unroll
+                for (int j = 0; j < ENC / 4; j++) {
+                    float4 v = dst[j];
+                    v.x += ge[4 * j]; v.y += ge[4 * j + 1]; v.z += ge[4 * j + 2]; v.w += ge[4 * j + 3];
+                    dst[j] = v;
+                }
+            }
+        }
+    }
+    // ---- per-CTA partial gradient vector
+    float* out = a.partial + (int64_t)blockIdx.x * NPARAM;
+    const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int o = ty + 16 * q, i = tx + 16 * b;
+            out[S2W + o * HID + i] = dWs2[q * 4 + b];
+            out[D1W + o * HID + i] = dWd1[q * 4 + b];
+            out[D2W + o * HID + i] = dWd2[q * 4 + b];
+            out[D3W + o * HID + i] = dWd3[q * 4 + b];
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const int o = ty + 16 * q, i = tx + 16 * b;
+            out[S1W + o * ENC + i] = dWs1[q * 2 + b];
+            out[D0W + o * ENC + i] = dWd0[q * 2 + b];
+        }
+    }
+    out[S3W + tid] = dWs3;                                          // [4][64] row-major == tid
+    {
+        const int o = tid >> 6, i = tid & 63;
+        if (o < 3) out[WPW + o * HID + i] = dWdh0; else out[SCW + i] = dWdh0;
+        if (tid < 128) out[SCW + (1 + (tid >> 6)) * HID + i] = dWdh1;
+    }
+    if (tid < HID) {
+        out[S1B + tid] = dbs1; out[S2B + tid] = dbs2;
+        out[D0B + tid] = dbd0; out[D1B + tid] = dbd1; out[D2B + tid] = dbd2; out[D3B + tid] = dbd3;
+    }
+    if (tid < 4) out[S3B + tid] = dbs3;
+    if (tid < 6) { if (tid < 3) out[WPB + tid] = dbdh; else out[SCB + tid - 3] = dbdh; }
+}
+
+// g_params[j] = sum over CTAs of partial[c][j]; g_w_pose[o][j] = g_bias0[o] * pose[j]
+__global__ void __launch_bounds__(256)
+mlp_reduce_kernel(const float* __restrict__ partial, int nparts, const float* __restrict__ pose, float* __restrict__ g_params,
+                  float* __restrict__ g_w_pose) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < NPARAM) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int c = 0;
+        for (; c + 3 < nparts; c += 4) {
+            s0 += partial[(int64_t)c * NPARAM + j]; s1 += partial[(int64_t)(c + 1) * NPARAM + j];
+            s2 += partial[(int64_t)(c + 2) * NPARAM + j]; s3 += partial[(int64_t)(c + 3) * NPARAM + j];
+        }
+        for (; c < nparts; c++) s0 += partial[(int64_t)c * NPARAM + j];
+        const float s = (s0 + s1) + (s2 + s3);
+        g_params[j] = s;
+        if (g_w_pose && j >= D0B && j < D0B + HID) {
+            const int o = j - D0B;
+            for (int k = 0; k < POSE; k++) g_w_pose[o * POSE + k] = s * pose[k];
+        }
+    }
+}
+
+static int g_sms = 0;
+static int num_sms() {
+    if (!g_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sms <= 0) g_sms = kNumSMs;
+    }
+    return g_sms;
+}
+constexpr size_t kFwdSmem = sizeof(float) * (size_t)(2 * ENC * HID + 4 * HID * HID + HID * 4 + HID * 8 + 7 * HID + 4 + 8 + HID * P) + 16;
+constexpr size_t kBwdSmem = sizeof(float) * (size_t)(((NPARAM + 3) & ~3) + 2 * HID * S) + 16;
+
+}  // namespace mlp
+}  // namespace dwg
+
+using namespace dwg;
+using namespace dwg::mlp;
+
+extern "C" int64_t dwg_avatar_mlp_param_count(void) { return NPARAM; }
+extern "C" int64_t dwg_avatar_mlp_scratch_bytes(void) { return (int64_t)sizeof(float) * NPARAM * num_sms(); }
+
+// Forward of both MLPs + activations for N Gaussians (the first Nu are unconstrained: both nets; the
+// rest are mesh-bound: colour only, opacity 1).  acts_s [2][64][Np], acts_d [4][64][Nup] (Np, Nup =
+// N, Nu rounded up to a multiple of 4) receive the hidden activations for the backward (pass null
+// for inference).
+extern "C" int dwg_avatar_mlp_fwd(const float* enc, const float* positions, const float* params, const float* w_pose, const float* body_pose,
+                                  float* colors, float* opac, float* pos_out, float* scales, float* acts_s, float* acts_d,
+                                  int64_t N, int64_t Nu, float init_offset, float init_scale, float max_scale, void* stream) {
+    DWG_REQUIRE(enc && params && w_pose && body_pose && colors && opac, "null pointer");
+    DWG_REQUIRE(N > 0 && Nu >= 0 && Nu <= N, "bad sizes");
+    DWG_REQUIRE(Nu == 0 || (positions && pos_out && scales), "null pointer (unconstrained outputs)");
+    DWG_REQUIRE(((uintptr_t)enc & 15) == 0, "enc must be 16-byte aligned");
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem); attr = true; }
+    FwdArgs a;
+    a.enc = enc; a.positions = positions; a.params = params; a.w_pose = w_pose; a.pose = body_pose;
+    a.colors = colors; a.opac = opac; a.pos_out = pos_out; a.scales = scales; a.acts_s = acts_s; a.acts_d = acts_d;
+    a.N = N; a.Nu = Nu; a.Np = (N + 3) & ~(int64_t)3; a.Nup = (Nu + 3) & ~(int64_t)3;
+    a.init_offset = init_offset; a.init_scale = init_scale; a.max_scale = max_scale;
+    const int64_t ntiles = (N + P - 1) / P;
+    const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
+    mlp_fwd_kernel<<<grid, P, kFwdSmem, (cudaStream_t)stream>>>(a);
+    return check_launch("dwg_avatar_mlp_fwd");
+}
+
+// Backward: g_enc [N,32] (overwritten), g_params [NPARAM] and g_w_pose [64,63] (overwritten); `scratch`
+// = dwg_avatar_mlp_scratch_bytes() bytes.  Null output-gradient pointers mean zero.
+extern "C" int dwg_avatar_mlp_bwd(const float* enc, const float* params, const float* body_pose,
+                                  const float* colors, const float* opac, const float* scales, const float* acts_s, const float* acts_d,
+                                  const float* g_colors, const float* g_opac, const float* g_pos, const float* g_scales,
+                                  float* g_enc, float* g_params, float* g_w_pose, void* scratch,
+                                  int64_t N, int64_t Nu, float init_offset, float max_scale, void* stream) {
+    DWG_REQUIRE(enc && params && body_pose && colors && opac && acts_s && g_enc && g_params && scratch, "null pointer");
+    DWG_REQUIRE(N > 0 && Nu >= 0 && Nu <= N, "bad sizes");
+    DWG_REQUIRE(Nu == 0 || (scales && acts_d), "null pointer (unconstrained inputs)");
+    DWG_REQUIRE(((uintptr_t)enc & 15) == 0 && ((uintptr_t)g_enc & 15) == 0 && ((uintptr_t)acts_s & 15) == 0 && ((uintptr_t)acts_d & 15) == 0,
+                "enc / g_enc / activations must be 16-byte aligned");
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem); attr = true; }
+    BwdArgs a;
+    a.enc = enc; a.params = params; a.colors = colors; a.opac = opac; a.scales = scales; a.acts_s = acts_s; a.acts_d = acts_d;
+    a.g_colors = g_colors; a.g_opac = g_opac; a.g_pos = g_pos; a.g_scales = g_scales;
+    a.g_enc = g_enc; a.partial = reinterpret_cast<float*>(scratch);
+    a.N = N; a.Nu = Nu; a.Np = (N + 3) & ~(int64_t)3; a.Nup = (Nu + 3) & ~(int64_t)3;
+    a.init_offset = init_offset; a.max_scale = max_scale;
+    const int64_t ntiles = (N + P - 1) / P;
+    const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
+    cudaStream_t st = (cudaStream_t)stream;
+    mlp_bwd_kernel<<<grid, P, kBwdSmem, st>>>(a);
+    mlp_reduce_kernel<<<(NPARAM + 255) / 256, 256, 0, st>>>(a.partial, grid, body_pose, g_params, g_w_pose);
+    return check_launch("dwg_avatar_mlp_bwd");
+}

@@ -70,7 +70,7 @@ struct Params {
     // tiling
     int BN, stages;
     int m_tiles, n_tiles, nz, ksplit, total_tiles;
-    float* workspace;               // split-K partial tiles
+    float* workspace;               // split-K fp32 tile accumulators (zero when idle)
     int* counters;                  // one per output tile, self-resetting
 };
 
@@ -355,19 +355,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t taddr_row = tmem_base + as * TMEM_STAGE_COLS + ((uint32_t)(q * 32) << 16);
 
             bool released = false;
+            const int out_tile = (tc.z * p.n_tiles + tc.n_tile) * p.m_tiles + tc.m_tile;
+            // fp32 tile accumulator in global memory (zero when idle), laid out [32-col chunk][float4 j][row]: coalesced
+            float4* wsp = reinterpret_cast<float4*>(p.workspace) + (int64_t)out_tile * (p.BN / 32) * (8 * 128) + r0 + lane;
             if (p.ksplit > 1) {
-                // ---- split-K: publish this CTA's partial tile, find out whether we are the last arriver
-                const int out_tile = (tc.z * p.n_tiles + tc.n_tile) * p.m_tiles + tc.m_tile;
+                // ---- split-K: every CTA of the tile adds its partial accumulator with 16-byte vector atomics
+                // (L2-side reduction), then bumps the tile counter; the LAST arriver owns the epilogue.
                 const int acc_chunks = p.BN / 32;
-                float4* wsp = reinterpret_cast<float4*>(p.workspace) + ((int64_t)out_tile * p.ksplit + tc.ks) * acc_chunks * (8 * 128);
 #pragma unroll 1
                 for (int c = half; c < acc_chunks; c += 2) {
                     float v[32];
                     tc_ld32(taddr_row + (uint32_t)(c * 32), v);
-                    float4* dst = wsp + (int64_t)c * (8 * 128) + r0 + lane;
+                    float4* dst = wsp + (int64_t)c * (8 * 128);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) dst[j * 128] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 8; j++) atomicAdd(dst + j * 128, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                 }
+                released = true;                                     // the accumulator stage is free again
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
                 __threadfence();
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");
                 if (e == 0 && lane == 0) {
@@ -380,12 +386,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");
                 const int last = *s_flag;
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");      // everyone has read the flag before the next tile rewrites it
-                if (!last) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[as]);
-                    continue;
-                }
+                if (!last) continue;
                 if (use_res && half < nchunks && lane == 0) {
                     const uint32_t b = slot & 1u;
                     mbar_expect_tx(&rbar[b], 2048);
@@ -421,21 +422,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         f[16 + 2 * j + 1] = fmaf(g[4 * j + 2], p.alpha, b1.z) * gelu_f(fmaf(g[4 * j + 3], p.alpha, b1.w));
                     }
                 } else {
-                    tc_ld32(taddr_row + (uint32_t)acol0, f);
                     if (p.ksplit > 1) {
-                        // last arriver: add the other splits' partial tiles (L2-resident, written by other SMs -> ld.cg)
-                        const int out_tile = (tc.z * p.n_tiles + tc.n_tile) * p.m_tiles + tc.m_tile;
-                        const int acc_chunks = p.BN / 32;
-                        for (int k = 0; k < p.ksplit; k++) {
-                            if (k == tc.ks) continue;
-                            const float4* src = reinterpret_cast<const float4*>(p.workspace) +
-                                                (((int64_t)out_tile * p.ksplit + k) * acc_chunks + c) * (8 * 128) + r0 + lane;
+                        // last arriver: the complete sums are in the L2-resident tile accumulator; read and re-zero it
+                        float4* src = wsp + (int64_t)c * (8 * 128);
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const float4 u = __ldcg(src + j * 128);
-                                f[4 * j] += u.x; f[4 * j + 1] += u.y; f[4 * j + 2] += u.z; f[4 * j + 3] += u.w;
-                            }
+                        for (int j = 0; j < 8; j++) {
+                            const float4 u = __ldcg(src + j * 128);
+                            f[4 * j] = u.x; f[4 * j + 1] = u.y; f[4 * j + 2] = u.z; f[4 * j + 3] = u.w;
+                            __stcg(src + j * 128, make_float4(0.f, 0.f, 0.f, 0.f));
                         }
+                    } else {
+                        tc_ld32(taddr_row + (uint32_t)acol0, f);
                     }
                     const bool full_chunk = (ocol0 + 32 <= p.N) && !p.direct;
                     if (full_chunk) {
@@ -534,7 +531,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
             }
         }
-        if (lane == 0) bulk_wait_all();                      // smem must stay valid until the last TMA store has read it
+        if (lane == 0) bulk_wait_read<0>();                  // smem must stay valid until the last TMA store has read it
     }
     tc_fence_before();
     __syncthreads();
@@ -585,7 +582,7 @@ static int make_map_bf16(CUtensorMap* m, const void* base, const uint64_t dims[4
 }
 
 static int g_num_sms = 0;
-static float* g_ws = nullptr;            // split-K partial tiles (grown on demand, never shrunk)
+static float* g_ws = nullptr;            // split-K fp32 tile accumulators (zero when idle)
 static size_t g_ws_bytes = 0;
 static int* g_counters = nullptr;        // split-K arrival counters (zero when idle)
 constexpr int kMaxCounters = 1 << 16;
@@ -600,7 +597,28 @@ static size_t smem_fixed(int epi, int has_res) {
 //   k-iteration = max(tensor pipe 2*BN, smem operand read 128 + BN, L2->SM feed of the CTAs running together)
 //   tile        = k-iterations + epilogue (TMEM drain + math + staging, two warps per lane quadrant)
 struct Plan { int BN, ks, stages; };
+static int g_force_bn = 0, g_force_ks = 0;        // tuning override (dwg_gemm_tune), 0 = automatic
+static Plan g_last_plan = {0, 0, 0};
+static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats);
 static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats) {
+    Plan pl = plan_tiles_auto(m_tiles, nz, N, iters, epi, has_res, ws_cap_floats);
+    if (g_force_bn > 0) {
+        const int gran = (epi == EPI_GEGLU) ? 64 : 32;
+        int BN = (g_force_bn + gran - 1) / gran * gran;
+        if (BN > 256) BN = 256;
+        int ks = g_force_ks > 0 ? g_force_ks : 1;
+        if (epi == EPI_GEGLU) ks = 1;
+        if (ks > iters) ks = iters;
+        const int64_t tiles = (int64_t)m_tiles * ((N + BN - 1) / BN) * nz;
+        if (ks > 1 && (tiles > (1 << 16) || tiles * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
+        int stages = (int)((kSmemBudget - smem_fixed(epi, has_res)) / (A_BYTES + (size_t)BN * 128));
+        if (stages > kMaxStages) stages = kMaxStages;
+        pl = {BN, ks, stages};
+    }
+    g_last_plan = pl;
+    return pl;
+}
+static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats) {
     const int gran = (epi == EPI_GEGLU) ? 64 : 32;
     Plan best = {gran, 1, 2};
     double best_t = 1e30;
@@ -612,9 +630,9 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
         if (stages > kMaxStages) stages = kMaxStages;
         if (stages < 2) continue;
         const int64_t tiles = (int64_t)m_tiles * n_tiles * nz;
-        for (int ks = 1; ks <= 16; ks++) {
+        for (int ks = 1; ks <= 32; ks++) {
             if (ks > 1 && (epi == EPI_GEGLU || iters / ks < 2 || tiles * ks > 2 * g_num_sms)) break;
-            if (ks > 1 && (tiles > kMaxCounters || tiles * ks * 128 * (int64_t)BN > ws_cap_floats)) break;
+            if (ks > 1 && (tiles > kMaxCounters || tiles * 128 * (int64_t)BN > ws_cap_floats)) break;
             const int64_t ctas = tiles * ks;
             const double active = (double)(ctas < g_num_sms ? ctas : g_num_sms);
             const double feed = (double)stage_bytes * active / 6000.0;          // ~6.3 KB/cycle chip-wide TMA throughput
@@ -628,7 +646,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
             const double waves = (double)((ctas + g_num_sms - 1) / g_num_sms);
             double t_tile = t_main > t_epi ? t_main : t_epi;                    // steady state of a persistent CTA
             double t = 2500.0 + 1500.0 /* first TMA */ + (waves - 1.0) * t_tile + t_main + t_epi;
-            if (ks > 1) t += 1200.0 + (ks - 1) * BN * 6.0;                      // partial write + counter + reading the other partials
+            if (ks > 1) t += 1500.0 + BN * 8.0;                                 // vector-atomic partial adds + counter + tile read-back
             if (t < best_t) { best_t = t; best = {BN, ks, stages}; }
         }
     }
@@ -657,6 +675,8 @@ static int ensure_globals() {
         cudaMemset(g_counters, 0, sizeof(int) * kMaxCounters);
         g_ws_bytes = (size_t)64 << 20;
         if (cudaMalloc(&g_ws, g_ws_bytes) != cudaSuccess) { g_ws = nullptr; g_ws_bytes = 0; set_error("split-K workspace allocation failed"); return DWG_ERR_CUDA; }
+        cudaMemset(g_ws, 0, g_ws_bytes);                 // tile accumulators are zero when idle (the last arriver re-zeroes what it reads)
+        cudaDeviceSynchronize();
     }
     return DWG_OK;
 }
@@ -839,4 +859,13 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
         }
     }
     return launch(tmA, tmB, tmC, tmR, p, epi, (cudaStream_t)stream);
+}
+
+/* Tuning / introspection (tools/gemm_sweep.py): force the tile width and split count of the next
+ * launches (0, 0 = automatic), and read back the plan of the last launch as (BN, ksplit, stages). */
+extern "C" int dwg_gemm_tune(int force_bn, int force_ks) { g_force_bn = force_bn; g_force_ks = force_ks; return DWG_OK; }
+extern "C" int dwg_gemm_last_plan(int* out3) {
+    DWG_REQUIRE(out3, "null pointer");
+    out3[0] = g_last_plan.BN; out3[1] = g_last_plan.ks; out3[2] = g_last_plan.stages;
+    return DWG_OK;
 }

@@ -35,7 +35,8 @@ class GaussianOutput:
 
 
 class MLP(nn.Module):
-    """core/nerf/nerf_model.py:12-33."""
+    """Parameters of core/nerf/nerf_model.py:12-33 (state-dict names net.{i}.{weight,bias}).  The
+    arithmetic runs in the fused kernel dwg_avatar_mlp_fwd/bwd (ops.avatar_mlp); there is no torch path."""
 
     def __init__(self, dim_in, dim_out, dim_hidden, num_layers, bias=True):
         super().__init__()
@@ -44,16 +45,9 @@ class MLP(nn.Module):
                                             dim_out if l == num_layers - 1 else dim_hidden, bias=bias)
                                   for l in range(num_layers)])
 
-    def forward(self, x):
-        for l in range(self.num_layers):
-            x = self.net[l](x)
-            if l != self.num_layers - 1:
-                x = F.relu(x)
-        return x
-
 
 class DeformNetwork(nn.Module):
-    """core/deformation/deform_model.py:61-143 (D=4, W=64, no skip, is_6dof=False)."""
+    """Parameters of core/deformation/deform_model.py:61-143 (D=4, W=64, no skip, is_6dof=False); see MLP."""
 
     def __init__(self, xyz_input_ch=32, pose_input_ch=63, D=4, W=64):
         super().__init__()
@@ -61,12 +55,6 @@ class DeformNetwork(nn.Module):
         self.gaussian_warp = nn.Linear(W, 3)
         self.gaussian_rotation = nn.Linear(W, 4)
         self.gaussian_scaling = nn.Linear(W, 3)
-
-    def forward(self, x, body_pose):
-        h = torch.cat([x, body_pose.expand(x.shape[0], -1)], dim=-1)
-        for lin in self.layers:
-            h = F.leaky_relu(lin(h))
-        return self.gaussian_warp(h), self.gaussian_scaling(h), self.gaussian_rotation(h)
 
 
 class GridEncoder(nn.Module):
@@ -162,11 +150,9 @@ class DreamWaltzGAvatar(nn.Module):
     def _joint_pose_transform(self, transforms):
         return dlbs.RigidTransform.compose(transforms['J_pose_rigid'], transforms['G_transl_offset']).squeeze(0)
 
-    def static_mlp_forward(self, enc, fix_opacities=False):
-        o = self.nerf_opacity_and_color_net(enc)
-        colors = torch.sigmoid(o[:, 1:])
-        opac = torch.ones_like(o[:, :1]) if fix_opacities else torch.sigmoid(o[:, :1])
-        return colors, opac
+    def _mlp_params(self):
+        named = dict(self.named_parameters())
+        return [named[n] for n in ops.AVATAR_MLP_PARAMS]
 
     def animate(self, smpl_observed_inputs: Optional[dict] = None) -> GaussianOutput:
         if smpl_observed_inputs is None:
@@ -184,33 +170,34 @@ class DreamWaltzGAvatar(nn.Module):
         W = self.get_lbs_weights()
         cnl_jt = self._joint_pose_transform(cnl_tr)
         obs_jt = self._joint_pose_transform(obs_tr)
-        canonical_positions = cnl_jt.transform_points(positions, weights=W)
-        enc = self.nerf_encoder(canonical_positions, bound=self.nerf_bound)
-        colors, opacities = self.static_mlp_forward(enc)
-        body_pose = smpl_observed_inputs.get('body_pose', torch.zeros(1, 63, device=self.device))
-        offsets, d_scales, _ = self.nerf_scale_and_quaternion_net(enc, body_pose)
-        # non_rigid_transform (avatar.py:1464-1498, shipped flags)
-        pos = positions + offsets * self.init_offset
-        scales = (torch.exp(d_scales) * self.init_scale).clamp_max(self.max_scale)
+        n_unc = positions.shape[0]
+        cnl_T = cnl_V.squeeze(0) if cnl_V.SE3.dim() == 4 else cnl_V
+        obs_T = obs_V.squeeze(0) if obs_V.SE3.dim() == 4 else obs_V
+        # canonical positions of every Gaussian (unconstrained first, then the mesh-bound parts): ONE grid
+        # encode and ONE fused MLP launch serve all of them (avatar.py:1519-1535,1567-1572)
+        canon = [cnl_jt.transform_points(positions, weights=W)]
+        for _, gm in self.mesh_binding_gaussians.items():
+            cnl_vc = cnl_T.transform_points(gm._vertex_coords, indices=gm.predefined_vertex_indices)
+            canon.append(gm.get_positions(cnl_vc))
+        enc = self.nerf_encoder(torch.cat(canon, dim=0) if len(canon) > 1 else canon[0], bound=self.nerf_bound)
+        body_pose = smpl_observed_inputs.get('body_pose')
+        if body_pose is None:
+            body_pose = torch.zeros(1, 63, device=self.device)
+        # sigma net + deform net + non_rigid_transform (avatar.py:1283-1294,1464-1498, shipped flags) in one kernel
+        colors, opacities, pos, scales = ops.avatar_mlp(enc, positions, body_pose, self._mlp_params(), n_unc,
+                                                        self.init_offset, self.init_scale, self.max_scale)
         quats = F.normalize(self._quaternions)
         pos, quats = obs_jt.transform_points_and_quaternions(pos, quats, W)
-        out = GaussianOutput(positions=pos, opacities=opacities, colors=colors, quaternions=quats, scales=scales)
-        parts = [out]
+        if len(self.mesh_binding_gaussians) == 0:
+            return GaussianOutput(positions=pos, opacities=opacities, colors=colors, quaternions=quats, scales=scales)
+        all_pos, all_q, all_sc = [pos], [quats], [scales]
         for _, gm in self.mesh_binding_gaussians.items():
-            cnl_T, obs_T = cnl_V.squeeze(0) if cnl_V.SE3.dim() == 4 else cnl_V, obs_V.squeeze(0) if obs_V.SE3.dim() == 4 else obs_V
-            vidx = gm.predefined_vertex_indices
-            cnl_vc = cnl_T.transform_points(gm._vertex_coords, indices=vidx)
-            m_enc = self.nerf_encoder(gm.get_positions(cnl_vc), bound=self.nerf_bound)
-            m_col, m_op = self.static_mlp_forward(m_enc, fix_opacities=True)
-            obs_vc = obs_T.transform_points(gm._vertex_coords, indices=vidx)
+            obs_vc = obs_T.transform_points(gm._vertex_coords, indices=gm.predefined_vertex_indices)
             m_pos = gm.get_positions(obs_vc)
             m_sc, m_q = gm.get_scales_and_quaternions(obs_vc, m_pos)
-            parts.append(GaussianOutput(positions=m_pos, opacities=m_op, colors=m_col, quaternions=m_q, scales=m_sc))
-        if len(parts) == 1:
-            return out
-        cat = lambda k: torch.cat([getattr(p, k) for p in parts], dim=0)
-        return GaussianOutput(positions=cat('positions'), opacities=cat('opacities'), colors=cat('colors'),
-                              quaternions=cat('quaternions'), scales=cat('scales'))
+            all_pos.append(m_pos); all_q.append(m_q); all_sc.append(m_sc)
+        return GaussianOutput(positions=torch.cat(all_pos, dim=0), opacities=opacities, colors=colors,
+                              quaternions=torch.cat(all_q, dim=0), scales=torch.cat(all_sc, dim=0))
 
 
 class GaussianRenderer:

@@ -157,6 +157,85 @@ def grid_encode(x, table, spec):
     return _GridEncode.apply(x, table, spec)
 
 
+# ------------------------------------------------------------------------------ avatar MLPs
+class _AvatarMLP(torch.autograd.Function):
+    """(colors [N,3], opacities [N,1], positions' [Nu,3], scales [Nu,3]) = fused sigma-net + deform-net +
+    non-rigid transform (dwg_avatar_mlp_fwd/bwd).  Inputs after the scalars are the 18 parameter tensors in
+    the order of AVATAR_MLP_PARAMS; layers.0.weight is split into its grid ([:, :32]) and pose ([:, 32:]) parts."""
+
+    @staticmethod
+    def forward(ctx, enc, positions, body_pose, n_unc, init_offset, init_scale, max_scale, *params):
+        enc, positions = f32c(enc), f32c(positions)
+        N, Nu = enc.shape[0], int(n_unc)
+        assert enc.shape[1] == 32 and positions.shape == (Nu, 3) and len(params) == 18
+        w0 = params[6]                                           # layers.0.weight [64, 95]
+        flat = torch.cat([p.detach()[:, :32].reshape(-1) if i == 6 else p.detach().reshape(-1) for i, p in enumerate(params)])
+        L = lib()
+        assert flat.numel() == L.dwg_avatar_mlp_param_count()
+        w_pose = w0.detach()[:, 32:].contiguous()
+        pose = f32c(body_pose).reshape(-1)
+        dev = enc.device
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        colors, opac, pos, scales = e(N, 3), e(N, 1), e(Nu, 3), e(Nu, 3)
+        need_bwd = any(ctx.needs_input_grad)
+        Np, Nup = (N + 3) // 4 * 4, (Nu + 3) // 4 * 4
+        acts_s = e(2, 64, Np) if need_bwd else None
+        acts_d = e(4, 64, max(Nup, 4)) if need_bwd else None
+        check(L.dwg_avatar_mlp_fwd(ptr(enc), ptr(positions), ptr(flat), ptr(w_pose), ptr(pose), ptr(colors), ptr(opac), ptr(pos), ptr(scales),
+                                   ptr(acts_s), ptr(acts_d), N, Nu, float(init_offset), float(init_scale), float(max_scale), stream()),
+              'dwg_avatar_mlp_fwd')
+        ctx.save_for_backward(enc, flat, pose, colors, opac, scales, acts_s, acts_d)
+        ctx.dims = (N, Nu, float(init_offset), float(max_scale))
+        ctx.shapes = [p.shape for p in params]
+        return colors, opac, pos, scales
+
+    @staticmethod
+    def backward(ctx, g_colors, g_opac, g_pos, g_scales):
+        enc, flat, pose, colors, opac, scales, acts_s, acts_d = ctx.saved_tensors
+        N, Nu, init_offset, max_scale = ctx.dims
+        L = lib()
+        gc = lambda g: None if g is None else f32c(g)
+        g_colors, g_opac, g_pos, g_scales = gc(g_colors), gc(g_opac), gc(g_pos), gc(g_scales)
+        g_enc = torch.empty_like(enc)
+        g_flat = torch.empty_like(flat)
+        g_w_pose = torch.empty(64, 63, device=enc.device, dtype=torch.float32)
+        scratch = torch.empty(int(L.dwg_avatar_mlp_scratch_bytes()), device=enc.device, dtype=torch.uint8)
+        check(L.dwg_avatar_mlp_bwd(ptr(enc), ptr(flat), ptr(pose), ptr(colors), ptr(opac), ptr(scales), ptr(acts_s), ptr(acts_d),
+                                   ptr(g_colors), ptr(g_opac), ptr(g_pos), ptr(g_scales), ptr(g_enc), ptr(g_flat), ptr(g_w_pose), ptr(scratch),
+                                   N, Nu, init_offset, max_scale, stream()), 'dwg_avatar_mlp_bwd')
+        grads, off = [], 0
+        for i, shp in enumerate(ctx.shapes):
+            if i == 6:
+                ge = g_flat[off:off + 64 * 32].view(64, 32)
+                grads.append(torch.cat([ge, g_w_pose], dim=1))
+                off += 64 * 32
+            else:
+                n = int(np.prod(shp))
+                grads.append(g_flat[off:off + n].view(shp))
+                off += n
+        return (g_enc, g_pos, None, None, None, None, None, *grads)
+
+
+# parameter order of the flat vector (module-relative names)
+AVATAR_MLP_PARAMS = ('nerf_opacity_and_color_net.net.0.weight', 'nerf_opacity_and_color_net.net.0.bias',
+                     'nerf_opacity_and_color_net.net.1.weight', 'nerf_opacity_and_color_net.net.1.bias',
+                     'nerf_opacity_and_color_net.net.2.weight', 'nerf_opacity_and_color_net.net.2.bias',
+                     'nerf_scale_and_quaternion_net.layers.0.weight', 'nerf_scale_and_quaternion_net.layers.0.bias',
+                     'nerf_scale_and_quaternion_net.layers.1.weight', 'nerf_scale_and_quaternion_net.layers.1.bias',
+                     'nerf_scale_and_quaternion_net.layers.2.weight', 'nerf_scale_and_quaternion_net.layers.2.bias',
+                     'nerf_scale_and_quaternion_net.layers.3.weight', 'nerf_scale_and_quaternion_net.layers.3.bias',
+                     'nerf_scale_and_quaternion_net.gaussian_warp.weight', 'nerf_scale_and_quaternion_net.gaussian_warp.bias',
+                     'nerf_scale_and_quaternion_net.gaussian_scaling.weight', 'nerf_scale_and_quaternion_net.gaussian_scaling.bias')
+
+
+def avatar_mlp(enc, positions, body_pose, params, n_unconstrained, init_offset=0.01, init_scale=1e-3, max_scale=0.01):
+    """enc [N,32] (first n_unconstrained rows: unconstrained Gaussians), positions [Nu,3], body_pose [1,63],
+    params: the 18 tensors of AVATAR_MLP_PARAMS order -> colors [N,3], opacities [N,1], positions' [Nu,3], scales [Nu,3]."""
+    p = list(params)
+    assert len(p) == 18
+    return _AvatarMLP.apply(enc, positions, body_pose, n_unconstrained, init_offset, init_scale, max_scale, *p)
+
+
 # ------------------------------------------------------------------------------ rasteriser
 def _camera_struct(H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier):
     cam = _lib.DwgRasterCamera()

@@ -161,6 +161,40 @@ int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                   const float* bias, const float* bias2, int bias2_rows_per,
                   const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
                   float alpha, int act, void* stream);
+/* dwg_avatar_mlp_fwd / _bwd: the two per-Gaussian MLPs of DreamWaltzG.animate with their
+ * activations, fused (fp32).  Replaces reference core/nerf/nerf_model.py:12-33 (MLP 32-64-64-4,
+ * ReLU) as used by static_mlp_forward core/system/avatar.py:1283-1290, DeformNetwork.forward
+ * core/deformation/deform_model.py:102-143 (D=4, W=64, leaky_relu; heads warp / scaling) as used by
+ * dynamic_mlp_forward avatar.py:1292-1294, and non_rigid_transform avatar.py:1464-1498 with the
+ * shipped flags (pos = positions + init_offset*warp; scales = min(exp(scaling)*init_scale, max_scale)).
+ *   enc [N,32] grid features; the first Nu Gaussians are unconstrained (both nets), the remaining
+ *   N-Nu are mesh-bound (colour net only, opacity = 1).
+ *   params: flat fp32 vector of dwg_avatar_mlp_param_count() floats, concatenation of
+ *     net.0.{weight[64,32],bias} net.1.{weight[64,64],bias} net.2.{weight[4,64],bias}
+ *     layers.0.weight[:, :32] layers.0.bias layers.{1,2,3}.{weight,bias}
+ *     gaussian_warp.{weight[3,64],bias} gaussian_scaling.{weight[3,64],bias};
+ *   w_pose = layers.0.weight[:, 32:95] [64,63], body_pose [63].
+ *   acts_s [2][64][Np], acts_d [4][64][Nup] (Np/Nup = N/Nu rounded up to 4): hidden activations kept
+ *   for the backward (null = inference).  Backward overwrites g_enc [N,32], g_params (same layout as
+ *   params) and g_w_pose [64,63]; null output-gradient pointers mean zero; scratch =
+ *   dwg_avatar_mlp_scratch_bytes() bytes. */
+int64_t dwg_avatar_mlp_param_count(void);
+int64_t dwg_avatar_mlp_scratch_bytes(void);
+int dwg_avatar_mlp_fwd(const float* enc, const float* positions, const float* params, const float* w_pose, const float* body_pose,
+                       float* colors, float* opac, float* pos_out, float* scales, float* acts_s, float* acts_d,
+                       int64_t N, int64_t Nu, float init_offset, float init_scale, float max_scale, void* stream);
+int dwg_avatar_mlp_bwd(const float* enc, const float* params, const float* body_pose,
+                       const float* colors, const float* opac, const float* scales, const float* acts_s, const float* acts_d,
+                       const float* g_colors, const float* g_opac, const float* g_pos, const float* g_scales,
+                       float* g_enc, float* g_params, float* g_w_pose, void* scratch,
+                       int64_t N, int64_t Nu, float init_offset, float max_scale, void* stream);
+
+/* Tuning / introspection of the tcgen05 GEMM tile planner (no reference counterpart; used by
+ * tools/gemm_sweep.py): force BN (tile width) and the split-K factor of subsequent launches
+ * (0, 0 = automatic); read the (BN, ksplit, stages) the last launch ran with. */
+int dwg_gemm_tune(int force_bn, int force_ks);
+int dwg_gemm_last_plan(int* out3);
+
 /* dwg_conv2d_nhwc_bf16: implicit-GEMM convolution, no im2col buffer.
  *   x [Nimg,H,W,Cin] bf16 (Cin % 8 == 0), w [Cout,k,k,Cin] bf16, y [Nimg,Ho,Wo,Cout] bf16/fp32,
  *   ksize 1|3, stride 1|2, zero padding pad_h/pad_w on the top/left (bottom/right implied by

@@ -362,3 +362,52 @@ def test_render_end_to_end_gradients_flow_to_all_avatar_parameters():
               'mesh_binding_gaussians.hands._scales'):
         p = dict(m.named_parameters())[n]
         assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0, n
+
+
+@pytest.mark.parametrize('N,Nu', [(1000, 701), (300, 300), (259, 0), (5000, 4093)])
+def test_avatar_mlp_fused_forward_backward_vs_oracle(N, Nu):
+    """dwg_avatar_mlp_fwd/bwd (sigma net + DeformNetwork + non_rigid_transform, fp32) against the oracle's
+    torch-CPU restatement (oracle/avatar.py, pinned to the reference's own MLP / DeformNetwork by the golden
+    vectors) and its autograd gradients.  Tolerance: fp32 with a different summation order -> 2e-5 relative
+    on the outputs, 2e-4 of the largest gradient entry on every gradient."""
+    from oracle import avatar as oav
+    g = torch.Generator().manual_seed(N + Nu)
+    rnd = lambda *s, sc=0.3: torch.randn(*s, generator=g) * sc
+    shapes = [(64, 32), (64,), (64, 64), (64,), (4, 64), (4,), (64, 95), (64,), (64, 64), (64,), (64, 64), (64,), (64, 64), (64,),
+              (3, 64), (3,), (3, 64), (3,)]
+    params = [rnd(*s).requires_grad_(True) for s in shapes]
+    enc = (torch.rand(N, 32, generator=g) - 0.5).requires_grad_(True)
+    positions = rnd(Nu, 3, sc=1.0).requires_grad_(True)
+    body_pose = rnd(1, 63, sc=0.5)
+    # ---- oracle
+    colors_u, opac_u = oav.static_heads(enc[:Nu], params[0:6:2], params[1:6:2])
+    colors_m, opac_m = oav.static_heads(enc[Nu:], params[0:6:2], params[1:6:2], fix_opacities=True)
+    dp = {**{f'layers.{i}.weight': params[6 + 2 * i] for i in range(4)}, **{f'layers.{i}.bias': params[7 + 2 * i] for i in range(4)},
+          'gaussian_warp.weight': params[14], 'gaussian_warp.bias': params[15], 'gaussian_scaling.weight': params[16],
+          'gaussian_scaling.bias': params[17], 'gaussian_rotation.weight': torch.zeros(4, 64), 'gaussian_rotation.bias': torch.zeros(4)}
+    d_xyz, d_scale, _ = oav.deform_forward(enc[:Nu], body_pose, dp)
+    # a large scaling bias on a few rows exercises the clamp_max branch
+    pos_r, scales_r, _ = oav.non_rigid(positions, d_xyz, d_scale + 2.0, torch.ones(max(Nu, 1), 4))
+    ref = [torch.cat([colors_u, colors_m]), torch.cat([opac_u, opac_m]), pos_r, scales_r]
+    wts = [torch.randn(r.shape, generator=g) for r in ref]
+    loss = sum((r * w).sum() for r, w in zip(ref, wts))
+    gr = torch.autograd.grad(loss, [enc, positions] + params, allow_unused=True)
+    # ---- device (the +2.0 on the scaling head is a bias shift)
+    dev_params = [p.detach().clone().to(DEV).requires_grad_(True) for p in params]
+    with torch.no_grad():
+        dev_params[17] += 2.0
+    enc_d = enc.detach().to(DEV).requires_grad_(True)
+    pos_d = positions.detach().to(DEV).requires_grad_(True)
+    out = ops.avatar_mlp(enc_d, pos_d, body_pose.to(DEV), dev_params, Nu)
+    for o, r, name in zip(out, ref, ('colors', 'opacities', 'positions', 'scales')):
+        torch.testing.assert_close(o.detach().cpu(), r.detach(), rtol=2e-5, atol=2e-6, msg=lambda s, n=name: f'{n}: {s}')
+    loss_d = sum((o * w.to(DEV)).sum() for o, w in zip(out, wts))
+    gd = torch.autograd.grad(loss_d, [enc_d, pos_d] + dev_params, allow_unused=True)
+    names = ['enc', 'positions'] + [f'param{i}' for i in range(18)]
+    for a, b, name in zip(gd, gr, names):
+        if b is None or b.numel() == 0:
+            continue
+        assert a is not None, name
+        scale = float(b.abs().max()) + 1e-12
+        err = float((a.cpu() - b).abs().max()) / scale
+        assert err < 2e-4, (name, err)
