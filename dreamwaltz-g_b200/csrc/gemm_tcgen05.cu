@@ -599,9 +599,28 @@ static size_t smem_fixed(int epi, int has_res) {
 struct Plan { int BN, ks, stages; };
 static int g_force_bn = 0, g_force_ks = 0;        // tuning override (dwg_gemm_tune), 0 = automatic
 static Plan g_last_plan = {0, 0, 0};
+static int g_last_key[6] = {0, 0, 0, 0, 0, 0};
+// Measured plans for the shapes of the SDS step on a 148-SM B200 (tools/gemm_autotune.py writes the
+// table: cold weights, warm activations, CUDA-graph replays); anything else falls back to the model.
+struct TunedPlan { int m_tiles, nz, N, iters, epi, has_res, BN, ks; };
+static const TunedPlan kTuned[] = {
+#include "gemm_plan_table.inc"
+    {0, 0, 0, 0, 0, 0, 0, 0}};
 static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats);
 static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats) {
     Plan pl = plan_tiles_auto(m_tiles, nz, N, iters, epi, has_res, ws_cap_floats);
+    g_last_key[0] = m_tiles; g_last_key[1] = nz; g_last_key[2] = N; g_last_key[3] = iters; g_last_key[4] = epi; g_last_key[5] = has_res;
+    if (g_num_sms == kNumSMs && g_force_bn == 0) {
+        for (const TunedPlan* t = kTuned; t->BN; t++) {
+            if (t->m_tiles == m_tiles && t->nz == nz && t->N == N && t->iters == iters && t->epi == epi && t->has_res == has_res) {
+                const int64_t tiles = (int64_t)m_tiles * ((N + t->BN - 1) / t->BN) * nz;
+                int stages = (int)((kSmemBudget - smem_fixed(epi, has_res)) / (A_BYTES + (size_t)t->BN * 128));
+                if (stages > kMaxStages) stages = kMaxStages;
+                if (stages >= 2 && (t->ks == 1 || (tiles <= (1 << 16) && tiles * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters))) pl = {t->BN, t->ks, stages};
+                break;
+            }
+        }
+    }
     if (g_force_bn > 0) {
         const int gran = (epi == EPI_GEGLU) ? 64 : 32;
         int BN = (g_force_bn + gran - 1) / gran * gran;
@@ -867,5 +886,11 @@ extern "C" int dwg_gemm_tune(int force_bn, int force_ks) { g_force_bn = force_bn
 extern "C" int dwg_gemm_last_plan(int* out3) {
     DWG_REQUIRE(out3, "null pointer");
     out3[0] = g_last_plan.BN; out3[1] = g_last_plan.ks; out3[2] = g_last_plan.stages;
+    return DWG_OK;
+}
+/* the planner key of the last launch: (m_tiles, nz, N, k_iterations, epilogue kind, has_residual) */
+extern "C" int dwg_gemm_last_key(int* out6) {
+    DWG_REQUIRE(out6, "null pointer");
+    for (int i = 0; i < 6; i++) out6[i] = g_last_key[i];
     return DWG_OK;
 }

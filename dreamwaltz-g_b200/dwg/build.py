@@ -36,7 +36,7 @@ def sources():
 def _digest(path, flags):
     h = hashlib.sha1()
     h.update(' '.join(flags).encode())
-    for dep in [path] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cuh', '.h'))] + \
+    for dep in [path] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cuh', '.h', '.inc'))] + \
             [os.path.join(os.path.dirname(PKG), 'include', 'dwg.h')]:
         with open(dep, 'rb') as fh:
             h.update(fh.read())

@@ -354,6 +354,7 @@ def rasterize(means3D, means2D, colors, opacities, scales, rotations, *, image_h
 # ------------------------------------------------------------------------------ tensor-core GEMM / conv
 ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3}
 PROFILE = None        # set to a list to record (start_event, end_event, flops, kind) per tensor-core launch
+TUNE_RECORD = None    # set to a list to record the arguments of every GEMM / conv call (tools/gemm_autotune.py)
 
 
 class _prof:
@@ -404,6 +405,8 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
         assert r4.stride(-1) == 1
     bias = None if bias is None else f32c(bias)
     bias2 = None if bias2 is None else f32c(bias2)
+    if TUNE_RECORD is not None:
+        TUNE_RECORD.append(('gemm', M, N, K, nb1, nb2, act, residual is not None, c4.dtype, bias is not None, bias2 is not None))
     with _prof(2.0 * M * N * K * nb1 * nb2, f'gemm M{M} N{N} K{K} b{nb1 * nb2}'):
         check(lib().dwg_gemm_bf16(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
                                   b4.data_ptr(), b4.stride(2), b4.stride(1), b4.stride(0),
@@ -435,6 +438,8 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
         assert residual.shape == y.shape and residual.is_contiguous()
     bias = None if bias is None else f32c(bias)
     bias2 = None if bias2 is None else f32c(bias2)
+    if TUNE_RECORD is not None:
+        TUNE_RECORD.append(('conv', Nimg, H, W, Cin, Cout, k, stride, ph, pw, Ho, Wo, residual is not None, out_dtype, bias2 is not None))
     with _prof(2.0 * Nimg * Ho * Wo * Cout * Cin * k * k, f'conv{k}x{k}s{stride} {Nimg}x{Ho}x{Wo} {Cin}->{Cout}'):
         check(lib().dwg_conv2d_nhwc_bf16(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.bfloat16), Nimg, H, W, Cin, Cout, k,
                                          stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], stream()),
