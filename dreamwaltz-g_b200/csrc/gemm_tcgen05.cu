@@ -72,8 +72,11 @@ struct Params {
     int m_tiles, n_tiles, nz, ksplit, total_tiles;
     float* workspace;               // split-K fp32 tile accumulators (zero when idle)
     int* counters;                  // one per output tile, self-resetting
+    unsigned long long* trace;      // optional [8] per-launch timeline of CTA 0 (globaltimer ns), null = off
 };
 
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TRACE(i) do { if (p.trace && blockIdx.x == 0) p.trace[i] = gtimer(); } while (0)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
@@ -136,6 +139,27 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
 }
 
+// asynchronous variant: the registers are valid only after tc_wait_ld() + reg_fence() on the same array
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// empty asm that "modifies" the 32 registers: pins every later use behind the preceding tc_wait_ld()
+__device__ __forceinline__ void reg_fence(float (&v)[32]) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                      "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                      "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]));
+}
+
 // K-major, 128B-swizzled operand tile [rows][64 bf16]: 8-row groups are 1024 B apart (SBO),
 // LBO is unused for swizzled K-major layouts (canonical value 1), descriptor version 1 (sm_100).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -194,7 +218,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* sB = sA + p.stages * A_BYTES;
     uint8_t* sStage = sB + p.stages * B_BYTES;                         // [kEpiWarps][2][STG_BYTES]
     uint8_t* sRes = sStage + kEpiWarps * 2 * STG_BYTES;                // [kEpiWarps][2][2048] (only when has_res)
-    uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.has_res ? kEpiWarps * 2 * 2048 : 0));
+    float* s_bias = reinterpret_cast<float*>(sRes + (p.has_res ? kEpiWarps * 2 * 2048 : 0));      // [tile parity][image 0/1][256]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + 2 * 2 * 256);
     uint64_t* empty = full + kMaxStages;
     uint64_t* tmem_full = empty + kMaxStages;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;              // [2]
@@ -204,6 +229,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5;
     const int iters_total = p.taps_h * p.taps_w * p.k_chunks;
+    if (threadIdx.x == 0) TRACE(0);
 
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
@@ -225,7 +251,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                 // everything above overlapped the predecessor's tail; its outputs are visible from here on
+    if (threadIdx.x == 0) TRACE(1);
+    pdl_wait();
+    if (threadIdx.x == 0) TRACE(2);                 // everything above overlapped the predecessor's tail; its outputs are visible from here on
     pdl_trigger();
 
     // k-iteration range of a split
@@ -285,13 +313,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 if (elect_one()) {
+                    if (tl == 0 && it == it0) TRACE(3);
                     const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES));
                     const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++)
                         tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
                     tc_commit(&empty[s]);
-                    if (it == it1 - 1) tc_commit(&tmem_full[as]);
+                    if (it == it1 - 1) { tc_commit(&tmem_full[as]); if (tl == 0) TRACE(4); }
                 }
                 __syncwarp();
                 if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
@@ -344,6 +373,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int ntile0 = tc.n_tile * p.BN;
             const int otile0 = (EPI == EPI_GEGLU) ? (ntile0 >> 1) : ntile0;      // first OUTPUT column of the tile
             const bool use_res = p.has_res && box_ok && !p.direct;
+            // ---- bias (+ per-image time-embedding bias) of the tile's columns -> shared memory, while the MMAs run.
+            // Double-buffered by tile parity: the one barrier per tile also orders the reuse two tiles later.
+            const bool stage_b2 = p.bias2 && p.conv_mode && p.BNI <= 2;
+            float* sb = s_bias + (tl & 1u) * 512;
+            {
+                const int img0 = p.conv_mode ? (tc.m_tile / (p.tiles_w * p.tiles_h)) * p.BNI : 0;
+                for (int cc = threadIdx.x - 128; cc < p.BN; cc += 32 * kEpiWarps) {
+                    const int n = ntile0 + cc;
+                    float v0 = 0.f, v1 = 0.f;
+                    if (n < p.N) {
+                        if (p.bias) v0 = v1 = p.bias[n];
+                        if (stage_b2) {
+                            v0 += p.bias2[(int64_t)img0 * p.N + n];
+                            if (img0 + 1 < p.Nimg) v1 += p.bias2[(int64_t)(img0 + 1) * p.N + n];
+                        }
+                    }
+                    sb[cc] = v0; sb[256 + cc] = v1;
+                }
+                asm volatile("bar.sync 2, %0;" :: "n"(32 * kEpiWarps) : "memory");
+            }
+            const float* sbr = sb + ((stage_b2 && (r0 + lane) / (p.BW * p.BH) > 0) ? 256 : 0);
+            const bool b2_global = p.bias2 && !stage_b2;                           // generic (plain GEMM / many images per tile) path
             // residual chunk of this warp's first chunk: in flight while the MMA main loop runs
             if (use_res && half < nchunks && lane == 0 && (p.ksplit == 1)) {
                 const uint32_t b = slot & 1u;
@@ -352,6 +403,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             mbar_wait(&tmem_full[as], (tl >> 1) & 1u);
             tc_fence_after();
+            if (tl == 0 && e == 0 && lane == 0) TRACE(5);
             const uint32_t taddr_row = tmem_base + as * TMEM_STAGE_COLS + ((uint32_t)(q * 32) << 16);
 
             bool released = false;
@@ -394,6 +446,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             }
 
+            // software-pipelined TMEM reads: chunk c+2 is in flight while chunk c is processed
+            const bool pipelined = (EPI != EPI_GEGLU) && (p.ksplit == 1);
+            float nx[32];
+            if (pipelined && half < nchunks) tc_ld32_nowait(taddr_row + (uint32_t)(half * ACC_PER_CHUNK), nx);
 #pragma unroll 1
             for (int c = half; c < nchunks; c += 2, slot++) {
                 const uint32_t b = slot & 1u;
@@ -406,15 +462,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float f[32];
                 const int acol0 = c * ACC_PER_CHUNK;                    // accumulator column of the chunk inside the tile
                 const int ocol0 = otile0 + c * 32;                      // output column
+                const float4* bp = reinterpret_cast<const float4*>(sbr + acol0);
                 if (EPI == EPI_GEGLU) {
                     float v[32], g[32];
                     tc_ld32(taddr_row + (uint32_t)acol0, v);
                     tc_ld32(taddr_row + (uint32_t)(acol0 + 32), g);
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + ntile0 + acol0);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                        if (p.bias) { b0 = __ldg(bp + j); b1 = __ldg(bp + 8 + j); }
+                        const float4 b0 = bp[j], b1 = bp[8 + j];
                         // (value, gate) pairs are interleaved along N
                         f[2 * j] = fmaf(v[4 * j], p.alpha, b0.x) * gelu_f(fmaf(v[4 * j + 1], p.alpha, b0.y));
                         f[2 * j + 1] = fmaf(v[4 * j + 2], p.alpha, b0.z) * gelu_f(fmaf(v[4 * j + 3], p.alpha, b0.w));
@@ -432,30 +487,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             __stcg(src + j * 128, make_float4(0.f, 0.f, 0.f, 0.f));
                         }
                     } else {
-                        tc_ld32(taddr_row + (uint32_t)acol0, f);
-                    }
-                    const bool full_chunk = (ocol0 + 32 <= p.N) && !p.direct;
-                    if (full_chunk) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + ocol0);
-                        const float4* b2p = reinterpret_cast<const float4*>(p.bias2 + b2row * p.N + ocol0);
+                        tc_wait_ld();
+                        reg_fence(nx);
+                        if (tl == 0 && e == 0 && lane == 0 && c == 0) TRACE(8);
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias) bb = __ldg(bp + j);
-                            if (p.bias2) { const float4 t2 = __ldg(b2p + j); bb.x += t2.x; bb.y += t2.y; bb.z += t2.z; bb.w += t2.w; }
-                            f[4 * j] = fmaf(f[4 * j], p.alpha, bb.x); f[4 * j + 1] = fmaf(f[4 * j + 1], p.alpha, bb.y);
-                            f[4 * j + 2] = fmaf(f[4 * j + 2], p.alpha, bb.z); f[4 * j + 3] = fmaf(f[4 * j + 3], p.alpha, bb.w);
-                        }
-                    } else {
+                        for (int j = 0; j < 32; j++) f[j] = nx[j];
+                        reg_fence(f);                                   // the copy is complete before nx is handed to the next load
+                        if (c + 2 < nchunks) tc_ld32_nowait(taddr_row + (uint32_t)((c + 2) * ACC_PER_CHUNK), nx);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 bb = bp[j];
+                        f[4 * j] = fmaf(f[4 * j], p.alpha, bb.x); f[4 * j + 1] = fmaf(f[4 * j + 1], p.alpha, bb.y);
+                        f[4 * j + 2] = fmaf(f[4 * j + 2], p.alpha, bb.z); f[4 * j + 3] = fmaf(f[4 * j + 3], p.alpha, bb.w);
+                    }
+                    if (b2_global) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const int n = ocol0 + j;
-                            float bb = 0.f;
-                            if (n < p.N) {
-                                if (p.bias) bb = p.bias[n];
-                                if (p.bias2) bb += p.bias2[b2row * p.N + n];
-                            }
-                            f[j] = fmaf(f[j], p.alpha, bb);
+                            if (n < p.N) f[j] += p.bias2[b2row * p.N + n];
                         }
                     }
                     if (p.act == ACT_SILU) {
@@ -501,6 +551,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                 }
+                if (tl == 0 && e == 0 && lane == 0 && c == 0) TRACE(9);
                 // staging buffer b was last read by the TMA store issued two chunks ago
                 if (lane == 0) bulk_wait_read<1>();
                 __syncwarp();
@@ -518,12 +569,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = pk;
                     }
                 }
+                if (tl == 0 && e == 0 && lane == 0 && c == 0) TRACE(10);
                 fence_async_smem();
                 __syncwarp();
+                if (tl == 0 && e == 0 && lane == 0 && c == 0) TRACE(11);
                 if (lane == 0) {
                     tma_store_4d(&tmC, stg + b * STG_BYTES, ocol0, c1, c2, c3);
                     bulk_commit();
                 }
+                if (tl == 0 && e == 0 && lane == 0 && c == 0) TRACE(12);
             }
             if (!released) {                                 // warps with no chunk in this tile (BN == 32, half == 1)
                 tc_fence_before();
@@ -531,7 +585,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
             }
         }
+        if (e == 0 && lane == 0) TRACE(6);
         if (lane == 0) bulk_wait_read<0>();                  // smem must stay valid until the last TMA store has read it
+        if (e == 0 && lane == 0) TRACE(7);
     }
     tc_fence_before();
     __syncthreads();
@@ -590,13 +646,14 @@ constexpr size_t kSmemBudget = 232448 - 1024;       // opt-in maximum minus the 
 
 static size_t smem_fixed(int epi, int has_res) {
     const size_t stg = (epi == EPI_F32) ? 4096 : 2048;
-    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + (2 * kMaxStages + 4 + 2 * kEpiWarps) * 8 + 64;
+    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + 2 * 2 * 256 * 4 + (2 * kMaxStages + 4 + 2 * kEpiWarps) * 8 + 64;
 }
 
 // Tile / split selection: a small analytic model of one CTA's critical path, in SM cycles.
 //   k-iteration = max(tensor pipe 2*BN, smem operand read 128 + BN, L2->SM feed of the CTAs running together)
 //   tile        = k-iterations + epilogue (TMEM drain + math + staging, two warps per lane quadrant)
 struct Plan { int BN, ks, stages; };
+static unsigned long long* g_trace = nullptr;
 static int g_force_bn = 0, g_force_ks = 0;        // tuning override (dwg_gemm_tune), 0 = automatic
 static Plan g_last_plan = {0, 0, 0};
 static int g_last_key[6] = {0, 0, 0, 0, 0, 0};
@@ -759,7 +816,7 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
     p.n_tiles = (N + p.BN - 1) / p.BN;
     p.total_tiles = p.m_tiles * p.n_tiles * p.nz * p.ksplit;
-    p.workspace = g_ws; p.counters = g_counters;
+    p.workspace = g_ws; p.counters = g_counters; p.trace = g_trace;
 
     CUtensorMap tmA, tmB, tmC, tmR;
     const uint32_t ones[4] = {1, 1, 1, 1};
@@ -843,7 +900,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
     p.n_tiles = (Cout + p.BN - 1) / p.BN;
     p.total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
-    p.workspace = g_ws; p.counters = g_counters;
+    p.workspace = g_ws; p.counters = g_counters; p.trace = g_trace;
 
     CUtensorMap tmA, tmB, tmC, tmR;
     {
@@ -894,3 +951,7 @@ extern "C" int dwg_gemm_last_key(int* out6) {
     for (int i = 0; i < 6; i++) out6[i] = g_last_key[i];
     return DWG_OK;
 }
+/* Debug: device pointer to 8 x u64 that CTA 0 of every following launch fills with globaltimer stamps
+ * (0 kernel entry, 1 setup done, 2 after griddepcontrol.wait, 3 first operand stage landed, 4 last MMA
+ * committed, 5 accumulator visible to the epilogue, 6 last store issued, 7 stores drained); null = off. */
+extern "C" int dwg_gemm_trace(void* dev_u64x8) { g_trace = reinterpret_cast<unsigned long long*>(dev_u64x8); return DWG_OK; }
