@@ -654,6 +654,11 @@ static size_t smem_fixed(int epi, int has_res) {
 //   tile        = k-iterations + epilogue (TMEM drain + math + staging, two warps per lane quadrant)
 struct Plan { int BN, ks, stages; };
 static unsigned long long* g_trace = nullptr;
+// Split-K scratch is per "lane": GEMMs enqueued on two streams that may run concurrently (ControlNet
+// beside the UNet encoder) must not share tile accumulators / counters.  dwg_gemm_set_lane() selects the
+// half the following launches use (host-side state, baked into the launch parameters).
+constexpr int kLanes = 2;
+static int g_lane = 0;
 static int g_force_bn = 0, g_force_ks = 0;        // tuning override (dwg_gemm_tune), 0 = automatic
 static Plan g_last_plan = {0, 0, 0};
 static int g_last_key[6] = {0, 0, 0, 0, 0, 0};
@@ -673,7 +678,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
                 const int64_t tiles = (int64_t)m_tiles * ((N + t->BN - 1) / t->BN) * nz;
                 int stages = (int)((kSmemBudget - smem_fixed(epi, has_res)) / (A_BYTES + (size_t)t->BN * 128));
                 if (stages > kMaxStages) stages = kMaxStages;
-                if (stages >= 2 && (t->ks == 1 || (tiles <= (1 << 16) && tiles * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters))) pl = {t->BN, t->ks, stages};
+                if (stages >= 2 && (t->ks == 1 || (tiles <= kMaxCounters / kLanes && tiles * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters))) pl = {t->BN, t->ks, stages};
                 break;
             }
         }
@@ -686,7 +691,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
         if (epi == EPI_GEGLU) ks = 1;
         if (ks > iters) ks = iters;
         const int64_t tiles = (int64_t)m_tiles * ((N + BN - 1) / BN) * nz;
-        if (ks > 1 && (tiles > (1 << 16) || tiles * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
+        if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
         int stages = (int)((kSmemBudget - smem_fixed(epi, has_res)) / (A_BYTES + (size_t)BN * 128));
         if (stages > kMaxStages) stages = kMaxStages;
         pl = {BN, ks, stages};
@@ -708,7 +713,7 @@ static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int 
         const int64_t tiles = (int64_t)m_tiles * n_tiles * nz;
         for (int ks = 1; ks <= 32; ks++) {
             if (ks > 1 && (epi == EPI_GEGLU || iters / ks < 2 || tiles * ks > 2 * g_num_sms)) break;
-            if (ks > 1 && (tiles > kMaxCounters || tiles * 128 * (int64_t)BN > ws_cap_floats)) break;
+            if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * 128 * (int64_t)BN > ws_cap_floats)) break;
             const int64_t ctas = tiles * ks;
             const double active = (double)(ctas < g_num_sms ? ctas : g_num_sms);
             const double feed = (double)stage_bytes * active / 6000.0;          // ~6.3 KB/cycle chip-wide TMA throughput
@@ -812,11 +817,11 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.r_b1 = r_b1; p.r_b2 = r_b2;
     p.alpha = alpha; p.act = act;
     p.m_tiles = (M + BM - 1) / BM; p.nz = nb1 * nb2;
-    const Plan pl = plan_tiles(p.m_tiles, p.nz, N, p.k_chunks, epi, p.has_res, (int64_t)(g_ws_bytes / 4));
+    const Plan pl = plan_tiles(p.m_tiles, p.nz, N, p.k_chunks, epi, p.has_res, (int64_t)(g_ws_bytes / 4 / kLanes));
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
     p.n_tiles = (N + p.BN - 1) / p.BN;
     p.total_tiles = p.m_tiles * p.n_tiles * p.nz * p.ksplit;
-    p.workspace = g_ws; p.counters = g_counters; p.trace = g_trace;
+    p.workspace = g_ws + (size_t)g_lane * (g_ws_bytes / 4 / kLanes); p.counters = g_counters + g_lane * (kMaxCounters / kLanes); p.trace = g_trace;
 
     CUtensorMap tmA, tmB, tmC, tmR;
     const uint32_t ones[4] = {1, 1, 1, 1};
@@ -896,11 +901,11 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     p.alpha = 1.0f; p.act = act;
     p.m_tiles = tiles_w * tiles_h * tiles_n; p.nz = 1;
     const int iters = ksize * ksize * p.k_chunks;
-    const Plan pl = plan_tiles(p.m_tiles, 1, Cout, iters, epi, p.has_res, (int64_t)(g_ws_bytes / 4));
+    const Plan pl = plan_tiles(p.m_tiles, 1, Cout, iters, epi, p.has_res, (int64_t)(g_ws_bytes / 4 / kLanes));
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
     p.n_tiles = (Cout + p.BN - 1) / p.BN;
     p.total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
-    p.workspace = g_ws; p.counters = g_counters; p.trace = g_trace;
+    p.workspace = g_ws + (size_t)g_lane * (g_ws_bytes / 4 / kLanes); p.counters = g_counters + g_lane * (kMaxCounters / kLanes); p.trace = g_trace;
 
     CUtensorMap tmA, tmB, tmC, tmR;
     {
@@ -954,4 +959,9 @@ extern "C" int dwg_gemm_last_key(int* out6) {
 /* Debug: device pointer to 8 x u64 that CTA 0 of every following launch fills with globaltimer stamps
  * (0 kernel entry, 1 setup done, 2 after griddepcontrol.wait, 3 first operand stage landed, 4 last MMA
  * committed, 5 accumulator visible to the epilogue, 6 last store issued, 7 stores drained); null = off. */
+extern "C" int dwg_gemm_set_lane(int lane) {
+    DWG_REQUIRE(lane >= 0 && lane < kLanes, "lane must be 0 or 1");
+    g_lane = lane;
+    return DWG_OK;
+}
 extern "C" int dwg_gemm_trace(void* dev_u64x8) { g_trace = reinterpret_cast<unsigned long long*>(dev_u64x8); return DWG_OK; }

@@ -24,8 +24,9 @@ __device__ __forceinline__ bf8 pack8(const float f[8]) {
     for (int i = 0; i < 4; i++) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return p;
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float silu_grad(float x) { const float s = 1.0f / (1.0f + __expf(-x)); return s * (1.0f + x * (1.0f - s)); }
+// fast-division forms (MUFU.RCP + FMUL, ~2 ulp): these kernels are issue-bound on the big VAE tensors
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad(float x) { const float s = __fdividef(1.0f, 1.0f + __expf(-x)); return s * fmaf(x, 1.0f - s, 1.0f); }
 
 // ---------------------------------------------------------------------------- GroupNorm
 // x [N, HW, C] bf16, C % 8 == 0, (C/G) % 8 == 0 or 8 % (C/G) == 0 handled generically via smem bins.
@@ -152,7 +153,10 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
     }
 }
 
-// Backward of y = act(GN(x)).  Pass 1: per-(n,g) sums of (gamma*dz) and (gamma*dz*xhat), dz = dy * act'(z).
+// Backward of y = act(GN(x)).  Both passes use the forward's work split (thread -> row lane x fixed
+// 8-channel column, per-channel constants hoisted out of the row loop, 4 rows = 8 independent
+// 16-byte loads in flight); with a = rstd*gamma, b = beta - mean*a:   z = a x + b,  dz = dy * act'(z).
+// Pass 1: per-(n,g) sums of (gamma*dz) and (gamma*dz*xhat).
 __global__ void __launch_bounds__(256)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ bstats,
@@ -171,72 +175,128 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     const int rp = c8 <= 256 ? 256 / c8 : 1;
     const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
     for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
-        float s1[8], s2[8], mean[8], rstd[8], gm[8], bt[8];
+        float s1[8], s2[8], a[8], b[8], rs[8], mr[8], gm[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int c = cv * 8 + i, g = c / cpg;
             s1[i] = 0.f; s2[i] = 0.f;
-            mean[i] = stats[((size_t)n * G + g) * 2] * inv_cnt;
-            const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean[i] * mean[i], 0.f);
-            rstd[i] = rsqrtf(var + eps);
-            gm[i] = gamma[c]; bt[i] = beta[c];
+            const float mean = stats[((size_t)n * G + g) * 2] * inv_cnt;
+            const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
+            rs[i] = rsqrtf(var + eps); mr[i] = -mean * rs[i];
+            gm[i] = gamma[c];
+            a[i] = rs[i] * gm[i]; b[i] = beta[c] - mean * a[i];
         }
-        for (int r = row0 + rl; r < row1; r += rp) {
+        auto accum = [&](const bf8& xv, const bf8& dv) {
             float f[8], d[8];
-            unpack8(xp[(size_t)r * c8 + cv], f);
-            unpack8(dp[(size_t)r * c8 + cv], d);
+            unpack8(xv, f);
+            unpack8(dv, d);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const float xh = (f[i] - mean[i]) * rstd[i];
                 float dz = d[i];
-                if (do_silu) dz *= silu_grad(xh * gm[i] + bt[i]);
+                if (do_silu) dz *= silu_grad(fmaf(f[i], a[i], b[i]));
                 const float gd = gm[i] * dz;
-                s1[i] += gd; s2[i] += gd * xh;
+                s1[i] += gd; s2[i] = fmaf(gd, fmaf(f[i], rs[i], mr[i]), s2[i]);
             }
-        }
+        };
+        int r = row0 + rl;
+        for (; r + 3 * rp < row1; r += 4 * rp) {
+            bf8 xv[4], dv[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int g = (cv * 8 + i) / cpg;
-            atomicAdd(&s_bins[2 * g], s1[i]);
-            atomicAdd(&s_bins[2 * g + 1], s2[i]);
+            for (int u = 0; u < 4; u++) { xv[u] = xp[(size_t)(r + u * rp) * c8 + cv]; dv[u] = dp[(size_t)(r + u * rp) * c8 + cv]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) accum(xv[u], dv[u]);
+        }
+        for (; r < row1; r += rp) accum(xp[(size_t)r * c8 + cv], dp[(size_t)r * c8 + cv]);
+        if (cpg % 8 == 0) {
+            float u = 0.f, v = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { u += s1[i]; v += s2[i]; }
+            const int g = (cv * 8) / cpg;
+            atomicAdd(&s_bins[2 * g], u);
+            atomicAdd(&s_bins[2 * g + 1], v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int g = (cv * 8 + i) / cpg;
+                atomicAdd(&s_bins[2 * g], s1[i]);
+                atomicAdd(&s_bins[2 * g + 1], s2[i]);
+            }
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&bstats[(size_t)n * 2 * G + i], s_bins[i]);
 }
 
-// Pass 2: dx = rstd * (gamma*dz - mean(gamma*dz) - xhat * mean(gamma*dz*xhat)); optional += dx_add
+// Pass 2: dx = rstd * (gamma*dz - mean(gamma*dz) - xhat * mean(gamma*dz*xhat))  [+ dx_add]
+//            = a*dz + k3*x + k4     with k3 = -rstd^2 m2,  k4 = rstd (rstd m2 mean - m1)
+__device__ __forceinline__ uint4 gn_bwd_one(uint4 xv, uint4 dv, uint4 av, bool has_add, bool do_silu, const float (&a)[8],
+                                            const float (&b)[8], const float (&k3)[8], const float (&k4)[8]) {
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w}, aw[4] = {av.x, av.y, av.z, av.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[h]));
+        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[h]));
+        const float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[h]));
+        float dz0 = d.x, dz1 = d.y;
+        if (do_silu) { dz0 *= silu_grad(fmaf(f.x, a[2 * h], b[2 * h])); dz1 *= silu_grad(fmaf(f.y, a[2 * h + 1], b[2 * h + 1])); }
+        float o0 = fmaf(a[2 * h], dz0, fmaf(f.x, k3[2 * h], k4[2 * h]));
+        float o1 = fmaf(a[2 * h + 1], dz1, fmaf(f.y, k3[2 * h + 1], k4[2 * h + 1]));
+        if (has_add) { o0 += e.x; o1 += e.y; }
+        const __nv_bfloat162 o = __floats2bfloat162_rn(o0, o1);
+        ow[h] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
                     const float* __restrict__ bstats, const float* __restrict__ gamma, const float* __restrict__ beta,
                     const __nv_bfloat16* __restrict__ dx_add, __nv_bfloat16* __restrict__ dx, int HW, int C, int G, float eps,
-                    int do_silu, int64_t total_vec) {
+                    int do_silu, int rows_per_cta) {
     pdl_wait();
     pdl_trigger();
+    const int n = blockIdx.y;
     const int c8 = C / 8, cpg = C / G;
     const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(v % c8);
-        const int n = (int)(v / ((int64_t)HW * c8));
-        float f[8], d[8], a[8];
-        unpack8(reinterpret_cast<const bf8*>(x)[v], f);
-        unpack8(reinterpret_cast<const bf8*>(dy)[v], d);
-        if (dx_add) unpack8(reinterpret_cast<const bf8*>(dx_add)[v], a);
+    const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
+    const size_t base = (size_t)n * HW * C;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + base);
+    const uint4* dp = reinterpret_cast<const uint4*>(dy + base);
+    const bool has_add = dx_add != nullptr;
+    const uint4* ap = has_add ? reinterpret_cast<const uint4*>(dx_add + base) : xp;
+    uint4* op = reinterpret_cast<uint4*>(dx + base);
+    const int rp = c8 <= 256 ? 256 / c8 : 1;
+    const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
+    for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
+        float a[8], b[8], k3[8], k4[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int c = cv * 8 + i, g = c / cpg;
             const float mean = stats[((size_t)n * G + g) * 2] * inv_cnt;
             const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
             const float rstd = rsqrtf(var + eps);
-            const float xh = (f[i] - mean) * rstd;
-            float dz = d[i];
-            if (do_silu) dz *= silu_grad(xh * gamma[c] + beta[c]);
             const float m1 = bstats[((size_t)n * G + g) * 2] * inv_cnt, m2 = bstats[((size_t)n * G + g) * 2 + 1] * inv_cnt;
-            float o = rstd * (gamma[c] * dz - m1 - xh * m2);
-            if (dx_add) o += a[i];
-            f[i] = o;
+            a[i] = rstd * gamma[c]; b[i] = beta[c] - mean * a[i];
+            k3[i] = -rstd * rstd * m2; k4[i] = rstd * (rstd * m2 * mean - m1);
         }
-        reinterpret_cast<bf8*>(dx)[v] = pack8(f);
+        int r = row0 + rl;
+        for (; r + 3 * rp < row1; r += 4 * rp) {
+            const size_t o0 = (size_t)r * c8 + cv, o1 = o0 + (size_t)rp * c8, o2 = o1 + (size_t)rp * c8, o3 = o2 + (size_t)rp * c8;
+            const uint4 x0 = xp[o0], x1 = xp[o1], x2 = xp[o2], x3 = xp[o3];
+            const uint4 d0 = dp[o0], d1 = dp[o1], d2 = dp[o2], d3 = dp[o3];
+            uint4 a0 = x0, a1 = x1, a2 = x2, a3 = x3;
+            if (has_add) { a0 = ap[o0]; a1 = ap[o1]; a2 = ap[o2]; a3 = ap[o3]; }
+            op[o0] = gn_bwd_one(x0, d0, a0, has_add, do_silu, a, b, k3, k4);
+            op[o1] = gn_bwd_one(x1, d1, a1, has_add, do_silu, a, b, k3, k4);
+            op[o2] = gn_bwd_one(x2, d2, a2, has_add, do_silu, a, b, k3, k4);
+            op[o3] = gn_bwd_one(x3, d3, a3, has_add, do_silu, a, b, k3, k4);
+        }
+        for (; r < row1; r += rp) {
+            const size_t o = (size_t)r * c8 + cv;
+            const uint4 xv = xp[o];
+            op[o] = gn_bwd_one(xv, dp[o], has_add ? ap[o] : xv, has_add, do_silu, a, b, k3, k4);
+        }
     }
 }
 
@@ -500,13 +560,15 @@ extern "C" int dwg_groupnorm_bwd(const void* x, const void* dy, const float* sta
     DWG_REQUIRE(C % 8 == 0 && C % G == 0, "C must be a multiple of 8 and of G");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * N * G, st);
-    int rows_per_cta = (int)((int64_t)4096 * 8 / C);
-    if (rows_per_cta < 1) rows_per_cta = 1;
+    const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;        // row lanes per CTA
+    int rows_per_cta = (int)(((int64_t)N * HW + 6 * kNumSMs - 1) / (6 * kNumSMs));      // ~6 CTAs per SM
+    if (rows_per_cta < 4 * rp_) rows_per_cta = 4 * rp_;
+    if (rows_per_cta > 64 * rp_) rows_per_cta = 64 * rp_;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
-    gn_bwd_stats_kernel<<<grid, 256, sizeof(float) * 2 * G, st>>>((const bf16*)x, (const bf16*)dy, stats, gamma, beta, bstats, HW, C, G, eps, do_silu, rows_per_cta);
-    const int64_t total = (int64_t)N * HW * (C / 8);
-    gn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, stats, bstats, gamma, beta, (const bf16*)dx_add,
-                                                              (bf16*)dx, HW, C, G, eps, do_silu, total);
+    launch_pdl(gn_bwd_stats_kernel, grid, dim3(256), sizeof(float) * 2 * G, st, (const bf16*)x, (const bf16*)dy, stats, gamma, beta, bstats,
+               HW, C, G, eps, do_silu, rows_per_cta);
+    launch_pdl(gn_bwd_apply_kernel, grid, dim3(256), 0, st, (const bf16*)x, (const bf16*)dy, stats, (const float*)bstats, gamma, beta,
+               (const bf16*)dx_add, (bf16*)dx, HW, C, G, eps, do_silu, rows_per_cta);
     return check_launch("dwg_groupnorm_bwd");
 }
 

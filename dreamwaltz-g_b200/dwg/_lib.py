@@ -57,6 +57,7 @@ SIGNATURES = {
     'dwg_gemm_last_plan': (c_int, [c_void_p]),
     'dwg_gemm_last_key': (c_int, [c_void_p]),
     'dwg_gemm_trace': (c_int, [c_void_p]),
+    'dwg_gemm_set_lane': (c_int, [c_int]),
     'dwg_conv2d_nhwc_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 11 +
                              [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'dwg_groupnorm_fwd': (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),

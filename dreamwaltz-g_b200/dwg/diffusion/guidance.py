@@ -51,10 +51,12 @@ class ControlNetScoreDistillation:
         self.gen.manual_seed(seed)
         self.use_default_generator = False      # True inside whole-step CUDA-graph capture (graph-safe philox state)
         self.timestep = None
+        self.two_streams = True                 # ControlNet beside the UNet encoder (_controlnet_unet)
+        self._side = None
 
     # ---- CUDA graphs: the diffusion blocks have static shapes; one capture each for
     # ControlNet+UNet, VAE forward and VAE backward removes ~1500 launches of host overhead per step
-    def enable_graphs(self, image_hw=(512, 512), batch=2):
+    def enable_graphs(self, image_hw=(512, 512), batch=2, cond_batch=1):
         from .._lib import lib
         dev, L = self.device, self.vae.cfg['latent']
         H, Wd = image_hw
@@ -63,7 +65,7 @@ class ControlNetScoreDistillation:
         self._g = {}
         st = {
             'x2': torch.zeros(batch, L, h, w, device=dev), 't': torch.zeros(1, dtype=torch.long, device=dev),
-            'ctx': torch.zeros(batch, 77, ctx_dim, device=dev), 'cond': torch.zeros(batch, 3, H, Wd, device=dev),
+            'ctx': torch.zeros(batch, 77, ctx_dim, device=dev), 'cond': torch.zeros(cond_batch, 3, H, Wd, device=dev),
             'img': torch.zeros(1, 3, H, Wd, device=dev), 'veps': torch.zeros(1, L, h, w, device=dev),
             'glat': torch.zeros(1, L, h, w, device=dev),
         }
@@ -71,8 +73,7 @@ class ControlNetScoreDistillation:
 
         def predict():
             self.timestep = st['t']
-            down, mid = self.controlnet.forward(st['x2'], st['t'], st['ctx'], st['cond'], self.conditioning_scale)
-            return self.unet.forward(st['x2'], st['t'], st['ctx'], down, mid)
+            return self._controlnet_unet(st['x2'], st['ctx'], st['cond'])
 
         tape = []
 
@@ -124,12 +125,35 @@ class ControlNetScoreDistillation:
         if getattr(self, '_g', None):
             st = self._static
             st['x2'].copy_(latents_model_input); st['t'].copy_(self.timestep.reshape(-1)[:1]); st['ctx'].copy_(text_embeddings)
-            st['cond'].copy_(cond if cond.shape[0] == st['cond'].shape[0] else cond.expand_as(st['cond']))
+            assert cond.shape[0] == st['cond'].shape[0], 'enable_graphs(cond_batch=...) must match the condition batch'
+            st['cond'].copy_(cond)
             return self._replay('predict')
-        if cond.shape[0] == 1:
-            cond = cond.repeat_interleave(latents_model_input.shape[0], dim=0)
-        down, mid = self.controlnet.forward(latents_model_input, self.timestep, text_embeddings, cond, self.conditioning_scale)
-        return self.unet.forward(latents_model_input, self.timestep, text_embeddings, down, mid)
+        return self._controlnet_unet(latents_model_input, text_embeddings, cond)
+
+    def _controlnet_unet(self, x2, ctx, cond):
+        """ControlNet and the UNet encoder + mid block are independent until the residuals are added
+        (controlnet.py:98-114 / diffusers): the ControlNet is enqueued on a second stream (its own
+        split-K scratch lane) and joins before the UNet decoder.  At batch 2 most layers leave SMs idle,
+        so the two chains fill each other's gaps; fork/join are graph edges under CUDA-graph capture."""
+        if not self.two_streams:
+            down, mid = self.controlnet.forward(x2, self.timestep, ctx, cond, self.conditioning_scale)
+            return self.unet.forward(x2, self.timestep, ctx, down, mid)
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.gemm_lane(1)
+            try:
+                down, mid = self.controlnet.forward(x2, self.timestep, ctx, cond, self.conditioning_scale)
+            finally:
+                ops.gemm_lane(0)
+        state = self.unet.encode(x2, self.timestep, ctx)
+        main.wait_stream(side)
+        for r in down + [mid]:
+            r.record_stream(main)
+        return self.unet.decode(state, down, mid)
 
     def get_timestep(self, batch_size):
         return torch.randint(self.t_lo, self.t_hi + 1, (batch_size,), device=self.device,

@@ -232,11 +232,18 @@ class ControlNet(DiffusionNet):
         ctx = ctx.to(BF).contiguous()
         self._ctx_kv = self.project_context(ctx)
         h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
+        # condition embedding: with classifier-free guidance the reference feeds the SAME condition image
+        # for every sample (controlnet.py:33-55 prepare_image duplicates it); a batch-1 condition is
+        # embedded once and added to every sample
         c = ops.silu(conv(W, 'controlnet_cond_embedding.conv_in', to_nhwc_bf16(cond_nchw01)))
         nblk = 2 * (len(self.cfg['cond_embed']) - 1)
         for k in range(nblk):
             c = ops.silu(conv(W, f'controlnet_cond_embedding.blocks.{k}', c, stride=2 if k % 2 == 1 else 1))
-        h = conv(W, 'controlnet_cond_embedding.conv_out', c, residual=h)
+        if c.shape[0] == B:
+            h = conv(W, 'controlnet_cond_embedding.conv_out', c, residual=h)
+        else:
+            assert c.shape[0] == 1, 'condition batch must be 1 or the sample batch'
+            h = h + conv(W, 'controlnet_cond_embedding.conv_out', c)
         h, skips = self.down_path(h, tproj, ctx)
         h = self.mid(h, tproj, ctx)
         down = [conv(W, f'controlnet_down_blocks.{i}', s, padding=0) for i, s in enumerate(skips)]
@@ -251,17 +258,30 @@ class UNet(DiffusionNet):
     @torch.no_grad()
     def forward(self, sample_nchw, t, ctx, down_residuals=None, mid_residual=None):
         """-> eps [B,out_ch,H,W] fp32 (NCHW, the reference layout)."""
-        W, cfg = self.W, self.cfg
-        nb = len(cfg['block_out'])
+        return self.decode(self.encode(sample_nchw, t, ctx), down_residuals, mid_residual)
+
+    @torch.no_grad()
+    def encode(self, sample_nchw, t, ctx):
+        """conv_in + down blocks + mid block: everything that does not need the ControlNet residuals
+        (diffusers adds them to the skip list / the mid output afterwards), so it can run beside the
+        ControlNet on another stream (guidance._predict)."""
+        W = self.W
         B = sample_nchw.shape[0]
         tproj = self.time_embed(t, B)
         ctx = ctx.to(BF).contiguous()
         self._ctx_kv = self.project_context(ctx)
         h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
         h, skips = self.down_path(h, tproj, ctx)
+        h = self.mid(h, tproj, ctx)
+        return h, skips, tproj, ctx
+
+    @torch.no_grad()
+    def decode(self, state, down_residuals=None, mid_residual=None):
+        W, cfg = self.W, self.cfg
+        nb = len(cfg['block_out'])
+        h, skips, tproj, ctx = state
         if down_residuals is not None:
             skips = [ops.add(s, r) for s, r in zip(skips, down_residuals)]
-        h = self.mid(h, tproj, ctx)
         if mid_residual is not None:
             h = ops.add(h, mid_residual)
         for i in range(nb):

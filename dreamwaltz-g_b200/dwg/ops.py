@@ -372,6 +372,12 @@ class _prof:
             PROFILE.append((self.e0, self.e1, self.flops, self.kind))
 
 
+def gemm_lane(lane):
+    """Select the split-K scratch lane (0 / 1) of the GEMM / conv launches that follow (include/dwg.h:
+    dwg_gemm_set_lane).  Launches enqueued on a second, possibly concurrent stream must use lane 1."""
+    check(lib().dwg_gemm_set_lane(int(lane)), 'gemm_set_lane')
+
+
 def _chk_bf16(t):
     assert t.is_cuda and t.dtype == torch.bfloat16, 'tcgen05 layers take bf16 CUDA tensors'
     return t

@@ -194,6 +194,9 @@ int dwg_avatar_mlp_bwd(const float* enc, const float* params, const float* body_
  * (0, 0 = automatic); read the (BN, ksplit, stages) the last launch ran with. */
 int dwg_gemm_tune(int force_bn, int force_ks);
 int dwg_gemm_last_plan(int* out3);
+/* Split-K scratch lane (0 or 1) used by the launches that follow: GEMMs enqueued on two streams that may run
+ * concurrently (ControlNet beside the UNet encoder, dwg/diffusion/guidance.py) must use different lanes. */
+int dwg_gemm_set_lane(int lane);
 int dwg_gemm_trace(void* dev_u64x8);   /* debug timeline of CTA 0 (globaltimer ns), NULL = off; see csrc/gemm_tcgen05.cu */
 int dwg_gemm_last_key(int* out6);   /* planner key of the last launch: m_tiles, nz, N, k-iterations, epilogue kind, has_residual */
 
