@@ -21,6 +21,14 @@
 //   split-K   : the CTAs of one output tile write fp32 partial tiles (coalesced, tile-private
 //               layout) and bump a per-tile counter; the LAST arriver adds the other partials to
 //               its own TMEM accumulator and runs the normal epilogue -- no finalize kernel.
+//   CTA pairs : (PAIR = true) two CTAs of one cluster (same TPC) run tcgen05.mma.cta_group::2 on a 256 x BN
+//               tile: each CTA stages its own 128 A rows and HALF of the B tile (BN/2 rows); the leader's
+//               single MMA lane drives both tensor cores, reading the B halves from both shared memories.
+//               Per k-iteration a CTA then pulls 16 KB + BN*64 B instead of 16 KB + BN*128 B through the
+//               ~6.3 KB/cycle chip-wide L2 port (B300_MICROARCH.md "LTS throughput cap"), which is what
+//               bounds every large GEMM / convolution of the step.  Barriers: operand "full" lives in the
+//               leader (both CTAs' TMA loads complete_tx on it), "empty" / "accumulator full" are reached
+//               by multicast tcgen05.commit, "accumulator empty" collects local + remote epilogue arrivals.
 // The epilogue body is deliberately compact (no unrolling over chunks, one instantiation per
 // output kind): v2's 265 KB of SASS made short kernels instruction-fetch bound (ncu: stall_no_inst).
 #include <cuda.h>
@@ -70,6 +78,7 @@ struct Params {
     // tiling
     int BN, stages;
     int m_tiles, n_tiles, nz, ksplit, total_tiles;
+    int m_sched;                    // scheduler units along M: m_tiles (single CTA) or m_tiles / 2 (CTA pair)
     float* workspace;               // split-K fp32 tile accumulators (zero when idle)
     int* counters;                  // one per output tile, self-resetting
     unsigned long long* trace;      // optional [8] per-launch timeline of CTA 0 (globaltimer ns), null = off
@@ -96,6 +105,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same-offset mbarrier of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" :: "r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the pair's even (leader) CTA
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -104,6 +123,11 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// CTA-pair variant: executed by both CTAs, the transaction bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -118,6 +142,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// CTA pair: the commit arrives on the same-offset barrier of both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -188,9 +222,9 @@ __device__ __forceinline__ float gelu_f(float x) {
 }
 
 struct TileCoord { int m_tile, n_tile, z, ks; };
-__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t) {
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, int m_mul, int m_add) {
     TileCoord c;
-    c.m_tile = t % p.m_tiles; t /= p.m_tiles;          // m fastest: CTAs running together share the B (weight) tile in L2
+    c.m_tile = (t % p.m_sched) * m_mul + m_add; t /= p.m_sched;          // m fastest: CTAs running together share the B (weight) tile in L2
     c.n_tile = t % p.n_tiles; t /= p.n_tiles;
     c.ks = t % p.ksplit; t /= p.ksplit;
     c.z = t;
@@ -204,7 +238,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // Persistent, warp-specialised: the CTA walks tiles blockIdx.x, +gridDim.x, ...; the smem ring and
 // the two TMEM accumulator stages let the TMA / MMA of tile i+1 overlap the epilogue of tile i.
-template <int EPI>
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -213,7 +247,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int ACC_PER_CHUNK = (EPI == EPI_GEGLU) ? 64 : 32;        // accumulator columns per epilogue chunk (-> 32 outputs)
     constexpr uint32_t STG_BYTES = (EPI == EPI_F32) ? 4096 : 2048;     // 32 rows x 32 outputs
-    const uint32_t B_BYTES = (uint32_t)p.BN * (BK * 2);
+    const uint32_t B_BYTES = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * (BK * 2);      // this CTA's share of the B tile
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                      // 0 = leader (issues the MMAs of the pair)
+    const int m_mul = PAIR ? 2 : 1, m_add = (int)rank;
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     uint8_t* sA = smem;
     uint8_t* sB = sA + p.stages * A_BYTES;
     uint8_t* sStage = sB + p.stages * B_BYTES;                         // [kEpiWarps][2][STG_BYTES]
@@ -239,16 +277,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], PAIR ? 2 * kEpiWarps : kEpiWarps); }
         for (int i = 0; i < 2 * kEpiWarps; i++) mbar_init(&res_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(2 * TMEM_STAGE_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(2 * TMEM_STAGE_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(2 * TMEM_STAGE_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();            // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TRACE(1);
@@ -265,8 +309,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0) {
         if (elect_one()) {
             uint32_t s = 0, ph = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(p, t);
+            const int n_off = PAIR ? (int)rank * (p.BN / 2) : 0;          // this CTA's half of the B tile
+            for (int t = tile0; t < p.total_tiles; t += tile_step) {
+                const TileCoord tc = decode_tile(p, t, m_mul, m_add);
                 int a_c1, a_c2, a_c3, b1 = 0, b2 = 0;
                 if (p.conv_mode) {
                     const int tw = tc.m_tile % p.tiles_w;
@@ -284,25 +329,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 int kc = it0 % p.k_chunks, tap = it0 / p.k_chunks;
                 for (int it = it0; it < it1; it++) {
                     mbar_wait(&empty[s], ph ^ 1u);
-                    mbar_expect_tx(&full[s], p.a_bytes + B_BYTES);
-                    if (p.conv_mode) {
-                        const int kw = tap % p.taps_w, kh = tap / p.taps_w;
-                        tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1 + kw, a_c2 + kh, a_c3);
-                        tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, tc.n_tile * p.BN, 0);
+                    if (PAIR) {
+                        // the leader's barrier counts the bytes of BOTH CTAs (the peer only issues its loads)
+                        if (rank == 0) mbar_expect_tx(&full[s], 2u * (p.a_bytes + B_BYTES));
+                        if (p.conv_mode) {
+                            const int kw = tap % p.taps_w, kh = tap / p.taps_w;
+                            tma_load_4d_pair(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1 + kw, a_c2 + kh, a_c3);
+                            tma_load_4d_pair(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, tc.n_tile * p.BN + n_off, 0);
+                        } else {
+                            tma_load_4d_pair(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1, a_c2, a_c3);
+                            tma_load_4d_pair(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tc.n_tile * p.BN + n_off, b1, b2);
+                        }
                     } else {
-                        tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1, a_c2, a_c3);
-                        tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tc.n_tile * p.BN, b1, b2);
+                        mbar_expect_tx(&full[s], p.a_bytes + B_BYTES);
+                        if (p.conv_mode) {
+                            const int kw = tap % p.taps_w, kh = tap / p.taps_w;
+                            tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1 + kw, a_c2 + kh, a_c3);
+                            tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, tc.n_tile * p.BN, 0);
+                        } else {
+                            tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], kc * BK, a_c1, a_c2, a_c3);
+                            tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tc.n_tile * p.BN, b1, b2);
+                        }
                     }
                     if (++kc == p.k_chunks) { kc = 0; tap++; }
                     if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    } else if (warp == 1 && rank == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
         uint32_t s = 0, ph = 0, tl = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, tl++) {
-            const TileCoord tc = decode_tile(p, t);
+        for (int t = tile0; t < p.total_tiles; t += tile_step, tl++) {
+            const TileCoord tc = decode_tile(p, t, m_mul, m_add);
             int it0, it1;
             it_range(tc.ks, it0, it1);
             const uint32_t as = tl & 1u;
@@ -317,10 +375,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES));
                     const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++)
-                        tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
-                    tc_commit(&empty[s]);
-                    if (it == it1 - 1) { tc_commit(&tmem_full[as]); if (tl == 0) TRACE(4); }
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        else tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
+                    }
+                    if (PAIR) tc_commit_pair(&empty[s]); else tc_commit(&empty[s]);
+                    if (it == it1 - 1) {
+                        if (PAIR) tc_commit_pair(&tmem_full[as]); else tc_commit(&tmem_full[as]);
+                        if (tl == 0) TRACE(4);
+                    }
                 }
                 __syncwarp();
                 if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
@@ -340,8 +403,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t row_off = (EPI == EPI_F32) ? (uint32_t)lane * 128u : (uint32_t)lane * 64u;
         const uint32_t sw = (EPI == EPI_F32) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
         const uint32_t rsw = (uint32_t)((lane >> 1) & 3);   // residual rows are always bf16 (64 B, SWIZZLE_64B)
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, tl++) {
-            const TileCoord tc = decode_tile(p, t);
+        for (int t = tile0; t < p.total_tiles; t += tile_step, tl++) {
+            const TileCoord tc = decode_tile(p, t, m_mul, m_add);
             const uint32_t as = tl & 1u;
             const int r0 = q * 32;
             int c1, c2, c3;
@@ -425,7 +488,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 released = true;                                     // the accumulator stage is free again
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
                 __threadfence();
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");
                 if (e == 0 && lane == 0) {
@@ -520,7 +583,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     released = true;
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                    if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
                 }
                 if (p.direct) {
                     // ---- slow path: unaligned strides; masked per-thread stores
@@ -582,7 +645,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (!released) {                                 // warps with no chunk in this tile (BN == 32, half == 1)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
             }
         }
         if (e == 0 && lane == 0) TRACE(6);
@@ -590,10 +653,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (e == 0 && lane == 0) TRACE(7);
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();            // neither CTA may retire (or free TMEM) while the pair's MMAs / remote arrivals are in flight
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * TMEM_STAGE_COLS));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * TMEM_STAGE_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * TMEM_STAGE_COLS));
     }
 }
 
@@ -652,7 +717,7 @@ static size_t smem_fixed(int epi, int has_res) {
 // Tile / split selection: a small analytic model of one CTA's critical path, in SM cycles.
 //   k-iteration = max(tensor pipe 2*BN, smem operand read 128 + BN, L2->SM feed of the CTAs running together)
 //   tile        = k-iterations + epilogue (TMEM drain + math + staging, two warps per lane quadrant)
-struct Plan { int BN, ks, stages; };
+struct Plan { int BN, ks, stages, pair; };
 static unsigned long long* g_trace = nullptr;
 // Split-K scratch is per "lane": GEMMs enqueued on two streams that may run concurrently (ControlNet
 // beside the UNet encoder) must not share tile accumulators / counters.  dwg_gemm_set_lane() selects the
@@ -660,14 +725,21 @@ static unsigned long long* g_trace = nullptr;
 constexpr int kLanes = 2;
 static int g_lane = 0;
 static int g_force_bn = 0, g_force_ks = 0;        // tuning override (dwg_gemm_tune), 0 = automatic
-static Plan g_last_plan = {0, 0, 0};
+static int g_force_pair = -1;                     // dwg_gemm_tune_pair: -1 = automatic, 0 = never, 1 = whenever legal
+static Plan g_last_plan = {0, 0, 0, 0};
 static int g_last_key[6] = {0, 0, 0, 0, 0, 0};
 // Measured plans for the shapes of the SDS step on a 148-SM B200 (tools/gemm_autotune.py writes the
 // table: cold weights, warm activations, CUDA-graph replays); anything else falls back to the model.
-struct TunedPlan { int m_tiles, nz, N, iters, epi, has_res, BN, ks; };
+struct TunedPlan { int m_tiles, nz, N, iters, epi, has_res, BN, ks, pair; };
 static const TunedPlan kTuned[] = {
 #include "gemm_plan_table.inc"
-    {0, 0, 0, 0, 0, 0, 0, 0}};
+    {0, 0, 0, 0, 0, 0, 0, 0, 0}};
+// CTA pairs need an even number of 128-row tiles (no phantom half) and a tile width whose halves are whole swizzle groups
+static bool pair_legal(int m_tiles, int BN) { return (m_tiles % 2) == 0 && (BN % 32) == 0 && BN >= 32; }
+static int stages_for(int BN, int pair, int epi, int has_res) {
+    int stages = (int)((kSmemBudget - smem_fixed(epi, has_res)) / (A_BYTES + (size_t)(pair ? BN / 2 : BN) * 128));
+    return stages > kMaxStages ? kMaxStages : stages;
+}
 static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats);
 static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats) {
     Plan pl = plan_tiles_auto(m_tiles, nz, N, iters, epi, has_res, ws_cap_floats);
@@ -676,9 +748,9 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
         for (const TunedPlan* t = kTuned; t->BN; t++) {
             if (t->m_tiles == m_tiles && t->nz == nz && t->N == N && t->iters == iters && t->epi == epi && t->has_res == has_res) {
                 const int64_t tiles = (int64_t)m_tiles * ((N + t->BN - 1) / t->BN) * nz;
-                int stages = (int)((kSmemBudget - smem_fixed(epi, has_res)) / (A_BYTES + (size_t)t->BN * 128));
-                if (stages > kMaxStages) stages = kMaxStages;
-                if (stages >= 2 && (t->ks == 1 || (tiles <= kMaxCounters / kLanes && tiles * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters))) pl = {t->BN, t->ks, stages};
+                const int pair = (t->pair && pair_legal(m_tiles, t->BN)) ? 1 : 0;
+                const int stages = stages_for(t->BN, pair, epi, has_res);
+                if (stages >= 2 && (t->ks == 1 || (tiles <= kMaxCounters / kLanes && tiles * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters))) pl = {t->BN, t->ks, stages, pair};
                 break;
             }
         }
@@ -692,16 +764,18 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
         if (ks > iters) ks = iters;
         const int64_t tiles = (int64_t)m_tiles * ((N + BN - 1) / BN) * nz;
         if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
-        int stages = (int)((kSmemBudget - smem_fixed(epi, has_res)) / (A_BYTES + (size_t)BN * 128));
-        if (stages > kMaxStages) stages = kMaxStages;
-        pl = {BN, ks, stages};
+        pl = {BN, ks, stages_for(BN, 0, epi, has_res), 0};
+    }
+    if (g_force_pair >= 0) {
+        pl.pair = (g_force_pair == 1 && pair_legal(m_tiles, pl.BN)) ? 1 : 0;
+        pl.stages = stages_for(pl.BN, pl.pair, epi, has_res);
     }
     g_last_plan = pl;
     return pl;
 }
 static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats) {
     const int gran = (epi == EPI_GEGLU) ? 64 : 32;
-    Plan best = {gran, 1, 2};
+    Plan best = {gran, 1, 2, 0};
     double best_t = 1e30;
     const size_t fixed = smem_fixed(epi, has_res);
     for (int BN = gran; BN <= 256; BN += gran) {
@@ -728,19 +802,31 @@ static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int 
             double t_tile = t_main > t_epi ? t_main : t_epi;                    // steady state of a persistent CTA
             double t = 2500.0 + 1500.0 /* first TMA */ + (waves - 1.0) * t_tile + t_main + t_epi;
             if (ks > 1) t += 1500.0 + BN * 8.0;                                 // vector-atomic partial adds + counter + tile read-back
-            if (t < best_t) { best_t = t; best = {BN, ks, stages}; }
+            if (t < best_t) { best_t = t; best = {BN, ks, stages, 0}; }
         }
     }
     return best;
 }
 
-template <int EPI>
-static void set_smem_attr() {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024));
-        done = true;
+template <int EPI, bool PAIR>
+static cudaError_t launch_one(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                              const CUtensorMap& tmR, const Params& p) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gemm_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024));
+        attr_done = true;
     }
+    if (!PAIR) return launch_pdl(gemm_kernel<EPI, PAIR>, grid, dim3(kThreads), smem, st, tmA, tmB, tmC, tmR, p);
+    // CTA pair = cluster of 2 (same TPC) + programmatic dependent launch
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, PAIR>, tmA, tmB, tmC, tmR, p);
 }
 
 static int ensure_globals() {
@@ -763,11 +849,20 @@ static int ensure_globals() {
 }
 
 static int launch(const CUtensorMap& tmA, CUtensorMap& tmB_out, const CUtensorMap& tmC, const CUtensorMap& tmR, Params& p, int epi, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)p.stages * (A_BYTES + (size_t)p.BN * 128) + smem_fixed(epi, p.has_res);
-    const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-    if (epi == EPI_BF16) { set_smem_attr<EPI_BF16>(); launch_pdl(gemm_kernel<EPI_BF16>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB_out, tmC, tmR, p); }
-    else if (epi == EPI_F32) { set_smem_attr<EPI_F32>(); launch_pdl(gemm_kernel<EPI_F32>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB_out, tmC, tmR, p); }
-    else { set_smem_attr<EPI_GEGLU>(); launch_pdl(gemm_kernel<EPI_GEGLU>, dim3(grid), dim3(kThreads), smem, st, tmA, tmB_out, tmC, tmR, p); }
+    const bool pair = p.m_sched != p.m_tiles;
+    const size_t smem = 1024 + (size_t)p.stages * (A_BYTES + (size_t)(pair ? p.BN / 2 : p.BN) * 128) + smem_fixed(epi, p.has_res);
+    if (pair) {
+        const int pairs = g_num_sms / 2;
+        const dim3 grid(2 * (p.total_tiles < pairs ? p.total_tiles : pairs));
+        if (epi == EPI_BF16) launch_one<EPI_BF16, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+        else if (epi == EPI_F32) launch_one<EPI_F32, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+        else launch_one<EPI_GEGLU, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+    } else {
+        const dim3 grid(p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms);
+        if (epi == EPI_BF16) launch_one<EPI_BF16, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+        else if (epi == EPI_F32) launch_one<EPI_F32, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+        else launch_one<EPI_GEGLU, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+    }
     return check_launch("tcgen05 gemm");
 }
 
@@ -820,7 +915,8 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     const Plan pl = plan_tiles(p.m_tiles, p.nz, N, p.k_chunks, epi, p.has_res, (int64_t)(g_ws_bytes / 4 / kLanes));
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
     p.n_tiles = (N + p.BN - 1) / p.BN;
-    p.total_tiles = p.m_tiles * p.n_tiles * p.nz * p.ksplit;
+    p.m_sched = pl.pair ? p.m_tiles / 2 : p.m_tiles;
+    p.total_tiles = p.m_sched * p.n_tiles * p.nz * p.ksplit;
     p.workspace = g_ws + (size_t)g_lane * (g_ws_bytes / 4 / kLanes); p.counters = g_counters + g_lane * (kMaxCounters / kLanes); p.trace = g_trace;
 
     CUtensorMap tmA, tmB, tmC, tmR;
@@ -835,7 +931,7 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     {
         const uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)nb1, (uint64_t)nb2};
         const uint64_t str[3] = {(uint64_t)ldb * 2, (uint64_t)(nb1 > 1 ? b_b1 : ldb * (int64_t)N) * 2, (uint64_t)(nb2 > 1 ? b_b2 : ldb * (int64_t)N) * 2};
-        const uint32_t box[4] = {BK, (uint32_t)p.BN, 1, 1};
+        const uint32_t box[4] = {BK, (uint32_t)(pl.pair ? p.BN / 2 : p.BN), 1, 1};
         rc = make_map_bf16(&tmB, B, dims, str, box, ones);
         if (rc) return rc;
     }
@@ -904,7 +1000,8 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     const Plan pl = plan_tiles(p.m_tiles, 1, Cout, iters, epi, p.has_res, (int64_t)(g_ws_bytes / 4 / kLanes));
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
     p.n_tiles = (Cout + p.BN - 1) / p.BN;
-    p.total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+    p.m_sched = pl.pair ? p.m_tiles / 2 : p.m_tiles;
+    p.total_tiles = p.m_sched * p.n_tiles * p.ksplit;
     p.workspace = g_ws + (size_t)g_lane * (g_ws_bytes / 4 / kLanes); p.counters = g_counters + g_lane * (kMaxCounters / kLanes); p.trace = g_trace;
 
     CUtensorMap tmA, tmB, tmC, tmR;
@@ -921,7 +1018,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
         const int taps = ksize * ksize;
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout, 1};
         const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2, (uint64_t)Cout * taps * Cin * 2};
-        const uint32_t box[4] = {BK, 1, (uint32_t)p.BN, 1};
+        const uint32_t box[4] = {BK, 1, (uint32_t)(pl.pair ? p.BN / 2 : p.BN), 1};
         rc = make_map_bf16(&tmB, w, dims, str, box, ones);
         if (rc) return rc;
     }
@@ -950,6 +1047,10 @@ extern "C" int dwg_gemm_last_plan(int* out3) {
     out3[0] = g_last_plan.BN; out3[1] = g_last_plan.ks; out3[2] = g_last_plan.stages;
     return DWG_OK;
 }
+/* CTA-pair (tcgen05 cta_group::2) mode of the following launches: -1 automatic, 0 never, 1 whenever legal;
+ * dwg_gemm_last_pair() reads back what the last launch used. */
+extern "C" int dwg_gemm_tune_pair(int mode) { g_force_pair = mode < 0 ? -1 : (mode ? 1 : 0); return DWG_OK; }
+extern "C" int dwg_gemm_last_pair(void) { return g_last_plan.pair; }
 /* the planner key of the last launch: (m_tiles, nz, N, k_iterations, epilogue kind, has_residual) */
 extern "C" int dwg_gemm_last_key(int* out6) {
     DWG_REQUIRE(out6, "null pointer");

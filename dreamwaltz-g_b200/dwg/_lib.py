@@ -55,6 +55,8 @@ SIGNATURES = {
     'dwg_avatar_mlp_bwd': (c_int, [c_void_p] * 16 + [c_int64, c_int64, c_float, c_float, c_void_p]),
     'dwg_gemm_tune': (c_int, [c_int, c_int]),
     'dwg_gemm_last_plan': (c_int, [c_void_p]),
+    'dwg_gemm_tune_pair': (c_int, [c_int]),
+    'dwg_gemm_last_pair': (c_int, []),
     'dwg_gemm_last_key': (c_int, [c_void_p]),
     'dwg_gemm_trace': (c_int, [c_void_p]),
     'dwg_gemm_set_lane': (c_int, [c_int]),

@@ -194,6 +194,10 @@ int dwg_avatar_mlp_bwd(const float* enc, const float* params, const float* body_
  * (0, 0 = automatic); read the (BN, ksplit, stages) the last launch ran with. */
 int dwg_gemm_tune(int force_bn, int force_ks);
 int dwg_gemm_last_plan(int* out3);
+/* CTA-pair (tcgen05.mma.cta_group::2, cluster of 2) mode of the following launches: -1 automatic (planner / tuned
+ * table), 0 never, 1 whenever legal (even number of 128-row tiles); dwg_gemm_last_pair() -> what the last launch used. */
+int dwg_gemm_tune_pair(int mode);
+int dwg_gemm_last_pair(void);
 /* Split-K scratch lane (0 or 1) used by the launches that follow: GEMMs enqueued on two streams that may run
  * concurrently (ControlNet beside the UNet encoder, dwg/diffusion/guidance.py) must use different lanes. */
 int dwg_gemm_set_lane(int lane);

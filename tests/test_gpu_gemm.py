@@ -129,3 +129,68 @@ def test_gemm_tiny_m_and_deep_split_k():
         res = torch.randn(M, N, device=DEV).bfloat16()
         c = ops.gemm(a, b, residual=res, out_dtype=torch.float32)
         assert _rel(c, a.float() @ b.float().t() + res.float()) < 2e-3
+
+
+@pytest.fixture
+def force_pair():
+    """Force the CTA-pair (tcgen05.mma.cta_group::2) path wherever it is legal, restore the planner afterwards."""
+    from dwg._lib import lib
+    lib().dwg_gemm_tune_pair(1)
+    yield lib()
+    lib().dwg_gemm_tune_pair(-1)
+    lib().dwg_gemm_tune(0, 0)
+
+
+@pytest.mark.parametrize('M,N,K,bn,ks', [(256, 128, 64, 0, 0), (8192, 320, 320, 0, 0), (4096, 1280, 2560, 256, 1), (512, 1280, 1280, 128, 1),
+                                         (2048, 640, 640, 160, 1), (1024, 250, 72, 64, 1), (512, 1280, 5120, 128, 4), (8192, 4096, 512, 256, 1)])
+def test_gemm_cta_pair_matches_torch(force_pair, M, N, K, bn, ks):
+    L = force_pair
+    L.dwg_gemm_tune(bn, ks)
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = torch.randn(N, K, device=DEV).bfloat16()
+    ref = a.float() @ b.float().t()
+    c = ops.gemm(a, b, out_dtype=torch.float32)
+    assert L.dwg_gemm_last_pair() == 1, 'pair mode was not taken'
+    assert _rel(c, ref) < 2e-3
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV).bfloat16()
+    c2 = ops.gemm(a, b, bias=bias, residual=res, alpha=0.5, act='silu')
+    assert c2.dtype == torch.bfloat16 and _rel(c2, F.silu(0.5 * ref + bias) + res.float()) < 2e-2
+    # repeated launches (persistent tiles, barrier phases, TMEM stages) stay correct
+    for _ in range(3):
+        c = ops.gemm(a, b, out_dtype=torch.float32)
+    assert _rel(c, ref) < 2e-3
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k,stride', [
+    (2, 64, 64, 320, 320, 3, 1), (2, 32, 32, 640, 640, 3, 1), (2, 16, 16, 1280, 1280, 3, 1), (2, 64, 64, 320, 320, 3, 2),
+    (1, 128, 128, 128, 128, 3, 1), (2, 32, 32, 640, 320, 1, 1), (1, 256, 256, 128, 256, 3, 1)])
+def test_conv2d_cta_pair_matches_torch(force_pair, N, H, W, Cin, Cout, k, stride):
+    L = force_pair
+    torch.manual_seed(2)
+    x = torch.randn(N, H, W, Cin, device=DEV).bfloat16()
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device=DEV)
+    pad = k // 2
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    y = ops.conv2d_nhwc(x, w, bias=bias, stride=stride, padding=pad, out_dtype=torch.float32)
+    assert L.dwg_gemm_last_pair() == 1, 'pair mode was not taken'
+    assert y.shape == ref.shape and _rel(y, ref) < 2e-3
+    temb = torch.randn(N, Cout, device=DEV)
+    res = torch.randn_like(ref).bfloat16()
+    y2 = ops.conv2d_nhwc(x, w, bias=bias, bias2=temb, residual=res, stride=stride, padding=pad)
+    assert _rel(y2, ref + temb[:, None, None, :] + res.float()) < 2e-2
+
+
+def test_geglu_cta_pair(force_pair):
+    torch.manual_seed(3)
+    M, K, inner = 2048, 640, 2560
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(2 * inner, K, device=DEV) / K ** 0.5).bfloat16()        # rows interleaved (value_i, gate_i)
+    bias = torch.randn(2 * inner, device=DEV)
+    y = ops.gemm(a, w, bias=bias, act='geglu')
+    assert force_pair.dwg_gemm_last_pair() == 1
+    full = a.float() @ w.float().t() + bias
+    ref = full[:, 0::2] * F.gelu(full[:, 1::2])
+    assert y.shape == (M, inner) and _rel(y, ref) < 2e-2

@@ -1,0 +1,72 @@
+"""Single CTA vs CTA pair (tcgen05 cta_group::2) on the large GEMM / conv shapes of the SDS step: cold weights
+(rotating copies), CUDA-graph replays, CUDA events.      python tools/gemm_pair_micro.py"""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'dreamwaltz-g_b200'))
+from dwg import ops  # noqa: E402
+from dwg._lib import lib  # noqa: E402
+
+DEV, NCOPY = 'cuda', 8
+L = lib()
+
+
+def timeit(fn):
+    fn(0)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.cuda.graph(g):
+        for i in range(NCOPY):
+            fn(i)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e3 / NCOPY)
+    return best
+
+
+def run(name, fn, flops, bns):
+    plan = (ctypes.c_int * 3)()
+    out = []
+    for pair in (0, 1):
+        L.dwg_gemm_tune_pair(pair)
+        for bn in bns:
+            L.dwg_gemm_tune(bn, 1)
+            fn(0)
+            if L.dwg_gemm_last_pair() != pair:
+                continue
+            L.dwg_gemm_last_plan(plan)
+            t = timeit(fn)
+            out.append((t, pair, plan[0], plan[2]))
+    L.dwg_gemm_tune(0, 0); L.dwg_gemm_tune_pair(-1)
+    t_auto = timeit(fn)
+    s = '  '.join(f"{'P' if p else 'S'}{bn}/{st}st {t:6.1f}us" for t, p, bn, st in out)
+    best = min(out)
+    print(f'{name:36s} auto {t_auto:6.1f}us ({flops / t_auto / 1e6:6.0f} TF/s) | best {"pair" if best[1] else "single"} BN{best[2]} {best[0]:6.1f}us ({flops / best[0] / 1e6:6.0f} TF/s) | {s}', flush=True)
+
+
+def main():
+    torch.manual_seed(0)
+    for M, N, K in ((8192, 4096, 4096), (8192, 320, 320), (8192, 2560, 320), (8192, 320, 1280), (2048, 640, 640), (2048, 5120, 640),
+                    (2048, 640, 2560), (512, 1280, 1280), (512, 10240, 1280), (512, 1280, 5120), (4096, 512, 512), (4096, 512, 4096)):
+        a = torch.randn(M, K, device=DEV).bfloat16()
+        bs = [torch.randn(N, K, device=DEV).bfloat16() for _ in range(NCOPY)]
+        run(f'gemm M{M} N{N} K{K}', lambda i: ops.gemm(a, bs[i % NCOPY]), 2.0 * M * N * K, (128, 160, 256))
+    for Ni, H, Ci, Co in ((1, 512, 128, 128), (1, 256, 256, 256), (1, 128, 512, 512), (1, 64, 512, 512), (2, 64, 320, 320), (2, 32, 640, 640),
+                          (2, 16, 1280, 1280), (2, 8, 1280, 1280), (2, 64, 640, 320), (2, 32, 1280, 640)):
+        x = torch.randn(Ni, H, H, Ci, device=DEV).bfloat16()
+        ws = [(torch.randn(Co, 3, 3, Ci, device=DEV) * 0.02).bfloat16() for _ in range(NCOPY)]
+        run(f'conv3x3 {Ni}x{H}x{H} {Ci}->{Co}', lambda i: ops.conv2d_nhwc(x, ws[i % NCOPY]), 2.0 * Ni * H * H * Ci * Co * 9, (128, 160, 256))
+
+
+if __name__ == '__main__':
+    main()
