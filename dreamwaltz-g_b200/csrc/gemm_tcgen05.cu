@@ -29,6 +29,11 @@
 //               bounds every large GEMM / convolution of the step.  Barriers: operand "full" lives in the
 //               leader (both CTAs' TMA loads complete_tx on it), "empty" / "accumulator full" are reached
 //               by multicast tcgen05.commit, "accumulator empty" collects local + remote epilogue arrivals.
+//   halo mode : (3x3, stride 1, "same") the nine taps of one 64-channel slice read shifted windows of ONE
+//               (16+2) x (8+2) pixel halo that is fetched once (18 line loads of 10 pixels, 16-row pitch) into
+//               its own ring; the A descriptor of tap (kh,kw) simply starts kh lines + kw rows into the halo
+//               (8-row groups = image lines, SBO = line pitch).  A traffic through the L2 port drops from
+//               9x to 1.4x of the activation; the B (weight) taps stream through the ordinary ring.
 // The epilogue body is deliberately compact (no unrolling over chunks, one instantiation per
 // output kind): v2's 265 KB of SASS made short kernels instruction-fetch bound (ncu: stall_no_inst).
 #include <cuda.h>
@@ -47,6 +52,14 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr uint32_t A_BYTES = BM * BK * 2;
 constexpr int TMEM_STAGE_COLS = 256;
+// halo mode (3x3 stride-1 convolutions): tile = 8 (w) x 16 (h) output pixels of one image
+constexpr int HALO_BW = 8, HALO_BH = 16;
+constexpr int HALO_LINES = HALO_BH + 2;                       // 18 input lines
+constexpr int HALO_LINE_PIX = HALO_BW + 2;                    // 10 pixels fetched per line
+constexpr uint32_t HALO_LINE_BYTES = 16 * 128;                // 16-row pitch: every line starts on a swizzle-atom boundary
+constexpr uint32_t HALO_BYTES = HALO_LINES * HALO_LINE_BYTES; // 36 KB per stage
+constexpr uint32_t HALO_TX = HALO_LINES * HALO_LINE_PIX * 128;
+constexpr int kMaxAStages = 4;
 
 enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };   // GEGLU: columns are (value, gate) pairs -> N/2 outputs
 enum Epi { EPI_BF16 = 0, EPI_F32 = 1, EPI_GEGLU = 2 };
@@ -78,6 +91,7 @@ struct Params {
     // tiling
     int BN, stages;
     int m_tiles, n_tiles, nz, ksplit, total_tiles;
+    int halo, a_stages, halo_bo;    // halo mode, depth of the halo ring, descriptor base-offset convention (see make_desc_halo)
     int m_sched;                    // scheduler units along M: m_tiles (single CTA) or m_tiles / 2 (CTA pair)
     float* workspace;               // split-K fp32 tile accumulators (zero when idle)
     int* counters;                  // one per output tile, self-resetting
@@ -206,6 +220,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
+// Halo operand of tap (kh, kw): 16 groups of 8 rows, one group per image line (SBO = line pitch), starting kw rows
+// into the line.  The start is then not aligned to the 1024-byte swizzle repeat.  Measured on sm_100a
+// (tools/halo_probe.py): the 128B-swizzle XOR is applied to the ABSOLUTE shared-memory address (exactly as TMA
+// wrote the lines), so the shifted start needs NO correction -- the "base offset" field [49,52) must stay 0
+// (setting it to (start >> 7) & 7 gives wrong results).
+__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(HALO_LINE_BYTES >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_off & 7u) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // exact-erf GELU (diffusers GEGLU / F.gelu default) with erf from Abramowitz-Stegun 7.1.26
 // (|abs err| <= 1.5e-7, far below the bf16 output rounding): one rcp + one ex2 instead of erff's
@@ -253,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     uint8_t* sA = smem;
-    uint8_t* sB = sA + p.stages * A_BYTES;
+    uint8_t* sB = sA + (p.halo ? p.a_stages * HALO_BYTES : p.stages * A_BYTES);
     uint8_t* sStage = sB + p.stages * B_BYTES;                         // [kEpiWarps][2][STG_BYTES]
     uint8_t* sRes = sStage + kEpiWarps * 2 * STG_BYTES;                // [kEpiWarps][2][2048] (only when has_res)
     float* s_bias = reinterpret_cast<float*>(sRes + (p.has_res ? kEpiWarps * 2 * 2048 : 0));      // [tile parity][image 0/1][256]
@@ -264,6 +294,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* res_bar = tmem_empty + 2;                // [kEpiWarps][2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
     volatile int* s_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(tmem_slot + 2);      // [kMaxAStages] halo ring
+    uint64_t* emptyA = fullA + kMaxAStages;
 
     const int warp = threadIdx.x >> 5;
     const int iters_total = p.taps_h * p.taps_w * p.k_chunks;
@@ -279,6 +311,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], PAIR ? 2 * kEpiWarps : kEpiWarps); }
         for (int i = 0; i < 2 * kEpiWarps; i++) mbar_init(&res_bar[i], 1);
+        for (int a = 0; a < kMaxAStages; a++) { mbar_init(&fullA[a], 1); mbar_init(&emptyA[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -326,6 +359,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 int it0, it1;
                 it_range(tc.ks, it0, it1);
+                if (p.halo) {
+                    // halo mode: this lane streams the weight taps only (channel-slice major, tap minor)
+                    for (int kc = 0; kc < p.k_chunks; kc++) {
+                        for (int tap = 0; tap < 9; tap++) {
+                            mbar_wait(&empty[s], ph ^ 1u);
+                            if (PAIR) {
+                                if (rank == 0) mbar_expect_tx(&full[s], 2u * B_BYTES);
+                                tma_load_4d_pair(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, tc.n_tile * p.BN + n_off, 0);
+                            } else {
+                                mbar_expect_tx(&full[s], B_BYTES);
+                                tma_load_4d(sB + s * B_BYTES, &tmB, &full[s], kc * BK, tap, tc.n_tile * p.BN, 0);
+                            }
+                            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                        }
+                    }
+                    continue;
+                }
                 int kc = it0 % p.k_chunks, tap = it0 / p.k_chunks;
                 for (int it = it0; it < it1; it++) {
                     mbar_wait(&empty[s], ph ^ 1u);
@@ -356,9 +406,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             }
         }
+    } else if (warp == 3) {
+        // halo ring producer: 18 line loads (10 pixels x 64 channels each) per 64-channel slice of a tile
+        if (p.halo && elect_one()) {
+            uint32_t sa = 0, pha = 0;
+            for (int t = tile0; t < p.total_tiles; t += tile_step) {
+                const TileCoord tc = decode_tile(p, t, m_mul, m_add);
+                const int tw = tc.m_tile % p.tiles_w;
+                const int th = (tc.m_tile / p.tiles_w) % p.tiles_h;
+                const int tn = tc.m_tile / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * HALO_BW - 1, h0 = th * HALO_BH - 1;
+                for (int kc = 0; kc < p.k_chunks; kc++) {
+                    mbar_wait(&emptyA[sa], pha ^ 1u);
+                    uint8_t* dst = sA + sa * HALO_BYTES;
+                    if (PAIR) {
+                        if (rank == 0) mbar_expect_tx(&fullA[sa], 2u * HALO_TX);       // the leader's barrier counts both CTAs' bytes
+                        for (int ln = 0; ln < HALO_LINES; ln++)
+                            tma_load_4d_pair(dst + ln * HALO_LINE_BYTES, &tmA, &fullA[sa], kc * BK, w0, h0 + ln, tn);
+                    } else {
+                        mbar_expect_tx(&fullA[sa], HALO_TX);
+                        for (int ln = 0; ln < HALO_LINES; ln++)
+                            tma_load_4d(dst + ln * HALO_LINE_BYTES, &tmA, &fullA[sa], kc * BK, w0, h0 + ln, tn);
+                    }
+                    if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
+                }
+            }
+        }
     } else if (warp == 1 && rank == 0) {
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
-        uint32_t s = 0, ph = 0, tl = 0;
+        uint32_t s = 0, ph = 0, tl = 0, sa = 0, pha = 0;
         for (int t = tile0; t < p.total_tiles; t += tile_step, tl++) {
             const TileCoord tc = decode_tile(p, t, m_mul, m_add);
             int it0, it1;
@@ -367,6 +443,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(&tmem_empty[as], ((tl >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator stage
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * TMEM_STAGE_COLS;
+            if (p.halo) {
+                for (int kc = 0; kc < p.k_chunks; kc++) {
+                    mbar_wait(&fullA[sa], pha);
+                    for (int tap = 0; tap < 9; tap++) {
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            if (tl == 0 && kc == 0 && tap == 0) TRACE(3);
+                            const uint32_t kh = (uint32_t)tap / 3u, kw = (uint32_t)tap % 3u;
+                            const uint64_t da = make_desc_halo(smem_u32(sA + sa * HALO_BYTES) + kh * HALO_LINE_BYTES + kw * 128u, p.halo_bo ? kw : 0u);
+                            const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; k++) {
+                                const uint32_t acc = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                                if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc);
+                                else tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc);
+                            }
+                            if (PAIR) tc_commit_pair(&empty[s]); else tc_commit(&empty[s]);
+                            if (tap == 8) { if (PAIR) tc_commit_pair(&emptyA[sa]); else tc_commit(&emptyA[sa]); }
+                            if (tap == 8 && kc == p.k_chunks - 1) {
+                                if (PAIR) tc_commit_pair(&tmem_full[as]); else tc_commit(&tmem_full[as]);
+                                if (tl == 0) TRACE(4);
+                            }
+                        }
+                        __syncwarp();
+                        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
+                    }
+                    if (++sa == (uint32_t)p.a_stages) { sa = 0; pha ^= 1u; }
+                }
+                continue;
+            }
             for (int it = it0; it < it1; it++) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
@@ -589,7 +696,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     // ---- slow path: unaligned strides; masked per-thread stores
                     if (row_ok) {
                         const int nvalid = min(32, ((EPI == EPI_GEGLU) ? (p.N >> 1) : p.N) - ocol0);
-                        for (int j = 0; j < nvalid; j++) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {                  // fully unrolled: a dynamic index would push f[] into local memory
+                            if (j >= nvalid) break;
                             float x = f[j];
                             if (p.residual) x += __bfloat162float(p.residual[d_res + ocol0 + j]);
                             if (EPI == EPI_F32) reinterpret_cast<float*>(p.C)[d_row + ocol0 + j] = x;
@@ -711,13 +820,13 @@ constexpr size_t kSmemBudget = 232448 - 1024;       // opt-in maximum minus the 
 
 static size_t smem_fixed(int epi, int has_res) {
     const size_t stg = (epi == EPI_F32) ? 4096 : 2048;
-    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + 2 * 2 * 256 * 4 + (2 * kMaxStages + 4 + 2 * kEpiWarps) * 8 + 64;
+    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + 2 * 2 * 256 * 4 + (2 * kMaxStages + 4 + 2 * kEpiWarps + 2 * kMaxAStages) * 8 + 64;
 }
 
 // Tile / split selection: a small analytic model of one CTA's critical path, in SM cycles.
 //   k-iteration = max(tensor pipe 2*BN, smem operand read 128 + BN, L2->SM feed of the CTAs running together)
 //   tile        = k-iterations + epilogue (TMEM drain + math + staging, two warps per lane quadrant)
-struct Plan { int BN, ks, stages, pair; };
+struct Plan { int BN, ks, stages, pair, halo; };      // halo: wanted for 3x3 stride-1 convolutions (the entry point checks legality)
 static unsigned long long* g_trace = nullptr;
 // Split-K scratch is per "lane": GEMMs enqueued on two streams that may run concurrently (ControlNet
 // beside the UNet encoder) must not share tile accumulators / counters.  dwg_gemm_set_lane() selects the
@@ -725,15 +834,18 @@ static unsigned long long* g_trace = nullptr;
 constexpr int kLanes = 2;
 static int g_lane = 0;
 static int g_force_bn = 0, g_force_ks = 0;        // tuning override (dwg_gemm_tune), 0 = automatic
+static int g_force_halo = -1;                     // dwg_gemm_tune_halo: -1 = automatic, 0 = never, 1 = whenever legal
+static int g_halo_bo = 0;                         // descriptor base-offset field of the shifted halo windows (debug knob; 0 is what sm_100a wants)
+static int g_last_halo = 0;
 static int g_force_pair = -1;                     // dwg_gemm_tune_pair: -1 = automatic, 0 = never, 1 = whenever legal
-static Plan g_last_plan = {0, 0, 0, 0};
+static Plan g_last_plan = {0, 0, 0, 0, 0};
 static int g_last_key[6] = {0, 0, 0, 0, 0, 0};
 // Measured plans for the shapes of the SDS step on a 148-SM B200 (tools/gemm_autotune.py writes the
 // table: cold weights, warm activations, CUDA-graph replays); anything else falls back to the model.
-struct TunedPlan { int m_tiles, nz, N, iters, epi, has_res, BN, ks, pair; };
+struct TunedPlan { int m_tiles, nz, N, iters, epi, has_res, BN, ks, pair, halo; };
 static const TunedPlan kTuned[] = {
 #include "gemm_plan_table.inc"
-    {0, 0, 0, 0, 0, 0, 0, 0, 0}};
+    {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
 // CTA pairs need an even number of 128-row tiles (no phantom half) and a tile width whose halves are whole swizzle groups
 static bool pair_legal(int m_tiles, int BN) { return (m_tiles % 2) == 0 && (BN % 32) == 0 && BN >= 32; }
 static int stages_for(int BN, int pair, int epi, int has_res) {
@@ -750,7 +862,8 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
                 const int64_t tiles = (int64_t)m_tiles * ((N + t->BN - 1) / t->BN) * nz;
                 const int pair = (t->pair && pair_legal(m_tiles, t->BN)) ? 1 : 0;
                 const int stages = stages_for(t->BN, pair, epi, has_res);
-                if (stages >= 2 && (t->ks == 1 || (tiles <= kMaxCounters / kLanes && tiles * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters))) pl = {t->BN, t->ks, stages, pair};
+                if (stages >= 2 && (t->ks == 1 || (tiles <= kMaxCounters / kLanes && tiles * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters)))
+                    pl = {t->BN, t->ks, stages, pair, t->halo && t->ks == 1};
                 break;
             }
         }
@@ -764,7 +877,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
         if (ks > iters) ks = iters;
         const int64_t tiles = (int64_t)m_tiles * ((N + BN - 1) / BN) * nz;
         if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
-        pl = {BN, ks, stages_for(BN, 0, epi, has_res), 0};
+        pl = {BN, ks, stages_for(BN, 0, epi, has_res), 0, 0};
     }
     if (g_force_pair >= 0) {
         pl.pair = (g_force_pair == 1 && pair_legal(m_tiles, pl.BN)) ? 1 : 0;
@@ -775,7 +888,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
 }
 static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats) {
     const int gran = (epi == EPI_GEGLU) ? 64 : 32;
-    Plan best = {gran, 1, 2, 0};
+    Plan best = {gran, 1, 2, 0, 0};
     double best_t = 1e30;
     const size_t fixed = smem_fixed(epi, has_res);
     for (int BN = gran; BN <= 256; BN += gran) {
@@ -802,8 +915,15 @@ static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int 
             double t_tile = t_main > t_epi ? t_main : t_epi;                    // steady state of a persistent CTA
             double t = 2500.0 + 1500.0 /* first TMA */ + (waves - 1.0) * t_tile + t_main + t_epi;
             if (ks > 1) t += 1500.0 + BN * 8.0;                                 // vector-atomic partial adds + counter + tile read-back
-            if (t < best_t) { best_t = t; best = {BN, ks, stages, 0}; }
+            if (t < best_t) { best_t = t; best = {BN, ks, stages, 0, 0}; }
         }
+    }
+    // shapes outside the measured table: pairs / halos pay once the launch is bound by the L2 -> SM operand feed,
+    // i.e. every SM has a tile and the K loop is long enough to amortise the cluster hand-shakes
+    const int64_t tiles = (int64_t)m_tiles * ((N + best.BN - 1) / best.BN) * nz;
+    if (best.ks == 1 && tiles >= g_num_sms) {
+        best.halo = 1;
+        if (pair_legal(m_tiles, best.BN) && iters >= 8) { best.pair = 1; best.stages = stages_for(best.BN, 1, epi, has_res); }
     }
     return best;
 }
@@ -850,7 +970,9 @@ static int ensure_globals() {
 
 static int launch(const CUtensorMap& tmA, CUtensorMap& tmB_out, const CUtensorMap& tmC, const CUtensorMap& tmR, Params& p, int epi, cudaStream_t st) {
     const bool pair = p.m_sched != p.m_tiles;
-    const size_t smem = 1024 + (size_t)p.stages * (A_BYTES + (size_t)(pair ? p.BN / 2 : p.BN) * 128) + smem_fixed(epi, p.has_res);
+    const size_t b_bytes = (size_t)(pair ? p.BN / 2 : p.BN) * 128;
+    const size_t smem = 1024 + (p.halo ? (size_t)p.a_stages * HALO_BYTES + (size_t)p.stages * b_bytes : (size_t)p.stages * (A_BYTES + b_bytes)) +
+                        smem_fixed(epi, p.has_res);
     if (pair) {
         const int pairs = g_num_sms / 2;
         const dim3 grid(2 * (p.total_tiles < pairs ? p.total_tiles : pairs));
@@ -990,7 +1112,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     p.stride = stride; p.pad_h = pad_h; p.pad_w = pad_w;
     p.ebw = BW < 32 ? BW : 32;
     p.ebh = (32 / p.ebw) < BH ? (32 / p.ebw) : BH;
-    const int ebn = 32 / (p.ebw * p.ebh);
+    int ebn = 32 / (p.ebw * p.ebh);
     p.C = y; p.ldc = Cout;
     p.bias = bias; p.bias2 = bias2_per_image; p.bias2_rows_per = bias2_per_image ? Ho * Wo : 0;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
@@ -999,6 +1121,25 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     const int iters = ksize * ksize * p.k_chunks;
     const Plan pl = plan_tiles(p.m_tiles, 1, Cout, iters, epi, p.has_res, (int64_t)(g_ws_bytes / 4 / kLanes));
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
+    // ---- halo mode: 3x3 / stride 1 / "same" on images that tile into 8 x 16 pixel blocks, no split-K
+    p.halo = 0;
+    const bool halo_legal = ksize == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && Ho == H && Wo == W && (Ho % HALO_BH) == 0 &&
+                            (Wo % HALO_BW) == 0 && pl.ks == 1 && !p.direct;
+    if (halo_legal && g_force_halo != 0 && (g_force_halo == 1 || pl.halo)) {
+        const size_t b_bytes = (size_t)(pl.pair ? pl.BN / 2 : pl.BN) * 128;
+        const int a_stages = 2;
+        int64_t bst = ((int64_t)kSmemBudget - (int64_t)smem_fixed(epi, p.has_res) - (int64_t)a_stages * HALO_BYTES) / (int64_t)b_bytes;
+        if (bst > kMaxStages) bst = kMaxStages;
+        const int halo_m_tiles = (Wo / HALO_BW) * (Ho / HALO_BH) * Nimg;
+        if (bst >= 3 && (!pl.pair || (halo_m_tiles % 2) == 0)) {         // the pair plan was made for an even tile count
+            p.halo = 1; p.a_stages = a_stages; p.halo_bo = g_halo_bo; p.stages = (int)bst;
+            BW = HALO_BW; BH = HALO_BH; BNI = 1;
+            p.BH = BH; p.BW = BW; p.BNI = BNI; p.tiles_w = Wo / BW; p.tiles_h = Ho / BH;
+            p.ebw = BW; p.ebh = 32 / BW; ebn = 1;
+            p.m_tiles = p.tiles_w * p.tiles_h * Nimg;
+        }
+    }
+    g_last_halo = p.halo;
     p.n_tiles = (Cout + p.BN - 1) / p.BN;
     p.m_sched = pl.pair ? p.m_tiles / 2 : p.m_tiles;
     p.total_tiles = p.m_sched * p.n_tiles * p.ksplit;
@@ -1008,7 +1149,9 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     {
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-        const uint32_t box[4] = {BK, (uint32_t)((BW - 1) * stride + 1), (uint32_t)((BH - 1) * stride + 1), (uint32_t)BNI};
+        const uint32_t box_t[4] = {BK, (uint32_t)((BW - 1) * stride + 1), (uint32_t)((BH - 1) * stride + 1), (uint32_t)BNI};
+        const uint32_t box_h[4] = {BK, (uint32_t)HALO_LINE_PIX, 1, 1};          // one halo line
+        const uint32_t* box = p.halo ? box_h : box_t;
         const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         rc = make_map_bf16(&tmA, x, dims, str, box, es);
         if (rc) return rc;
@@ -1049,6 +1192,14 @@ extern "C" int dwg_gemm_last_plan(int* out3) {
 }
 /* CTA-pair (tcgen05 cta_group::2) mode of the following launches: -1 automatic, 0 never, 1 whenever legal;
  * dwg_gemm_last_pair() reads back what the last launch used. */
+/* halo mode of 3x3 stride-1 convolutions: -1 automatic, 0 never, 1 whenever legal; base_offset_mode = 1 puts
+ * (start >> 7) & 7 into the descriptors' base-offset field (wrong on sm_100a, kept for tools/halo_probe.py), 0 = default. */
+extern "C" int dwg_gemm_tune_halo(int mode, int base_offset_mode) {
+    g_force_halo = mode < 0 ? -1 : (mode ? 1 : 0);
+    g_halo_bo = base_offset_mode ? 1 : 0;
+    return DWG_OK;
+}
+extern "C" int dwg_gemm_last_halo(void) { return g_last_halo; }
 extern "C" int dwg_gemm_tune_pair(int mode) { g_force_pair = mode < 0 ? -1 : (mode ? 1 : 0); return DWG_OK; }
 extern "C" int dwg_gemm_last_pair(void) { return g_last_plan.pair; }
 /* the planner key of the last launch: (m_tiles, nz, N, k_iterations, epilogue kind, has_residual) */

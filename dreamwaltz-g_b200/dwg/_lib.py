@@ -56,6 +56,8 @@ SIGNATURES = {
     'dwg_gemm_tune': (c_int, [c_int, c_int]),
     'dwg_gemm_last_plan': (c_int, [c_void_p]),
     'dwg_gemm_tune_pair': (c_int, [c_int]),
+    'dwg_gemm_tune_halo': (c_int, [c_int, c_int]),
+    'dwg_gemm_last_halo': (c_int, []),
     'dwg_gemm_last_pair': (c_int, []),
     'dwg_gemm_last_key': (c_int, [c_void_p]),
     'dwg_gemm_trace': (c_int, [c_void_p]),

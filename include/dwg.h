@@ -197,6 +197,11 @@ int dwg_gemm_last_plan(int* out3);
 /* CTA-pair (tcgen05.mma.cta_group::2, cluster of 2) mode of the following launches: -1 automatic (planner / tuned
  * table), 0 never, 1 whenever legal (even number of 128-row tiles); dwg_gemm_last_pair() -> what the last launch used. */
 int dwg_gemm_tune_pair(int mode);
+/* Halo mode of 3x3 / stride-1 / "same" convolutions (one (16+2)x(8+2) activation halo per 64-channel slice feeds all nine
+ * taps): -1 automatic, 0 never, 1 whenever legal.  base_offset_mode: 0 (default, correct on sm_100a) leaves the
+ * matrix-descriptor base-offset field of the shifted windows zero; 1 sets it to (start >> 7) & 7 (probe only). */
+int dwg_gemm_tune_halo(int mode, int base_offset_mode);
+int dwg_gemm_last_halo(void);
 int dwg_gemm_last_pair(void);
 /* Split-K scratch lane (0 or 1) used by the launches that follow: GEMMs enqueued on two streams that may run
  * concurrently (ControlNet beside the UNet encoder, dwg/diffusion/guidance.py) must use different lanes. */

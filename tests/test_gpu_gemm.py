@@ -194,3 +194,37 @@ def test_geglu_cta_pair(force_pair):
     full = a.float() @ w.float().t() + bias
     ref = full[:, 0::2] * F.gelu(full[:, 1::2])
     assert y.shape == (M, inner) and _rel(y, ref) < 2e-2
+
+
+@pytest.mark.parametrize('pair', [0, 1])
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(1, 32, 32, 64, 64), (2, 64, 64, 320, 320), (1, 128, 128, 128, 128), (1, 64, 64, 8, 32),
+                                            (2, 16, 16, 1280, 640), (1, 48, 24, 72, 96), (3, 16, 8, 64, 320)])
+def test_conv3x3_halo_mode_matches_torch(pair, N, H, W, Cin, Cout):
+    """Halo mode: one (16+2)x(8+2) activation halo per 64-channel slice feeds the nine taps through shifted descriptors."""
+    from dwg._lib import lib
+    L = lib()
+    if pair and ((W // 8) * (H // 16) * N) % 2:
+        pytest.skip('CTA pairs need an even number of 8x16-pixel tiles (the planner falls back to the per-tap path)')
+    torch.manual_seed(4)
+    x = torch.randn(N, H, W, Cin, device=DEV).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device=DEV) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device=DEV)
+    temb = torch.randn(N, Cout, device=DEV)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    res = torch.randn_like(ref).bfloat16()
+    L.dwg_gemm_tune_halo(1, 0)
+    L.dwg_gemm_tune_pair(pair)
+    L.dwg_gemm_tune(128, 1)                          # halo mode does not split K
+    try:
+        y = ops.conv2d_nhwc(x, w, bias=bias, out_dtype=torch.float32)
+        took = L.dwg_gemm_last_halo()
+        y2 = ops.conv2d_nhwc(x, w, bias=bias, bias2=temb, residual=res)
+        for _ in range(2):
+            y3 = ops.conv2d_nhwc(x, w, bias=bias, out_dtype=torch.float32)
+    finally:
+        L.dwg_gemm_tune_halo(-1, 0)
+        L.dwg_gemm_tune_pair(-1)
+        L.dwg_gemm_tune(0, 0)
+    assert took == 1, 'halo mode was not taken'
+    assert _rel(y, ref) < 2e-3 and _rel(y3, ref) < 2e-3
+    assert _rel(y2, ref + temb[:, None, None, :] + res.float()) < 2e-2

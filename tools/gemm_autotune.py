@@ -109,46 +109,64 @@ def main():
     plan, key = (ctypes.c_int * 3)(), (ctypes.c_int * 6)()
     seen, rows = {}, []
     tot_auto = tot_best = 0.0
+    def force(bn, ks, pair, halo):
+        L.dwg_gemm_tune(bn, ks)
+        L.dwg_gemm_tune_pair(pair)
+        L.dwg_gemm_tune_halo(halo, 0)
+
+    def taken():
+        L.dwg_gemm_last_plan(plan)
+        return (plan[0], plan[1], L.dwg_gemm_last_pair(), L.dwg_gemm_last_halo())
+
+    import time
+    t_begin, budget = time.time(), float(os.environ.get('DWG_TUNE_BUDGET_S', '1e9'))
     for call in rec:
+        if time.time() - t_begin > budget:
+            print('time budget reached: remaining keys keep the analytic plan', flush=True)
+            break
         fn, touch = make_problem(call)
-        L.dwg_gemm_tune(-1, 0)                  # -1: analytic model only (ignore the table)
+        force(-1, 0, -1, -1)                    # -1: analytic model only (ignore the table)
         fn(0)
         L.dwg_gemm_last_key(key)
         k = tuple(key)
         if k in seen:
             seen[k][0] += 1
             continue
-        L.dwg_gemm_last_plan(plan)
-        auto = tuple(plan)
+        auto = taken()
         t_auto = time_config(fn, touch)
         geglu = k[4] == 2
-        res = [(t_auto, auto[0], auto[1])]
-        for bn in ((64, 128, 192, 256) if geglu else (32, 64, 96, 128, 160, 192, 224, 256)):
-            for ks in ((1,) if geglu else (1, 2, 3, 4, 6, 8, 12, 16)):
-                if (bn, ks) == (auto[0], auto[1]):
+        conv3 = call[0] == 'conv' and call[6] == 3 and call[7] == 1
+        res = {auto: t_auto}
+        bns = (64, 128, 192, 256) if geglu else (32, 64, 96, 128, 160, 192, 224, 256)
+        kss = (1,) if geglu else (1, 2, 3, 4, 6, 8, 12, 16)
+        cands = [(bn, ks, 0, 0) for bn in bns for ks in kss]
+        cands += [(bn, ks, 1, 0) for bn in bns if bn >= 64 for ks in kss if ks <= 4 and k[0] % 2 == 0]
+        if conv3:
+            cands += [(bn, 1, pr, 1) for bn in bns if bn >= 64 for pr in (0, 1)]
+        for bn, ks, pr, hl in cands:
+            if ks > 1:
+                n_tiles = (k[2] + bn - 1) // bn
+                if k[0] * k[1] * n_tiles * ks > 2 * 148:
                     continue
-                L.dwg_gemm_tune(bn, ks)
-                fn(0)
-                L.dwg_gemm_last_plan(plan)
-                if plan[0] != bn or plan[1] != ks:
-                    continue
-                if ks > 1:
-                    n_tiles = (k[2] + bn - 1) // bn
-                    if k[0] * k[1] * n_tiles * ks > 2 * 148:
-                        continue
-                res.append((time_config(fn, touch), bn, ks))
-        L.dwg_gemm_tune(0, 0)
-        res.sort()
-        best = res[0]
+            force(bn, ks, pr, hl)
+            fn(0)
+            got = taken()
+            if got != (bn, ks, pr, hl) or got in res:
+                continue
+            res[got] = time_config(fn, touch)
+        force(0, 0, -1, -1)
+        ranked = sorted((t, c) for c, t in res.items())
+        best = ranked[0]
         # keep the model's choice unless the measured winner is clearly (3%) better
         if best[0] > 0.97 * t_auto:
-            best = (t_auto, auto[0], auto[1])
+            best = (t_auto, auto)
         seen[k] = [1, t_auto, best]
-        print(f'{str(call[:12]):70s} key={k} auto {t_auto:7.1f} us BN{auto[0]:3d}/ks{auto[1]:2d} -> best {best[0]:7.1f} us BN{best[1]:3d}/ks{best[2]:2d}', flush=True)
+        print(f'{str(call[:12]):70s} key={k} auto {t_auto:7.1f} us {auto} -> best {best[0]:7.1f} us {best[1]}', flush=True)
     with open(out, 'w') as fh:
-        fh.write('// generated by tools/gemm_autotune.py on a 148-SM B200: {m_tiles, nz, N, k_iters, epi, has_res, BN, ksplit}\n')
+        fh.write('// generated by tools/gemm_autotune.py on a 148-SM B200: {m_tiles, nz, N, k_iters, epi, has_res, BN, ksplit, pair, halo}\n')
         for k, (n, t_auto, best) in sorted(seen.items()):
-            fh.write(f'    {{{k[0]}, {k[1]}, {k[2]}, {k[3]}, {k[4]}, {k[5]}, {best[1]}, {best[2]}}},   // x{n}: {t_auto:.1f} -> {best[0]:.1f} us\n')
+            bn, ks, pr, hl = best[1]
+            fh.write(f'    {{{k[0]}, {k[1]}, {k[2]}, {k[3]}, {k[4]}, {k[5]}, {bn}, {ks}, {pr}, {hl}}},   // x{n}: {t_auto:.1f} -> {best[0]:.1f} us\n')
             tot_auto += n * t_auto
             tot_best += n * best[0]
     print(f'{len(seen)} keys; per step: model {tot_auto / 1e3:.3f} ms -> tuned {tot_best / 1e3:.3f} ms; wrote {out}')

@@ -34,29 +34,31 @@ def timeit(fn):
     return best
 
 
-def run(name, fn, flops, bns):
+def run(name, fn, flops, bns, conv=False):
     plan = (ctypes.c_int * 3)()
     out = []
-    for pair in (0, 1):
-        L.dwg_gemm_tune_pair(pair)
-        for bn in bns:
-            L.dwg_gemm_tune(bn, 1)
-            fn(0)
-            if L.dwg_gemm_last_pair() != pair:
-                continue
-            L.dwg_gemm_last_plan(plan)
-            t = timeit(fn)
-            out.append((t, pair, plan[0], plan[2]))
-    L.dwg_gemm_tune(0, 0); L.dwg_gemm_tune_pair(-1)
+    for halo in ((0, 1) if conv else (0,)):
+        L.dwg_gemm_tune_halo(halo, 0)
+        for pair in (0, 1):
+            L.dwg_gemm_tune_pair(pair)
+            for bn in bns:
+                L.dwg_gemm_tune(bn, 1)
+                fn(0)
+                if L.dwg_gemm_last_pair() != pair or (conv and L.dwg_gemm_last_halo() != halo):
+                    continue
+                L.dwg_gemm_last_plan(plan)
+                t = timeit(fn)
+                out.append((t, ('H' if halo else '') + ('P' if pair else 'S'), plan[0], plan[2]))
+    L.dwg_gemm_tune(0, 0); L.dwg_gemm_tune_pair(-1); L.dwg_gemm_tune_halo(-1, 0)
     t_auto = timeit(fn)
-    s = '  '.join(f"{'P' if p else 'S'}{bn}/{st}st {t:6.1f}us" for t, p, bn, st in out)
+    s = '  '.join(f"{m}{bn}/{st}st {t:6.1f}" for t, m, bn, st in out)
     best = min(out)
-    print(f'{name:36s} auto {t_auto:6.1f}us ({flops / t_auto / 1e6:6.0f} TF/s) | best {"pair" if best[1] else "single"} BN{best[2]} {best[0]:6.1f}us ({flops / best[0] / 1e6:6.0f} TF/s) | {s}', flush=True)
+    print(f'{name:32s} auto {t_auto:6.1f}us ({flops / t_auto / 1e6:5.0f} TF/s) | best {best[1]:2s} BN{best[2]} {best[0]:6.1f}us ({flops / best[0] / 1e6:5.0f} TF/s) | {s}', flush=True)
 
 
 def main():
     torch.manual_seed(0)
-    for M, N, K in ((8192, 4096, 4096), (8192, 320, 320), (8192, 2560, 320), (8192, 320, 1280), (2048, 640, 640), (2048, 5120, 640),
+    for M, N, K in () if '--conv' in sys.argv else ((8192, 4096, 4096), (8192, 320, 320), (8192, 2560, 320), (8192, 320, 1280), (2048, 640, 640), (2048, 5120, 640),
                     (2048, 640, 2560), (512, 1280, 1280), (512, 10240, 1280), (512, 1280, 5120), (4096, 512, 512), (4096, 512, 4096)):
         a = torch.randn(M, K, device=DEV).bfloat16()
         bs = [torch.randn(N, K, device=DEV).bfloat16() for _ in range(NCOPY)]
@@ -65,7 +67,7 @@ def main():
                           (2, 16, 1280, 1280), (2, 8, 1280, 1280), (2, 64, 640, 320), (2, 32, 1280, 640)):
         x = torch.randn(Ni, H, H, Ci, device=DEV).bfloat16()
         ws = [(torch.randn(Co, 3, 3, Ci, device=DEV) * 0.02).bfloat16() for _ in range(NCOPY)]
-        run(f'conv3x3 {Ni}x{H}x{H} {Ci}->{Co}', lambda i: ops.conv2d_nhwc(x, ws[i % NCOPY]), 2.0 * Ni * H * H * Ci * Co * 9, (128, 160, 256))
+        run(f'conv3x3 {Ni}x{H}x{H} {Ci}->{Co}', lambda i: ops.conv2d_nhwc(x, ws[i % NCOPY]), 2.0 * Ni * H * H * Ci * Co * 9, (128, 160, 256), conv=True)
 
 
 if __name__ == '__main__':
