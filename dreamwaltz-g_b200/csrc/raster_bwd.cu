@@ -14,6 +14,46 @@ namespace dwg {
 namespace raster {
 
 constexpr int NG = 10;      // mean2D.xy, conic.xyz, opacity, colour.rgb, depth
+constexpr int BWD_BATCH = 2;
+
+// Sum each of 10 per-lane values over the 32 lanes with 12 shuffles: at every butterfly step a lane keeps half
+// of the values it still holds and hands the other half to its partner, so the value count halves as the lane
+// span doubles (5 + 3 + 2 + 1 + 1 shuffles).  Returns the complete sum of value `q` (q = -1: this lane owns none;
+// every value is owned by exactly one even lane).
+__device__ __forceinline__ float reduce10(const float (&v)[NG], int lane, int& q) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float a[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const float send = b4 ? v[i] : v[5 + i], keep = b4 ? v[5 + i] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float b[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float hi = (i < 2) ? a[3 + (i < 2 ? i : 0)] : 0.f;
+        const float send = b3 ? a[i] : hi, keep = b3 ? hi : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float c[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float hi = (i < 1) ? b[2] : 0.f;
+        const float send = b2 ? b[i] : hi, keep = b2 ? hi : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    float d;
+    {
+        const float send = b1 ? c[0] : c[1], keep = b1 ? c[1] : c[0];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    // which value this lane ended up with: groups {0..4 | 5..9} -> {0,1,2 | 3,4,-} -> {0,1 | 2,-} -> {0 | 1}
+    const int s5 = b3 ? (3 + (b1 ? 1 : 0)) : ((b2 ? 2 : 0) + (b1 ? 1 : 0));
+    const bool valid = !(b2 && (b3 || b1)) && !(lane & 1);
+    q = valid ? (b4 ? 5 : 0) + s5 : -1;
+    return d;
+}
 
 __global__ void __launch_bounds__(TILE_PIX)
 render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
@@ -98,18 +138,38 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
               touch = strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1);
           }
           unsigned tmask = __ballot_sync(0xffffffffu, touch);
+          // Touched instances are replayed back to front, BWD_BATCH at a time: the alphas (the long, position-only
+          // chain) are evaluated together, the short T / accumulator recurrences run in order, and the 10
+          // per-instance sums are reduced across the warp with a 12-shuffle "split" butterfly (reduce10) instead
+          // of 10 x 5 shuffles; the lanes that end up owning a sum add it to shared memory in parallel.
           while (tmask) {
-            const int bit = 31 - __clz(tmask);
-            tmask &= ~(1u << bit);
-            const int j = j0 + bit;
-            const uint32_t k = (uint32_t)(c * CHUNK + j);
-            float v[NG];
-            bool contrib = false;
-            if (k < last_contributor) {
-                const Rec rc = s_rec[buf][j];
-                float alpha, G, dx, dy;
-                if (eval_alpha(rc, pxf, pyf, alpha, G, dx, dy)) {
-                    contrib = true;
+            int jb[BWD_BATCH];
+            bool ok[BWD_BATCH];
+            float al[BWD_BATCH], Gv[BWD_BATCH], dxv[BWD_BATCH], dyv[BWD_BATCH];
+            Rec rcs[BWD_BATCH];
+#pragma unroll
+            for (int u = 0; u < BWD_BATCH; u++) {
+                const int bit = tmask ? 31 - __clz(tmask) : 0;
+                ok[u] = tmask != 0u;
+                tmask &= ~(1u << bit);
+                jb[u] = j0 + bit;
+                ok[u] = ok[u] && ((uint32_t)(c * CHUNK + jb[u]) < last_contributor);
+            }
+#pragma unroll
+            for (int u = 0; u < BWD_BATCH; u++) {
+                rcs[u] = s_rec[buf][jb[u]];
+                ok[u] &= eval_alpha_nb(rcs[u], pxf, pyf, al[u], Gv[u], dxv[u], dyv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < BWD_BATCH; u++) {
+                const unsigned m = __ballot_sync(0xffffffffu, ok[u]);
+                if (m == 0u) continue;                          // warp-uniform: nobody in this strip blends the instance
+                float v[NG];
+#pragma unroll
+                for (int q = 0; q < NG; q++) v[q] = 0.f;
+                if (ok[u]) {
+                    const Rec& rc = rcs[u];
+                    const float alpha = al[u], G = Gv[u], dx = dxv[u], dy = dyv[u];
                     T = T / (1.f - alpha);
                     const float dchannel_dcolor = alpha * T;
                     float dL_dalpha_ = 0.f;
@@ -139,26 +199,9 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                     v[4] = -0.5f * gdy * dy * dL_dG;
                     v[5] = G * dL_dalpha_;
                 }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, contrib);
-            if (m == 0u) continue;                              // warp-uniform
-            if (!contrib) {
-#pragma unroll
-                for (int q = 0; q < NG; q++) v[q] = 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < NG; q++) {
-                float s = v[q];
-                s += __shfl_xor_sync(0xffffffffu, s, 16);
-                s += __shfl_xor_sync(0xffffffffu, s, 8);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                v[q] = s;
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < NG; q++) atomicAdd(&s_acc[j][q], v[q]);
+                int q;
+                const float tot = reduce10(v, lane, q);
+                if (q >= 0) atomicAdd(&s_acc[jb[u]][q], tot);
             }
           }
         }

@@ -141,6 +141,21 @@ __device__ __forceinline__ bool eval_alpha(const Rec& rc, float pxf, float pyf, 
     return !(alpha < 1.0f / 255.0f);
 }
 
+// Branch-free variant for batched evaluation (several instances in flight per thread): identical operations and
+// results for every accepted instance; rejected ones evaluate the exponential of a harmless argument.
+__device__ __forceinline__ bool eval_alpha_nb(const Rec& rc, float pxf, float pyf, float& alpha, float& G, float& dx, float& dy) {
+    dx = __fsub_rn(rc.x, pxf);
+    dy = __fsub_rn(rc.y, pyf);
+    const float a = __fmul_rn(__fmul_rn(rc.cx, dx), dx);
+    const float b = __fmul_rn(__fmul_rn(rc.cz, dy), dy);
+    const float c = __fmul_rn(__fmul_rn(rc.cy, dx), dy);
+    const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(a, b)), c);
+    const bool rej = (power > 0.0f) | ((power < -5.6f) & (rc.op <= 1.0f));
+    G = spec_expf(rej ? -1.0f : power);
+    alpha = fminf(0.99f, __fmul_rn(rc.op, G));
+    return !rej & !(alpha < 1.0f / 255.0f);
+}
+
 // Conservative test: can ANY pixel of the strip [x0,x1] x [y0,y1] get alpha >= 1/255 ?
 __device__ __forceinline__ bool strip_may_touch(float rx, float ry, uint32_t ext, float x0, float x1, float y0, float y1) {
     const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&ext));

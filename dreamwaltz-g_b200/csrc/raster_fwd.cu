@@ -17,6 +17,8 @@ int launch_pre(const DwgRasterCamera& cam, const DwgRasterCamera* cam_dev, int64
 int launch_sort(int T, BinView b, GeomView g, const float* colors, const int32_t* status, int64_t P_cap,
                 int write_keys, cudaStream_t st);
 
+constexpr int FWD_BATCH = 4;      // touched instances whose alphas are evaluated together (ILP)
+
 __global__ void __launch_bounds__(TILE_PIX)
 render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
                   float bg0, float bg1, float bg2, const float* __restrict__ bg_dev,
@@ -83,23 +85,45 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                     touch = strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1);
                 }
                 unsigned mask = __ballot_sync(0xffffffffu, touch);
+                // The touched instances are taken FWD_BATCH at a time: their alphas (position-only maths, the
+                // long dependent chain with the exp) are evaluated independently of each other first, then the
+                // short transmittance chain is applied in source order -- same operations per instance, same
+                // order, hence the same bits; ~3x shorter critical path per instance on heavy tiles.
                 while (mask) {
-                    const int j = j0 + __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    if (done) continue;
-                    const Rec rc = s_rec[buf][j];
-                    float alpha, G, dx, dy;
-                    if (!eval_alpha(rc, pxf, pyf, alpha, G, dx, dy)) continue;
-                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                    if (test_T < 0.0001f) { done = true; continue; }
-                    const float w = __fmul_rn(alpha, T);
-                    C0 = __fadd_rn(C0, __fmul_rn(rc.r, w));
-                    C1 = __fadd_rn(C1, __fmul_rn(rc.g, w));
-                    C2 = __fadd_rn(C2, __fmul_rn(rc.b, w));
-                    D = __fadd_rn(D, __fmul_rn(rc.depth, w));
-                    A = __fadd_rn(A, w);
-                    T = test_T;
-                    last = (uint32_t)(c * CHUNK + j + 1);
+                    int jb[FWD_BATCH];
+                    bool ok[FWD_BATCH];
+                    float al[FWD_BATCH], cr[FWD_BATCH], cg[FWD_BATCH], cb[FWD_BATCH], cd[FWD_BATCH];
+#pragma unroll
+                    for (int u = 0; u < FWD_BATCH; u++) {
+                        ok[u] = (mask != 0u) && !done;
+                        jb[u] = j0 + (mask ? __ffs(mask) - 1 : 0);
+                        mask &= mask - 1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < FWD_BATCH; u++) {                  // straight-line: FWD_BATCH independent chains
+                        const Rec rc = s_rec[buf][jb[u]];
+                        float G, dx, dy;
+                        ok[u] &= eval_alpha_nb(rc, pxf, pyf, al[u], G, dx, dy);
+                        cr[u] = rc.r; cg[u] = rc.g; cb[u] = rc.b; cd[u] = rc.depth;
+                    }
+#pragma unroll
+                    for (int u = 0; u < FWD_BATCH; u++) {
+                        if (ok[u] && !done) {
+                            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
+                            if (test_T < 0.0001f) {
+                                done = true;
+                            } else {
+                                const float w = __fmul_rn(al[u], T);
+                                C0 = __fadd_rn(C0, __fmul_rn(cr[u], w));
+                                C1 = __fadd_rn(C1, __fmul_rn(cg[u], w));
+                                C2 = __fadd_rn(C2, __fmul_rn(cb[u], w));
+                                D = __fadd_rn(D, __fmul_rn(cd[u], w));
+                                A = __fadd_rn(A, w);
+                                T = test_T;
+                                last = (uint32_t)(c * CHUNK + jb[u] + 1);
+                            }
+                        }
+                    }
                 }
             }
         }
