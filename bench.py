@@ -27,6 +27,9 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# rank 0 prints exactly ONE JSON line on stdout: NCCL's own banner / debug output goes to stderr
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -129,6 +132,7 @@ class Scene:
     def step(self, pose_dev, data, embeds, cond):
         for p in self.params:
             p.grad = None
+        self.guidance.prepare(embeds, cond)
         gs = self.avatar.animate(pose_dev)
         out = self.renderer.render(data, gs)
         res = self.guidance(out['image_chw'].unsqueeze(0), embeds, cond_inputs=cond)
@@ -159,6 +163,7 @@ class StepGraph:
         def body():
             for p in sc.params:
                 p.grad = None
+            sc.guidance.prepare(self.embeds, self.cond)          # prompt / condition / timestep work starts on the side stream
             gs = sc.avatar.animate(self.pose)
             out = sc.renderer.render(self.data, gs, cam_dev=self.cam)
             res = sc.guidance(out['image_chw'].unsqueeze(0), self.embeds, cond_inputs=self.cond)
@@ -316,6 +321,7 @@ def run_dwg(args):
         saved = getattr(g, '_g', None)
         g._g = None
         ops.PROFILE = []
+        ops.PROFILE_BYTES = 0.0
         img = torch.rand(1, 3, args.image, args.image, device=dev, requires_grad=True)
         for _ in range(5):
             torch.cuda._sleep(int(4e8))          # ~1 s head start: the CPU enqueues the whole un-graphed pass while the GPU is parked
@@ -332,6 +338,23 @@ def run_dwg(args):
                 'peak': peak, 'unit': 'TFLOP/s', 'frac': round(ach / peak, 4), 'traffic': None, 'launches': len(prof),
                 'algorithmic_tflop_per_step': round(tot_fl / 1e12, 3), 'kernel_ms_per_step': round(tot_ms, 3),
                 'peak_source': pk_src + ' bf16_tflops_sustained (kernel timed inside a long step)'}
+
+    # ---- rasteriser roofline (SURVEY 8d formula): fwd + bwd of the last view, un-graphed, CUDA events on the stream
+    roof_r = None
+    if rank == 0:
+        try:
+            roof_r = raster_roofline(sc, args.image, pk, pk_src)
+        except Exception as e:                       # reported, never fatal for the headline number
+            roof_r = {'error': f'{type(e).__name__}: {e}'}
+        if roof is not None:
+            tj = os.path.join(ROOT, 'profiles', 'r1c_gemm_traffic.json')
+            if os.path.exists(tj):
+                t = json.load(open(tj))
+                roof['traffic'] = round(t['gemm']['dram_bytes_per_launch'] / 1e6, 3)
+                roof['traffic_unit'] = 'MB of DRAM read+write per launch, mean over the %d gemm_kernel launches of one step (ncu, %s)' % (
+                    t['gemm']['launches'], 'profiles/r1c_gemm_traffic.json')
+                n_gemm = sum(1 for _, _, _, kind in prof if not kind.startswith('attention'))
+                roof['algorithmic_MB_per_launch'] = round(ops.PROFILE_BYTES / 1e6 / max(n_gemm, 1), 3)
 
     if rank != 0:
         if world > 1:
@@ -351,12 +374,64 @@ def run_dwg(args):
                    'cuda_graphs': ('whole step' if sg is not None else ('sub-graphs' if not args.no_graphs else False))},
         'e2e': {'value': round(e2e_v, 3), 'unit': 'steps/s', 'ms_per_step': round(ms_e2e, 3), 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 12},
         'gpu_launches': int(round(launches)), 'host_enqueue_ms_per_step': round(cpu_enqueue_ms, 3), 'clocks': clocks, 'roofline': roof,
+        'roofline_raster': roof_r,
     }
     if not args.skip_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(sample_only=True)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def raster_roofline(sc, img, pk, pk_src):
+    """Achieved GB/s of dwg_raster_forward + dwg_raster_backward against the HBM copy peak.
+    Algorithmic bytes: fwd 56 N + 24 P + 44 P + 28 HW, bwd 44 P + 32 HW + 124 N, P measured on this view."""
+    from dwg import camera, ops
+    dev = sc.dev
+    pose, data = sc.next_view()
+    with torch.no_grad():
+        gs = sc.avatar.animate({k: v.to(dev) for k, v in pose.items()})
+    view, proj, campos, tfx, tfy = camera.raster_matrices(data)
+    kw = dict(image_height=img, image_width=img, tanfovx=tfx, tanfovy=tfy, viewmatrix=view, projmatrix=proj, bg=torch.zeros(3))
+    t = [v.detach().clone().requires_grad_(True) for v in (gs.positions, gs.colors, gs.opacities, gs.scales, gs.quaternions)]
+    N = t[0].shape[0]
+    m2 = torch.zeros(N, 3, device=dev, requires_grad=True)
+    states = []
+    color, radii, depth, alpha = ops.rasterize(t[0], m2, t[1], t[2], t[3], t[4], state_out=states, **kw)
+    P = int(states[0].status.cpu().numpy()[1])
+    gc = torch.randn_like(color)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, n=5):
+        best = []
+        for _ in range(n):
+            flush.zero_()                                  # L2 flush between timed iterations
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            best.append(a.elapsed_time(b))
+        return float(np.median(best))
+
+    def fwd():
+        with torch.no_grad():
+            ops.rasterize(t[0], m2, t[1], t[2], t[3], t[4], **kw)
+
+    def fwdbwd():
+        c, _, _, _ = ops.rasterize(t[0], m2, t[1], t[2], t[3], t[4], **kw)
+        torch.autograd.backward([c], [gc])
+    for _ in range(3):
+        fwdbwd()
+    ms_f, ms_fb = timed(fwd), timed(fwdbwd)
+    HW = img * img
+    bytes_f = 56 * N + 68 * P + 28 * HW
+    bytes_b = 44 * P + 32 * HW + 124 * N
+    ach = (bytes_f + bytes_b) / (ms_fb * 1e-3) / 1e9
+    return {'bound': 'hbm', 'kernel': 'dwg_raster_forward + dwg_raster_backward (preprocess, bin, sort, pack, render fwd/bwd, preprocess bwd)',
+            'achieved': round(ach, 1), 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm_gbs'], 4), 'traffic': None,
+            'algorithmic_MB': round((bytes_f + bytes_b) / 1e6, 2), 'ms_fwd': round(ms_f, 4), 'ms_fwd_bwd': round(ms_fb, 4),
+            'instances_P': P, 'gaussians': int(N), 'peak_source': pk_src + ' hbm_gbs',
+            'note': 'latency / load-balance bound: ~60 MB of compulsory traffic is ~10 us of HBM time; the stage is 14 launches and the '
+                    'heaviest 16x16 tiles hold thousands of depth-ordered instances (DESIGN.md section 4)'}
 
 
 # ----------------------------------------------------------------------------------------- CPU arm

@@ -24,9 +24,11 @@ __device__ __forceinline__ bf8 pack8(const float f[8]) {
     for (int i = 0; i < 4; i++) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return p;
 }
-// fast-division forms (MUFU.RCP + FMUL, ~2 ulp): these kernels are issue-bound on the big VAE tensors
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float silu_grad(float x) { const float s = __fdividef(1.0f, 1.0f + __expf(-x)); return s * fmaf(x, 1.0f - s, 1.0f); }
+// These kernels are issue-bound on the big VAE tensors: sigmoid(x) = 0.5 + 0.5 tanh(x/2) costs ONE MUFU op
+// (tanh.approx.f32, max rel err 2^-11, below the bf16 rounding of every result) instead of exp + reciprocal.
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float silu(float x) { const float h = 0.5f * x; return fmaf(h, tanh_fast(h), h); }
+__device__ __forceinline__ float silu_grad(float x) { const float s = fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); return s * fmaf(x, 1.0f - s, 1.0f); }
 
 // ---------------------------------------------------------------------------- GroupNorm
 // x [N, HW, C] bf16, C % 8 == 0, (C/G) % 8 == 0 or 8 % (C/G) == 0 handled generically via smem bins.
@@ -151,6 +153,119 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
             yp[(size_t)r * c8 + cv] = pack8(f);
         }
     }
+}
+
+// One-launch GroupNorm (+SiLU) for tensors that fit the shared memory of one cluster per (image, 4-group slab)
+// -- every GroupNorm of the UNet / ControlNet at batch 2.  A cluster of GN_CS CTAs owns one image and a slab of
+// 4 consecutive groups (4*cpg channels, always a multiple of 8); CTA r of the cluster takes the r-th share of the
+// pixels: (1) load its [rows x slab] block once into shared memory while accumulating per-group sum / sumsq,
+// (2) exchange the 8 partial sums through distributed shared memory (barrier.cluster + ld.shared::cluster),
+// (3) normalise (+SiLU) from shared memory and store.  One read and one write of the tensor, one launch, no
+// global atomics, no memset -- against stats kernel + memset + apply kernel (two reads, three launches).
+constexpr int GN_CS = 8;
+__device__ __forceinline__ float ld_dsmem_f32(const float* p, uint32_t rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_sync_gn() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(256)
+gn_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __nv_bfloat16* __restrict__ y, float* __restrict__ stats_out, int HW, int C, int G, float eps, int do_silu,
+                int rows_per_cta) {
+    extern __shared__ __align__(16) uint8_t gsm[];
+    __shared__ float s_part[8];          // this CTA's (sum, sumsq) of the slab's 4 groups
+    __shared__ float s_ab[2 * 4];        // (mean, rstd) of the 4 groups
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int slab = blockIdx.y, n = blockIdx.z;
+    const int cpg = C / G, c8 = C / 8;
+    const int sc8 = (4 * cpg) / 8;                           // 16-byte vectors per pixel in the slab
+    const int cv0 = slab * sc8;                              // first vector column of the slab
+    const int row0 = (int)rank * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
+    const int nvec = max(0, row1 - row0) * sc8;
+    if (threadIdx.x < 8) s_part[threadIdx.x] = 0.f;
+    pdl_wait();
+    pdl_trigger();
+    __syncthreads();
+    const bf8* xp = reinterpret_cast<const bf8*>(x + (size_t)n * HW * C);
+    bf8* sv = reinterpret_cast<bf8*>(gsm);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < nvec; i += 256) {
+        const int r = i / sc8, cv = i - r * sc8;
+        const bf8 v = xp[(size_t)(row0 + r) * c8 + cv0 + cv];
+        sv[i] = v;
+        float f[8];
+        unpack8(v, f);
+        if (cpg % 8 == 0) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { a += f[k]; b = fmaf(f[k], f[k], b); }
+            const int g = (cv * 8) / cpg;
+#pragma unroll
+            for (int q = 0; q < 4; q++) if (g == q) { s[q] += a; ss[q] += b; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int g = (cv * 8 + k) / cpg;
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (g == q) { s[q] += f[k]; ss[q] = fmaf(f[k], f[k], ss[q]); }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        float a = s[q], b = ss[q];
+        for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_part[2 * q], a); atomicAdd(&s_part[2 * q + 1], b); }
+    }
+    __syncthreads();
+    cluster_sync_gn();                                       // every CTA's partials are complete and visible cluster-wide
+    if (threadIdx.x < 8) {
+        float tot = 0.f;
+#pragma unroll
+        for (uint32_t r = 0; r < (uint32_t)GN_CS; r++) tot += ld_dsmem_f32(&s_part[threadIdx.x], r);
+        if (stats_out && rank == 0) stats_out[((size_t)n * G + slab * 4) * 2 + threadIdx.x] = tot;
+        s_ab[threadIdx.x] = tot;
+    }
+    __syncthreads();
+    // per-channel scale / shift of the slab -> shared memory (behind the data block)
+    float* s_a = reinterpret_cast<float*>(gsm + (((size_t)rows_per_cta * sc8 * 16 + 15) & ~(size_t)15));
+    float* s_b = s_a + 4 * cpg;
+    const int c_slab0 = slab * 4 * cpg;
+    {
+        const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+        for (int cl = threadIdx.x; cl < 4 * cpg; cl += 256) {
+            const int g = cl / cpg;
+            const float mean = s_ab[2 * g] * inv_cnt;
+            const float var = fmaxf(s_ab[2 * g + 1] * inv_cnt - mean * mean, 0.f);
+            const float a = rsqrtf(var + eps) * gamma[c_slab0 + cl];
+            s_a[cl] = a;
+            s_b[cl] = beta[c_slab0 + cl] - mean * a;
+        }
+    }
+    __syncthreads();
+    bf8* yp = reinterpret_cast<bf8*>(y + (size_t)n * HW * C);
+    for (int i = threadIdx.x; i < nvec; i += 256) {
+        const int r = i / sc8, cv = i - r * sc8;
+        float f[8];
+        unpack8(sv[i], f);
+        const float4 a0 = *reinterpret_cast<const float4*>(s_a + cv * 8), a1 = *reinterpret_cast<const float4*>(s_a + cv * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_b + cv * 8), b1 = *reinterpret_cast<const float4*>(s_b + cv * 8 + 4);
+        const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float o = fmaf(f[k], aa[k], bb[k]);
+            f[k] = do_silu ? silu(o) : o;
+        }
+        yp[(size_t)(row0 + r) * c8 + cv0 + cv] = pack8(f);
+    }
+    cluster_sync_gn();                                       // peers may still be reading this CTA's partials
 }
 
 // Backward of y = act(GN(x)).  Both passes use the forward's work split (thread -> row lane x fixed
@@ -534,12 +649,41 @@ using namespace dwg::nn;
 typedef __nv_bfloat16 bf16;
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static int g_gn_last_launches = 2;
+/* kernels the last dwg_groupnorm_fwd call launched: 1 (one-launch cluster kernel) or 2 (stats + apply) */
+extern "C" int dwg_groupnorm_last_launches(void) { return g_gn_last_launches; }
 
 extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
                                  int N, int HW, int C, int G, float eps, int do_silu, void* stream) {
     DWG_REQUIRE(x && gamma && beta && y && stats, "null pointer");
     DWG_REQUIRE(C % 8 == 0 && C % G == 0 && al16(x) && al16(y), "C must be a multiple of 8 and of G; 16-byte aligned tensors");
     cudaStream_t st = (cudaStream_t)stream;
+    // one-launch cluster kernel when the (image, 4-group slab) block fits the shared memory of 8 CTAs
+    {
+        const int cpg = C / G;
+        const int rows_c = (HW + GN_CS - 1) / GN_CS;
+        const size_t smem = (((size_t)rows_c * (size_t)(4 * cpg) * 2 + 15) & ~(size_t)15) + (size_t)(8 * cpg) * 4;
+        static int fused_ok = -1;
+        if (fused_ok < 0) {
+            const char* e = getenv("DWG_GN_FUSED");
+            fused_ok = (e && e[0] == '0') ? 0 : 1;
+            if (fused_ok) cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        }
+        if (fused_ok && (G % 4) == 0 && ((4 * cpg) % 8) == 0 && smem <= 200 * 1024 && (int64_t)N * (G / 4) * GN_CS <= 4 * kNumSMs) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(GN_CS, G / 4, N); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = GN_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+            cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const bf16*)x, gamma, beta, (bf16*)y, stats, HW, C, G, eps, do_silu, rows_c);
+            g_gn_last_launches = 1;
+            return check_launch("dwg_groupnorm_fwd (fused)");
+        }
+    }
+    g_gn_last_launches = 2;
     cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, st);
     const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;        // row lanes per CTA
     int rows_per_cta = (int)(((int64_t)N * HW + 4 * kNumSMs - 1) / (4 * kNumSMs));      // ~4 CTAs per SM

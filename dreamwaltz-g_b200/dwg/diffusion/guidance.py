@@ -53,6 +53,7 @@ class ControlNetScoreDistillation:
         self.timestep = None
         self.two_streams = True                 # ControlNet beside the UNet encoder (_controlnet_unet)
         self._side = None
+        self._prepared = None                   # results of prepare() waiting for the next __call__
 
     # ---- CUDA graphs: the diffusion blocks have static shapes; one capture each for
     # ControlNet+UNet, VAE forward and VAE backward removes ~1500 launches of host overhead per step
@@ -130,6 +131,30 @@ class ControlNetScoreDistillation:
             return self._replay('predict')
         return self._controlnet_unet(latents_model_input, text_embeddings, cond)
 
+    @torch.no_grad()
+    def prepare(self, text_embeds_dict, cond_inputs, batch_size=1, timestep=None, use_negative_text=True):
+        """Optional head start (not part of the reference surface): everything of the step that does not depend on
+        the rendered image -- the timestep draw, both networks' time-embedding projections and cross-attention
+        K / V, the ControlNet condition embedding -- is enqueued on the second stream, to run while the caller
+        animates and rasterises the avatar.  The next __call__ consumes it (same timestep semantics)."""
+        if not self.two_streams:
+            return
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        t = timestep if timestep is not None else self.get_timestep(batch_size)
+        neg = text_embeds_dict['neg' if use_negative_text else 'null']
+        ctx = torch.cat([neg, text_embeds_dict['text']], dim=0)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            ops.gemm_lane(1)
+            try:
+                pre_c = self.controlnet.prepare(t, ctx, ctx.shape[0], cond_inputs)
+                pre_u = self.unet.prepare(t, ctx, ctx.shape[0])
+            finally:
+                ops.gemm_lane(0)
+        self._prepared = {'t': t, 'ctx': ctx, 'controlnet': pre_c, 'unet': pre_u}
+
     def _controlnet_unet(self, x2, ctx, cond):
         """ControlNet and the UNet encoder + mid block are independent until the residuals are added
         (controlnet.py:98-114 / diffusers): the ControlNet is enqueued on a second stream (its own
@@ -142,14 +167,24 @@ class ControlNetScoreDistillation:
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
         side = self._side
+        prep, self._prepared = self._prepared, None
+        pre_c = prep['controlnet'] if prep else None
+        pre_u = prep['unet'] if prep else None
+        if prep:
+            main.wait_stream(side)              # the UNet encoder (this stream) reads the prepared tensors
+            for d in (pre_c, pre_u):
+                for v in d.values():
+                    for tns in (v.values() if isinstance(v, dict) else [v]):
+                        for x in (tns if isinstance(tns, tuple) else [tns]):
+                            x.record_stream(main)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             ops.gemm_lane(1)
             try:
-                down, mid = self.controlnet.forward(x2, self.timestep, ctx, cond, self.conditioning_scale)
+                down, mid = self.controlnet.forward(x2, self.timestep, ctx, cond, self.conditioning_scale, pre=pre_c)
             finally:
                 ops.gemm_lane(0)
-        state = self.unet.encode(x2, self.timestep, ctx)
+        state = self.unet.encode(x2, self.timestep, ctx, pre=pre_u)
         main.wait_stream(side)
         for r in down + [mid]:
             r.record_stream(main)
@@ -169,7 +204,11 @@ class ControlNetScoreDistillation:
         Returns the reference's dict: latents, timestep, sources, targets, gradients, diffusion_loss."""
         assert inputs.shape[1] == 3 and inputs.shape[-2:] == (self.default_image_size, self.default_image_size) or True
         latents = self.encode_images(inputs, vae_eps)
-        self.timestep = timestep if timestep is not None else self.get_timestep(inputs.shape[0])
+        if self._prepared is not None and timestep is None:
+            self.timestep = self._prepared['t']                 # drawn by prepare()
+        else:
+            self._prepared = None
+            self.timestep = timestep if timestep is not None else self.get_timestep(inputs.shape[0])
         with torch.no_grad():
             if noise is None:
                 noise = torch.randn(latents.shape, device=latents.device, generator=None if self.use_default_generator else self.gen)

@@ -97,11 +97,19 @@ def attention(W, p, x, ctx, heads, residual, kv=None):
     Tk = ctx.shape[1]
     hd = C // heads
     Tkp = (Tk + 7) // 8 * 8
-    q3 = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_q'], bias=W.b.get(p + '.to_q')).view(B, T, C)
+    k3 = None
+    if kv is None and ctx is x and (p + '.to_qk') in W.w:
+        # self-attention: Q and K projections of the same input as ONE GEMM (weights concatenated at load time);
+        # the attention kernel takes the two halves as strided views
+        qk = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_qk']).view(B, T, 2 * C)
+        q3, k3 = qk[:, :, :C], qk[:, :, C:]
+    else:
+        q3 = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_q'], bias=W.b.get(p + '.to_q')).view(B, T, C)
     if kv is not None:
         k3, vT = kv
     else:
-        k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
+        if k3 is None:
+            k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
         vT = torch.zeros(B, C, Tkp, device=x.device, dtype=BF) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=BF)
         for b in range(B):
             ops.gemm(W.w[p + '.to_v'], ctx[b], out=vT[b][:, :Tk] if Tkp != Tk else vT[b])
@@ -148,6 +156,10 @@ class DiffusionNet:
             offs[n] = (o, o + c)
             o += c
         self._xattn_off, self._xattn_total = offs, o
+        # self-attention Q | K projection weights concatenated (bias-free in the public SD architectures)
+        for n in sorted(n[:-len('.to_q')] for n in self.W.w if n.endswith('.attn1.to_q')):
+            if (n + '.to_q') not in self.W.b and (n + '.to_k') not in self.W.b:
+                self.W.w[n + '.to_qk'] = torch.cat([self.W.w[n + '.to_q'], self.W.w[n + '.to_k']], dim=0).contiguous()
 
     def project_context(self, ctx):
         """ctx [B,Tk,Ck] -> {attn2 prefix: (K [B,Tk,C] view, V^T [B,C,Tkp] view)}."""
@@ -174,6 +186,13 @@ class DiffusionNet:
         temb = linear(W, 'time_embedding.linear_2', e)
         tp = ops.gemm(ops.silu(temb), self._tproj_w, bias=self._tproj_b, out_dtype=torch.float32)[:B]      # [B, sum Cout]
         return {n: tp[:, a:b].contiguous() for n, (a, b) in self._tproj_off.items()}
+
+    @torch.no_grad()
+    def prepare(self, t, ctx, B):
+        """Everything that depends only on the timestep and the prompt embeddings (time-embedding projections of
+        every resnet, K / V^T of every cross-attention): can be computed while the avatar is still being rendered."""
+        ctx = ctx.to(BF).contiguous()
+        return {'tproj': self.time_embed(t, B), 'ctx': ctx, 'ctx_kv': self.project_context(ctx)}
 
     def resnet(self, p, x, tproj):
         W, G = self.W, self.G
@@ -224,26 +243,38 @@ def to_nhwc_bf16(x_nchw):
 
 class ControlNet(DiffusionNet):
     @torch.no_grad()
-    def forward(self, sample_nchw, t, ctx, cond_nchw01, conditioning_scale=1.0):
-        """-> (list of 12 down residuals, mid residual), NHWC bf16."""
+    def embed_condition(self, cond_nchw01):
+        """controlnet_cond_embedding of the condition image(s) -> [Bc,h,w,C0] (before the residual add)."""
         W = self.W
-        B = sample_nchw.shape[0]
-        tproj = self.time_embed(t, B)
-        ctx = ctx.to(BF).contiguous()
-        self._ctx_kv = self.project_context(ctx)
-        h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
-        # condition embedding: with classifier-free guidance the reference feeds the SAME condition image
-        # for every sample (controlnet.py:33-55 prepare_image duplicates it); a batch-1 condition is
-        # embedded once and added to every sample
         c = ops.silu(conv(W, 'controlnet_cond_embedding.conv_in', to_nhwc_bf16(cond_nchw01)))
         nblk = 2 * (len(self.cfg['cond_embed']) - 1)
         for k in range(nblk):
             c = ops.silu(conv(W, f'controlnet_cond_embedding.blocks.{k}', c, stride=2 if k % 2 == 1 else 1))
-        if c.shape[0] == B:
-            h = conv(W, 'controlnet_cond_embedding.conv_out', c, residual=h)
-        else:
-            assert c.shape[0] == 1, 'condition batch must be 1 or the sample batch'
-            h = h + conv(W, 'controlnet_cond_embedding.conv_out', c)
+        return conv(W, 'controlnet_cond_embedding.conv_out', c)
+
+    @torch.no_grad()
+    def prepare(self, t, ctx, B, cond_nchw01=None):
+        pre = super().prepare(t, ctx, B)
+        if cond_nchw01 is not None:
+            pre['cond_emb'] = self.embed_condition(cond_nchw01)
+        return pre
+
+    @torch.no_grad()
+    def forward(self, sample_nchw, t, ctx, cond_nchw01, conditioning_scale=1.0, pre=None):
+        """-> (list of 12 down residuals, mid residual), NHWC bf16.  ``pre`` = prepare(...) results computed earlier."""
+        W = self.W
+        B = sample_nchw.shape[0]
+        if pre is None:
+            pre = self.prepare(t, ctx, B, cond_nchw01)
+        tproj, ctx = pre['tproj'], pre['ctx']
+        self._ctx_kv = pre['ctx_kv']
+        h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
+        # condition embedding: with classifier-free guidance the reference feeds the SAME condition image
+        # for every sample (controlnet.py:33-55 prepare_image duplicates it); a batch-1 condition is
+        # embedded once and added to every sample
+        c = pre['cond_emb'] if 'cond_emb' in pre else self.embed_condition(cond_nchw01)
+        assert c.shape[0] in (1, B), 'condition batch must be 1 or the sample batch'
+        h = ops.add(h, c) if c.shape[0] == B else h + c
         h, skips = self.down_path(h, tproj, ctx)
         h = self.mid(h, tproj, ctx)
         down = [conv(W, f'controlnet_down_blocks.{i}', s, padding=0) for i, s in enumerate(skips)]
@@ -256,20 +287,21 @@ class ControlNet(DiffusionNet):
 
 class UNet(DiffusionNet):
     @torch.no_grad()
-    def forward(self, sample_nchw, t, ctx, down_residuals=None, mid_residual=None):
+    def forward(self, sample_nchw, t, ctx, down_residuals=None, mid_residual=None, pre=None):
         """-> eps [B,out_ch,H,W] fp32 (NCHW, the reference layout)."""
-        return self.decode(self.encode(sample_nchw, t, ctx), down_residuals, mid_residual)
+        return self.decode(self.encode(sample_nchw, t, ctx, pre), down_residuals, mid_residual)
 
     @torch.no_grad()
-    def encode(self, sample_nchw, t, ctx):
+    def encode(self, sample_nchw, t, ctx, pre=None):
         """conv_in + down blocks + mid block: everything that does not need the ControlNet residuals
         (diffusers adds them to the skip list / the mid output afterwards), so it can run beside the
         ControlNet on another stream (guidance._predict)."""
         W = self.W
         B = sample_nchw.shape[0]
-        tproj = self.time_embed(t, B)
-        ctx = ctx.to(BF).contiguous()
-        self._ctx_kv = self.project_context(ctx)
+        if pre is None:
+            pre = self.prepare(t, ctx, B)
+        tproj, ctx = pre['tproj'], pre['ctx']
+        self._ctx_kv = pre['ctx_kv']
         h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
         h, skips = self.down_path(h, tproj, ctx)
         h = self.mid(h, tproj, ctx)

@@ -354,12 +354,13 @@ def rasterize(means3D, means2D, colors, opacities, scales, rotations, *, image_h
 # ------------------------------------------------------------------------------ tensor-core GEMM / conv
 ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3}
 PROFILE = None        # set to a list to record (start_event, end_event, flops, kind) per tensor-core launch
+PROFILE_BYTES = 0.0   # running sum of the compulsory operand bytes (A + B + C [+ residual], each once) of the recorded launches
 TUNE_RECORD = None    # set to a list to record the arguments of every GEMM / conv call (tools/gemm_autotune.py)
 
 
 class _prof:
-    def __init__(self, flops, kind):
-        self.flops, self.kind = flops, kind
+    def __init__(self, flops, kind, nbytes=0.0):
+        self.flops, self.kind, self.nbytes = flops, kind, nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -370,6 +371,8 @@ class _prof:
         if PROFILE is not None:
             self.e1.record()
             PROFILE.append((self.e0, self.e1, self.flops, self.kind))
+            global PROFILE_BYTES
+            PROFILE_BYTES += self.nbytes
 
 
 def gemm_lane(lane):
@@ -413,7 +416,8 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
     bias2 = None if bias2 is None else f32c(bias2)
     if TUNE_RECORD is not None:
         TUNE_RECORD.append(('gemm', M, N, K, nb1, nb2, act, residual is not None, c4.dtype, bias is not None, bias2 is not None))
-    with _prof(2.0 * M * N * K * nb1 * nb2, f'gemm M{M} N{N} K{K} b{nb1 * nb2}'):
+    nbytes = nb1 * nb2 * (2.0 * (M * K + N * K) + M * No * (c4.element_size() + (2 if r4 is not None else 0)))
+    with _prof(2.0 * M * N * K * nb1 * nb2, f'gemm M{M} N{N} K{K} b{nb1 * nb2}', nbytes):
         check(lib().dwg_gemm_bf16(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
                                   b4.data_ptr(), b4.stride(2), b4.stride(1), b4.stride(0),
                                   c4.data_ptr(), c4.stride(2), c4.stride(1), c4.stride(0), int(c4.dtype == torch.bfloat16),
@@ -446,7 +450,8 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
     bias2 = None if bias2 is None else f32c(bias2)
     if TUNE_RECORD is not None:
         TUNE_RECORD.append(('conv', Nimg, H, W, Cin, Cout, k, stride, ph, pw, Ho, Wo, residual is not None, out_dtype, bias2 is not None))
-    with _prof(2.0 * Nimg * Ho * Wo * Cout * Cin * k * k, f'conv{k}x{k}s{stride} {Nimg}x{Ho}x{Wo} {Cin}->{Cout}'):
+    nbytes = 2.0 * (x.numel() + w.numel()) + y.numel() * (y.element_size() + (2 if residual is not None else 0))
+    with _prof(2.0 * Nimg * Ho * Wo * Cout * Cin * k * k, f'conv{k}x{k}s{stride} {Nimg}x{Ho}x{Wo} {Cin}->{Cout}', nbytes):
         check(lib().dwg_conv2d_nhwc_bf16(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.bfloat16), Nimg, H, W, Cin, Cout, k,
                                          stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], stream()),
               'dwg_conv2d_nhwc_bf16')
@@ -462,8 +467,10 @@ def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, return_stats=Fal
     HW = x.numel() // (N * C)
     y = torch.empty_like(x)
     stats = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
-    check(lib().dwg_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), N, HW, C, groups, float(eps), int(silu),
-                                  stream()), 'dwg_groupnorm_fwd')
+    L = lib()
+    check(L.dwg_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), N, HW, C, groups, float(eps), int(silu),
+                              stream()), 'dwg_groupnorm_fwd')
+    object.__setattr__(L, 'launches', L.launches + L.dwg_groupnorm_last_launches() - 2)      # the proxy counted 2
     return (y, stats) if return_stats else y
 
 

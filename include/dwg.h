@@ -228,6 +228,9 @@ int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int out_bf16,
 /* y = [SiLU](GroupNorm_G(x));  x,y [N,HW,C] bf16; stats [N,G,2] fp32 workspace (sum, sumsq), kept for bwd */
 int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
                       int N, int HW, int C, int G, float eps, int do_silu, void* stream);
+/* kernels launched by the last dwg_groupnorm_fwd: 1 = one-launch cluster kernel (tensor fits the shared memory of 8 CTAs
+ * per (image, 4-group slab): every UNet / ControlNet norm at batch 2), 2 = statistics + apply passes. */
+int dwg_groupnorm_last_launches(void);
 /* dx = d/dx [SiLU](GroupNorm(x)) . dy  (+ dx_add if given);  bstats [N,G,2] fp32 workspace */
 int dwg_groupnorm_bwd(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta,
                       const void* dx_add, void* dx, float* bstats, int N, int HW, int C, int G, float eps,

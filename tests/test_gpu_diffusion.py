@@ -131,3 +131,50 @@ def test_sds_step_matches_oracle_and_specify_gradient():
     gr, npd = ops.sds_grad(eu, ec, nz, 50.0, 1.0)
     torch.testing.assert_close(npd, eu + 50.0 * (ec - eu), rtol=1e-6, atol=1e-5)
     torch.testing.assert_close(gr, npd - nz, rtol=1e-6, atol=1e-5)
+
+
+def test_prepare_head_start_and_two_streams_change_nothing():
+    """guidance.prepare() (timestep / prompt / condition work enqueued early on the second stream) and the
+    ControlNet-beside-UNet-encoder schedule are pure scheduling: same numbers as the single-stream path."""
+    cfg, u_sd, c_sd, v_sd = _tiny()
+    torch.manual_seed(5)
+    img = torch.rand(1, 3, 128, 128, device=DEV)
+    cond = torch.rand(1, 3, 128, 128, device=DEV)
+    emb = {'neg': torch.randn(1, 77, cfg['ctx_dim'], device=DEV), 'text': torch.randn(1, 77, cfg['ctx_dim'], device=DEV)}
+    t = torch.tensor([431], device=DEV)
+    noise, veps = torch.randn(1, 4, 16, 16, device=DEV), torch.randn(1, 4, 16, 16, device=DEV)
+    outs = []
+    for mode in ('single', 'two_streams', 'prepared'):
+        g = G.ControlNetScoreDistillation(u_sd, c_sd, v_sd, cfg, W.TINY_VAE, DEV, guidance_scale=7.5)
+        g.two_streams = mode != 'single'
+        x = img.clone().requires_grad_(True)
+        if mode == 'prepared':
+            g.prepare(emb, cond, timestep=t)
+            out = g(x, emb, cond_inputs=cond, noise=noise, vae_eps=veps)          # timestep comes from prepare()
+            assert int(out['timestep'][0]) == 431 and g._prepared is None
+        else:
+            out = g(x, emb, cond_inputs=cond, timestep=t, noise=noise, vae_eps=veps)
+        out['diffusion_loss'].backward()
+        torch.cuda.synchronize()
+        outs.append((out['noise_pred'].clone(), x.grad.clone()))
+    # identical kernels and operands; only the split-K atomics may round in a different order
+    for npd, gr in outs[1:]:
+        assert rel_l2(npd, outs[0][0].cpu()) < 2e-3 and rel_l2(gr, outs[0][1].cpu()) < 2e-3
+
+
+@pytest.mark.parametrize('N,H,W,C', [(2, 64, 64, 320), (2, 8, 8, 1280), (2, 32, 32, 960), (2, 16, 16, 2560), (1, 64, 64, 512),
+                                     (2, 8, 4, 128), (2, 128, 128, 128)])
+def test_group_norm_one_launch_cluster_path_vs_torch(N, H, W, C):
+    """UNet / ControlNet-sized tensors take the one-launch cluster kernel (DSMEM exchange of the partial sums); big tensors
+    (last case) the two-pass kernels.  Both return the same raw (sum, sumsq) statistics the backward consumes."""
+    torch.manual_seed(1)
+    x = (torch.randn(N, H, W, C, device=DEV) * 1.7 + 0.3).bfloat16()
+    g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
+    ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, g, b, 1e-6)
+    for silu in (False, True):
+        y, st = ops.group_norm(x, g, b, 32, 1e-6, silu=silu, return_stats=True)
+        r = torch.nn.functional.silu(ref) if silu else ref
+        assert rel_l2(y.permute(0, 3, 1, 2), r.cpu()) < 1e-2
+    xs = x.float().view(N, H * W, 32, C // 32)
+    st_ref = torch.stack([xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))], dim=-1)          # [N, 32, 2]
+    torch.testing.assert_close(st.view(N, 32, 2).cpu(), st_ref.cpu(), rtol=2e-4, atol=1e-2)

@@ -8,7 +8,7 @@ TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
 NCU="ncu --clock-control none"
-timeout 420 $NCU --metrics gpu__time_duration.sum -c 40000 --csv --log-file $OUT/${TAG}_launches_bench.csv \
+timeout 600 $NCU --metrics gpu__time_duration.sum -c 60000 --csv --log-file $OUT/${TAG}_launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --skip-cpu-baseline > $OUT/${TAG}_bench_under_ncu.log 2>&1
 echo "launch list rc=$?"
 for spec in "gemm:gemm_kernel:9" "gemm:fa_fwd:2" "geom:render_:4" "geom:preprocess_kernel|run_sort|scatter_kernel|pack_kernel|lbs_skin|grid_:12" "nn:gn_|layernorm:8"; do
@@ -18,4 +18,8 @@ for spec in "gemm:gemm_kernel:9" "gemm:fa_fwd:2" "geom:render_:4" "geom:preproce
         python tools/ncu_targets.py $part > $OUT/${TAG}_${name}.log 2>&1
     echo "$pat rc=$?"
 done
+# 3. DRAM traffic + duration of every tensor-core launch of ONE guidance pass (un-graphed, profiler-bracketed)
+timeout 400 $NCU --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+    -k "regex:gemm_kernel|fa_fwd" --csv --log-file $OUT/${TAG}_gemm_traffic.csv python tools/gemm_pass.py > $OUT/${TAG}_gemm_pass.log 2>&1
+echo "gemm traffic rc=$?"
 ls -la $OUT/*.ncu-rep

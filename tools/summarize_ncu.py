@@ -108,8 +108,43 @@ def launch_list(tag):
     print('wrote', out, len(launches), 'launches')
 
 
+def gemm_traffic(tag):
+    """Per-launch DRAM bytes / duration of the tensor-core launches of one guidance pass -> profiles/<tag>_gemm_traffic.json"""
+    import json
+    path = os.path.join(OUT, f'{tag}_gemm_traffic.csv')
+    if not os.path.exists(path):
+        return
+    text = open(path).read()
+    rows = list(csv.reader(io.StringIO(text[text.find('"ID"'):])))
+    col = {h: i for i, h in enumerate(rows[0])}
+    per = collections.defaultdict(dict)
+    for r in rows[1:]:
+        if len(r) <= col['Metric Value']:
+            continue
+        try:
+            v = float(r[col['Metric Value']].replace(',', '')) * SCALE.get(r[col['Metric Unit']], 1.0)
+        except ValueError:
+            continue
+        per[r[col['ID']]]['kernel'] = short(r[col['Kernel Name']])
+        per[r[col['ID']]][r[col['Metric Name']]] = v
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for d in per.values():
+        a = agg['attention' if 'fa_fwd' in d['kernel'] else 'gemm']
+        a[0] += 1
+        a[1] += d.get('dram__bytes_read.sum', 0.0) + d.get('dram__bytes_write.sum', 0.0)
+        a[2] += d.get('gpu__time_duration.sum', 0.0)
+    out = {k: {'launches': n, 'dram_bytes_total': b, 'dram_bytes_per_launch': b / max(n, 1), 'duration_us_total_under_ncu': t}
+           for k, (n, b, t) in agg.items()}
+    out['how'] = ('ncu --profile-from-start off --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum '
+                  '-k regex:gemm_kernel|fa_fwd python tools/gemm_pass.py (one un-graphed guidance pass, serialised launches)')
+    dst = os.path.join(PROF, f'{tag}_gemm_traffic.json')
+    json.dump(out, open(dst, 'w'), indent=1)
+    print('wrote', dst, {k: v['launches'] for k, v in out.items() if isinstance(v, dict)})
+
+
 if __name__ == '__main__':
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r1b'
     os.makedirs(PROF, exist_ok=True)
     launch_list(tag)
     full_reports(tag)
+    gemm_traffic(tag)
