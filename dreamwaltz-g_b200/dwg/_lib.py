@@ -65,6 +65,7 @@ SIGNATURES = {
     'dwg_conv2d_nhwc_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 11 +
                              [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'dwg_groupnorm_last_launches': (c_int, []),
+    'dwg_groupnorm_set_fused': (c_int, [c_int]),
     'dwg_groupnorm_fwd': (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     'dwg_groupnorm_bwd': (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     'dwg_layernorm_fwd': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),

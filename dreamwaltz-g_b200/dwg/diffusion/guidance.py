@@ -7,6 +7,8 @@ core/guidance/controlnet.py:83-114 (_predict) for the shipped configuration: los
 [0.02, 0.98] * 1000, ControlNet conditioning scale 1.  No host synchronisation: the timestep
 stays on the device.
 """
+import os
+
 import torch
 
 from .. import ops
@@ -137,7 +139,7 @@ class ControlNetScoreDistillation:
         the rendered image -- the timestep draw, both networks' time-embedding projections and cross-attention
         K / V, the ControlNet condition embedding -- is enqueued on the second stream, to run while the caller
         animates and rasterises the avatar.  The next __call__ consumes it (same timestep semantics)."""
-        if not self.two_streams:
+        if not self.two_streams or os.environ.get('DWG_NO_PREPARE') == '1':
             return
         main = torch.cuda.current_stream()
         if self._side is None:

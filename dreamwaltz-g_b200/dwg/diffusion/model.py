@@ -10,6 +10,7 @@ The public architectures (diffusers; reference call sites core/guidance/controln
 core/guidance/vae.py:34-40) are consumed as diffusers-format state dicts (weights.py).
 """
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -158,7 +159,7 @@ class DiffusionNet:
         self._xattn_off, self._xattn_total = offs, o
         # self-attention Q | K projection weights concatenated (bias-free in the public SD architectures)
         for n in sorted(n[:-len('.to_q')] for n in self.W.w if n.endswith('.attn1.to_q')):
-            if (n + '.to_q') not in self.W.b and (n + '.to_k') not in self.W.b:
+            if (n + '.to_q') not in self.W.b and (n + '.to_k') not in self.W.b and os.environ.get('DWG_NO_QK') != '1':
                 self.W.w[n + '.to_qk'] = torch.cat([self.W.w[n + '.to_q'], self.W.w[n + '.to_k']], dim=0).contiguous()
 
     def project_context(self, ctx):

@@ -231,6 +231,8 @@ int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void
 /* kernels launched by the last dwg_groupnorm_fwd: 1 = one-launch cluster kernel (tensor fits the shared memory of 8 CTAs
  * per (image, 4-group slab): every UNet / ControlNet norm at batch 2), 2 = statistics + apply passes. */
 int dwg_groupnorm_last_launches(void);
+/* enable (1) / disable (0, default: measured slower inside the step) the one-launch cluster kernel */
+int dwg_groupnorm_set_fused(int on);
 /* dx = d/dx [SiLU](GroupNorm(x)) . dy  (+ dx_add if given);  bstats [N,G,2] fp32 workspace */
 int dwg_groupnorm_bwd(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta,
                       const void* dx_add, void* dx, float* bstats, int N, int HW, int C, int G, float eps,
