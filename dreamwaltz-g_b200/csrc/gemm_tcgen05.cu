@@ -460,11 +460,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const uint32_t kh = (uint32_t)tap / 3u, kw = (uint32_t)tap % 3u;
                             const uint64_t da = make_desc_halo(smem_u32(sA + sa * HALO_BYTES) + kh * HALO_LINE_BYTES + kw * 128u, p.halo_bo ? kw : 0u);
                             const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES));
+                            const int nk = min(BK / UMMA_K, (p.K - kc * BK + UMMA_K - 1) / UMMA_K);
 #pragma unroll
                             for (int k = 0; k < BK / UMMA_K; k++) {
                                 const uint32_t acc = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
-                                if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc);
-                                else tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc);
+                                if (k < nk) {
+                                    if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc);
+                                    else tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc);
+                                }
                             }
                             if (PAIR) tc_commit_pair(&empty[s]); else tc_commit(&empty[s]);
                             if (tap == 8) { if (PAIR) tc_commit_pair(&emptyA[sa]); else tc_commit(&emptyA[sa]); }
@@ -487,10 +490,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (tl == 0 && it == it0) TRACE(3);
                     const uint64_t da = make_desc(smem_u32(sA + s * A_BYTES));
                     const uint64_t db = make_desc(smem_u32(sB + s * B_BYTES));
+                    // K = 16 steps of this 64-wide chunk that hold real data (the rest is TMA zero-fill: K tails, 8/16-channel convs)
+                    const int nk = min(BK / UMMA_K, (p.K - (it % p.k_chunks) * BK + UMMA_K - 1) / UMMA_K);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
-                        if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
-                        else tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        if (k < nk) {
+                            if (PAIR) tc_mma_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
+                            else tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     if (PAIR) tc_commit_pair(&empty[s]); else tc_commit(&empty[s]);
                     if (it == it1 - 1) {

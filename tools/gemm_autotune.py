@@ -142,7 +142,7 @@ def main():
         cands = [(bn, ks, 0, 0) for bn in bns for ks in kss]
         cands += [(bn, ks, 1, 0) for bn in bns if bn >= 64 for ks in kss if ks <= 4 and k[0] % 2 == 0]
         if conv3:
-            cands += [(bn, 1, pr, 1) for bn in bns if bn >= 64 for pr in (0, 1)]
+            cands += [(bn, 1, pr, 1) for bn in bns for pr in (0, 1)]
         for bn, ks, pr, hl in cands:
             if ks > 1:
                 n_tiles = (k[2] + bn - 1) // bn
