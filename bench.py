@@ -27,8 +27,19 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-# rank 0 prints exactly ONE JSON line on stdout: NCCL's own banner / debug output goes to stderr
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+# rank 0 prints exactly ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) write to file descriptor 1
+# directly, so main() moves fd 1 onto stderr and keeps the original stdout for the JSON line alone.
+_JSON_OUT = sys.stdout
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    try:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+    except OSError:
+        _JSON_OUT = sys.stdout
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -378,7 +389,7 @@ def run_dwg(args):
     }
     if not args.skip_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(sample_only=True)
-    print(json.dumps(out))
+    print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -540,7 +551,7 @@ def run_reference(args):
             break
     ms = 1000.0 * float(np.mean(times))
     v = 1000.0 / ms
-    print(json.dumps({
+    line = json.dumps({
         'impl': 'reference', 'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)', 'value': round(v, 5), 'unit': 'steps/s',
         'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': len(times), 'warmup': min(args.warmup, 1), 'ms_per_step': round(ms, 1),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -549,7 +560,8 @@ def run_reference(args):
         'cpu_baseline': {'value': round(v, 5), 'unit': 'steps/s', 'cores': min(os.cpu_count(), 32), 'kind': 'port',
                          'sample': f'{len(times)} full SDS steps of the same workload'},
         'e2e': {'value': round(v, 5), 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0,
-    }))
+    })
+    print(line, file=_JSON_OUT, flush=True)
 
 
 def main():
@@ -566,6 +578,7 @@ def main():
     ap.add_argument('--n-unconstrained', type=int, default=N_UNCONSTRAINED)
     ap.add_argument('--image', type=int, default=IMG)
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
