@@ -324,13 +324,15 @@ def run_dwg(args):
     clocks = sampler.stop() if rank == 0 else {}
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): one instrumented,
-    # un-graphed guidance pass with CUDA events around every tensor-core launch; the GPU is kept
+    # un-graphed, single-stream guidance pass with CUDA events around every tensor-core launch; the GPU is kept
     # busy ahead of the CPU (torch.cuda._sleep) so the events bracket pure execution time.
     roof = None
     if rank == 0:
         g = sc.guidance
         saved = getattr(g, '_g', None)
         g._g = None
+        saved_ts, g.two_streams = g.two_streams, False      # one stream: each launch is timed alone (no ControlNet || UNet overlap)
+        g._prepared = None
         ops.PROFILE = []
         ops.PROFILE_BYTES = 0.0
         img = torch.rand(1, 3, args.image, args.image, device=dev, requires_grad=True)
@@ -341,6 +343,7 @@ def run_dwg(args):
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         g._g = saved
+        g.two_streams = saved_ts
         tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
         tot_fl = sum(f for _, _, f, _ in prof)
         ach = tot_fl / (tot_ms * 1e-3) / 1e12

@@ -33,6 +33,9 @@ struct Params {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one MUFU.EX2 per element (ex2_fast() wraps the same instruction in denormal range handling: ~4 issue slots; results
+// below 2^-126 flush to zero here, which is what softmax wants).  The softmax warps are issue / MUFU bound.
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
 }
@@ -235,7 +238,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             // lazy running maximum: move the reference only when the block exceeds it by > 2^8
             const bool move = m_blk > m_ref + 8.0f;
             const float m_new = move ? m_blk : m_ref;
-            const float alpha = move ? exp2f(m_ref - m_new) : 1.0f;      // 0 on the first block (m_ref = -inf)
+            const float alpha = move ? ex2_fast(m_ref - m_new) : 1.0f;      // 0 on the first block (m_ref = -inf)
             if (j > 0) {
                 mbar_wait(o_full, (uint32_t)((j - 1) & 1));     // PV(j-1) done: O is stable and sP may be rewritten
                 tc_fence_after();
@@ -259,8 +262,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 uint32_t pk[8];
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const float p0 = exp2f(fmaf(sv[c0 + i], p.scale_log2, -m_new));
-                    const float p1 = exp2f(fmaf(sv[c0 + i + 1], p.scale_log2, -m_new));
+                    const float p0 = ex2_fast(fmaf(sv[c0 + i], p.scale_log2, -m_new));
+                    const float p1 = ex2_fast(fmaf(sv[c0 + i + 1], p.scale_log2, -m_new));
                     ls0 += p0; ls1 += p1;
                     const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
                     pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
