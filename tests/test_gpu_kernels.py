@@ -411,3 +411,39 @@ def test_avatar_mlp_fused_forward_backward_vs_oracle(N, Nu):
         scale = float(b.abs().max()) + 1e-12
         err = float((a.cpu() - b).abs().max()) / scale
         assert err < 2e-4, (name, err)
+
+
+def test_raster_full_benchmark_size_bit_exact_and_psnr():
+    """cfg2 size (150k Gaussians, 512x512): index state bit-exact with the oracle, render PSNR >= 40 dB (it is exact),
+    gradients within the atomics-reorder tolerance -- the north-star parity gate at BASELINE.json's own size."""
+    from oracle import raster as orast
+    n, H, W = 150000, 512, 512
+    g, cam, kw = _raster_case(n, H, W, seed=11, scale_range=(0.002, 0.012))
+    o = orast.forward(cam, g['positions'], g['scales'], g['quaternions'], g['opacities'], g['colors'])
+    rng = np.random.default_rng(11)
+    dc = rng.normal(size=(3, H, W)).astype(np.float32)
+    dd = rng.normal(size=(H, W)).astype(np.float32)
+    da = rng.normal(size=(H, W)).astype(np.float32)
+    color, radii, depth, alpha, st, t, m2 = _run_gpu(g, kw, grads=(dc, dd, da))
+    P = o['P']
+    T = (W // 16) * (H // 16)
+    status = st.status.cpu().numpy()
+    assert status[0] == 0 and status[1] == P and P > n            # every visible Gaussian touches >= 1 tile
+    assert np.array_equal(radii.cpu().numpy(), o['radii'])
+    assert np.array_equal(st.view(6, torch.int32, (T, 2)).cpu().numpy().view(np.uint32), o['ranges'])
+    keys = st.view(7, torch.int64, (st.P_cap,)).cpu().numpy().view(np.uint64)[:P]
+    vals = st.view(8, torch.int32, (st.P_cap,)).cpu().numpy().view(np.uint32)[:P]
+    assert np.array_equal(keys, o['keys']) and np.array_equal(vals, o['vals'])
+    assert np.all(keys[1:] >= keys[:-1])                          # size-independent property: globally sorted (tile, depth)
+    assert np.array_equal(st.view(10, torch.int32, (H, W)).cpu().numpy().view(np.uint32), o['n_contrib'])
+    got, ref = color.detach().cpu().numpy(), o['color']
+    mse = float(np.mean((got - ref) ** 2))
+    assert (99.0 if mse == 0 else 10 * np.log10(1.0 / mse)) >= 40.0
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6)
+    b = orast.backward(cam, o, dc, dd, da)
+    for name, gotg in (('means3D', t['positions'].grad), ('colors', t['colors'].grad), ('opacities', t['opacities'].grad),
+                       ('scales', t['scales'].grad), ('rots', t['quaternions'].grad), ('means2D', m2.grad)):
+        refg = b[name]
+        gg = gotg.cpu().numpy().reshape(refg.shape)
+        err = np.abs(gg - refg).max() / (np.abs(refg).max() + 1e-20)
+        assert err < 2e-4, (name, float(err))
