@@ -204,7 +204,8 @@ class ControlNetScoreDistillation:
                  vae_eps=None, use_negative_text=True, **_):
         """inputs [1,3,H,W] in [0,1] (autograd-connected); cond_inputs [1,3,512,512] in [0,1] (device tensor).
         Returns the reference's dict: latents, timestep, sources, targets, gradients, diffusion_loss."""
-        assert inputs.shape[1] == 3 and inputs.shape[-2:] == (self.default_image_size, self.default_image_size) or True
+        assert inputs.dim() == 4 and inputs.shape[1] == 3 and inputs.shape[-2] % 8 == 0 and inputs.shape[-1] % 8 == 0, \
+            'inputs must be [B,3,H,W] with H, W multiples of the VAE factor 8 (basic.py:354-366 resizes to 512 when needed)'
         latents = self.encode_images(inputs, vae_eps)
         if self._prepared is not None and timestep is None:
             self.timestep = self._prepared['t']                 # drawn by prepare()
