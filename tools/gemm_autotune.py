@@ -140,7 +140,7 @@ def main():
         bns = (64, 128, 192, 256) if geglu else (32, 64, 96, 128, 160, 192, 224, 256)
         kss = (1,) if geglu else (1, 2, 3, 4, 6, 8, 12, 16)
         cands = [(bn, ks, 0, 0) for bn in bns for ks in kss]
-        cands += [(bn, ks, 1, 0) for bn in bns if bn >= 64 for ks in kss if ks <= 4 and k[0] % 2 == 0]
+        cands += [(bn, ks, 1, 0) for bn in bns for ks in kss if ks <= 6 and k[0] % 2 == 0]
         if conv3:
             cands += [(bn, 1, pr, 1) for bn in bns for pr in (0, 1)]
         for bn, ks, pr, hl in cands:
