@@ -12,11 +12,16 @@ import torch
 from dwg._lib import check, lib, ptr, stream
 
 
+_TABLE_CACHE = {}
+
+
 def _tables(offsets, L, S, H, device):
-    lv = np.arange(L, dtype=np.float32)
-    scale = (np.exp2(lv * np.float32(S)).astype(np.float32) * np.float32(H) - np.float32(1.0)).astype(np.float32)
-    res = (np.ceil(scale).astype(np.uint32) + np.uint32(1)).astype(np.int32)
-    return torch.from_numpy(scale).to(device), torch.from_numpy(res).to(device)
+    """Per-level (scale, resolution) device tables, evaluated once per configuration by dwg_grid_level_table."""
+    from dwg.ops import device_level_table
+    key = (int(L), float(np.float32(S)), int(H), str(device))
+    if key not in _TABLE_CACHE:
+        _TABLE_CACHE[key] = device_level_table(np.float32(S), H, L, device)
+    return _TABLE_CACHE[key]
 
 
 def _check(inputs, embeddings, D, C):

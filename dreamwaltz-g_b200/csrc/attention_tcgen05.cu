@@ -16,7 +16,6 @@
 // V is consumed as V^T ([d, Tk], key index contiguous = K-major B operand), which the projection
 // GEMM produces for free by swapping its operands (see dwg/diffusion/model.py).
 #include <cuda.h>
-#include <cuda_bf16.h>
 
 #include "common.cuh"
 
@@ -28,7 +27,7 @@ constexpr int BQ = 128, BKV = 128;
 struct Params {
     int T, Tk, heads, hd;
     float scale_log2;               // softmax scale * log2(e)
-    __nv_bfloat16* out;             // [B, T, heads*hd]
+    act_t* out;             // [B, T, heads*hd]
     int64_t out_row_stride;         // = heads*hd
 };
 
@@ -111,7 +110,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 __device__ __forceinline__ uint32_t make_idesc(int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+    return (1u << 4) | kIdescFmtAB | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
 }
 
 template <int CH /* ceil(hd/64) */, int NPV /* round16(hd) */>
@@ -265,7 +264,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     const float p0 = ex2_fast(fmaf(sv[c0 + i], p.scale_log2, -m_new));
                     const float p1 = ex2_fast(fmaf(sv[c0 + i + 1], p.scale_log2, -m_new));
                     ls0 += p0; ls1 += p1;
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+                    const act2_t h = f2_to_act2(p0, p1);
                     pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
                 }
                 // 16 columns = two 16-byte chunks of the 128-byte row; chunk index XOR (row & 7)
@@ -284,7 +283,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tc_fence_after();
         const int t = q0 + r;
         const float inv = 1.0f / l;
-        __nv_bfloat16* dst = p.out + ((int64_t)b * p.T + t) * p.out_row_stride + (int64_t)head * p.hd;
+        act_t* dst = p.out + ((int64_t)b * p.T + t) * p.out_row_stride + (int64_t)head * p.hd;
 #pragma unroll
         for (int c0 = 0; c0 < NPV; c0 += 16) {
             uint32_t v[16];
@@ -293,10 +292,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             for (int h8 = 0; h8 < 16; h8 += 8) {
                 if (t < p.T && c0 + h8 < p.hd) {
                     uint4 pk;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[h8]) * inv, __uint_as_float(v[h8 + 1]) * inv);
-                    __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[h8 + 2]) * inv, __uint_as_float(v[h8 + 3]) * inv);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[h8 + 4]) * inv, __uint_as_float(v[h8 + 5]) * inv);
-                    __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[h8 + 6]) * inv, __uint_as_float(v[h8 + 7]) * inv);
+                    act2_t h0 = f2_to_act2(__uint_as_float(v[h8]) * inv, __uint_as_float(v[h8 + 1]) * inv);
+                    act2_t h1 = f2_to_act2(__uint_as_float(v[h8 + 2]) * inv, __uint_as_float(v[h8 + 3]) * inv);
+                    act2_t h2 = f2_to_act2(__uint_as_float(v[h8 + 4]) * inv, __uint_as_float(v[h8 + 5]) * inv);
+                    act2_t h3 = f2_to_act2(__uint_as_float(v[h8 + 6]) * inv, __uint_as_float(v[h8 + 7]) * inv);
                     pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
                     pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
                     *reinterpret_cast<uint4*>(dst + c0 + h8) = pk;
@@ -333,7 +332,7 @@ static int make_map(CUtensorMap* m, const void* base, const uint64_t d[4], const
     cuuint64_t ss[3] = {s[0], s[1], s[2]};
     cuuint32_t bb[4] = {box[0], box[1], box[2], box[3]};
     cuuint32_t ee[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dd, ss, bb, ee, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, DWG_TMAP_ACT, 4, const_cast<void*>(base), dd, ss, bb, ee, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("attention: cuTensorMapEncodeTiled failed (%d)", (int)r); return DWG_ERR_INVALID; }
     return DWG_OK;
@@ -383,7 +382,7 @@ extern "C" int dwg_attention_fwd(const void* q, int64_t q_ld, const void* k, int
     }
     Params p;
     p.T = T; p.Tk = Tk; p.heads = heads; p.hd = hd; p.scale_log2 = scale * 1.4426950408889634f;
-    p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_row_stride = C;
+    p.out = reinterpret_cast<act_t*>(out); p.out_row_stride = C;
     dim3 grid((T + BQ - 1) / BQ, heads, B);
     cudaStream_t st = (cudaStream_t)stream;
     const int ch = (hd + 63) / 64;

@@ -18,9 +18,10 @@
 //                               (+ residual chunk fetched by TMA into smem) -> swizzled smem
 //                               staging -> TMA store (cp.async.bulk.tensor ... global.shared).
 //                               TMA clips the M / N tails, so the fast path has no masks.
-//   split-K   : the CTAs of one output tile write fp32 partial tiles (coalesced, tile-private
-//               layout) and bump a per-tile counter; the LAST arriver adds the other partials to
-//               its own TMEM accumulator and runs the normal epilogue -- no finalize kernel.
+//   split-K   : the CTAs of one output tile store fp32 partial tiles (coalesced, one private slice per
+//               (tile, split)) and bump a per-tile counter; the LAST arriver adds the slices in split
+//               order (fixed summation order = run-to-run deterministic) and runs the normal
+//               epilogue -- no finalize kernel, no atomics on the data.
 //   CTA pairs : (PAIR = true) two CTAs of one cluster (same TPC) run tcgen05.mma.cta_group::2 on a 256 x BN
 //               tile: each CTA stages its own 128 A rows and HALF of the B tile (BN/2 rows); the leader's
 //               single MMA lane drives both tensor cores, reading the B halves from both shared memories.
@@ -37,7 +38,6 @@
 // The epilogue body is deliberately compact (no unrolling over chunks, one instantiation per
 // output kind): v2's 265 KB of SASS made short kernels instruction-fetch bound (ncu: stall_no_inst).
 #include <cuda.h>
-#include <cuda_bf16.h>
 
 #include "common.cuh"
 
@@ -62,7 +62,7 @@ constexpr uint32_t HALO_TX = HALO_LINES * HALO_LINE_PIX * 128;
 constexpr int kMaxAStages = 4;
 
 enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_GEGLU = 3 };   // GEGLU: columns are (value, gate) pairs -> N/2 outputs
-enum Epi { EPI_BF16 = 0, EPI_F32 = 1, EPI_GEGLU = 2 };
+enum Epi { EPI_F16 = 0, EPI_F32 = 1, EPI_GEGLU = 2 };
 
 struct Params {
     // problem
@@ -87,13 +87,13 @@ struct Params {
     // slow path (unaligned output / residual strides): direct per-thread stores
     int direct;
     void* C; int64_t ldc, c_b1, c_b2;
-    const __nv_bfloat16* residual; int64_t ldr, r_b1, r_b2;
+    const act_t* residual; int64_t ldr, r_b1, r_b2;
     // tiling
     int BN, stages;
     int m_tiles, n_tiles, nz, ksplit, total_tiles;
     int halo, a_stages, halo_bo;    // halo mode, depth of the halo ring, descriptor base-offset convention (see make_desc_halo)
     int m_sched;                    // scheduler units along M: m_tiles (single CTA) or m_tiles / 2 (CTA pair)
-    float* workspace;               // split-K fp32 tile accumulators (zero when idle)
+    float* workspace;               // split-K fp32 partial-tile slices [tile][split]
     int* counters;                  // one per output tile, self-resetting
     unsigned long long* trace;      // optional [8] per-launch timeline of CTA 0 (globaltimer ns), null = off
 };
@@ -267,10 +267,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, int m_m
     return c;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
+__device__ __forceinline__ uint32_t pack_act(float a, float b) { return pack_act2(a, b); }
 
 // Persistent, warp-specialised: the CTA walks tiles blockIdx.x, +gridDim.x, ...; the smem ring and
 // the two TMEM accumulator stages let the TMA / MMA of tile i+1 overlap the epilogue of tile i.
@@ -439,7 +436,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp == 1 && rank == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | kIdescFmtAB | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
         uint32_t s = 0, ph = 0, tl = 0, sa = 0, pha = 0;
         for (int t = tile0; t < p.total_tiles; t += tile_step, tl++) {
             const TileCoord tc = decode_tile(p, t, m_mul, m_add);
@@ -591,19 +588,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
             bool released = false;
             const int out_tile = (tc.z * p.n_tiles + tc.n_tile) * p.m_tiles + tc.m_tile;
-            // fp32 tile accumulator in global memory (zero when idle), laid out [32-col chunk][float4 j][row]: coalesced
-            float4* wsp = reinterpret_cast<float4*>(p.workspace) + (int64_t)out_tile * (p.BN / 32) * (8 * 128) + r0 + lane;
+            // split-K partial tiles in global memory (L2-resident), one private slice per (tile, split), laid out
+            // [32-col chunk][float4 j][row]: coalesced.  Plain stores, no atomics: the last arriver adds the slices in the
+            // fixed order 0 .. ksplit-1, so the result does not depend on which CTA finishes last (run-to-run deterministic).
+            const int64_t tile_f4 = (int64_t)(p.BN / 32) * (8 * 128);
+            float4* wsp = reinterpret_cast<float4*>(p.workspace) + (int64_t)out_tile * p.ksplit * tile_f4 + r0 + lane;
             if (p.ksplit > 1) {
-                // ---- split-K: every CTA of the tile adds its partial accumulator with 16-byte vector atomics
-                // (L2-side reduction), then bumps the tile counter; the LAST arriver owns the epilogue.
+                // ---- split-K: every CTA of the tile stores its partial accumulator, then bumps the tile counter;
+                // the LAST arriver owns the reduction and the epilogue.
                 const int acc_chunks = p.BN / 32;
+                float4* mine = wsp + (int64_t)tc.ks * tile_f4;
 #pragma unroll 1
                 for (int c = half; c < acc_chunks; c += 2) {
                     float v[32];
                     tc_ld32(taddr_row + (uint32_t)(c * 32), v);
-                    float4* dst = wsp + (int64_t)c * (8 * 128);
+                    float4* dst = mine + (int64_t)c * (8 * 128);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) atomicAdd(dst + j * 128, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                    for (int j = 0; j < 8; j++) __stcg(dst + j * 128, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                 }
                 released = true;                                     // the accumulator stage is free again
                 tc_fence_before();
@@ -661,13 +662,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 } else {
                     if (p.ksplit > 1) {
-                        // last arriver: the complete sums are in the L2-resident tile accumulator; read and re-zero it
-                        float4* src = wsp + (int64_t)c * (8 * 128);
+                        // last arriver: add the ksplit partial slices of this chunk in split order (fixed summation order)
+                        const float4* src = wsp + (int64_t)c * (8 * 128);
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             const float4 u = __ldcg(src + j * 128);
                             f[4 * j] = u.x; f[4 * j + 1] = u.y; f[4 * j + 2] = u.z; f[4 * j + 3] = u.w;
-                            __stcg(src + j * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+                        }
+#pragma unroll 1
+                        for (int sp = 1; sp < p.ksplit; sp++) {
+                            const float4* s2 = src + (int64_t)sp * tile_f4;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float4 u = __ldcg(s2 + j * 128);
+                                f[4 * j] += u.x; f[4 * j + 1] += u.y; f[4 * j + 2] += u.z; f[4 * j + 3] += u.w;
+                            }
                         }
                     } else {
                         tc_wait_ld();
@@ -713,9 +722,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < 32; j++) {                  // fully unrolled: a dynamic index would push f[] into local memory
                             if (j >= nvalid) break;
                             float x = f[j];
-                            if (p.residual) x += __bfloat162float(p.residual[d_res + ocol0 + j]);
+                            if (p.residual) x += act_to_f(p.residual[d_res + ocol0 + j]);
                             if (EPI == EPI_F32) reinterpret_cast<float*>(p.C)[d_row + ocol0 + j] = x;
-                            else reinterpret_cast<__nv_bfloat16*>(p.C)[d_row + ocol0 + j] = __float2bfloat16(x);
+                            else reinterpret_cast<act_t*>(p.C)[d_row + ocol0 + j] = f_to_act(x);
                         }
                     }
                     continue;
@@ -731,7 +740,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+                            const float2 t2 = act2_to_f2(*reinterpret_cast<const act2_t*>(&w4[k]));
                             f[8 * j + 2 * k] += t2.x; f[8 * j + 2 * k + 1] += t2.y;
                         }
                     }
@@ -749,8 +758,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         uint4 pk;
-                        pk.x = pack_bf16(f[8 * j], f[8 * j + 1]); pk.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-                        pk.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]); pk.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+                        pk.x = pack_act(f[8 * j], f[8 * j + 1]); pk.y = pack_act(f[8 * j + 2], f[8 * j + 3]);
+                        pk.z = pack_act(f[8 * j + 4], f[8 * j + 5]); pk.w = pack_act(f[8 * j + 6], f[8 * j + 7]);
                         *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = pk;
                     }
                 }
@@ -819,13 +828,13 @@ static int make_map(CUtensorMap* m, CUtensorMapDataType dt, CUtensorMapSwizzle s
     }
     return DWG_OK;
 }
-static int make_map_bf16(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+static int make_map_act(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
                          const uint32_t box[4], const uint32_t estr[4]) {
-    return make_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, base, dims, strides_bytes, box, estr);
+    return make_map(m, DWG_TMAP_ACT, CU_TENSOR_MAP_SWIZZLE_128B, base, dims, strides_bytes, box, estr);
 }
 
 static int g_num_sms = 0;
-static float* g_ws = nullptr;            // split-K fp32 tile accumulators (zero when idle)
+static float* g_ws = nullptr;            // split-K fp32 partial-tile slices
 static size_t g_ws_bytes = 0;
 static int* g_counters = nullptr;        // split-K arrival counters (zero when idle)
 constexpr int kMaxCounters = 1 << 16;
@@ -875,7 +884,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
                 const int64_t tiles = (int64_t)m_tiles * ((N + t->BN - 1) / t->BN) * nz;
                 const int pair = (t->pair && pair_legal(m_tiles, t->BN)) ? 1 : 0;
                 const int stages = stages_for(t->BN, pair, epi, has_res);
-                if (stages >= 2 && (t->ks == 1 || (tiles <= kMaxCounters / kLanes && tiles * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters)))
+                if (stages >= 2 && (t->ks == 1 || (tiles <= kMaxCounters / kLanes && tiles * t->ks * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters)))
                     pl = {t->BN, t->ks, stages, pair, t->halo && t->ks == 1};
                 break;
             }
@@ -889,7 +898,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
         if (epi == EPI_GEGLU) ks = 1;
         if (ks > iters) ks = iters;
         const int64_t tiles = (int64_t)m_tiles * ((N + BN - 1) / BN) * nz;
-        if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
+        if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * ks * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
         pl = {BN, ks, stages_for(BN, 0, epi, has_res), 0, 0};
     }
     if (g_force_pair >= 0) {
@@ -913,7 +922,7 @@ static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int 
         const int64_t tiles = (int64_t)m_tiles * n_tiles * nz;
         for (int ks = 1; ks <= 32; ks++) {
             if (ks > 1 && (epi == EPI_GEGLU || iters / ks < 2 || tiles * ks > 2 * g_num_sms)) break;
-            if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * 128 * (int64_t)BN > ws_cap_floats)) break;
+            if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * ks * 128 * (int64_t)BN > ws_cap_floats)) break;
             const int64_t ctas = tiles * ks;
             const double active = (double)(ctas < g_num_sms ? ctas : g_num_sms);
             const double feed = (double)stage_bytes * active / 6000.0;          // ~6.3 KB/cycle chip-wide TMA throughput
@@ -989,12 +998,12 @@ static int launch(const CUtensorMap& tmA, CUtensorMap& tmB_out, const CUtensorMa
     if (pair) {
         const int pairs = g_num_sms / 2;
         const dim3 grid(2 * (p.total_tiles < pairs ? p.total_tiles : pairs));
-        if (epi == EPI_BF16) launch_one<EPI_BF16, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+        if (epi == EPI_F16) launch_one<EPI_F16, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
         else if (epi == EPI_F32) launch_one<EPI_F32, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
         else launch_one<EPI_GEGLU, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
     } else {
         const dim3 grid(p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms);
-        if (epi == EPI_BF16) launch_one<EPI_BF16, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+        if (epi == EPI_F16) launch_one<EPI_F16, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
         else if (epi == EPI_F32) launch_one<EPI_F32, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
         else launch_one<EPI_GEGLU, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
     }
@@ -1012,10 +1021,10 @@ using namespace dwg;
 using namespace dwg::gemm;
 
 // D[b2][b1][M,N] = act(alpha * A[b2][b1][M,K] @ B[b2][b1][N,K]^T + bias[N] + bias2) + residual
-// All strides in ELEMENTS.  A/B bf16, K contiguous.  out_bf16: 1 -> bf16 C, 0 -> fp32 C.
-extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
+// All strides in ELEMENTS.  A/B bf16, K contiguous.  out_f16: 1 -> bf16 C, 0 -> fp32 C.
+extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                              const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
-                             void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_bf16,
+                             void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16,
                              int M, int N, int K, int nb1, int nb2,
                              const float* bias, const float* bias2, int bias2_rows_per,
                              const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
@@ -1025,12 +1034,12 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     DWG_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && (a_b1 % 8) == 0 && (a_b2 % 8) == 0 && (b_b1 % 8) == 0 && (b_b2 % 8) == 0,
                 "A/B strides must be multiples of 8 elements (16 bytes) for TMA");
     DWG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "A/B must be 16-byte aligned");
-    DWG_REQUIRE(act != ACT_GEGLU || (N % 2 == 0 && out_bf16 && !residual), "GEGLU epilogue: even N, bf16 output, no residual");
+    DWG_REQUIRE(act != ACT_GEGLU || (N % 2 == 0 && out_f16 && !residual), "GEGLU epilogue: even N, 16-bit output, no residual");
     DWG_REQUIRE(act != ACT_GEGLU || !bias || ((uintptr_t)bias & 15) == 0, "GEGLU bias must be 16-byte aligned");
     int rc = ensure_globals();
     if (rc) return rc;
-    const int epi = act == ACT_GEGLU ? EPI_GEGLU : (out_bf16 ? EPI_BF16 : EPI_F32);
-    const int64_t esz = out_bf16 ? 2 : 4;
+    const int epi = act == ACT_GEGLU ? EPI_GEGLU : (out_f16 ? EPI_F16 : EPI_F32);
+    const int64_t esz = out_f16 ? 2 : 4;
     if (nb1 == 1) c_b1 = ldc * (int64_t)M;
     if (nb2 == 1) c_b2 = c_b1 * nb1;
     if (residual && nb1 == 1) r_b1 = ldr * (int64_t)M;
@@ -1044,7 +1053,7 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
     p.a_bytes = A_BYTES;
     p.C = C; p.ldc = ldc; p.c_b1 = c_b1; p.c_b2 = c_b2;
     p.bias = bias; p.bias2 = bias2; p.bias2_rows_per = bias2_rows_per;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.r_b1 = r_b1; p.r_b2 = r_b2;
+    p.residual = reinterpret_cast<const act_t*>(residual); p.ldr = ldr; p.r_b1 = r_b1; p.r_b2 = r_b2;
     p.alpha = alpha; p.act = act;
     p.m_tiles = (M + BM - 1) / BM; p.nz = nb1 * nb2;
     const Plan pl = plan_tiles(p.m_tiles, p.nz, N, p.k_chunks, epi, p.has_res, (int64_t)(g_ws_bytes / 4 / kLanes));
@@ -1060,14 +1069,14 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
         const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)nb1, (uint64_t)nb2};
         const uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)(nb1 > 1 ? a_b1 : lda * (int64_t)M) * 2, (uint64_t)(nb2 > 1 ? a_b2 : lda * (int64_t)M) * 2};
         const uint32_t box[4] = {BK, BM, 1, 1};
-        rc = make_map_bf16(&tmA, A, dims, str, box, ones);
+        rc = make_map_act(&tmA, A, dims, str, box, ones);
         if (rc) return rc;
     }
     {
         const uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)nb1, (uint64_t)nb2};
         const uint64_t str[3] = {(uint64_t)ldb * 2, (uint64_t)(nb1 > 1 ? b_b1 : ldb * (int64_t)N) * 2, (uint64_t)(nb2 > 1 ? b_b2 : ldb * (int64_t)N) * 2};
         const uint32_t box[4] = {BK, (uint32_t)(pl.pair ? p.BN / 2 : p.BN), 1, 1};
-        rc = make_map_bf16(&tmB, B, dims, str, box, ones);
+        rc = make_map_act(&tmB, B, dims, str, box, ones);
         if (rc) return rc;
     }
     tmC = tmA; tmR = tmA;                                   // placeholders on the direct path (never dereferenced)
@@ -1076,12 +1085,12 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
         const uint64_t dims[4] = {No, (uint64_t)M, (uint64_t)nb1, (uint64_t)nb2};
         const uint64_t str[3] = {(uint64_t)(ldc * esz), (uint64_t)(c_b1 * esz), (uint64_t)(c_b2 * esz)};
         const uint32_t box[4] = {32, 32, 1, 1};
-        rc = make_map(&tmC, out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                      out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, C, dims, str, box, ones);
+        rc = make_map(&tmC, out_f16 ? DWG_TMAP_ACT : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      out_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, C, dims, str, box, ones);
         if (rc) return rc;
         if (p.has_res) {
             const uint64_t rstr[3] = {(uint64_t)ldr * 2, (uint64_t)r_b1 * 2, (uint64_t)r_b2 * 2};
-            rc = make_map(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, residual, dims, rstr, box, ones);
+            rc = make_map(&tmR, DWG_TMAP_ACT, CU_TENSOR_MAP_SWIZZLE_64B, residual, dims, rstr, box, ones);
             if (rc) return rc;
         }
     }
@@ -1091,7 +1100,7 @@ extern "C" int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a
 // NHWC convolution as implicit GEMM.  x [Nimg,H,W,Cin] bf16 (Cin % 8 == 0), w [Cout,kh,kw,Cin] bf16,
 // y [Nimg,Ho,Wo,Cout] (bf16 or fp32).  Padding is zero-fill (pad_h/pad_w applied on the top/left;
 // the bottom/right extent follows from Ho/Wo, which covers SD's asymmetric (0,1,0,1) padding).
-extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int out_bf16,
+extern "C" int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int out_f16,
                                     int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
                                     int pad_h, int pad_w, int Ho, int Wo,
                                     const float* bias, const float* bias2_per_image,
@@ -1112,8 +1121,8 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     int BNI = BM / (BW * BH);
     if (BNI > Nimg) BNI = 1 << (31 - __builtin_clz(Nimg));         // largest power of two <= Nimg
     const int tiles_w = (Wo + BW - 1) / BW, tiles_h = (Ho + BH - 1) / BH, tiles_n = (Nimg + BNI - 1) / BNI;
-    const int epi = out_bf16 ? EPI_BF16 : EPI_F32;
-    const int64_t esz = out_bf16 ? 2 : 4;
+    const int epi = out_f16 ? EPI_F16 : EPI_F32;
+    const int64_t esz = out_f16 ? 2 : 4;
     Params p = {};
     p.direct = (((uintptr_t)y & 15) || (Cout * esz) % 16 || (residual && (((uintptr_t)residual & 15) || (Cout * 2) % 16)) ||
                 (bias && ((uintptr_t)bias & 15)) || (bias2_per_image && (((uintptr_t)bias2_per_image & 15) || (Cout % 4)))) ? 1 : 0;
@@ -1128,7 +1137,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
     int ebn = 32 / (p.ebw * p.ebh);
     p.C = y; p.ldc = Cout;
     p.bias = bias; p.bias2 = bias2_per_image; p.bias2_rows_per = bias2_per_image ? Ho * Wo : 0;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
+    p.residual = reinterpret_cast<const act_t*>(residual); p.ldr = Cout;
     p.alpha = 1.0f; p.act = act;
     p.m_tiles = tiles_w * tiles_h * tiles_n; p.nz = 1;
     const int iters = ksize * ksize * p.k_chunks;
@@ -1166,7 +1175,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
         const uint32_t box_h[4] = {BK, (uint32_t)HALO_LINE_PIX, 1, 1};          // one halo line
         const uint32_t* box = p.halo ? box_h : box_t;
         const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-        rc = make_map_bf16(&tmA, x, dims, str, box, es);
+        rc = make_map_act(&tmA, x, dims, str, box, es);
         if (rc) return rc;
     }
     const uint32_t ones[4] = {1, 1, 1, 1};
@@ -1175,7 +1184,7 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout, 1};
         const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2, (uint64_t)Cout * taps * Cin * 2};
         const uint32_t box[4] = {BK, 1, (uint32_t)(pl.pair ? p.BN / 2 : p.BN), 1};
-        rc = make_map_bf16(&tmB, w, dims, str, box, ones);
+        rc = make_map_act(&tmB, w, dims, str, box, ones);
         if (rc) return rc;
     }
     tmC = tmA; tmR = tmA;
@@ -1183,12 +1192,12 @@ extern "C" int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int o
         const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)Nimg};
         const uint64_t str[3] = {(uint64_t)(Cout * esz), (uint64_t)((int64_t)Wo * Cout * esz), (uint64_t)((int64_t)Ho * Wo * Cout * esz)};
         const uint32_t box[4] = {32, (uint32_t)p.ebw, (uint32_t)p.ebh, (uint32_t)ebn};
-        rc = make_map(&tmC, out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                      out_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, y, dims, str, box, ones);
+        rc = make_map(&tmC, out_f16 ? DWG_TMAP_ACT : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      out_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, y, dims, str, box, ones);
         if (rc) return rc;
         if (p.has_res) {
             const uint64_t rstr[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
-            rc = make_map(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, residual, dims, rstr, box, ones);
+            rc = make_map(&tmR, DWG_TMAP_ACT, CU_TENSOR_MAP_SWIZZLE_64B, residual, dims, rstr, box, ones);
             if (rc) return rc;
         }
     }

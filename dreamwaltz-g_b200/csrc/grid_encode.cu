@@ -8,8 +8,12 @@
 //     on B200's 126 MB L2);
 //   * the backward reduces dL/dx over the 16 levels with shuffles instead of a second kernel
 //     over a stored dy_dx buffer (the reference stores 384 B/point of dy_dx, grid.py:54).
-// Index arithmetic is uint32 and bit-exact with the oracle; per-level scale / resolution are
-// host-evaluated constants (gridencoder.cu:138-139) so CPU and GPU agree on them.
+// Index arithmetic is uint32 and bit-exact with the oracle and with the reference kernel.  The per-level scale /
+// resolution (gridencoder.cu:138-139: exp2f(level * S) * H - 1, ceil(scale) + 1) are evaluated ONCE by
+// dwg_grid_level_table ON THE DEVICE with the same exp2f the reference kernel calls per thread: a host libm exp2 is
+// correctly rounded while the device function is not (<= 2 ulp), and one ulp of scale at the 4096-wide level moves
+// the interpolation position enough to change outputs by 1e-4 (found when the oracle was pinned to the reference
+// kernel's own outputs, tests/test_grid_golden.py).
 #include "common.cuh"
 
 namespace dwg {
@@ -58,7 +62,10 @@ __device__ __forceinline__ void level_setup(LevelCtx& c, const float* __restrict
         const float fl = floorf(p);
         c.pg[d] = (uint32_t)fl;
         p -= fl;
-        c.deriv[d] = 1.0f;
+        // reference quirk, reproduced for parity (found by the golden vectors of the reference's own kernel): with LINEAR
+        // interpolation `float pos_deriv[D] = {1.0f}` (gridencoder.cu:143) initialises only element 0, so dy/dx_1 and dy/dx_2
+        // are multiplied by 0.  The avatar grid uses smoothstep, where every element is overwritten.
+        c.deriv[d] = d == 0 ? 1.0f : 0.0f;
         if (interp == 1) {
             c.deriv[d] = 6.f * p * (1.0f - p);
             p = p * p * (3.0f - 2.0f * p);
@@ -201,6 +208,24 @@ grid_bwd_kernel(const float* __restrict__ grad, int64_t gsb, int64_t gsl, const 
 }  // namespace dwg
 
 using namespace dwg;
+
+namespace dwg {
+namespace {
+__global__ void level_table_kernel(float S, uint32_t H, int L, float* __restrict__ level_scale, uint32_t* __restrict__ level_res) {
+    const uint32_t level = threadIdx.x;
+    if ((int)level >= L) return;
+    const float scale = exp2f(level * S) * H - 1.0f;              // gridencoder.cu:138, same expression, same device function
+    level_scale[level] = scale;
+    level_res[level] = (uint32_t)ceil(scale) + 1;                 // gridencoder.cu:139
+}
+}  // namespace
+}  // namespace dwg
+
+extern "C" int dwg_grid_level_table(float S, int H, int L, float* level_scale, uint32_t* level_res, void* stream) {
+    DWG_REQUIRE(level_scale && level_res && L > 0 && L <= 32 && H > 0, "bad arguments");
+    dwg::level_table_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(S, (uint32_t)H, L, level_scale, level_res);
+    return dwg::check_launch("dwg_grid_level_table");
+}
 
 extern "C" int dwg_grid_encode_fwd(const float* x, float bound, const float* table, const int32_t* offsets,
                                    const float* level_scale, const uint32_t* level_res, float* out,

@@ -4,24 +4,23 @@
 //   a few atomics) + apply pass; backward (VAE encoder input-gradient) the same two-pass shape;
 //   layernorm over channels (one warp per token); row softmax (bf16 in place); GEGLU; SiLU;
 //   the fused CFG + SDS-gradient epilogue (core/guidance/basic.py:595-603,642).
-#include <cuda_bf16.h>
 
 #include "common.cuh"
 
 namespace dwg {
 namespace nn {
 
-struct bf8 { __nv_bfloat162 v[4]; };
-static_assert(sizeof(bf8) == 16, "bf8");
+struct h8 { act2_t v[4]; };
+static_assert(sizeof(h8) == 16, "h8");
 
-__device__ __forceinline__ void unpack8(const bf8& p, float f[8]) {
+__device__ __forceinline__ void unpack8(const h8& p, float f[8]) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(p.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    for (int i = 0; i < 4; i++) { const float2 t = act2_to_f2(p.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
-__device__ __forceinline__ bf8 pack8(const float f[8]) {
-    bf8 p;
+__device__ __forceinline__ h8 pack8(const float f[8]) {
+    h8 p;
 #pragma unroll
-    for (int i = 0; i < 4; i++) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    for (int i = 0; i < 4; i++) p.v[i] = f2_to_act2(f[2 * i], f[2 * i + 1]);
     return p;
 }
 // These kernels are issue-bound on the big VAE tensors: sigmoid(x) = 0.5 + 0.5 tanh(x/2) costs ONE MUFU op
@@ -31,21 +30,40 @@ __device__ __forceinline__ float silu(float x) { const float h = 0.5f * x; retur
 __device__ __forceinline__ float silu_grad(float x) { const float s = fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); return s * fmaf(x, 1.0f - s, 1.0f); }
 
 // ---------------------------------------------------------------------------- GroupNorm
-// x [N, HW, C] bf16, C % 8 == 0, (C/G) % 8 == 0 or 8 % (C/G) == 0 handled generically via smem bins.
-// stats[n][g] = (sum, sumsq) accumulated with atomics (caller zeroes).
+// Run-to-run DETERMINISTIC statistics: every per-thread fp32 partial sum is converted to 64-bit fixed point and
+// accumulated with INTEGER atomics (shared, then global) -- integer addition is associative, so the result does not
+// depend on the arrival order, unlike fp32 atomics whose last-bit differences are blown up to the full 16-bit rounding
+// noise by the next few layers (tools/determinism_probe.py).  Forward moments use 2^-20 resolution (|sum| < 2^43);
+// the backward sums (gradients, much smaller) 2^-36 (|sum| < 2^27).  Mean / variance are then formed in double, which
+// also removes the one-pass E[x^2] - E[x]^2 cancellation on large-mean activations.
+typedef unsigned long long fix_t;
+constexpr float kFixFwd = 1048576.0f;               // 2^20
+constexpr float kFixBwd = 68719476736.0f;           // 2^36
+__device__ __forceinline__ fix_t to_fix(float v, float scale) { return (fix_t)__float2ll_rn(v * scale); }
+__device__ __forceinline__ double from_fix(fix_t v, double inv_scale) { return (double)(long long)v * inv_scale; }
+// (mean, rstd) of group idx = n * G + g from the fixed-point (sum, sumsq)
+__device__ __forceinline__ void gn_moments(const fix_t* __restrict__ stats, size_t idx, double inv_cnt, float eps, float& mean, float& rstd) {
+    const double m = from_fix(stats[2 * idx], inv_cnt * (1.0 / 1048576.0));
+    const double q = from_fix(stats[2 * idx + 1], inv_cnt * (1.0 / 1048576.0));
+    mean = (float)m;
+    rstd = rsqrtf((float)fmax(q - m * m, 0.0) + eps);
+}
+
+// x [N, HW, C] fp16, C % 8 == 0, (C/G) % 8 == 0 or 8 % (C/G) == 0 handled generically via smem bins.
+// stats[n][g] = fixed-point (sum, sumsq) accumulated with integer atomics (zeroed by the entry point).
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, int HW, int C, int G, int rows_per_cta) {
+gn_stats_kernel(const act_t* __restrict__ x, fix_t* __restrict__ stats, int HW, int C, int G, int rows_per_cta) {
     pdl_wait();
     pdl_trigger();
-    extern __shared__ float s_bins[];        // [G][2]
+    extern __shared__ fix_t s_bins[];        // [G][2]
     const int n = blockIdx.y;
     const int cpg = C / G;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_bins[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_bins[i] = 0ull;
     __syncthreads();
     const int c8 = C / 8;                    // 16-byte vectors per row
     const int row0 = blockIdx.x * rows_per_cta;
     const int row1 = min(HW, row0 + rows_per_cta);
-    const bf8* xp = reinterpret_cast<const bf8*>(x + (size_t)n * HW * C);
+    const h8* xp = reinterpret_cast<const h8*>(x + (size_t)n * HW * C);
     // thread -> (row lane, fixed vector column): per-thread register accumulation over rows, a
     // handful of shared-memory atomics at the end
     const int rp = c8 <= 256 ? 256 / c8 : 1;
@@ -56,8 +74,8 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, 
         for (int i = 0; i < 8; i++) { s[i] = 0.f; ss[i] = 0.f; }
         int r = row0 + rl;
         for (; r + 3 * rp < row1; r += 4 * rp) {          // 4 independent 16-byte loads in flight
-            bf8 v0 = xp[(size_t)r * c8 + cv], v1 = xp[(size_t)(r + rp) * c8 + cv];
-            bf8 v2 = xp[(size_t)(r + 2 * rp) * c8 + cv], v3 = xp[(size_t)(r + 3 * rp) * c8 + cv];
+            h8 v0 = xp[(size_t)r * c8 + cv], v1 = xp[(size_t)(r + rp) * c8 + cv];
+            h8 v2 = xp[(size_t)(r + 2 * rp) * c8 + cv], v3 = xp[(size_t)(r + 3 * rp) * c8 + cv];
             float f[8];
             unpack8(v0, f);
 #pragma unroll
@@ -83,14 +101,14 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, 
 #pragma unroll
             for (int i = 0; i < 8; i++) { a += s[i]; b += ss[i]; }
             const int g = (cv * 8) / cpg;
-            atomicAdd(&s_bins[2 * g], a);
-            atomicAdd(&s_bins[2 * g + 1], b);
+            atomicAdd(&s_bins[2 * g], to_fix(a, kFixFwd));
+            atomicAdd(&s_bins[2 * g + 1], to_fix(b, kFixFwd));
         } else {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int g = (cv * 8 + i) / cpg;
-                atomicAdd(&s_bins[2 * g], s[i]);
-                atomicAdd(&s_bins[2 * g + 1], ss[i]);
+                atomicAdd(&s_bins[2 * g], to_fix(s[i], kFixFwd));
+                atomicAdd(&s_bins[2 * g + 1], to_fix(ss[i], kFixFwd));
             }
         }
     }
@@ -102,32 +120,33 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, 
 // fixed 8-channel column): scale/shift are computed once per thread, then one 16-byte load, 8 FMAs
 // and one 16-byte store per row.
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int HW, int C, int G, float eps, int do_silu,
+gn_apply_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, act_t* __restrict__ y, int HW, int C, int G, float eps, int do_silu,
                 int rows_per_cta) {
     pdl_wait();
     pdl_trigger();
     const int n = blockIdx.y;
     const int c8 = C / 8, cpg = C / G;
-    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    const double inv_cnt = 1.0 / ((double)HW * (double)cpg);
     const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
-    const bf8* xp = reinterpret_cast<const bf8*>(x + (size_t)n * HW * C);
-    bf8* yp = reinterpret_cast<bf8*>(y + (size_t)n * HW * C);
+    const h8* xp = reinterpret_cast<const h8*>(x + (size_t)n * HW * C);
+    h8* yp = reinterpret_cast<h8*>(y + (size_t)n * HW * C);
     const int rp = c8 <= 256 ? 256 / c8 : 1;
     const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
     for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
         float a[8], b[8];
+        int g_prev = -1;
+        float mean = 0.f, rstd = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int c = cv * 8 + i, g = c / cpg;
-            const float mean = stats[((size_t)n * G + g) * 2] * inv_cnt;
-            const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
-            a[i] = rsqrtf(var + eps) * gamma[c];
+            if (g != g_prev) { gn_moments(stats, (size_t)n * G + g, inv_cnt, eps, mean, rstd); g_prev = g; }
+            a[i] = rstd * gamma[c];
             b[i] = beta[c] - mean * a[i];
         }
         int r = row0 + rl;
         for (; r + 3 * rp < row1; r += 4 * rp) {          // 4 independent 16-byte loads in flight
-            bf8 v[4];
+            h8 v[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) v[u] = xp[(size_t)(r + u * rp) * c8 + cv];
 #pragma unroll
@@ -171,16 +190,24 @@ __device__ __forceinline__ float ld_dsmem_f32(const float* p, uint32_t rank) {
     asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
     return v;
 }
+__device__ __forceinline__ fix_t ld_dsmem_u64(const fix_t* p, uint32_t rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
+    fix_t v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(ra) : "memory");
+    return v;
+}
 __device__ __forceinline__ void cluster_sync_gn() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(GN_THREADS)
-gn_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                __nv_bfloat16* __restrict__ y, float* __restrict__ stats_out, int HW, int C, int G, float eps, int do_silu,
+gn_fused_kernel(const act_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                act_t* __restrict__ y, fix_t* __restrict__ stats_out, int HW, int C, int G, float eps, int do_silu,
                 int rows_per_cta) {
     extern __shared__ __align__(16) uint8_t gsm[];
-    __shared__ float s_part[8];          // this CTA's (sum, sumsq) of the slab's 4 groups
+    __shared__ fix_t s_part[8];          // this CTA's fixed-point (sum, sumsq) of the slab's 4 groups
+    __shared__ fix_t s_tot[8];           // cluster totals (private copy: peers keep reading s_part until the final barrier)
     __shared__ float s_ab[2 * 4];        // (mean, rstd) of the 4 groups
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -190,14 +217,14 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g
     const int cv0 = slab * sc8;                              // first vector column of the slab
     const int row0 = (int)rank * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
     const int nvec = max(0, row1 - row0) * sc8;
-    if (threadIdx.x < 8) s_part[threadIdx.x] = 0.f;
+    if (threadIdx.x < 8) s_part[threadIdx.x] = 0ull;
     pdl_wait();
     pdl_trigger();
     __syncthreads();
-    const bf8* xp = reinterpret_cast<const bf8*>(x + (size_t)n * HW * C);
-    bf8* sv = reinterpret_cast<bf8*>(gsm);
+    const h8* xp = reinterpret_cast<const h8*>(x + (size_t)n * HW * C);
+    h8* sv = reinterpret_cast<h8*>(gsm);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-    auto accum = [&](const bf8& v, int cv) {
+    auto accum = [&](const h8& v, int cv) {
         float f[8];
         unpack8(v, f);
         if (cpg % 8 == 0) {
@@ -218,7 +245,7 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g
     };
     // 4 independent 16-byte loads in flight per thread (the block comes from L2: latency-, not bandwidth-bound)
     for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * GN_THREADS) {
-        bf8 v[4];
+        h8 v[4];
         int cvs[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -239,16 +266,23 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g
     for (int q = 0; q < 4; q++) {
         float a = s[q], b = ss[q];
         for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_part[2 * q], a); atomicAdd(&s_part[2 * q + 1], b); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_part[2 * q], to_fix(a, kFixFwd)); atomicAdd(&s_part[2 * q + 1], to_fix(b, kFixFwd)); }
     }
     __syncthreads();
     cluster_sync_gn();                                       // every CTA's partials are complete and visible cluster-wide
     if (threadIdx.x < 8) {
-        float tot = 0.f;
+        fix_t tot = 0ull;
 #pragma unroll
-        for (uint32_t r = 0; r < (uint32_t)GN_CS; r++) tot += ld_dsmem_f32(&s_part[threadIdx.x], r);
+        for (uint32_t r = 0; r < (uint32_t)GN_CS; r++) tot += ld_dsmem_u64(&s_part[threadIdx.x], r);
         if (stats_out && rank == 0) stats_out[((size_t)n * G + slab * 4) * 2 + threadIdx.x] = tot;
-        s_ab[threadIdx.x] = tot;
+        s_tot[threadIdx.x] = tot;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const double inv = 1.0 / ((double)HW * (double)cpg) * (1.0 / 1048576.0);
+        const double m = (double)(long long)s_tot[2 * threadIdx.x] * inv, q = (double)(long long)s_tot[2 * threadIdx.x + 1] * inv;
+        s_ab[2 * threadIdx.x] = (float)m;
+        s_ab[2 * threadIdx.x + 1] = rsqrtf((float)fmax(q - m * m, 0.0) + eps);
     }
     __syncthreads();
     // per-channel scale / shift of the slab -> shared memory (behind the data block)
@@ -256,18 +290,15 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g
     float* s_b = s_a + 4 * cpg;
     const int c_slab0 = slab * 4 * cpg;
     {
-        const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
         for (int cl = threadIdx.x; cl < 4 * cpg; cl += GN_THREADS) {
             const int g = cl / cpg;
-            const float mean = s_ab[2 * g] * inv_cnt;
-            const float var = fmaxf(s_ab[2 * g + 1] * inv_cnt - mean * mean, 0.f);
-            const float a = rsqrtf(var + eps) * gamma[c_slab0 + cl];
+            const float a = s_ab[2 * g + 1] * gamma[c_slab0 + cl];
             s_a[cl] = a;
-            s_b[cl] = beta[c_slab0 + cl] - mean * a;
+            s_b[cl] = beta[c_slab0 + cl] - s_ab[2 * g] * a;
         }
     }
     __syncthreads();
-    bf8* yp = reinterpret_cast<bf8*>(y + (size_t)n * HW * C);
+    h8* yp = reinterpret_cast<h8*>(y + (size_t)n * HW * C);
     for (int i = threadIdx.x; i < nvec; i += GN_THREADS) {
         const int r = i / sc8, cv = i - r * sc8;
         float f[8];
@@ -290,35 +321,36 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g
 // 16-byte loads in flight); with a = rstd*gamma, b = beta - mean*a:   z = a x + b,  dz = dy * act'(z).
 // Pass 1: per-(n,g) sums of (gamma*dz) and (gamma*dz*xhat).
 __global__ void __launch_bounds__(256)
-gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ bstats,
+gn_bwd_stats_kernel(const act_t* __restrict__ x, const act_t* __restrict__ dy, const fix_t* __restrict__ stats,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, fix_t* __restrict__ bstats,
                     int HW, int C, int G, float eps, int do_silu, int rows_per_cta) {
     pdl_wait();
     pdl_trigger();
-    extern __shared__ float s_bins[];
+    extern __shared__ fix_t s_bins[];
     const int n = blockIdx.y;
     const int cpg = C / G, c8 = C / 8;
-    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_bins[i] = 0.f;
+    const double inv_cnt = 1.0 / ((double)HW * (double)cpg);
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_bins[i] = 0ull;
     __syncthreads();
     const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
-    const bf8* xp = reinterpret_cast<const bf8*>(x + (size_t)n * HW * C);
-    const bf8* dp = reinterpret_cast<const bf8*>(dy + (size_t)n * HW * C);
+    const h8* xp = reinterpret_cast<const h8*>(x + (size_t)n * HW * C);
+    const h8* dp = reinterpret_cast<const h8*>(dy + (size_t)n * HW * C);
     const int rp = c8 <= 256 ? 256 / c8 : 1;
     const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
     for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
         float s1[8], s2[8], a[8], b[8], rs[8], mr[8], gm[8];
+        int g_prev = -1;
+        float mean = 0.f, rstd = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int c = cv * 8 + i, g = c / cpg;
             s1[i] = 0.f; s2[i] = 0.f;
-            const float mean = stats[((size_t)n * G + g) * 2] * inv_cnt;
-            const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
-            rs[i] = rsqrtf(var + eps); mr[i] = -mean * rs[i];
+            if (g != g_prev) { gn_moments(stats, (size_t)n * G + g, inv_cnt, eps, mean, rstd); g_prev = g; }
+            rs[i] = rstd; mr[i] = -mean * rs[i];
             gm[i] = gamma[c];
             a[i] = rs[i] * gm[i]; b[i] = beta[c] - mean * a[i];
         }
-        auto accum = [&](const bf8& xv, const bf8& dv) {
+        auto accum = [&](const h8& xv, const h8& dv) {
             float f[8], d[8];
             unpack8(xv, f);
             unpack8(dv, d);
@@ -332,7 +364,7 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
         };
         int r = row0 + rl;
         for (; r + 3 * rp < row1; r += 4 * rp) {
-            bf8 xv[4], dv[4];
+            h8 xv[4], dv[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) { xv[u] = xp[(size_t)(r + u * rp) * c8 + cv]; dv[u] = dp[(size_t)(r + u * rp) * c8 + cv]; }
 #pragma unroll
@@ -344,14 +376,14 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
 #pragma unroll
             for (int i = 0; i < 8; i++) { u += s1[i]; v += s2[i]; }
             const int g = (cv * 8) / cpg;
-            atomicAdd(&s_bins[2 * g], u);
-            atomicAdd(&s_bins[2 * g + 1], v);
+            atomicAdd(&s_bins[2 * g], to_fix(u, kFixBwd));
+            atomicAdd(&s_bins[2 * g + 1], to_fix(v, kFixBwd));
         } else {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int g = (cv * 8 + i) / cpg;
-                atomicAdd(&s_bins[2 * g], s1[i]);
-                atomicAdd(&s_bins[2 * g + 1], s2[i]);
+                atomicAdd(&s_bins[2 * g], to_fix(s1[i], kFixBwd));
+                atomicAdd(&s_bins[2 * g + 1], to_fix(s2[i], kFixBwd));
             }
         }
     }
@@ -367,30 +399,30 @@ __device__ __forceinline__ uint4 gn_bwd_one(uint4 xv, uint4 dv, uint4 av, bool h
     uint32_t ow[4];
 #pragma unroll
     for (int h = 0; h < 4; h++) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[h]));
-        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[h]));
-        const float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[h]));
+        const float2 f = act2_to_f2(*reinterpret_cast<const act2_t*>(&xw[h]));
+        const float2 d = act2_to_f2(*reinterpret_cast<const act2_t*>(&dw[h]));
+        const float2 e = act2_to_f2(*reinterpret_cast<const act2_t*>(&aw[h]));
         float dz0 = d.x, dz1 = d.y;
         if (do_silu) { dz0 *= silu_grad(fmaf(f.x, a[2 * h], b[2 * h])); dz1 *= silu_grad(fmaf(f.y, a[2 * h + 1], b[2 * h + 1])); }
         float o0 = fmaf(a[2 * h], dz0, fmaf(f.x, k3[2 * h], k4[2 * h]));
         float o1 = fmaf(a[2 * h + 1], dz1, fmaf(f.y, k3[2 * h + 1], k4[2 * h + 1]));
         if (has_add) { o0 += e.x; o1 += e.y; }
-        const __nv_bfloat162 o = __floats2bfloat162_rn(o0, o1);
+        const act2_t o = f2_to_act2(o0, o1);
         ow[h] = *reinterpret_cast<const uint32_t*>(&o);
     }
     return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
 __global__ void __launch_bounds__(256)
-gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
-                    const float* __restrict__ bstats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const __nv_bfloat16* __restrict__ dx_add, __nv_bfloat16* __restrict__ dx, int HW, int C, int G, float eps,
+gn_bwd_apply_kernel(const act_t* __restrict__ x, const act_t* __restrict__ dy, const fix_t* __restrict__ stats,
+                    const fix_t* __restrict__ bstats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const act_t* __restrict__ dx_add, act_t* __restrict__ dx, int HW, int C, int G, float eps,
                     int do_silu, int rows_per_cta) {
     pdl_wait();
     pdl_trigger();
     const int n = blockIdx.y;
     const int c8 = C / 8, cpg = C / G;
-    const float inv_cnt = 1.0f / ((float)HW * (float)cpg);
+    const double inv_cnt = 1.0 / ((double)HW * (double)cpg);
     const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
     const size_t base = (size_t)n * HW * C;
     const uint4* xp = reinterpret_cast<const uint4*>(x + base);
@@ -402,13 +434,17 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
     for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
         float a[8], b[8], k3[8], k4[8];
+        int g_prev = -1;
+        float mean = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int c = cv * 8 + i, g = c / cpg;
-            const float mean = stats[((size_t)n * G + g) * 2] * inv_cnt;
-            const float var = fmaxf(stats[((size_t)n * G + g) * 2 + 1] * inv_cnt - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + eps);
-            const float m1 = bstats[((size_t)n * G + g) * 2] * inv_cnt, m2 = bstats[((size_t)n * G + g) * 2 + 1] * inv_cnt;
+            if (g != g_prev) {
+                gn_moments(stats, (size_t)n * G + g, inv_cnt, eps, mean, rstd);
+                m1 = (float)from_fix(bstats[((size_t)n * G + g) * 2], inv_cnt * (1.0 / 68719476736.0));
+                m2 = (float)from_fix(bstats[((size_t)n * G + g) * 2 + 1], inv_cnt * (1.0 / 68719476736.0));
+                g_prev = g;
+            }
             a[i] = rstd * gamma[c]; b[i] = beta[c] - mean * a[i];
             k3[i] = -rstd * rstd * m2; k4[i] = rstd * (rstd * m2 * mean - m1);
         }
@@ -434,18 +470,18 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
 
 // ---------------------------------------------------------------------------- LayerNorm (one warp per row)
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps) {
+layernorm_kernel(const act_t* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 act_t* __restrict__ y, int64_t rows, int C, float eps) {
     pdl_wait();
     pdl_trigger();
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, c8 = C / 8;
-    const bf8* xp = reinterpret_cast<const bf8*>(x + row * C);
-    bf8* yp = reinterpret_cast<bf8*>(y + row * C);
+    const h8* xp = reinterpret_cast<const h8*>(x + row * C);
+    h8* yp = reinterpret_cast<h8*>(y + row * C);
     constexpr int MAXV = 5;                            // C <= 1280 stays in registers (all loads issued up front)
     if (c8 <= MAXV * 32) {
-        bf8 v[MAXV];
+        h8 v[MAXV];
 #pragma unroll
         for (int u = 0; u < MAXV; u++) if (lane + u * 32 < c8) v[u] = xp[lane + u * 32];
         float s = 0.f, ss = 0.f;
@@ -497,16 +533,16 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 // ---------------------------------------------------------------------------- row softmax (bf16, in place)
 // rows x cols_pad (cols valid, the padding columns are written as 0); one CTA per row.
 __global__ void __launch_bounds__(256)
-softmax_kernel(__nv_bfloat16* __restrict__ s, int cols, int cols_pad) {
+softmax_kernel(act_t* __restrict__ s, int cols, int cols_pad) {
     pdl_wait();
     pdl_trigger();
     __shared__ float red[8];
-    __nv_bfloat16* row = s + (size_t)blockIdx.x * cols_pad;
+    act_t* row = s + (size_t)blockIdx.x * cols_pad;
     const int c8 = cols_pad / 8;
     float mx = -INFINITY;
     for (int v = threadIdx.x; v < c8; v += blockDim.x) {
         float f[8];
-        unpack8(reinterpret_cast<const bf8*>(row)[v], f);
+        unpack8(reinterpret_cast<const h8*>(row)[v], f);
 #pragma unroll
         for (int i = 0; i < 8; i++) if (v * 8 + i < cols) mx = fmaxf(mx, f[i]);
     }
@@ -520,7 +556,7 @@ softmax_kernel(__nv_bfloat16* __restrict__ s, int cols, int cols_pad) {
     float sum = 0.f;
     for (int v = threadIdx.x; v < c8; v += blockDim.x) {
         float f[8];
-        unpack8(reinterpret_cast<const bf8*>(row)[v], f);
+        unpack8(reinterpret_cast<const h8*>(row)[v], f);
 #pragma unroll
         for (int i = 0; i < 8; i++) if (v * 8 + i < cols) sum += __expf(f[i] - mx);
     }
@@ -533,26 +569,26 @@ softmax_kernel(__nv_bfloat16* __restrict__ s, int cols, int cols_pad) {
     const float inv = 1.0f / sum;
     for (int v = threadIdx.x; v < c8; v += blockDim.x) {
         float f[8];
-        unpack8(reinterpret_cast<const bf8*>(row)[v], f);
+        unpack8(reinterpret_cast<const h8*>(row)[v], f);
 #pragma unroll
         for (int i = 0; i < 8; i++) f[i] = (v * 8 + i < cols) ? __expf(f[i] - mx) * inv : 0.f;
-        reinterpret_cast<bf8*>(row)[v] = pack8(f);
+        reinterpret_cast<h8*>(row)[v] = pack8(f);
     }
 }
 
 // short rows (cols_pad <= 256): one warp per row, 8 rows per CTA
 __global__ void __launch_bounds__(256)
-softmax_warp_kernel(__nv_bfloat16* __restrict__ s, int64_t rows, int cols, int cols_pad) {
+softmax_warp_kernel(act_t* __restrict__ s, int64_t rows, int cols, int cols_pad) {
     pdl_wait();
     pdl_trigger();
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= rows) return;
     const int lane = threadIdx.x & 31;
-    __nv_bfloat16* row = s + (size_t)r * cols_pad;
+    act_t* row = s + (size_t)r * cols_pad;
     const int c8 = cols_pad / 8;
     float f[8];
     const bool act = lane < c8;
-    if (act) unpack8(reinterpret_cast<const bf8*>(row)[lane], f);
+    if (act) unpack8(reinterpret_cast<const h8*>(row)[lane], f);
     float mx = -INFINITY;
     if (act) {
 #pragma unroll
@@ -569,24 +605,24 @@ softmax_warp_kernel(__nv_bfloat16* __restrict__ s, int64_t rows, int cols, int c
         const float inv = 1.0f / sum;
 #pragma unroll
         for (int i = 0; i < 8; i++) f[i] *= inv;
-        reinterpret_cast<bf8*>(row)[lane] = pack8(f);
+        reinterpret_cast<h8*>(row)[lane] = pack8(f);
     }
 }
 
 // softmax backward in place on dP -> dS:  dS = P * (dP - sum(dP*P))      (VAE mid attention)
 __global__ void __launch_bounds__(256)
-softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ dp, int cols_pad) {
+softmax_bwd_kernel(const act_t* __restrict__ p, act_t* __restrict__ dp, int cols_pad) {
     pdl_wait();
     pdl_trigger();
     __shared__ float red[8];
-    const __nv_bfloat16* pr = p + (size_t)blockIdx.x * cols_pad;
-    __nv_bfloat16* dr = dp + (size_t)blockIdx.x * cols_pad;
+    const act_t* pr = p + (size_t)blockIdx.x * cols_pad;
+    act_t* dr = dp + (size_t)blockIdx.x * cols_pad;
     const int c8 = cols_pad / 8;
     float dot = 0.f;
     for (int v = threadIdx.x; v < c8; v += blockDim.x) {
         float a[8], b[8];
-        unpack8(reinterpret_cast<const bf8*>(pr)[v], a);
-        unpack8(reinterpret_cast<const bf8*>(dr)[v], b);
+        unpack8(reinterpret_cast<const h8*>(pr)[v], a);
+        unpack8(reinterpret_cast<const h8*>(dr)[v], b);
 #pragma unroll
         for (int i = 0; i < 8; i++) dot += a[i] * b[i];
     }
@@ -598,17 +634,17 @@ softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restric
     for (int w = 0; w < 8; w++) dot += red[w];
     for (int v = threadIdx.x; v < c8; v += blockDim.x) {
         float a[8], b[8];
-        unpack8(reinterpret_cast<const bf8*>(pr)[v], a);
-        unpack8(reinterpret_cast<const bf8*>(dr)[v], b);
+        unpack8(reinterpret_cast<const h8*>(pr)[v], a);
+        unpack8(reinterpret_cast<const h8*>(dr)[v], b);
 #pragma unroll
         for (int i = 0; i < 8; i++) b[i] = a[i] * (b[i] - dot);
-        reinterpret_cast<bf8*>(dr)[v] = pack8(b);
+        reinterpret_cast<h8*>(dr)[v] = pack8(b);
     }
 }
 
 // ---------------------------------------------------------------------------- GEGLU: y = a * gelu(b), x = [rows, 2*inner]
 __global__ void __launch_bounds__(256)
-geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t rows, int inner) {
+geglu_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, int64_t rows, int inner) {
     pdl_wait();
     pdl_trigger();
     const int i8 = inner / 8;
@@ -617,28 +653,28 @@ geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
         const int64_t r = v / i8;
         const int cv = (int)(v % i8);
         float a[8], b[8];
-        unpack8(reinterpret_cast<const bf8*>(x + r * 2 * inner)[cv], a);
-        unpack8(reinterpret_cast<const bf8*>(x + r * 2 * inner + inner)[cv], b);
+        unpack8(reinterpret_cast<const h8*>(x + r * 2 * inner)[cv], a);
+        unpack8(reinterpret_cast<const h8*>(x + r * 2 * inner + inner)[cv], b);
 #pragma unroll
         for (int i = 0; i < 8; i++) a[i] *= 0.5f * b[i] * (1.0f + erff(b[i] * 0.70710678118654752f));
-        reinterpret_cast<bf8*>(y + r * inner)[cv] = pack8(a);
+        reinterpret_cast<h8*>(y + r * inner)[cv] = pack8(a);
     }
 }
 
 // ---------------------------------------------------------------------------- elementwise helpers
 // mode 0: y = silu(x); mode 1: y = x + a; mode 2: dy * silu'(x)
 __global__ void __launch_bounds__(256)
-eltwise_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ y,
+eltwise_kernel(const act_t* __restrict__ x, const act_t* __restrict__ a, act_t* __restrict__ y,
                int64_t n8, int mode) {
     pdl_wait();
     pdl_trigger();
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n8; v += (int64_t)gridDim.x * blockDim.x) {
         float f[8], g[8];
-        unpack8(reinterpret_cast<const bf8*>(x)[v], f);
-        if (mode != 0) unpack8(reinterpret_cast<const bf8*>(a)[v], g);
+        unpack8(reinterpret_cast<const h8*>(x)[v], f);
+        if (mode != 0) unpack8(reinterpret_cast<const h8*>(a)[v], g);
 #pragma unroll
         for (int i = 0; i < 8; i++) f[i] = mode == 0 ? silu(f[i]) : (mode == 1 ? f[i] + g[i] : g[i] * silu_grad(f[i]));
-        reinterpret_cast<bf8*>(y)[v] = pack8(f);
+        reinterpret_cast<h8*>(y)[v] = pack8(f);
     }
 }
 
@@ -663,7 +699,7 @@ static inline unsigned grid_for(int64_t work, int threads) {
 
 using namespace dwg;
 using namespace dwg::nn;
-typedef __nv_bfloat16 bf16;
+typedef act_t h16;
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static int g_gn_last_launches = 2;
@@ -675,10 +711,11 @@ extern "C" int dwg_groupnorm_set_fused(int on) { g_gn_fused = on ? 1 : 0; return
 /* kernels the last dwg_groupnorm_fwd call launched: 1 (one-launch cluster kernel) or 2 (stats + apply) */
 extern "C" int dwg_groupnorm_last_launches(void) { return g_gn_last_launches; }
 
-extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
+extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, void* stats_,
                                  int N, int HW, int C, int G, float eps, int do_silu, void* stream) {
+    fix_t* stats = reinterpret_cast<fix_t*>(stats_);
     DWG_REQUIRE(x && gamma && beta && y && stats, "null pointer");
-    DWG_REQUIRE(C % 8 == 0 && C % G == 0 && al16(x) && al16(y), "C must be a multiple of 8 and of G; 16-byte aligned tensors");
+    DWG_REQUIRE(C % 8 == 0 && C % G == 0 && al16(x) && al16(y) && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, "C must be a multiple of 8 and of G; 16-byte aligned tensors");
     cudaStream_t st = (cudaStream_t)stream;
     // one-launch cluster kernel when the (image, 4-group slab) block fits the shared memory of 8 CTAs
     {
@@ -699,75 +736,77 @@ extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float*
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-            cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const bf16*)x, gamma, beta, (bf16*)y, stats, HW, C, G, eps, do_silu, rows_c);
+            cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const h16*)x, gamma, beta, (h16*)y, stats, HW, C, G, eps, do_silu, rows_c);
             g_gn_last_launches = 1;
             return check_launch("dwg_groupnorm_fwd (fused)");
         }
     }
     g_gn_last_launches = 2;
-    cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, st);
+    cudaMemsetAsync(stats, 0, sizeof(fix_t) * 2 * N * G, st);
     const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;        // row lanes per CTA
     int rows_per_cta = (int)(((int64_t)N * HW + 4 * kNumSMs - 1) / (4 * kNumSMs));      // ~4 CTAs per SM
     if (rows_per_cta < 4 * rp_) rows_per_cta = 4 * rp_;
     if (rows_per_cta > 64 * rp_) rows_per_cta = 64 * rp_;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
-    launch_pdl(gn_stats_kernel, grid, dim3(256), sizeof(float) * 2 * G, st, (const bf16*)x, stats, HW, C, G, rows_per_cta);
+    launch_pdl(gn_stats_kernel, grid, dim3(256), sizeof(fix_t) * 2 * G, st, (const h16*)x, stats, HW, C, G, rows_per_cta);
     int rows_apply = rows_per_cta;
     dim3 grid2((HW + rows_apply - 1) / rows_apply, N);
-    launch_pdl(gn_apply_kernel, grid2, dim3(256), 0, st, (const bf16*)x, (const float*)stats, gamma, beta, (bf16*)y, HW, C, G, eps, do_silu, rows_apply);
+    launch_pdl(gn_apply_kernel, grid2, dim3(256), 0, st, (const h16*)x, (const fix_t*)stats, gamma, beta, (h16*)y, HW, C, G, eps, do_silu, rows_apply);
     return check_launch("dwg_groupnorm_fwd");
 }
 
-extern "C" int dwg_groupnorm_bwd(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta,
-                                 const void* dx_add, void* dx, float* bstats, int N, int HW, int C, int G, float eps,
+extern "C" int dwg_groupnorm_bwd(const void* x, const void* dy, const void* stats_, const float* gamma, const float* beta,
+                                 const void* dx_add, void* dx, void* bstats_, int N, int HW, int C, int G, float eps,
                                  int do_silu, void* stream) {
+    const fix_t* stats = reinterpret_cast<const fix_t*>(stats_);
+    fix_t* bstats = reinterpret_cast<fix_t*>(bstats_);
     DWG_REQUIRE(x && dy && stats && gamma && beta && dx && bstats, "null pointer");
     DWG_REQUIRE(C % 8 == 0 && C % G == 0, "C must be a multiple of 8 and of G");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * N * G, st);
+    cudaMemsetAsync(bstats, 0, sizeof(fix_t) * 2 * N * G, st);
     const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;        // row lanes per CTA
     int rows_per_cta = (int)(((int64_t)N * HW + 6 * kNumSMs - 1) / (6 * kNumSMs));      // ~6 CTAs per SM
     if (rows_per_cta < 4 * rp_) rows_per_cta = 4 * rp_;
     if (rows_per_cta > 64 * rp_) rows_per_cta = 64 * rp_;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
-    launch_pdl(gn_bwd_stats_kernel, grid, dim3(256), sizeof(float) * 2 * G, st, (const bf16*)x, (const bf16*)dy, stats, gamma, beta, bstats,
+    launch_pdl(gn_bwd_stats_kernel, grid, dim3(256), sizeof(fix_t) * 2 * G, st, (const h16*)x, (const h16*)dy, stats, gamma, beta, bstats,
                HW, C, G, eps, do_silu, rows_per_cta);
-    launch_pdl(gn_bwd_apply_kernel, grid, dim3(256), 0, st, (const bf16*)x, (const bf16*)dy, stats, (const float*)bstats, gamma, beta,
-               (const bf16*)dx_add, (bf16*)dx, HW, C, G, eps, do_silu, rows_per_cta);
+    launch_pdl(gn_bwd_apply_kernel, grid, dim3(256), 0, st, (const h16*)x, (const h16*)dy, stats, (const fix_t*)bstats, gamma, beta,
+               (const h16*)dx_add, (h16*)dx, HW, C, G, eps, do_silu, rows_per_cta);
     return check_launch("dwg_groupnorm_bwd");
 }
 
 extern "C" int dwg_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps, void* stream) {
     DWG_REQUIRE(x && gamma && beta && y && C % 8 == 0, "bad arguments");
-    launch_pdl(layernorm_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, gamma, beta, (bf16*)y, rows, C, eps);
+    launch_pdl(layernorm_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, (const h16*)x, gamma, beta, (h16*)y, rows, C, eps);
     return check_launch("dwg_layernorm_fwd");
 }
 
 extern "C" int dwg_softmax_rows(void* s, int64_t rows, int cols, int cols_pad, void* stream) {
     DWG_REQUIRE(s && cols > 0 && cols_pad >= cols && cols_pad % 8 == 0 && rows < (1ll << 31), "bad arguments");
     if (cols_pad <= 256)
-        softmax_warp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((bf16*)s, rows, cols, cols_pad);
+        softmax_warp_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((h16*)s, rows, cols, cols_pad);
     else
-        softmax_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((bf16*)s, cols, cols_pad);
+        softmax_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((h16*)s, cols, cols_pad);
     return check_launch("dwg_softmax_rows");
 }
 
 extern "C" int dwg_softmax_rows_bwd(const void* p, void* dp, int64_t rows, int cols_pad, void* stream) {
     DWG_REQUIRE(p && dp && cols_pad % 8 == 0 && rows < (1ll << 31), "bad arguments");
-    softmax_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)p, (bf16*)dp, cols_pad);
+    softmax_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const h16*)p, (h16*)dp, cols_pad);
     return check_launch("dwg_softmax_rows_bwd");
 }
 
 extern "C" int dwg_geglu(const void* x, void* y, int64_t rows, int inner, void* stream) {
     DWG_REQUIRE(x && y && inner % 8 == 0, "bad arguments");
-    launch_pdl(geglu_kernel, dim3(grid_for(rows * (inner / 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, rows, inner);
+    launch_pdl(geglu_kernel, dim3(grid_for(rows * (inner / 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const h16*)x, (h16*)y, rows, inner);
     return check_launch("dwg_geglu");
 }
 
-extern "C" int dwg_eltwise_bf16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream) {
+extern "C" int dwg_eltwise_f16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream) {
     DWG_REQUIRE(x && y && n % 8 == 0 && mode >= 0 && mode <= 2 && (mode == 0 || a), "bad arguments");
-    launch_pdl(eltwise_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)a, (bf16*)y, n / 8, mode);
-    return check_launch("dwg_eltwise_bf16");
+    launch_pdl(eltwise_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, (const h16*)x, (const h16*)a, (h16*)y, n / 8, mode);
+    return check_launch("dwg_eltwise_f16");
 }
 
 extern "C" int dwg_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float* grad, float* noise_pred,

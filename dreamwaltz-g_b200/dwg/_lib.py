@@ -33,6 +33,7 @@ SIGNATURES = {
     'dwg_sh_eval_fwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'dwg_sh_eval_bwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_void_p]),
+    'dwg_grid_level_table': (c_int, [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'dwg_grid_encode_fwd': (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                     c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     'dwg_grid_encode_bwd': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
@@ -46,7 +47,7 @@ SIGNATURES = {
     'dwg_raster_backward': (c_int, [ctypes.POINTER(DwgRasterCamera), c_int64] + [c_void_p] * 5 +
                             [c_void_p, c_void_p, c_int64, c_void_p] + [c_void_p] * 3 + [c_void_p] * 6 +
                             [c_void_p, c_void_p, c_void_p]),
-    'dwg_gemm_bf16': (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
+    'dwg_gemm_f16': (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                               c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_float, c_int, c_void_p]),
     'dwg_avatar_mlp_param_count': (c_int64, []),
@@ -62,7 +63,7 @@ SIGNATURES = {
     'dwg_gemm_last_key': (c_int, [c_void_p]),
     'dwg_gemm_trace': (c_int, [c_void_p]),
     'dwg_gemm_set_lane': (c_int, [c_int]),
-    'dwg_conv2d_nhwc_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 11 +
+    'dwg_conv2d_nhwc_f16': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 11 +
                              [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'dwg_groupnorm_last_launches': (c_int, []),
     'dwg_groupnorm_set_fused': (c_int, [c_int]),
@@ -72,7 +73,7 @@ SIGNATURES = {
     'dwg_softmax_rows': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p]),
     'dwg_softmax_rows_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'dwg_geglu': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
-    'dwg_eltwise_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'dwg_eltwise_f16': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'dwg_sds_grad': (c_int, [c_void_p] * 5 + [c_float, c_float, c_int64, c_void_p]),
     'dwg_attention_fwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_void_p]),
@@ -99,9 +100,9 @@ def lib():
 KERNELS_PER_CALL = {
     'dwg_lbs_skin_fwd': 1, 'dwg_lbs_skin_bwd': 1, 'dwg_sh_eval_fwd': 1, 'dwg_sh_eval_bwd': 1,
     'dwg_grid_encode_fwd': 1, 'dwg_grid_encode_bwd': 1, 'dwg_avatar_mlp_fwd': 1, 'dwg_avatar_mlp_bwd': 2, 'dwg_raster_forward': 12, 'dwg_raster_backward': 2,
-    'dwg_gemm_bf16': 1, 'dwg_conv2d_nhwc_bf16': 1, 'dwg_groupnorm_fwd': 2, 'dwg_groupnorm_bwd': 2,
+    'dwg_gemm_f16': 1, 'dwg_conv2d_nhwc_f16': 1, 'dwg_groupnorm_fwd': 2, 'dwg_groupnorm_bwd': 2,
     'dwg_layernorm_fwd': 1, 'dwg_softmax_rows': 1, 'dwg_softmax_rows_bwd': 1, 'dwg_geglu': 1,
-    'dwg_eltwise_bf16': 1, 'dwg_sds_grad': 1, 'dwg_attention_fwd': 1,
+    'dwg_eltwise_f16': 1, 'dwg_sds_grad': 1, 'dwg_attention_fwd': 1,
 }
 
 

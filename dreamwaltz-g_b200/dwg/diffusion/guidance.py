@@ -9,7 +9,9 @@ stays on the device.
 """
 import os
 
+import numpy as np
 import torch
+import torch.nn.functional as F
 
 from .. import ops
 from . import model as M
@@ -39,15 +41,18 @@ class ControlNetScoreDistillation:
     """SD1.5 + ControlNet(openpose) score distillation on dwg kernels."""
 
     def __init__(self, unet_sd, controlnet_sd, vae_sd, cfg=Wt.SD15, vae_cfg=Wt.VAE15, device='cuda', guidance_scale=50.0,
-                 conditioning_scale=1.0, min_timestep=0.02, max_timestep=0.98, seed=0):
+                 conditioning_scale=1.0, min_timestep=0.02, max_timestep=0.98, seed=0, default_image_size=512, input_interpolate=True,
+                 guidance_adjust='constant'):
         self.device = device
         self.unet = M.UNet(unet_sd, cfg, device)
         self.controlnet = M.ControlNet(controlnet_sd, cfg, device)
         self.vae = M.VAEEncoder(vae_sd, vae_cfg, device)
         self.guidance_scale, self.conditioning_scale = guidance_scale, conditioning_scale
+        self.initial_guidance_scale, self.guidance_adjust = guidance_scale, guidance_adjust
         self.acp = alphas_cumprod(device)
         self.t_lo, self.t_hi = int(min_timestep * 1000), int(max_timestep * 1000)
-        self.default_image_size = 512
+        self.default_image_size = default_image_size     # 512 (SD1.5) / 768 (SD2.1), basic.py:296-300
+        self.input_interpolate = input_interpolate       # basic.py:360-362
         self.vae_scale_factor = 8
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(seed)
@@ -139,7 +144,10 @@ class ControlNetScoreDistillation:
         the rendered image -- the timestep draw, both networks' time-embedding projections and cross-attention
         K / V, the ControlNet condition embedding -- is enqueued on the second stream, to run while the caller
         animates and rasterises the avatar.  The next __call__ consumes it (same timestep semantics)."""
-        if not self.two_streams or os.environ.get('DWG_NO_PREPARE') == '1':
+        # Under enable_graphs() the prediction is a replay of a captured graph that does its own (captured) preparation:
+        # eager work enqueued here would never be consumed and its lane-1 split-K scratch could race the replay.
+        if not self.two_streams or os.environ.get('DWG_NO_PREPARE') == '1' or getattr(self, '_g', None):
+            self._prepared = None
             return
         main = torch.cuda.current_stream()
         if self._side is None:
@@ -155,7 +163,7 @@ class ControlNetScoreDistillation:
                 pre_u = self.unet.prepare(t, ctx, ctx.shape[0])
             finally:
                 ops.gemm_lane(0)
-        self._prepared = {'t': t, 'ctx': ctx, 'controlnet': pre_c, 'unet': pre_u}
+        self._prepared = {'t': t, 'ctx': ctx, 'controlnet': pre_c, 'unet': pre_u, 'embeds': (neg, text_embeds_dict['text']), 'cond': cond_inputs}
 
     def _controlnet_unet(self, x2, ctx, cond):
         """ControlNet and the UNet encoder + mid block are independent until the residuals are added
@@ -200,26 +208,57 @@ class ControlNetScoreDistillation:
         a = self.acp[t].reshape(-1, 1, 1, 1)
         return a.sqrt() * latents + (1 - a).sqrt() * noise
 
+    def get_guidance_scale(self, train_step, max_iteration):
+        """basic.py:404-418."""
+        s0 = self.initial_guidance_scale
+        if self.guidance_adjust == 'constant':
+            return s0
+        if self.guidance_adjust == 'uniform':
+            return float(np.random.uniform(7.5, s0))
+        delta = (s0 - 7.5) / max(max_iteration - 1, 1)
+        if self.guidance_adjust == 'linear':
+            return s0 - (train_step - 1) * delta
+        if self.guidance_adjust == 'linear_reverse':
+            return 7.5 + (train_step - 1) * delta
+        raise NotImplementedError(self.guidance_adjust)
+
+    def prepare_latents(self, inputs):
+        """basic.py:354-383: a 3-channel render that is not default_image_size^2 is resized bilinearly
+        (align_corners=False, differentiable) before the VAE; cfg4 renders 1024^2 and feeds SD2.1 at 768^2."""
+        size = (self.default_image_size, self.default_image_size)
+        if self.input_interpolate and tuple(inputs.shape[-2:]) != size:
+            inputs = F.interpolate(inputs, size, mode='bilinear', align_corners=False)
+        assert inputs.shape[-2] % 8 == 0 and inputs.shape[-1] % 8 == 0, 'image size must be a multiple of the VAE factor 8'
+        return inputs
+
     def __call__(self, inputs, text_embeds_dict, train_step=0, max_iteration=1, cond_inputs=None, timestep=None, noise=None,
-                 vae_eps=None, use_negative_text=True, **_):
-        """inputs [1,3,H,W] in [0,1] (autograd-connected); cond_inputs [1,3,512,512] in [0,1] (device tensor).
+                 vae_eps=None, use_negative_text=True, guidance_scale=None, **_):
+        """inputs [1,3,H,W] in [0,1] (autograd-connected); cond_inputs [1,3,S,S] in [0,1] (device tensor).
         Returns the reference's dict: latents, timestep, sources, targets, gradients, diffusion_loss."""
-        assert inputs.dim() == 4 and inputs.shape[1] == 3 and inputs.shape[-2] % 8 == 0 and inputs.shape[-1] % 8 == 0, \
-            'inputs must be [B,3,H,W] with H, W multiples of the VAE factor 8 (basic.py:354-366 resizes to 512 when needed)'
+        assert inputs.dim() == 4 and inputs.shape[1] == 3, 'inputs must be [B,3,H,W]'
+        inputs = self.prepare_latents(inputs)
+        self.guidance_scale = guidance_scale if guidance_scale is not None else self.get_guidance_scale(train_step, max_iteration)
         latents = self.encode_images(inputs, vae_eps)
-        if self._prepared is not None and timestep is None:
-            self.timestep = self._prepared['t']                 # drawn by prepare()
+        neg = text_embeds_dict['neg' if use_negative_text else 'null']
+        prep = self._prepared
+        if prep is not None and timestep is None and not getattr(self, '_g', None):
+            # prepare() results are only valid for the inputs they were made from
+            assert prep['embeds'][0] is neg and prep['embeds'][1] is text_embeds_dict['text'] and prep['cond'] is cond_inputs, \
+                'prepare() was called with other prompt embeddings / condition than this __call__'
+            self.timestep = prep['t']                           # drawn by prepare()
         else:
+            if prep is not None and self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)      # discard: join the side stream so nothing stays in flight
             self._prepared = None
             self.timestep = timestep if timestep is not None else self.get_timestep(inputs.shape[0])
         with torch.no_grad():
             if noise is None:
                 noise = torch.randn(latents.shape, device=latents.device, generator=None if self.use_default_generator else self.gen)
             latents_noisy = self.add_noise(latents.detach(), noise, self.timestep)
-            neg = text_embeds_dict['neg' if use_negative_text else 'null']
             ctx = torch.cat([neg, text_embeds_dict['text']], dim=0)
             x2 = torch.cat([latents_noisy] * 2, dim=0)
             eps = self._predict(x2, ctx, cond_inputs)
+            self._prepared = None                              # consumed (or never used): a later call must not see it
             e_u, e_c = eps.chunk(2)
             gradients, noise_pred = ops.sds_grad(e_u.contiguous(), e_c.contiguous(), noise, self.guidance_scale, 1.0)
         loss = SpecifyGradient.apply(latents, gradients)

@@ -1,7 +1,7 @@
 """UNet2DConditionModel / ControlNetModel / AutoencoderKL-encoder on the dwg tcgen05 kernels.
 
 Activations are NHWC bf16 end to end ([B,H,W,C] == token layout [B,HW,C] for free); every conv /
-linear / attention matmul is dwg_gemm_bf16 or dwg_conv2d_nhwc_bf16 (implicit GEMM, TMA-fed
+linear / attention matmul is dwg_gemm_f16 or dwg_conv2d_nhwc_f16 (implicit GEMM, TMA-fed
 tcgen05, fp32 accumulation in TMEM) with bias / time-embedding / residual fused into the
 epilogue; GroupNorm(+SiLU), LayerNorm, softmax, GEGLU are the streaming kernels of nn_kernels.cu.
 torch is used for allocation and pure data movement (cat, pad, nearest upsample, transposes).
@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from .. import ops
 
-BF = torch.bfloat16
+F16 = torch.float16
 
 
 def _pad_c(t, mult=8, dim=-1):
@@ -42,18 +42,18 @@ class Weights:
             if k.endswith('.weight'):
                 name = k[:-7]
                 if v.dim() == 4:
-                    self.w[name] = _pad_c(v.permute(0, 2, 3, 1)).to(BF).contiguous()
+                    self.w[name] = _pad_c(v.permute(0, 2, 3, 1)).to(F16).contiguous()
                     if with_dgrad:
                         # dgrad weights: [Cin, k, k, Cout8] with the taps flipped
-                        self.dg[name] = _pad_c(v.flip(2, 3).permute(1, 2, 3, 0)).to(BF).contiguous()
+                        self.dg[name] = _pad_c(v.flip(2, 3).permute(1, 2, 3, 0)).to(F16).contiguous()
                 elif v.dim() == 2:
                     if name.endswith('.ff.net.0.proj'):
                         # GEGLU projection: interleave (value_i, gate_i) rows so the GEMM epilogue can fuse hidden * gelu(gate)
                         inner = v.shape[0] // 2
                         v = torch.stack([v[:inner], v[inner:]], dim=1).reshape(2 * inner, v.shape[1])
-                    self.w[name] = v.to(BF).contiguous()
+                    self.w[name] = v.to(F16).contiguous()
                     if with_dgrad:
-                        self.dg[name] = v.t().to(BF).contiguous()
+                        self.dg[name] = v.t().to(F16).contiguous()
                 else:
                     self.w[name] = v.contiguous()          # norm scale (fp32)
             elif k.endswith('.bias'):
@@ -66,7 +66,7 @@ class Weights:
         return name in self.w
 
 
-def conv(W, name, x, stride=1, padding=1, bias2=None, residual=None, out_dtype=BF, out_hw=None, use_bias=True):
+def conv(W, name, x, stride=1, padding=1, bias2=None, residual=None, out_dtype=F16, out_hw=None, use_bias=True):
     w = W.w[name]
     if x.shape[-1] != w.shape[-1]:
         x = _pad_c(x)
@@ -74,7 +74,7 @@ def conv(W, name, x, stride=1, padding=1, bias2=None, residual=None, out_dtype=B
                            padding=padding, out_hw=out_hw, out_dtype=out_dtype)
 
 
-def linear(W, name, x2d, residual=None, act=None, out_dtype=BF, alpha=1.0):
+def linear(W, name, x2d, residual=None, act=None, out_dtype=F16, alpha=1.0):
     return ops.gemm(x2d, W.w[name], bias=W.b.get(name), residual=residual, act=act, out_dtype=out_dtype, alpha=alpha)
 
 
@@ -111,19 +111,19 @@ def attention(W, p, x, ctx, heads, residual, kv=None):
     else:
         if k3 is None:
             k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
-        vT = torch.zeros(B, C, Tkp, device=x.device, dtype=BF) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=BF)
+        vT = torch.zeros(B, C, Tkp, device=x.device, dtype=F16) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=F16)
         for b in range(B):
             ops.gemm(W.w[p + '.to_v'], ctx[b], out=vT[b][:, :Tk] if Tkp != Tk else vT[b])
         if (p + '.to_v') in W.b:
-            vT += W.b[p + '.to_v'].to(BF)[None, :, None]
+            vT += W.b[p + '.to_v'].to(F16)[None, :, None]
     if hd <= 128:
         o = ops.attention(q3, k3, vT, heads, Tk)                       # fused: scores never reach HBM
     else:
         q, k = q3.view(B, T, heads, hd).permute(0, 2, 1, 3), k3.view(B, Tk, heads, hd).permute(0, 2, 1, 3)
-        S = torch.empty(B, heads, T, Tkp, device=x.device, dtype=BF)
+        S = torch.empty(B, heads, T, Tkp, device=x.device, dtype=F16)
         ops.gemm(q, k, alpha=hd ** -0.5, out=S[..., :Tk] if Tkp != Tk else S)
         ops.softmax_rows_(S, Tk)
-        o = torch.empty(B, T, C, device=x.device, dtype=BF)
+        o = torch.empty(B, T, C, device=x.device, dtype=F16)
         ops.gemm(S, vT.unflatten(1, (heads, hd)), out=o.view(B, T, heads, hd).permute(0, 2, 1, 3))
     return linear(W, p + '.to_out.0', o.reshape(B * T, C), residual=residual.reshape(B * T, C)).view(B, T, C)
 
@@ -168,7 +168,7 @@ class DiffusionNet:
         Tkp = (Tk + 7) // 8 * 8
         S = self._xattn_total
         K_all = ops.gemm(ctx.reshape(B * Tk, Ck), self._xattn_wk).view(B, Tk, S)
-        vT_all = torch.zeros(B, S, Tkp, device=ctx.device, dtype=BF)
+        vT_all = torch.zeros(B, S, Tkp, device=ctx.device, dtype=F16)
         for b in range(B):
             ops.gemm(self._xattn_wv, ctx[b], out=vT_all[b][:, :Tk])
         return {n: (K_all[:, :, a:c], vT_all[:, a:c, :]) for n, (a, c) in self._xattn_off.items()}
@@ -181,8 +181,8 @@ class DiffusionNet:
         W = self.W
         # TMA boxes that are mostly out of bounds are slow: run the M = B (= 2) GEMMs on a zero-padded
         # 128-row operand and slice the two valid rows afterwards
-        e = torch.zeros(128, self.cfg['block_out'][0], device=t.device, dtype=BF)
-        e[:B] = timestep_embedding(t.reshape(-1).expand(B), self.cfg['block_out'][0]).to(BF)
+        e = torch.zeros(128, self.cfg['block_out'][0], device=t.device, dtype=F16)
+        e[:B] = timestep_embedding(t.reshape(-1).expand(B), self.cfg['block_out'][0]).to(F16)
         e = linear(W, 'time_embedding.linear_1', e, act='silu')
         temb = linear(W, 'time_embedding.linear_2', e)
         tp = ops.gemm(ops.silu(temb), self._tproj_w, bias=self._tproj_b, out_dtype=torch.float32)[:B]      # [B, sum Cout]
@@ -192,7 +192,7 @@ class DiffusionNet:
     def prepare(self, t, ctx, B):
         """Everything that depends only on the timestep and the prompt embeddings (time-embedding projections of
         every resnet, K / V^T of every cross-attention): can be computed while the avatar is still being rendered."""
-        ctx = ctx.to(BF).contiguous()
+        ctx = ctx.to(F16).contiguous()
         return {'tproj': self.time_embed(t, B), 'ctx': ctx, 'ctx_kv': self.project_context(ctx)}
 
     def resnet(self, p, x, tproj):
@@ -238,8 +238,8 @@ class DiffusionNet:
         return self.resnet('mid_block.resnets.1', h, tproj)
 
 
-def to_nhwc_bf16(x_nchw):
-    return _pad_c(x_nchw.permute(0, 2, 3, 1)).to(BF).contiguous()
+def to_nhwc_f16(x_nchw):
+    return _pad_c(x_nchw.permute(0, 2, 3, 1)).to(F16).contiguous()
 
 
 class ControlNet(DiffusionNet):
@@ -247,7 +247,7 @@ class ControlNet(DiffusionNet):
     def embed_condition(self, cond_nchw01):
         """controlnet_cond_embedding of the condition image(s) -> [Bc,h,w,C0] (before the residual add)."""
         W = self.W
-        c = ops.silu(conv(W, 'controlnet_cond_embedding.conv_in', to_nhwc_bf16(cond_nchw01)))
+        c = ops.silu(conv(W, 'controlnet_cond_embedding.conv_in', to_nhwc_f16(cond_nchw01)))
         nblk = 2 * (len(self.cfg['cond_embed']) - 1)
         for k in range(nblk):
             c = ops.silu(conv(W, f'controlnet_cond_embedding.blocks.{k}', c, stride=2 if k % 2 == 1 else 1))
@@ -269,7 +269,7 @@ class ControlNet(DiffusionNet):
             pre = self.prepare(t, ctx, B, cond_nchw01)
         tproj, ctx = pre['tproj'], pre['ctx']
         self._ctx_kv = pre['ctx_kv']
-        h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
+        h = conv(W, 'conv_in', to_nhwc_f16(sample_nchw))
         # condition embedding: with classifier-free guidance the reference feeds the SAME condition image
         # for every sample (controlnet.py:33-55 prepare_image duplicates it); a batch-1 condition is
         # embedded once and added to every sample
@@ -303,7 +303,7 @@ class UNet(DiffusionNet):
             pre = self.prepare(t, ctx, B)
         tproj, ctx = pre['tproj'], pre['ctx']
         self._ctx_kv = pre['ctx_kv']
-        h = conv(W, 'conv_in', to_nhwc_bf16(sample_nchw))
+        h = conv(W, 'conv_in', to_nhwc_f16(sample_nchw))
         h, skips = self.down_path(h, tproj, ctx)
         h = self.mid(h, tproj, ctx)
         return h, skips, tproj, ctx
@@ -373,7 +373,7 @@ class VAEEncoder:
         W, cfg, G = self.W, self.cfg, self.G
         tape = [] if tape is None else tape
         nb = len(cfg['block_out'])
-        x = to_nhwc_bf16(2.0 * images01_nchw - 1.0)
+        x = to_nhwc_f16(2.0 * images01_nchw - 1.0)
         h = conv(W, 'encoder.conv_in', x)
         for i in range(nb):
             for j in range(cfg['layers_per_block']):
@@ -440,7 +440,7 @@ class VAEEncoder:
         gl = g_latents_nchw.float() * cfg['scaling_factor']
         g_mean = gl
         g_logvar = gl * eps * std * 0.5 * unclamped.float()
-        gm = torch.cat([g_mean, g_logvar], dim=1).permute(0, 2, 3, 1).to(BF).contiguous()         # [B,h,w,8]
+        gm = torch.cat([g_mean, g_logvar], dim=1).permute(0, 2, 3, 1).to(F16).contiguous()         # [B,h,w,8]
         g = ops.conv2d_nhwc(gm, W.dg['quant_conv'], padding=0)
         g = self._dgrad('encoder.conv_out', g)
         _, h, st = tape.pop()
@@ -453,7 +453,7 @@ class VAEEncoder:
                 g = self._attn_bwd(rec, g)
             elif rec[0] == 'down':
                 _, name, (Hh, Ww) = rec
-                up = torch.zeros(g.shape[0], Hh, Ww, g.shape[-1], device=g.device, dtype=BF)
+                up = torch.zeros(g.shape[0], Hh, Ww, g.shape[-1], device=g.device, dtype=F16)
                 up[:, ::2, ::2] = g                                       # zero-insertion (data movement)
                 g = ops.conv2d_nhwc(up, W.dg[name], stride=1, padding=(2, 2), out_hw=(Hh, Ww))
         g = self._dgrad('encoder.conv_in', g)                               # [B,H,W,8] (3 valid channels)

@@ -85,8 +85,9 @@ def sh_colors(sh_features, positions, campos, sh_levels):
 # ------------------------------------------------------------------------------ grid encoder
 def grid_level_table(num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
                      desired_resolution=4096, per_level_scale=None, input_dim=3, align_corners=False):
-    """GridEncoder.__init__ (core/nerf/gridencoder/grid.py:104-133) + the per-level kernel
-    constants of gridencoder.cu:138-139, evaluated once on the host in float32."""
+    """GridEncoder.__init__ (core/nerf/gridencoder/grid.py:104-133): level offsets, per_level_scale and
+    S = log2(per_level_scale) as float32 (grid.py:40).  The per-level kernel constants (gridencoder.cu:138-139) are
+    evaluated on the device by device_level_table()."""
     if desired_resolution is not None:
         per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
     offsets, offset = [], 0
@@ -98,29 +99,36 @@ def grid_level_table(num_levels=16, level_dim=2, base_resolution=16, log2_hashma
         offsets.append(offset)
         offset += params
     offsets.append(offset)
-    S = np.float32(np.log2(per_level_scale))
-    lv = np.arange(num_levels, dtype=np.float32)
-    scale = (np.exp2(lv * S).astype(np.float32) * np.float32(base_resolution) - np.float32(1.0)).astype(np.float32)
-    res = (np.ceil(scale).astype(np.uint32) + np.uint32(1)).astype(np.uint32)
-    return np.array(offsets, np.int32), float(per_level_scale), scale, res
+    return np.array(offsets, np.int32), float(per_level_scale), np.float32(np.log2(per_level_scale))
+
+
+def device_level_table(S, H, L, device):
+    """(level_scale f32 [L], level_res i32-bit-pattern-of-u32 [L]) as DEVICE tensors: exp2f(l * S) * H - 1 and ceil + 1
+    evaluated by the GPU exactly as reference gridencoder.cu:138-139 does (host exp2 differs by 1 ulp at some levels)."""
+    scale = torch.empty(int(L), device=device, dtype=torch.float32)
+    res = torch.empty(int(L), device=device, dtype=torch.int32)
+    with torch.cuda.device(scale.device):
+        check(lib().dwg_grid_level_table(float(np.float32(S)), int(H), int(L), ptr(scale), ptr(res), stream()), 'dwg_grid_level_table')
+    return scale, res
 
 
 class GridSpec:
     """Device-resident level table of one grid encoder."""
 
     def __init__(self, device, bound=2.0, gridtype='tiled', align_corners=False, interpolation='smoothstep', **kw):
-        offsets, pls, scale, res = grid_level_table(align_corners=align_corners, **kw)
-        self.num_levels = len(scale)
+        offsets, pls, S = grid_level_table(align_corners=align_corners, **kw)
+        self.num_levels = len(offsets) - 1
         self.n_rows = int(offsets[-1])
         self.per_level_scale = pls
         self.bound = float(bound)
         self.gridtype = {'hash': 0, 'tiled': 1}[gridtype]
         self.interp = {'linear': 0, 'smoothstep': 1}[interpolation]
         self.align_corners = bool(align_corners)
-        self.offsets_np, self.scale_np, self.res_np = offsets, scale, res
+        self.offsets_np = offsets
         self.offsets = torch.from_numpy(offsets).to(device)
-        self.level_scale = torch.from_numpy(scale).to(device)
-        self.level_res = torch.from_numpy(res.astype(np.int32)).to(device)       # bit pattern of uint32
+        # per-level constants evaluated on the device with the reference kernel's own expression (dwg_grid_level_table)
+        self.level_scale, self.level_res = device_level_table(S, kw.get('base_resolution', 16), self.num_levels, device)
+        self.scale_np, self.res_np = self.level_scale.cpu().numpy(), self.level_res.cpu().numpy().view(np.uint32)
 
 
 class _GridEncode(torch.autograd.Function):
@@ -286,8 +294,49 @@ class RasterState:
         return base[off:off + n * isz].view(dtype).reshape(shape)
 
 
-def default_instance_capacity(N):
-    return int(max(4 * N, 1 << 20))
+_CAP_FLOOR = {}            # device index -> capacity learnt from an overflow report (next allocation uses it)
+MAX_TILE_LOAD = 131072     # SORT_CHUNK * 2^MAX_MERGE_PASSES of csrc/raster_sort.cu: a tile holding more instances cannot be sorted
+
+
+def default_instance_capacity(N, device=None):
+    floor = _CAP_FLOOR.get(torch.device(device).index if device is not None else None, 0)
+    return int(max(4 * N, 1 << 20, floor))
+
+
+class _StatusMonitor:
+    """Deferred check of the rasteriser's device status words {overflow flag, P, max tile load, -} without a host
+    synchronisation: every forward copies them asynchronously into pinned host memory (a memcpy node under CUDA-graph
+    capture), the NEXT forward looks at what has landed.  An overflow (P > P_cap: the kernel clamps tile ranges and drops
+    instances) or an unsortable tile raises RuntimeError one call late -- upstream sizes its buffers from num_rendered
+    with a host sync instead (diff_gaussian_rasterization resizeFunctional); the reference trainer's
+    `except RuntimeError` path (core/trainer.py:919-923) then checkpoints and exits."""
+
+    def __init__(self):
+        self.host = {}
+
+    def check(self, device, P_cap):
+        h = self.host.get(device.index)
+        if h is None:
+            return
+        flag, P, load = int(h[0]), int(h[1]), int(h[2])
+        if flag or load > MAX_TILE_LOAD:
+            h.zero_()
+            if flag:
+                _CAP_FLOOR[device.index] = max(_CAP_FLOOR.get(device.index, 0), int(P * 1.25) + 1024)
+                raise RuntimeError(f'dwg rasteriser: instance capacity exceeded in the previous call (P = {P} (tile, Gaussian) instances > '
+                                   f'capacity): instances were dropped.  Pass instance_capacity >= {P} (the next default allocation will use '
+                                   f'{_CAP_FLOOR[device.index]}).')
+            raise RuntimeError(f'dwg rasteriser: a tile held {load} instances in the previous call; at most {MAX_TILE_LOAD} can be depth-sorted')
+
+    def post(self, status):
+        dev = status.device
+        h = self.host.get(dev.index)
+        if h is None:
+            h = self.host[dev.index] = torch.zeros(4, dtype=torch.int32).pin_memory()
+        h.copy_(status, non_blocking=True)
+
+
+STATUS_MONITOR = _StatusMonitor()
 
 
 class _Rasterize(torch.autograd.Function):
@@ -300,7 +349,8 @@ class _Rasterize(torch.autograd.Function):
         N = means3D.shape[0]
         L = lib()
         cam = _camera_struct(H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier)
-        P_cap = int(P_cap or default_instance_capacity(N))
+        STATUS_MONITOR.check(dev, P_cap)                       # overflow / unsortable tile reported by the previous call
+        P_cap = int(P_cap or default_instance_capacity(N, dev))
         st = RasterState()
         st.cam, st.N, st.H, st.W, st.P_cap = cam, N, H, W, P_cap
         st.cam_dev = cam_dev
@@ -316,6 +366,7 @@ class _Rasterize(torch.autograd.Function):
         check(L.dwg_raster_forward(ctypes.byref(cam), N, ptr(means3D), ptr(colors), ptr(opac), ptr(scales),
                                    ptr(rotations), ptr(color), ptr(depth), ptr(alpha), ptr(st.radii), ptr(st.geom),
                                    ptr(st.bin), P_cap, ptr(st.img), ptr(st.status), ptr(cam_dev), stream()), 'dwg_raster_forward')
+        STATUS_MONITOR.post(st.status)
         ctx.save_for_backward(means3D, colors, opac, scales, rotations)
         ctx.st = st
         ctx.opac_shape = opacities.shape
@@ -381,17 +432,17 @@ def gemm_lane(lane):
     check(lib().dwg_gemm_set_lane(int(lane)), 'gemm_set_lane')
 
 
-def _chk_bf16(t):
-    assert t.is_cuda and t.dtype == torch.bfloat16, 'tcgen05 layers take bf16 CUDA tensors'
+def _chk_f16(t):
+    assert t.is_cuda and t.dtype == torch.float16, 'tcgen05 layers take bf16 CUDA tensors'
     return t
 
 
-def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=1.0, act=None, out_dtype=torch.bfloat16,
+def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=1.0, act=None, out_dtype=torch.float16,
          out=None):
-    """C[..., M, N] = act(alpha * A[..., M, K] @ B[..., N, K]^T + bias + bias2) + residual  (dwg_gemm_bf16).
+    """C[..., M, N] = act(alpha * A[..., M, K] @ B[..., N, K]^T + bias + bias2) + residual  (dwg_gemm_f16).
     a: [M,K] / [b1,M,K] / [b2,b1,M,K] bf16, last dim contiguous (any strides that are multiples of 8);
     b: same rank with N rows."""
-    _chk_bf16(a), _chk_bf16(b)
+    _chk_f16(a), _chk_f16(b)
     assert a.stride(-1) == 1 and b.stride(-1) == 1 and a.dim() == b.dim() and 2 <= a.dim() <= 4
     lead = (1,) * (4 - a.dim())
     a4 = a.as_strided(lead + tuple(a.shape), tuple(a.stride(0) * a.shape[0] for _ in lead) + tuple(a.stride()))
@@ -409,7 +460,7 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
         assert c4.stride(-1) == 1
     r4 = None
     if residual is not None:
-        _chk_bf16(residual)
+        _chk_f16(residual)
         r4 = residual.as_strided((1,) * (4 - residual.dim()) + tuple(residual.shape), (0,) * (4 - residual.dim()) + tuple(residual.stride())) if residual.dim() < 4 else residual
         assert r4.stride(-1) == 1
     bias = None if bias is None else f32c(bias)
@@ -418,21 +469,21 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
         TUNE_RECORD.append(('gemm', M, N, K, nb1, nb2, act, residual is not None, c4.dtype, bias is not None, bias2 is not None))
     nbytes = nb1 * nb2 * (2.0 * (M * K + N * K) + M * No * (c4.element_size() + (2 if r4 is not None else 0)))
     with _prof(2.0 * M * N * K * nb1 * nb2, f'gemm M{M} N{N} K{K} b{nb1 * nb2}', nbytes):
-        check(lib().dwg_gemm_bf16(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
+        check(lib().dwg_gemm_f16(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
                                   b4.data_ptr(), b4.stride(2), b4.stride(1), b4.stride(0),
-                                  c4.data_ptr(), c4.stride(2), c4.stride(1), c4.stride(0), int(c4.dtype == torch.bfloat16),
+                                  c4.data_ptr(), c4.stride(2), c4.stride(1), c4.stride(0), int(c4.dtype == torch.float16),
                                   M, N, K, nb1, nb2, ptr(bias), ptr(bias2), int(bias2_rows_per),
                                   None if r4 is None else r4.data_ptr(), 0 if r4 is None else r4.stride(2),
                                   0 if r4 is None else r4.stride(1), 0 if r4 is None else r4.stride(0),
-                                  float(alpha), ACT[act], stream()), 'dwg_gemm_bf16')
+                                  float(alpha), ACT[act], stream()), 'dwg_gemm_f16')
     return out
 
 
 def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding=1, out_hw=None, act=None,
-                out_dtype=torch.bfloat16):
-    """NHWC implicit-GEMM convolution (dwg_conv2d_nhwc_bf16).  x [N,H,W,Cin], w [Cout,k,k,Cin] bf16.
+                out_dtype=torch.float16):
+    """NHWC implicit-GEMM convolution (dwg_conv2d_nhwc_f16).  x [N,H,W,Cin], w [Cout,k,k,Cin] bf16.
     padding: int (symmetric) or (top, left) with out_hw=(Ho, Wo) for asymmetric cases."""
-    _chk_bf16(x), _chk_bf16(w)
+    _chk_f16(x), _chk_f16(w)
     assert x.is_contiguous() and w.is_contiguous()
     Nimg, H, W, Cin = x.shape
     Cout, k, k2, Cin2 = w.shape
@@ -444,7 +495,7 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
         Ho, Wo = out_hw
     y = torch.empty(Nimg, Ho, Wo, Cout, device=x.device, dtype=out_dtype)
     if residual is not None:
-        _chk_bf16(residual)
+        _chk_f16(residual)
         assert residual.shape == y.shape and residual.is_contiguous()
     bias = None if bias is None else f32c(bias)
     bias2 = None if bias2 is None else f32c(bias2)
@@ -452,21 +503,21 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
         TUNE_RECORD.append(('conv', Nimg, H, W, Cin, Cout, k, stride, ph, pw, Ho, Wo, residual is not None, out_dtype, bias2 is not None))
     nbytes = 2.0 * (x.numel() + w.numel()) + y.numel() * (y.element_size() + (2 if residual is not None else 0))
     with _prof(2.0 * Nimg * Ho * Wo * Cout * Cin * k * k, f'conv{k}x{k}s{stride} {Nimg}x{Ho}x{Wo} {Cin}->{Cout}', nbytes):
-        check(lib().dwg_conv2d_nhwc_bf16(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.bfloat16), Nimg, H, W, Cin, Cout, k,
+        check(lib().dwg_conv2d_nhwc_f16(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.float16), Nimg, H, W, Cin, Cout, k,
                                          stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], stream()),
-              'dwg_conv2d_nhwc_bf16')
+              'dwg_conv2d_nhwc_f16')
     return y
 
 
 # ------------------------------------------------------------------------------ norm / activation kernels (bf16 NHWC)
 def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, return_stats=False):
     """x [N, ..., C] bf16 channels-last -> [SiLU](GroupNorm(x)) (dwg_groupnorm_fwd)."""
-    _chk_bf16(x)
+    _chk_f16(x)
     assert x.is_contiguous()
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     y = torch.empty_like(x)
-    stats = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
+    stats = torch.empty(N, groups, 2, device=x.device, dtype=torch.int64)       # fixed-point (sum, sumsq), include/dwg.h
     L = lib()
     check(L.dwg_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), N, HW, C, groups, float(eps), int(silu),
                               stream()), 'dwg_groupnorm_fwd')
@@ -475,19 +526,19 @@ def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, return_stats=Fal
 
 
 def group_norm_bwd(x, dy, stats, gamma, beta, groups=32, eps=1e-5, silu=False, dx_add=None):
-    _chk_bf16(x), _chk_bf16(dy)
+    _chk_f16(x), _chk_f16(dy)
     assert x.is_contiguous() and dy.is_contiguous()
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     dx = torch.empty_like(x)
-    bstats = torch.empty(N, groups, 2, device=x.device, dtype=torch.float32)
+    bstats = torch.empty(N, groups, 2, device=x.device, dtype=torch.int64)       # fixed-point (sum, sumsq), include/dwg.h
     check(lib().dwg_groupnorm_bwd(ptr(x), ptr(dy), ptr(stats), ptr(gamma), ptr(beta), ptr(dx_add), ptr(dx), ptr(bstats), N, HW, C,
                                   groups, float(eps), int(silu), stream()), 'dwg_groupnorm_bwd')
     return dx
 
 
 def layer_norm(x, gamma, beta, eps=1e-5):
-    _chk_bf16(x)
+    _chk_f16(x)
     assert x.is_contiguous()
     C = x.shape[-1]
     y = torch.empty_like(x)
@@ -497,7 +548,7 @@ def layer_norm(x, gamma, beta, eps=1e-5):
 
 def softmax_rows_(s, cols):
     """In-place softmax over the last dim of bf16 scores [..., cols_pad]; columns >= cols become 0."""
-    _chk_bf16(s)
+    _chk_f16(s)
     assert s.is_contiguous()
     cp = s.shape[-1]
     check(lib().dwg_softmax_rows(ptr(s), s.numel() // cp, int(cols), cp, stream()), 'dwg_softmax_rows')
@@ -505,7 +556,7 @@ def softmax_rows_(s, cols):
 
 
 def softmax_rows_bwd_(p, dp):
-    _chk_bf16(p), _chk_bf16(dp)
+    _chk_f16(p), _chk_f16(dp)
     assert p.is_contiguous() and dp.is_contiguous()
     cp = p.shape[-1]
     check(lib().dwg_softmax_rows_bwd(ptr(p), ptr(dp), p.numel() // cp, cp, stream()), 'dwg_softmax_rows_bwd')
@@ -513,25 +564,25 @@ def softmax_rows_bwd_(p, dp):
 
 
 def geglu(x):
-    _chk_bf16(x)
+    _chk_f16(x)
     assert x.is_contiguous()
     inner = x.shape[-1] // 2
-    y = torch.empty(x.shape[:-1] + (inner,), device=x.device, dtype=torch.bfloat16)
+    y = torch.empty(x.shape[:-1] + (inner,), device=x.device, dtype=torch.float16)
     check(lib().dwg_geglu(ptr(x), ptr(y), x.numel() // x.shape[-1], inner, stream()), 'dwg_geglu')
     return y
 
 
 def silu(x):
-    _chk_bf16(x)
+    _chk_f16(x)
     y = torch.empty_like(x)
-    check(lib().dwg_eltwise_bf16(ptr(x.contiguous()), None, ptr(y), x.numel(), 0, stream()), 'dwg_eltwise_bf16')
+    check(lib().dwg_eltwise_f16(ptr(x.contiguous()), None, ptr(y), x.numel(), 0, stream()), 'dwg_eltwise_f16')
     return y
 
 
 def add(x, a):
-    _chk_bf16(x), _chk_bf16(a)
+    _chk_f16(x), _chk_f16(a)
     y = torch.empty_like(x)
-    check(lib().dwg_eltwise_bf16(ptr(x.contiguous()), ptr(a.contiguous()), ptr(y), x.numel(), 1, stream()), 'dwg_eltwise_bf16')
+    check(lib().dwg_eltwise_f16(ptr(x.contiguous()), ptr(a.contiguous()), ptr(y), x.numel(), 1, stream()), 'dwg_eltwise_f16')
     return y
 
 
@@ -547,12 +598,12 @@ def sds_grad(eps_uncond, eps_cond, noise, guidance_scale, weight=1.0):
 def attention(q, k, vt, heads, Tk, scale=None):
     """Fused attention forward (dwg_attention_fwd).  q [B,T,C], k [B,Tk,C] bf16 (last dim contiguous),
     vt [B,C,Tkp] = V transposed.  Returns [B,T,C] bf16."""
-    _chk_bf16(q), _chk_bf16(k), _chk_bf16(vt)
+    _chk_f16(q), _chk_f16(k), _chk_f16(vt)
     B, T, C = q.shape
     hd = C // heads
     assert q.stride(2) == 1 and k.stride(2) == 1 and vt.stride(2) == 1 and vt.stride(1) == vt.shape[2]
     assert q.stride(0) == T * q.stride(1) and k.stride(0) == Tk * k.stride(1)
-    out = torch.empty(B, T, C, device=q.device, dtype=torch.bfloat16)
+    out = torch.empty(B, T, C, device=q.device, dtype=torch.float16)
     scale = hd ** -0.5 if scale is None else scale
     fl = 4.0 * B * heads * T * Tk * hd
     with _prof(fl, f'attention B{B} h{heads} T{T} Tk{Tk} d{hd}'):

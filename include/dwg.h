@@ -71,12 +71,16 @@ int dwg_sh_eval_bwd(const float* sh, int sh_stride, int deg, const float* pos, c
  * (core/nerf/gridencoder/src/gridencoder.h:12-15, gridencoder.cu:87-500) incl. the
  * (x+bound)/(2*bound) mapping of GridEncoder.forward (grid.py:153).  D = 3, C = 2.
  *   x [B,3] world positions (bound > 0) or inputs already mapped to [0,1] (bound <= 0); table [rows,2]; offsets i32 [L+1]; level_scale f32 [L] and
- *   level_res u32 [L] = host-evaluated exp2f(l*S)*H-1 and ceil(scale)+1 (gridencoder.cu:138-139);
+ *   level_res u32 [L] = exp2f(l*S)*H-1 and ceil(scale)+1 (gridencoder.cu:138-139) as written by dwg_grid_level_table;
  *   out: element (b, l, c) at out[b*out_stride_b + l*out_stride_l + c]  (so both the final
  *   [B, L*C] layout and the reference's [L,B,C] staging layout are expressible);
  *   dy_dx [B, L*3*C] or NULL (derivative w.r.t. the [0,1]-mapped input, as the reference).
  *   gridtype 0 hash / 1 tiled; interp 0 linear / 1 smoothstep.
  */
+/* Per-level constants, evaluated on the device exactly as the reference kernel does per thread
+ * (gridencoder.cu:138-139): level_scale[l] = exp2f(l * S) * H - 1.0f, level_res[l] = (uint32)ceil(scale) + 1.
+ * S = log2(per_level_scale) as float32 (grid.py:40), H = base resolution.  Outputs are DEVICE arrays of L entries. */
+int dwg_grid_level_table(float S, int H, int L, float* level_scale, uint32_t* level_res, void* stream);
 int dwg_grid_encode_fwd(const float* x, float bound, const float* table, const int32_t* offsets,
                         const float* level_scale, const uint32_t* level_res,
                         float* out, int64_t out_stride_b, int64_t out_stride_l, float* dy_dx,
@@ -149,14 +153,14 @@ void* dwg_raster_view(int which, void* geom, void* bin, void* img, int64_t N, in
  * UNet2DConditionModel, ControlNetModel and AutoencoderKL (third party; call sites
  * core/guidance/controlnet.py:98-114, core/guidance/vae.py:34-40).
  *
- * dwg_gemm_bf16:  C[b2][b1][M,N] = act(alpha * A[b2][b1][M,K] . B[b2][b1][N,K]^T + bias[N]
+ * dwg_gemm_f16:  C[b2][b1][M,N] = act(alpha * A[b2][b1][M,K] . B[b2][b1][N,K]^T + bias[N]
  *                                      + bias2[row / bias2_rows_per][N]) + residual
- *   A, B bf16 with K contiguous; strides in ELEMENTS and multiples of 8; C bf16 (out_bf16=1) or
+ *   A, B bf16 with K contiguous; strides in ELEMENTS and multiples of 8; C bf16 (out_f16=1) or
  *   fp32; residual bf16 with its own strides; act 0 none / 1 SiLU / 2 GELU(erf).
  */
-int dwg_gemm_bf16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
+int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                   const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
-                  void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_bf16,
+                  void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16,
                   int M, int N, int K, int nb1, int nb2,
                   const float* bias, const float* bias2, int bias2_rows_per,
                   const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
@@ -209,12 +213,12 @@ int dwg_gemm_set_lane(int lane);
 int dwg_gemm_trace(void* dev_u64x8);   /* debug timeline of CTA 0 (globaltimer ns), NULL = off; see csrc/gemm_tcgen05.cu */
 int dwg_gemm_last_key(int* out6);   /* planner key of the last launch: m_tiles, nz, N, k-iterations, epilogue kind, has_residual */
 
-/* dwg_conv2d_nhwc_bf16: implicit-GEMM convolution, no im2col buffer.
+/* dwg_conv2d_nhwc_f16: implicit-GEMM convolution, no im2col buffer.
  *   x [Nimg,H,W,Cin] bf16 (Cin % 8 == 0), w [Cout,k,k,Cin] bf16, y [Nimg,Ho,Wo,Cout] bf16/fp32,
  *   ksize 1|3, stride 1|2, zero padding pad_h/pad_w on the top/left (bottom/right implied by
  *   Ho/Wo: covers the VAE's asymmetric (0,1,0,1) padding); bias [Cout], bias2_per_image
  *   [Nimg,Cout] (time embedding), residual [Nimg,Ho,Wo,Cout] bf16. */
-int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int out_bf16,
+int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int out_f16,
                          int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
                          int pad_h, int pad_w, int Ho, int Wo,
                          const float* bias, const float* bias2_per_image,
@@ -225,17 +229,18 @@ int dwg_conv2d_nhwc_bf16(const void* x, const void* w, void* y, int out_bf16,
  * Replace torch.nn.GroupNorm / LayerNorm / softmax / GEGLU / SiLU calls inside the diffusers
  * modules, and the CFG + SDS-gradient arithmetic of core/guidance/basic.py:595-603,642.
  */
-/* y = [SiLU](GroupNorm_G(x));  x,y [N,HW,C] bf16; stats [N,G,2] fp32 workspace (sum, sumsq), kept for bwd */
-int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
+/* y = [SiLU](GroupNorm_G(x));  x,y [N,HW,C] fp16; stats [N,G,2] i64 workspace: (sum, sumsq) in 2^-20 fixed point,
+ * accumulated with integer atomics so that the statistics are run-to-run deterministic; kept for bwd */
+int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, void* stats,
                       int N, int HW, int C, int G, float eps, int do_silu, void* stream);
 /* kernels launched by the last dwg_groupnorm_fwd: 1 = one-launch cluster kernel (tensor fits the shared memory of 8 CTAs
  * per (image, 4-group slab): every UNet / ControlNet norm at batch 2), 2 = statistics + apply passes. */
 int dwg_groupnorm_last_launches(void);
 /* enable (1) / disable (0, default: measured slower inside the step) the one-launch cluster kernel */
 int dwg_groupnorm_set_fused(int on);
-/* dx = d/dx [SiLU](GroupNorm(x)) . dy  (+ dx_add if given);  bstats [N,G,2] fp32 workspace */
-int dwg_groupnorm_bwd(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta,
-                      const void* dx_add, void* dx, float* bstats, int N, int HW, int C, int G, float eps,
+/* dx = d/dx [SiLU](GroupNorm(x)) . dy  (+ dx_add if given);  bstats [N,G,2] i64 workspace (2^-36 fixed point) */
+int dwg_groupnorm_bwd(const void* x, const void* dy, const void* stats, const float* gamma, const float* beta,
+                      const void* dx_add, void* dx, void* bstats, int N, int HW, int C, int G, float eps,
                       int do_silu, void* stream);
 int dwg_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int C, float eps, void* stream);
 /* in-place row softmax of bf16 scores [rows, cols_pad] (columns >= cols are written as 0) */
@@ -245,7 +250,7 @@ int dwg_softmax_rows_bwd(const void* p, void* dp, int64_t rows, int cols_pad, vo
 /* y[rows, inner] = x[:, :inner] * gelu(x[:, inner:]) */
 int dwg_geglu(const void* x, void* y, int64_t rows, int inner, void* stream);
 /* mode 0: y = silu(x); 1: y = x + a; 2: y = a * silu'(x)   (n bf16 elements, n % 8 == 0) */
-int dwg_eltwise_bf16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream);
+int dwg_eltwise_f16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream);
 /* noise_pred = eps_u + s (eps_c - eps_u);  grad = weight * (noise_pred - noise)   (fp32) */
 int dwg_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float* grad, float* noise_pred,
                  float guidance_scale, float weight, int64_t n, void* stream);

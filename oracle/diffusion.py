@@ -1,5 +1,5 @@
 """Oracle: Stable-Diffusion UNet / ControlNet / VAE-encoder forward and the SDS arithmetic
-(rows R14-R16), plain torch fp32 on the CPU, NCHW, functional over a diffusers-style state dict.
+(rows R14-R16), plain torch fp32 (CPU, or any device the state dict / inputs live on), NCHW, functional over a diffusers-style state dict.
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED: ``diffusers`` is an un-vendored
 third-party dependency of the reference (requirements.txt:4 pins 0.24.0, scripts/install.sh:27
@@ -23,7 +23,7 @@ VAE15 = dict(block_out=(128, 256, 512, 512), layers_per_block=2, latent=4, group
 def timestep_embedding(t, dim):
     """diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin]."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t.float()[:, None] * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -78,7 +78,7 @@ def transformer(sd, p, x, ctx, heads, groups):
 
 
 def _time_embed(sd, t, cfg, B):
-    temb = timestep_embedding(t.reshape(-1).expand(B), cfg['block_out'][0])
+    temb = timestep_embedding(t.reshape(-1).expand(B), cfg['block_out'][0]).to(sd['time_embedding.linear_1.weight'].dtype)
     return _lin(sd, 'time_embedding.linear_2', F.silu(_lin(sd, 'time_embedding.linear_1', temb)))
 
 
@@ -189,7 +189,7 @@ def alphas_cumprod(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012)
 
 
 def add_noise(latents, noise, t, acp=None):
-    acp = alphas_cumprod() if acp is None else acp
+    acp = alphas_cumprod().to(latents.device) if acp is None else acp
     a = acp[t].reshape(-1, 1, 1, 1)
     return a.sqrt() * latents + (1 - a).sqrt() * noise
 

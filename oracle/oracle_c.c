@@ -65,7 +65,9 @@ void orc_grid_forward(const float* x01, const float* table, const int* offsets,
             uint32_t hs = (uint32_t)(offsets[l + 1] - offsets[l]);
             float scale = level_scale[l];
             uint32_t res = level_res[l];
-            float pos[3], pderiv[3] = {1.f, 1.f, 1.f};
+            /* gridencoder.cu:143 `float pos_deriv[D] = {1.0f}`: ONLY element 0 is 1 -- with linear interpolation the
+               reference's dy_dx (hence grad_inputs) is zero along y and z; pinned by tests/golden/grid.npz */
+            float pos[3], pderiv[3] = {1.f, 0.f, 0.f};
             uint32_t pg[3];
             for (int d = 0; d < 3; d++) {
                 pos[d] = fmaf(x[d], scale, align_corners ? 0.0f : 0.5f);

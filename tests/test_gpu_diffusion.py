@@ -1,7 +1,8 @@
 """GPU: the diffusion blocks (UNet, ControlNet, VAE encoder fwd + input-gradient bwd, SDS algebra)
 on dwg kernels against the fp32 CPU oracle, on a reduced-width model with the full topology
-(tests run in seconds; bench.py runs the SD1.5 sizes).  bf16 tensor-core arithmetic vs an fp32
-oracle: stated tolerance rel-L2 <= 2e-2 on eps / latents, <= 5e-2 on the VAE input gradient."""
+(seconds; tests/test_gpu_diffusion_sd15.py repeats the comparison at the benchmark's SD1.5 sizes and guidance
+scale 50).  fp16 tensor-core arithmetic (fp32 accumulate) vs an fp32 oracle: stated tolerance rel-L2 <= 5e-3 on
+eps / latents (measured ~2e-3), <= 1e-2 on the VAE input gradient."""
 import numpy as np
 import pytest
 import torch
@@ -19,7 +20,7 @@ def rel_l2(got, ref):
 
 def test_norm_kernels_vs_torch():
     torch.manual_seed(0)
-    x = torch.randn(2, 16, 16, 320, device=DEV).bfloat16()
+    x = torch.randn(2, 16, 16, 320, device=DEV).half()
     g, b = torch.rand(320, device=DEV) + 0.5, torch.randn(320, device=DEV) * 0.1
     ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, g, b, 1e-5)
     y = ops.group_norm(x, g, b, 32, 1e-5, silu=False)
@@ -30,23 +31,23 @@ def test_norm_kernels_vs_torch():
     # backward
     xr = x.float().requires_grad_(True)
     out = torch.nn.functional.silu(torch.nn.functional.group_norm(xr.permute(0, 3, 1, 2), 32, g, b, 1e-5)).permute(0, 2, 3, 1)
-    dy = torch.randn(out.shape, device=DEV).bfloat16()
+    dy = torch.randn(out.shape, device=DEV).half()
     out.backward(dy.float())
     _, st = ops.group_norm(x, g, b, 32, 1e-5, silu=True, return_stats=True)
     dx = ops.group_norm_bwd(x, dy, st, g, b, 32, 1e-5, True)
     e3 = rel_l2(dx, xr.grad.cpu())
     assert e3 < 2e-2, ('gn bwd', e3)
     # layernorm / softmax / geglu
-    t = torch.randn(50, 640, device=DEV).bfloat16()
+    t = torch.randn(50, 640, device=DEV).half()
     e4 = rel_l2(ops.layer_norm(t, g.repeat(2), b.repeat(2)), torch.nn.functional.layer_norm(t.float(), (640,), g.repeat(2), b.repeat(2)).cpu())
     assert e4 < 1e-2, ('ln', e4)
     for cols, pad in ((77, 80), (4096, 4096), (300, 304)):
-        s = torch.randn(33, pad, device=DEV).bfloat16()
+        s = torch.randn(33, pad, device=DEV).half()
         ref = torch.softmax(s.float()[:, :cols], -1)
         ops.softmax_rows_(s, cols)
         e5 = rel_l2(s[:, :cols], ref.cpu())
         assert e5 < 1e-2 and float(s[:, cols:].float().abs().sum()) == 0, ('softmax', cols, e5, float(s[:, cols:].float().abs().sum()))
-    gg = torch.randn(64, 2560, device=DEV).bfloat16()
+    gg = torch.randn(64, 2560, device=DEV).half()
     a, bb = gg.float().chunk(2, -1)
     e6 = rel_l2(ops.geglu(gg), (a * torch.nn.functional.gelu(bb)).cpu())
     assert e6 < 1e-2, ('geglu', e6)
@@ -72,11 +73,11 @@ def test_unet_and_controlnet_match_oracle():
     cn, un = M.ControlNet(c_sd, cfg, DEV), M.UNet(u_sd, cfg, DEV)
     down, mid = cn.forward(x.to(DEV), t.to(DEV), ctx.to(DEV), cond.to(DEV))
     for i, (d, r) in enumerate(zip(down, down_r)):
-        assert rel_l2(d.permute(0, 3, 1, 2), r) < 2e-2, i
-    assert rel_l2(mid.permute(0, 3, 1, 2), mid_r) < 2e-2
+        assert rel_l2(d.permute(0, 3, 1, 2), r) < 5e-3, i
+    assert rel_l2(mid.permute(0, 3, 1, 2), mid_r) < 5e-3
     eps = un.forward(x.to(DEV), t.to(DEV), ctx.to(DEV), down, mid)
-    assert eps.shape == eps_r.shape and rel_l2(eps, eps_r) < 2e-2
-    assert rel_l2(un.forward(x.to(DEV), t.to(DEV), ctx.to(DEV)), eps_plain) < 2e-2
+    assert eps.shape == eps_r.shape and rel_l2(eps, eps_r) < 5e-3
+    assert rel_l2(un.forward(x.to(DEV), t.to(DEV), ctx.to(DEV)), eps_plain) < 5e-3
 
 
 def test_vae_encode_forward_and_input_gradient_match_oracle():
@@ -93,9 +94,9 @@ def test_vae_encode_forward_and_input_gradient_match_oracle():
     enc = M.VAEEncoder(v_sd, vcfg, DEV)
     img_g = img.to(DEV).requires_grad_(True)
     lat = M.vae_encode(enc, img_g, eps.to(DEV))
-    assert rel_l2(lat, lat_r.detach()) < 2e-2
+    assert rel_l2(lat, lat_r.detach()) < 5e-3
     (lat * gl.to(DEV)).sum().backward()
-    assert rel_l2(img_g.grad, img_r.grad) < 5e-2
+    assert rel_l2(img_g.grad, img_r.grad) < 1e-2
 
 
 def test_sds_step_matches_oracle_and_specify_gradient():
@@ -117,15 +118,14 @@ def test_sds_step_matches_oracle_and_specify_gradient():
     with torch.no_grad():
         ln = od.add_noise(lat_r.detach(), noise, t)
         grad_r, np_r = od.sds_gradient(u_sd, c_sd, cfg, ln, noise, t, emb['neg'], emb['text'], cond, guidance_scale=7.5)
-    assert rel_l2(out['latents'], lat_r.detach()) < 2e-2
-    # CFG amplifies the bf16 error of eps by ~(1 + 2 s): eps itself is held to 2e-2 (test above)
-    s_cfg = 7.5
-    assert rel_l2(out['noise_pred'], np_r) < 2e-2 * (1 + 2 * s_cfg) / 2
-    assert rel_l2(out['gradients'], grad_r) < 2e-2 * (1 + 2 * s_cfg) / 2
+    assert rel_l2(out['latents'], lat_r.detach()) < 5e-3
+    # CFG amplifies the rounding error of (eps_c - eps_u) by the guidance scale s: eps itself is held to 5e-3 (test above)
+    assert rel_l2(out['noise_pred'], np_r) < 1.5e-2
+    assert rel_l2(out['gradients'], grad_r) < 1.5e-2
     assert out['diffusion_loss'].shape == (1,) and float(out['diffusion_loss']) == 1.0
     out['diffusion_loss'].backward()
     (lat_r * grad_r).sum().backward()
-    assert rel_l2(img_g.grad, img_r.grad) < 0.2          # dominated by the CFG-amplified eps error above
+    assert rel_l2(img_g.grad, img_r.grad) < 2e-2         # dominated by the CFG-amplified eps error above
     # CFG/SDS algebra alone (fp32 kernel): exact formula
     eu, ec, nz = torch.randn(3, 1, 4, 8, 8, device=DEV)
     gr, npd = ops.sds_grad(eu, ec, nz, 50.0, 1.0)
@@ -157,12 +157,11 @@ def test_prepare_head_start_and_two_streams_change_nothing():
         out['diffusion_loss'].backward()
         torch.cuda.synchronize()
         outs.append((out['noise_pred'].clone(), x.grad.clone()))
-    # Identical kernels and operands; only the order of floating-point atomics (GroupNorm statistics, split-K) differs
-    # run to run.  Measured: two runs of the SAME mode differ by ~1e-2 on eps (bf16 rounding flips amplified through the
-    # random-weight net), i.e. ~0.1 on the CFG-amplified prediction -- the bound is the oracle test's bf16 tolerance.
-    tol = 2e-2 * (1 + 2 * 7.5) / 2
+    # Identical kernels and operands, and every reduction has a fixed order (GroupNorm statistics: integer atomics on
+    # fixed-point partials; split-K: per-split slices added in split order), so the three schedules agree BITWISE --
+    # a stream / PDL race would show up here.
     for npd, gr in outs[1:]:
-        assert rel_l2(npd, outs[0][0].cpu()) < tol and rel_l2(gr, outs[0][1].cpu()) < 0.2
+        assert torch.equal(npd, outs[0][0]) and torch.equal(gr, outs[0][1])
 
 
 @pytest.mark.parametrize('N,H,W,C', [(2, 64, 64, 320), (2, 8, 8, 1280), (2, 32, 32, 960), (2, 16, 16, 2560), (1, 64, 64, 512),
@@ -172,7 +171,7 @@ def test_group_norm_one_launch_cluster_path_vs_torch(N, H, W, C):
     (last case) the two-pass kernels.  Both return the same raw (sum, sumsq) statistics the backward consumes."""
     from dwg._lib import lib
     torch.manual_seed(1)
-    x = (torch.randn(N, H, W, C, device=DEV) * 1.7 + 0.3).bfloat16()
+    x = (torch.randn(N, H, W, C, device=DEV) * 1.7 + 0.3).half()
     g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
     ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, g, b, 1e-6)
     lib().dwg_groupnorm_set_fused(1)
@@ -185,6 +184,7 @@ def test_group_norm_one_launch_cluster_path_vs_torch(N, H, W, C):
             assert rel_l2(y.permute(0, 3, 1, 2), r.cpu()) < 1e-2
     finally:
         lib().dwg_groupnorm_set_fused(0)
-    xs = x.float().view(N, H * W, 32, C // 32)
+    xs = x.double().view(N, H * W, 32, C // 32)
     st_ref = torch.stack([xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))], dim=-1)          # [N, 32, 2]
-    torch.testing.assert_close(st.view(N, 32, 2).cpu(), st_ref.cpu(), rtol=2e-4, atol=1e-2)
+    assert st.dtype == torch.int64                                                         # 2^-20 fixed point (include/dwg.h)
+    torch.testing.assert_close(st.view(N, 32, 2).double().cpu() / 2.0 ** 20, st_ref.cpu(), rtol=2e-5, atol=1e-2)

@@ -19,16 +19,16 @@ def _rel(got, ref):
                                    (130, 250, 72), (2, 1280, 320)])
 def test_gemm_plain(M, N, K):
     torch.manual_seed(0)
-    a = torch.randn(M, K, device=DEV).bfloat16()
-    b = torch.randn(N, K, device=DEV).bfloat16()
+    a = torch.randn(M, K, device=DEV).half()
+    b = torch.randn(N, K, device=DEV).half()
     ref = a.float() @ b.float().t()
     c = ops.gemm(a, b, out_dtype=torch.float32)
     assert _rel(c, ref) < 2e-3
     bias = torch.randn(N, device=DEV)
-    res = torch.randn(M, N, device=DEV).bfloat16()
+    res = torch.randn(M, N, device=DEV).half()
     c2 = ops.gemm(a, b, bias=bias, residual=res, alpha=0.5, act='silu')
     ref2 = F.silu(0.5 * ref + bias) + res.float()
-    assert c2.dtype == torch.bfloat16 and _rel(c2, ref2) < 2e-2
+    assert c2.dtype == torch.float16 and _rel(c2, ref2) < 2e-2
     c3 = ops.gemm(a, b, bias=bias, act='gelu', out_dtype=torch.float32)
     assert _rel(c3, F.gelu(ref + bias)) < 2e-3
 
@@ -37,8 +37,8 @@ def test_gemm_strided_batched_attention_shapes():
     """QK^T and PV for 8 heads x 2 samples with head dim 40, straight from [B, T, heads*hd] tensors."""
     torch.manual_seed(1)
     B, T, Hh, hd, Tk = 2, 1024, 8, 40, 77
-    q = torch.randn(B, T, Hh * hd, device=DEV).bfloat16()
-    k = torch.randn(B, Tk, Hh * hd, device=DEV).bfloat16()
+    q = torch.randn(B, T, Hh * hd, device=DEV).half()
+    k = torch.randn(B, Tk, Hh * hd, device=DEV).half()
     q4 = q.view(B, T, Hh, hd).permute(0, 2, 1, 3)          # [B, heads, T, hd] strided view
     k4 = k.view(B, Tk, Hh, hd).permute(0, 2, 1, 3)
     s = ops.gemm(q4, k4, alpha=hd ** -0.5, out_dtype=torch.float32)
@@ -47,11 +47,11 @@ def test_gemm_strided_batched_attention_shapes():
     # PV with V^T [B, heads, hd, Tk] (K = Tk = 80 after padding to a multiple of 8)
     p = torch.softmax(ref, -1)
     Tkp = 80
-    pp = torch.zeros(B, Hh, T, Tkp, device=DEV, dtype=torch.bfloat16)
-    pp[..., :Tk] = p.bfloat16()
-    vt = torch.zeros(B, Hh, hd, Tkp, device=DEV, dtype=torch.bfloat16)
-    vt[..., :Tk] = torch.randn(B, Hh, hd, Tk, device=DEV).bfloat16()
-    out = torch.empty(B, T, Hh * hd, device=DEV, dtype=torch.bfloat16)
+    pp = torch.zeros(B, Hh, T, Tkp, device=DEV, dtype=torch.float16)
+    pp[..., :Tk] = p.half()
+    vt = torch.zeros(B, Hh, hd, Tkp, device=DEV, dtype=torch.float16)
+    vt[..., :Tk] = torch.randn(B, Hh, hd, Tk, device=DEV).half()
+    out = torch.empty(B, T, Hh * hd, device=DEV, dtype=torch.float16)
     o4 = out.view(B, T, Hh, hd).permute(0, 2, 1, 3)
     ops.gemm(pp, vt, out=o4)
     ref_o = torch.einsum('bhts,bhds->bhtd', pp.float(), vt.float())
@@ -64,15 +64,15 @@ def test_gemm_strided_batched_attention_shapes():
     (1, 128, 128, 128, 128, 3, 1), (1, 256, 256, 16, 32, 3, 2), (3, 8, 8, 64, 96, 3, 1), (1, 24, 40, 64, 64, 3, 1)])
 def test_conv2d_nhwc_vs_torch(N, H, W, Cin, Cout, k, stride):
     torch.manual_seed(2)
-    x = torch.randn(N, H, W, Cin, device=DEV).bfloat16()
-    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).bfloat16()
+    x = torch.randn(N, H, W, Cin, device=DEV).half()
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).half()
     bias = torch.randn(Cout, device=DEV)
     pad = k // 2
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
     y = ops.conv2d_nhwc(x, w, bias=bias, stride=stride, padding=pad, out_dtype=torch.float32)
     assert y.shape == ref.shape and _rel(y, ref) < 2e-3
     temb = torch.randn(N, Cout, device=DEV)
-    res = torch.randn_like(ref).bfloat16()
+    res = torch.randn_like(ref).half()
     y2 = ops.conv2d_nhwc(x, w, bias=bias, bias2=temb, residual=res, stride=stride, padding=pad)
     ref2 = ref + temb[:, None, None, :] + res.float()
     assert _rel(y2, ref2) < 2e-2
@@ -82,8 +82,8 @@ def test_conv2d_asymmetric_padding_downsample():
     """VAE encoder downsample: F.pad(x, (0,1,0,1)) then 3x3 stride-2 conv with padding 0."""
     torch.manual_seed(3)
     N, H, W, C = 1, 64, 64, 128
-    x = torch.randn(N, H, W, C, device=DEV).bfloat16()
-    w = (torch.randn(C, 3, 3, C, device=DEV) / (9 * C) ** 0.5).bfloat16()
+    x = torch.randn(N, H, W, C, device=DEV).half()
+    w = (torch.randn(C, 3, 3, C, device=DEV) / (9 * C) ** 0.5).half()
     xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
     ref = F.conv2d(xp, w.float().permute(0, 3, 1, 2), None, stride=2, padding=0).permute(0, 2, 3, 1)
     y = ops.conv2d_nhwc(x, w, stride=2, padding=(0, 0), out_hw=(H // 2, W // 2), out_dtype=torch.float32)
@@ -95,11 +95,11 @@ def test_conv2d_asymmetric_padding_downsample():
 def test_fused_attention_vs_sdpa(B, heads, T, Tk, hd):
     torch.manual_seed(5)
     C = heads * hd
-    q = torch.randn(B, T, C, device=DEV).bfloat16()
-    k = torch.randn(B, Tk, C, device=DEV).bfloat16()
-    v = torch.randn(B, Tk, C, device=DEV).bfloat16()
+    q = torch.randn(B, T, C, device=DEV).half()
+    k = torch.randn(B, Tk, C, device=DEV).half()
+    v = torch.randn(B, Tk, C, device=DEV).half()
     Tkp = (Tk + 7) // 8 * 8
-    vt = torch.zeros(B, C, Tkp, device=DEV, dtype=torch.bfloat16)
+    vt = torch.zeros(B, C, Tkp, device=DEV, dtype=torch.float16)
     vt[:, :, :Tk] = v.transpose(1, 2)
     out = ops.attention(q, k, vt, heads, Tk)
     sp = lambda t: t.float().view(B, -1, heads, hd).transpose(1, 2)
@@ -110,8 +110,8 @@ def test_fused_attention_vs_sdpa(B, heads, T, Tk, hd):
 def test_gemm_fused_geglu_epilogue():
     torch.manual_seed(7)
     M, K, inner = 2048, 640, 2560
-    a = torch.randn(M, K, device=DEV).bfloat16()
-    w = (torch.randn(2 * inner, K, device=DEV) / K ** 0.5).bfloat16()
+    a = torch.randn(M, K, device=DEV).half()
+    w = (torch.randn(2 * inner, K, device=DEV) / K ** 0.5).half()
     bias = torch.randn(2 * inner, device=DEV) * 0.1
     full = a.float() @ w.float().t() + bias
     ref = full[:, :inner] * F.gelu(full[:, inner:])
@@ -124,9 +124,9 @@ def test_gemm_fused_geglu_epilogue():
 def test_gemm_tiny_m_and_deep_split_k():
     torch.manual_seed(8)
     for (M, N, K) in ((2, 1280, 320), (128, 1280, 5120), (128, 1280, 1280), (512, 1280, 1280)):
-        a = torch.randn(M, K, device=DEV).bfloat16()
-        b = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
-        res = torch.randn(M, N, device=DEV).bfloat16()
+        a = torch.randn(M, K, device=DEV).half()
+        b = (torch.randn(N, K, device=DEV) / K ** 0.5).half()
+        res = torch.randn(M, N, device=DEV).half()
         c = ops.gemm(a, b, residual=res, out_dtype=torch.float32)
         assert _rel(c, a.float() @ b.float().t() + res.float()) < 2e-3
 
@@ -147,16 +147,16 @@ def test_gemm_cta_pair_matches_torch(force_pair, M, N, K, bn, ks):
     L = force_pair
     L.dwg_gemm_tune(bn, ks)
     torch.manual_seed(0)
-    a = torch.randn(M, K, device=DEV).bfloat16()
-    b = torch.randn(N, K, device=DEV).bfloat16()
+    a = torch.randn(M, K, device=DEV).half()
+    b = torch.randn(N, K, device=DEV).half()
     ref = a.float() @ b.float().t()
     c = ops.gemm(a, b, out_dtype=torch.float32)
     assert L.dwg_gemm_last_pair() == 1, 'pair mode was not taken'
     assert _rel(c, ref) < 2e-3
     bias = torch.randn(N, device=DEV)
-    res = torch.randn(M, N, device=DEV).bfloat16()
+    res = torch.randn(M, N, device=DEV).half()
     c2 = ops.gemm(a, b, bias=bias, residual=res, alpha=0.5, act='silu')
-    assert c2.dtype == torch.bfloat16 and _rel(c2, F.silu(0.5 * ref + bias) + res.float()) < 2e-2
+    assert c2.dtype == torch.float16 and _rel(c2, F.silu(0.5 * ref + bias) + res.float()) < 2e-2
     # repeated launches (persistent tiles, barrier phases, TMEM stages) stay correct
     for _ in range(3):
         c = ops.gemm(a, b, out_dtype=torch.float32)
@@ -169,8 +169,8 @@ def test_gemm_cta_pair_matches_torch(force_pair, M, N, K, bn, ks):
 def test_conv2d_cta_pair_matches_torch(force_pair, N, H, W, Cin, Cout, k, stride):
     L = force_pair
     torch.manual_seed(2)
-    x = torch.randn(N, H, W, Cin, device=DEV).bfloat16()
-    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).bfloat16()
+    x = torch.randn(N, H, W, Cin, device=DEV).half()
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).half()
     bias = torch.randn(Cout, device=DEV)
     pad = k // 2
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
@@ -178,7 +178,7 @@ def test_conv2d_cta_pair_matches_torch(force_pair, N, H, W, Cin, Cout, k, stride
     assert L.dwg_gemm_last_pair() == 1, 'pair mode was not taken'
     assert y.shape == ref.shape and _rel(y, ref) < 2e-3
     temb = torch.randn(N, Cout, device=DEV)
-    res = torch.randn_like(ref).bfloat16()
+    res = torch.randn_like(ref).half()
     y2 = ops.conv2d_nhwc(x, w, bias=bias, bias2=temb, residual=res, stride=stride, padding=pad)
     assert _rel(y2, ref + temb[:, None, None, :] + res.float()) < 2e-2
 
@@ -186,8 +186,8 @@ def test_conv2d_cta_pair_matches_torch(force_pair, N, H, W, Cin, Cout, k, stride
 def test_geglu_cta_pair(force_pair):
     torch.manual_seed(3)
     M, K, inner = 2048, 640, 2560
-    a = torch.randn(M, K, device=DEV).bfloat16()
-    w = (torch.randn(2 * inner, K, device=DEV) / K ** 0.5).bfloat16()        # rows interleaved (value_i, gate_i)
+    a = torch.randn(M, K, device=DEV).half()
+    w = (torch.randn(2 * inner, K, device=DEV) / K ** 0.5).half()        # rows interleaved (value_i, gate_i)
     bias = torch.randn(2 * inner, device=DEV)
     y = ops.gemm(a, w, bias=bias, act='geglu')
     assert force_pair.dwg_gemm_last_pair() == 1
@@ -206,12 +206,12 @@ def test_conv3x3_halo_mode_matches_torch(pair, N, H, W, Cin, Cout):
     if pair and ((W // 8) * (H // 16) * N) % 2:
         pytest.skip('CTA pairs need an even number of 8x16-pixel tiles (the planner falls back to the per-tap path)')
     torch.manual_seed(4)
-    x = torch.randn(N, H, W, Cin, device=DEV).bfloat16()
-    w = (torch.randn(Cout, 3, 3, Cin, device=DEV) / (9 * Cin) ** 0.5).bfloat16()
+    x = torch.randn(N, H, W, Cin, device=DEV).half()
+    w = (torch.randn(Cout, 3, 3, Cin, device=DEV) / (9 * Cin) ** 0.5).half()
     bias = torch.randn(Cout, device=DEV)
     temb = torch.randn(N, Cout, device=DEV)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
-    res = torch.randn_like(ref).bfloat16()
+    res = torch.randn_like(ref).half()
     L.dwg_gemm_tune_halo(1, 0)
     L.dwg_gemm_tune_pair(pair)
     L.dwg_gemm_tune(128, 1)                          # halo mode does not split K

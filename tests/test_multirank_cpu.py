@@ -28,8 +28,19 @@ def _worker(rank, world, port, out):
     params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2))]
     params[0].grad = torch.full((5, 3), float(rank + 1))
     params[1].grad = torch.arange(7.0) * (rank + 1)
-    nbytes = parallel.allreduce_grads(params)            # params[2] has no grad: skipped
-    out.put((rank, float(cam['azimuth']), params[0].grad.tolist(), params[1].grad.tolist(), params[2].grad, nbytes))
+    if rank == 1:
+        params[2].grad = torch.tensor([5.0, 7.0])        # rank 0 has NO gradient for params[2] this step: fixed layout, zeros contributed
+    nbytes = parallel.allreduce_grads(params)
+    # persistent flat bucket: p.grad are views, autograd accumulates in place, one in-place collective
+    w = [torch.nn.Parameter(torch.ones(4, 2) * (rank + 1)), torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(6))]
+    bucket = parallel.GradBucket(w)
+    bucket.zero()
+    loss = (w[0] ** 2).sum() + (w[1] * float(rank + 2)).sum()          # w[2] unused on every rank -> stays zero
+    loss.backward()
+    views_ok = all(p.grad.data_ptr() == bucket.flat.data_ptr() + o * 4 for p, o in zip(w, bucket.offsets))
+    nb2 = bucket.all_reduce()
+    out.put((rank, float(cam['azimuth']), params[0].grad.tolist(), params[1].grad.tolist(), params[2].grad.tolist(), nbytes,
+             views_ok, w[0].grad.tolist(), w[1].grad.tolist(), w[2].grad.tolist(), nb2, bucket.offsets))
     dist.destroy_process_group()
 
 
@@ -45,7 +56,11 @@ def test_two_rank_gradient_allreduce_and_independent_views():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0][1] != res[1][1]                                        # ranks drew different views
-    for _, _, g0, g1, g2, nb in res:
+    for _, _, g0, g1, g2, nb, views_ok, w0, w1, w2, nb2, offs in res:
         torch.testing.assert_close(torch.tensor(g0), torch.full((5, 3), 3.0))          # 1 + 2
         torch.testing.assert_close(torch.tensor(g1), torch.arange(7.0) * 3.0)
-        assert g2 is None and nb == (15 + 7) * 4
+        assert g2 == [5.0, 7.0] and nb == (15 + 7 + 2) * 4                             # same buffer length on both ranks
+        assert views_ok and offs == [0, 8, 12] and nb2 == (8 + 4 + 8) * 4              # 16-byte aligned segments
+        torch.testing.assert_close(torch.tensor(w0), torch.full((4, 2), 2.0 * 1 + 2.0 * 2))
+        torch.testing.assert_close(torch.tensor(w1), torch.full((3,), 2.0 + 3.0))
+        assert w2 == [0.0] * 6

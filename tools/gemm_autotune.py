@@ -56,19 +56,19 @@ def make_problem(call):
     torch.manual_seed(0)
     if call[0] == 'gemm':
         _, M, N, K, nb1, nb2, act, has_res, cdt, has_bias, has_b2 = call
-        a = torch.randn(nb2, nb1, M, K, device=DEV).bfloat16()
-        bs = [torch.randn(nb2, nb1, N, K, device=DEV).bfloat16() for _ in range(NCOPY)]
+        a = torch.randn(nb2, nb1, M, K, device=DEV).half()
+        bs = [torch.randn(nb2, nb1, N, K, device=DEV).half() for _ in range(NCOPY)]
         No = N // 2 if act == 'geglu' else N
-        r = torch.randn(nb2, nb1, M, No, device=DEV).bfloat16() if has_res else None
+        r = torch.randn(nb2, nb1, M, No, device=DEV).half() if has_res else None
         bias = torch.randn(N, device=DEV) if has_bias else None
         b2 = torch.randn(M, N, device=DEV) if has_b2 else None
         fn = lambda i: ops.gemm(a, bs[i % NCOPY], bias=bias, bias2=b2, bias2_rows_per=1 if has_b2 else 0, residual=r, act=act, out_dtype=cdt)
         touch = [a] + ([r] if r is not None else [])
     else:
         _, Ni, H, Wd, Ci, Co, k, stride, ph, pw, Ho, Wo, has_res, odt, has_b2 = call
-        x = torch.randn(Ni, H, Wd, Ci, device=DEV).bfloat16()
-        ws = [torch.randn(Co, k, k, Ci, device=DEV).bfloat16() for _ in range(NCOPY)]
-        r = torch.randn(Ni, Ho, Wo, Co, device=DEV).bfloat16() if has_res else None
+        x = torch.randn(Ni, H, Wd, Ci, device=DEV).half()
+        ws = [torch.randn(Co, k, k, Ci, device=DEV).half() for _ in range(NCOPY)]
+        r = torch.randn(Ni, Ho, Wo, Co, device=DEV).half() if has_res else None
         bias = torch.randn(Co, device=DEV)
         b2 = torch.randn(Ni, Co, device=DEV) if has_b2 else None
         fn = lambda i: ops.conv2d_nhwc(x, ws[i % NCOPY], bias=bias, bias2=b2, residual=r, stride=stride, padding=(ph, pw), out_hw=(Ho, Wo), out_dtype=odt)

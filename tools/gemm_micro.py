@@ -59,34 +59,34 @@ def main():
     torch.manual_seed(0)
     print(f'{"shape":40s} {"dwg us":>8s} {"TFLOP/s":>8s} {"cublas us":>9s} {"ratio":>6s}')
     for M, N, K, act, res in shapes:
-        a = torch.randn(M, K, device=dev).bfloat16()
-        b = torch.randn(N, K, device=dev).bfloat16()
+        a = torch.randn(M, K, device=dev).half()
+        b = torch.randn(N, K, device=dev).half()
         bias = torch.randn(N, device=dev)
-        r = torch.randn(M, N, device=dev).bfloat16() if res else None
+        r = torch.randn(M, N, device=dev).half() if res else None
         t = timeit(lambda: ops.gemm(a, b, bias=bias, act=act, residual=r), iters)
-        tc = 0.0 if ncu else timeit(lambda: torch.addmm(bias.bfloat16(), a, b.t()), iters)
+        tc = 0.0 if ncu else timeit(lambda: torch.addmm(bias.half(), a, b.t()), iters)
         fl = 2.0 * M * N * K
         print(f'{f"gemm M{M} N{N} K{K} {act or chr(45)} res={int(res)}":40s} {t:8.1f} {fl / t / 1e6:8.1f} {tc:9.1f} {t / max(tc, 1e-9):6.2f}', flush=True)
     for Ni, H, W, Ci, Co, k in convs:
-        x = torch.randn(Ni, H, W, Ci, device=dev).bfloat16()
-        w = torch.randn(Co, k, k, Ci, device=dev).bfloat16()
+        x = torch.randn(Ni, H, W, Ci, device=dev).half()
+        w = torch.randn(Co, k, k, Ci, device=dev).half()
         bias = torch.randn(Co, device=dev)
         t = timeit(lambda: ops.conv2d_nhwc(x, w, bias=bias, padding=k // 2), iters)
         tc = 0.0
         if not ncu:
             xc = x.permute(0, 3, 1, 2)          # channels_last NCHW view
             wc = w.permute(0, 3, 1, 2)
-            tc = timeit(lambda: torch.nn.functional.conv2d(xc, wc, bias.bfloat16(), padding=k // 2), iters)
+            tc = timeit(lambda: torch.nn.functional.conv2d(xc, wc, bias.half(), padding=k // 2), iters)
         fl = 2.0 * Ni * H * W * Ci * Co * k * k
         print(f'{f"conv{k}x{k} {Ni}x{H}x{W} {Ci}->{Co}":40s} {t:8.1f} {fl / t / 1e6:8.1f} {tc:9.1f} {t / max(tc, 1e-9):6.2f}', flush=True)
 
     if not ncu:
         for B, h, T, Tk, hd in ((2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 4096, 77, 40), (2, 8, 256, 256, 160 // 1 if False else 128)):
             C = h * hd
-            q = torch.randn(B, T, C, device=dev).bfloat16()
-            k = torch.randn(B, Tk, C, device=dev).bfloat16()
+            q = torch.randn(B, T, C, device=dev).half()
+            k = torch.randn(B, Tk, C, device=dev).half()
             Tkp = (Tk + 7) // 8 * 8
-            vt = torch.randn(B, C, Tkp, device=dev).bfloat16()
+            vt = torch.randn(B, C, Tkp, device=dev).half()
             t = timeit(lambda: ops.attention(q, k, vt, h, Tk), iters)
             sp = lambda x: x.view(B, -1, h, hd).transpose(1, 2)
             v = vt[:, :, :Tk].transpose(1, 2).contiguous()

@@ -10,10 +10,10 @@ from dwg import ops  # noqa: E402
 
 M, N, K = (int(x) for x in sys.argv[1:4])
 res = len(sys.argv) > 4
-a = torch.randn(M, K, device='cuda').bfloat16()
-b = torch.randn(N, K, device='cuda').bfloat16()
+a = torch.randn(M, K, device='cuda').half()
+b = torch.randn(N, K, device='cuda').half()
 bias = torch.randn(N, device='cuda')
-r = torch.randn(M, N, device='cuda').bfloat16() if res else None
+r = torch.randn(M, N, device='cuda').half() if res else None
 for _ in range(5):
     ops.gemm(a, b, bias=bias, residual=r)
 torch.cuda.synchronize()

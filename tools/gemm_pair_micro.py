@@ -60,21 +60,21 @@ def main():
     torch.manual_seed(0)
     for M, N, K in () if '--conv' in sys.argv else ((8192, 4096, 4096), (8192, 320, 320), (8192, 2560, 320), (8192, 320, 1280), (2048, 640, 640), (2048, 5120, 640),
                     (2048, 640, 2560), (512, 1280, 1280), (512, 10240, 1280), (512, 1280, 5120), (4096, 512, 512), (4096, 512, 4096)):
-        a = torch.randn(M, K, device=DEV).bfloat16()
-        bs = [torch.randn(N, K, device=DEV).bfloat16() for _ in range(NCOPY)]
+        a = torch.randn(M, K, device=DEV).half()
+        bs = [torch.randn(N, K, device=DEV).half() for _ in range(NCOPY)]
         run(f'gemm M{M} N{N} K{K}', lambda i: ops.gemm(a, bs[i % NCOPY]), 2.0 * M * N * K, (128, 160, 256))
     if '--tiny-channels' in sys.argv:
         # the 3/8/16/32-channel convolutions at 512^2 / 256^2 (VAE conv_in and its dgrad, ControlNet condition embedding)
         for Ni, H, Ci, Co in ((1, 512, 128, 3), (1, 512, 8, 128), (1, 512, 8, 16), (1, 512, 16, 16), (1, 256, 32, 32), (1, 128, 96, 96)):
-            x = torch.randn(Ni, H, H, Ci, device=DEV).bfloat16()
-            ws = [(torch.randn(Co, 3, 3, Ci, device=DEV) * 0.02).bfloat16() for _ in range(NCOPY)]
-            run(f'conv3x3 {Ni}x{H}x{H} {Ci}->{Co}', lambda i: ops.conv2d_nhwc(x, ws[i % NCOPY], out_dtype=torch.float32 if Co == 3 else torch.bfloat16),
+            x = torch.randn(Ni, H, H, Ci, device=DEV).half()
+            ws = [(torch.randn(Co, 3, 3, Ci, device=DEV) * 0.02).half() for _ in range(NCOPY)]
+            run(f'conv3x3 {Ni}x{H}x{H} {Ci}->{Co}', lambda i: ops.conv2d_nhwc(x, ws[i % NCOPY], out_dtype=torch.float32 if Co == 3 else torch.float16),
                 2.0 * Ni * H * H * Ci * Co * 9, (32, 64, 96, 128), conv=True)
         return
     for Ni, H, Ci, Co in ((1, 512, 128, 128), (1, 256, 256, 256), (1, 128, 512, 512), (1, 64, 512, 512), (2, 64, 320, 320), (2, 32, 640, 640),
                           (2, 16, 1280, 1280), (2, 8, 1280, 1280), (2, 64, 640, 320), (2, 32, 1280, 640)):
-        x = torch.randn(Ni, H, H, Ci, device=DEV).bfloat16()
-        ws = [(torch.randn(Co, 3, 3, Ci, device=DEV) * 0.02).bfloat16() for _ in range(NCOPY)]
+        x = torch.randn(Ni, H, H, Ci, device=DEV).half()
+        ws = [(torch.randn(Co, 3, 3, Ci, device=DEV) * 0.02).half() for _ in range(NCOPY)]
         run(f'conv3x3 {Ni}x{H}x{H} {Ci}->{Co}', lambda i: ops.conv2d_nhwc(x, ws[i % NCOPY]), 2.0 * Ni * H * H * Ci * Co * 9, (128, 160, 256), conv=True)
 
 

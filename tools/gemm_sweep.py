@@ -80,17 +80,17 @@ def main():
     torch.manual_seed(0)
     tot_a = tot_b = 0.0
     for M, N, K, act, res in GEMMS:
-        a = torch.randn(M, K, device=dev).bfloat16()
-        b = torch.randn(N, K, device=dev).bfloat16()
+        a = torch.randn(M, K, device=dev).half()
+        b = torch.randn(N, K, device=dev).half()
         bias = torch.randn(N, device=dev)
-        r = torch.randn(M, N, device=dev).bfloat16() if res else None
+        r = torch.randn(M, N, device=dev).half() if res else None
         ta, tb = sweep(f'gemm M{M} N{N} K{K} {act or "-"} res={int(res)}', lambda: ops.gemm(a, b, bias=bias, act=act, residual=r), act == 'geglu', quick)
         tot_a += ta; tot_b += tb
     for Ni, H, W, Ci, Co, k, res in CONVS:
-        x = torch.randn(Ni, H, W, Ci, device=dev).bfloat16()
-        w = torch.randn(Co, k, k, Ci, device=dev).bfloat16()
+        x = torch.randn(Ni, H, W, Ci, device=dev).half()
+        w = torch.randn(Co, k, k, Ci, device=dev).half()
         bias = torch.randn(Co, device=dev)
-        r = torch.randn(Ni, H, W, Co, device=dev).bfloat16() if res else None
+        r = torch.randn(Ni, H, W, Co, device=dev).half() if res else None
         ta, tb = sweep(f'conv{k}x{k} {Ni}x{H}x{W} {Ci}->{Co} res={int(res)}', lambda: ops.conv2d_nhwc(x, w, bias=bias, residual=r, padding=k // 2), False, quick)
         tot_a += ta; tot_b += tb
     print(f'sum auto {tot_a:.1f} us, sum best {tot_b:.1f} us')

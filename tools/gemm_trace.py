@@ -14,9 +14,9 @@ dev = 'cuda'
 tr = torch.zeros(16, dtype=torch.int64, device=dev)
 names = ['entry', 'setup', 'pdl_wait', 'first_stage', 'last_mma', 'acc_visible', 'last_store', 'drained', 'c0_ld', 'c0_math', 'c0_sts', 'c0_fence', 'c0_store']
 for M, N, K, res in ((128, 32, 64, False), (8192, 320, 320, False), (8192, 320, 320, True), (512, 1280, 1280, True), (128, 1280, 1280, False), (2048, 640, 640, True)):
-    a = torch.randn(M, K, device=dev).bfloat16()
-    b = torch.randn(N, K, device=dev).bfloat16()
-    r = torch.randn(M, N, device=dev).bfloat16() if res else None
+    a = torch.randn(M, K, device=dev).half()
+    b = torch.randn(N, K, device=dev).half()
+    r = torch.randn(M, N, device=dev).half() if res else None
     bias = torch.randn(N, device=dev)
     for _ in range(3):
         ops.gemm(a, b, bias=bias, residual=r)

@@ -22,8 +22,8 @@ def rel(a, b):
 
 def check(bo, pair, N, H, Ci, Co):
     torch.manual_seed(1)
-    x = torch.randn(N, H, H, Ci, device=DEV).bfloat16()
-    w = (torch.randn(Co, 3, 3, Ci, device=DEV) / (9 * Ci) ** 0.5).bfloat16()
+    x = torch.randn(N, H, H, Ci, device=DEV).half()
+    w = (torch.randn(Co, 3, 3, Ci, device=DEV) / (9 * Ci) ** 0.5).half()
     bias = torch.randn(Co, device=DEV)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
     L.dwg_gemm_tune_halo(1, bo)

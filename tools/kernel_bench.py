@@ -56,13 +56,13 @@ def report(name, ms, best, algo_bytes, pk, src, **extra):
 def gemm_bench(pk, src):
     torch.manual_seed(0)
     for (M, N, K) in ((8192, 320, 320), (8192, 1280, 320), (8192, 4096, 4096), (2048, 1280, 1280)):
-        a = torch.randn(M, K, device=DEV).bfloat16(); b = torch.randn(N, K, device=DEV).bfloat16()
+        a = torch.randn(M, K, device=DEV).half(); b = torch.randn(N, K, device=DEV).half()
         ms, best = timeit(lambda: ops.gemm(a, b), iters=10)
         tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
         ms2, _ = timeit(lambda: a @ b.t(), iters=10)
         print(json.dumps({'kernel': f'tcgen05_gemm_{M}x{N}x{K}', 'ms': round(ms, 4), 'TFLOPs': round(tf, 1), 'frac_of_bf16_peak': round(tf / pk['bf16_tflops'], 3), 'cublas_ms': round(ms2, 4), 'peak': src}), flush=True)
     for (Nn, H, C, Co) in ((2, 64, 320, 320), (2, 32, 640, 640), (2, 16, 1280, 1280), (1, 256, 128, 128), (1, 512, 128, 128)):
-        x = torch.randn(Nn, H, H, C, device=DEV).bfloat16(); w = (torch.randn(Co, 3, 3, C, device=DEV) * 0.02).bfloat16()
+        x = torch.randn(Nn, H, H, C, device=DEV).half(); w = (torch.randn(Co, 3, 3, C, device=DEV) * 0.02).half()
         ms, best = timeit(lambda: ops.conv2d_nhwc(x, w), iters=10)
         tf = 2.0 * Nn * H * H * Co * C * 9 / (ms * 1e-3) / 1e12
         xc = x.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last); wc = w.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)

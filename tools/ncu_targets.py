@@ -19,20 +19,20 @@ torch.manual_seed(0)
 
 def gemm_part():
     for (M, N, K) in ((8192, 320, 320), (8192, 4096, 4096), (512, 1280, 1280)):
-        a = torch.randn(M, K, device=DEV).bfloat16(); b = torch.randn(N, K, device=DEV).bfloat16()
-        res = torch.randn(M, N, device=DEV).bfloat16(); bias = torch.randn(N, device=DEV)
+        a = torch.randn(M, K, device=DEV).half(); b = torch.randn(N, K, device=DEV).half()
+        res = torch.randn(M, N, device=DEV).half(); bias = torch.randn(N, device=DEV)
         for _ in range(2):
             ops.gemm(a, b, bias=bias, residual=res)
-    x = torch.randn(2, 64, 64, 320, device=DEV).bfloat16(); w = (torch.randn(320, 3, 3, 320, device=DEV) * 0.02).bfloat16()
+    x = torch.randn(2, 64, 64, 320, device=DEV).half(); w = (torch.randn(320, 3, 3, 320, device=DEV) * 0.02).half()
     for _ in range(2):
         ops.conv2d_nhwc(x, w)
-    x = torch.randn(1, 512, 512, 128, device=DEV).bfloat16(); w = (torch.randn(128, 3, 3, 128, device=DEV) * 0.02).bfloat16()
+    x = torch.randn(1, 512, 512, 128, device=DEV).half(); w = (torch.randn(128, 3, 3, 128, device=DEV) * 0.02).half()
     ops.conv2d_nhwc(x, w)
-    q = torch.randn(2, 4096, 320, device=DEV).bfloat16(); k = torch.randn(2, 4096, 320, device=DEV).bfloat16()
-    vt = torch.randn(2, 320, 4096, device=DEV).bfloat16()
+    q = torch.randn(2, 4096, 320, device=DEV).half(); k = torch.randn(2, 4096, 320, device=DEV).half()
+    vt = torch.randn(2, 320, 4096, device=DEV).half()
     for _ in range(2):
         ops.attention(q, k, vt, 8, 4096)
-    gx = torch.randn(2, 64, 64, 320, device=DEV).bfloat16()
+    gx = torch.randn(2, 64, 64, 320, device=DEV).half()
     ops.group_norm(gx, torch.ones(320, device=DEV), torch.zeros(320, device=DEV), 32, 1e-5, True)
 
 
@@ -54,26 +54,26 @@ def geom_part():
 
 
 def nn_part():
-    x = torch.randn(2, 64, 64, 320, device=DEV).bfloat16()
+    x = torch.randn(2, 64, 64, 320, device=DEV).half()
     g, b = torch.ones(320, device=DEV), torch.zeros(320, device=DEV)
     for _ in range(2):
         ops.group_norm(x, g, b, 32, 1e-5, True)
-    t = torch.randn(8192, 320, device=DEV).bfloat16()
+    t = torch.randn(8192, 320, device=DEV).half()
     for _ in range(2):
         ops.layer_norm(t, g, b)
-    gg = torch.randn(8192, 2560, device=DEV).bfloat16()
+    gg = torch.randn(8192, 2560, device=DEV).half()
     for _ in range(2):
         ops.geglu(gg)
     for _ in range(2):
         ops.add(x, x)
-    xv = torch.randn(1, 512, 512, 128, device=DEV).bfloat16()
+    xv = torch.randn(1, 512, 512, 128, device=DEV).half()
     gv, bv = torch.ones(128, device=DEV), torch.zeros(128, device=DEV)
     y, st = ops.group_norm(xv, gv, bv, 32, 1e-6, True, return_stats=True)
     ops.group_norm_bwd(xv, y, st, gv, bv, 32, 1e-6, True)
-    a = torch.randn(128, 1280, device=DEV).bfloat16(); w = torch.randn(1280, 1280, device=DEV).bfloat16()
+    a = torch.randn(128, 1280, device=DEV).half(); w = torch.randn(1280, 1280, device=DEV).half()
     for _ in range(2):
         ops.gemm(a, w)                      # split-K + finalize
-    a2 = torch.randn(2, 320, device=DEV).bfloat16(); w2 = torch.randn(1280, 320, device=DEV).bfloat16()
+    a2 = torch.randn(2, 320, device=DEV).half(); w2 = torch.randn(1280, 320, device=DEV).half()
     for _ in range(2):
         ops.gemm(a2, w2, act='silu')
 

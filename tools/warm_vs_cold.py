@@ -42,15 +42,15 @@ torch.manual_seed(0)
 tot_c = tot_w = 0.0
 for (M, N, K, cnt) in ((512, 1280, 1280, 35), (512, 10240, 1280, 7), (512, 1280, 5120, 7), (128, 1280, 1280, 12), (2048, 640, 640, 35), (2048, 5120, 640, 7),
                        (2048, 640, 2560, 7), (8192, 320, 320, 35)):
-    a = torch.randn(M, K, device=DEV).bfloat16()
-    bs = [torch.randn(N, K, device=DEV).bfloat16() for _ in range(8)]
+    a = torch.randn(M, K, device=DEV).half()
+    bs = [torch.randn(N, K, device=DEV).half() for _ in range(8)]
     c = timeit(lambda i: ops.gemm(a, bs[i]), 8, False)
     w = timeit(lambda i: ops.gemm(a, bs[i]), 1, True)
     tot_c += c * cnt; tot_w += w * cnt
     print(f'gemm M{M} N{N} K{K}: cold {c:6.1f} us  warm {w:6.1f} us  x{cnt}', flush=True)
 for (Ni, H, Ci, Co, cnt) in ((2, 8, 1280, 1280, 19), (2, 16, 1280, 1280, 10), (2, 8, 2560, 1280, 3), (2, 16, 2560, 1280, 2), (2, 32, 640, 640, 9), (2, 32, 1280, 640, 1)):
-    x = torch.randn(Ni, H, H, Ci, device=DEV).bfloat16()
-    ws = [(torch.randn(Co, 3, 3, Ci, device=DEV) * 0.02).bfloat16() for _ in range(8)]
+    x = torch.randn(Ni, H, H, Ci, device=DEV).half()
+    ws = [(torch.randn(Co, 3, 3, Ci, device=DEV) * 0.02).half() for _ in range(8)]
     c = timeit(lambda i: ops.conv2d_nhwc(x, ws[i]), 8, False)
     w = timeit(lambda i: ops.conv2d_nhwc(x, ws[i]), 1, True)
     tot_c += c * cnt; tot_w += w * cnt
