@@ -102,11 +102,12 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- dwg arm
-class Scene:
-    """Everything one rank needs: avatar, renderer, guidance, per-step inputs."""
+class Workload:
+    """Everything one rank needs, built from the PACKAGE's public objects (dwg.step.Scene / SDSTrainStep are the R17 API;
+    nothing of the step lives in this file any more): avatar, renderer, guidance, per-step inputs."""
 
-    def __init__(self, device, rank, n_unc=N_UNCONSTRAINED, n_tri=N_MESH_TRI, img=IMG, tiny=False):
-        from dwg import avatar as dav, synth
+    def __init__(self, device, rank, n_unc=N_UNCONSTRAINED, n_tri=N_MESH_TRI, img=IMG, tiny=False, allreduce=False):
+        from dwg import avatar as dav, step as dstep, synth
         from dwg.diffusion import guidance as G, weights as W
         self.dev, self.rank, self.img = device, rank, img
         model = synth.make_body_model(0)
@@ -118,7 +119,7 @@ class Scene:
         self.renderer = dav.GaussianRenderer()
         cfg, vcfg = (W.TINY, W.TINY_VAE) if tiny else (W.SD15, W.VAE15)
         self.guidance = G.ControlNetScoreDistillation(W.make_unet(cfg), W.make_controlnet(cfg), W.make_vae_encoder(vcfg), cfg, vcfg, device,
-                                                      seed=1000 + rank)
+                                                      seed=1000 + rank, default_image_size=img)
         self.ctx_dim = cfg['ctx_dim']
         self.rng = np.random.default_rng(1000 + rank)          # dwg.parallel.rank_seed(1000, rank)
         self.pose_rows = poses()
@@ -129,156 +130,67 @@ class Scene:
         self.h_cond = cond.pin_memory()
         self.d_embeds = {k: v.to(device) for k, v in self.h_embeds.items()}
         self.d_cond = self.h_cond.to(device)
-        self.params = [p for p in self.avatar.parameters() if p.requires_grad]
+        self.scene = dstep.Scene(self.avatar, self.renderer)
+        self.trainer = dstep.SDSTrainStep(self.scene, self.guidance, self.d_embeds, allreduce=allreduce)
+        self.params = self.trainer.params
         self.step_i = 0
 
-    def next_view(self):
+    def next_view(self, device_inputs=True):
+        """The reference's per-step ``data`` dict (camera fields of data/camera/utils.py:301-357 + smpl_inputs + cond_images)."""
         from dwg import camera, synth
         row = self.pose_rows[self.step_i % len(self.pose_rows)]
         self.step_i += 1
-        pose = synth.pose_from_row(row)
         data = camera.random_camera(self.rng, self.img, self.img)
-        return pose, data
-
-    def step(self, pose_dev, data, embeds, cond):
-        for p in self.params:
-            p.grad = None
-        self.guidance.prepare(embeds, cond)
-        gs = self.avatar.animate(pose_dev)
-        out = self.renderer.render(data, gs)
-        res = self.guidance(out['image_chw'].unsqueeze(0), embeds, cond_inputs=cond)
-        res['diffusion_loss'].backward()
-        return res
-
-
-class StepGraph:
-    """The WHOLE SDS step (animate -> raster -> VAE -> ControlNet+UNet -> SDS -> backward to every
-    avatar parameter) captured as ONE CUDA graph.  Per-step inputs live in static device buffers
-    (pose, device-resident camera struct, prompt embeddings, condition image); noise / timestep are
-    drawn inside the graph from torch's graph-safe default generator."""
-
-    def __init__(self, sc):
-        from dwg import ops
-        self.sc, dev = sc, sc.dev
-        g = sc.guidance
-        g._g = None
-        g.use_default_generator = True
-        pose, data = sc.next_view()
-        self.data = data                                   # image size / template; matrices come from cam_dev
-        self.pose = {k: v.to(dev).clone() for k, v in pose.items()}
-        self.cam = torch.zeros(ops.CAMERA_WORDS, device=dev)
-        self.embeds = {k: v.clone() for k, v in sc.d_embeds.items()}
-        self.cond = sc.d_cond.clone()
-        self.set_camera(data)
-
-        def body():
-            for p in sc.params:
-                p.grad = None
-            sc.guidance.prepare(self.embeds, self.cond)          # prompt / condition / timestep work starts on the side stream
-            gs = sc.avatar.animate(self.pose)
-            out = sc.renderer.render(self.data, gs, cam_dev=self.cam)
-            res = sc.guidance(out['image_chw'].unsqueeze(0), self.embeds, cond_inputs=self.cond)
-            res['diffusion_loss'].backward()
-            return res['gradients'].abs().mean(), res['timestep']
-        from dwg._lib import lib
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                body()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = lib().launches
-        with torch.cuda.graph(self.graph):
-            self.out = body()
-        self.launches = lib().launches - n0
-        torch.cuda.synchronize()
-
-    def pack_camera(self, data, out=None):
-        from dwg import camera, ops
-        view, proj, campos, tfx, tfy = camera.raster_matrices(data)
-        return ops.pack_camera(data['image_height'], data['image_width'], tfx, tfy, view, proj, self.sc.renderer.bg_color, 1.0, out=out)
-
-    def set_camera(self, data):
-        self.cam.copy_(self.pack_camera(data))
-
-    def replay(self):
-        from dwg._lib import lib
-        self.graph.replay()
-        L = lib()
-        object.__setattr__(L, 'launches', L.launches + self.launches)
-        return self.out
-
-
-def flat_grads(params):
-    return torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+        data['smpl_inputs'] = synth.pose_from_row(row)                               # host tensors; staged through pinned memory
+        data['cond_images'] = self.d_cond if device_inputs else self.h_cond
+        return data
 
 
 def run_dwg(args):
     import torch.distributed as dist
-    from dwg import _lib, ops, parallel
+    from dwg import _lib, ops
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     torch.cuda.set_device(local_rank)
     dev = f'cuda:{local_rank}'
-    # the avatar MLPs are still torch nn.Linear (DESIGN.md section 6): run them on the TF32 tensor-core path
-    torch.backends.cuda.matmul.allow_tf32 = True
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(dev))
     pk, pk_src = peaks()
-    sc = Scene(dev, rank, tiny=args.tiny, n_unc=args.n_unconstrained, img=args.image)
-    sg = None
+    sc = Workload(dev, rank, tiny=args.tiny, n_unc=args.n_unconstrained, img=args.image, allreduce=world > 1)
+    tr = sc.trainer
+    graphed = False
     if not args.no_graphs and not args.no_step_graph:
         try:
-            sg = StepGraph(sc)
+            tr.capture(sc.next_view())
+            graphed = True
         except Exception as e:                       # fall back to sub-graphs (reported in config)
             print(f'[bench] whole-step graph capture failed ({type(e).__name__}: {e}); using sub-graphs', file=sys.stderr)
-            sg = None
+            tr._graph = None
             torch.cuda.synchronize()
-    if sg is None and not args.no_graphs:
+    if not graphed and not args.no_graphs:
         sc.guidance.use_default_generator = False
         sc.guidance.enable_graphs((args.image, args.image))
     L = _lib.lib()
-    pin = lambda t: t.pin_memory()
-    h_cam = pin(torch.zeros(ops.CAMERA_WORDS))
+    host_parts = {}
 
     def one_step(e2e):
-        pose, data = sc.next_view()
-        if sg is not None:
-            # static-buffer updates + ONE graph replay
-            sg.pack_camera(data, out=h_cam)
-            if e2e:
-                for k, v in pose.items():
-                    sg.pose[k].copy_(pin(v), non_blocking=True)
-                for k, v in sc.h_embeds.items():
-                    sg.embeds[k].copy_(v, non_blocking=True)
-                sg.cond.copy_(sc.h_cond, non_blocking=True)
-            else:
-                for k, v in pose.items():
-                    sg.pose[k].copy_(v, non_blocking=True)
-            sg.cam.copy_(h_cam, non_blocking=True)
-            metric, tstep = sg.replay()
-            if world > 1:
-                parallel.allreduce_grads(sc.params)
-            if e2e:
-                return float(metric), int(tstep[0])
-            return None
+        # e2e: this step's inputs come from (pinned) HOST memory -- pose, camera struct, prompt embeddings, condition image
+        data = sc.next_view(device_inputs=not e2e)
         if e2e:
-            # per-step host -> device copies of that step's inputs (pinned memory, async)
-            pose_dev = {k: v.pin_memory().to(dev, non_blocking=True) for k, v in pose.items()}
-            embeds = {k: v.to(dev, non_blocking=True) for k, v in sc.h_embeds.items()}
-            cond = sc.h_cond.to(dev, non_blocking=True)
-        else:
-            pose_dev = {k: v.to(dev) for k, v in pose.items()}
-            embeds, cond = sc.d_embeds, sc.d_cond
-        res = sc.step(pose_dev, data, embeds, cond)
-        if world > 1:
-            parallel.allreduce_grads(sc.params)      # ONE NCCL all-reduce of every parameter gradient
+            if graphed:
+                tr.set_text_embeds(sc.h_embeds)
+            else:
+                tr.text_embeds_dict = {k: v.to(dev, non_blocking=True) for k, v in sc.h_embeds.items()}
+                data['cond_images'] = sc.h_cond.to(dev, non_blocking=True)
+        if not graphed:
+            data['smpl_inputs'] = {k: v.pin_memory().to(dev, non_blocking=True) for k, v in data['smpl_inputs'].items()}
+        loss, ro, so, _ = tr.step(data)                 # ONE graph replay (+ ONE NCCL all-reduce of the flat gradient buffer when N > 1)
+        for k, v in tr.host_ms.items():
+            host_parts[k] = host_parts.get(k, 0.0) + v
         if e2e:
             # device -> host read of the step's result
-            return float(res['gradients'].abs().mean()), int(res['timestep'][0])
+            return float(so['gradients'].abs().mean()), int(so['timestep'][0])
         return None
 
     cpu_ms = [0.0]
@@ -378,16 +290,19 @@ def run_dwg(args):
     e2e_v = world * 1000.0 / ms_e2e
     h2d = sc.h_cond.numel() * 4 + sum(v.numel() * 4 for v in sc.h_embeds.values()) + 265 * 4
     out = {
-        'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)', 'value': round(value, 3), 'unit': 'steps/s', 'n_gpus': world,
+        'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)' + ('' if world == 1 else ' -- single-view SDS steps (views) per second of the whole job'),
+        'value': round(value, 3), 'unit': 'steps/s' if world == 1 else 'views/s', 'n_gpus': world,
+        'optimizer_steps_per_s': round(1000.0 / ms_step, 3),
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_step, 3), 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'bf16 tensor-core GEMMs (fp32 accumulate); fp32 geometry/raster', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': 'f16 tensor-core GEMMs (fp32 accumulate in TMEM), fp16 activations; fp32 geometry/raster', 'data': 'synthetic',
         'config': {'workload': WORKLOAD if not args.tiny else 'TINY smoke configuration (not the benchmark workload)',
                    'gaussians': int(sc.avatar._positions.shape[0] + sum(m._scales.shape[0] for m in sc.avatar.mesh_binding_gaussians.values())),
                    'image': args.image, 'views_per_step': world, 'parallelism': f'view-dp{world} + 1 NCCL all-reduce' if world > 1 else 'single GPU',
-                   'cache': 'inputs larger than L2 (2.6 GB of bf16 weights streamed every step; 126 MB L2)',
-                   'cuda_graphs': ('whole step' if sg is not None else ('sub-graphs' if not args.no_graphs else False))},
+                   'cache': 'inputs larger than L2 (2.6 GB of fp16 weights streamed every step; 126 MB L2)',
+                   'cuda_graphs': ('whole step' if graphed else ('sub-graphs' if not args.no_graphs else False))},
         'e2e': {'value': round(e2e_v, 3), 'unit': 'steps/s', 'ms_per_step': round(ms_e2e, 3), 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 12},
-        'gpu_launches': int(round(launches)), 'host_enqueue_ms_per_step': round(cpu_enqueue_ms, 3), 'clocks': clocks, 'roofline': roof,
+        'gpu_launches': int(round(launches)), 'host_enqueue_ms_per_step': round(cpu_enqueue_ms, 3),
+        'host_ms_parts_per_step': {k: round(v / max(1, 2 * args.steps + args.warmup + min(2, args.warmup)), 3) for k, v in host_parts.items()}, 'clocks': clocks, 'roofline': roof,
         'roofline_raster': roof_r,
     }
     if not args.skip_cpu_baseline:
@@ -402,7 +317,8 @@ def raster_roofline(sc, img, pk, pk_src):
     Algorithmic bytes: fwd 56 N + 24 P + 44 P + 28 HW, bwd 44 P + 32 HW + 124 N, P measured on this view."""
     from dwg import camera, ops
     dev = sc.dev
-    pose, data = sc.next_view()
+    data = sc.next_view()
+    pose = data['smpl_inputs']
     with torch.no_grad():
         gs = sc.avatar.animate({k: v.to(dev) for k, v in pose.items()})
     view, proj, campos, tfx, tfy = camera.raster_matrices(data)

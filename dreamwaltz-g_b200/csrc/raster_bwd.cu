@@ -61,6 +61,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                   const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                   const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
                   const float* __restrict__ dL_dalpha,
+                  const float* __restrict__ bg_image, const float* __restrict__ out_alpha, float* __restrict__ g_bg_image,
                   float* __restrict__ g_mean2D /* [N,3] */, float4* __restrict__ g_conic_depth /* [N] */,
                   float* __restrict__ g_opacity, float* __restrict__ g_color /* [N,3] */) {
     __shared__ __align__(128) Rec s_rec[2][CHUNK];
@@ -75,19 +76,28 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     const float pxf = (float)px, pyf = (float)py;
     const uint2 rg = ranges[tile];
     const int n = (int)(rg.y - rg.x);
-    if (n <= 0) return;
-    const Rec* src = recs + rg.x;
     const size_t pix = (size_t)py * W + px;
     const size_t HW = (size_t)H * W;
-    const uint32_t last_contributor = inside ? n_contrib[pix] : 0u;
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
     float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLd = 0.f, dLa = 0.f;
     if (inside) {
         dLp0 = dL_dcolor[pix]; dLp1 = dL_dcolor[HW + pix]; dLp2 = dL_dcolor[2 * HW + pix];
         if (dL_ddepth) dLd = dL_ddepth[pix];
         if (dL_dalpha) dLa = dL_dalpha[pix];
+        if (bg_image) {
+            // backward of image = image_fg + image_bg * (1 - alpha)  (scene.py:153-166): the composite only adds a term to
+            // dL/dalpha and yields dL/dimage_bg = dL/dimage * (1 - alpha); dL/dimage_fg = dL/dimage unchanged
+            dLa -= bg_image[pix] * dLp0 + bg_image[HW + pix] * dLp1 + bg_image[2 * HW + pix] * dLp2;
+            if (g_bg_image) {
+                const float k = 1.0f - out_alpha[pix];
+                g_bg_image[pix] = dLp0 * k; g_bg_image[HW + pix] = dLp1 * k; g_bg_image[2 * HW + pix] = dLp2 * k;
+            }
+        }
     }
+    if (n <= 0) return;
+    const Rec* src = recs + rg.x;
+    const uint32_t last_contributor = inside ? n_contrib[pix] : 0u;
+    const float T_final = inside ? final_T[pix] : 0.f;
+    float T = T_final;
     // tile-wide max of n_contrib: chunks beyond it are never touched
     uint32_t mx = last_contributor;
     for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
@@ -372,9 +382,10 @@ extern "C" int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N, const 
                                    const void* img, const float* dL_dcolor, const float* dL_ddepth,
                                    const float* dL_dalpha, float* g_means3D, float* g_means2D, float* g_colors,
                                    float* g_opacities, float* g_scales, float* g_rotations, void* scratch,
-                                   const void* cam_dev, void* stream) {
+                                   const void* cam_dev, const float* bg_image, const float* out_alpha, float* g_bg_image, void* stream) {
     (void)colors_precomp; (void)opacities;
     DWG_REQUIRE(cam && geom && bin && img && dL_dcolor && scratch, "null pointer");
+    DWG_REQUIRE(!g_bg_image || (bg_image && out_alpha), "g_bg_image needs bg_image and the forward's out_alpha");
     DWG_REQUIRE(N == 0 || (means3D && scales && rotations && g_means3D && g_means2D && g_colors && g_opacities && g_scales && g_rotations),
                 "null gradient buffer");
     if (N == 0) return DWG_OK;
@@ -393,7 +404,7 @@ extern "C" int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N, const 
     cudaMemsetAsync(gcd, 0, sizeof(float4) * N, st);
     render_bwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2], cd ? cd->bg : nullptr,
                                                         im.final_T, im.n_contrib, dL_dcolor, dL_ddepth, dL_dalpha,
-                                                        g_means2D, gcd, g_opacities, g_colors);
+                                                        bg_image, out_alpha, g_bg_image, g_means2D, gcd, g_opacities, g_colors);
     preprocess_bwd_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, means3D, scales, rotations, *cam, cd, g, g_means2D, gcd,
                                                                      g_means3D, g_scales, g_rotations);
     return check_launch("dwg_raster_backward");

@@ -22,6 +22,7 @@ constexpr int FWD_BATCH = 4;      // touched instances whose alphas are evaluate
 __global__ void __launch_bounds__(TILE_PIX)
 render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
                   float bg0, float bg1, float bg2, const float* __restrict__ bg_dev,
+                  const float* __restrict__ bg_image, float* __restrict__ out_fg,
                   float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
                   float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
     __shared__ __align__(128) Rec s_rec[2][CHUNK];
@@ -133,9 +134,18 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
         const size_t HW = (size_t)H * W;
         final_T[pix] = T;
         n_contrib[pix] = last;
-        out_color[pix] = __fadd_rn(C0, __fmul_rn(T, bg0));
-        out_color[HW + pix] = __fadd_rn(C1, __fmul_rn(T, bg1));
-        out_color[2 * HW + pix] = __fadd_rn(C2, __fmul_rn(T, bg2));
+        float o0 = __fadd_rn(C0, __fmul_rn(T, bg0)), o1 = __fadd_rn(C1, __fmul_rn(T, bg1)), o2 = __fadd_rn(C2, __fmul_rn(T, bg2));
+        if (bg_image) {
+            // R13 (core/system/scene.py:153-166) fused into the epilogue: image = image_fg + image_bg * (1 - alpha)
+            if (out_fg) { out_fg[pix] = o0; out_fg[HW + pix] = o1; out_fg[2 * HW + pix] = o2; }
+            const float k = __fsub_rn(1.0f, A);
+            o0 = __fadd_rn(o0, __fmul_rn(bg_image[pix], k));
+            o1 = __fadd_rn(o1, __fmul_rn(bg_image[HW + pix], k));
+            o2 = __fadd_rn(o2, __fmul_rn(bg_image[2 * HW + pix], k));
+        }
+        out_color[pix] = o0;
+        out_color[HW + pix] = o1;
+        out_color[2 * HW + pix] = o2;
         out_depth[pix] = D;
         out_alpha[pix] = A;
     }
@@ -158,7 +168,7 @@ extern "C" int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N, const f
                                   const float* colors_precomp, const float* opacities, const float* scales,
                                   const float* rotations, float* out_color, float* out_depth, float* out_alpha,
                                   int32_t* radii, void* geom, void* bin, int64_t P_cap, void* img,
-                                  int32_t* status, const void* cam_dev, void* stream) {
+                                  int32_t* status, const void* cam_dev, const float* bg_image, float* out_color_fg, void* stream) {
     DWG_REQUIRE(cam && out_color && out_depth && out_alpha && geom && bin && img && status, "null pointer");
     DWG_REQUIRE(N == 0 || (means3D && colors_precomp && opacities && scales && rotations && radii), "null input");
     DWG_REQUIRE(cam->image_height > 0 && cam->image_width > 0, "bad image size");
@@ -177,7 +187,7 @@ extern "C" int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N, const f
     rc = launch_sort(T, b, g, colors_precomp, status, P_cap, 1, st);
     if (rc != DWG_OK) return rc;
     render_fwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2], cd ? cd->bg : nullptr,
-                                                        out_color, out_depth, out_alpha, im.final_T, im.n_contrib);
+                                                        bg_image, out_color_fg, out_color, out_depth, out_alpha, im.final_T, im.n_contrib);
     return check_launch("dwg_raster_forward");
 }
 

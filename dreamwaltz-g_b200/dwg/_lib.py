@@ -43,10 +43,10 @@ SIGNATURES = {
     'dwg_raster_img_bytes': (c_int64, [c_int, c_int]),
     'dwg_raster_bwd_scratch_bytes': (c_int64, [c_int64]),
     'dwg_raster_forward': (c_int, [ctypes.POINTER(DwgRasterCamera), c_int64] + [c_void_p] * 9 +
-                           [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                           [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'dwg_raster_backward': (c_int, [ctypes.POINTER(DwgRasterCamera), c_int64] + [c_void_p] * 5 +
                             [c_void_p, c_void_p, c_int64, c_void_p] + [c_void_p] * 3 + [c_void_p] * 6 +
-                            [c_void_p, c_void_p, c_void_p]),
+                            [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'dwg_gemm_f16': (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                               c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_float, c_int, c_void_p]),

@@ -207,7 +207,8 @@ class GaussianRenderer:
         self.sh_levels = sh_levels
         self.bg_color = torch.tensor(bg_color)
 
-    def render(self, data: dict, gaussians: GaussianOutput, return_2d_radii: bool = False, cam_dev=None) -> dict:
+    def render(self, data: dict, gaussians: GaussianOutput, return_2d_radii: bool = False, cam_dev=None, bg_image=None) -> dict:
+        """bg_image [1,H,W,3] / [3,H,W] (optional): composited in the blend epilogue, outputs then carry image_fg too."""
         from .camera import raster_matrices
         view, proj, campos, tanfovx, tanfovy = raster_matrices(data)         # host tensors: no device sync
         means3D = gaussians.positions
@@ -215,12 +216,18 @@ class GaussianRenderer:
         colors = gaussians.colors
         if colors is None:
             colors = ops.sh_colors(gaussians.sh_features, means3D, campos.to(means3D.device), self.sh_levels)
-        img, radii, depth, alpha = ops.rasterize(
+        H, W = data['image_height'], data['image_width']
+        if bg_image is not None and bg_image.shape[-1] == 3:                 # reference layout [1,H,W,3] -> planar
+            bg_image = bg_image.reshape(H, W, 3).permute(2, 0, 1).contiguous()
+        res = ops.rasterize(
             means3D, screenspace_points, colors, gaussians.opacities, gaussians.scales, gaussians.quaternions,
-            image_height=data['image_height'], image_width=data['image_width'], tanfovx=tanfovx, tanfovy=tanfovy,
-            viewmatrix=view, projmatrix=proj, bg=self.bg_color, cam_dev=cam_dev)
+            image_height=H, image_width=W, tanfovx=tanfovx, tanfovy=tanfovy,
+            viewmatrix=view, projmatrix=proj, bg=self.bg_color, cam_dev=cam_dev, bg_image=bg_image)
+        img, radii, depth, alpha = res[:4]
         out = {'image': img.permute(1, 2, 0).unsqueeze(0), 'depth': depth.permute(1, 2, 0).unsqueeze(0),
                'alpha': alpha.permute(1, 2, 0).unsqueeze(0), 'image_chw': img}
+        if bg_image is not None:
+            out['image_fg'] = res[4].permute(1, 2, 0).unsqueeze(0)
         if return_2d_radii:
             out['radii'] = radii
             out['viewspace_points'] = screenspace_points

@@ -341,7 +341,7 @@ STATUS_MONITOR = _StatusMonitor()
 
 class _Rasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, means2D, colors, opacities, scales, rotations, cam_args, state_out):
+    def forward(ctx, means3D, means2D, colors, opacities, scales, rotations, bg_image, cam_args, state_out):
         H, W, tanfovx, tanfovy, viewmatrix, projmatrix, bg, scale_modifier, P_cap, cam_dev = cam_args
         dev = means3D.device
         means3D, colors, scales, rotations = f32c(means3D), f32c(colors), f32c(scales), f32c(rotations)
@@ -363,21 +363,31 @@ class _Rasterize(torch.autograd.Function):
         color = torch.empty(3, H, W, device=dev, dtype=torch.float32)
         depth = torch.empty(1, H, W, device=dev, dtype=torch.float32)
         alpha = torch.empty(1, H, W, device=dev, dtype=torch.float32)
+        bgi = None
+        color_fg = color
+        if bg_image is not None:
+            bgi = f32c(bg_image).reshape(3, H, W)
+            color_fg = torch.empty(3, H, W, device=dev, dtype=torch.float32)
         check(L.dwg_raster_forward(ctypes.byref(cam), N, ptr(means3D), ptr(colors), ptr(opac), ptr(scales),
                                    ptr(rotations), ptr(color), ptr(depth), ptr(alpha), ptr(st.radii), ptr(st.geom),
-                                   ptr(st.bin), P_cap, ptr(st.img), ptr(st.status), ptr(cam_dev), stream()), 'dwg_raster_forward')
+                                   ptr(st.bin), P_cap, ptr(st.img), ptr(st.status), ptr(cam_dev), ptr(bgi),
+                                   ptr(color_fg) if bgi is not None else None, stream()), 'dwg_raster_forward')
         STATUS_MONITOR.post(st.status)
-        ctx.save_for_backward(means3D, colors, opac, scales, rotations)
+        ctx.save_for_backward(means3D, colors, opac, scales, rotations, bgi, alpha if bgi is not None else None)
         ctx.st = st
         ctx.opac_shape = opacities.shape
+        ctx.bg_shape = None if bg_image is None else bg_image.shape
         if state_out is not None:
             state_out.append(st)
         ctx.mark_non_differentiable(st.radii)
-        return color, st.radii, depth, alpha
+        if bgi is not None:
+            ctx.mark_non_differentiable(color_fg)
+            return color, st.radii, depth, alpha, color_fg
+        return color, st.radii, depth, alpha, color.detach()
 
     @staticmethod
-    def backward(ctx, g_color, _g_radii, g_depth, g_alpha):
-        means3D, colors, opac, scales, rotations = ctx.saved_tensors
+    def backward(ctx, g_color, _g_radii, g_depth, g_alpha, _g_fg):
+        means3D, colors, opac, scales, rotations, bgi, alpha = ctx.saved_tensors
         st = ctx.st
         N, dev = st.N, means3D.device
         L = lib()
@@ -386,20 +396,27 @@ class _Rasterize(torch.autograd.Function):
         g_alpha = f32c(g_alpha) if g_alpha is not None else None
         e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
         g_m3, g_m2, g_c, g_o, g_s, g_r = e(N, 3), e(N, 3), e(N, 3), e(N), e(N, 3), e(N, 4)
+        g_bg = e(3, st.H, st.W) if (bgi is not None and ctx.needs_input_grad[6]) else None
         scratch = torch.empty(int(L.dwg_raster_bwd_scratch_bytes(N)), device=dev, dtype=torch.uint8)
         check(L.dwg_raster_backward(ctypes.byref(st.cam), N, ptr(means3D), ptr(colors), ptr(opac), ptr(scales),
                                     ptr(rotations), ptr(st.geom), ptr(st.bin), st.P_cap, ptr(st.img), ptr(g_color),
                                     ptr(g_depth), ptr(g_alpha), ptr(g_m3), ptr(g_m2), ptr(g_c), ptr(g_o), ptr(g_s),
-                                    ptr(g_r), ptr(scratch), ptr(st.cam_dev), stream()), 'dwg_raster_backward')
-        return g_m3, g_m2, g_c, g_o.reshape(ctx.opac_shape), g_s, g_r, None, None
+                                    ptr(g_r), ptr(scratch), ptr(st.cam_dev), ptr(bgi), ptr(alpha), ptr(g_bg), stream()), 'dwg_raster_backward')
+        if g_bg is not None:
+            g_bg = g_bg.reshape(ctx.bg_shape)
+        return g_m3, g_m2, g_c, g_o.reshape(ctx.opac_shape), g_s, g_r, g_bg, None, None
 
 
 def rasterize(means3D, means2D, colors, opacities, scales, rotations, *, image_height, image_width, tanfovx,
-              tanfovy, viewmatrix, projmatrix, bg, scale_modifier=1.0, instance_capacity=None, state_out=None, cam_dev=None):
-    """Differentiable tile rasteriser -> (color [3,H,W], radii i32 [N], depth [1,H,W], alpha [1,H,W])."""
+              tanfovy, viewmatrix, projmatrix, bg, scale_modifier=1.0, instance_capacity=None, state_out=None, cam_dev=None,
+              bg_image=None):
+    """Differentiable tile rasteriser -> (color [3,H,W], radii i32 [N], depth [1,H,W], alpha [1,H,W]).
+    With ``bg_image`` [3,H,W] the per-pixel background is composited in the blend epilogue
+    (color = color_fg + bg_image * (1 - alpha), scene.py:153-166) and a 5th output color_fg is returned."""
     cam_args = (int(image_height), int(image_width), float(tanfovx), float(tanfovy), viewmatrix, projmatrix, bg,
                 float(scale_modifier), instance_capacity, cam_dev)
-    return _Rasterize.apply(means3D, means2D, colors, opacities, scales, rotations, cam_args, state_out)
+    out = _Rasterize.apply(means3D, means2D, colors, opacities, scales, rotations, bg_image, cam_args, state_out)
+    return out if bg_image is not None else out[:4]
 
 
 # ------------------------------------------------------------------------------ tensor-core GEMM / conv

@@ -120,17 +120,21 @@ int64_t dwg_raster_img_bytes(int H, int W);                     /* final_T, n_co
  * geom/bin/img are caller workspaces of the sizes above (kept for the backward).
  * status: i32[4] device words {overflow flag, P (num_rendered), max tile load, reserved}.
  * cam_dev: NULL, or a DEVICE copy of the camera struct that overrides the matrices / tanfov / bg of
- * `cam` (same image size): lets a captured CUDA graph be replayed with a new camera. */
+ * `cam` (same image size): lets a captured CUDA graph be replayed with a new camera.
+ * bg_image: NULL, or a per-pixel background [3,H,W] composited in the blend epilogue exactly as
+ * Scene.forward does (core/system/scene.py:153-166): out_color = image_fg + bg_image * (1 - out_alpha), with
+ * image_fg = blended colour + final_T * cam.bg written to out_color_fg [3,H,W] when that is not NULL. */
 int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N,
                        const float* means3D, const float* colors_precomp, const float* opacities,
                        const float* scales, const float* rotations,
                        float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
                        void* geom, void* bin, int64_t P_cap, void* img, int32_t* status,
-                       const void* cam_dev, void* stream);
+                       const void* cam_dev, const float* bg_image, float* out_color_fg, void* stream);
 /* Backward.  dL_dcolor [3,H,W], dL_ddepth [H,W] or NULL, dL_dalpha [H,W] or NULL ->
  * g_means3D [N,3], g_means2D [N,3] (z = 0), g_colors [N,3], g_opacities [N], g_scales [N,3],
  * g_rotations [N,4].  All outputs are fully written (no pre-zeroing needed); `scratch` must
- * hold dwg_raster_bwd_scratch_bytes(N) bytes. */
+ * hold dwg_raster_bwd_scratch_bytes(N) bytes.  dL_dcolor is the gradient of out_color (the composite when bg_image was
+ * given: pass the same bg_image and the forward's out_alpha; g_bg_image [3,H,W] or NULL receives dL/d bg_image). */
 int64_t dwg_raster_bwd_scratch_bytes(int64_t N);
 int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N,
                         const float* means3D, const float* colors_precomp, const float* opacities,
@@ -138,7 +142,8 @@ int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N,
                         const void* geom, const void* bin, int64_t P_cap, const void* img,
                         const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                         float* g_means3D, float* g_means2D, float* g_colors, float* g_opacities,
-                        float* g_scales, float* g_rotations, void* scratch, const void* cam_dev, void* stream);
+                        float* g_scales, float* g_rotations, void* scratch, const void* cam_dev,
+                        const float* bg_image, const float* out_alpha, float* g_bg_image, void* stream);
 /* Debug / parity views into the workspaces (device pointers into geom / bin / img):
  * which = 0 xy f32[N,2] | 1 depth f32[N] | 2 cov3D f32[N,6] | 3 conic_opacity f32[N,4]
  *       | 4 rect i32[N,4] | 5 tiles_touched u32[N] | 6 tile ranges u32[tiles,2]
