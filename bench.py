@@ -305,6 +305,15 @@ def run_dwg(args):
         'host_ms_parts_per_step': {k: round(v / max(1, 2 * args.steps + args.warmup + min(2, args.warmup)), 3) for k, v in host_parts.items()}, 'clocks': clocks, 'roofline': roof,
         'roofline_raster': roof_r,
     }
+    if world == 1 and not args.skip_ref_gpu:
+        # the north-star target is stated against the reference's single-GPU step: time the reference-equivalent GPU arm
+        # on the same box right after the dwg arm (rank 0, N = 1 only; bounded to a few steps)
+        try:
+            out['ref_gpu'] = ref_gpu_block(args)
+            out['ref_gpu']['speedup_dwg_over_ref_gpu'] = {'device_timed': round(value / out['ref_gpu']['value'], 2),
+                                                          'e2e': round(e2e_v / out['ref_gpu']['value'], 2), 'target': 10.0}
+        except Exception as e:
+            out['ref_gpu'] = {'unavailable': f'{type(e).__name__}: {e}'}
     if not args.skip_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(sample_only=True)
     print(json.dumps(out), file=_JSON_OUT, flush=True)
@@ -452,6 +461,37 @@ def cpu_baseline(sample_only=True, tiny=False):
             'sample': f'1 full SDS step of the same workload on the CPU oracle ({dt:.1f} s; setup {t1 - t0:.0f} s not counted)'}
 
 
+def ref_gpu_block(args, steps=4, warmup=2):
+    """Reference-equivalent GPU arm (oracle/ref_gpu.py): eager fp32 torch modules on cuDNN / cuBLAS / SDPA with torch's default
+    TF32 flags + the reference's own gridencoder.cu + a plain-SIMT raster stand-in, same workload, CUDA-event timed."""
+    from oracle import ref_gpu
+    dev = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+    sc = ref_gpu.RefGpuScene(dev, tiny=args.tiny, n_unc=args.n_unconstrained, img=args.image, poses=poses())
+    ms = ref_gpu.time_steps(sc, steps, warmup)
+    del sc
+    torch.cuda.empty_cache()
+    return {'value': round(1000.0 / ms, 4), 'unit': 'steps/s', 'ms_per_step': round(ms, 2), 'steps': steps, 'warmup': warmup,
+            'dtype': 'f32 (torch defaults: TF32 cuDNN convolutions, fp32 matmuls), eager, no CUDA graphs',
+            'what': 'oracle eager torch modules on the GPU (avatar path, VAE, ControlNet, UNet: cuDNN / cuBLAS / SDPA) + the reference\'s own '
+                    'gridencoder.cu (unmodified, sm_100a) + plain-SIMT 3DGS raster stand-in (oracle/ref_gpu_raster.cu) -- BASELINE.md section 3'}
+
+
+def run_reference_gpu(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+    sampler = ClockSampler(int(os.environ.get('LOCAL_RANK', 0)))
+    sampler.start()
+    blk = ref_gpu_block(args, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)))
+    clocks = sampler.stop()
+    line = {'impl': 'reference-gpu', 'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)', 'value': blk['value'], 'unit': 'steps/s',
+            'n_gpus': 1, 'steps': blk['steps'], 'warmup': blk['warmup'], 'ms_per_step': blk['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': blk['dtype'], 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'note': blk['what']},
+            'clocks': clocks, 'e2e': {'value': blk['value'], 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 8}, 'gpu_launches': 0}
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
@@ -488,18 +528,21 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='dwg', choices=['dwg', 'reference'])
+    ap.add_argument('--impl', default='dwg', choices=['dwg', 'reference', 'reference-gpu'])
     ap.add_argument('--tiny', action='store_true', help='reduced-width smoke configuration (NOT the benchmark workload)')
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-step-graph', action='store_true', help='capture only the diffusion sub-graphs')
     ap.add_argument('--profile', action='store_true', help='print a CUPTI kernel table of 3 steps to stderr')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--skip-ref-gpu', action='store_true', help='do not time the reference-equivalent GPU arm after the dwg arm')
     ap.add_argument('--n-unconstrained', type=int, default=N_UNCONSTRAINED)
     ap.add_argument('--image', type=int, default=IMG)
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.impl == 'reference-gpu':
+        run_reference_gpu(args)
     else:
         run_dwg(args)
 

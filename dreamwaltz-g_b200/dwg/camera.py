@@ -12,43 +12,52 @@ import torch
 
 
 def _normalize(v, eps=1e-20):
-    return v / torch.sqrt(torch.clamp((v * v).sum(-1, keepdim=True), min=eps))
+    return v / np.sqrt(np.maximum((v * v).sum(-1, keepdims=True), np.float32(eps)))
 
 
 def to_extrinsic(radius, azimuth, elevation, at_vector=None):
-    """radius/azimuth/elevation [B] (degrees) -> (extrinsic w2c [B,4,4], c2w [B,4,4]).
-    Camera looks down +z; c2w columns = right, up, look-at (utils.py:101-113)."""
+    """radius/azimuth/elevation [B] (degrees) -> (extrinsic w2c [B,4,4], c2w [B,4,4]) float32 tensors.
+    Camera looks down +z; c2w columns = right, up, look-at (utils.py:101-113).  Host arithmetic in numpy float32 (a few
+    microseconds per view instead of ~25 tiny torch ops); c2w is a rigid transform, so its inverse is written in closed
+    form [R^T | -R^T t] (the reference calls torch.inverse: same matrix to fp32 rounding, tests/test_camera_golden.py)."""
+    f32 = np.float32
+    radius, azimuth, elevation = (np.asarray(torch.as_tensor(x).numpy() if torch.is_tensor(x) else x, dtype=f32).reshape(-1)
+                                  for x in (radius, azimuth, elevation))
     B = radius.shape[0]
-    az = azimuth * math.pi / 180.0
-    el = elevation * math.pi / 180.0
-    sph = torch.stack([radius * torch.sin(el) * torch.sin(az),
-                       radius * torch.cos(el),
-                       radius * torch.sin(el) * torch.cos(az)], dim=-1)
-    if at_vector is None:
-        at_vector = torch.zeros(B, 3, dtype=torch.float32)
-    up = torch.tensor([[0.0, 1.0, 0.0]]).repeat(B, 1)
-    pos = at_vector + sph
+    az = azimuth * f32(math.pi) / f32(180.0)
+    el = elevation * f32(math.pi) / f32(180.0)
+    sph = np.stack([radius * np.sin(el) * np.sin(az), radius * np.cos(el), radius * np.sin(el) * np.cos(az)], axis=-1).astype(f32)
+    at = np.zeros((B, 3), f32) if at_vector is None else np.asarray(torch.as_tensor(at_vector).numpy() if torch.is_tensor(at_vector) else at_vector, f32).reshape(B, 3)
+    up = np.tile(np.array([[0.0, 1.0, 0.0]], f32), (B, 1))
+    pos = at + sph
     look = _normalize(-sph)
-    right = _normalize(torch.cross(look, up, dim=-1))
-    up2 = _normalize(torch.cross(right, look, dim=-1))
-    c2w = torch.eye(4, dtype=torch.float32).unsqueeze(0).repeat(B, 1, 1)
-    c2w[:, :3, :3] = torch.stack((right, up2, look), dim=-1)
+    right = _normalize(np.cross(look, up))
+    up2 = _normalize(np.cross(right, look))
+    R = np.stack((right, up2, look), axis=-1).astype(f32)                      # columns
+    c2w = np.tile(np.eye(4, dtype=f32)[None], (B, 1, 1))
+    c2w[:, :3, :3] = R
     c2w[:, :3, 3] = pos
-    return torch.inverse(c2w), c2w
+    ext = np.tile(np.eye(4, dtype=f32)[None], (B, 1, 1))
+    Rt = R.transpose(0, 2, 1)
+    ext[:, :3, :3] = Rt
+    ext[:, :3, 3] = -(Rt @ pos[:, :, None])[:, :, 0]
+    return torch.from_numpy(ext), torch.from_numpy(c2w)
 
 
 def to_projection(tanfov, z_near=0.01, z_far=1000.0, tanfov_x=None):
     """utils.py:149-201: y flipped, z_sign=+1, z range (-1,1)."""
+    f32 = np.float32
+    tanfov = np.asarray(torch.as_tensor(tanfov).numpy() if torch.is_tensor(tanfov) else tanfov, f32).reshape(-1)
     B = tanfov.shape[0]
-    max_y = tanfov * z_near
-    max_x = max_y if tanfov_x is None else tanfov_x * z_near
-    K = torch.zeros(B, 4, 4, dtype=torch.float32)
-    K[:, 0, 0] = 2.0 * z_near / (2 * max_x)
-    K[:, 1, 1] = -2.0 * z_near / (2 * max_y)
-    K[:, 2, 2] = (z_far + z_near) / (z_far - z_near)
-    K[:, 2, 3] = -(2 * z_far * z_near) / (z_far - z_near)
+    max_y = tanfov * f32(z_near)
+    max_x = max_y if tanfov_x is None else np.asarray(torch.as_tensor(tanfov_x).numpy(), f32).reshape(-1) * f32(z_near)
+    K = np.zeros((B, 4, 4), f32)
+    K[:, 0, 0] = f32(2.0) * f32(z_near) / (max_x - (-max_x))
+    K[:, 1, 1] = -f32(2.0) * f32(z_near) / (max_y - (-max_y))
+    K[:, 2, 2] = f32((z_far + z_near) / (z_far - z_near))
+    K[:, 2, 3] = f32(-(2 * z_far * z_near) / (z_far - z_near))
     K[:, 3, 2] = 1.0
-    return K
+    return torch.from_numpy(K)
 
 
 def make_camera(radius, azimuth, elevation, fov, image_height, image_width, at=(0.0, 0.0, 0.0),
@@ -56,13 +65,12 @@ def make_camera(radius, azimuth, elevation, fov, image_height, image_width, at=(
     """Build the ``data`` dict for one view from scalar parameters (degrees)."""
     f32 = lambda v: torch.tensor([float(v)], dtype=torch.float32)
     radius, azimuth, elevation, fov = f32(radius), f32(azimuth), f32(elevation), f32(fov)
-    tanfov = torch.tan(fov * math.pi / 180.0 * 0.5)
-    extrinsic, c2w = to_extrinsic(radius, azimuth, elevation,
-                                  at_vector=torch.tensor([list(at)], dtype=torch.float32))
+    tanfov = torch.from_numpy(np.tan(fov.numpy() * np.float32(math.pi) / np.float32(180.0) / np.float32(2.0)).astype(np.float32))
+    extrinsic, c2w = to_extrinsic(radius, azimuth, elevation, at_vector=np.asarray([list(at)], np.float32))
     projection = to_projection(tanfov, z_near, z_far)
     return {
         'extrinsic': extrinsic, 'c2w': c2w, 'projection': projection,
-        'mvp': torch.bmm(projection, extrinsic),
+        'mvp': torch.from_numpy(projection.numpy() @ extrinsic.numpy()),
         'azimuth': azimuth, 'elevation': elevation, 'radius': radius, 'fov': fov, 'tanfov': tanfov,
         'z_far': z_far, 'z_near': z_near, 'image_height': int(image_height), 'image_width': int(image_width),
     }

@@ -7,6 +7,9 @@ repository; /root/reference is never written.
   _gridencoder_ref*.so   <- core/nerf/gridencoder/src/{gridencoder.cu,bindings.cpp}  (the reference's
                             only native code on the hot path), UNMODIFIED, built with the flags of
                             core/nerf/gridencoder/backend.py:8-12 plus -gencode sm_100a.
+  libref_raster_simt.so  <- oracle/ref_gpu_raster.cu (OUR plain-SIMT restatement of the published 3DGS
+                            rasteriser, the labelled stand-in for the un-installable third-party
+                            diff_gaussian_rasterization in the reference-equivalent GPU arm of bench.py).
 
 It needs torch headers (pybind11 module taking at::Tensor) and a GPU to RUN, so it is used only
 by `tests/golden/make_grid_golden.py` (golden vectors for R6, generated on a B200 through gpurun)
@@ -53,6 +56,22 @@ def build(force=False, verbose=False):
     return dst
 
 
+RASTER_SO = os.path.join(OUT, 'libref_raster_simt.so')
+
+
+def build_raster(force=False):
+    """nvcc oracle/ref_gpu_raster.cu -> oracle/_ref/libref_raster_simt.so (works without /root/reference)."""
+    import subprocess
+    src = os.path.join(_HERE, 'ref_gpu_raster.cu')
+    if not force and os.path.exists(RASTER_SO) and os.path.getmtime(RASTER_SO) >= os.path.getmtime(src):
+        return RASTER_SO
+    os.makedirs(OUT, exist_ok=True)
+    nvcc = '/usr/local/cuda/bin/nvcc' if os.path.exists('/usr/local/cuda/bin/nvcc') else 'nvcc'
+    subprocess.check_call([nvcc, '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-Xcompiler', '-fPIC',
+                           '-o', RASTER_SO, src, '-lcudart'])
+    return RASTER_SO
+
+
 def load_module():
     """Import the prebuilt reference extension (needs torch; raises if it was never built)."""
     so = built_so()
@@ -68,3 +87,4 @@ def load_module():
 
 if __name__ == '__main__':
     print(build(force='-f' in sys.argv, verbose='-v' in sys.argv))
+    print(build_raster(force='-f' in sys.argv))

@@ -103,7 +103,7 @@ def test_sds_step_matches_oracle_and_specify_gradient():
     from oracle import diffusion as od
     cfg, u_sd, c_sd, v_sd = _tiny()
     torch.manual_seed(3)
-    g = G.ControlNetScoreDistillation(u_sd, c_sd, v_sd, cfg, W.TINY_VAE, DEV, guidance_scale=7.5)
+    g = G.ControlNetScoreDistillation(u_sd, c_sd, v_sd, cfg, W.TINY_VAE, DEV, guidance_scale=7.5, default_image_size=128)
     img = torch.rand(1, 3, 128, 128)
     cond = torch.rand(1, 3, 128, 128)
     emb = {'neg': torch.randn(1, 77, cfg['ctx_dim']), 'text': torch.randn(1, 77, cfg['ctx_dim'])}
@@ -145,7 +145,7 @@ def test_prepare_head_start_and_two_streams_change_nothing():
     noise, veps = torch.randn(1, 4, 16, 16, device=DEV), torch.randn(1, 4, 16, 16, device=DEV)
     outs = []
     for mode in ('single', 'two_streams', 'prepared'):
-        g = G.ControlNetScoreDistillation(u_sd, c_sd, v_sd, cfg, W.TINY_VAE, DEV, guidance_scale=7.5)
+        g = G.ControlNetScoreDistillation(u_sd, c_sd, v_sd, cfg, W.TINY_VAE, DEV, guidance_scale=7.5, default_image_size=128)
         g.two_streams = mode != 'single'
         x = img.clone().requires_grad_(True)
         if mode == 'prepared':

@@ -71,7 +71,7 @@ def main():
     res['norms'] = {'eps': float(ref['eps'].norm()), 'e_c-e_u': float(ref['diff'].norm()), 'grad': float(ref['grad'].norm()),
                     'noise': float(noise.norm()), 'lat': float(ref['lat'].norm())}
 
-    gd = G.ControlNetScoreDistillation(u_sd, c_sd, v_sd, cfg, vcfg, dev, guidance_scale=args.scale)
+    gd = G.ControlNetScoreDistillation(u_sd, c_sd, v_sd, cfg, vcfg, dev, guidance_scale=args.scale, default_image_size=img_hw)
 
     def dwg_run(feed_ref_latents=False):
         im = img.clone().requires_grad_(True)
