@@ -78,11 +78,11 @@ __global__ void __launch_bounds__(kThreads)
 grid_fwd_kernel(const float* __restrict__ x, float bound, const float2* __restrict__ table,
                 const int32_t* __restrict__ offsets, const float* __restrict__ level_scale,
                 const uint32_t* __restrict__ level_res, float* __restrict__ out, int64_t osb, int64_t osl,
-                float* __restrict__ dy_dx, int64_t B, int L, int gridtype, bool align_corners, int interp) {
+                float* __restrict__ dy_dx, int64_t B, int L, int LP, int gridtype, bool align_corners, int interp) {
     const int64_t gid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int64_t b = gid / L;
-    const int l = (int)(gid - b * L);
-    if (b >= B) return;
+    const int64_t b = gid / LP;                 // LP = lanes per point = L rounded up to a power of two (<= 32)
+    const int l = (int)(gid - b * LP);
+    if (b >= B || l >= L) return;
     LevelCtx c;
     level_setup(c, x, b, bound, offsets, level_scale, level_res, l, align_corners, interp);
     float2* o = reinterpret_cast<float2*>(out + b * osb + (int64_t)l * osl);
@@ -142,13 +142,14 @@ __global__ void __launch_bounds__(kThreads)
 grid_bwd_kernel(const float* __restrict__ grad, int64_t gsb, int64_t gsl, const float* __restrict__ x, float bound,
                 const float2* __restrict__ table, const int32_t* __restrict__ offsets,
                 const float* __restrict__ level_scale, const uint32_t* __restrict__ level_res,
-                float2* __restrict__ g_table, float* __restrict__ g_x, int64_t B, int L, int gridtype,
+                float2* __restrict__ g_table, float* __restrict__ g_x, int64_t B, int L, int LP, int gridtype,
                 bool align_corners, int interp) {
     const int64_t gid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    int64_t b = gid / L;
-    const int l = (int)(gid - b * L);
-    const bool active = b < B;
-    if (!active) b = B - 1;          // keep the lane for the shuffles below
+    int64_t b = gid / LP;
+    int l = (int)(gid - b * LP);
+    const bool active = b < B && l < L;
+    if (b >= B) b = B - 1;           // keep the lane for the shuffles below
+    if (l >= L) l = L - 1;
     LevelCtx c;
     level_setup(c, x, b, bound, offsets, level_scale, level_res, l, align_corners, interp);
     float gxv[3] = {0.f, 0.f, 0.f};
@@ -190,11 +191,11 @@ grid_bwd_kernel(const float* __restrict__ grad, int64_t gsb, int64_t gsl, const 
         }
     }
     if (WANT_GX) {
-        // sum over the L lanes of this point (L divides 32: 1,2,4,8,16,32)
+        // sum over the LP lanes of this point (LP is a power of two <= 32; lanes >= L hold zeros)
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             float vsum = gxv[d];
-            for (int off = L >> 1; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
+            for (int off = LP >> 1; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
             gxv[d] = vsum;
         }
         if (active && l == 0) {
@@ -232,16 +233,18 @@ extern "C" int dwg_grid_encode_fwd(const float* x, float bound, const float* tab
                                    int64_t out_stride_b, int64_t out_stride_l, float* dy_dx, int64_t B, int L,
                                    int gridtype, int align_corners, int interp, void* stream) {
     DWG_REQUIRE(x && table && offsets && level_scale && level_res && out, "null pointer");
-    DWG_REQUIRE(L >= 1 && L <= 32 && (32 % L) == 0, "L must divide 32");
+    DWG_REQUIRE(L >= 1 && L <= 32, "1 <= L <= 32");
     DWG_REQUIRE((out_stride_b % 2) == 0 && (out_stride_l % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
                 "out must be 8-byte aligned with even strides");
     DWG_REQUIRE(gridtype == 0 || gridtype == 1, "gridtype must be 0 (hash) or 1 (tiled)");
     DWG_REQUIRE(interp == 0 || interp == 1, "interp must be 0 (linear) or 1 (smoothstep)");
     if (B == 0) return DWG_OK;
-    const int64_t threads = B * L;
+    int LP = 1;
+    while (LP < L) LP <<= 1;
+    const int64_t threads = B * LP;
     grid_fwd_kernel<<<(unsigned)ceil_div(threads, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         x, bound, reinterpret_cast<const float2*>(table), offsets, level_scale, level_res, out, out_stride_b,
-        out_stride_l, dy_dx, B, L, gridtype, align_corners != 0, interp);
+        out_stride_l, dy_dx, B, L, LP, gridtype, align_corners != 0, interp);
     return check_launch("dwg_grid_encode_fwd");
 }
 
@@ -250,21 +253,23 @@ extern "C" int dwg_grid_encode_bwd(const float* grad, int64_t g_stride_b, int64_
                                    const float* level_scale, const uint32_t* level_res, float* g_table, float* g_x,
                                    int64_t B, int L, int gridtype, int align_corners, int interp, void* stream) {
     DWG_REQUIRE(grad && x && table && offsets && level_scale && level_res && g_table, "null pointer");
-    DWG_REQUIRE(L >= 1 && L <= 32 && (32 % L) == 0, "L must divide 32");
+    DWG_REQUIRE(L >= 1 && L <= 32, "1 <= L <= 32");
     DWG_REQUIRE((g_stride_b % 2) == 0 && (g_stride_l % 2) == 0 && (reinterpret_cast<uintptr_t>(grad) & 7) == 0,
                 "grad must be 8-byte aligned with even strides");
     DWG_REQUIRE(gridtype == 0 || gridtype == 1, "gridtype must be 0 (hash) or 1 (tiled)");
     if (B == 0) return DWG_OK;
-    const int64_t threads = B * L;
+    int LP = 1;
+    while (LP < L) LP <<= 1;
+    const int64_t threads = B * LP;
     const unsigned grid = (unsigned)ceil_div(threads, kThreads);
     cudaStream_t st = (cudaStream_t)stream;
     if (g_x)
         grid_bwd_kernel<true><<<grid, kThreads, 0, st>>>(grad, g_stride_b, g_stride_l, x, bound,
             reinterpret_cast<const float2*>(table), offsets, level_scale, level_res,
-            reinterpret_cast<float2*>(g_table), g_x, B, L, gridtype, align_corners != 0, interp);
+            reinterpret_cast<float2*>(g_table), g_x, B, L, LP, gridtype, align_corners != 0, interp);
     else
         grid_bwd_kernel<false><<<grid, kThreads, 0, st>>>(grad, g_stride_b, g_stride_l, x, bound,
             reinterpret_cast<const float2*>(table), offsets, level_scale, level_res,
-            reinterpret_cast<float2*>(g_table), g_x, B, L, gridtype, align_corners != 0, interp);
+            reinterpret_cast<float2*>(g_table), g_x, B, L, LP, gridtype, align_corners != 0, interp);
     return check_launch("dwg_grid_encode_bwd");
 }

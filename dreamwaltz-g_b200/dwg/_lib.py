@@ -77,6 +77,8 @@ SIGNATURES = {
     'dwg_sds_grad': (c_int, [c_void_p] * 5 + [c_float, c_float, c_int64, c_void_p]),
     'dwg_attention_fwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_void_p]),
+    'dwg_adam_step': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'dwg_frame_pack': (c_int, [c_void_p] * 8 + [c_int, c_int, c_float, c_void_p]),
     'dwg_raster_view': (c_void_p, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int]),
 }
 
@@ -102,7 +104,7 @@ KERNELS_PER_CALL = {
     'dwg_grid_encode_fwd': 1, 'dwg_grid_encode_bwd': 1, 'dwg_avatar_mlp_fwd': 1, 'dwg_avatar_mlp_bwd': 2, 'dwg_raster_forward': 12, 'dwg_raster_backward': 2,
     'dwg_gemm_f16': 1, 'dwg_conv2d_nhwc_f16': 1, 'dwg_groupnorm_fwd': 2, 'dwg_groupnorm_bwd': 2,
     'dwg_layernorm_fwd': 1, 'dwg_softmax_rows': 1, 'dwg_softmax_rows_bwd': 1, 'dwg_geglu': 1,
-    'dwg_eltwise_f16': 1, 'dwg_sds_grad': 1, 'dwg_attention_fwd': 1,
+    'dwg_eltwise_f16': 1, 'dwg_sds_grad': 1, 'dwg_attention_fwd': 1, 'dwg_adam_step': 2, 'dwg_grid_level_table': 1, 'dwg_frame_pack': 1,
 }
 
 

@@ -328,6 +328,12 @@ class _StatusMonitor:
                                    f'{_CAP_FLOOR[device.index]}).')
             raise RuntimeError(f'dwg rasteriser: a tile held {load} instances in the previous call; at most {MAX_TILE_LOAD} can be depth-sorted')
 
+    def reset(self):
+        """Forget pending reports and learnt capacities (tests)."""
+        for h in self.host.values():
+            h.zero_()
+        _CAP_FLOOR.clear()
+
     def post(self, status):
         dev = status.device
         h = self.host.get(dev.index)

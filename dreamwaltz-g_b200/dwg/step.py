@@ -107,6 +107,9 @@ class SDSTrainStep:
         self.params = [p for p in scene.parameters() if p.requires_grad]
         self.bucket = GradBucket(self.params)
         self.dev = self.params[0].device
+        # Eager steps and the graph capture run on ONE private stream: autograd binds each parameter's AccumulateGrad node to the
+        # stream it was created on, and a node bound to the legacy default stream would break a later capture on another stream.
+        self._stream = torch.cuda.Stream(device=self.dev)
         self._graph = None
         self.graph_launches = 0
         self.host_ms = {}
@@ -145,12 +148,17 @@ class SDSTrainStep:
         self.train_step += 1
         if self._graph is not None:
             return self._replay(data)
-        out = self._body(data)
+        cur = torch.cuda.current_stream()
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):
+            out = self._body(data)
+        cur.wait_stream(self._stream)
         self._post()
         return out
 
     # ---- whole-step CUDA graph
     def capture(self, data, warmup=3):
+        """Capture the whole step (on the private stream the eager steps use as well)."""
         g = self.guidance
         g._g = None
         g.use_default_generator = True                          # graph-safe philox state
@@ -176,7 +184,7 @@ class SDSTrainStep:
         def body():
             loss, ro, so, _ = self._body(sdata, cam_dev=st['cam'])
             return loss, ro, so
-        side = torch.cuda.Stream()
+        side = self._stream
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -186,7 +194,7 @@ class SDSTrainStep:
         from ._lib import lib
         graph = torch.cuda.CUDAGraph()
         n0 = lib().launches
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):
             self._out = body()
         self.graph_launches = lib().launches - n0
         torch.cuda.synchronize()

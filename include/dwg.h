@@ -270,6 +270,29 @@ int dwg_sds_grad(const float* eps_uncond, const float* eps_cond, const float* no
 int dwg_attention_fwd(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* vt, int64_t Tkp,
                       int64_t vt_batch_stride, void* out, int B, int heads, int T, int Tk, int hd, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (f2) Fused multi-tensor Adam.  Replaces the torch.optim.Adam instances the reference steps every iteration
+ * (core/trainer.py:880-882; groups of core/gaussian/gaussian_optimizer.py:49-141, core/system/avatar.py:1590-1635,
+ * :1081-1094): ONE launch updates every parameter of the flat buffers (fp32, 16-byte aligned segments).
+ *   params / grads / exp_avg / exp_avg_sq [n]; segment i covers elements [seg_end[i-1], seg_end[i]) and belongs to
+ *   hyper-parameter group seg_group[i]; beta1 / beta2 / eps [n_group] (host arrays); lr_dev [n_group] DEVICE array
+ *   (refreshed by the caller when a schedule changes it); step_dev DEVICE int64 step counter (incremented here).
+ * Update rule = torch.optim.Adam(amsgrad=False, weight_decay=0): bias-corrected, eps added outside the square root. */
+int dwg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  int n_seg, const int64_t* seg_end, const int32_t* seg_group,
+                  int n_group, const float* beta1, const float* beta2, const float* eps,
+                  const float* lr_dev, int64_t* step_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (f4) Inference output stage.  Replaces the per-frame post-processing of Trainer.evaluate (core/trainer.py:1068-1084:
+ * depth / 3, concat_alpha) + tensor2image (utils/image.py:52-61: (x * 255).clip(0, 255).astype(uint8), channel-last)
+ * with ONE kernel from the rasteriser's planar fp32 outputs to interleaved uint8 frames ready for the encoder:
+ *   image [3,H,W] -> rgb u8 [H,W,3];  image_fg [3,H,W] + alpha [H,W] -> rgba_fg u8 [H,W,4];
+ *   depth [H,W] / depth_div -> depth_u8 [H,W];  alpha -> alpha_u8 [H,W].   NULL outputs are skipped. */
+int dwg_frame_pack(const float* image, const float* image_fg, const float* depth, const float* alpha,
+                   uint8_t* rgb, uint8_t* rgba_fg, uint8_t* depth_u8, uint8_t* alpha_u8,
+                   int H, int W, float depth_div, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

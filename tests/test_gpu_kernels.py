@@ -242,6 +242,11 @@ def test_raster_large_tile_merge_path_and_capacity_overflow():
     s2 = st2.status.cpu().numpy()
     assert s2[0] == 1 and s2[1] == P
     assert torch.isfinite(color2.detach()).all()
+    # ... and the host wrapper reports it at the NEXT call (deferred, no sync inside the step); see tests/test_gpu_step.py
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match='instance capacity exceeded'):
+        _run_gpu(g, kw)
+    ops.STATUS_MONITOR.reset()
 
 
 def test_raster_empty_and_all_culled():

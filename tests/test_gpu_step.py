@@ -83,7 +83,7 @@ def test_train_step_graph_replay_equals_eager_step():
     d0['cond_images'], d1['cond_images'] = cond, cond
     loss, ro, so, text = tr.step(d1)                                            # eager
     assert float(loss) == 1.0 and text is None and ro['regularizations'] == {}
-    eager_sds, eager_flat, eager_img = so['gradients'].clone(), tr.bucket.flat.clone(), ro['image'].clone()
+    eager_sds, eager_flat, eager_img = so['gradients'].clone(), tr.bucket.flat.clone(), ro['image'].detach().clone()
     assert all(p.grad.data_ptr() == tr.bucket.flat.data_ptr() + o * 4 for p, o in zip(tr.params, tr.bucket.offsets))
     assert float(eager_flat.abs().sum()) > 0
     tr.capture(d0)                                                              # captured on ANOTHER view / pose
@@ -113,7 +113,7 @@ def test_rasteriser_overflow_is_reported_by_the_next_call():
     with pytest.raises(RuntimeError, match='instance capacity exceeded'):
         ops.rasterize(t['positions'], m2, t['colors'], t['opacities'], t['scales'], t['quaternions'], **kw)
     assert ops.default_instance_capacity(10, DEV) >= int(status[1])             # the next default allocation is large enough
-    ops._CAP_FLOOR.clear()
+    ops.STATUS_MONITOR.reset()
     color, *_ = ops.rasterize(t['positions'], m2, t['colors'], t['opacities'], t['scales'], t['quaternions'], **kw)      # clean again
     torch.cuda.synchronize()
     assert torch.isfinite(color).all()
