@@ -58,6 +58,6 @@ def test_bad_arguments_return_error_codes_without_a_gpu():
     assert rc == -1 and b'null' in L.dwg_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, 'dwg_lbs_skin_fwd')
-    rc = L.dwg_grid_encode_fwd(1, 2.0, 1, 1, 1, 1, 8, 32, 2, None, 4, 5, 1, 0, 1, None)
-    assert rc == -1 and b'L must divide 32' in L.dwg_last_error()
+    rc = L.dwg_grid_encode_fwd(1, 2.0, 1, 1, 1, 1, 8, 32, 2, None, 4, 33, 1, 0, 1, None)
+    assert rc == -1 and b'1 <= L <= 32' in L.dwg_last_error()
     assert L.dwg_raster_geom_bytes(1000) > 1000 * 56
