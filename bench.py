@@ -46,6 +46,16 @@ import torch  # noqa: E402
 
 N_UNCONSTRAINED, N_MESH_TRI, IMG = 135000, 2500, 512
 WORKLOAD = 'cfg2: 150k-Gaussian SMPL-X avatar SDS step @512^2, SD1.5 + ControlNet-openpose shapes (synthetic weights/data)'
+# BASELINE.json configs[1] (cfg2, the benchmark), configs[3] (cfg4) and configs[4] (cfg5); cfg3 = cfg2 under torchrun
+CONFIGS = {
+    'cfg2': dict(n_unc=135000, n_tri=2500, n_face=0, img=512, sd='SD15', sd_size=512, workload=WORKLOAD),
+    'cfg4': dict(n_unc=270000, n_tri=2500, n_face=2500, img=1024, sd='SD21', sd_size=768,
+                 workload='cfg4: 300k-Gaussian avatar with mesh-bound hands + face and expression, rendered @1024^2, resized to 768^2 '
+                          '(basic.py:360-366), SD2.1 + ControlNet shapes (synthetic weights/data)'),
+    'cfg5': dict(n_unc=135000, n_tri=2500, n_face=0, img=1024, sd=None, sd_size=0,
+                 workload='cfg5: inference_reenact -- 500-frame motion sequence, 150k Gaussians @1024^2, animate + rasterise + uint8 frames '
+                          '(image, image_fg+alpha, depth, alpha) delivered to host memory'),
+}
 
 
 def peaks():
@@ -106,34 +116,39 @@ class Workload:
     """Everything one rank needs, built from the PACKAGE's public objects (dwg.step.Scene / SDSTrainStep are the R17 API;
     nothing of the step lives in this file any more): avatar, renderer, guidance, per-step inputs."""
 
-    def __init__(self, device, rank, n_unc=N_UNCONSTRAINED, n_tri=N_MESH_TRI, img=IMG, tiny=False, allreduce=False):
+    def __init__(self, device, rank, n_unc=N_UNCONSTRAINED, n_tri=N_MESH_TRI, img=IMG, tiny=False, allreduce=False, n_face=0, sd='SD15',
+                 sd_size=None):
         from dwg import avatar as dav, step as dstep, synth
         from dwg.diffusion import guidance as G, weights as W
         self.dev, self.rank, self.img = device, rank, img
+        sd_size = sd_size or img
         model = synth.make_body_model(0)
-        av = synth.make_avatar(model, n_unc, n_tri, seed=0)
+        av = synth.make_avatar(model, n_unc, n_tri, seed=0, n_face_triangles=n_face)
         self.avatar = dav.DreamWaltzGAvatar(model, av, device=device)
+        self.expr_rng = np.random.default_rng(77 + rank) if n_face else None
         with torch.no_grad():
             g = torch.Generator(device='cpu').manual_seed(1)
             self.avatar.nerf_encoder.embeddings.copy_((torch.rand(self.avatar.nerf_encoder.embeddings.shape, generator=g) - 0.5).to(device))
         self.renderer = dav.GaussianRenderer()
-        cfg, vcfg = (W.TINY, W.TINY_VAE) if tiny else (W.SD15, W.VAE15)
-        self.guidance = G.ControlNetScoreDistillation(W.make_unet(cfg), W.make_controlnet(cfg), W.make_vae_encoder(vcfg), cfg, vcfg, device,
-                                                      seed=1000 + rank, default_image_size=img)
-        self.ctx_dim = cfg['ctx_dim']
+        self.scene = dstep.Scene(self.avatar, self.renderer)
+        self.step_i = 0
         self.rng = np.random.default_rng(1000 + rank)          # dwg.parallel.rank_seed(1000, rank)
         self.pose_rows = poses()
+        if sd is None:                                          # render-only workload (cfg5)
+            return
+        cfg, vcfg = (W.TINY, W.TINY_VAE) if tiny else (getattr(W, sd), W.VAE15)
+        self.guidance = G.ControlNetScoreDistillation(W.make_unet(cfg), W.make_controlnet(cfg), W.make_vae_encoder(vcfg), cfg, vcfg, device,
+                                                      seed=1000 + rank, default_image_size=sd_size)
+        self.ctx_dim = cfg['ctx_dim']
         g = torch.Generator().manual_seed(7)
         # host-side (pinned) per-step inputs of the e2e arm
         self.h_embeds = {'neg': torch.randn(1, 77, self.ctx_dim, generator=g).pin_memory(), 'text': torch.randn(1, 77, self.ctx_dim, generator=g).pin_memory()}
-        cond = (torch.rand(1, 3, img, img, generator=g) > 0.97).float()          # sparse skeleton-like image
+        cond = (torch.rand(1, 3, sd_size, sd_size, generator=g) > 0.97).float()  # sparse skeleton-like image (8 x the latent size)
         self.h_cond = cond.pin_memory()
         self.d_embeds = {k: v.to(device) for k, v in self.h_embeds.items()}
         self.d_cond = self.h_cond.to(device)
-        self.scene = dstep.Scene(self.avatar, self.renderer)
         self.trainer = dstep.SDSTrainStep(self.scene, self.guidance, self.d_embeds, allreduce=allreduce)
         self.params = self.trainer.params
-        self.step_i = 0
 
     def next_view(self, device_inputs=True):
         """The reference's per-step ``data`` dict (camera fields of data/camera/utils.py:301-357 + smpl_inputs + cond_images)."""
@@ -142,8 +157,86 @@ class Workload:
         self.step_i += 1
         data = camera.random_camera(self.rng, self.img, self.img)
         data['smpl_inputs'] = synth.pose_from_row(row)                               # host tensors; staged through pinned memory
-        data['cond_images'] = self.d_cond if device_inputs else self.h_cond
+        if self.expr_rng is not None:                                                # random_pose_sampler=...,expr (train_w_expr.sh:10)
+            data['smpl_inputs']['expression'] = torch.from_numpy(self.expr_rng.normal(0, 0.5, size=(1, 100)).astype(np.float32))
+        if hasattr(self, 'd_cond'):
+            data['cond_images'] = self.d_cond if device_inputs else self.h_cond
         return data
+
+
+def run_reenact(args, dev, rank, world, C):
+    """cfg5: frames/s of the re-enactment inference loop (Trainer.evaluate for scripts/inference_reenact.sh) on one GPU."""
+    from dwg import _lib, inference
+    if rank != 0:
+        return
+    img = args.image or C['img']
+    sc = Workload(dev, rank, n_unc=args.n_unconstrained or C['n_unc'], img=img, sd=None)
+    re = inference.Reenactor(sc.scene, bg_mode='white')
+    frames = [sc.next_view() for _ in range(args.frames)]
+    cam0 = frames[0]
+    for f in frames:                                            # a re-enactment sequence keeps ONE camera; only the pose changes
+        for k in ('extrinsic', 'c2w', 'projection', 'mvp', 'tanfov', 'fov', 'azimuth', 'elevation', 'radius'):
+            f[k] = cam0[k]
+    re.capture(frames[0])
+    L = _lib.lib()
+    sampler = ClockSampler(int(os.environ.get('LOCAL_RANK', 0)))
+    got = [0]
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    re.run(frames[:min(20, len(frames))])                        # warm-up
+    sampler.start()
+    n0 = L.launches
+
+    def device_only():
+        for f in frames:
+            re._send(f)
+            re._graph.replay()
+    ms_dev = timed(device_only)
+    t0 = time.perf_counter()
+    ms_e2e = timed(lambda: re.run(frames, on_frame=lambda i, fr: got.__setitem__(0, got[0] + int(fr['image'][0, 0, 0] >= 0))))
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    per_frame_bytes = sum(v.numel() for v in re._out.values())
+    out = {'metric': 'inference_reenact frames/sec (150k Gaussians @1024^2, 500-frame sequence)', 'value': round(len(frames) * 1000.0 / ms_dev, 2),
+           'unit': 'frames/s', 'n_gpus': 1, 'steps': len(frames), 'warmup': min(20, len(frames)), 'ms_per_step': round(ms_dev / len(frames), 4),
+           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': C['workload'], 'name': 'cfg5', 'gaussians': int(sc.avatar._positions.shape[0] + sum(m._scales.shape[0] for m in sc.avatar.mesh_binding_gaussians.values())),
+                      'image': img, 'cuda_graphs': 'whole frame', 'cache': 'L2 flushed by the workload itself: every frame streams the 48 MB grid table, '
+                      '106 MB of skinning weights and 9.4 MB of output frames'},
+           'e2e': {'value': round(len(frames) * 1000.0 / ms_e2e, 2), 'unit': 'frames/s', 'ms_per_step': round(ms_e2e / len(frames), 4),
+                   'h2d_bytes_per_step': int(re._packed.numel() * 4), 'd2h_bytes_per_step': int(per_frame_bytes), 'frames_delivered': got[0],
+                   'wall_s': round(wall, 3)},
+           'gpu_launches': int(re.graph_launches), 'clocks': clocks}
+    if not args.skip_ref_gpu:
+        try:
+            out['ref_gpu'] = ref_gpu_reenact(args, dev, img, min(len(frames), 60))
+            out['ref_gpu']['speedup_dwg_over_ref_gpu'] = {'e2e': round(out['e2e']['value'] / out['ref_gpu']['value'], 2)}
+        except Exception as e:
+            out['ref_gpu'] = {'unavailable': f'{type(e).__name__}: {e}'}
+    print(json.dumps(out), file=_JSON_OUT, flush=True)
+
+
+def ref_gpu_reenact(args, dev, img, n_frames):
+    """The reference's own inference loop on the GPU: eager animate + SIMT raster stand-in + the torch / numpy post-processing of
+    Trainer.evaluate (trainer.py:1068-1084, utils/image.py:52-61: .cpu().numpy() per output, synchronous)."""
+    from oracle import ref_gpu
+    sc = ref_gpu.RefGpuScene(dev, n_unc=args.n_unconstrained or CONFIGS['cfg5']['n_unc'], img=img, poses=poses(), diffusion=False)
+    for _ in range(3):
+        sc.render_frame()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_frames):
+        sc.render_frame()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {'value': round(n_frames / dt, 2), 'unit': 'frames/s', 'ms_per_step': round(1000.0 * dt / n_frames, 3), 'steps': n_frames,
+            'what': 'oracle eager torch avatar path on the GPU + reference gridencoder.cu + plain-SIMT raster stand-in + per-output '
+                    '(x * 255).clip().astype(uint8) on the host after .cpu() -- as Trainer.evaluate runs'}
 
 
 def run_dwg(args):
@@ -157,7 +250,12 @@ def run_dwg(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(dev))
     pk, pk_src = peaks()
-    sc = Workload(dev, rank, tiny=args.tiny, n_unc=args.n_unconstrained, img=args.image, allreduce=world > 1)
+    C = CONFIGS[args.config]
+    if args.config == 'cfg5':
+        return run_reenact(args, dev, rank, world, C)
+    sc = Workload(dev, rank, tiny=args.tiny, n_unc=args.n_unconstrained or C['n_unc'], img=args.image or C['img'], allreduce=world > 1,
+                  n_face=C['n_face'], sd=C['sd'], sd_size=(args.image or C['sd_size']) if args.config == 'cfg2' else C['sd_size'])
+    args.image = args.image or C['img']
     tr = sc.trainer
     graphed = False
     if not args.no_graphs and not args.no_step_graph:
@@ -170,7 +268,7 @@ def run_dwg(args):
             torch.cuda.synchronize()
     if not graphed and not args.no_graphs:
         sc.guidance.use_default_generator = False
-        sc.guidance.enable_graphs((args.image, args.image))
+        sc.guidance.enable_graphs((sc.guidance.default_image_size,) * 2)
     L = _lib.lib()
     host_parts = {}
 
@@ -247,7 +345,7 @@ def run_dwg(args):
         g._prepared = None
         ops.PROFILE = []
         ops.PROFILE_BYTES = 0.0
-        img = torch.rand(1, 3, args.image, args.image, device=dev, requires_grad=True)
+        img = torch.rand(1, 3, sc.guidance.default_image_size, sc.guidance.default_image_size, device=dev, requires_grad=True)
         for _ in range(5):
             torch.cuda._sleep(int(4e8))          # ~1 s head start: the CPU enqueues the whole un-graphed pass while the GPU is parked
         res = g(img, sc.d_embeds, cond_inputs=sc.d_cond)
@@ -295,7 +393,7 @@ def run_dwg(args):
         'optimizer_steps_per_s': round(1000.0 / ms_step, 3),
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_step, 3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f16 tensor-core GEMMs (fp32 accumulate in TMEM), fp16 activations; fp32 geometry/raster', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD if not args.tiny else 'TINY smoke configuration (not the benchmark workload)',
+        'config': {'workload': C['workload'] if not args.tiny else 'TINY smoke configuration (not the benchmark workload)', 'name': args.config,
                    'gaussians': int(sc.avatar._positions.shape[0] + sum(m._scales.shape[0] for m in sc.avatar.mesh_binding_gaussians.values())),
                    'image': args.image, 'views_per_step': world, 'parallelism': f'view-dp{world} + 1 NCCL all-reduce' if world > 1 else 'single GPU',
                    'cache': 'inputs larger than L2 (2.6 GB of fp16 weights streamed every step; 126 MB L2)',
@@ -305,7 +403,7 @@ def run_dwg(args):
         'host_ms_parts_per_step': {k: round(v / max(1, 2 * args.steps + args.warmup + min(2, args.warmup)), 3) for k, v in host_parts.items()}, 'clocks': clocks, 'roofline': roof,
         'roofline_raster': roof_r,
     }
-    if world == 1 and not args.skip_ref_gpu:
+    if world == 1 and not args.skip_ref_gpu and args.config == 'cfg2':
         # the north-star target is stated against the reference's single-GPU step: time the reference-equivalent GPU arm
         # on the same box right after the dwg arm (rank 0, N = 1 only; bounded to a few steps)
         try:
@@ -535,8 +633,10 @@ def main():
     ap.add_argument('--profile', action='store_true', help='print a CUPTI kernel table of 3 steps to stderr')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-ref-gpu', action='store_true', help='do not time the reference-equivalent GPU arm after the dwg arm')
-    ap.add_argument('--n-unconstrained', type=int, default=N_UNCONSTRAINED)
-    ap.add_argument('--image', type=int, default=IMG)
+    ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS), help='BASELINE.json configuration (cfg2 = the benchmark)')
+    ap.add_argument('--n-unconstrained', type=int, default=0, help='override the number of unconstrained Gaussians')
+    ap.add_argument('--image', type=int, default=0, help='override the render size')
+    ap.add_argument('--frames', type=int, default=500, help='cfg5: frames of the motion sequence')
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == 'reference':

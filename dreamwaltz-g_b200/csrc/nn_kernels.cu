@@ -711,6 +711,25 @@ extern "C" int dwg_groupnorm_set_fused(int on) { g_gn_fused = on ? 1 : 0; return
 /* kernels the last dwg_groupnorm_fwd call launched: 1 (one-launch cluster kernel) or 2 (stats + apply) */
 extern "C" int dwg_groupnorm_last_launches(void) { return g_gn_last_launches; }
 
+/* Shared-memory carve-out preference of the streaming kernels (percent of the L1/shared array, -1 = driver default).
+ * The tcgen05 GEMM / attention kernels need the maximum carve-out; when the small kernels between them ask for the
+ * default one, every GEMM <-> norm alternation re-partitions the SM's L1/shared memory (tools/carveout_probe.py). */
+extern "C" int dwg_nn_set_carveout(int percent) {
+    const int v = percent < 0 ? (int)cudaSharedmemCarveoutDefault : (percent > 100 ? 100 : percent);
+    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(layernorm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(softmax_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(softmax_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(softmax_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(geglu_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(eltwise_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(sds_grad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    return check_launch("dwg_nn_set_carveout");
+}
+
 extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, void* stats_,
                                  int N, int HW, int C, int G, float eps, int do_silu, void* stream) {
     fix_t* stats = reinterpret_cast<fix_t*>(stats_);
@@ -736,13 +755,13 @@ extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float*
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-            cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const h16*)x, gamma, beta, (h16*)y, stats, HW, C, G, eps, do_silu, rows_c);
+            cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const h16*)x, gamma, beta, (h16*)y, stats, HW, C, G, eps, do_silu & 1, rows_c);
             g_gn_last_launches = 1;
             return check_launch("dwg_groupnorm_fwd (fused)");
         }
     }
     g_gn_last_launches = 2;
-    cudaMemsetAsync(stats, 0, sizeof(fix_t) * 2 * N * G, st);
+    if (!(do_silu & 2)) cudaMemsetAsync(stats, 0, sizeof(fix_t) * 2 * N * G, st);      // bit 1: the caller pre-zeroed the statistics
     const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;        // row lanes per CTA
     int rows_per_cta = (int)(((int64_t)N * HW + 4 * kNumSMs - 1) / (4 * kNumSMs));      // ~4 CTAs per SM
     if (rows_per_cta < 4 * rp_) rows_per_cta = 4 * rp_;
@@ -751,7 +770,7 @@ extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float*
     launch_pdl(gn_stats_kernel, grid, dim3(256), sizeof(fix_t) * 2 * G, st, (const h16*)x, stats, HW, C, G, rows_per_cta);
     int rows_apply = rows_per_cta;
     dim3 grid2((HW + rows_apply - 1) / rows_apply, N);
-    launch_pdl(gn_apply_kernel, grid2, dim3(256), 0, st, (const h16*)x, (const fix_t*)stats, gamma, beta, (h16*)y, HW, C, G, eps, do_silu, rows_apply);
+    launch_pdl(gn_apply_kernel, grid2, dim3(256), 0, st, (const h16*)x, (const fix_t*)stats, gamma, beta, (h16*)y, HW, C, G, eps, do_silu & 1, rows_apply);
     return check_launch("dwg_groupnorm_fwd");
 }
 
@@ -763,16 +782,16 @@ extern "C" int dwg_groupnorm_bwd(const void* x, const void* dy, const void* stat
     DWG_REQUIRE(x && dy && stats && gamma && beta && dx && bstats, "null pointer");
     DWG_REQUIRE(C % 8 == 0 && C % G == 0, "C must be a multiple of 8 and of G");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(bstats, 0, sizeof(fix_t) * 2 * N * G, st);
+    if (!(do_silu & 2)) cudaMemsetAsync(bstats, 0, sizeof(fix_t) * 2 * N * G, st);
     const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;        // row lanes per CTA
     int rows_per_cta = (int)(((int64_t)N * HW + 6 * kNumSMs - 1) / (6 * kNumSMs));      // ~6 CTAs per SM
     if (rows_per_cta < 4 * rp_) rows_per_cta = 4 * rp_;
     if (rows_per_cta > 64 * rp_) rows_per_cta = 64 * rp_;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
     launch_pdl(gn_bwd_stats_kernel, grid, dim3(256), sizeof(fix_t) * 2 * G, st, (const h16*)x, (const h16*)dy, stats, gamma, beta, bstats,
-               HW, C, G, eps, do_silu, rows_per_cta);
+               HW, C, G, eps, do_silu & 1, rows_per_cta);
     launch_pdl(gn_bwd_apply_kernel, grid, dim3(256), 0, st, (const h16*)x, (const h16*)dy, stats, (const fix_t*)bstats, gamma, beta,
-               (const h16*)dx_add, (h16*)dx, HW, C, G, eps, do_silu, rows_per_cta);
+               (const h16*)dx_add, (h16*)dx, HW, C, G, eps, do_silu & 1, rows_per_cta);
     return check_launch("dwg_groupnorm_bwd");
 }
 

@@ -73,7 +73,7 @@ class GridEncoder(nn.Module):
 class MeshBindingGaussianModel(nn.Module):
     """core/system/avatar.py:921-1094."""
 
-    def __init__(self, mesh: dict, n_per_triangle=6, device='cuda'):
+    def __init__(self, mesh: dict, n_per_triangle=6, device='cuda', lbs_model=None):
         super().__init__()
         self.n_per_triangle = n_per_triangle
         self.register_buffer('predefined_vertex_indices', mesh['predefined_vertex_indices'].to(device))
@@ -88,6 +88,35 @@ class MeshBindingGaussianModel(nn.Module):
         self.register_buffer('_zaxis', torch.tensor([0.0, 0.0, 1.0], device=device))
         self.register_buffer('_xaxis', torch.tensor([1.0, 0.0, 0.0], device=device))
         self.register_buffer('_flip', torch.tensor([1.0, -1.0, -1.0], device=device).view(1, 3, 1))
+        self._build_tables(lbs_model)
+
+    def _build_tables(self, lbs_model=None):
+        """Static tables of the kernel path (ops.glbs_vertices / ops.mesh_gaussians); rebuilt after a checkpoint changed the mesh."""
+        device = self.triangles.device
+        tri = self.triangles.cpu()
+        Vp = int(self.predefined_vertex_indices.shape[0])
+        order = torch.argsort(tri.reshape(-1), stable=True)                  # incidences grouped by vertex, triangle order kept
+        counts = torch.bincount(tri.reshape(-1), minlength=Vp)
+        nb = lambda n, t: self.register_buffer(n, t.to(device), persistent=False)
+        nb('_tri_i32', tri.to(torch.int32).contiguous())
+        nb('_adj_ptr', torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(counts, 0)]).to(torch.int32))
+        nb('_adj_tri', (order // 3).to(torch.int32))
+        self._has_dirs = lbs_model is not None
+        if lbs_model is not None:
+            vi = self.predefined_vertex_indices
+            ns = lbs_model._shapedirs_full.shape[1]
+            V = lbs_model.v_template.shape[0]
+            nb('_sdirs_sel', lbs_model._shapedirs_full.view(V, 3, ns)[vi].contiguous())                     # [Vp,3,400]
+            nb('_pdirs_sel', lbs_model.posedirs.data.view(-1, V, 3)[:, vi].permute(1, 2, 0).contiguous())   # [Vp,3,486]
+            nb('_w_sel', lbs_model.lbs_weights.data[vi].contiguous())                                       # [Vp,55]
+
+    def posed_vertex_coords(self, jt):
+        """The part's predefined vertices under the GLBS vertex transform of joint state ``jt`` (ops.glbs_joints)."""
+        return ops.glbs_vertices(jt, self._sdirs_sel, self._pdirs_sel, self._w_sel, self._vertex_coords)
+
+    def gaussians(self, vertex_coords):
+        """(positions, scales, quaternions) = get_positions + get_scales_and_quaternions as one kernel each way."""
+        return ops.mesh_gaussians(self._bary_coords, self._scales, vertex_coords, self._tri_i32, self._adj_ptr, self._adj_tri, self.n_per_triangle)
 
     def get_positions(self, vertex_coords):
         bary = self._bary_coords / self._bary_coords.sum(dim=-1, keepdim=True)
@@ -125,7 +154,7 @@ class DreamWaltzGAvatar(nn.Module):
     """The animate() path of reference DreamWaltzG (avatar.py:1500-1588) on dwg kernels."""
 
     def __init__(self, body_model: dict, avatar: dict, device='cuda', nerf_bound=2.0,
-                 init_offset=0.01, init_scale=1e-3, max_scale=0.01):
+                 init_offset=0.01, init_scale=1e-3, max_scale=0.01, learn_hand_betas=False, learn_face_betas=False):
         super().__init__()
         self.device = device
         self.lbs_model = dlbs.GeneralLinearBlendSkinning(body_model, device=device)
@@ -138,11 +167,17 @@ class DreamWaltzGAvatar(nn.Module):
         self.nerf_opacity_and_color_net = MLP(32, 4, 64, 3).to(device)
         self.nerf_scale_and_quaternion_net = DeformNetwork(32, 63, 4, 64).to(device)
         self.mesh_binding_gaussians = nn.ModuleDict()
-        if avatar.get('mesh') is not None:
-            self.mesh_binding_gaussians['hands'] = MeshBindingGaussianModel(avatar['mesh'], device=device)
+        meshes = avatar.get('meshes') or ({'hands': avatar['mesh']} if avatar.get('mesh') is not None else {})
+        for part, mesh in meshes.items():                       # predefined_body_parts: 'hands' [, 'face'] (scripts/train_w_expr.sh:9)
+            self.mesh_binding_gaussians[part] = MeshBindingGaussianModel(mesh, device=device, lbs_model=self.lbs_model)
+        # avatar.py:1222-1225: optional learnable shape offset used by the mesh-bound parts
+        self.learn_hand_betas, self.learn_face_betas = learn_hand_betas, learn_face_betas
+        self.learn_betas = learn_hand_betas or learn_face_betas
+        self._betas = nn.Parameter(self.lbs_model.betas.data.clone(), requires_grad=self.learn_betas)
         self.init_offset, self.init_scale, self.max_scale = init_offset, init_scale, max_scale
         self.smpl_canonical_inputs = {}
         self._canonical_cache = None
+        self.use_kernels = True          # False: GLBS module + torch mesh ops (kept for parity tests and the learn_betas case)
 
     def get_lbs_weights(self):
         return self._lbs_weights / self._lbs_weights.sum(dim=-1, keepdim=True)          # avatar.py:914-917
@@ -157,33 +192,66 @@ class DreamWaltzGAvatar(nn.Module):
     def animate(self, smpl_observed_inputs: Optional[dict] = None) -> GaussianOutput:
         if smpl_observed_inputs is None:
             smpl_observed_inputs = self.smpl_canonical_inputs
-        # canonical LBS: constant while the shape is frozen -> evaluated once and cached
-        # (the reference recomputes it every step, avatar.py:1508)
+        if self.learn_betas or not self.use_kernels:
+            return self._animate_torch(smpl_observed_inputs)     # gradient w.r.t. the shape offset: autograd through the GLBS module
+        # ---- R1: joint state of the canonical (cached: constant while the shape is frozen; the reference recomputes it
+        # every step, avatar.py:1508) and the observed pose -- ONE kernel each (dwg_glbs_joints)
         if self._canonical_cache is None:
-            with torch.no_grad():
-                _, cV, ctr = self.lbs_model.forward(**self.smpl_canonical_inputs)
-            self._canonical_cache = (cV, ctr)
-        cnl_V, cnl_tr = self._canonical_cache
+            cj = self.lbs_model.joint_transforms(**self.smpl_canonical_inputs)
+            self._canonical_cache = (cj, [gm.posed_vertex_coords(cj) for gm in self.mesh_binding_gaussians.values()])
+        cnl_j, cnl_vcs = self._canonical_cache
+        obs_j = self.lbs_model.joint_transforms(**smpl_observed_inputs)
+        positions = self._positions
+        W = self.get_lbs_weights()
+        n_unc = positions.shape[0]
+        # canonical positions of every Gaussian (unconstrained first, then the mesh-bound parts): ONE grid encode and ONE
+        # fused MLP launch serve all of them (avatar.py:1519-1535,1567-1572)
+        canon = [ops.lbs_skin(W, cnl_j['A_t'], positions)]
+        for gm, cvc in zip(self.mesh_binding_gaussians.values(), cnl_vcs):
+            canon.append(gm.gaussians(cvc)[0])
+        enc = self.nerf_encoder(torch.cat(canon, dim=0) if len(canon) > 1 else canon[0], bound=self.nerf_bound)
+        body_pose = smpl_observed_inputs.get('body_pose')
+        if body_pose is None:
+            body_pose = self.lbs_model.body_pose
+        colors, opacities, pos, scales = ops.avatar_mlp(enc, positions, body_pose, self._mlp_params(), n_unc,
+                                                        self.init_offset, self.init_scale, self.max_scale)
+        quats = F.normalize(self._quaternions)
+        pos, quats = ops.lbs_skin(W, obs_j['A_t'], pos, quats)
+        if len(self.mesh_binding_gaussians) == 0:
+            return GaussianOutput(positions=pos, opacities=opacities, colors=colors, quaternions=quats, scales=scales)
+        all_pos, all_q, all_sc = [pos], [quats], [scales]
+        for gm in self.mesh_binding_gaussians.values():         # R5: two kernels per part (vertices, Gaussians)
+            m_pos, m_sc, m_q = gm.gaussians(gm.posed_vertex_coords(obs_j))
+            all_pos.append(m_pos); all_q.append(m_q); all_sc.append(m_sc)
+        return GaussianOutput(positions=torch.cat(all_pos, dim=0), opacities=opacities, colors=colors,
+                              quaternions=torch.cat(all_q, dim=0), scales=torch.cat(all_sc, dim=0))
+
+    def _animate_torch(self, smpl_observed_inputs):
+        """The same path on the torch GLBS module / torch mesh ops (autograd reaches the shape offset `_betas`)."""
         with torch.no_grad():
+            _, cnl_V, cnl_tr = self.lbs_model.forward(**self.smpl_canonical_inputs)
             _, obs_V, obs_tr = self.lbs_model.forward(**smpl_observed_inputs)
         positions = self._positions
         W = self.get_lbs_weights()
         cnl_jt = self._joint_pose_transform(cnl_tr)
         obs_jt = self._joint_pose_transform(obs_tr)
         n_unc = positions.shape[0]
-        cnl_T = cnl_V.squeeze(0) if cnl_V.SE3.dim() == 4 else cnl_V
-        obs_T = obs_V.squeeze(0) if obs_V.SE3.dim() == 4 else obs_V
-        # canonical positions of every Gaussian (unconstrained first, then the mesh-bound parts): ONE grid
-        # encode and ONE fused MLP launch serve all of them (avatar.py:1519-1535,1567-1572)
+        sq = lambda t: t.squeeze(0) if t.SE3.dim() == 4 else t
+        cnl_T, obs_T = sq(cnl_V), sq(obs_V)
+        cnl_Tb, obs_Tb = cnl_T, obs_T
+        if self.learn_betas:                                    # avatar.py:1551-1553
+            _, cVb, _ = self.lbs_model.forward(**self.smpl_canonical_inputs, extra_betas=self._betas)
+            _, oVb, _ = self.lbs_model.forward(**smpl_observed_inputs, extra_betas=self._betas)
+            cnl_Tb, obs_Tb = sq(cVb), sq(oVb)
+        with_betas = lambda part: (part == 'hands' and self.learn_hand_betas) or (part == 'face' and self.learn_face_betas)
         canon = [cnl_jt.transform_points(positions, weights=W)]
-        for _, gm in self.mesh_binding_gaussians.items():
-            cnl_vc = cnl_T.transform_points(gm._vertex_coords, indices=gm.predefined_vertex_indices)
+        for part, gm in self.mesh_binding_gaussians.items():
+            cnl_vc = (cnl_Tb if with_betas(part) else cnl_T).transform_points(gm._vertex_coords, indices=gm.predefined_vertex_indices)
             canon.append(gm.get_positions(cnl_vc))
         enc = self.nerf_encoder(torch.cat(canon, dim=0) if len(canon) > 1 else canon[0], bound=self.nerf_bound)
         body_pose = smpl_observed_inputs.get('body_pose')
         if body_pose is None:
             body_pose = torch.zeros(1, 63, device=self.device)
-        # sigma net + deform net + non_rigid_transform (avatar.py:1283-1294,1464-1498, shipped flags) in one kernel
         colors, opacities, pos, scales = ops.avatar_mlp(enc, positions, body_pose, self._mlp_params(), n_unc,
                                                         self.init_offset, self.init_scale, self.max_scale)
         quats = F.normalize(self._quaternions)
@@ -191,8 +259,8 @@ class DreamWaltzGAvatar(nn.Module):
         if len(self.mesh_binding_gaussians) == 0:
             return GaussianOutput(positions=pos, opacities=opacities, colors=colors, quaternions=quats, scales=scales)
         all_pos, all_q, all_sc = [pos], [quats], [scales]
-        for _, gm in self.mesh_binding_gaussians.items():
-            obs_vc = obs_T.transform_points(gm._vertex_coords, indices=gm.predefined_vertex_indices)
+        for part, gm in self.mesh_binding_gaussians.items():
+            obs_vc = (obs_Tb if with_betas(part) else obs_T).transform_points(gm._vertex_coords, indices=gm.predefined_vertex_indices)
             m_pos = gm.get_positions(obs_vc)
             m_sc, m_q = gm.get_scales_and_quaternions(obs_vc, m_pos)
             all_pos.append(m_pos); all_q.append(m_q); all_sc.append(m_sc)

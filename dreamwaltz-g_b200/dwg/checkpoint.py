@@ -126,7 +126,10 @@ def load_scene_state_dict(scene, state_dict, strict=False):
     """Scene.load_state_dict (scene.py:202-207)."""
     by = organize_state_dict(state_dict)
     reset_by_state_dict(scene.avatar, by.get('avatar', {}))
-    return scene.load_state_dict(state_dict, strict=strict)
+    res = scene.load_state_dict(state_dict, strict=strict)
+    for gm in getattr(scene.avatar, 'mesh_binding_gaussians', {}).values():      # derived kernel tables follow the loaded mesh
+        gm._build_tables(scene.avatar.lbs_model)
+    return res
 
 
 def save_checkpoint(path, scene, train_step, past_checkpoints=None, optimizers=None, full=False):

@@ -92,6 +92,7 @@ class ControlNetScoreDistillation:
         def vae_b():
             return self.vae.backward(tape, st['glat'])
 
+        ops.STATS_ARENA.enabled = False              # sub-graphs are replayed independently: each GroupNorm zeroes its own statistics
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s), torch.no_grad():
@@ -108,6 +109,7 @@ class ControlNetScoreDistillation:
             counts[name] = lib().launches - n0
             self._g[name] = (g, out)
         self._graph_launches = counts
+        ops.STATS_ARENA.enabled = True
         return counts
 
     def _replay(self, name):
@@ -237,6 +239,8 @@ class ControlNetScoreDistillation:
         Returns the reference's dict: latents, timestep, sources, targets, gradients, diffusion_loss."""
         assert inputs.dim() == 4 and inputs.shape[1] == 3, 'inputs must be [B,3,H,W]'
         inputs = self.prepare_latents(inputs)
+        if not getattr(self, '_g', None):
+            ops.STATS_ARENA.reset(inputs.device)               # ONE memset serves every GroupNorm statistic of this step
         self.guidance_scale = guidance_scale if guidance_scale is not None else self.get_guidance_scale(train_step, max_iteration)
         latents = self.encode_images(inputs, vae_eps)
         neg = text_embeds_dict['neg' if use_negative_text else 'null']

@@ -207,7 +207,11 @@ class DiffusionNet:
         W = self.W
         B, H, Wd, C = x.shape
         h = gn(W, p + '.norm', x, self.G, 1e-6, False)
-        h = conv(W, p + '.proj_in', h, padding=0).view(B, H * Wd, C)
+        lin_proj = W.w[p + '.proj_in'].dim() == 2               # SD2.1 use_linear_projection: nn.Linear on the token layout (same memory)
+        if lin_proj:
+            h = linear(W, p + '.proj_in', h.view(B * H * Wd, C)).view(B, H * Wd, C)
+        else:
+            h = conv(W, p + '.proj_in', h, padding=0).view(B, H * Wd, C)
         b = p + '.transformer_blocks.0'
         n = ops.layer_norm(h, W.w[b + '.norm1'], W.b[b + '.norm1'])
         h = attention(W, b + '.attn1', n, n, heads, h)
@@ -216,6 +220,8 @@ class DiffusionNet:
         n = ops.layer_norm(h, W.w[b + '.norm3'], W.b[b + '.norm3'])
         g = linear(W, b + '.ff.net.0.proj', n.reshape(B * H * Wd, C), act='geglu')        # GEGLU fused in the epilogue
         h = linear(W, b + '.ff.net.2', g, residual=h.reshape(B * H * Wd, C)).view(B, H, Wd, C)
+        if lin_proj:
+            return linear(W, p + '.proj_out', h.view(B * H * Wd, C), residual=x.view(B * H * Wd, C)).view(B, H, Wd, C)
         return conv(W, p + '.proj_out', h, padding=0, residual=x)
 
     def down_path(self, h, tproj, ctx):

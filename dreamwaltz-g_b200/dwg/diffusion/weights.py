@@ -8,11 +8,15 @@ import torch
 
 SD15 = dict(block_out=(320, 640, 1280, 1280), layers_per_block=2, heads=8, ctx_dim=768, in_ch=4, out_ch=4,
             cond_embed=(16, 32, 96, 256), groups=32)
+# SD2.1: attention_head_dim (5, 10, 20, 20) = HEADS per level (head width 64), OpenCLIP context 1024,
+# use_linear_projection=True (proj_in / proj_out of every Transformer2DModel are nn.Linear)
 SD21 = dict(block_out=(320, 640, 1280, 1280), layers_per_block=2, heads=(5, 10, 20, 20), ctx_dim=1024, in_ch=4, out_ch=4,
-            cond_embed=(16, 32, 96, 256), groups=32)
+            cond_embed=(16, 32, 96, 256), groups=32, linear_proj=True)
 VAE15 = dict(block_out=(128, 256, 512, 512), layers_per_block=2, latent=4, groups=32, scaling_factor=0.18215)
 TINY = dict(block_out=(64, 128, 256, 256), layers_per_block=2, heads=8, ctx_dim=96, in_ch=4, out_ch=4,
             cond_embed=(16, 32, 32, 64), groups=32)
+TINY21 = dict(block_out=(64, 128, 256, 256), layers_per_block=2, heads=(1, 2, 4, 4), ctx_dim=128, in_ch=4, out_ch=4,
+              cond_embed=(16, 32, 32, 64), groups=32, linear_proj=True)
 TINY_VAE = dict(block_out=(32, 64, 64, 64), layers_per_block=2, latent=4, groups=32, scaling_factor=0.18215)
 
 
@@ -45,9 +49,12 @@ class _Init:
         if cin != cout:
             self.conv(p + '.conv_shortcut', cin, cout, k=1)
 
-    def transformer(self, p, c, ctx_dim):
+    def transformer(self, p, c, ctx_dim, linear_proj=False):
         self.norm(p + '.norm', c)
-        self.conv(p + '.proj_in', c, c, k=1)
+        if linear_proj:
+            self.lin(p + '.proj_in', c, c)
+        else:
+            self.conv(p + '.proj_in', c, c, k=1)
         b = p + '.transformer_blocks.0'
         for n in ('norm1', 'norm2', 'norm3'):
             self.norm(f'{b}.{n}', c)
@@ -58,7 +65,10 @@ class _Init:
             self.lin(f'{b}.{a}.to_out.0', c, c, gain=0.5)
         self.lin(f'{b}.ff.net.0.proj', c, 8 * c)
         self.lin(f'{b}.ff.net.2', 4 * c, c, gain=0.5)
-        self.conv(p + '.proj_out', c, c, k=1, gain=0.5)
+        if linear_proj:
+            self.lin(p + '.proj_out', c, c, gain=0.5)
+        else:
+            self.conv(p + '.proj_out', c, c, k=1, gain=0.5)
 
     def encoder_path(self, cfg):
         bo, temb_dim = cfg['block_out'], cfg['block_out'][0] * 4
@@ -70,12 +80,12 @@ class _Init:
             for j in range(cfg['layers_per_block']):
                 self.resnet(f'down_blocks.{i}.resnets.{j}', cin, c, temb_dim)
                 if i < len(bo) - 1:
-                    self.transformer(f'down_blocks.{i}.attentions.{j}', c, cfg['ctx_dim'])
+                    self.transformer(f'down_blocks.{i}.attentions.{j}', c, cfg['ctx_dim'], cfg.get('linear_proj', False))
                 cin = c
             if i < len(bo) - 1:
                 self.conv(f'down_blocks.{i}.downsamplers.0.conv', c, c)
         self.resnet('mid_block.resnets.0', bo[-1], bo[-1], temb_dim)
-        self.transformer('mid_block.attentions.0', bo[-1], cfg['ctx_dim'])
+        self.transformer('mid_block.attentions.0', bo[-1], cfg['ctx_dim'], cfg.get('linear_proj', False))
         self.resnet('mid_block.resnets.1', bo[-1], bo[-1], temb_dim)
 
 
@@ -102,7 +112,7 @@ def make_unet(cfg=SD15, seed=1):
             sk = skips.pop()
             w.resnet(f'up_blocks.{i}.resnets.{j}', cin + sk, c, temb_dim)
             if i > 0:
-                w.transformer(f'up_blocks.{i}.attentions.{j}', c, cfg['ctx_dim'])
+                w.transformer(f'up_blocks.{i}.attentions.{j}', c, cfg['ctx_dim'], cfg.get('linear_proj', False))
             cin = c
         if i < len(bo) - 1:
             w.conv(f'up_blocks.{i}.upsamplers.0.conv', c, c)

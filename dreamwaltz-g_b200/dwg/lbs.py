@@ -238,6 +238,29 @@ class GeneralLinearBlendSkinning(nn.Module):
         self.register_buffer('J_template', torch.einsum('ik,ji->jk', self.v_template.data, self.J_regressor.data))
         self.register_buffer('_shapedirs_full', torch.cat([self.shapedirs.data, self.expr_dirs.data], dim=-1)
                              .reshape(-1, self.shapedirs.shape[-1] + self.expr_dirs.shape[-1]).contiguous())
+        # fused joint path (ops.glbs_joints): the joint regressor is linear, so J = J_template + JS . shape with the
+        # constant JS = J_regressor . shapedirs [55*3, 400] -- no full-mesh blend shapes for the joints
+        V, ns = self.v_template.shape[0], self._shapedirs_full.shape[1]
+        JS = torch.einsum('ji,ick->jck', self.J_regressor.data, self._shapedirs_full.view(V, 3, ns)).reshape(-1, ns).contiguous()
+        self.register_buffer('_JS', JS, persistent=False)
+        self.register_buffer('_parents_i32', torch.tensor([p if p >= 0 else 0 for p in self.parents], dtype=torch.int32, device=device),
+                             persistent=False)
+
+    @torch.no_grad()
+    def joint_transforms(self, body_pose=None, global_orient=None, left_hand_pose=None, right_hand_pose=None, expression=None,
+                         transl=None, betas=None, extra_betas=None, **_):
+        """The part of forward() that DreamWaltzG.animate consumes, as ONE kernel (dwg_glbs_joints): the joint transforms
+        A (= tr['J_pose_rigid']), transl o A (= _joint_pose_transform), and the pose feature / shape vector that the
+        per-part vertex kernel (dwg_glbs_vertices) needs.  Same argument semantics as forward() (jaw / eye poses always
+        come from the module, inverse_lbs.py:617-619)."""
+        betas = self.betas if betas is None else betas
+        if extra_betas is not None:
+            betas = betas + extra_betas
+        d = lambda v, dflt: dflt if v is None else v
+        parts = (d(global_orient, self.global_orient), d(body_pose, self.body_pose), self.jaw_pose, self.leye_pose, self.reye_pose,
+                 d(left_hand_pose, self.left_hand_pose), d(right_hand_pose, self.right_hand_pose))
+        return ops.glbs_joints(parts, self.pose_mean, betas, d(expression, self.expression), self.J_template, self._JS, self._parents_i32,
+                               transl=transl)
 
     def get_full_shape(self, betas=None, expression=None, extra_betas=None):
         betas = self.betas if betas is None else betas

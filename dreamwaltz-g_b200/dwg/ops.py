@@ -51,6 +51,63 @@ def lbs_skin(W, A, x, q=None):
     return _LbsSkin.apply(W, A, x, q)
 
 
+# ------------------------------------------------------------------------------ R1 / R5 kernels
+def glbs_joints(pose_parts, pose_mean, betas, expression, J_template, JS, parents_i32, transl=None):
+    """dwg_glbs_joints: pose_parts = (global_orient, body_pose, jaw, leye, reye, left_hand, right_hand) fp32 device tensors.
+    -> dict(A [55,4,4], A_t [55,4,4], pose_feature [486], shape [ns], joints [55,3]).  No autograd (pose inputs carry none)."""
+    dev = betas.device
+    pp = [f32c(t).reshape(-1) for t in pose_parts]
+    betas, expression = f32c(betas).reshape(-1), f32c(expression).reshape(-1)
+    nb, ne = betas.numel(), expression.numel()
+    e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    out = {'A': e(55, 4, 4), 'A_t': e(55, 4, 4), 'pose_feature': e(486), 'shape': e(nb + ne), 'joints': e(55, 3)}
+    tr = None if transl is None else f32c(transl).reshape(-1)
+    check(lib().dwg_glbs_joints(*[ptr(t) for t in pp], ptr(pose_mean), ptr(betas), nb, ptr(expression), ne, ptr(J_template), ptr(JS),
+                                ptr(parents_i32), ptr(tr), ptr(out['A']), ptr(out['A_t']), ptr(out['pose_feature']), ptr(out['shape']),
+                                ptr(out['joints']), stream()), 'dwg_glbs_joints')
+    out['transl'] = tr
+    return out
+
+
+def glbs_vertices(jt, shapedirs_sel, posedirs_sel, weights_sel, points):
+    """dwg_glbs_vertices: the vertex composite transform of GLBS applied to the predefined vertices `points` [Vp,3]."""
+    Vp = points.shape[0]
+    out = torch.empty(Vp, 3, device=points.device, dtype=torch.float32)
+    check(lib().dwg_glbs_vertices(Vp, jt['shape'].numel(), ptr(jt['shape']), ptr(jt['pose_feature']), ptr(jt['A']), ptr(jt['transl']),
+                                  ptr(shapedirs_sel), ptr(posedirs_sel), ptr(weights_sel), ptr(f32c(points)), ptr(out), stream()), 'dwg_glbs_vertices')
+    return out
+
+
+class _MeshGaussians(torch.autograd.Function):
+    """(positions, scales, quaternions) of the mesh-bound Gaussians of one part (dwg_mesh_gaussians_fwd/bwd)."""
+
+    @staticmethod
+    def forward(ctx, bary, scales_param, vertex_coords, triangles, adj_ptr, adj_tri, n_per_tri):
+        b, sp, vc = f32c(bary).reshape(-1, 3), f32c(scales_param), f32c(vertex_coords)
+        Vp, F, P = vc.shape[0], triangles.shape[0], b.shape[0]
+        assert P == F * n_per_tri and sp.shape == (P, 3)
+        e = lambda *s: torch.empty(*s, device=vc.device, dtype=torch.float32)
+        vn, pos, sc, q = e(Vp, 3), e(P, 3), e(P, 3), e(P, 4)
+        check(lib().dwg_mesh_gaussians_fwd(Vp, F, int(n_per_tri), ptr(vc), ptr(triangles), ptr(adj_ptr), ptr(adj_tri), ptr(b), ptr(sp), ptr(vn),
+                                           ptr(pos), ptr(sc), ptr(q), stream()), 'dwg_mesh_gaussians_fwd')
+        ctx.save_for_backward(b, sp, vc, vn, triangles)
+        ctx.n, ctx.bshape = int(n_per_tri), bary.shape
+        return pos, sc, q
+
+    @staticmethod
+    def backward(ctx, g_pos, g_sc, g_q):
+        b, sp, vc, vn, triangles = ctx.saved_tensors
+        gc = lambda g: None if g is None else f32c(g)
+        g_b, g_sp = torch.empty_like(b), torch.empty_like(sp)
+        check(lib().dwg_mesh_gaussians_bwd(triangles.shape[0], ctx.n, ptr(vc), ptr(vn), ptr(triangles), ptr(b), ptr(sp), ptr(gc(g_pos)), ptr(gc(g_sc)),
+                                           ptr(gc(g_q)), ptr(g_b), ptr(g_sp), stream()), 'dwg_mesh_gaussians_bwd')
+        return g_b.reshape(ctx.bshape), g_sp, None, None, None, None, None
+
+
+def mesh_gaussians(bary, scales_param, vertex_coords, triangles_i32, adj_ptr, adj_tri, n_per_tri):
+    return _MeshGaussians.apply(bary, scales_param, vertex_coords, triangles_i32, adj_ptr, adj_tri, n_per_tri)
+
+
 # ------------------------------------------------------------------------------ SH colour
 class _ShEval(torch.autograd.Function):
     @staticmethod
@@ -533,16 +590,52 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
 
 
 # ------------------------------------------------------------------------------ norm / activation kernels (bf16 NHWC)
+class StatsArena:
+    """One zero-initialised int64 buffer per device that serves the statistics workspace of EVERY GroupNorm (forward and
+    backward) of a step: ONE memset per step (reset(), called by the guidance at the top of __call__) instead of one memset
+    node in front of each of the ~130 GroupNorm launches.  A slice is handed out at most once between two resets; when the
+    arena is exhausted or disabled the caller falls back to a private buffer that the C entry point zeroes itself."""
+
+    def __init__(self, entries=1 << 17):
+        self.entries, self.buf, self.cur, self.enabled = entries, {}, {}, True
+
+    def reset(self, device):
+        dev = torch.device(device)
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        if key not in self.buf:
+            self.buf[key] = torch.zeros(self.entries, device=dev, dtype=torch.int64)
+        else:
+            self.buf[key].zero_()
+        self.cur[key] = 0
+
+    def take(self, device, n):
+        if not self.enabled:
+            return None
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        cur = self.cur.get(key)
+        if cur is None or cur + n > self.entries:
+            return None
+        self.cur[key] = cur + n
+        return self.buf[key][cur:cur + n]
+
+
+STATS_ARENA = StatsArena()
+
+
 def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, return_stats=False):
-    """x [N, ..., C] bf16 channels-last -> [SiLU](GroupNorm(x)) (dwg_groupnorm_fwd)."""
+    """x [N, ..., C] fp16 channels-last -> [SiLU](GroupNorm(x)) (dwg_groupnorm_fwd)."""
     _chk_f16(x)
     assert x.is_contiguous()
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     y = torch.empty_like(x)
-    stats = torch.empty(N, groups, 2, device=x.device, dtype=torch.int64)       # fixed-point (sum, sumsq), include/dwg.h
+    stats = STATS_ARENA.take(x.device, N * groups * 2)        # fixed-point (sum, sumsq), include/dwg.h
+    flags = int(silu) | (2 if stats is not None else 0)
+    if stats is None:
+        stats = torch.empty(N * groups * 2, device=x.device, dtype=torch.int64)
+    stats = stats.view(N, groups, 2)
     L = lib()
-    check(L.dwg_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), N, HW, C, groups, float(eps), int(silu),
+    check(L.dwg_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), N, HW, C, groups, float(eps), flags,
                               stream()), 'dwg_groupnorm_fwd')
     object.__setattr__(L, 'launches', L.launches + L.dwg_groupnorm_last_launches() - 2)      # the proxy counted 2
     return (y, stats) if return_stats else y
@@ -554,9 +647,12 @@ def group_norm_bwd(x, dy, stats, gamma, beta, groups=32, eps=1e-5, silu=False, d
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     dx = torch.empty_like(x)
-    bstats = torch.empty(N, groups, 2, device=x.device, dtype=torch.int64)       # fixed-point (sum, sumsq), include/dwg.h
+    bstats = STATS_ARENA.take(x.device, N * groups * 2)
+    flags = int(silu) | (2 if bstats is not None else 0)
+    if bstats is None:
+        bstats = torch.empty(N * groups * 2, device=x.device, dtype=torch.int64)
     check(lib().dwg_groupnorm_bwd(ptr(x), ptr(dy), ptr(stats), ptr(gamma), ptr(beta), ptr(dx_add), ptr(dx), ptr(bstats), N, HW, C,
-                                  groups, float(eps), int(silu), stream()), 'dwg_groupnorm_bwd')
+                                  groups, float(eps), flags, stream()), 'dwg_groupnorm_bwd')
     return dx
 
 

@@ -176,8 +176,31 @@ def hand_triangles(model, max_triangles=2500):
     return tri
 
 
-def make_avatar(model, n_unconstrained=135000, n_mesh_triangles=2500, seed=0, dtype=torch.float32):
-    """Synthetic avatar state: unconstrained Gaussians + mesh-bound hand Gaussians."""
+def face_triangles(model, max_triangles=2500):
+    """Triangle subset on the head (head / jaw / eye joints 15, 22-24) for the mesh-bound 'face' part
+    (predefined_body_parts=hands,face of scripts/train_w_expr.sh)."""
+    vj = model['vertex_joint']
+    f = model['faces']
+    on_face = ((vj[f] == 15) | ((vj[f] >= 22) & (vj[f] <= 24))).all(1)
+    tri = torch.nonzero(on_face)[:, 0]
+    if tri.numel() > max_triangles:
+        tri = tri[torch.linspace(0, tri.numel() - 1, max_triangles).long()]
+    return tri
+
+
+def _mesh_part(model, tri_sel, dtype):
+    f, vt = model['faces'], model['v_template']
+    tris = f[tri_sel]
+    vidx, inv = torch.unique(tris.reshape(-1), return_inverse=True)
+    bary6 = torch.tensor([[2 / 3, 1 / 6, 1 / 6], [1 / 6, 2 / 3, 1 / 6], [1 / 6, 1 / 6, 2 / 3],
+                          [1 / 6, 5 / 12, 5 / 12], [5 / 12, 1 / 6, 5 / 12], [5 / 12, 5 / 12, 1 / 6]], dtype=dtype)
+    return {'predefined_vertex_indices': vidx, 'triangles': inv.reshape(-1, 3), '_vertex_coords': vt[vidx].clone(),
+            '_bary_coords': bary6.expand(tris.shape[0], -1, -1).clone(), '_scales': torch.ones(tris.shape[0] * 6, 3, dtype=dtype)}
+
+
+def make_avatar(model, n_unconstrained=135000, n_mesh_triangles=2500, seed=0, dtype=torch.float32, n_face_triangles=0):
+    """Synthetic avatar state: unconstrained Gaussians + mesh-bound hand Gaussians (+ a mesh-bound 'face' part when
+    n_face_triangles > 0: avatar['meshes'] = {'hands': ..., 'face': ...})."""
     g = torch.Generator().manual_seed(seed)
     f = model['faces']
     vt = model['v_template']
@@ -209,6 +232,10 @@ def make_avatar(model, n_unconstrained=135000, n_mesh_triangles=2500, seed=0, dt
         '_bary_coords': bary6.expand(tris.shape[0], -1, -1).clone(),
         '_scales': torch.ones(tris.shape[0] * 6, 3, dtype=dtype),
     }
+    if n_face_triangles > 0:
+        ft = face_triangles(model, n_face_triangles)
+        if ft.numel() > 0:
+            avatar['meshes'] = {'hands': avatar['mesh'], 'face': _mesh_part(model, ft, dtype)}
     return avatar
 
 

@@ -234,8 +234,13 @@ int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int out_f16,
  * Replace torch.nn.GroupNorm / LayerNorm / softmax / GEGLU / SiLU calls inside the diffusers
  * modules, and the CFG + SDS-gradient arithmetic of core/guidance/basic.py:595-603,642.
  */
+/* Shared-memory carve-out preference (percent, -1 = driver default) of the streaming kernels below: 100 keeps the SMs in
+ * the partition the tcgen05 kernels need, so GEMM <-> norm alternations do not re-partition L1/shared memory. */
+int dwg_nn_set_carveout(int percent);
 /* y = [SiLU](GroupNorm_G(x));  x,y [N,HW,C] fp16; stats [N,G,2] i64 workspace: (sum, sumsq) in 2^-20 fixed point,
- * accumulated with integer atomics so that the statistics are run-to-run deterministic; kept for bwd */
+ * accumulated with integer atomics so that the statistics are run-to-run deterministic; kept for bwd.
+ * do_silu: bit 0 = apply SiLU after the normalisation; bit 1 = `stats` (`bstats` in the backward) was pre-zeroed by the
+ * caller (e.g. one memset of an arena that serves every GroupNorm of a step), skip the internal memset. */
 int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, void* stats,
                       int N, int HW, int C, int G, float eps, int do_silu, void* stream);
 /* kernels launched by the last dwg_groupnorm_fwd: 1 = one-launch cluster kernel (tensor fits the shared memory of 8 CTAs
@@ -269,6 +274,39 @@ int dwg_sds_grad(const float* eps_uncond, const float* eps_cond, const float* no
  *   out [B,T,heads*hd] bf16.  hd multiple of 8, <= 128. */
 int dwg_attention_fwd(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* vt, int64_t Tkp,
                       int64_t vt_batch_stride, void* out, int B, int heads, int T, int Tk, int hd, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R1  GeneralLinearBlendSkinning.forward as DreamWaltzG.animate consumes it (core/human/inverse_lbs.py:570-784 with
+ * smplx.lbs batch_rodrigues / blend_shapes / vertices2joints / batch_rigid_transform), without the full-mesh blend shapes.
+ * dwg_glbs_joints (ONE CTA): pose parts (axis-angle, [1,3] / [1,63] / [1,45] as the reference passes them) + pose_mean [165],
+ *   betas [n_betas] (extra_betas already added), expression [n_expr]; J_template [55,3]; JS [165, n_betas+n_expr] =
+ *   J_regressor . shapedirs (constant, pre-multiplied by the caller); parents i32 [55]; transl [3] or NULL ->
+ *   A [55,4,4] relative rigid joint transforms (tr['J_pose_rigid']), A_transl = transl o A (the joint transform the Gaussians are
+ *   skinned with, avatar.py:1446-1460), pose_feature [486], shape_out [n_betas+n_expr], joints [55,3].
+ * dwg_glbs_vertices (one warp per vertex): the composite V_shape_offset o V_pose_offset o V_pose_rigid [o transl] applied to
+ *   points [Vp,3] of Vp PREDEFINED vertices only; shapedirs_sel [Vp,3,n_shape], posedirs_sel [Vp,3,486], weights_sel [Vp,55]
+ *   are the per-vertex slices of the model tensors gathered once by the caller. */
+int dwg_glbs_joints(const float* global_orient, const float* body_pose, const float* jaw_pose, const float* leye_pose,
+                    const float* reye_pose, const float* left_hand_pose, const float* right_hand_pose, const float* pose_mean,
+                    const float* betas, int n_betas, const float* expression, int n_expr,
+                    const float* J_template, const float* JS, const int32_t* parents, const float* transl,
+                    float* A, float* A_transl, float* pose_feature, float* shape_out, float* joints, void* stream);
+int dwg_glbs_vertices(int Vp, int n_shape, const float* shape, const float* pose_feature, const float* A, const float* transl,
+                      const float* shapedirs_sel, const float* posedirs_sel, const float* weights_sel, const float* points,
+                      float* out, void* stream);
+
+/* R5  Mesh-bound Gaussians (MeshBindingGaussianModel.get_positions / get_scales_and_quaternions, core/system/avatar.py:
+ * 1016-1079, with compute_normal of utils/mesh.py:34-97).  vertex_coords [Vp,3]; triangles i32 [F,3]; adj_ptr i32 [Vp+1] /
+ * adj_tri i32 [3F]: static vertex -> incident-triangle lists; bary [F*n_per_tri,3] RAW barycentric weights; scales_param
+ * [F*n_per_tri,3] -> vertex_normals [Vp,3] (kept for the backward), positions [P,3], scales [P,3] (column 0 = 0),
+ * quaternions [P,4] (real first, standardised).  Backward: gradients w.r.t. bary and scales_param (vertex coordinates are
+ * constants of the step); NULL upstream gradients mean zero. */
+int dwg_mesh_gaussians_fwd(int Vp, int F, int n_per_tri, const float* vertex_coords, const int32_t* triangles,
+                           const int32_t* adj_ptr, const int32_t* adj_tri, const float* bary, const float* scales_param,
+                           float* vertex_normals, float* positions, float* scales, float* quaternions, void* stream);
+int dwg_mesh_gaussians_bwd(int F, int n_per_tri, const float* vertex_coords, const float* vertex_normals, const int32_t* triangles,
+                           const float* bary, const float* scales_param, const float* g_positions, const float* g_scales,
+                           const float* g_quaternions, float* g_bary, float* g_scales_param, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (f2) Fused multi-tensor Adam.  Replaces the torch.optim.Adam instances the reference steps every iteration

@@ -130,10 +130,16 @@ def animate(model, avatar, nets, grid_encode, smpl_canonical, smpl_observed, bou
     pos, scales, quats = non_rigid(positions, d_xyz, d_scale, avatar['_quaternions'])
     pos, quats = olbs.lbs_transform(pos, obs_tr, W, quaternions=quats)
     out = {'positions': pos, 'opacities': opac, 'colors': colors, 'quaternions': quats, 'scales': scales}
-    mesh = avatar.get('mesh')
-    if mesh is not None:
+    meshes = avatar.get('meshes') or ({'hands': avatar['mesh']} if avatar.get('mesh') is not None else {})
+    betas = avatar.get('_betas')                 # avatar.py:1551-1553: learn_hand_betas / learn_face_betas
+    learn = avatar.get('learn_betas_parts', ())
+    if betas is not None and learn:
+        _, cnl_Vb, _ = olbs.glbs_forward(model, **smpl_canonical, extra_betas=betas)
+        _, obs_Vb, _ = olbs.glbs_forward(model, **smpl_observed, extra_betas=betas)
+    for part, mesh in meshes.items():
         vidx = mesh['predefined_vertex_indices']
-        cnl_T, obs_T = cnl_V.squeeze(0), obs_V.squeeze(0)
+        use_b = betas is not None and part in learn
+        cnl_T, obs_T = (cnl_Vb if use_b else cnl_V).squeeze(0), (obs_Vb if use_b else obs_V).squeeze(0)
         cnl_vc = cnl_T.transform_points(mesh['_vertex_coords'], indices=vidx)
         cnl_p = mesh_positions(cnl_vc, mesh['triangles'], mesh['_bary_coords'])
         m_enc = grid_encode(cnl_p)

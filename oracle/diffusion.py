@@ -59,11 +59,21 @@ def attention(sd, p, x, ctx, heads):
     return _lin(sd, p + '.to_out.0', o.transpose(1, 2).reshape(B, T, C))
 
 
+def _heads_at(cfg, level):
+    """attention_head_dim of the diffusers configs: an int (SD1.5: 8 heads everywhere) or per-level heads (SD2.1)."""
+    h = cfg['heads']
+    return h if isinstance(h, int) else h[level]
+
+
 def transformer(sd, p, x, ctx, heads, groups):
     B, C, H, W = x.shape
     res = x
-    h = _conv(sd, p + '.proj_in', _gn(sd, p + '.norm', x, groups, 1e-6), padding=0)
-    h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
+    n0 = _gn(sd, p + '.norm', x, groups, 1e-6)
+    lin_proj = sd[p + '.proj_in.weight'].dim() == 2            # use_linear_projection (SD2.1): Linear after the reshape
+    if lin_proj:
+        h = _lin(sd, p + '.proj_in', n0.permute(0, 2, 3, 1).reshape(B, H * W, C))
+    else:
+        h = _conv(sd, p + '.proj_in', n0, padding=0).permute(0, 2, 3, 1).reshape(B, H * W, C)
     b = p + '.transformer_blocks.0'
     n = F.layer_norm(h, (C,), sd[b + '.norm1.weight'], sd[b + '.norm1.bias'])
     h = h + attention(sd, b + '.attn1', n, n, heads)
@@ -73,6 +83,8 @@ def transformer(sd, p, x, ctx, heads, groups):
     g = _lin(sd, b + '.ff.net.0.proj', n)
     a, gate = g.chunk(2, dim=-1)
     h = h + _lin(sd, b + '.ff.net.2', a * F.gelu(gate))
+    if lin_proj:
+        return _lin(sd, p + '.proj_out', h).reshape(B, H, W, C).permute(0, 3, 1, 2) + res
     h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
     return _conv(sd, p + '.proj_out', h, padding=0) + res
 
@@ -91,7 +103,7 @@ def _down_path(sd, cfg, h, temb, ctx):
         for j in range(cfg['layers_per_block']):
             h = resnet(sd, f'down_blocks.{i}.resnets.{j}', h, temb, G, 1e-5)
             if has_attn:
-                h = transformer(sd, f'down_blocks.{i}.attentions.{j}', h, ctx, cfg['heads'], G)
+                h = transformer(sd, f'down_blocks.{i}.attentions.{j}', h, ctx, _heads_at(cfg, i), G)
             skips.append(h)
         if i < nb - 1:
             h = _conv(sd, f'down_blocks.{i}.downsamplers.0.conv', h, stride=2, padding=1)
@@ -102,7 +114,7 @@ def _down_path(sd, cfg, h, temb, ctx):
 def _mid(sd, cfg, h, temb, ctx):
     G = cfg['groups']
     h = resnet(sd, 'mid_block.resnets.0', h, temb, G, 1e-5)
-    h = transformer(sd, 'mid_block.attentions.0', h, ctx, cfg['heads'], G)
+    h = transformer(sd, 'mid_block.attentions.0', h, ctx, _heads_at(cfg, len(cfg['block_out']) - 1), G)
     return resnet(sd, 'mid_block.resnets.1', h, temb, G, 1e-5)
 
 
@@ -143,7 +155,7 @@ def unet_forward(sd, cfg, sample, t, ctx, down_residuals=None, mid_residual=None
             h = torch.cat([h, skips.pop()], dim=1)
             h = resnet(sd, f'up_blocks.{i}.resnets.{j}', h, temb, G, 1e-5)
             if has_attn:
-                h = transformer(sd, f'up_blocks.{i}.attentions.{j}', h, ctx, cfg['heads'], G)
+                h = transformer(sd, f'up_blocks.{i}.attentions.{j}', h, ctx, _heads_at(cfg, nb - 1 - i), G)
         if i < nb - 1:
             h = F.interpolate(h, scale_factor=2.0, mode='nearest')
             h = _conv(sd, f'up_blocks.{i}.upsamplers.0.conv', h)

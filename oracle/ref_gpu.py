@@ -140,7 +140,7 @@ class RefGridEncode(torch.autograd.Function):
 class RefGpuScene:
     """One SDS step of the cfg2 workload the way the reference would run it on a GPU (see module docstring)."""
 
-    def __init__(self, device, tiny=False, n_unc=135000, n_tri=2500, img=512, seed_rank=0, poses=None):
+    def __init__(self, device, tiny=False, n_unc=135000, n_tri=2500, img=512, seed_rank=0, poses=None, diffusion=True):
         import sys
         pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'dreamwaltz-g_b200')
         if pkg not in sys.path:
@@ -156,7 +156,8 @@ class RefGpuScene:
         self.av = {k: ({kk: to(vv) for kk, vv in v.items()} if isinstance(v, dict) else to(v)) for k, v in av.items()}
         self.cfg, self.vcfg = (W.TINY, W.TINY_VAE) if tiny else (W.SD15, W.VAE15)
         cu = lambda sd: {k: v.to(device) for k, v in sd.items()}
-        self.unet, self.cn, self.vae = cu(W.make_unet(self.cfg)), cu(W.make_controlnet(self.cfg)), cu(W.make_vae_encoder(self.vcfg))
+        if diffusion:
+            self.unet, self.cn, self.vae = cu(W.make_unet(self.cfg)), cu(W.make_controlnet(self.cfg)), cu(W.make_vae_encoder(self.vcfg))
         offsets, pls, S, _, _ = ogrid.level_table()
         self.offsets = torch.from_numpy(offsets).to(device)
         self.S = float(np.log2(pls))
@@ -206,6 +207,34 @@ class RefGpuScene:
             grad, _ = od.sds_gradient(self.unet, self.cn, self.cfg, ln, noise, t, self.emb['neg'], self.emb['text'], self.cond, 50.0)
         (lat * grad).sum().backward()                            # SpecifyGradient (basic.py:213-226) == this inner product
         return grad
+
+
+def _render_frame(self):
+    """One inference frame the way Trainer.evaluate produces it (trainer.py:1019-1112): no_grad render with a white
+    background composite (scene.py:153-156), then per output tensor2image (utils/image.py:52-61): .cpu().numpy(), * 255, clip, uint8."""
+    from dwg import camera, synth
+    from . import avatar as oav
+    dev = self.dev
+    row = self.rows[self.i % len(self.rows)]
+    self.i += 1
+    obs = {k: v.to(dev) for k, v in synth.pose_from_row(row).items()}
+    if not hasattr(self, '_cam'):
+        data = camera.random_camera(self.rng, self.img, self.img)
+        view, proj, campos, tfx, tfy = camera.raster_matrices(data)
+        self._cam = make_camera(self.img, self.img, tfx, tfy, view.numpy(), proj.numpy())
+    with torch.no_grad():
+        enc = lambda x: RefGridEncode.apply(((x + 2.0) / 4.0), self.table, self.offsets, self.S, 16, 1, False, 1, self.ge)
+        with torch.device(dev):
+            gs = oav.animate(self.model, self.av, self.nets, enc, {}, obs)
+        color, radii, depth, alpha = SimtRasterize.apply(gs['positions'], gs['colors'], gs['opacities'], gs['scales'], gs['quaternions'], self._cam)
+        image_fg = color.permute(1, 2, 0).unsqueeze(0)
+        a = alpha.permute(1, 2, 0).unsqueeze(0)
+        image = image_fg + torch.ones_like(image_fg) * (1 - a)
+        outs = {'image': image, 'image_fg': torch.cat([image_fg, a], dim=3), 'depth': depth.permute(1, 2, 0).unsqueeze(0) / 3.0, 'alpha': a}
+        return {k: (v[0].detach().cpu().numpy() * 255.0).clip(0.0, 255.0).astype(np.uint8) for k, v in outs.items()}
+
+
+RefGpuScene.render_frame = _render_frame
 
 
 def time_steps(scene, steps, warmup):

@@ -188,3 +188,25 @@ def test_group_norm_one_launch_cluster_path_vs_torch(N, H, W, C):
     st_ref = torch.stack([xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))], dim=-1)          # [N, 32, 2]
     assert st.dtype == torch.int64                                                         # 2^-20 fixed point (include/dwg.h)
     torch.testing.assert_close(st.view(N, 32, 2).double().cpu() / 2.0 ** 20, st_ref.cpu(), rtol=2e-5, atol=1e-2)
+
+
+def test_sd21_style_unet_controlnet_match_oracle():
+    """cfg4 (SD2.1): per-level head counts (attention_head_dim = (5, 10, 20, 20) -> head width 64), OpenCLIP-width context,
+    use_linear_projection (nn.Linear proj_in / proj_out) on a reduced-width model with the same topology."""
+    from oracle import diffusion as od
+    cfg = W.TINY21
+    u_sd, c_sd = W.make_unet(cfg), W.make_controlnet(cfg)
+    assert u_sd['down_blocks.0.attentions.0.proj_in.weight'].dim() == 2
+    torch.manual_seed(11)
+    x = torch.randn(2, 4, 16, 16)
+    t = torch.tensor([333])
+    ctx = torch.randn(2, 77, cfg['ctx_dim'])
+    cond = torch.rand(2, 3, 128, 128)
+    with torch.no_grad():
+        down_r, mid_r = od.controlnet_forward(c_sd, cfg, x, t, ctx, cond)
+        eps_r = od.unet_forward(u_sd, cfg, x, t, ctx, down_r, mid_r)
+    cn, un = M.ControlNet(c_sd, cfg, DEV), M.UNet(u_sd, cfg, DEV)
+    down, mid = cn.forward(x.to(DEV), t.to(DEV), ctx.to(DEV), cond.to(DEV))
+    assert rel_l2(mid.permute(0, 3, 1, 2), mid_r) < 5e-3
+    eps = un.forward(x.to(DEV), t.to(DEV), ctx.to(DEV), down, mid)
+    assert rel_l2(eps, eps_r) < 5e-3, rel_l2(eps, eps_r)

@@ -452,3 +452,118 @@ def test_raster_full_benchmark_size_bit_exact_and_psnr():
         gg = gotg.cpu().numpy().reshape(refg.shape)
         err = np.abs(gg - refg).max() / (np.abs(refg).max() + 1e-20)
         assert err < 2e-4, (name, float(err))
+
+
+def test_animate_with_face_part_expression_and_learnable_betas(golden):
+    """cfg4 (scripts/train_w_expr.sh: predefined_body_parts=hands,face, expression in the pose sampler) plus the
+    learn_hand_betas / learn_face_betas branch of animate (avatar.py:1551-1562): two mesh-bound parts, a non-zero
+    expression vector, and a shape offset that only the face part sees."""
+    from dwg import avatar as dav
+    from oracle import avatar as oav, grid as ogrid
+    model = synth.make_body_model(0)
+    av = synth.make_avatar(model, 2000, 200, seed=4, n_face_triangles=150)
+    assert set(av['meshes']) == {'hands', 'face'}
+    obs = synth.pose_from_row(golden('poses')['rows'][2])
+    g = torch.Generator().manual_seed(8)
+    obs['expression'] = torch.randn(1, 100, generator=g) * 0.5
+    m = dav.DreamWaltzGAvatar(model, av, device=DEV, learn_face_betas=True)
+    assert m._betas.requires_grad and list(m.mesh_binding_gaussians) == ['hands', 'face']
+    with torch.no_grad():
+        m.nerf_encoder.embeddings.uniform_(-0.5, 0.5)
+        m._betas.copy_(torch.randn(m._betas.shape, generator=g) * 0.3)
+        for p in list(m.nerf_opacity_and_color_net.parameters()) + list(m.nerf_scale_and_quaternion_net.parameters()):
+            p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+    out = m.animate({k: v.to(DEV) for k, v in obs.items()})
+    n_face = av['meshes']['face']['_scales'].shape[0]
+    assert out.positions.shape[0] == 2000 + av['meshes']['hands']['_scales'].shape[0] + n_face
+    table = m.nerf_encoder.embeddings.detach().cpu().numpy()
+    offsets, _, _, scale, res = ogrid.level_table()
+    enc_fn = lambda x: torch.from_numpy(ogrid.forward(x.detach().numpy(), table, offsets, scale, res, bound=2.0, want_dy_dx=False)[0])
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    nets = {'sigma_w': [sd[f'nerf_opacity_and_color_net.net.{i}.weight'] for i in range(3)],
+            'sigma_b': [sd[f'nerf_opacity_and_color_net.net.{i}.bias'] for i in range(3)],
+            'deform': {k[len('nerf_scale_and_quaternion_net.'):]: v for k, v in sd.items() if k.startswith('nerf_scale_and_quaternion_net.')}}
+    av_o = dict(av, _betas=sd['_betas'], learn_betas_parts=('face',))
+    ref = oav.animate(model, av_o, nets, enc_fn, {}, obs)
+    av_nob = dict(av, _betas=None)
+    ref_nob = oav.animate(model, av_nob, nets, enc_fn, {}, obs)
+    assert float((ref['positions'][-n_face:] - ref_nob['positions'][-n_face:]).abs().max()) > 1e-3       # the betas DO move the face part
+    torch.testing.assert_close(ref['positions'][:-n_face], ref_nob['positions'][:-n_face])                 # ... and only it
+    torch.testing.assert_close(out.positions.detach().cpu(), ref['positions'], rtol=1e-3, atol=3e-5)
+    torch.testing.assert_close(out.colors.detach().cpu(), ref['colors'], rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(out.scales.detach().cpu(), ref['scales'], rtol=1e-3, atol=2e-6)
+    # the shape offset receives a gradient through the face part
+    out.positions[-n_face:].sum().backward()
+    assert m._betas.grad is not None and float(m._betas.grad.abs().sum()) > 0
+
+
+def test_glbs_joint_and_vertex_kernels_match_the_module(golden):
+    """R1 as kernels: dwg_glbs_joints / dwg_glbs_vertices against GeneralLinearBlendSkinning.forward (itself pinned to the
+    reference's outputs by lbs_small.npz): joint transforms with and without transl, pose feature, and the composite vertex
+    transform applied at predefined vertices -- with a non-zero expression and an extra shape offset."""
+    from dwg import avatar as dav, lbs as dlbs
+    model = synth.make_body_model(0)
+    m = dlbs.GeneralLinearBlendSkinning(model, device=DEV)
+    g = torch.Generator().manual_seed(21)
+    obs = {k: v.to(DEV) for k, v in synth.pose_from_row(golden('poses')['rows'][6]).items()}
+    obs['expression'] = (torch.randn(1, 100, generator=g) * 0.4).to(DEV)
+    obs['transl'] = torch.tensor([[0.03, -0.02, 0.05]], device=DEV)
+    extra = (torch.randn(1, 300, generator=g) * 0.2).to(DEV)
+    t_J, t_V, tr = m.forward(**obs, extra_betas=extra)
+    jt = m.joint_transforms(**obs, extra_betas=extra)
+    torch.testing.assert_close(jt['A'], tr['J_pose_rigid'].SE3[0], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(jt['A_t'], dlbs.RigidTransform.compose(tr['J_pose_rigid'], tr['G_transl_offset']).SE3[0], rtol=1e-4, atol=2e-6)
+    av = synth.make_avatar(model, 10, 300, seed=1, n_face_triangles=100)
+    for part in ('hands', 'face'):
+        gm = dav.MeshBindingGaussianModel(av['meshes'][part], device=DEV, lbs_model=m)
+        got = gm.posed_vertex_coords(jt)
+        ref = dlbs.RigidTransform(SE3=t_V.SE3[0]).transform_points(gm._vertex_coords, indices=gm.predefined_vertex_indices)
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=3e-6)
+
+
+def test_mesh_gaussian_kernels_match_torch_forward_and_backward():
+    """R5 as kernels: positions / scales / quaternions of the mesh-bound Gaussians and their gradients w.r.t. the barycentric
+    weights and scale multipliers (forward-mode duals in the kernel) against the torch ops + autograd of the module
+    (pinned to the reference by mesh.npz)."""
+    from dwg import avatar as dav
+    model = synth.make_body_model(0)
+    av = synth.make_avatar(model, 10, 400, seed=2)
+    gm = dav.MeshBindingGaussianModel(av['mesh'], device=DEV)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        gm._bary_coords.copy_((torch.rand(gm._bary_coords.shape, generator=g) + 0.1).to(DEV))
+        gm._scales.copy_((torch.rand(gm._scales.shape, generator=g) * 2.4 + 0.2).to(DEV))          # some outside the [0.5, 2] clamp
+    vc = (gm._vertex_coords + 0.01 * torch.randn(gm._vertex_coords.shape, generator=g).to(DEV)).detach()
+    pos, sc, q = gm.gaussians(vc)
+    pos_r = gm.get_positions(vc)
+    sc_r, q_r = gm.get_scales_and_quaternions(vc, pos_r)
+    torch.testing.assert_close(pos, pos_r, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(sc, sc_r, rtol=2e-4, atol=1e-8)
+    qr_c = q_r.detach()
+    well = (1.0 - 2.0 * (qr_c[:, 2] ** 2 + qr_c[:, 3] ** 2)).abs() < 0.99           # frames built from cross(n, x): skip n ~ +-x
+    torch.testing.assert_close(q[well], q_r[well], rtol=1e-3, atol=2e-5)
+    w_p, w_s, w_q = (torch.randn(t.shape, generator=g).to(DEV) for t in (pos, sc, q))
+    w_q = w_q * well[:, None]
+    params = [gm._bary_coords, gm._scales]
+    got = torch.autograd.grad((pos * w_p).sum() + (sc * w_s).sum() + (q * w_q).sum(), params)
+    ref = torch.autograd.grad((pos_r * w_p).sum() + (sc_r * w_s).sum() + (q_r * w_q).sum(), params)
+    for a, b in zip(got, ref):
+        err = float((a - b).norm() / (b.norm() + 1e-30))
+        assert err < 2e-3, err
+    assert float(got[1][:, 0].abs().max()) == 0.0                                     # scale column 0 is unused
+
+
+def test_animate_kernel_path_equals_torch_path(golden):
+    from dwg import avatar as dav
+    model = synth.make_body_model(0)
+    av = synth.make_avatar(model, 1500, 150, seed=6, n_face_triangles=80)
+    m = dav.DreamWaltzGAvatar(model, av, device=DEV)
+    with torch.no_grad():
+        m.nerf_encoder.embeddings.uniform_(-0.5, 0.5)
+    obs = {k: v.to(DEV) for k, v in synth.pose_from_row(golden('poses')['rows'][1]).items()}
+    obs['transl'] = torch.tensor([[0.01, 0.0, -0.02]], device=DEV)
+    a = m.animate(obs)
+    m.use_kernels = False
+    b = m.animate(obs)
+    for k in ('positions', 'opacities', 'colors', 'scales'):
+        torch.testing.assert_close(getattr(a, k), getattr(b, k), rtol=1e-3, atol=3e-5, msg=lambda s, k=k: f'{k}: {s}')
