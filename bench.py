@@ -117,7 +117,7 @@ class Workload:
     nothing of the step lives in this file any more): avatar, renderer, guidance, per-step inputs."""
 
     def __init__(self, device, rank, n_unc=N_UNCONSTRAINED, n_tri=N_MESH_TRI, img=IMG, tiny=False, allreduce=False, n_face=0, sd='SD15',
-                 sd_size=None):
+                 sd_size=None, produce_cond=True):
         from dwg import avatar as dav, step as dstep, synth
         from dwg.diffusion import guidance as G, weights as W
         self.dev, self.rank, self.img = device, rank, img
@@ -147,7 +147,15 @@ class Workload:
         self.h_cond = cond.pin_memory()
         self.d_embeds = {k: v.to(device) for k, v in self.h_embeds.items()}
         self.d_cond = self.h_cond.to(device)
-        self.trainer = dstep.SDSTrainStep(self.scene, self.guidance, self.d_embeds, allreduce=allreduce)
+        # (f1) the ControlNet condition image is produced ON THE DEVICE every step from the posed body's keypoints and the view's own
+        # depth / alpha (the reference does this on the CPU per view: Embree + cv2 + PIL); --cond-from-host feeds a fixed image instead
+        prod = ks = None
+        if produce_cond:
+            from dwg import condition
+            prod = condition.PoseConditionProducer(sd_size, sd_size, device=device)
+            ks = condition.synthetic_keypoint_source(self.avatar.lbs_model, model)
+        self.produce_cond = produce_cond
+        self.trainer = dstep.SDSTrainStep(self.scene, self.guidance, self.d_embeds, allreduce=allreduce, cond_producer=prod, keypoint_source=ks)
         self.params = self.trainer.params
 
     def next_view(self, device_inputs=True):
@@ -254,7 +262,8 @@ def run_dwg(args):
     if args.config == 'cfg5':
         return run_reenact(args, dev, rank, world, C)
     sc = Workload(dev, rank, tiny=args.tiny, n_unc=args.n_unconstrained or C['n_unc'], img=args.image or C['img'], allreduce=world > 1,
-                  n_face=C['n_face'], sd=C['sd'], sd_size=(args.image or C['sd_size']) if args.config == 'cfg2' else C['sd_size'])
+                  n_face=C['n_face'], sd=C['sd'], sd_size=(args.image or C['sd_size']) if args.config == 'cfg2' else C['sd_size'],
+                  produce_cond=not args.cond_from_host)
     args.image = args.image or C['img']
     tr = sc.trainer
     graphed = False
@@ -386,7 +395,7 @@ def run_dwg(args):
         return
     value = world * 1000.0 / ms_step
     e2e_v = world * 1000.0 / ms_e2e
-    h2d = sc.h_cond.numel() * 4 + sum(v.numel() * 4 for v in sc.h_embeds.values()) + 265 * 4
+    h2d = (0 if sc.produce_cond else sc.h_cond.numel() * 4) + sum(v.numel() * 4 for v in sc.h_embeds.values()) + (265 + 40) * 4
     out = {
         'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)' + ('' if world == 1 else ' -- single-view SDS steps (views) per second of the whole job'),
         'value': round(value, 3), 'unit': 'steps/s' if world == 1 else 'views/s', 'n_gpus': world,
@@ -397,7 +406,9 @@ def run_dwg(args):
                    'gaussians': int(sc.avatar._positions.shape[0] + sum(m._scales.shape[0] for m in sc.avatar.mesh_binding_gaussians.values())),
                    'image': args.image, 'views_per_step': world, 'parallelism': f'view-dp{world} + 1 NCCL all-reduce' if world > 1 else 'single GPU',
                    'cache': 'inputs larger than L2 (2.6 GB of fp16 weights streamed every step; 126 MB L2)',
-                   'cuda_graphs': ('whole step' if graphed else ('sub-graphs' if not args.no_graphs else False))},
+                   'cuda_graphs': ('whole step' if graphed else ('sub-graphs' if not args.no_graphs else False)),
+                   'condition_image': 'produced on the device every step (keypoints -> projection -> depth-tested -> OpenPose image)' if sc.produce_cond
+                   else 'fixed image copied from pinned host memory'},
         'e2e': {'value': round(e2e_v, 3), 'unit': 'steps/s', 'ms_per_step': round(ms_e2e, 3), 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 12},
         'gpu_launches': int(round(launches)), 'host_enqueue_ms_per_step': round(cpu_enqueue_ms, 3),
         'host_ms_parts_per_step': {k: round(v / max(1, 2 * args.steps + args.warmup + min(2, args.warmup)), 3) for k, v in host_parts.items()}, 'clocks': clocks, 'roofline': roof,
@@ -632,6 +643,7 @@ def main():
     ap.add_argument('--no-step-graph', action='store_true', help='capture only the diffusion sub-graphs')
     ap.add_argument('--profile', action='store_true', help='print a CUPTI kernel table of 3 steps to stderr')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--cond-from-host', action='store_true', help='feed a fixed condition image from host memory instead of producing it on the device')
     ap.add_argument('--skip-ref-gpu', action='store_true', help='do not time the reference-equivalent GPU arm after the dwg arm')
     ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS), help='BASELINE.json configuration (cfg2 = the benchmark)')
     ap.add_argument('--n-unconstrained', type=int, default=0, help='override the number of unconstrained Gaussians')

@@ -35,7 +35,8 @@ struct JointArgs {
     float* A_t;                    // [55,16]  transl o A  (joint transforms used for the Gaussians)
     float* pose_feature;           // [486]
     float* shape_out;              // [nb+ne]  assembled shape vector (consumed by the vertex kernel)
-    float* joints;                 // [55,3]   (debug / parity)
+    float* joints;                 // [55,3]   rest joints (debug / parity)
+    float* posed_joints;           // [55,3]   posed joints incl. transl (smplx posed_joints; keypoint source of the condition producer)
 };
 
 __global__ void __launch_bounds__(256) glbs_joints_kernel(const JointArgs a) {
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) glbs_joints_kernel(const JointArgs a) {
         }
     }
     __syncthreads();
+    if (t < NP) a.posed_joints[t] = s_chain[t / 3][4 * (t % 3) + 3] + (a.transl ? a.transl[t % 3] : 0.f);
     for (int i = t; i < NJ * 16; i += blockDim.x) {              // A_j = [R_chain | t_chain - R_chain J_j]
         const int j = i / 16, r = (i % 16) / 4, c = i % 4;
         float v;
@@ -326,16 +328,16 @@ extern "C" int dwg_glbs_joints(const float* global_orient, const float* body_pos
                                const float* reye_pose, const float* left_hand_pose, const float* right_hand_pose, const float* pose_mean,
                                const float* betas, int n_betas, const float* expression, int n_expr,
                                const float* J_template, const float* JS, const int32_t* parents, const float* transl,
-                               float* A, float* A_transl, float* pose_feature, float* shape_out, float* joints, void* stream) {
+                               float* A, float* A_transl, float* pose_feature, float* shape_out, float* joints, float* posed_joints, void* stream) {
     DWG_REQUIRE(global_orient && body_pose && jaw_pose && leye_pose && reye_pose && left_hand_pose && right_hand_pose && pose_mean && betas &&
-                expression && J_template && JS && parents && A && A_transl && pose_feature && shape_out && joints, "null pointer");
+                expression && J_template && JS && parents && A && A_transl && pose_feature && shape_out && joints && posed_joints, "null pointer");
     DWG_REQUIRE(n_betas > 0 && n_expr >= 0 && n_betas + n_expr <= NS, "at most 400 shape components");
     JointArgs a;
     a.pose_part[0] = global_orient; a.pose_part[1] = body_pose; a.pose_part[2] = jaw_pose; a.pose_part[3] = leye_pose;
     a.pose_part[4] = reye_pose; a.pose_part[5] = left_hand_pose; a.pose_part[6] = right_hand_pose;
     a.pose_mean = pose_mean; a.betas = betas; a.expression = expression; a.nb = n_betas; a.ne = n_expr;
     a.J_template = J_template; a.JS = JS; a.parents = parents; a.transl = transl;
-    a.A = A; a.A_t = A_transl; a.pose_feature = pose_feature; a.shape_out = shape_out; a.joints = joints;
+    a.A = A; a.A_t = A_transl; a.pose_feature = pose_feature; a.shape_out = shape_out; a.joints = joints; a.posed_joints = posed_joints;
     glbs_joints_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("dwg_glbs_joints");
 }

@@ -78,10 +78,13 @@ SIGNATURES = {
     'dwg_sds_grad': (c_int, [c_void_p] * 5 + [c_float, c_float, c_int64, c_void_p]),
     'dwg_attention_fwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_void_p]),
-    'dwg_glbs_joints': (c_int, [c_void_p] * 9 + [c_int, c_void_p, c_int] + [c_void_p] * 10),
+    'dwg_glbs_joints': (c_int, [c_void_p] * 9 + [c_int, c_void_p, c_int] + [c_void_p] * 11),
     'dwg_glbs_vertices': (c_int, [c_int, c_int] + [c_void_p] * 10),
     'dwg_mesh_gaussians_fwd': (c_int, [c_int, c_int, c_int] + [c_void_p] * 11),
     'dwg_mesh_gaussians_bwd': (c_int, [c_int, c_int] + [c_void_p] * 11),
+    'dwg_pose_keypoints_2d': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
+                                      c_float, c_float, c_float, c_void_p, c_void_p]),
+    'dwg_pose_image': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'dwg_adam_step': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'dwg_frame_pack': (c_int, [c_void_p] * 8 + [c_int, c_int, c_float, c_void_p]),
     'dwg_raster_view': (c_void_p, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int]),
@@ -110,7 +113,7 @@ KERNELS_PER_CALL = {
     'dwg_gemm_f16': 1, 'dwg_conv2d_nhwc_f16': 1, 'dwg_groupnorm_fwd': 2, 'dwg_groupnorm_bwd': 2,
     'dwg_layernorm_fwd': 1, 'dwg_softmax_rows': 1, 'dwg_softmax_rows_bwd': 1, 'dwg_geglu': 1,
     'dwg_eltwise_f16': 1, 'dwg_sds_grad': 1, 'dwg_attention_fwd': 1, 'dwg_adam_step': 2, 'dwg_grid_level_table': 1, 'dwg_frame_pack': 1, 'dwg_glbs_joints': 1, 'dwg_glbs_vertices': 1,
-    'dwg_mesh_gaussians_fwd': 2, 'dwg_mesh_gaussians_bwd': 1,
+    'dwg_mesh_gaussians_fwd': 2, 'dwg_mesh_gaussians_bwd': 1, 'dwg_pose_keypoints_2d': 1, 'dwg_pose_image': 1,
 }
 
 

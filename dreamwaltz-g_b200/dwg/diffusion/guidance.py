@@ -247,7 +247,7 @@ class ControlNetScoreDistillation:
         prep = self._prepared
         if prep is not None and timestep is None and not getattr(self, '_g', None):
             # prepare() results are only valid for the inputs they were made from
-            assert prep['embeds'][0] is neg and prep['embeds'][1] is text_embeds_dict['text'] and prep['cond'] is cond_inputs, \
+            assert prep['embeds'][0] is neg and prep['embeds'][1] is text_embeds_dict['text'] and (prep['cond'] is None or prep['cond'] is cond_inputs), \
                 'prepare() was called with other prompt embeddings / condition than this __call__'
             self.timestep = prep['t']                           # drawn by prepare()
         else:

@@ -60,11 +60,11 @@ def glbs_joints(pose_parts, pose_mean, betas, expression, J_template, JS, parent
     betas, expression = f32c(betas).reshape(-1), f32c(expression).reshape(-1)
     nb, ne = betas.numel(), expression.numel()
     e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
-    out = {'A': e(55, 4, 4), 'A_t': e(55, 4, 4), 'pose_feature': e(486), 'shape': e(nb + ne), 'joints': e(55, 3)}
+    out = {'A': e(55, 4, 4), 'A_t': e(55, 4, 4), 'pose_feature': e(486), 'shape': e(nb + ne), 'joints': e(55, 3), 'posed_joints': e(55, 3)}
     tr = None if transl is None else f32c(transl).reshape(-1)
     check(lib().dwg_glbs_joints(*[ptr(t) for t in pp], ptr(pose_mean), ptr(betas), nb, ptr(expression), ne, ptr(J_template), ptr(JS),
                                 ptr(parents_i32), ptr(tr), ptr(out['A']), ptr(out['A_t']), ptr(out['pose_feature']), ptr(out['shape']),
-                                ptr(out['joints']), stream()), 'dwg_glbs_joints')
+                                ptr(out['joints']), ptr(out['posed_joints']), stream()), 'dwg_glbs_joints')
     out['transl'] = tr
     return out
 

@@ -97,12 +97,15 @@ class Scene(torch.nn.Module):
 class SDSTrainStep:
     """trainer.train_forward + the gradient half of the training loop, on dwg objects."""
 
-    def __init__(self, scene, guidance, text_embeds_dict, lambda_guidance=1.0, optimizer=None, allreduce=True, max_step=1):
+    def __init__(self, scene, guidance, text_embeds_dict, lambda_guidance=1.0, optimizer=None, allreduce=True, max_step=1,
+                 cond_producer=None, keypoint_source=None):
         self.scene, self.guidance = scene, guidance
         self.text_embeds_dict = text_embeds_dict
         self.lambda_guidance = lambda_guidance
         self.optimizer = optimizer
         self.allreduce = allreduce
+        # (f1) condition image produced on the device from the posed body's keypoints and the view's own depth / alpha
+        self.cond_producer, self.keypoint_source = cond_producer, keypoint_source
         self.train_step, self.max_step = 0, max_step
         self.params = [p for p in scene.parameters() if p.requires_grad]
         self.bucket = GradBucket(self.params)
@@ -121,8 +124,15 @@ class SDSTrainStep:
 
     # ---- core/trainer.py:933-1017 (stage 'gs'; no text augmentation / sparsity loss in the shipped script)
     def train_forward(self, data, cam_dev=None):
-        self.guidance.prepare(self.text_embeds_dict, data.get('cond_images'))     # head start on the second stream (no-op under sub-graphs)
+        produce = self.cond_producer is not None
+        # head start on the second stream (no-op under sub-graphs); a produced condition depends on the render and is embedded later
+        self.guidance.prepare(self.text_embeds_dict, None if produce else data.get('cond_images'))
         render_outputs = self.render(data, cam_dev=cam_dev)
+        if produce:
+            jt = self.scene.avatar.lbs_model.joint_transforms(**data['smpl_inputs'])
+            cond = self.cond_producer(self.keypoint_source(jt), data, render_outputs, cam_dev=cam_dev)
+            data = dict(data, cond_images=cond)
+            render_outputs['cond_images'] = cond
         sd_inputs = render_outputs['image_chw'].unsqueeze(0)                       # == image.permute(0,3,1,2).contiguous() without the copy
         sd_outputs = self.guidance(inputs=sd_inputs, text_embeds_dict=self.text_embeds_dict, train_step=self.train_step,
                                    max_iteration=self.max_step, cond_inputs=data.get('cond_images'), **(self.fixed_draws or {}))

@@ -282,7 +282,8 @@ int dwg_attention_fwd(const void* q, int64_t q_ld, const void* k, int64_t k_ld, 
  *   betas [n_betas] (extra_betas already added), expression [n_expr]; J_template [55,3]; JS [165, n_betas+n_expr] =
  *   J_regressor . shapedirs (constant, pre-multiplied by the caller); parents i32 [55]; transl [3] or NULL ->
  *   A [55,4,4] relative rigid joint transforms (tr['J_pose_rigid']), A_transl = transl o A (the joint transform the Gaussians are
- *   skinned with, avatar.py:1446-1460), pose_feature [486], shape_out [n_betas+n_expr], joints [55,3].
+ *   skinned with, avatar.py:1446-1460), pose_feature [486], shape_out [n_betas+n_expr], joints [55,3] (rest), posed_joints [55,3]
+ *   (smplx posed joints + transl: keypoint source of the condition producer).
  * dwg_glbs_vertices (one warp per vertex): the composite V_shape_offset o V_pose_offset o V_pose_rigid [o transl] applied to
  *   points [Vp,3] of Vp PREDEFINED vertices only; shapedirs_sel [Vp,3,n_shape], posedirs_sel [Vp,3,486], weights_sel [Vp,55]
  *   are the per-vertex slices of the model tensors gathered once by the caller. */
@@ -290,7 +291,7 @@ int dwg_glbs_joints(const float* global_orient, const float* body_pose, const fl
                     const float* reye_pose, const float* left_hand_pose, const float* right_hand_pose, const float* pose_mean,
                     const float* betas, int n_betas, const float* expression, int n_expr,
                     const float* J_template, const float* JS, const int32_t* parents, const float* transl,
-                    float* A, float* A_transl, float* pose_feature, float* shape_out, float* joints, void* stream);
+                    float* A, float* A_transl, float* pose_feature, float* shape_out, float* joints, float* posed_joints, void* stream);
 int dwg_glbs_vertices(int Vp, int n_shape, const float* shape, const float* pose_feature, const float* A, const float* transl,
                       const float* shapedirs_sel, const float* posedirs_sel, const float* weights_sel, const float* points,
                       float* out, void* stream);
@@ -307,6 +308,23 @@ int dwg_mesh_gaussians_fwd(int Vp, int F, int n_per_tri, const float* vertex_coo
 int dwg_mesh_gaussians_bwd(int F, int n_per_tri, const float* vertex_coords, const float* vertex_normals, const int32_t* triangles,
                            const float* bary, const float* scales_param, const float* g_positions, const float* g_scales,
                            const float* g_quaternions, float* g_bary, float* g_scales_param, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (f1) ControlNet condition producer.  Replaces the per-view CPU stage of the reference (core/human/smpl_condition.py:
+ * 191-235 export_pose: numpy projection + Embree occlusion culling (utils/open3d.py:8-45) + cv2 drawing
+ * (core/human/open_pose.py:282-333) + PIL -> tensor (core/guidance/controlnet.py:33-55)).
+ * dwg_pose_keypoints_2d: kp_world [K,3] (K = 128: body 18, hands 21 + 21, face 51 + 17, smpl_condition.py:22);
+ *   extrinsic_dev = DEVICE world->camera 4x4 (row-major); fx, fy, cx, cy = intrinsics at the condition size
+ *   (data/camera/utils.py:116-147,233-242; fy < 0), overridden by intrinsics_dev = DEVICE (fx, fy, cx, cy) when not NULL (a captured
+ *   CUDA graph is replayed with a new camera); depth / alpha [Hd,Wd] = the rasteriser's outputs of the same view or
+ *   NULL (no occlusion culling) -> kp2d [K,2] pixels, NaN = behind the camera or occluded.
+ * dwg_pose_image: kp2d [128,2] -> out [3,H,W] in [0,1] (RGB planes); flags: 1 body, 2 hands, 4 face, 8 flip_LR;
+ *   hand_edge_colors_dev u8 [20,3] = rint(hsv_to_rgb(e / 20, 1, 1) * 255) (open_pose.py:211). */
+int dwg_pose_keypoints_2d(const float* kp_world, int K, const float* extrinsic_dev, const float* intrinsics_dev,
+                          float fx, float fy, float cx, float cy,
+                          const float* depth, const float* alpha, int Hd, int Wd, float cond_w, float cond_h,
+                          float thres_body, float thres_face, float thres_hand, float* kp2d, void* stream);
+int dwg_pose_image(const float* kp2d, int H, int W, int flags, const uint8_t* hand_edge_colors_dev, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (f2) Fused multi-tensor Adam.  Replaces the torch.optim.Adam instances the reference steps every iteration

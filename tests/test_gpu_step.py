@@ -140,3 +140,37 @@ def test_guidance_resizes_non_default_renders_bilinearly():
     out2['diffusion_loss'].backward()
     ref = torch.autograd.grad(torch.nn.functional.interpolate(big, (128, 128), mode='bilinear', align_corners=False), big, small.grad)[0]
     torch.testing.assert_close(big.grad, ref, rtol=1e-5, atol=1e-7)
+
+
+def test_train_step_with_device_side_condition_producer():
+    """(f1) in the step: the condition image is produced on the device from the posed body's keypoints and the view's own
+    depth / alpha, eager and under the whole-step graph (device-resident camera), and equals the producer run by hand."""
+    from dwg import condition
+    cfg, vcfg = W.TINY, W.TINY_VAE
+    gd = G.ControlNetScoreDistillation(W.make_unet(cfg), W.make_controlnet(cfg), W.make_vae_encoder(vcfg), cfg, vcfg, DEV,
+                                       guidance_scale=50.0, default_image_size=128)
+    sc = _small_scene()
+    model = synth.make_body_model(0)
+    ks = condition.synthetic_keypoint_source(sc.avatar.lbs_model, model)
+    prod = condition.PoseConditionProducer(128, 128, device=DEV)
+    g = torch.Generator().manual_seed(4)
+    emb = {'neg': torch.randn(1, 77, cfg['ctx_dim'], generator=g).to(DEV), 'text': torch.randn(1, 77, cfg['ctx_dim'], generator=g).to(DEV)}
+    tr = dstep.SDSTrainStep(sc, gd, emb, allreduce=False, cond_producer=prod, keypoint_source=ks)
+    tr.fixed_draws = {'timestep': torch.tensor([400], device=DEV), 'noise': torch.randn(1, 4, 16, 16, generator=g).to(DEV),
+                      'vae_eps': torch.randn(1, 4, 16, 16, generator=g).to(DEV)}
+    d0, d1 = _data(seed=1, row=1), _data(seed=2, row=4)
+    d0['cond_images'] = d1['cond_images'] = torch.zeros(1, 3, 128, 128, device=DEV)      # placeholder: replaced by the produced image
+    loss, ro, so, _ = tr.step(d1)
+    cond_eager, sds_eager = ro['cond_images'].clone(), so['gradients'].clone()
+    assert cond_eager.shape == (1, 3, 128, 128) and float(cond_eager.sum()) > 0           # a skeleton was drawn
+    jt = sc.avatar.lbs_model.joint_transforms(**d1['smpl_inputs'])
+    by_hand = prod(ks(jt), d1, {'depth': ro['depth'], 'alpha': ro['alpha']})
+    assert torch.equal(by_hand, cond_eager)
+    kp = ks(jt)
+    assert kp.shape == (128, 3) and torch.isfinite(kp).all()
+    del loss, ro, so
+    tr.capture(d0)
+    loss, ro, so, _ = tr.step(d1)
+    torch.cuda.synchronize()
+    assert (ro['cond_images'] != cond_eager).float().mean() < 1e-3                       # device-side fov arithmetic: boundary pixels at most
+    assert rel(so['gradients'], sds_eager) < 2e-2
