@@ -355,8 +355,8 @@ def run_dwg(args):
         ops.PROFILE = []
         ops.PROFILE_BYTES = 0.0
         img = torch.rand(1, 3, sc.guidance.default_image_size, sc.guidance.default_image_size, device=dev, requires_grad=True)
-        for _ in range(5):
-            torch.cuda._sleep(int(4e8))          # ~1 s head start: the CPU enqueues the whole un-graphed pass while the GPU is parked
+        for _ in range(15):
+            torch.cuda._sleep(int(4e8))          # ~3 s head start: the CPU enqueues the whole un-graphed pass while the GPU is parked
         res = g(img, sc.d_embeds, cond_inputs=sc.d_cond)
         res['diffusion_loss'].backward()
         torch.cuda.synchronize()

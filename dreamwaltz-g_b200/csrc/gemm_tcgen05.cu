@@ -874,6 +874,7 @@ static int stages_for(int BN, int pair, int epi, int has_res) {
     int stages = (int)((kSmemBudget - smem_fixed(epi, has_res)) / (A_BYTES + (size_t)(pair ? BN / 2 : BN) * 128));
     return stages > kMaxStages ? kMaxStages : stages;
 }
+static int g_counter_cap = 0;              // counters available to the launch being planned (set by the entry point from its workspace)
 static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats);
 static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_res, int64_t ws_cap_floats) {
     Plan pl = plan_tiles_auto(m_tiles, nz, N, iters, epi, has_res, ws_cap_floats);
@@ -884,7 +885,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
                 const int64_t tiles = (int64_t)m_tiles * ((N + t->BN - 1) / t->BN) * nz;
                 const int pair = (t->pair && pair_legal(m_tiles, t->BN)) ? 1 : 0;
                 const int stages = stages_for(t->BN, pair, epi, has_res);
-                if (stages >= 2 && (t->ks == 1 || (tiles <= kMaxCounters / kLanes && tiles * t->ks * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters)))
+                if (stages >= 2 && (t->ks == 1 || (tiles <= g_counter_cap && tiles * t->ks * 128 * (int64_t)t->BN <= ws_cap_floats && t->ks <= iters)))
                     pl = {t->BN, t->ks, stages, pair, t->halo && t->ks == 1};
                 break;
             }
@@ -898,7 +899,7 @@ static Plan plan_tiles(int m_tiles, int nz, int N, int iters, int epi, int has_r
         if (epi == EPI_GEGLU) ks = 1;
         if (ks > iters) ks = iters;
         const int64_t tiles = (int64_t)m_tiles * ((N + BN - 1) / BN) * nz;
-        if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * ks * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
+        if (ks > 1 && (tiles > g_counter_cap || tiles * ks * 128 * (int64_t)BN > ws_cap_floats)) ks = 1;
         pl = {BN, ks, stages_for(BN, 0, epi, has_res), 0, 0};
     }
     if (g_force_pair >= 0) {
@@ -922,7 +923,7 @@ static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int 
         const int64_t tiles = (int64_t)m_tiles * n_tiles * nz;
         for (int ks = 1; ks <= 32; ks++) {
             if (ks > 1 && (epi == EPI_GEGLU || iters / ks < 2 || tiles * ks > 2 * g_num_sms)) break;
-            if (ks > 1 && (tiles > kMaxCounters / kLanes || tiles * ks * 128 * (int64_t)BN > ws_cap_floats)) break;
+            if (ks > 1 && (tiles > g_counter_cap || tiles * ks * 128 * (int64_t)BN > ws_cap_floats)) break;
             const int64_t ctas = tiles * ks;
             const double active = (double)(ctas < g_num_sms ? ctas : g_num_sms);
             const double feed = (double)stage_bytes * active / 6000.0;          // ~6.3 KB/cycle chip-wide TMA throughput
@@ -971,13 +972,17 @@ static cudaError_t launch_one(dim3 grid, size_t smem, cudaStream_t st, const CUt
     return cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, PAIR>, tmA, tmB, tmC, tmR, p);
 }
 
-static int ensure_globals() {
+static int ensure_sms() {
     if (!g_num_sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms <= 0) g_num_sms = kNumSMs;
     }
+    return DWG_OK;
+}
+static int ensure_globals() {
+    ensure_sms();
     if (!g_counters) {
         // NOTE: allocated outside of stream capture (the first, un-captured warm-up call creates it)
         if (cudaMalloc(&g_counters, sizeof(int) * kMaxCounters) != cudaSuccess) { g_counters = nullptr; set_error("split-K counter allocation failed"); return DWG_ERR_CUDA; }
@@ -1022,13 +1027,33 @@ using namespace dwg::gemm;
 
 // D[b2][b1][M,N] = act(alpha * A[b2][b1][M,K] @ B[b2][b1][N,K]^T + bias[N] + bias2) + residual
 // All strides in ELEMENTS.  A/B bf16, K contiguous.  out_f16: 1 -> bf16 C, 0 -> fp32 C.
-extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
+// Split-K scratch of one launch: counters (zero when idle, self-resetting) + fp32 partial-tile slices.
+struct Scratch { float* data; int64_t floats; int* counters; int n_counters; };
+constexpr int64_t kWsCounterBytes = 128 << 10;            // 32768 counters at the head of a caller-provided workspace
+static int scratch_from_caller(void* ws, int64_t bytes, Scratch& s) {
+    if (!ws || bytes < kWsCounterBytes + (1 << 20) || (reinterpret_cast<uintptr_t>(ws) & 255)) {
+        set_error("workspace must be 256-byte aligned and hold at least dwg_gemm_workspace_bytes() bytes");
+        return DWG_ERR_CAPACITY;
+    }
+    s.counters = reinterpret_cast<int*>(ws); s.n_counters = (int)(kWsCounterBytes / 4);
+    s.data = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsCounterBytes); s.floats = (bytes - kWsCounterBytes) / 4;
+    return DWG_OK;
+}
+static int scratch_from_library(Scratch& s) {
+    int rc = ensure_globals();
+    if (rc) return rc;
+    s.data = g_ws + (size_t)g_lane * (g_ws_bytes / 4 / kLanes); s.floats = (int64_t)(g_ws_bytes / 4 / kLanes);
+    s.counters = g_counters + g_lane * (kMaxCounters / kLanes); s.n_counters = kMaxCounters / kLanes;
+    return DWG_OK;
+}
+
+static int gemm_impl(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                              const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
                              void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16,
                              int M, int N, int K, int nb1, int nb2,
                              const float* bias, const float* bias2, int bias2_rows_per,
                              const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
-                             float alpha, int act, void* stream) {
+                             float alpha, int act, const Scratch& ws, void* stream) {
     DWG_REQUIRE(A && B && C, "null pointer");
     DWG_REQUIRE(M > 0 && N > 0 && K > 0 && nb1 > 0 && nb2 > 0, "bad sizes");
     DWG_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && (a_b1 % 8) == 0 && (a_b2 % 8) == 0 && (b_b1 % 8) == 0 && (b_b2 % 8) == 0,
@@ -1036,8 +1061,9 @@ extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_
     DWG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "A/B must be 16-byte aligned");
     DWG_REQUIRE(act != ACT_GEGLU || (N % 2 == 0 && out_f16 && !residual), "GEGLU epilogue: even N, 16-bit output, no residual");
     DWG_REQUIRE(act != ACT_GEGLU || !bias || ((uintptr_t)bias & 15) == 0, "GEGLU bias must be 16-byte aligned");
-    int rc = ensure_globals();
+    int rc = ensure_sms();
     if (rc) return rc;
+    g_counter_cap = ws.n_counters;
     const int epi = act == ACT_GEGLU ? EPI_GEGLU : (out_f16 ? EPI_F16 : EPI_F32);
     const int64_t esz = out_f16 ? 2 : 4;
     if (nb1 == 1) c_b1 = ldc * (int64_t)M;
@@ -1056,12 +1082,12 @@ extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_
     p.residual = reinterpret_cast<const act_t*>(residual); p.ldr = ldr; p.r_b1 = r_b1; p.r_b2 = r_b2;
     p.alpha = alpha; p.act = act;
     p.m_tiles = (M + BM - 1) / BM; p.nz = nb1 * nb2;
-    const Plan pl = plan_tiles(p.m_tiles, p.nz, N, p.k_chunks, epi, p.has_res, (int64_t)(g_ws_bytes / 4 / kLanes));
+    const Plan pl = plan_tiles(p.m_tiles, p.nz, N, p.k_chunks, epi, p.has_res, ws.floats);
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
     p.n_tiles = (N + p.BN - 1) / p.BN;
     p.m_sched = pl.pair ? p.m_tiles / 2 : p.m_tiles;
     p.total_tiles = p.m_sched * p.n_tiles * p.nz * p.ksplit;
-    p.workspace = g_ws + (size_t)g_lane * (g_ws_bytes / 4 / kLanes); p.counters = g_counters + g_lane * (kMaxCounters / kLanes); p.trace = g_trace;
+    p.workspace = ws.data; p.counters = ws.counters; p.trace = g_trace;
 
     CUtensorMap tmA, tmB, tmC, tmR;
     const uint32_t ones[4] = {1, 1, 1, 1};
@@ -1100,18 +1126,19 @@ extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_
 // NHWC convolution as implicit GEMM.  x [Nimg,H,W,Cin] bf16 (Cin % 8 == 0), w [Cout,kh,kw,Cin] bf16,
 // y [Nimg,Ho,Wo,Cout] (bf16 or fp32).  Padding is zero-fill (pad_h/pad_w applied on the top/left;
 // the bottom/right extent follows from Ho/Wo, which covers SD's asymmetric (0,1,0,1) padding).
-extern "C" int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int out_f16,
+static int conv_impl(const void* x, const void* w, void* y, int out_f16,
                                     int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
                                     int pad_h, int pad_w, int Ho, int Wo,
                                     const float* bias, const float* bias2_per_image,
-                                    const void* residual, int act, void* stream) {
+                                    const void* residual, int act, const Scratch& ws, void* stream) {
     DWG_REQUIRE(x && w && y, "null pointer");
     DWG_REQUIRE(Cin % 8 == 0, "Cin must be a multiple of 8 (pad the channels)");
     DWG_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
     DWG_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
     DWG_REQUIRE(act != ACT_GEGLU, "GEGLU is a linear-layer epilogue");
-    int rc = ensure_globals();
+    int rc = ensure_sms();
     if (rc) return rc;
+    g_counter_cap = ws.n_counters;
     // pixel box of one 128-row tile
     int BW = 1;
     while (BW * 2 <= Wo && BW * 2 <= BM) BW *= 2;
@@ -1141,7 +1168,7 @@ extern "C" int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int ou
     p.alpha = 1.0f; p.act = act;
     p.m_tiles = tiles_w * tiles_h * tiles_n; p.nz = 1;
     const int iters = ksize * ksize * p.k_chunks;
-    const Plan pl = plan_tiles(p.m_tiles, 1, Cout, iters, epi, p.has_res, (int64_t)(g_ws_bytes / 4 / kLanes));
+    const Plan pl = plan_tiles(p.m_tiles, 1, Cout, iters, epi, p.has_res, ws.floats);
     p.BN = pl.BN; p.ksplit = pl.ks; p.stages = pl.stages;
     // ---- halo mode: 3x3 / stride 1 / "same" on images that tile into 8 x 16 pixel blocks, no split-K
     p.halo = 0;
@@ -1165,7 +1192,7 @@ extern "C" int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int ou
     p.n_tiles = (Cout + p.BN - 1) / p.BN;
     p.m_sched = pl.pair ? p.m_tiles / 2 : p.m_tiles;
     p.total_tiles = p.m_sched * p.n_tiles * p.ksplit;
-    p.workspace = g_ws + (size_t)g_lane * (g_ws_bytes / 4 / kLanes); p.counters = g_counters + g_lane * (kMaxCounters / kLanes); p.trace = g_trace;
+    p.workspace = ws.data; p.counters = ws.counters; p.trace = g_trace;
 
     CUtensorMap tmA, tmB, tmC, tmR;
     {
@@ -1202,6 +1229,48 @@ extern "C" int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int ou
         }
     }
     return launch(tmA, tmB, tmC, tmR, p, epi, (cudaStream_t)stream);
+}
+
+// ---- public entry points.  The *_ws forms take the split-K scratch from the caller (no library-owned memory, safe for
+// concurrent streams / host threads as long as each uses its own workspace); the plain forms are conveniences over a
+// per-process scratch with two lanes (dwg_gemm_set_lane).
+extern "C" int64_t dwg_gemm_workspace_bytes(void) { return kWsCounterBytes + ((int64_t)32 << 20); }
+
+extern "C" int dwg_gemm_f16_ws(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2, const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
+                               void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16, int M, int N, int K, int nb1, int nb2,
+                               const float* bias, const float* bias2, int bias2_rows_per, const void* residual, int64_t ldr, int64_t r_b1,
+                               int64_t r_b2, float alpha, int act, void* workspace, int64_t workspace_bytes, void* stream) {
+    Scratch s;
+    int rc = scratch_from_caller(workspace, workspace_bytes, s);
+    if (rc) return rc;
+    return gemm_impl(A, lda, a_b1, a_b2, B, ldb, b_b1, b_b2, C, ldc, c_b1, c_b2, out_f16, M, N, K, nb1, nb2, bias, bias2, bias2_rows_per, residual, ldr,
+                     r_b1, r_b2, alpha, act, s, stream);
+}
+extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2, const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
+                            void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16, int M, int N, int K, int nb1, int nb2,
+                            const float* bias, const float* bias2, int bias2_rows_per, const void* residual, int64_t ldr, int64_t r_b1,
+                            int64_t r_b2, float alpha, int act, void* stream) {
+    Scratch s;
+    int rc = scratch_from_library(s);
+    if (rc) return rc;
+    return gemm_impl(A, lda, a_b1, a_b2, B, ldb, b_b1, b_b2, C, ldc, c_b1, c_b2, out_f16, M, N, K, nb1, nb2, bias, bias2, bias2_rows_per, residual, ldr,
+                     r_b1, r_b2, alpha, act, s, stream);
+}
+extern "C" int dwg_conv2d_nhwc_f16_ws(const void* x, const void* w, void* y, int out_f16, int Nimg, int H, int W, int Cin, int Cout, int ksize,
+                                      int stride, int pad_h, int pad_w, int Ho, int Wo, const float* bias, const float* bias2_per_image,
+                                      const void* residual, int act, void* workspace, int64_t workspace_bytes, void* stream) {
+    Scratch s;
+    int rc = scratch_from_caller(workspace, workspace_bytes, s);
+    if (rc) return rc;
+    return conv_impl(x, w, y, out_f16, Nimg, H, W, Cin, Cout, ksize, stride, pad_h, pad_w, Ho, Wo, bias, bias2_per_image, residual, act, s, stream);
+}
+extern "C" int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int out_f16, int Nimg, int H, int W, int Cin, int Cout, int ksize,
+                                   int stride, int pad_h, int pad_w, int Ho, int Wo, const float* bias, const float* bias2_per_image,
+                                   const void* residual, int act, void* stream) {
+    Scratch s;
+    int rc = scratch_from_library(s);
+    if (rc) return rc;
+    return conv_impl(x, w, y, out_f16, Nimg, H, W, Cin, Cout, ksize, stride, pad_h, pad_w, Ho, Wo, bias, bias2_per_image, residual, act, s, stream);
 }
 
 /* Tuning / introspection (tools/gemm_sweep.py): force the tile width and split count of the next

@@ -506,10 +506,27 @@ class _prof:
             PROFILE_BYTES += self.nbytes
 
 
+_GEMM_LANE = 0
+_GEMM_WS = {}
+
+
 def gemm_lane(lane):
-    """Select the split-K scratch lane (0 / 1) of the GEMM / conv launches that follow (include/dwg.h:
-    dwg_gemm_set_lane).  Launches enqueued on a second, possibly concurrent stream must use lane 1."""
-    check(lib().dwg_gemm_set_lane(int(lane)), 'gemm_set_lane')
+    """Select the split-K workspace (lane 0 / 1) of the GEMM / conv launches that follow.  Launches enqueued on a second,
+    possibly concurrent stream must use lane 1.  Host-side state of THIS wrapper: the C ABI receives the workspace as an
+    argument (dwg_gemm_f16_ws / dwg_conv2d_nhwc_f16_ws), the library itself keeps none."""
+    global _GEMM_LANE
+    assert lane in (0, 1)
+    _GEMM_LANE = int(lane)
+
+
+def _gemm_workspace(device):
+    """Caller-owned split-K scratch of (device, lane): allocated and zero-filled once (include/dwg.h)."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _GEMM_LANE)
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        ws = _GEMM_WS[key] = torch.zeros(int(lib().dwg_gemm_workspace_bytes()), device=dev, dtype=torch.uint8)
+    return ws
 
 
 def _chk_f16(t):
@@ -549,13 +566,14 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
         TUNE_RECORD.append(('gemm', M, N, K, nb1, nb2, act, residual is not None, c4.dtype, bias is not None, bias2 is not None))
     nbytes = nb1 * nb2 * (2.0 * (M * K + N * K) + M * No * (c4.element_size() + (2 if r4 is not None else 0)))
     with _prof(2.0 * M * N * K * nb1 * nb2, f'gemm M{M} N{N} K{K} b{nb1 * nb2}', nbytes):
-        check(lib().dwg_gemm_f16(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
+        ws = _gemm_workspace(a.device)
+        check(lib().dwg_gemm_f16_ws(a4.data_ptr(), a4.stride(2), a4.stride(1), a4.stride(0),
                                   b4.data_ptr(), b4.stride(2), b4.stride(1), b4.stride(0),
                                   c4.data_ptr(), c4.stride(2), c4.stride(1), c4.stride(0), int(c4.dtype == torch.float16),
                                   M, N, K, nb1, nb2, ptr(bias), ptr(bias2), int(bias2_rows_per),
                                   None if r4 is None else r4.data_ptr(), 0 if r4 is None else r4.stride(2),
                                   0 if r4 is None else r4.stride(1), 0 if r4 is None else r4.stride(0),
-                                  float(alpha), ACT[act], stream()), 'dwg_gemm_f16')
+                                  float(alpha), ACT[act], ws.data_ptr(), ws.numel(), stream()), 'dwg_gemm_f16_ws')
     return out
 
 
@@ -583,9 +601,10 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
         TUNE_RECORD.append(('conv', Nimg, H, W, Cin, Cout, k, stride, ph, pw, Ho, Wo, residual is not None, out_dtype, bias2 is not None))
     nbytes = 2.0 * (x.numel() + w.numel()) + y.numel() * (y.element_size() + (2 if residual is not None else 0))
     with _prof(2.0 * Nimg * Ho * Wo * Cout * Cin * k * k, f'conv{k}x{k}s{stride} {Nimg}x{Ho}x{Wo} {Cin}->{Cout}', nbytes):
-        check(lib().dwg_conv2d_nhwc_f16(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.float16), Nimg, H, W, Cin, Cout, k,
-                                         stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], stream()),
-              'dwg_conv2d_nhwc_f16')
+        ws = _gemm_workspace(x.device)
+        check(lib().dwg_conv2d_nhwc_f16_ws(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.float16), Nimg, H, W, Cin, Cout, k,
+                                            stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], ws.data_ptr(), ws.numel(),
+                                            stream()), 'dwg_conv2d_nhwc_f16_ws')
     return y
 
 

@@ -3,13 +3,17 @@
  * Conventions (all entry points):
  *   - plain C types only: device pointers, int/int64_t sizes, float scalars; `stream` is a
  *     cudaStream_t passed as void* (NULL = legacy default stream);
- *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or
- *     freed by the library except the opaque handles created by dwg_*_create();
+ *   - the caller owns every buffer (inputs, outputs, workspaces): every entry point on the product path takes its
+ *     scratch from the caller (rasteriser workspaces, dwg_gemm_f16_ws / dwg_conv2d_nhwc_f16_ws + dwg_gemm_workspace_bytes,
+ *     GroupNorm statistics, optimiser state).  The forms WITHOUT the _ws suffix are conveniences that lazily allocate one
+ *     per-process split-K scratch (two lanes, dwg_gemm_set_lane) and are therefore not re-entrant across host threads;
  *   - all tensors are dense row-major fp32 unless stated; "i32"/"u32"/"u64" = integer types;
  *   - return value 0 = success, negative = error (dwg_last_error() gives the message);
  *     kernels are launched asynchronously on `stream`, errors of the launch itself are
  *     reported, execution errors surface at the caller's next synchronisation;
- *   - re-entrant per stream; no global mutable state besides the last-error string.
+ *   - re-entrant per stream; besides the last-error string the only process-global state is (a) the convenience scratch above
+ *     and (b) the tuning / introspection knobs (dwg_gemm_tune*, dwg_gemm_last_*, dwg_groupnorm_set_fused, dwg_nn_set_carveout),
+ *     which are debugging aids of tools/ and never change results.
  *
  * Each function cites the reference interface it replaces (paths into the reference repo).
  */
@@ -163,6 +167,17 @@ void* dwg_raster_view(int which, void* geom, void* bin, void* img, int64_t N, in
  *   A, B bf16 with K contiguous; strides in ELEMENTS and multiples of 8; C bf16 (out_f16=1) or
  *   fp32; residual bf16 with its own strides; act 0 none / 1 SiLU / 2 GELU(erf).
  */
+/* bytes of split-K scratch one workspace must hold (counters + fp32 partial-tile slices).  A workspace must be zero-filled
+ * ONCE by the caller before its first use (the kernels leave the counters zero); launches that may run concurrently
+ * (two streams) need different workspaces. */
+int64_t dwg_gemm_workspace_bytes(void);
+int dwg_gemm_f16_ws(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
+                    const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
+                    void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16,
+                    int M, int N, int K, int nb1, int nb2,
+                    const float* bias, const float* bias2, int bias2_rows_per,
+                    const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
+                    float alpha, int act, void* workspace, int64_t workspace_bytes, void* stream);
 int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                   const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
                   void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16,
@@ -223,6 +238,11 @@ int dwg_gemm_last_key(int* out6);   /* planner key of the last launch: m_tiles, 
  *   ksize 1|3, stride 1|2, zero padding pad_h/pad_w on the top/left (bottom/right implied by
  *   Ho/Wo: covers the VAE's asymmetric (0,1,0,1) padding); bias [Cout], bias2_per_image
  *   [Nimg,Cout] (time embedding), residual [Nimg,Ho,Wo,Cout] bf16. */
+int dwg_conv2d_nhwc_f16_ws(const void* x, const void* w, void* y, int out_f16,
+                           int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
+                           int pad_h, int pad_w, int Ho, int Wo,
+                           const float* bias, const float* bias2_per_image,
+                           const void* residual, int act, void* workspace, int64_t workspace_bytes, void* stream);
 int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int out_f16,
                          int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
                          int pad_h, int pad_w, int Ho, int Wo,
