@@ -96,6 +96,8 @@ struct Params {
     float* workspace;               // split-K fp32 partial-tile slices [tile][split]
     int* counters;                  // one per output tile, self-resetting
     unsigned long long* trace;      // optional [8] per-launch timeline of CTA 0 (globaltimer ns), null = off
+    unsigned long long* colstats;   // optional [groups][N][2] fixed-point (2^-20) per-column sum / sum of squares of the fp16 OUTPUT (GroupNorm statistics)
+    int cs_rows;                    // plain GEMM: rows per statistics group (image); conv: unused (group = image)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -269,6 +271,40 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, int m_m
 
 __device__ __forceinline__ uint32_t pack_act(float a, float b) { return pack_act2(a, b); }
 
+// Column statistics of one finished tile: thread `col` folds the (up to four) 32-row quadrants that belong to the same
+// statistics group and adds the totals as 2^-20 fixed-point integers (order-free => deterministic) to
+// colstats[slot][group][column][2]; slot = m_tile & 3 spreads the same-address atomics of concurrently finishing tiles.
+__device__ __forceinline__ void cs_flush(const Params& p, const float* s_cs, const int* s_csmeta, uint32_t parity, int col) {
+    const int* meta = s_csmeta + parity * 8;
+    if (col < 0 || col >= p.BN || !meta[0]) return;
+    const int n = meta[2] + col;
+    if (n >= p.N) return;
+    const int slot = meta[1];
+    const int64_t groups = p.conv_mode ? p.Nimg : ((int64_t)p.nz * p.M + p.cs_rows - 1) / p.cs_rows;
+    float S = 0.f, Q = 0.f;
+    int cur = -1;
+    for (int q = 0; q < 4; q++) {
+        const int g = meta[4 + q];
+        if (g != cur) {
+            if (cur >= 0) {
+                unsigned long long* dst = p.colstats + (((size_t)slot * groups + cur) * p.N + n) * 2;
+                atomicAdd(dst, (unsigned long long)__float2ll_rn(S * 1048576.0f));
+                atomicAdd(dst + 1, (unsigned long long)__float2ll_rn(Q * 1048576.0f));
+            }
+            cur = g; S = 0.f; Q = 0.f;
+        }
+        if (g >= 0) {
+            const float2 v = *reinterpret_cast<const float2*>(s_cs + ((parity * 4 + q) * 256 + col) * 2);
+            S += v.x; Q += v.y;
+        }
+    }
+    if (cur >= 0) {
+        unsigned long long* dst = p.colstats + (((size_t)slot * groups + cur) * p.N + n) * 2;
+        atomicAdd(dst, (unsigned long long)__float2ll_rn(S * 1048576.0f));
+        atomicAdd(dst + 1, (unsigned long long)__float2ll_rn(Q * 1048576.0f));
+    }
+}
+
 // Persistent, warp-specialised: the CTA walks tiles blockIdx.x, +gridDim.x, ...; the smem ring and
 // the two TMEM accumulator stages let the TMA / MMA of tile i+1 overlap the epilogue of tile i.
 template <int EPI, bool PAIR>
@@ -290,7 +326,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* sStage = sB + p.stages * B_BYTES;                         // [kEpiWarps][2][STG_BYTES]
     uint8_t* sRes = sStage + kEpiWarps * 2 * STG_BYTES;                // [kEpiWarps][2][2048] (only when has_res)
     float* s_bias = reinterpret_cast<float*>(sRes + (p.has_res ? kEpiWarps * 2 * 2048 : 0));      // [tile parity][image 0/1][256]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + 2 * 2 * 256);
+    float* s_cs = s_bias + 2 * 2 * 256;                                // [tile parity][quadrant][256 columns][2]  (only when p.colstats)
+    int* s_csmeta = reinterpret_cast<int*>(s_cs + (p.colstats ? 2 * 4 * 256 * 2 : 0));      // [tile parity][8]: valid, slot, ntile0, -, grp[4]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_csmeta + (p.colstats ? 16 : 0));
     uint64_t* empty = full + kMaxStages;
     uint64_t* tmem_full = empty + kMaxStages;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;              // [2]
@@ -573,6 +611,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 asm volatile("bar.sync 2, %0;" :: "n"(32 * kEpiWarps) : "memory");
             }
+            if (EPI == EPI_F16 && p.colstats) {
+                // flush the column statistics of the PREVIOUS tile (every epilogue warp has passed the barrier above, so they are
+                // complete): thread = column folds the four lane quadrants and issues ONE integer RED per (group, column, moment)
+                if (tl > 0) cs_flush(p, s_cs, s_csmeta, (tl - 1) & 1u, (int)threadIdx.x - 128);
+                // this tile's record (read by the flush behind the NEXT barrier): statistics group of each lane quadrant, slot, first column
+                int* meta = s_csmeta + (tl & 1u) * 8;
+                if (half == 0 && lane == 0) {
+                    const int grp = p.conv_mode ? c3 : ((int)(((int64_t)(c3 * p.nb1 + c2) * p.M + c1) / p.cs_rows));
+                    meta[4 + q] = box_ok ? grp : -1;
+                }
+                if (e == 0 && lane == 0) { meta[0] = (p.ksplit == 1) ? 1 : 0; meta[1] = tc.m_tile & 3; meta[2] = ntile0; }
+            }
             const float* sbr = sb + ((stage_b2 && (r0 + lane) / (p.BW * p.BH) > 0) ? 256 : 0);
             const bool b2_global = p.bias2 && !stage_b2;                           // generic (plain GEMM / many images per tile) path
             // residual chunk of this warp's first chunk: in flight while the MMA main loop runs
@@ -623,6 +673,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int last = *s_flag;
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");      // everyone has read the flag before the next tile rewrites it
                 if (!last) continue;
+                if (EPI == EPI_F16 && p.colstats && e == 0 && lane == 0) s_csmeta[(tl & 1u) * 8] = 1;      // this CTA owns the epilogue of the tile
                 if (use_res && half < nchunks && lane == 0) {
                     const uint32_t b = slot & 1u;
                     mbar_expect_tx(&rbar[b], 2048);
@@ -772,12 +823,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     bulk_commit();
                 }
                 if (tl == 0 && e == 0 && lane == 0 && c == 0) TRACE(12);
+                if (EPI == EPI_F16 && p.colstats) {
+                    // ---- GroupNorm statistics of the consumer, taken from the staged fp16 chunk (exactly the values that reach
+                    // memory): lane = (column pair, row parity) walks 16 rows of the swizzled 32 x 32 staging tile (conflict-free:
+                    // a half-warp reads one 64-byte row), the two row parities meet by one shuffle, and the 32 column totals leave
+                    // as fixed-point integer REDs (order-independent => deterministic) into colstats[image][column][2].
+                    const uint8_t* sbuf = stg + b * STG_BYTES;
+                    const int cp = lane & 15, par = lane >> 4;
+                    const int nrows = p.conv_mode ? 32 : min(32, p.M - c1);
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 4
+                    for (int i = 0; i < 16; i++) {
+                        const int r = 2 * i + par;
+                        if (r < nrows) {
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(sbuf + r * 64 + ((((cp >> 2) ^ ((r >> 1) & 3))) << 4) + ((cp & 3) << 2));
+                            const float2 v = act2_to_f2(*reinterpret_cast<const act2_t*>(&w));
+                            s0 += v.x; s1 += v.y; q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+                        }
+                    }
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+                    if (par == 0) {
+                        // stage (sum, sumsq) of columns 2cp, 2cp+1 of this 32-row quadrant: single writer per (quadrant, column)
+                        float* dst = s_cs + ((((tl & 1u) * 4 + q) * 256) + (c * 32 + 2 * cp)) * 2;
+                        *reinterpret_cast<float4*>(dst) = make_float4(s0, q0, s1, q1);
+                    }
+                }
             }
             if (!released) {                                 // warps with no chunk in this tile (BN == 32, half == 1)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
             }
+        }
+        if (EPI == EPI_F16 && p.colstats && tl > 0) {
+            asm volatile("bar.sync 2, %0;" :: "n"(32 * kEpiWarps) : "memory");
+            cs_flush(p, s_cs, s_csmeta, (tl - 1) & 1u, (int)threadIdx.x - 128);
         }
         if (e == 0 && lane == 0) TRACE(6);
         if (lane == 0) bulk_wait_read<0>();                  // smem must stay valid until the last TMA store has read it
@@ -840,9 +921,11 @@ static int* g_counters = nullptr;        // split-K arrival counters (zero when 
 constexpr int kMaxCounters = 1 << 16;
 constexpr size_t kSmemBudget = 232448 - 1024;       // opt-in maximum minus the 1024-byte alignment slack
 
+static int g_plan_cs = 0;                  // the launch being planned accumulates column statistics (16 KB + 64 B more shared memory)
 static size_t smem_fixed(int epi, int has_res) {
     const size_t stg = (epi == EPI_F32) ? 4096 : 2048;
-    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + 2 * 2 * 256 * 4 + (2 * kMaxStages + 4 + 2 * kEpiWarps + 2 * kMaxAStages) * 8 + 64;
+    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + 2 * 2 * 256 * 4 + (g_plan_cs ? 2 * 4 * 256 * 2 * 4 + 64 : 0) +
+           (2 * kMaxStages + 4 + 2 * kEpiWarps + 2 * kMaxAStages) * 8 + 64;
 }
 
 // Tile / split selection: a small analytic model of one CTA's critical path, in SM cycles.
@@ -1053,7 +1136,7 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                              int M, int N, int K, int nb1, int nb2,
                              const float* bias, const float* bias2, int bias2_rows_per,
                              const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
-                             float alpha, int act, const Scratch& ws, void* stream) {
+                             float alpha, int act, const Scratch& ws, void* colstats, int cs_rows, void* stream) {
     DWG_REQUIRE(A && B && C, "null pointer");
     DWG_REQUIRE(M > 0 && N > 0 && K > 0 && nb1 > 0 && nb2 > 0, "bad sizes");
     DWG_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && (a_b1 % 8) == 0 && (a_b2 % 8) == 0 && (b_b1 % 8) == 0 && (b_b2 % 8) == 0,
@@ -1064,6 +1147,7 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
     int rc = ensure_sms();
     if (rc) return rc;
     g_counter_cap = ws.n_counters;
+    g_plan_cs = colstats ? 1 : 0;
     const int epi = act == ACT_GEGLU ? EPI_GEGLU : (out_f16 ? EPI_F16 : EPI_F32);
     const int64_t esz = out_f16 ? 2 : 4;
     if (nb1 == 1) c_b1 = ldc * (int64_t)M;
@@ -1088,6 +1172,9 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
     p.m_sched = pl.pair ? p.m_tiles / 2 : p.m_tiles;
     p.total_tiles = p.m_sched * p.n_tiles * p.nz * p.ksplit;
     p.workspace = ws.data; p.counters = ws.counters; p.trace = g_trace;
+    p.colstats = reinterpret_cast<unsigned long long*>(colstats); p.cs_rows = cs_rows;
+    DWG_REQUIRE(!colstats || (epi == EPI_F16 && !p.direct && cs_rows > 0 && (cs_rows % 32) == 0 && ((int64_t)M % cs_rows == 0 || nb1 * nb2 == 1)),
+                "column statistics need the fp16 TMA-store epilogue and statistics groups that are whole multiples of 32 rows");
 
     CUtensorMap tmA, tmB, tmC, tmR;
     const uint32_t ones[4] = {1, 1, 1, 1};
@@ -1130,7 +1217,7 @@ static int conv_impl(const void* x, const void* w, void* y, int out_f16,
                                     int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
                                     int pad_h, int pad_w, int Ho, int Wo,
                                     const float* bias, const float* bias2_per_image,
-                                    const void* residual, int act, const Scratch& ws, void* stream) {
+                                    const void* residual, int act, const Scratch& ws, void* colstats, void* stream) {
     DWG_REQUIRE(x && w && y, "null pointer");
     DWG_REQUIRE(Cin % 8 == 0, "Cin must be a multiple of 8 (pad the channels)");
     DWG_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
@@ -1139,6 +1226,7 @@ static int conv_impl(const void* x, const void* w, void* y, int out_f16,
     int rc = ensure_sms();
     if (rc) return rc;
     g_counter_cap = ws.n_counters;
+    g_plan_cs = colstats ? 1 : 0;
     // pixel box of one 128-row tile
     int BW = 1;
     while (BW * 2 <= Wo && BW * 2 <= BM) BW *= 2;
@@ -1193,6 +1281,9 @@ static int conv_impl(const void* x, const void* w, void* y, int out_f16,
     p.m_sched = pl.pair ? p.m_tiles / 2 : p.m_tiles;
     p.total_tiles = p.m_sched * p.n_tiles * p.ksplit;
     p.workspace = ws.data; p.counters = ws.counters; p.trace = g_trace;
+    p.colstats = reinterpret_cast<unsigned long long*>(colstats); p.cs_rows = 0;
+    DWG_REQUIRE(!colstats || (epi == EPI_F16 && !p.direct && (Wo % BW) == 0 && (Ho % BH) == 0 && (Nimg % BNI) == 0 && ((BW * BH) % 32) == 0),
+                "column statistics need the fp16 TMA-store epilogue and exactly tiled images with >= 32 pixels per tile image");
 
     CUtensorMap tmA, tmB, tmC, tmR;
     {
@@ -1239,12 +1330,12 @@ extern "C" int64_t dwg_gemm_workspace_bytes(void) { return kWsCounterBytes + ((i
 extern "C" int dwg_gemm_f16_ws(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2, const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
                                void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16, int M, int N, int K, int nb1, int nb2,
                                const float* bias, const float* bias2, int bias2_rows_per, const void* residual, int64_t ldr, int64_t r_b1,
-                               int64_t r_b2, float alpha, int act, void* workspace, int64_t workspace_bytes, void* stream) {
+                               int64_t r_b2, float alpha, int act, void* workspace, int64_t workspace_bytes, void* colstats, int colstats_rows, void* stream) {
     Scratch s;
     int rc = scratch_from_caller(workspace, workspace_bytes, s);
     if (rc) return rc;
     return gemm_impl(A, lda, a_b1, a_b2, B, ldb, b_b1, b_b2, C, ldc, c_b1, c_b2, out_f16, M, N, K, nb1, nb2, bias, bias2, bias2_rows_per, residual, ldr,
-                     r_b1, r_b2, alpha, act, s, stream);
+                     r_b1, r_b2, alpha, act, s, colstats, colstats_rows, stream);
 }
 extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2, const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
                             void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16, int M, int N, int K, int nb1, int nb2,
@@ -1254,15 +1345,15 @@ extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_
     int rc = scratch_from_library(s);
     if (rc) return rc;
     return gemm_impl(A, lda, a_b1, a_b2, B, ldb, b_b1, b_b2, C, ldc, c_b1, c_b2, out_f16, M, N, K, nb1, nb2, bias, bias2, bias2_rows_per, residual, ldr,
-                     r_b1, r_b2, alpha, act, s, stream);
+                     r_b1, r_b2, alpha, act, s, nullptr, 0, stream);
 }
 extern "C" int dwg_conv2d_nhwc_f16_ws(const void* x, const void* w, void* y, int out_f16, int Nimg, int H, int W, int Cin, int Cout, int ksize,
                                       int stride, int pad_h, int pad_w, int Ho, int Wo, const float* bias, const float* bias2_per_image,
-                                      const void* residual, int act, void* workspace, int64_t workspace_bytes, void* stream) {
+                                      const void* residual, int act, void* workspace, int64_t workspace_bytes, void* colstats, void* stream) {
     Scratch s;
     int rc = scratch_from_caller(workspace, workspace_bytes, s);
     if (rc) return rc;
-    return conv_impl(x, w, y, out_f16, Nimg, H, W, Cin, Cout, ksize, stride, pad_h, pad_w, Ho, Wo, bias, bias2_per_image, residual, act, s, stream);
+    return conv_impl(x, w, y, out_f16, Nimg, H, W, Cin, Cout, ksize, stride, pad_h, pad_w, Ho, Wo, bias, bias2_per_image, residual, act, s, colstats, stream);
 }
 extern "C" int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int out_f16, int Nimg, int H, int W, int Cin, int Cout, int ksize,
                                    int stride, int pad_h, int pad_w, int Ho, int Wo, const float* bias, const float* bias2_per_image,
@@ -1270,7 +1361,7 @@ extern "C" int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int ou
     Scratch s;
     int rc = scratch_from_library(s);
     if (rc) return rc;
-    return conv_impl(x, w, y, out_f16, Nimg, H, W, Cin, Cout, ksize, stride, pad_h, pad_w, Ho, Wo, bias, bias2_per_image, residual, act, s, stream);
+    return conv_impl(x, w, y, out_f16, Nimg, H, W, Cin, Cout, ksize, stride, pad_h, pad_w, Ho, Wo, bias, bias2_per_image, residual, act, s, nullptr, stream);
 }
 
 /* Tuning / introspection (tools/gemm_sweep.py): force the tile width and split count of the next

@@ -174,6 +174,83 @@ gn_apply_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ stats, co
     }
 }
 
+// GroupNorm (+SiLU) whose statistics were produced by the GEMM / conv epilogue of the layer that wrote x (per-column fixed-point
+// sums, csrc/gemm_tcgen05.cu): no statistics pass and no memset -- the prologue folds the cpg column sums of each group
+// (integer adds: exact and order-free), the body is the apply pass.  CTA 0 of every image also writes the group statistics
+// for the backward.
+__global__ void __launch_bounds__(256)
+gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colstats, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, act_t* __restrict__ y, fix_t* __restrict__ stats_out, int HW, int C, int G, float eps,
+                   int do_silu, int rows_per_cta) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float s_mean[64], s_rstd[64];
+    const int n = blockIdx.y;
+    const int c8 = C / 8, cpg = C / G;
+    {
+        // 8 threads per group (G <= 32) fold the group's columns
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        long long S = 0, Q = 0;
+        if (g < G) {
+            for (int slot = 0; slot < 4; slot++) {                // the producer spreads its atomics over 4 slots (m_tile & 3)
+                const fix_t* cs = colstats + (((size_t)slot * gridDim.y + n) * C + (size_t)g * cpg) * 2;
+                for (int k = sub; k < cpg; k += 8) { S += (long long)cs[2 * k]; Q += (long long)cs[2 * k + 1]; }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { S += __shfl_xor_sync(0xffffffffu, S, o); Q += __shfl_xor_sync(0xffffffffu, Q, o); }
+        if (g < G && sub == 0) {
+            const double inv = 1.0 / ((double)HW * (double)cpg) * (1.0 / 1048576.0);
+            const double m = (double)S * inv, q = (double)Q * inv;
+            s_mean[g] = (float)m;
+            s_rstd[g] = rsqrtf((float)fmax(q - m * m, 0.0) + eps);
+            if (stats_out && blockIdx.x == 0) { stats_out[((size_t)n * G + g) * 2] = (fix_t)S; stats_out[((size_t)n * G + g) * 2 + 1] = (fix_t)Q; }
+        }
+    }
+    __syncthreads();
+    const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
+    const h8* xp = reinterpret_cast<const h8*>(x + (size_t)n * HW * C);
+    h8* yp = reinterpret_cast<h8*>(y + (size_t)n * HW * C);
+    const int rp = c8 <= 256 ? 256 / c8 : 1;
+    const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
+    for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
+        float a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int c = cv * 8 + i, g = c / cpg;
+            a[i] = s_rstd[g] * gamma[c];
+            b[i] = beta[c] - s_mean[g] * a[i];
+        }
+        int r = row0 + rl;
+        for (; r + 3 * rp < row1; r += 4 * rp) {
+            h8 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = xp[(size_t)(r + u * rp) * c8 + cv];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float o = fmaf(f[i], a[i], b[i]);
+                    f[i] = do_silu ? silu(o) : o;
+                }
+                yp[(size_t)(r + u * rp) * c8 + cv] = pack8(f);
+            }
+        }
+        for (; r < row1; r += rp) {
+            float f[8];
+            unpack8(xp[(size_t)r * c8 + cv], f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float o = fmaf(f[i], a[i], b[i]);
+                f[i] = do_silu ? silu(o) : o;
+            }
+            yp[(size_t)r * c8 + cv] = pack8(f);
+        }
+    }
+}
+
 // One-launch GroupNorm (+SiLU) for tensors that fit the shared memory of one cluster per (image, 4-group slab)
 // -- every GroupNorm of the UNet / ControlNet at batch 2.  A cluster of GN_CS CTAs owns one image and a slab of
 // 4 consecutive groups (4*cpg channels, always a multiple of 8); CTA r of the cluster takes the r-th share of the
@@ -718,6 +795,7 @@ extern "C" int dwg_nn_set_carveout(int percent) {
     const int v = percent < 0 ? (int)cudaSharedmemCarveoutDefault : (percent > 100 ? 100 : percent);
     cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
     cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(gn_apply_cs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
     cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
     cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
     cudaFuncSetAttribute(layernorm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, v);
@@ -772,6 +850,21 @@ extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float*
     dim3 grid2((HW + rows_apply - 1) / rows_apply, N);
     launch_pdl(gn_apply_kernel, grid2, dim3(256), 0, st, (const h16*)x, (const fix_t*)stats, gamma, beta, (h16*)y, HW, C, G, eps, do_silu & 1, rows_apply);
     return check_launch("dwg_groupnorm_fwd");
+}
+
+extern "C" int dwg_groupnorm_apply_cs(const void* x, const float* gamma, const float* beta, void* y, const void* colstats, void* stats_out,
+                                      int N, int HW, int C, int G, float eps, int do_silu, void* stream) {
+    DWG_REQUIRE(x && gamma && beta && y && colstats, "null pointer");
+    DWG_REQUIRE(C % 8 == 0 && C % G == 0 && G <= 32 && al16(x) && al16(y), "C must be a multiple of 8 and of G, G <= 32; 16-byte aligned tensors");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;
+    int rows_per_cta = (int)(((int64_t)N * HW + 4 * kNumSMs - 1) / (4 * kNumSMs));
+    if (rows_per_cta < 4 * rp_) rows_per_cta = 4 * rp_;
+    if (rows_per_cta > 64 * rp_) rows_per_cta = 64 * rp_;
+    dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
+    launch_pdl(gn_apply_cs_kernel, grid, dim3(256), 0, st, (const h16*)x, (const fix_t*)colstats, gamma, beta, (h16*)y, (fix_t*)stats_out, HW, C, G, eps,
+               do_silu & 1, rows_per_cta);
+    return check_launch("dwg_groupnorm_apply_cs");
 }
 
 extern "C" int dwg_groupnorm_bwd(const void* x, const void* dy, const void* stats_, const float* gamma, const float* beta,

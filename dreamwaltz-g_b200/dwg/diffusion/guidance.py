@@ -172,9 +172,13 @@ class ControlNetScoreDistillation:
         (controlnet.py:98-114 / diffusers): the ControlNet is enqueued on a second stream (its own
         split-K scratch lane) and joins before the UNet decoder.  At batch 2 most layers leave SMs idle,
         so the two chains fill each other's gaps; fork/join are graph edges under CUDA-graph capture."""
+        B = x2.shape[0]
         if not self.two_streams:
-            down, mid = self.controlnet.forward(x2, self.timestep, ctx, cond, self.conditioning_scale)
-            return self.unet.forward(x2, self.timestep, ctx, down, mid)
+            pre_c = self.controlnet.prepare(self.timestep, ctx, B, cond)
+            skips_c, h_c = self.controlnet.features(x2, pre_c, cond)
+            state = self.unet.encode(x2, self.timestep, ctx)
+            down, mid = self.controlnet.residuals(skips_c, h_c, self.conditioning_scale, add_to=(state[1], state[0]))
+            return self.unet.decode(state, down, mid, summed=True)
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -193,14 +197,18 @@ class ControlNetScoreDistillation:
         with torch.cuda.stream(side):
             ops.gemm_lane(1)
             try:
-                down, mid = self.controlnet.forward(x2, self.timestep, ctx, cond, self.conditioning_scale, pre=pre_c)
+                if pre_c is None:
+                    pre_c = self.controlnet.prepare(self.timestep, ctx, B, cond)
+                skips_c, h_c = self.controlnet.features(x2, pre_c, cond)
             finally:
                 ops.gemm_lane(0)
         state = self.unet.encode(x2, self.timestep, ctx, pre=pre_u)
         main.wait_stream(side)
-        for r in down + [mid]:
+        for r in skips_c + [h_c]:
             r.record_stream(main)
-        return self.unet.decode(state, down, mid)
+        # the zero convolutions run after the join with the UNet skips as their residual operand: skip + residual in one epilogue
+        down, mid = self.controlnet.residuals(skips_c, h_c, self.conditioning_scale, add_to=(state[1], state[0]))
+        return self.unet.decode(state, down, mid, summed=True)
 
     def get_timestep(self, batch_size):
         return torch.randint(self.t_lo, self.t_hi + 1, (batch_size,), device=self.device,

@@ -66,20 +66,33 @@ class Weights:
         return name in self.w
 
 
-def conv(W, name, x, stride=1, padding=1, bias2=None, residual=None, out_dtype=F16, out_hw=None, use_bias=True):
+STATS_IN_EPILOGUE = os.environ.get('DWG_NO_EPILOGUE_STATS') != '1'      # GroupNorm statistics from the producing epilogue (A/B switch)
+
+
+def conv(W, name, x, stride=1, padding=1, bias2=None, residual=None, out_dtype=F16, out_hw=None, use_bias=True, stats=False):
+    """stats=True: the output feeds a GroupNorm -- its epilogue accumulates that layer's statistics (y._cs)."""
     w = W.w[name]
     if x.shape[-1] != w.shape[-1]:
         x = _pad_c(x)
     return ops.conv2d_nhwc(x, w, bias=W.b.get(name) if use_bias else None, bias2=bias2, residual=residual, stride=stride,
-                           padding=padding, out_hw=out_hw, out_dtype=out_dtype)
+                           padding=padding, out_hw=out_hw, out_dtype=out_dtype, stats=stats and STATS_IN_EPILOGUE)
 
 
-def linear(W, name, x2d, residual=None, act=None, out_dtype=F16, alpha=1.0):
-    return ops.gemm(x2d, W.w[name], bias=W.b.get(name), residual=residual, act=act, out_dtype=out_dtype, alpha=alpha)
+def linear(W, name, x2d, residual=None, act=None, out_dtype=F16, alpha=1.0, stats_rows=None):
+    return ops.gemm(x2d, W.w[name], bias=W.b.get(name), residual=residual, act=act, out_dtype=out_dtype, alpha=alpha,
+                    colstats_rows=stats_rows if STATS_IN_EPILOGUE else None)
+
+
+def _view_keep_stats(t, *shape):
+    v = t.view(*shape)
+    if getattr(t, '_cs', None) is not None:
+        v._cs = t._cs
+    return v
 
 
 def gn(W, name, x, groups, eps, silu, return_stats=False):
-    return ops.group_norm(x, W.w[name], W.b[name], groups=groups, eps=eps, silu=silu, return_stats=return_stats)
+    return ops.group_norm(x, W.w[name], W.b[name], groups=groups, eps=eps, silu=silu, return_stats=return_stats,
+                          colstats=getattr(x, '_cs', None))
 
 
 def timestep_embedding(t, dim):
@@ -198,10 +211,10 @@ class DiffusionNet:
     def resnet(self, p, x, tproj):
         W, G = self.W, self.G
         h = gn(W, p + '.norm1', x, G, 1e-5, True)
-        h = conv(W, p + '.conv1', h, bias2=tproj.get(p) if tproj else None)
+        h = conv(W, p + '.conv1', h, bias2=tproj.get(p) if tproj else None, stats=True)
         h = gn(W, p + '.norm2', h, G, 1e-5, True)
         sc = conv(W, p + '.conv_shortcut', x, padding=0) if W.has(p + '.conv_shortcut') else x
-        return conv(W, p + '.conv2', h, residual=sc)
+        return conv(W, p + '.conv2', h, residual=sc, stats=True)
 
     def transformer(self, p, x, ctx, heads):
         W = self.W
@@ -221,8 +234,8 @@ class DiffusionNet:
         g = linear(W, b + '.ff.net.0.proj', n.reshape(B * H * Wd, C), act='geglu')        # GEGLU fused in the epilogue
         h = linear(W, b + '.ff.net.2', g, residual=h.reshape(B * H * Wd, C)).view(B, H, Wd, C)
         if lin_proj:
-            return linear(W, p + '.proj_out', h.view(B * H * Wd, C), residual=x.view(B * H * Wd, C)).view(B, H, Wd, C)
-        return conv(W, p + '.proj_out', h, padding=0, residual=x)
+            return _view_keep_stats(linear(W, p + '.proj_out', h.view(B * H * Wd, C), residual=x.view(B * H * Wd, C), stats_rows=H * Wd), B, H, Wd, C)
+        return conv(W, p + '.proj_out', h, padding=0, residual=x, stats=True)
 
     def down_path(self, h, tproj, ctx):
         cfg, nb = self.cfg, len(self.cfg['block_out'])
@@ -234,7 +247,7 @@ class DiffusionNet:
                     h = self.transformer(f'down_blocks.{i}.attentions.{j}', h, ctx, self.heads_at(i))
                 skips.append(h)
             if i < nb - 1:
-                h = conv(self.W, f'down_blocks.{i}.downsamplers.0.conv', h, stride=2, padding=1)
+                h = conv(self.W, f'down_blocks.{i}.downsamplers.0.conv', h, stride=2, padding=1, stats=True)
                 skips.append(h)
         return h, skips
 
@@ -273,6 +286,15 @@ class ControlNet(DiffusionNet):
         B = sample_nchw.shape[0]
         if pre is None:
             pre = self.prepare(t, ctx, B, cond_nchw01)
+        skips, h = self.features(sample_nchw, pre, cond_nchw01)
+        return self.residuals(skips, h, conditioning_scale=conditioning_scale)
+
+    @torch.no_grad()
+    def features(self, sample_nchw, pre, cond_nchw01=None):
+        """conv_in + condition embedding + down blocks + mid block -> (13 skip features, mid feature): the part that can run
+        beside the UNet encoder on another stream."""
+        W = self.W
+        B = sample_nchw.shape[0]
         tproj, ctx = pre['tproj'], pre['ctx']
         self._ctx_kv = pre['ctx_kv']
         h = conv(W, 'conv_in', to_nhwc_f16(sample_nchw))
@@ -284,11 +306,28 @@ class ControlNet(DiffusionNet):
         h = ops.add(h, c) if c.shape[0] == B else h + c
         h, skips = self.down_path(h, tproj, ctx)
         h = self.mid(h, tproj, ctx)
+        return skips, h
+
+    @torch.no_grad()
+    def residuals(self, skips, h, conditioning_scale=1.0, add_to=None):
+        """The zero convolutions.  ``add_to`` = (UNet skip list, UNet mid output): the UNet tensors the residuals are added to
+        (diffusers: down_block_additional_residuals / mid_block_additional_residual) become the RESIDUAL operand of the zero
+        convolutions' epilogues, which return the sums directly -- no separate add kernels, and the epilogue also accumulates
+        the GroupNorm statistics the decoder needs for them."""
+        W = self.W
+        if add_to is not None and conditioning_scale == 1.0:
+            u_skips, u_mid = add_to
+            down = [conv(W, f'controlnet_down_blocks.{i}', s, padding=0, residual=u, stats=True) for i, (s, u) in enumerate(zip(skips, u_skips))]
+            mid = conv(W, 'controlnet_mid_block', h, padding=0, residual=u_mid, stats=True)
+            return down, mid
         down = [conv(W, f'controlnet_down_blocks.{i}', s, padding=0) for i, s in enumerate(skips)]
         mid = conv(W, 'controlnet_mid_block', h, padding=0)
         if conditioning_scale != 1.0:
             down = [d * conditioning_scale for d in down]
             mid = mid * conditioning_scale
+        if add_to is not None:
+            u_skips, u_mid = add_to
+            return [ops.add(u, d) for u, d in zip(u_skips, down)], ops.add(u_mid, mid)
         return down, mid
 
 
@@ -309,29 +348,34 @@ class UNet(DiffusionNet):
             pre = self.prepare(t, ctx, B)
         tproj, ctx = pre['tproj'], pre['ctx']
         self._ctx_kv = pre['ctx_kv']
-        h = conv(W, 'conv_in', to_nhwc_f16(sample_nchw))
+        h = conv(W, 'conv_in', to_nhwc_f16(sample_nchw), stats=True)
         h, skips = self.down_path(h, tproj, ctx)
         h = self.mid(h, tproj, ctx)
         return h, skips, tproj, ctx
 
     @torch.no_grad()
-    def decode(self, state, down_residuals=None, mid_residual=None):
+    def decode(self, state, down_residuals=None, mid_residual=None, summed=False):
+        """summed=True: down_residuals / mid_residual already ARE skip + residual (ControlNet.residuals(add_to=...))."""
         W, cfg = self.W, self.cfg
         nb = len(cfg['block_out'])
         h, skips, tproj, ctx = state
-        if down_residuals is not None:
-            skips = [ops.add(s, r) for s, r in zip(skips, down_residuals)]
-        if mid_residual is not None:
-            h = ops.add(h, mid_residual)
+        if summed:
+            skips, h = list(down_residuals), mid_residual
+        else:
+            if down_residuals is not None:
+                skips = [ops.add(s, r) for s, r in zip(skips, down_residuals)]
+            if mid_residual is not None:
+                h = ops.add(h, mid_residual)
+        skips = list(skips)
         for i in range(nb):
             for j in range(cfg['layers_per_block'] + 1):
-                h = torch.cat([h, skips.pop()], dim=-1)
+                h = ops.cat_channels(h, skips.pop())
                 h = self.resnet(f'up_blocks.{i}.resnets.{j}', h, tproj)
                 if i > 0:
                     h = self.transformer(f'up_blocks.{i}.attentions.{j}', h, ctx, self.heads_at(nb - 1 - i))
             if i < nb - 1:
                 h = h.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)            # nearest 2x (data movement)
-                h = conv(W, f'up_blocks.{i}.upsamplers.0.conv', h)
+                h = conv(W, f'up_blocks.{i}.upsamplers.0.conv', h, stats=True)
         h = gn(W, 'conv_norm_out', h, self.G, 1e-5, True)
         out = conv(W, 'conv_out', h, out_dtype=torch.float32)
         return out.permute(0, 3, 1, 2).contiguous()
@@ -349,11 +393,11 @@ class VAEEncoder:
     def _resnet_fwd(self, p, x, tape):
         W, G = self.W, self.G
         a, st1 = gn(W, p + '.norm1', x, G, 1e-6, True, return_stats=True)
-        h1 = conv(W, p + '.conv1', a)
+        h1 = conv(W, p + '.conv1', a, stats=True)
         b, st2 = gn(W, p + '.norm2', h1, G, 1e-6, True, return_stats=True)
         has_sc = W.has(p + '.conv_shortcut')
         sc = conv(W, p + '.conv_shortcut', x, padding=0) if has_sc else x
-        out = conv(W, p + '.conv2', b, residual=sc)
+        out = conv(W, p + '.conv2', b, residual=sc, stats=True)
         tape.append(('resnet', p, x, st1, h1, st2, has_sc))
         return out
 
@@ -380,14 +424,14 @@ class VAEEncoder:
         tape = [] if tape is None else tape
         nb = len(cfg['block_out'])
         x = to_nhwc_f16(2.0 * images01_nchw - 1.0)
-        h = conv(W, 'encoder.conv_in', x)
+        h = conv(W, 'encoder.conv_in', x, stats=True)
         for i in range(nb):
             for j in range(cfg['layers_per_block']):
                 h = self._resnet_fwd(f'encoder.down_blocks.{i}.resnets.{j}', h, tape)
             if i < nb - 1:
                 Hh, Ww = h.shape[1], h.shape[2]
                 tape.append(('down', f'encoder.down_blocks.{i}.downsamplers.0.conv', (Hh, Ww)))
-                h = conv(W, f'encoder.down_blocks.{i}.downsamplers.0.conv', h, stride=2, padding=(0, 0), out_hw=(Hh // 2, Ww // 2))
+                h = conv(W, f'encoder.down_blocks.{i}.downsamplers.0.conv', h, stride=2, padding=(0, 0), out_hw=(Hh // 2, Ww // 2), stats=True)
         h = self._resnet_fwd('encoder.mid_block.resnets.0', h, tape)
         h = self._attn_fwd('encoder.mid_block.attentions.0', h, tape)
         h = self._resnet_fwd('encoder.mid_block.resnets.1', h, tape)
@@ -415,7 +459,7 @@ class VAEEncoder:
         ops.softmax_rows_(P, T)
         vT = v.transpose(1, 2).contiguous()
         a = ops.gemm(P, vT)                                                  # [B,T,C]
-        out = linear(W, p + '.to_out.0', a.view(B * T, C), residual=h.view(B * T, C)).view(B, H, Wd, C)
+        out = _view_keep_stats(linear(W, p + '.to_out.0', a.view(B * T, C), residual=h.view(B * T, C), stats_rows=T), B, H, Wd, C)
         tape.append(('attn', p, h, st, n, q, k, v, P))
         return out
 

@@ -534,8 +534,17 @@ def _chk_f16(t):
     return t
 
 
+def _take_colstats(device, groups, N):
+    """Zero-initialised i64 [4, groups, N, 2] for the epilogue's column statistics: an arena slice (zeroed by the step's one
+    memset) or, outside a step, a private zero tensor."""
+    cs = STATS_ARENA.take(device, 4 * groups * N * 2)
+    if cs is None:
+        cs = torch.zeros(4 * groups * N * 2, device=device, dtype=torch.int64)
+    return cs.view(4, groups, N, 2)                             # 4 slots (include/dwg.h)
+
+
 def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=1.0, act=None, out_dtype=torch.float16,
-         out=None):
+         out=None, colstats_rows=None):
     """C[..., M, N] = act(alpha * A[..., M, K] @ B[..., N, K]^T + bias + bias2) + residual  (dwg_gemm_f16).
     a: [M,K] / [b1,M,K] / [b2,b1,M,K] bf16, last dim contiguous (any strides that are multiples of 8);
     b: same rank with N rows."""
@@ -564,6 +573,10 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
     bias2 = None if bias2 is None else f32c(bias2)
     if TUNE_RECORD is not None:
         TUNE_RECORD.append(('gemm', M, N, K, nb1, nb2, act, residual is not None, c4.dtype, bias is not None, bias2 is not None))
+    cs = None
+    if colstats_rows is not None and out_dtype == torch.float16 and act != 'geglu' and colstats_rows % 32 == 0 and (nb1 * nb2 * M) % colstats_rows == 0 \
+            and N % 8 == 0:
+        cs = _take_colstats(a.device, (nb1 * nb2 * M) // colstats_rows, N)
     nbytes = nb1 * nb2 * (2.0 * (M * K + N * K) + M * No * (c4.element_size() + (2 if r4 is not None else 0)))
     with _prof(2.0 * M * N * K * nb1 * nb2, f'gemm M{M} N{N} K{K} b{nb1 * nb2}', nbytes):
         ws = _gemm_workspace(a.device)
@@ -573,12 +586,29 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
                                   M, N, K, nb1, nb2, ptr(bias), ptr(bias2), int(bias2_rows_per),
                                   None if r4 is None else r4.data_ptr(), 0 if r4 is None else r4.stride(2),
                                   0 if r4 is None else r4.stride(1), 0 if r4 is None else r4.stride(0),
-                                  float(alpha), ACT[act], ws.data_ptr(), ws.numel(), stream()), 'dwg_gemm_f16_ws')
+                                  float(alpha), ACT[act], ws.data_ptr(), ws.numel(), ptr(cs), int(colstats_rows or 0), stream()), 'dwg_gemm_f16_ws')
+    if cs is not None:
+        out._cs = cs
     return out
 
 
+def _conv_stats_ok(Nimg, Ho, Wo, Cout):
+    """Mirror of the tile geometry of dwg_conv2d_nhwc_f16 (csrc/gemm_tcgen05.cu): column statistics need exactly tiled images
+    whose share of a 128-row tile is a multiple of 32 pixels (true for every layer of the SD UNets / VAE)."""
+    BW = 1
+    while BW * 2 <= Wo and BW * 2 <= 128:
+        BW *= 2
+    BH = 1
+    while BH * 2 <= Ho and BW * BH * 2 <= 128:
+        BH *= 2
+    BNI = 128 // (BW * BH)
+    if BNI > Nimg:
+        BNI = 1 << (Nimg.bit_length() - 1)
+    return Wo % BW == 0 and Ho % BH == 0 and Nimg % BNI == 0 and (BW * BH) % 32 == 0 and Cout % 8 == 0
+
+
 def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding=1, out_hw=None, act=None,
-                out_dtype=torch.float16):
+                out_dtype=torch.float16, stats=False):
     """NHWC implicit-GEMM convolution (dwg_conv2d_nhwc_f16).  x [N,H,W,Cin], w [Cout,k,k,Cin] bf16.
     padding: int (symmetric) or (top, left) with out_hw=(Ho, Wo) for asymmetric cases."""
     _chk_f16(x), _chk_f16(w)
@@ -599,12 +629,15 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
     bias2 = None if bias2 is None else f32c(bias2)
     if TUNE_RECORD is not None:
         TUNE_RECORD.append(('conv', Nimg, H, W, Cin, Cout, k, stride, ph, pw, Ho, Wo, residual is not None, out_dtype, bias2 is not None))
+    cs = _take_colstats(x.device, Nimg, Cout) if (stats and out_dtype == torch.float16 and _conv_stats_ok(Nimg, Ho, Wo, Cout)) else None
     nbytes = 2.0 * (x.numel() + w.numel()) + y.numel() * (y.element_size() + (2 if residual is not None else 0))
     with _prof(2.0 * Nimg * Ho * Wo * Cout * Cin * k * k, f'conv{k}x{k}s{stride} {Nimg}x{Ho}x{Wo} {Cin}->{Cout}', nbytes):
         ws = _gemm_workspace(x.device)
         check(lib().dwg_conv2d_nhwc_f16_ws(ptr(x), ptr(w), ptr(y), int(out_dtype == torch.float16), Nimg, H, W, Cin, Cout, k,
                                             stride, ph, pw, Ho, Wo, ptr(bias), ptr(bias2), ptr(residual), ACT[act], ws.data_ptr(), ws.numel(),
-                                            stream()), 'dwg_conv2d_nhwc_f16_ws')
+                                            ptr(cs), stream()), 'dwg_conv2d_nhwc_f16_ws')
+    if cs is not None:
+        y._cs = cs
     return y
 
 
@@ -615,7 +648,7 @@ class StatsArena:
     node in front of each of the ~130 GroupNorm launches.  A slice is handed out at most once between two resets; when the
     arena is exhausted or disabled the caller falls back to a private buffer that the C entry point zeroes itself."""
 
-    def __init__(self, entries=1 << 17):
+    def __init__(self, entries=1 << 22):
         self.entries, self.buf, self.cur, self.enabled = entries, {}, {}, True
 
     def reset(self, device):
@@ -641,23 +674,44 @@ class StatsArena:
 STATS_ARENA = StatsArena()
 
 
-def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, return_stats=False):
-    """x [N, ..., C] fp16 channels-last -> [SiLU](GroupNorm(x)) (dwg_groupnorm_fwd)."""
+def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, return_stats=False, colstats=None):
+    """x [N, ..., C] fp16 channels-last -> [SiLU](GroupNorm(x)).  ``colstats`` i64 [N,C,2]: the per-column statistics the
+    producing GEMM / conv epilogue accumulated (ops.gemm(colstats_rows=...) / ops.conv2d_nhwc(stats=True)) -- then ONE kernel
+    (dwg_groupnorm_apply_cs); otherwise statistics pass + apply pass (dwg_groupnorm_fwd)."""
     _chk_f16(x)
     assert x.is_contiguous()
     N, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (N * C)
     y = torch.empty_like(x)
+    L = lib()
+    if colstats is not None and groups <= 32:
+        assert colstats.shape == (4, N, C, 2) and colstats.dtype == torch.int64 and colstats.is_contiguous()
+        stats = None
+        if return_stats:
+            stats = STATS_ARENA.take(x.device, N * groups * 2)
+            stats = (stats if stats is not None else torch.empty(N * groups * 2, device=x.device, dtype=torch.int64)).view(N, groups, 2)
+        check(L.dwg_groupnorm_apply_cs(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(colstats), ptr(stats), N, HW, C, groups, float(eps), int(silu),
+                                       stream()), 'dwg_groupnorm_apply_cs')
+        return (y, stats) if return_stats else y
     stats = STATS_ARENA.take(x.device, N * groups * 2)        # fixed-point (sum, sumsq), include/dwg.h
     flags = int(silu) | (2 if stats is not None else 0)
     if stats is None:
         stats = torch.empty(N * groups * 2, device=x.device, dtype=torch.int64)
     stats = stats.view(N, groups, 2)
-    L = lib()
     check(L.dwg_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), N, HW, C, groups, float(eps), flags,
                               stream()), 'dwg_groupnorm_fwd')
     object.__setattr__(L, 'launches', L.launches + L.dwg_groupnorm_last_launches() - 2)      # the proxy counted 2
     return (y, stats) if return_stats else y
+
+
+def cat_channels(a, b):
+    """torch.cat([a, b], dim=-1) of two channels-last activations, carrying their column statistics along (the statistics of
+    a channel concatenation are the concatenation of the statistics)."""
+    y = torch.cat([a, b], dim=-1)
+    ca, cb = getattr(a, '_cs', None), getattr(b, '_cs', None)
+    if ca is not None and cb is not None:
+        y._cs = torch.cat([ca, cb], dim=2)
+    return y
 
 
 def group_norm_bwd(x, dy, stats, gamma, beta, groups=32, eps=1e-5, silu=False, dx_add=None):

@@ -171,13 +171,17 @@ void* dwg_raster_view(int which, void* geom, void* bin, void* img, int64_t N, in
  * ONCE by the caller before its first use (the kernels leave the counters zero); launches that may run concurrently
  * (two streams) need different workspaces. */
 int64_t dwg_gemm_workspace_bytes(void);
+/* colstats (NULL = off): i64 [4, groups, N, 2] (4 slots that spread the atomics; the consumer adds them), PRE-ZEROED by the caller; the epilogue adds, per output column, the sum and
+ * the sum of squares of the fp16 values it stores (2^-20 fixed point, integer atomics => deterministic), grouped by image
+ * (conv: the image index; GEMM: global row / colstats_rows, a multiple of 32).  These are the GroupNorm statistics of the
+ * layer that consumes the output: dwg_groupnorm_apply_cs folds them per group, so no statistics pass reads the tensor. */
 int dwg_gemm_f16_ws(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                     const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
                     void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16,
                     int M, int N, int K, int nb1, int nb2,
                     const float* bias, const float* bias2, int bias2_rows_per,
                     const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
-                    float alpha, int act, void* workspace, int64_t workspace_bytes, void* stream);
+                    float alpha, int act, void* workspace, int64_t workspace_bytes, void* colstats, int colstats_rows, void* stream);
 int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                   const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
                   void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16,
@@ -242,7 +246,7 @@ int dwg_conv2d_nhwc_f16_ws(const void* x, const void* w, void* y, int out_f16,
                            int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
                            int pad_h, int pad_w, int Ho, int Wo,
                            const float* bias, const float* bias2_per_image,
-                           const void* residual, int act, void* workspace, int64_t workspace_bytes, void* stream);
+                           const void* residual, int act, void* workspace, int64_t workspace_bytes, void* colstats, void* stream);
 int dwg_conv2d_nhwc_f16(const void* x, const void* w, void* y, int out_f16,
                          int Nimg, int H, int W, int Cin, int Cout, int ksize, int stride,
                          int pad_h, int pad_w, int Ho, int Wo,
@@ -268,6 +272,10 @@ int dwg_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void
 int dwg_groupnorm_last_launches(void);
 /* enable (1) / disable (0, default: measured slower inside the step) the one-launch cluster kernel */
 int dwg_groupnorm_set_fused(int on);
+/* y = [SiLU](GroupNorm_G(x)) from the column statistics the producing GEMM / conv epilogue accumulated (colstats i64 [4,N,C,2]);
+ * stats_out i64 [N,G,2] (optional) receives the group statistics in the format dwg_groupnorm_bwd consumes. */
+int dwg_groupnorm_apply_cs(const void* x, const float* gamma, const float* beta, void* y, const void* colstats, void* stats_out,
+                           int N, int HW, int C, int G, float eps, int do_silu, void* stream);
 /* dx = d/dx [SiLU](GroupNorm(x)) . dy  (+ dx_add if given);  bstats [N,G,2] i64 workspace (2^-36 fixed point) */
 int dwg_groupnorm_bwd(const void* x, const void* dy, const void* stats, const float* gamma, const float* beta,
                       const void* dx_add, void* dx, void* bstats, int N, int HW, int C, int G, float eps,

@@ -228,3 +228,45 @@ def test_conv3x3_halo_mode_matches_torch(pair, N, H, W, Cin, Cout):
     assert took == 1, 'halo mode was not taken'
     assert _rel(y, ref) < 2e-3 and _rel(y3, ref) < 2e-3
     assert _rel(y2, ref + temb[:, None, None, :] + res.float()) < 2e-2
+
+
+@pytest.mark.parametrize('case', ['gemm', 'gemm_res', 'conv3', 'conv1_res', 'conv_small', 'conv_s2'])
+def test_epilogue_column_statistics_feed_groupnorm(case):
+    """GroupNorm statistics from the PRODUCING epilogue: the per-column fixed-point sums a GEMM / conv launch accumulates equal
+    the sums of the fp16 tensor it wrote (exactly: integer accumulation of the rounded values), and dwg_groupnorm_apply_cs on
+    them equals the two-pass GroupNorm bit for bit."""
+    import torch
+    from dwg import ops
+    torch.manual_seed(7)
+    dev = 'cuda'
+    ops.STATS_ARENA.reset(dev)
+    if case.startswith('gemm'):
+        M, N, K, rows = 2 * 1024, 320, 192, 1024
+        a, b = torch.randn(M, K, device=dev).half(), (torch.randn(N, K, device=dev) * 0.1).half()
+        res = torch.randn(M, N, device=dev).half() if case == 'gemm_res' else None
+        y = ops.gemm(a, b, bias=torch.randn(N, device=dev), residual=res, colstats_rows=rows)
+        groups, C = M // rows, N
+        yv = y.view(groups, rows, C)
+    else:
+        Nimg, H, W, Cin, Cout, k, stride = {'conv3': (2, 32, 32, 64, 128, 3, 1), 'conv1_res': (2, 16, 16, 320, 320, 1, 1),
+                                            'conv_small': (2, 8, 8, 128, 256, 3, 1), 'conv_s2': (1, 64, 64, 32, 64, 3, 2)}[case]
+        x = torch.randn(Nimg, H, W, Cin, device=dev).half()
+        w = (torch.randn(Cout, k, k, Cin, device=dev) * 0.05).half()
+        Ho = H // stride
+        res = torch.randn(Nimg, Ho, Ho, Cout, device=dev).half() if case == 'conv1_res' else None
+        y = ops.conv2d_nhwc(x, w, bias=torch.randn(Cout, device=dev), residual=res, stride=stride, padding=1 if k == 3 else 0, stats=True)
+        groups, C = Nimg, Cout
+        yv = y.view(groups, -1, C)
+    cs = y._cs
+    assert cs.shape == (4, groups, C, 2) and cs.dtype == torch.int64
+    yd = yv.double()
+    ref = torch.stack([yd.sum(1), (yd * yd).sum(1)], dim=-1)                       # [groups, C, 2]
+    got = cs.sum(0).double() / 2.0 ** 20
+    # each 32-row partial is converted to 2^-20 fixed point once: |error| <= 2^-21 per partial + fp32 rounding of the 32-term partial sums
+    torch.testing.assert_close(got, ref, rtol=2e-6, atol=1e-3)
+    g, bta = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.1
+    y4 = y.view(groups, -1, 1, C) if y.dim() == 2 else y
+    two_pass, st_ref = ops.group_norm(y4.contiguous(), g, bta, 32, 1e-5, silu=True, return_stats=True)
+    one_pass, st = ops.group_norm(y4.contiguous(), g, bta, 32, 1e-5, silu=True, return_stats=True, colstats=cs)
+    assert (one_pass.float() - two_pass.float()).abs().max() <= 2e-3 * two_pass.float().abs().max()      # statistics agree to ~1e-7: a few fp16 ulps at most
+    torch.testing.assert_close(st.double() / 2.0 ** 20, st_ref.double() / 2.0 ** 20, rtol=2e-6, atol=1e-2)
