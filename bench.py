@@ -409,7 +409,8 @@ def run_dwg(args):
                    'cuda_graphs': ('whole step' if graphed else ('sub-graphs' if not args.no_graphs else False)),
                    'condition_image': 'produced on the device every step (keypoints -> projection -> depth-tested -> OpenPose image)' if sc.produce_cond
                    else 'fixed image copied from pinned host memory'},
-        'e2e': {'value': round(e2e_v, 3), 'unit': 'steps/s', 'ms_per_step': round(ms_e2e, 3), 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 12},
+        'e2e': {'value': round(e2e_v, 3), 'unit': 'steps/s' if world == 1 else 'views/s', 'ms_per_step': round(ms_e2e, 3), 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': 12},
         'gpu_launches': int(round(launches)), 'host_enqueue_ms_per_step': round(cpu_enqueue_ms, 3),
         'host_ms_parts_per_step': {k: round(v / max(1, 2 * args.steps + args.warmup + min(2, args.warmup)), 3) for k, v in host_parts.items()}, 'clocks': clocks, 'roofline': roof,
         'roofline_raster': roof_r,
@@ -423,7 +424,7 @@ def run_dwg(args):
                                                           'e2e': round(e2e_v / out['ref_gpu']['value'], 2), 'target': 10.0}
         except Exception as e:
             out['ref_gpu'] = {'unavailable': f'{type(e).__name__}: {e}'}
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:      # rank 0, N = 1 only (bounded sample)
         out['cpu_baseline'] = cpu_baseline(sample_only=True)
     print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
@@ -608,8 +609,13 @@ def run_reference(args):
     budget_s = 240.0
     sc = OracleScene(tiny=args.tiny)
     times = []
-    for _ in range(min(args.warmup, 1)):
+    t_begin = time.time()
+    n_warm = 0
+    for _ in range(args.warmup):
         sc.step()
+        n_warm += 1
+        if time.time() - t_begin > 60.0:
+            break
     t_begin = time.time()
     for _ in range(args.steps):
         t0 = time.time()
@@ -619,15 +625,17 @@ def run_reference(args):
             break
     ms = 1000.0 * float(np.mean(times))
     v = 1000.0 / ms
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    unit = 'steps/s' if world == 1 else 'views/s'      # one CPU step = one view; rank 0 alone runs this arm
     line = json.dumps({
-        'impl': 'reference', 'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)', 'value': round(v, 5), 'unit': 'steps/s',
-        'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': len(times), 'warmup': min(args.warmup, 1), 'ms_per_step': round(ms, 1),
+        'impl': 'reference', 'metric': 'SDS steps/sec (150k Gaussians, 512^2, SD1.5)', 'value': round(v, 5), 'unit': unit,
+        'n_gpus': world, 'steps': len(times), 'warmup': n_warm, 'ms_per_step': round(ms, 1),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'note': 'reference has no CPU path and is not installable here (diffusers, smplx, pytorch3d, '
                    'diff_gaussian_rasterization absent, no network): this arm times the CPU oracle restatement of the same step'},
-        'cpu_baseline': {'value': round(v, 5), 'unit': 'steps/s', 'cores': min(os.cpu_count(), 32), 'kind': 'port',
+        'cpu_baseline': {'value': round(v, 5), 'unit': unit, 'cores': min(os.cpu_count(), 32), 'kind': 'port',
                          'sample': f'{len(times)} full SDS steps of the same workload'},
-        'e2e': {'value': round(v, 5), 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0,
+        'e2e': {'value': round(v, 5), 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0,
     })
     print(line, file=_JSON_OUT, flush=True)
 

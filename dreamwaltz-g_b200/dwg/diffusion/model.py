@@ -1,6 +1,6 @@
 """UNet2DConditionModel / ControlNetModel / AutoencoderKL-encoder on the dwg tcgen05 kernels.
 
-Activations are NHWC bf16 end to end ([B,H,W,C] == token layout [B,HW,C] for free); every conv /
+Activations are NHWC fp16 end to end ([B,H,W,C] == token layout [B,HW,C] for free); every conv /
 linear / attention matmul is dwg_gemm_f16 or dwg_conv2d_nhwc_f16 (implicit GEMM, TMA-fed
 tcgen05, fp32 accumulation in TMEM) with bias / time-embedding / residual fused into the
 epilogue; GroupNorm(+SiLU), LayerNorm, softmax, GEGLU are the streaming kernels of nn_kernels.cu.
@@ -32,8 +32,8 @@ def _pad_c(t, mult=8, dim=-1):
 
 class Weights:
     """Device-side, layout-converted copy of a diffusers state dict.
-    conv  [Cout,Cin,k,k] fp32 -> [Cout,k,k,Cin8] bf16 (Cin zero-padded to a multiple of 8)
-    linear [out,in] -> bf16;  biases / norm affine -> fp32."""
+    conv  [Cout,Cin,k,k] fp32 -> [Cout,k,k,Cin8] fp16 (Cin zero-padded to a multiple of 8)
+    linear [out,in] -> fp16;  biases / norm affine -> fp32."""
 
     def __init__(self, sd, device='cuda', with_dgrad=False):
         self.w, self.b, self.dg = {}, {}, {}
@@ -103,7 +103,7 @@ def timestep_embedding(t, dim):
 
 
 def attention(W, p, x, ctx, heads, residual, kv=None):
-    """x [B,T,C] bf16 (queries), ctx [B,Tk,Ck] bf16.  Returns to_out(softmax(QK^T/sqrt(d)) V) + residual.
+    """x [B,T,C] fp16 (queries), ctx [B,Tk,Ck] fp16.  Returns to_out(softmax(QK^T/sqrt(d)) V) + residual.
     V is produced transposed ([B,C,Tk], the K-major operand of the PV matmul) by swapping the
     operands of its projection GEMM, so no transpose pass exists.  ``kv`` = precomputed (K, V^T)
     slices of the batched cross-attention projection (DiffusionNet.project_context)."""
@@ -281,7 +281,7 @@ class ControlNet(DiffusionNet):
 
     @torch.no_grad()
     def forward(self, sample_nchw, t, ctx, cond_nchw01, conditioning_scale=1.0, pre=None):
-        """-> (list of 12 down residuals, mid residual), NHWC bf16.  ``pre`` = prepare(...) results computed earlier."""
+        """-> (list of 12 down residuals, mid residual), NHWC fp16.  ``pre`` = prepare(...) results computed earlier."""
         W = self.W
         B = sample_nchw.shape[0]
         if pre is None:
@@ -455,7 +455,7 @@ class VAEEncoder:
         q = linear(W, p + '.to_q', n2).view(B, T, C)
         k = linear(W, p + '.to_k', n2).view(B, T, C)
         v = linear(W, p + '.to_v', n2).view(B, T, C)
-        P = ops.gemm(q, k, alpha=C ** -0.5)                                  # [B,T,T] bf16
+        P = ops.gemm(q, k, alpha=C ** -0.5)                                  # [B,T,T] fp16
         ops.softmax_rows_(P, T)
         vT = v.transpose(1, 2).contiguous()
         a = ops.gemm(P, vT)                                                  # [B,T,C]

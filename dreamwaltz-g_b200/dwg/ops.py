@@ -530,7 +530,7 @@ def _gemm_workspace(device):
 
 
 def _chk_f16(t):
-    assert t.is_cuda and t.dtype == torch.float16, 'tcgen05 layers take bf16 CUDA tensors'
+    assert t.is_cuda and t.dtype == torch.float16, 'tcgen05 layers take fp16 CUDA tensors'
     return t
 
 
@@ -546,7 +546,7 @@ def _take_colstats(device, groups, N):
 def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=1.0, act=None, out_dtype=torch.float16,
          out=None, colstats_rows=None):
     """C[..., M, N] = act(alpha * A[..., M, K] @ B[..., N, K]^T + bias + bias2) + residual  (dwg_gemm_f16).
-    a: [M,K] / [b1,M,K] / [b2,b1,M,K] bf16, last dim contiguous (any strides that are multiples of 8);
+    a: [M,K] / [b1,M,K] / [b2,b1,M,K] fp16, last dim contiguous (any strides that are multiples of 8);
     b: same rank with N rows."""
     _chk_f16(a), _chk_f16(b)
     assert a.stride(-1) == 1 and b.stride(-1) == 1 and a.dim() == b.dim() and 2 <= a.dim() <= 4
@@ -609,7 +609,7 @@ def _conv_stats_ok(Nimg, Ho, Wo, Cout):
 
 def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding=1, out_hw=None, act=None,
                 out_dtype=torch.float16, stats=False):
-    """NHWC implicit-GEMM convolution (dwg_conv2d_nhwc_f16).  x [N,H,W,Cin], w [Cout,k,k,Cin] bf16.
+    """NHWC implicit-GEMM convolution (dwg_conv2d_nhwc_f16).  x [N,H,W,Cin], w [Cout,k,k,Cin] fp16.
     padding: int (symmetric) or (top, left) with out_hw=(Ho, Wo) for asymmetric cases."""
     _chk_f16(x), _chk_f16(w)
     assert x.is_contiguous() and w.is_contiguous()
@@ -641,7 +641,7 @@ def conv2d_nhwc(x, w, *, bias=None, bias2=None, residual=None, stride=1, padding
     return y
 
 
-# ------------------------------------------------------------------------------ norm / activation kernels (bf16 NHWC)
+# ------------------------------------------------------------------------------ norm / activation kernels (fp16 NHWC)
 class StatsArena:
     """One zero-initialised int64 buffer per device that serves the statistics workspace of EVERY GroupNorm (forward and
     backward) of a step: ONE memset per step (reset(), called by the guidance at the top of __call__) instead of one memset
@@ -739,7 +739,7 @@ def layer_norm(x, gamma, beta, eps=1e-5):
 
 
 def softmax_rows_(s, cols):
-    """In-place softmax over the last dim of bf16 scores [..., cols_pad]; columns >= cols become 0."""
+    """In-place softmax over the last dim of fp16 scores [..., cols_pad]; columns >= cols become 0."""
     _chk_f16(s)
     assert s.is_contiguous()
     cp = s.shape[-1]
@@ -788,8 +788,8 @@ def sds_grad(eps_uncond, eps_cond, noise, guidance_scale, weight=1.0):
 
 
 def attention(q, k, vt, heads, Tk, scale=None):
-    """Fused attention forward (dwg_attention_fwd).  q [B,T,C], k [B,Tk,C] bf16 (last dim contiguous),
-    vt [B,C,Tkp] = V transposed.  Returns [B,T,C] bf16."""
+    """Fused attention forward (dwg_attention_fwd).  q [B,T,C], k [B,Tk,C] fp16 (last dim contiguous),
+    vt [B,C,Tkp] = V transposed.  Returns [B,T,C] fp16."""
     _chk_f16(q), _chk_f16(k), _chk_f16(vt)
     B, T, C = q.shape
     hd = C // heads

@@ -1,6 +1,6 @@
 """GPU: tcgen05 GEMM / implicit-GEMM conv against a plain PyTorch fp32 reference of the same op
-(inputs rounded to bf16 first, so the only difference is fp32 accumulation order and the bf16
-rounding of the output).  Tolerance: |err| <= 2e-2 * max|ref| for bf16 outputs, 2e-3 for fp32."""
+(inputs rounded to fp16 first, so the only difference is fp32 accumulation order and the fp16
+rounding of the output).  Tolerance: |err| <= 2e-2 * max|ref| for fp16 outputs, 2e-3 for fp32."""
 import pytest
 import torch
 import torch.nn.functional as F

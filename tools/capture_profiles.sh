@@ -9,7 +9,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 NCU="ncu --clock-control none"
 timeout 600 $NCU --metrics gpu__time_duration.sum -c 60000 --csv --log-file $OUT/${TAG}_launches_bench.csv \
-    python bench.py --steps 2 --warmup 1 --skip-cpu-baseline > $OUT/${TAG}_bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --skip-ref-gpu > $OUT/${TAG}_bench_under_ncu.log 2>&1
 echo "launch list rc=$?"
 for spec in "gemm:gemm_kernel:9" "gemm:fa_fwd:2" "geom:render_:4" "geom:preprocess_kernel|run_sort|scatter_kernel|pack_kernel|lbs_skin|grid_:12" "nn:gn_|layernorm:8"; do
     IFS=: read part pat cnt <<< "$spec"

@@ -1,5 +1,5 @@
 """Diffusion parity at the BENCHMARK's own size and settings (SD1.5 widths, latent 64^2, CFG batch 2, VAE 512^2,
-guidance scale 50): dwg (bf16 tensor-core path) against oracle/diffusion.py moved to the GPU in strict fp32
+guidance scale 50): dwg (fp16 tensor-core path) against oracle/diffusion.py moved to the GPU in strict fp32
 (allow_tf32 = False for matmul AND cuDNN), plus the reference's own default arithmetic (torch defaults: TF32 cuDNN
 convolutions, fp32 matmuls) against the same strict-fp32 oracle as a yardstick, plus run-to-run determinism.
 

@@ -1,5 +1,5 @@
 """GEMM micro-benchmark on the UNet / ControlNet / VAE shapes: dwg tcgen05 kernel vs cuBLAS
-(torch.matmul bf16) under identical conditions (back-to-back launches, CUDA events).
+(torch.matmul fp16) under identical conditions (back-to-back launches, CUDA events).
 python tools/gemm_micro.py [--ncu]   (--ncu: a few launches per shape only, for an ncu capture)"""
 import os
 import sys

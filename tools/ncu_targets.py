@@ -70,6 +70,11 @@ def nn_part():
     gv, bv = torch.ones(128, device=DEV), torch.zeros(128, device=DEV)
     y, st = ops.group_norm(xv, gv, bv, 32, 1e-6, True, return_stats=True)
     ops.group_norm_bwd(xv, y, st, gv, bv, 32, 1e-6, True)
+    # GroupNorm from the producing conv's epilogue statistics (gn_apply_cs: one node instead of memset + stats + apply)
+    wc = (torch.randn(320, 3, 3, 320, device=DEV) * 0.02).half()
+    for _ in range(2):
+        yc = ops.conv2d_nhwc(x, wc, stats=True)
+        ops.group_norm(yc, g, b, 32, 1e-5, True, colstats=yc._cs)
     a = torch.randn(128, 1280, device=DEV).half(); w = torch.randn(1280, 1280, device=DEV).half()
     for _ in range(2):
         ops.gemm(a, w)                      # split-K + finalize
