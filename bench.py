@@ -576,7 +576,7 @@ def ref_gpu_block(args, steps=4, warmup=2):
     TF32 flags + the reference's own gridencoder.cu + a plain-SIMT raster stand-in, same workload, CUDA-event timed."""
     from oracle import ref_gpu
     dev = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
-    sc = ref_gpu.RefGpuScene(dev, tiny=args.tiny, n_unc=args.n_unconstrained, img=args.image, poses=poses())
+    sc = ref_gpu.RefGpuScene(dev, tiny=args.tiny, n_unc=args.n_unconstrained or CONFIGS['cfg2']['n_unc'], img=args.image or CONFIGS['cfg2']['img'], poses=poses())
     ms = ref_gpu.time_steps(sc, steps, warmup)
     del sc
     torch.cuda.empty_cache()

@@ -1,10 +1,10 @@
 // Rasteriser backward (R12): per-tile back-to-front replay + per-Gaussian chain rule.
 //
-// Blend backward: one CTA per tile, one pixel per thread, instance records streamed in reverse
-// with double-buffered bulk TMA copies.  Per-instance gradient contributions of the 256 pixels
-// are first reduced inside each warp with shuffles (skipped entirely when no lane of the warp
-// touched the instance - the common case for small splats), then accumulated across the 8 warps
-// in shared memory, and only ONE global atomic per (instance, component) leaves the CTA.
+// Blend backward: one 64-thread CTA per 8x8 quadrant of a tile (same split as the forward render, see raster_fwd.cu),
+// one pixel per thread, instance records streamed in reverse with double-buffered bulk TMA copies.  Per-instance
+// gradient contributions are first reduced inside each warp (an 8x4 pixel block) with shuffles (skipped entirely when
+// no lane of the warp blends the instance), then accumulated across the CTA's warps in shared memory, and only ONE
+// global atomic per (instance, component) leaves the CTA.
 // Upstream issues one global atomic per (pixel, instance, component).
 //
 // Preprocess backward: conic -> cov2D -> cov3D -> (scale, quaternion), mean2D / depth -> mean3D.
@@ -55,7 +55,7 @@ __device__ __forceinline__ float reduce10(const float (&v)[NG], int lane, int& q
     return d;
 }
 
-__global__ void __launch_bounds__(TILE_PIX)
+__global__ void __launch_bounds__(QPIX)
 render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
                   float bg0, float bg1, float bg2, const float* __restrict__ bg_dev,
                   const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -67,11 +67,16 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     __shared__ __align__(128) Rec s_rec[2][CHUNK];
     __shared__ float s_acc[CHUNK][NG + 1];
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_max[TILE_PIX / 32];
+    __shared__ uint32_t s_max[QPIX / 32];
+    __shared__ uint8_t s_list[QPIX / 32][CHUNK];              // per warp: instances of the chunk touching the warp's block
+    __shared__ uint8_t s_surv[QPIX / 32][CHUNK];              // ... that at least one pixel of the block blends
     if (bg_dev) { bg0 = bg_dev[0]; bg1 = bg_dev[1]; bg2 = bg_dev[2]; }
-    const int tile = blockIdx.y * gx + blockIdx.x;
-    const int px = blockIdx.x * TILE + (threadIdx.x & (TILE - 1));
-    const int py = blockIdx.y * TILE + (threadIdx.x >> 4);
+    const int tile = (blockIdx.y >> 1) * gx + (blockIdx.x >> 1);
+    const int lane = threadIdx.x & 31;
+    const int bx0 = (blockIdx.x >> 1) * TILE + (blockIdx.x & 1) * QUAD;
+    const int by0 = (blockIdx.y >> 1) * TILE + (blockIdx.y & 1) * QUAD + (threadIdx.x >> 5) * 4;
+    const int px = bx0 + (lane & 7);
+    const int py = by0 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
     const uint2 rg = ranges[tile];
@@ -102,7 +107,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     uint32_t mx = last_contributor;
     for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
-    for (int i = threadIdx.x; i < CHUNK * (NG + 1); i += TILE_PIX) (&s_acc[0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < CHUNK * (NG + 1); i += QPIX) (&s_acc[0][0])[i] = 0.f;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -111,7 +116,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     __syncthreads();
     mx = 0;
 #pragma unroll
-    for (int w = 0; w < TILE_PIX / 32; w++) mx = max(mx, s_max[w]);
+    for (int w = 0; w < QPIX / 32; w++) mx = max(mx, s_max[w]);
     if (mx == 0) return;
     const int rounds = ((int)mx + CHUNK - 1) / CHUNK;        // chunks [0, rounds) hold contributors
     auto chunk_cnt = [&](int c) { return min(CHUNK, n - c * CHUNK); };
@@ -125,9 +130,10 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     float last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f, last_depth = 0.f;
     const float bg_dot = bg0 * dLp0 + bg1 * dLp1 + bg2 * dLp2;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-    const int lane = threadIdx.x & 31;
-    const float sx0 = (float)(blockIdx.x * TILE), sx1 = sx0 + (float)(TILE - 1);
-    const float sy0 = (float)(blockIdx.y * TILE + ((threadIdx.x >> 5) << 1)), sy1 = sy0 + 1.0f;
+    const float sx0 = (float)bx0, sx1 = sx0 + 7.0f;
+    const float sy0 = (float)by0, sy1 = sy0 + 3.0f;
+    uint8_t* my_list = s_list[threadIdx.x >> 5];
+    uint8_t* my_surv = s_surv[threadIdx.x >> 5];
     for (int it = 0; it < rounds; it++) {
         const int c = rounds - 1 - it;
         const int buf = it & 1;
@@ -140,47 +146,75 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
         }
         mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
         const int cnt = chunk_cnt(c);
-        for (int j0 = ((cnt - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
-          const int jl = j0 + lane;
-          bool touch = false;
-          if (jl < cnt) {
-              const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][jl]);
-              touch = strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1);
-          }
-          unsigned tmask = __ballot_sync(0xffffffffu, touch);
-          // Touched instances are replayed back to front, BWD_BATCH at a time: the alphas (the long, position-only
-          // chain) are evaluated together, the short T / accumulator recurrences run in order, and the 10
-          // per-instance sums are reduced across the warp with a 12-shuffle "split" butterfly (reduce10) instead
-          // of 10 x 5 shuffles; the lanes that end up owning a sum add it to shared memory in parallel.
-          while (tmask) {
+        // Three warp-uniform passes per chunk: A. cull against the block's rectangle -> ordered per-warp index list; B. power
+        // test + "index < this pixel's last contributor" at every pixel, four independent instances at a time; the
+        // instances kept by at least one lane (survivors) are compacted again; C. survivors replayed back to front,
+        // BWD_BATCH at a time: the alphas (the long, position-only chain) are evaluated together, the short T / accumulator
+        // recurrences run in order, and the 10 per-instance sums are reduced across the warp with a 12-shuffle "split"
+        // butterfly (reduce10) instead of 10 x 5 shuffles; the lanes that end up owning a sum add it to shared memory.
+        // (Per-lane lists as in the forward render were measured slower here: every (pixel, instance) pair then needs ten
+        // shared-memory float atomics, which are CAS loops on this architecture.)
+        int m = 0;
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            const int jl = j0 + lane;
+            bool touch = false;
+            if (jl < cnt) {
+                const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][jl]);
+                touch = strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1);
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, touch);
+            if (touch) my_list[m + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)jl;
+            m += __popc(mask);
+        }
+        __syncwarp();
+        int ms = 0;
+        const int lc_rel = (int)min(last_contributor, (uint32_t)0x7fffffff) - c * CHUNK;      // slots < lc_rel contribute to this pixel
+        for (int i0 = 0; i0 < m; i0 += 4) {
+            bool keep[4];
+            int jj[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                jj[u] = my_list[min(i0 + u, m - 1)];
+                const float4 h0 = *reinterpret_cast<const float4*>(&s_rec[buf][jj[u]]);
+                const float4 h1 = *(reinterpret_cast<const float4*>(&s_rec[buf][jj[u]]) + 1);     // cx, cy, cz, op
+                const float dx = __fsub_rn(h0.x, pxf), dy = __fsub_rn(h0.y, pyf);
+                const float a = __fmul_rn(__fmul_rn(h1.x, dx), dx);
+                const float b = __fmul_rn(__fmul_rn(h1.z, dy), dy);
+                const float cc = __fmul_rn(__fmul_rn(h1.y, dx), dy);
+                const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(a, b)), cc);
+                keep[u] = (i0 + u < m) & (jj[u] < lc_rel) & !((power > 0.0f) | ((power < -5.6f) & (h1.w <= 1.0f)));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const bool any = __any_sync(0xffffffffu, keep[u]);
+                if (any && lane == 0) my_surv[ms] = (uint8_t)jj[u];
+                ms += any ? 1 : 0;
+            }
+        }
+        __syncwarp();
+        for (int i0 = ms - 1; i0 >= 0; i0 -= BWD_BATCH) {
             int jb[BWD_BATCH];
             bool ok[BWD_BATCH];
             float al[BWD_BATCH], Gv[BWD_BATCH], dxv[BWD_BATCH], dyv[BWD_BATCH];
             Rec rcs[BWD_BATCH];
 #pragma unroll
             for (int u = 0; u < BWD_BATCH; u++) {
-                const int bit = tmask ? 31 - __clz(tmask) : 0;
-                ok[u] = tmask != 0u;
-                tmask &= ~(1u << bit);
-                jb[u] = j0 + bit;
-                ok[u] = ok[u] && ((uint32_t)(c * CHUNK + jb[u]) < last_contributor);
-            }
-#pragma unroll
-            for (int u = 0; u < BWD_BATCH; u++) {
+                jb[u] = my_surv[max(i0 - u, 0)];
                 rcs[u] = s_rec[buf][jb[u]];
-                ok[u] &= eval_alpha_nb(rcs[u], pxf, pyf, al[u], Gv[u], dxv[u], dyv[u]);
+                ok[u] = eval_alpha_nb(rcs[u], pxf, pyf, al[u], Gv[u], dxv[u], dyv[u]) & (i0 - u >= 0) & (jb[u] < lc_rel);
             }
 #pragma unroll
             for (int u = 0; u < BWD_BATCH; u++) {
-                const unsigned m = __ballot_sync(0xffffffffu, ok[u]);
-                if (m == 0u) continue;                          // warp-uniform: nobody in this strip blends the instance
+                const unsigned mk = __ballot_sync(0xffffffffu, ok[u]);
+                if (mk == 0u) continue;                         // warp-uniform: nobody in this block blends the instance
                 float v[NG];
 #pragma unroll
                 for (int q = 0; q < NG; q++) v[q] = 0.f;
                 if (ok[u]) {
                     const Rec& rc = rcs[u];
                     const float alpha = al[u], G = Gv[u], dx = dxv[u], dy = dyv[u];
-                    T = T / (1.f - alpha);
+                    const float inv = 1.f / (1.f - alpha);
+                    T = T * inv;
                     const float dchannel_dcolor = alpha * T;
                     float dL_dalpha_ = 0.f;
                     accum_r = last_alpha * last_r + (1.f - last_alpha) * accum_r; last_r = rc.r;
@@ -197,7 +231,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                     dL_dalpha_ += (1.f - accum_a) * dLa;
                     dL_dalpha_ *= T;
                     last_alpha = alpha;
-                    dL_dalpha_ += (-T_final / (1.f - alpha)) * bg_dot;
+                    dL_dalpha_ += (-T_final * inv) * bg_dot;
                     const float dL_dG = rc.op * dL_dalpha_;
                     const float gdx = G * dx, gdy = G * dy;
                     const float dG_ddelx = -gdx * rc.cx - gdy * rc.cy;
@@ -213,11 +247,9 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                 const float tot = reduce10(v, lane, q);
                 if (q >= 0) atomicAdd(&s_acc[jb[u]][q], tot);
             }
-          }
         }
         __syncthreads();            // chunk finished by every warp: flush, and release buffer `buf`
-        if ((int)threadIdx.x < cnt) {
-            const int j = threadIdx.x;
+        for (int j = threadIdx.x; j < cnt; j += QPIX) {
             const uint32_t gid = s_rec[buf][j].idx;
             float a[NG];
             bool any = false;
@@ -402,7 +434,7 @@ extern "C" int dwg_raster_backward(const DwgRasterCamera* cam, int64_t N, const 
     cudaMemsetAsync(g_colors, 0, sizeof(float) * 3 * N, st);
     cudaMemsetAsync(g_opacities, 0, sizeof(float) * N, st);
     cudaMemsetAsync(gcd, 0, sizeof(float4) * N, st);
-    render_bwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2], cd ? cd->bg : nullptr,
+    render_bwd_kernel<<<dim3(2 * gx, 2 * gy), QPIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2], cd ? cd->bg : nullptr,
                                                         im.final_T, im.n_contrib, dL_dcolor, dL_ddepth, dL_dalpha,
                                                         bg_image, out_alpha, g_bg_image, g_means2D, gcd, g_opacities, g_colors);
     preprocess_bwd_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(N, means3D, scales, rotations, *cam, cd, g, g_means2D, gcd,

@@ -9,7 +9,10 @@ namespace raster {
 
 constexpr int TILE = 16;                 // 16x16 pixel tiles, 256-thread CTAs (upstream BLOCK_X/Y)
 constexpr int TILE_PIX = TILE * TILE;
-constexpr int CHUNK = 256;               // instances staged per TMA bulk copy in the blend loops
+constexpr int QUAD = 8;                  // a 16x16 tile is blended by FOUR 64-thread CTAs, one per 8x8 quadrant: the heavy
+constexpr int QPIX = QUAD * QUAD;        // silhouette tiles (thousands of instances) bound the kernel, and their eight
+                                         // warps now run on four different SMs instead of sharing one SM's issue slots
+constexpr int CHUNK = 128;               // instances staged per TMA bulk copy in the blend loops
 constexpr int SORT_CHUNK = 2048;         // keys sorted in shared memory at a time
 
 // One (tile, Gaussian) instance in depth order, gathered once by the pack kernel and then
@@ -104,7 +107,7 @@ struct ImgView {
 // exp(x), x <= 0, as an explicit sequence of IEEE fp32 operations (never contracted): identical,
 // bit for bit, to spec_expf() in oracle/oracle_c.c.  ~1 ulp.
 __device__ __forceinline__ float spec_expf(float x) {
-    if (x < -87.0f) return 0.0f;
+    const bool tiny = x < -87.0f;                  // result 0 (selected at the end: no branch inside the blend loops)
     const float t = __fmul_rn(x, 1.44269504088896341f);
     const float n = rintf(t);
     float r = __fmaf_rn(n, -0.693145751953125f, x);
@@ -119,7 +122,7 @@ __device__ __forceinline__ float spec_expf(float x) {
     float y = __fmaf_rn(p, z, r);
     y = __fadd_rn(y, 1.0f);
     const float s = __int_as_float(((int)n + 127) << 23);
-    return __fmul_rn(y, s);
+    return tiny ? 0.0f : __fmul_rn(y, s);
 }
 
 // alpha of one instance at pixel (pxf,pyf); false when the instance is skipped (power > 0 or
@@ -154,6 +157,23 @@ __device__ __forceinline__ bool eval_alpha_nb(const Rec& rc, float pxf, float py
     G = spec_expf(rej ? -1.0f : power);
     alpha = fminf(0.99f, __fmul_rn(rc.op, G));
     return !rej & !(alpha < 1.0f / 255.0f);
+}
+
+// The same evaluation in two stages, so that a warp can skip the exponential of an instance that NO lane keeps after the
+// (cheap) power test: eval_power + eval_finish == eval_alpha_nb for every lane that keeps the instance.
+__device__ __forceinline__ bool eval_power(const Rec& rc, float pxf, float pyf, float& power, float& dx, float& dy) {
+    dx = __fsub_rn(rc.x, pxf);
+    dy = __fsub_rn(rc.y, pyf);
+    const float a = __fmul_rn(__fmul_rn(rc.cx, dx), dx);
+    const float b = __fmul_rn(__fmul_rn(rc.cz, dy), dy);
+    const float c = __fmul_rn(__fmul_rn(rc.cy, dx), dy);
+    power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(a, b)), c);
+    return !((power > 0.0f) | ((power < -5.6f) & (rc.op <= 1.0f)));
+}
+__device__ __forceinline__ bool eval_finish(float op, float power, bool live, float& alpha, float& G) {
+    G = spec_expf(live ? power : -1.0f);
+    alpha = fminf(0.99f, __fmul_rn(op, G));
+    return live & !(alpha < 1.0f / 255.0f);
 }
 
 // Conservative test: can ANY pixel of the strip [x0,x1] x [y0,y1] get alpha >= 1/255 ?

@@ -1,11 +1,13 @@
 // Rasteriser stage 3 (R12/R13): per-tile front-to-back alpha blending, and the C-ABI forward.
 //
-// One 256-thread CTA per 16x16 tile, one pixel per thread (the per-pixel transmittance chain is
-// evaluated sequentially in source order so that final_T and n_contrib are bit-exact with the
-// oracle).  The tile's depth-sorted 48-byte instance records are contiguous in HBM; they are
-// staged into shared memory by 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx),
-// double-buffered so the copy of chunk c+1 overlaps the blend of chunk c.  All threads read the
-// same record at the same time (shared-memory broadcast); warps vote to leave early.
+// One 64-thread CTA per 8x8 QUADRANT of a 16x16 tile (four CTAs walk the same instance list), one pixel per thread,
+// a warp = an 8x4 pixel block (the per-pixel transmittance chain is evaluated sequentially in source order so that
+// final_T and n_contrib are bit-exact with the oracle).  Why quadrants: every CTA of the launch is resident at once, so
+// the kernel lasts as long as its heaviest tile (a few silhouette tiles hold 5-9k instances, tools/raster_probe.py);
+// with one CTA per tile that tile's eight warps shared one SM's issue slots and a chunk barrier, now they are spread
+// over four SMs.  The tile's depth-sorted 48-byte instance records are contiguous in HBM; they are staged into shared
+// memory by 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx), double-buffered so the copy of chunk c+1
+// overlaps the blend of chunk c.  All threads read the same record at the same time (shared-memory broadcast).
 #include "raster_common.cuh"
 
 namespace dwg {
@@ -19,18 +21,31 @@ int launch_sort(int T, BinView b, GeomView g, const float* colors, const int32_t
 
 constexpr int FWD_BATCH = 4;      // touched instances whose alphas are evaluated together (ILP)
 
-__global__ void __launch_bounds__(TILE_PIX)
+__global__ void __launch_bounds__(QPIX)
 render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
                   float bg0, float bg1, float bg2, const float* __restrict__ bg_dev,
                   const float* __restrict__ bg_image, float* __restrict__ out_fg,
                   float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_alpha,
-                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, unsigned long long* __restrict__ probe) {
     __shared__ __align__(128) Rec s_rec[2][CHUNK];
+    __shared__ unsigned int s_probe[2];
+    __shared__ uint8_t s_list[QPIX / 32][CHUNK];              // per warp: instances of the chunk touching the warp's block
+    __shared__ uint8_t s_pix[QPIX / 32][CHUNK * 32];          // per lane ([slot][lane]): instances this pixel keeps
+    unsigned long long t_probe0 = 0;
+    unsigned int n_touch = 0, n_eval = 0;
+    if (probe) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_probe0));
+        if (threadIdx.x < 2) s_probe[threadIdx.x] = 0;
+    }
     __shared__ __align__(8) uint64_t s_bar[2];
     if (bg_dev) { bg0 = bg_dev[0]; bg1 = bg_dev[1]; bg2 = bg_dev[2]; }
-    const int tile = blockIdx.y * gx + blockIdx.x;
-    const int px = blockIdx.x * TILE + (threadIdx.x & (TILE - 1));
-    const int py = blockIdx.y * TILE + (threadIdx.x >> 4);
+    const int tile = (blockIdx.y >> 1) * gx + (blockIdx.x >> 1);
+    const int lane = threadIdx.x & 31;
+    // this warp's 8 x 4 pixel block inside the quadrant
+    const int bx0 = (blockIdx.x >> 1) * TILE + (blockIdx.x & 1) * QUAD;
+    const int by0 = (blockIdx.y >> 1) * TILE + (blockIdx.y & 1) * QUAD + (threadIdx.x >> 5) * 4;
+    const int px = bx0 + (lane & 7);
+    const int py = by0 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
     const uint2 rg = ranges[tile];
@@ -51,15 +66,15 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, A = 0.f;
     uint32_t last = 0;
-    const int lane = threadIdx.x & 31;
-    // this warp's pixel strip (16 x 2)
-    const float sx0 = (float)(blockIdx.x * TILE), sx1 = sx0 + (float)(TILE - 1);
-    const float sy0 = (float)(blockIdx.y * TILE + ((threadIdx.x >> 5) << 1)), sy1 = sy0 + 1.0f;
+    const float sx0 = (float)bx0, sx1 = sx0 + 7.0f;
+    const float sy0 = (float)by0, sy1 = sy0 + 3.0f;
+    uint8_t* my_list = s_list[threadIdx.x >> 5];
+    uint8_t* my_pix = s_pix[threadIdx.x >> 5];
     for (int c = 0; c < rounds; c++) {
         const int buf = c & 1;
         // every thread has finished reading buffer buf^1 (chunk c-1): safe to refill it with chunk c+1
         const int n_done = __syncthreads_count(done);
-        if (n_done == TILE_PIX) {
+        if (n_done == QPIX) {
             mbar_wait(&s_bar[buf], (uint32_t)((c >> 1) & 1));   // never exit with a bulk copy in flight
             break;
         }
@@ -71,62 +86,97 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
         }
         mbar_wait(&s_bar[buf], (uint32_t)((c >> 1) & 1));
         const int cnt = min(CHUNK, n - c * CHUNK);
-        // Warp-uniform loop: the first 16 bytes of a record decide whether ANY pixel of this warp's
-        // 16x2 strip can be touched; most instances of a tile are rejected here for most warps.
-        const bool warp_live = __any_sync(0xffffffffu, !done);
-        if (warp_live) {
-            // Warp-cooperative culling: each lane tests ONE instance header against this warp's
-            // 16x2 pixel strip; only the touched instances (ballot bits, ascending order) are
-            // visited by the whole warp.  32x fewer serial iterations for the typical small splat.
-            for (int j0 = 0; j0 < cnt; j0 += 32) {
-                const int jl = j0 + lane;
-                bool touch = false;
-                if (jl < cnt) {
-                    const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][jl]);
-                    touch = strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1);
-                }
-                unsigned mask = __ballot_sync(0xffffffffu, touch);
-                // The touched instances are taken FWD_BATCH at a time: their alphas (position-only maths, the
-                // long dependent chain with the exp) are evaluated independently of each other first, then the
-                // short transmittance chain is applied in source order -- same operations per instance, same
-                // order, hence the same bits; ~3x shorter critical path per instance on heavy tiles.
-                while (mask) {
-                    int jb[FWD_BATCH];
-                    bool ok[FWD_BATCH];
-                    float al[FWD_BATCH], cr[FWD_BATCH], cg[FWD_BATCH], cb[FWD_BATCH], cd[FWD_BATCH];
-#pragma unroll
-                    for (int u = 0; u < FWD_BATCH; u++) {
-                        ok[u] = (mask != 0u) && !done;
-                        jb[u] = j0 + (mask ? __ffs(mask) - 1 : 0);
-                        mask &= mask - 1;
-                    }
-#pragma unroll
-                    for (int u = 0; u < FWD_BATCH; u++) {                  // straight-line: FWD_BATCH independent chains
-                        const Rec rc = s_rec[buf][jb[u]];
-                        float G, dx, dy;
-                        ok[u] &= eval_alpha_nb(rc, pxf, pyf, al[u], G, dx, dy);
-                        cr[u] = rc.r; cg[u] = rc.g; cb[u] = rc.b; cd[u] = rc.depth;
-                    }
-#pragma unroll
-                    for (int u = 0; u < FWD_BATCH; u++) {
-                        if (ok[u] && !done) {
-                            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
-                            if (test_T < 0.0001f) {
-                                done = true;
-                            } else {
-                                const float w = __fmul_rn(al[u], T);
-                                C0 = __fadd_rn(C0, __fmul_rn(cr[u], w));
-                                C1 = __fadd_rn(C1, __fmul_rn(cg[u], w));
-                                C2 = __fadd_rn(C2, __fmul_rn(cb[u], w));
-                                D = __fadd_rn(D, __fmul_rn(cd[u], w));
-                                A = __fadd_rn(A, w);
-                                T = test_T;
-                                last = (uint32_t)(c * CHUNK + jb[u] + 1);
-                            }
-                        }
-                    }
-                }
+        if (!__any_sync(0xffffffffu, !done)) continue;          // warp-uniform: every pixel of this block is finished
+        // Three passes over the chunk (the blend loop is a latency chain on the heaviest block, tools/raster_probe.py: the
+        // benchmark's splats cover 1-4 pixels, so a block is "touched" by thousands of instances of which each PIXEL keeps
+        // a few per cent):
+        //  A. cull: each lane tests ONE record header (16 B) against the block's rectangle; the indices of the touched
+        //     instances are compacted, in order, into a per-warp list;
+        //  B. power test (the cheap half of the alpha evaluation) of every listed instance at every pixel, four
+        //     independent instances at a time; a lane appends the instances IT keeps to its own list;
+        //  C. every lane walks its own list: full alpha evaluation + the transmittance recurrence, in source order.  The
+        //     trip count is the longest per-pixel list of the block, not the number of instances touching the block.
+        // Per pixel and instance the arithmetic of C is exactly that of the oracle, in the same order: same bits.
+        int m = 0;
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            const int jl = j0 + lane;
+            bool touch = false;
+            if (jl < cnt) {
+                const float4 h = *reinterpret_cast<const float4*>(&s_rec[buf][jl]);
+                touch = strip_may_touch(h.x, h.y, __float_as_uint(h.z), sx0, sx1, sy0, sy1);
             }
+            const unsigned mask = __ballot_sync(0xffffffffu, touch);
+            if (touch) my_list[m + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)jl;
+            m += __popc(mask);
+        }
+        if (probe) n_touch += m;
+        __syncwarp();
+        int mine = 0;                                               // length of this lane's list
+        for (int i0 = 0; i0 < m; i0 += FWD_BATCH) {
+            bool keep[FWD_BATCH];
+            int jj[FWD_BATCH];
+#pragma unroll
+            for (int u = 0; u < FWD_BATCH; u++) {
+                jj[u] = my_list[min(i0 + u, m - 1)];
+                const float4 h0 = *reinterpret_cast<const float4*>(&s_rec[buf][jj[u]]);
+                const float4 h1 = *(reinterpret_cast<const float4*>(&s_rec[buf][jj[u]]) + 1);     // cx, cy, cz, op
+                const float dx = __fsub_rn(h0.x, pxf), dy = __fsub_rn(h0.y, pyf);
+                const float a = __fmul_rn(__fmul_rn(h1.x, dx), dx);
+                const float b = __fmul_rn(__fmul_rn(h1.z, dy), dy);
+                const float cc = __fmul_rn(__fmul_rn(h1.y, dx), dy);
+                const float power = __fsub_rn(__fmul_rn(-0.5f, __fadd_rn(a, b)), cc);
+                keep[u] = (i0 + u < m) & !done & !((power > 0.0f) | ((power < -5.6f) & (h1.w <= 1.0f)));
+            }
+#pragma unroll
+            for (int u = 0; u < FWD_BATCH; u++) {
+                if (keep[u]) { my_pix[mine * 32 + lane] = (uint8_t)jj[u]; mine++; }
+            }
+        }
+        const int longest = __reduce_max_sync(0xffffffffu, mine);
+        for (int i0 = 0; i0 < longest; i0 += FWD_BATCH) {
+            int jb[FWD_BATCH];
+            bool ok[FWD_BATCH];
+            float al[FWD_BATCH], cr[FWD_BATCH], cg[FWD_BATCH], cb[FWD_BATCH], cd[FWD_BATCH];
+#pragma unroll
+            for (int u = 0; u < FWD_BATCH; u++) {                  // straight-line: FWD_BATCH independent chains
+                const bool valid = i0 + u < mine;
+                jb[u] = valid ? (int)my_pix[(i0 + u) * 32 + lane] : 0;
+                const Rec rc = s_rec[buf][jb[u]];
+                float G, dx, dy;
+                ok[u] = eval_alpha_nb(rc, pxf, pyf, al[u], G, dx, dy) & valid;
+                cr[u] = rc.r; cg[u] = rc.g; cb[u] = rc.b; cd[u] = rc.depth;
+            }
+#pragma unroll
+            for (int u = 0; u < FWD_BATCH; u++) {                  // the recurrence, in source order, branch-free
+                const bool act = ok[u] & !done;
+                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
+                const bool stop = act & (test_T < 0.0001f);
+                const bool take = act & !stop;
+                const float w = __fmul_rn(al[u], T);
+                C0 = take ? __fadd_rn(C0, __fmul_rn(cr[u], w)) : C0;
+                C1 = take ? __fadd_rn(C1, __fmul_rn(cg[u], w)) : C1;
+                C2 = take ? __fadd_rn(C2, __fmul_rn(cb[u], w)) : C2;
+                D = take ? __fadd_rn(D, __fmul_rn(cd[u], w)) : D;
+                A = take ? __fadd_rn(A, w) : A;
+                T = take ? test_T : T;
+                last = take ? (uint32_t)(c * CHUNK + jb[u] + 1) : last;
+                done |= stop;
+                if (probe) n_eval += take ? 1u : 0u;
+            }
+        }
+        __syncwarp();                                               // lists are rewritten by the next chunk
+    }
+    if (probe) {       // debug timeline (dwg_raster_probe): [start ns, end ns, n, max strip touched, max pixel blended, smid]
+        atomicMax(&s_probe[0], n_touch);
+        atomicMax(&s_probe[1], n_eval);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t1;
+            unsigned int smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned long long* o = probe + 6 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+            o[0] = t_probe0; o[1] = t1; o[2] = (unsigned long long)n; o[3] = s_probe[0]; o[4] = s_probe[1]; o[5] = smid;
         }
     }
     if (inside) {
@@ -157,6 +207,11 @@ render_fwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
 using namespace dwg;
 using namespace dwg::raster;
 
+static unsigned long long* g_raster_probe = nullptr;
+/* Debug: device pointer to [4 * tiles][6] u64 that every quadrant CTA of the following forward renders fills with
+ * (start ns, end ns, instances, max touched per strip, max blended per pixel, smid); NULL = off.  tools/raster_probe.py */
+extern "C" int dwg_raster_probe(void* dev_u64) { g_raster_probe = reinterpret_cast<unsigned long long*>(dev_u64); return DWG_OK; }
+
 extern "C" int64_t dwg_raster_geom_bytes(int64_t N) { return (int64_t)GeomView::bytes(N > 0 ? N : 1); }
 extern "C" int64_t dwg_raster_bin_bytes(int64_t P_cap, int H, int W) {
     const int T = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
@@ -186,8 +241,8 @@ extern "C" int dwg_raster_forward(const DwgRasterCamera* cam, int64_t N, const f
     if (rc != DWG_OK) return rc;
     rc = launch_sort(T, b, g, colors_precomp, status, P_cap, 1, st);
     if (rc != DWG_OK) return rc;
-    render_fwd_kernel<<<dim3(gx, gy), TILE_PIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2], cd ? cd->bg : nullptr,
-                                                        bg_image, out_color_fg, out_color, out_depth, out_alpha, im.final_T, im.n_contrib);
+    render_fwd_kernel<<<dim3(2 * gx, 2 * gy), QPIX, 0, st>>>(H, W, gx, b.ranges, b.recs, cam->bg[0], cam->bg[1], cam->bg[2], cd ? cd->bg : nullptr,
+                                                        bg_image, out_color_fg, out_color, out_depth, out_alpha, im.final_T, im.n_contrib, g_raster_probe);
     return check_launch("dwg_raster_forward");
 }
 

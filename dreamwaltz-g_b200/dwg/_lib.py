@@ -68,6 +68,7 @@ SIGNATURES = {
     'dwg_gemm_last_pair': (c_int, []),
     'dwg_gemm_last_key': (c_int, [c_void_p]),
     'dwg_gemm_trace': (c_int, [c_void_p]),
+    'dwg_raster_probe': (c_int, [c_void_p]),
     'dwg_gemm_set_lane': (c_int, [c_int]),
     'dwg_conv2d_nhwc_f16': (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_int] * 11 +
                              [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -234,6 +234,7 @@ int dwg_gemm_last_pair(void);
 /* Split-K scratch lane (0 or 1) used by the launches that follow: GEMMs enqueued on two streams that may run
  * concurrently (ControlNet beside the UNet encoder, dwg/diffusion/guidance.py) must use different lanes. */
 int dwg_gemm_set_lane(int lane);
+int dwg_raster_probe(void* dev_u64_tiles_x6);   /* debug per-tile timeline of the forward render, NULL = off; csrc/raster_fwd.cu */
 int dwg_gemm_trace(void* dev_u64x8);   /* debug timeline of CTA 0 (globaltimer ns), NULL = off; see csrc/gemm_tcgen05.cu */
 int dwg_gemm_last_key(int* out6);   /* planner key of the last launch: m_tiles, nz, N, k-iterations, epilogue kind, has_residual */
 
