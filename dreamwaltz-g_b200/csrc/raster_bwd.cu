@@ -1,10 +1,10 @@
 // Rasteriser backward (R12): per-tile back-to-front replay + per-Gaussian chain rule.
 //
 // Blend backward: one 64-thread CTA per 8x8 quadrant of a tile (same split as the forward render, see raster_fwd.cu),
-// one pixel per thread, instance records streamed in reverse with double-buffered bulk TMA copies.  Per-instance
-// gradient contributions are first reduced inside each warp (an 8x4 pixel block) with shuffles (skipped entirely when
-// no lane of the warp blends the instance), then accumulated across the CTA's warps in shared memory, and only ONE
-// global atomic per (instance, component) leaves the CTA.
+// one pixel per thread, instance records streamed in reverse with double-buffered bulk TMA copies.  Each pixel replays
+// only the instances it blended (per-lane lists built by a cheap power-test pass); its gradient contributions are
+// accumulated per chunk slot in per-warp shared memory with plain read-modify-writes (lanes that meet on one instance
+// take turns; the benchmark's splats cover 1-4 pixels), and only ONE global atomic per (instance, component) leaves the CTA.
 // Upstream issues one global atomic per (pixel, instance, component).
 //
 // Preprocess backward: conic -> cov2D -> cov3D -> (scale, quaternion), mean2D / depth -> mean3D.
@@ -16,45 +16,6 @@ namespace raster {
 constexpr int NG = 10;      // mean2D.xy, conic.xyz, opacity, colour.rgb, depth
 constexpr int BWD_BATCH = 2;
 
-// Sum each of 10 per-lane values over the 32 lanes with 12 shuffles: at every butterfly step a lane keeps half
-// of the values it still holds and hands the other half to its partner, so the value count halves as the lane
-// span doubles (5 + 3 + 2 + 1 + 1 shuffles).  Returns the complete sum of value `q` (q = -1: this lane owns none;
-// every value is owned by exactly one even lane).
-__device__ __forceinline__ float reduce10(const float (&v)[NG], int lane, int& q) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-    float a[5];
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        const float send = b4 ? v[i] : v[5 + i], keep = b4 ? v[5 + i] : v[i];
-        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    float b[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const float hi = (i < 2) ? a[3 + (i < 2 ? i : 0)] : 0.f;
-        const float send = b3 ? a[i] : hi, keep = b3 ? hi : a[i];
-        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    float c[2];
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        const float hi = (i < 1) ? b[2] : 0.f;
-        const float send = b2 ? b[i] : hi, keep = b2 ? hi : b[i];
-        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    float d;
-    {
-        const float send = b1 ? c[0] : c[1], keep = b1 ? c[1] : c[0];
-        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    // which value this lane ended up with: groups {0..4 | 5..9} -> {0,1,2 | 3,4,-} -> {0,1 | 2,-} -> {0 | 1}
-    const int s5 = b3 ? (3 + (b1 ? 1 : 0)) : ((b2 ? 2 : 0) + (b1 ? 1 : 0));
-    const bool valid = !(b2 && (b3 || b1)) && !(lane & 1);
-    q = valid ? (b4 ? 5 : 0) + s5 : -1;
-    return d;
-}
-
 __global__ void __launch_bounds__(QPIX)
 render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const Rec* __restrict__ recs,
                   float bg0, float bg1, float bg2, const float* __restrict__ bg_dev,
@@ -65,11 +26,11 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                   float* __restrict__ g_mean2D /* [N,3] */, float4* __restrict__ g_conic_depth /* [N] */,
                   float* __restrict__ g_opacity, float* __restrict__ g_color /* [N,3] */) {
     __shared__ __align__(128) Rec s_rec[2][CHUNK];
-    __shared__ float s_acc[CHUNK][NG + 1];
+    __shared__ float s_acc[QPIX / 32][CHUNK][NG + 1];          // per warp: no cross-warp races, no atomics
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_max[QPIX / 32];
     __shared__ uint8_t s_list[QPIX / 32][CHUNK];              // per warp: instances of the chunk touching the warp's block
-    __shared__ uint8_t s_surv[QPIX / 32][CHUNK];              // ... that at least one pixel of the block blends
+    __shared__ uint8_t s_pix[QPIX / 32][CHUNK * 32];          // per lane ([slot][lane]): instances this pixel blends
     if (bg_dev) { bg0 = bg_dev[0]; bg1 = bg_dev[1]; bg2 = bg_dev[2]; }
     const int tile = (blockIdx.y >> 1) * gx + (blockIdx.x >> 1);
     const int lane = threadIdx.x & 31;
@@ -107,7 +68,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     uint32_t mx = last_contributor;
     for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
-    for (int i = threadIdx.x; i < CHUNK * (NG + 1); i += QPIX) (&s_acc[0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < (QPIX / 32) * CHUNK * (NG + 1); i += QPIX) (&s_acc[0][0][0])[i] = 0.f;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -133,7 +94,8 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
     const float sx0 = (float)bx0, sx1 = sx0 + 7.0f;
     const float sy0 = (float)by0, sy1 = sy0 + 3.0f;
     uint8_t* my_list = s_list[threadIdx.x >> 5];
-    uint8_t* my_surv = s_surv[threadIdx.x >> 5];
+    uint8_t* my_pix = s_pix[threadIdx.x >> 5];
+    float* my_acc = &s_acc[threadIdx.x >> 5][0][0];
     for (int it = 0; it < rounds; it++) {
         const int c = rounds - 1 - it;
         const int buf = it & 1;
@@ -146,14 +108,12 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
         }
         mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1));
         const int cnt = chunk_cnt(c);
-        // Three warp-uniform passes per chunk: A. cull against the block's rectangle -> ordered per-warp index list; B. power
-        // test + "index < this pixel's last contributor" at every pixel, four independent instances at a time; the
-        // instances kept by at least one lane (survivors) are compacted again; C. survivors replayed back to front,
-        // BWD_BATCH at a time: the alphas (the long, position-only chain) are evaluated together, the short T / accumulator
-        // recurrences run in order, and the 10 per-instance sums are reduced across the warp with a 12-shuffle "split"
-        // butterfly (reduce10) instead of 10 x 5 shuffles; the lanes that end up owning a sum add it to shared memory.
-        // (Per-lane lists as in the forward render were measured slower here: every (pixel, instance) pair then needs ten
-        // shared-memory float atomics, which are CAS loops on this architecture.)
+        // Three passes per chunk (same structure as the forward render, raster_fwd.cu): A. cull against the block's rectangle
+        // -> ordered per-warp index list; B. power test + "index < this pixel's last contributor" at every pixel, each lane
+        // appends the instances IT blends to its own list; C. every lane replays its own list back to front, BWD_BATCH at a
+        // time (the alphas -- the long, position-only chain -- are evaluated together, the short T / accumulator
+        // recurrences run in order) and adds its ten partial sums to the warp's shared-memory accumulators.  The trip
+        // count of C is the longest per-pixel list of the block, not the number of instances touching the block.
         int m = 0;
         for (int j0 = 0; j0 < cnt; j0 += 32) {
             const int jl = j0 + lane;
@@ -167,7 +127,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
             m += __popc(mask);
         }
         __syncwarp();
-        int ms = 0;
+        int mine = 0;
         const int lc_rel = (int)min(last_contributor, (uint32_t)0x7fffffff) - c * CHUNK;      // slots < lc_rel contribute to this pixel
         for (int i0 = 0; i0 < m; i0 += 4) {
             bool keep[4];
@@ -186,30 +146,25 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const bool any = __any_sync(0xffffffffu, keep[u]);
-                if (any && lane == 0) my_surv[ms] = (uint8_t)jj[u];
-                ms += any ? 1 : 0;
+                if (keep[u]) { my_pix[mine * 32 + lane] = (uint8_t)jj[u]; mine++; }
             }
         }
-        __syncwarp();
-        for (int i0 = ms - 1; i0 >= 0; i0 -= BWD_BATCH) {
+        const int longest = __reduce_max_sync(0xffffffffu, mine);
+        for (int it = 0; it < longest; it += BWD_BATCH) {
             int jb[BWD_BATCH];
             bool ok[BWD_BATCH];
             float al[BWD_BATCH], Gv[BWD_BATCH], dxv[BWD_BATCH], dyv[BWD_BATCH];
             Rec rcs[BWD_BATCH];
 #pragma unroll
             for (int u = 0; u < BWD_BATCH; u++) {
-                jb[u] = my_surv[max(i0 - u, 0)];
+                const int pos = mine - 1 - it - u;                 // back to front
+                jb[u] = pos >= 0 ? (int)my_pix[pos * 32 + lane] : 0;
                 rcs[u] = s_rec[buf][jb[u]];
-                ok[u] = eval_alpha_nb(rcs[u], pxf, pyf, al[u], Gv[u], dxv[u], dyv[u]) & (i0 - u >= 0) & (jb[u] < lc_rel);
+                ok[u] = eval_alpha_nb(rcs[u], pxf, pyf, al[u], Gv[u], dxv[u], dyv[u]) & (pos >= 0);
             }
 #pragma unroll
             for (int u = 0; u < BWD_BATCH; u++) {
-                const unsigned mk = __ballot_sync(0xffffffffu, ok[u]);
-                if (mk == 0u) continue;                         // warp-uniform: nobody in this block blends the instance
                 float v[NG];
-#pragma unroll
-                for (int q = 0; q < NG; q++) v[q] = 0.f;
                 if (ok[u]) {
                     const Rec& rc = rcs[u];
                     const float alpha = al[u], G = Gv[u], dx = dxv[u], dy = dyv[u];
@@ -223,10 +178,8 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                     dL_dalpha_ += (rc.g - accum_g) * dLp1;
                     accum_b = last_alpha * last_b + (1.f - last_alpha) * accum_b; last_b = rc.b;
                     dL_dalpha_ += (rc.b - accum_b) * dLp2;
-                    v[6] = dchannel_dcolor * dLp0; v[7] = dchannel_dcolor * dLp1; v[8] = dchannel_dcolor * dLp2;
                     accum_d = last_alpha * last_depth + (1.f - last_alpha) * accum_d; last_depth = rc.depth;
                     dL_dalpha_ += (rc.depth - accum_d) * dLd;
-                    v[9] = dchannel_dcolor * dLd;
                     accum_a = last_alpha + (1.f - last_alpha) * accum_a;
                     dL_dalpha_ += (1.f - accum_a) * dLa;
                     dL_dalpha_ *= T;
@@ -242,10 +195,24 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
                     v[3] = -0.5f * gdx * dy * dL_dG;
                     v[4] = -0.5f * gdy * dy * dL_dG;
                     v[5] = G * dL_dalpha_;
+                    v[6] = dchannel_dcolor * dLp0; v[7] = dchannel_dcolor * dLp1; v[8] = dchannel_dcolor * dLp2;
+                    v[9] = dchannel_dcolor * dLd;
                 }
-                int q;
-                const float tot = reduce10(v, lane, q);
-                if (q >= 0) atomicAdd(&s_acc[jb[u]][q], tot);
+                // Accumulate into this WARP's per-slot sums with plain read-modify-writes (shared-memory float atomics are
+                // CAS loops): lanes that hold the same instance in this step take turns, one per round -- splats cover
+                // 1-4 pixels, so one round is the common case.
+                const int key = ok[u] ? jb[u] : (CHUNK + lane);
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                const int rank = __popc(peers & ((1u << lane) - 1u));
+                const int nround = __reduce_max_sync(0xffffffffu, __popc(peers));
+                for (int r = 0; r < nround; r++) {
+                    if (ok[u] && rank == r) {
+                        float* acc = my_acc + jb[u] * (NG + 1);
+#pragma unroll
+                        for (int q = 0; q < NG; q++) acc[q] += v[q];
+                    }
+                    __syncwarp();
+                }
             }
         }
         __syncthreads();            // chunk finished by every warp: flush, and release buffer `buf`
@@ -254,7 +221,11 @@ render_bwd_kernel(int H, int W, int gx, const uint2* __restrict__ ranges, const 
             float a[NG];
             bool any = false;
 #pragma unroll
-            for (int q = 0; q < NG; q++) { a[q] = s_acc[j][q]; s_acc[j][q] = 0.f; any |= (a[q] != 0.f); }
+            for (int q = 0; q < NG; q++) {
+                a[q] = s_acc[0][j][q] + s_acc[1][j][q];
+                s_acc[0][j][q] = 0.f; s_acc[1][j][q] = 0.f;
+                any |= (a[q] != 0.f);
+            }
             if (any) {
                 atomicAdd(&g_mean2D[3 * (size_t)gid], a[0]);
                 atomicAdd(&g_mean2D[3 * (size_t)gid + 1], a[1]);
