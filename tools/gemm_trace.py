@@ -31,3 +31,37 @@ for M, N, K, res in ((128, 32, 64, False), (8192, 320, 320, False), (8192, 320, 
     L.dwg_gemm_trace(None)
     med = [sorted(r[i] for r in rows)[len(rows) // 2] for i in range(13)]
     print(f'M{M} N{N} K{K} res={int(res)}: ' + '  '.join(f'{n}={v / 1e3:.2f}us' for n, v in zip(names, med)))
+
+# ---- weight-bound convolutions (2 x 8 x 8 and 2 x 16 x 16, 1280 channels): timeline of CTA 0 + warm / cold launch times
+plan = (__import__('ctypes').c_int * 3)()
+for Ni, H, C in ((2, 8, 1280), (2, 16, 1280), (2, 32, 640)):
+    x = torch.randn(Ni, H, H, C, device=dev).half()
+    ws = [(torch.randn(C, 3, 3, C, device=dev) * 0.02).half() for _ in range(8)]
+    bias = torch.randn(C, device=dev)
+    for _ in range(3):
+        ops.conv2d_nhwc(x, ws[0], bias=bias)
+    L.dwg_gemm_last_plan(plan)
+    L.dwg_gemm_trace(tr.data_ptr())
+    rows = []
+    for _ in range(5):
+        ops.conv2d_nhwc(x, ws[0], bias=bias)
+        ops.conv2d_nhwc(x, ws[0], bias=bias)
+        torch.cuda.synchronize()
+        t = tr.cpu().tolist()
+        rows.append([t[i] - t[0] for i in range(13)])
+    L.dwg_gemm_trace(None)
+    med = [sorted(r[i] for r in rows)[len(rows) // 2] for i in range(13)]
+
+    def timed(fn, n=40):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / n
+    warm = timed(lambda i: ops.conv2d_nhwc(x, ws[0], bias=bias))
+    cold = timed(lambda i: ops.conv2d_nhwc(x, ws[i % 8], bias=bias))
+    print(f'conv3x3 {Ni}x{H}x{H} {C}->{C} plan BN={plan[0]} ks={plan[1]} pair={L.dwg_gemm_last_pair()} halo={L.dwg_gemm_last_halo()}: '
+          f'warm {warm:.1f} us, cold-weights {cold:.1f} us (back-to-back);  ' + '  '.join(f'{n}={v / 1e3:.2f}us' for n, v in zip(names, med)))
