@@ -498,6 +498,312 @@ mlp_reduce_kernel(const float* __restrict__ partial, int nparts, const float* __
     }
 }
 
+// =====================================================================================================================
+// Tensor-core forward (tcgen05, sm_100a).  The hidden width is 64: one layer of a 128-point tile is a 128 x 64 x 64 GEMM.
+//   * fp32 accuracy on fp16 tensor cores: every operand is split x = hi + lo (two fp16 values, 22 mantissa bits) and a
+//     layer is the three products  A_hi W_hi + A_hi W_lo + A_lo W_hi  accumulated in fp32 in TMEM (the dropped lo x lo
+//     term is 2^-22 relative): 12 MMAs (M128 N64 K16) per 64-wide layer.  The 32 grid features (|x| can be ~1e-4 right
+//     after initialisation, where an fp16 lo part would be subnormal) are scaled by 2^10 before the split and the
+//     accumulator by 2^-10 -- both exact.
+//   * all weights of both MLPs live in shared memory for the whole kernel as 128B-swizzled K-major fp16 tiles (hi + lo,
+//     104 KB); a thread owns one point (= one TMEM lane): it reads its accumulator row with tcgen05.ld, applies bias +
+//     activation, stores the fp32 activations for the backward (same [layer][feature][point] layout as the SIMT kernel)
+//     and writes the split row straight into the swizzled A-operand tile of the next layer.
+//   * two independent 128-point tiles per CTA (warps 0-3 / 4-7, one issuing lane each in warps 8 / 9): while one tile is
+//     in its epilogue the tensor pipe works on the other.
+constexpr int PT = 128;
+constexpr float kEncScale = 1024.0f, kEncInv = 1.0f / 1024.0f;
+constexpr uint32_t TC_TILE64 = 64 * 128, TC_TILE16 = 16 * 128, TC_ATILE = PT * 128;
+// byte offsets of the weight tiles inside one precision half
+constexpr uint32_t TW_S1 = 0, TW_S2 = TW_S1 + TC_TILE64, TW_S3 = TW_S2 + TC_TILE64, TW_D0 = TW_S3 + TC_TILE16, TW_D1 = TW_D0 + TC_TILE64,
+                   TW_D2 = TW_D1 + TC_TILE64, TW_D3 = TW_D2 + TC_TILE64, TW_DH = TW_D3 + TC_TILE64, TW_HALF = TW_DH + TC_TILE16;
+constexpr size_t kTcFwdSmem = 1024 + 2 * (size_t)TW_HALF + 2 * 2 * (size_t)TC_ATILE + sizeof(float) * (6 * HID + 32) + 64;
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+}
+// K-major, 128B-swizzled operand tile [rows][64 fp16]: 8-row groups 1024 B apart (same descriptor as csrc/gemm_tcgen05.cu)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t tc_idesc(int N) { return (1u << 4) | kIdescFmtAB | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(PT >> 4) << 24); }
+
+// byte offset of element (row, k) inside a swizzled tile
+__device__ __forceinline__ uint32_t tc_off(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+// W [O][K] fp32 row-major -> hi / lo tiles with `rows` rows (rows >= O, zero padded; K <= 64, zero padded)
+__device__ __forceinline__ void tc_fill_weight(uint8_t* hi, uint8_t* lo, const float* __restrict__ W, int O, int K, int rows, int tid, int nthr) {
+    for (int i = tid; i < rows * 64; i += nthr) {
+        const int o = i >> 6, k = i & 63;
+        const float w = (o < O && k < K) ? W[o * K + k] : 0.f;
+        const __half h = __float2half_rn(w);
+        const __half l = __float2half_rn(w - __half2float(h));
+        const uint32_t off = tc_off(o, k);
+        *reinterpret_cast<__half*>(hi + off) = h;
+        *reinterpret_cast<__half*>(lo + off) = l;
+    }
+}
+// one thread's row of NV values (NV = 32 or 64) -> split hi / lo -> its 128-byte row of the swizzled A tiles
+template <int NV>
+__device__ __forceinline__ void tc_store_row(uint8_t* Ahi, uint8_t* Alo, int r, const float (&v)[64]) {
+    uint8_t* rh = Ahi + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* rl = Alo + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int ch = 0; ch < NV / 8; ch++) {
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float x0 = v[ch * 8 + 2 * i], x1 = v[ch * 8 + 2 * i + 1];
+            ph[i] = pack_act2(x0, x1);
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&ph[i]));
+            pl[i] = pack_act2(x0 - hf.x, x1 - hf.y);
+        }
+        const int sw = ((ch ^ (r & 7)) & 7) << 4;
+        *reinterpret_cast<uint4*>(rh + sw) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4*>(rl + sw) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+}
+// the issuing lane: D[tmem] = A_hi W_hi + A_hi W_lo + A_lo W_hi over `ksteps` K = 16 steps, N output columns
+__device__ __forceinline__ void tc_issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, int ksteps, int N) {
+    const uint32_t idesc = tc_idesc(N);
+    const uint64_t dah = tc_desc(a_hi), dal = tc_desc(a_lo), dwh = tc_desc(w_hi), dwl = tc_desc(w_lo);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < ksteps; ks++) { tc_mma(tmem_d, dah + 2u * ks, dwh + 2u * ks, idesc, acc); acc = 1; }
+    for (int ks = 0; ks < ksteps; ks++) tc_mma(tmem_d, dah + 2u * ks, dwl + 2u * ks, idesc, 1);
+    for (int ks = 0; ks < ksteps; ks++) tc_mma(tmem_d, dal + 2u * ks, dwh + 2u * ks, idesc, 1);
+}
+
+__global__ void __launch_bounds__(320, 1)
+mlp_fwd_tc_kernel(const FwdArgs a) {
+    extern __shared__ uint8_t tc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* Whi = smem;
+    uint8_t* Wlo = Whi + TW_HALF;
+    uint8_t* Abase = Wlo + TW_HALF;                               // group g: hi at g * 2 * TC_ATILE, lo right behind
+    float* bias = reinterpret_cast<float*>(Abase + 4 * TC_ATILE);  // bs1, bs2, bd0 (effective), bd1, bd2, bd3 [64 each], bs3 [16], bdh [16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias + 6 * HID + 32);
+    uint64_t* acc_full = bars;                                     // [2]
+    uint64_t* a_ready = bars + 2;                                  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* W = a.params;
+
+    tc_fill_weight(Whi + TW_S1, Wlo + TW_S1, W + S1W, HID, ENC, 64, tid, 320);
+    tc_fill_weight(Whi + TW_S2, Wlo + TW_S2, W + S2W, HID, HID, 64, tid, 320);
+    tc_fill_weight(Whi + TW_S3, Wlo + TW_S3, W + S3W, 4, HID, 16, tid, 320);
+    tc_fill_weight(Whi + TW_D0, Wlo + TW_D0, W + D0W, HID, ENC, 64, tid, 320);
+    tc_fill_weight(Whi + TW_D1, Wlo + TW_D1, W + D1W, HID, HID, 64, tid, 320);
+    tc_fill_weight(Whi + TW_D2, Wlo + TW_D2, W + D2W, HID, HID, 64, tid, 320);
+    tc_fill_weight(Whi + TW_D3, Wlo + TW_D3, W + D3W, HID, HID, 64, tid, 320);
+    tc_fill_weight(Whi + TW_DH, Wlo + TW_DH, W + WPW, 3, HID, 3, tid, 320);                  // rows 0-2: warp head
+    for (int i = tid; i < 13 * 64; i += 320) {                                               // rows 3-5: scaling head, 6-15: zero
+        const int o = 3 + (i >> 6), k = i & 63;
+        const float w = o < 6 ? W[SCW + (o - 3) * HID + k] : 0.f;
+        const __half h = __float2half_rn(w);
+        const uint32_t off = tc_off(o, k);
+        *reinterpret_cast<__half*>(Whi + TW_DH + off) = h;
+        *reinterpret_cast<__half*>(Wlo + TW_DH + off) = __float2half_rn(w - __half2float(h));
+    }
+    if (tid < HID) {
+        bias[tid] = W[S1B + tid]; bias[HID + tid] = W[S2B + tid];
+        float b = W[D0B + tid];
+        for (int j = 0; j < POSE; j++) b = fmaf(a.w_pose[tid * POSE + j], a.pose[j], b);
+        bias[2 * HID + tid] = b;
+        bias[3 * HID + tid] = W[D1B + tid]; bias[4 * HID + tid] = W[D2B + tid]; bias[5 * HID + tid] = W[D3B + tid];
+    }
+    if (tid < 16) {
+        bias[6 * HID + tid] = tid < 4 ? W[S3B + tid] : 0.f;
+        bias[6 * HID + 16 + tid] = tid < 3 ? W[WPB + tid] : (tid < 6 ? W[SCB + tid - 3] : 0.f);
+    }
+    if (tid == 0) {
+        tc_mbar_init(&acc_full[0], 1); tc_mbar_init(&acc_full[1], 1);
+        tc_mbar_init(&a_ready[0], PT); tc_mbar_init(&a_ready[1], PT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(tmem_slot)), "n"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the weight tiles were written through the generic proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t ntiles = (a.N + PT - 1) / PT;
+    if (warp >= 8) {
+        // ---------------- issuing lanes: warp 8 -> tile group 0, warp 9 -> tile group 1
+        const int g = warp - 8;
+        if (lane == 0) {
+            const uint32_t a_hi = tc_smem_u32(Abase + g * 2 * TC_ATILE), a_lo = a_hi + TC_ATILE;
+            const uint32_t whi = tc_smem_u32(Whi), wlo = tc_smem_u32(Wlo);
+            const uint32_t tm = tmem_base + (uint32_t)(g * 64);
+            uint32_t par = 0;
+            for (int64_t it = blockIdx.x; 2 * it + g < ntiles; it += gridDim.x) {
+                const int64_t p0 = (2 * it + g) * PT;
+                const int nl = p0 < a.Nu ? 8 : 3;
+                for (int l = 0; l < nl; l++) {
+                    tc_mbar_wait(&a_ready[g], par);
+                    par ^= 1u;
+                    tc_fence_after();
+                    uint32_t off; int ks, N;
+                    switch (l) {
+                        case 0: off = TW_S1; ks = 2; N = 64; break;
+                        case 1: off = TW_S2; ks = 4; N = 64; break;
+                        case 2: off = TW_S3; ks = 4; N = 16; break;
+                        case 3: off = TW_D0; ks = 2; N = 64; break;
+                        case 4: off = TW_D1; ks = 4; N = 64; break;
+                        case 5: off = TW_D2; ks = 4; N = 64; break;
+                        case 6: off = TW_D3; ks = 4; N = 64; break;
+                        default: off = TW_DH; ks = 4; N = 16; break;
+                    }
+                    tc_issue_layer(tm, a_hi, a_lo, whi + off, wlo + off, ks, N);
+                    tc_commit(&acc_full[g]);
+                }
+            }
+        }
+    } else {
+        // ---------------- point threads: group g = warp / 4, TMEM lane = row = 32 * (warp % 4) + lane
+        const int g = warp >> 2, r = ((warp & 3) << 5) + lane;
+        uint8_t* Ahi = Abase + g * 2 * TC_ATILE;
+        uint8_t* Alo = Ahi + TC_ATILE;
+        const uint32_t tm = tmem_base + (uint32_t)(g * 64) + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t par = 0;
+        float v[64];
+        auto publish = [&]() {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            tc_mbar_arrive(&a_ready[g]);
+        };
+        auto load_enc = [&](int64_t p, bool ok) {
+            if (ok) {
+                const float4* e = reinterpret_cast<const float4*>(a.enc + p * ENC);
+#pragma unroll
+                for (int j = 0; j < ENC / 4; j++) {
+                    const float4 t = __ldg(e + j);
+                    v[4 * j] = t.x * kEncScale; v[4 * j + 1] = t.y * kEncScale; v[4 * j + 2] = t.z * kEncScale; v[4 * j + 3] = t.w * kEncScale;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < ENC; j++) v[j] = 0.f;
+            }
+            tc_store_row<ENC>(Ahi, Alo, r, v);
+        };
+        auto wait_acc = [&](bool both) {
+            tc_mbar_wait(&acc_full[g], par);
+            par ^= 1u;
+            tc_fence_after();
+            float t0[32];
+            tc_ld32(tm, t0);
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = t0[j];
+            if (both) {
+                tc_ld32(tm + 32u, t0);
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[32 + j] = t0[j];
+            }
+        };
+        // hidden layer epilogue: v <- act(v * scale + b); save; write the next A tile
+        auto hidden = [&](const float* b, float scale, int act, float* gsave, int64_t Nrow, bool ok) {
+#pragma unroll
+            for (int o = 0; o < HID; o++) v[o] = act_fn(fmaf(v[o], scale, b[o]), act);
+            if (gsave && ok) {
+#pragma unroll
+                for (int o = 0; o < HID; o++) gsave[o * Nrow] = v[o];
+            }
+            tc_store_row<HID>(Ahi, Alo, r, v);
+        };
+        for (int64_t it = blockIdx.x; 2 * it + g < ntiles; it += gridDim.x) {
+            const int64_t p0 = (2 * it + g) * PT, p = p0 + r;
+            const bool valid = p < a.N;
+            load_enc(p, valid);
+            publish();
+            wait_acc(true);
+            hidden(bias, kEncInv, ACT_RELU, a.acts_s ? a.acts_s + p : nullptr, a.Np, valid);
+            publish();
+            wait_acc(true);
+            hidden(bias + HID, 1.0f, ACT_RELU, a.acts_s ? a.acts_s + HID * a.Np + p : nullptr, a.Np, valid);
+            publish();
+            wait_acc(false);
+            if (valid) {
+                const float* b3 = bias + 6 * HID;
+                a.opac[p] = p < a.Nu ? sigmoidf(v[0] + b3[0]) : 1.0f;      // mesh-bound Gaussians: opacity fixed to 1 (avatar.py:1287-1288)
+                a.colors[p * 3] = sigmoidf(v[1] + b3[1]); a.colors[p * 3 + 1] = sigmoidf(v[2] + b3[2]); a.colors[p * 3 + 2] = sigmoidf(v[3] + b3[3]);
+            }
+            if (p0 < a.Nu) {
+                const bool vu = p < a.Nu;
+                load_enc(p, vu);
+                publish();
+                wait_acc(true);
+                hidden(bias + 2 * HID, kEncInv, ACT_LRELU, a.acts_d ? a.acts_d + p : nullptr, a.Nup, vu);
+                publish();
+#pragma unroll 1
+                for (int l = 1; l <= 3; l++) {
+                    wait_acc(true);
+                    hidden(bias + (2 + l) * HID, 1.0f, ACT_LRELU, a.acts_d ? a.acts_d + (int64_t)l * HID * a.Nup + p : nullptr, a.Nup, vu);
+                    publish();
+                }
+                wait_acc(false);
+                if (vu) {
+                    const float* bh = bias + 6 * HID + 16;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        a.pos_out[p * 3 + c] = a.positions[p * 3 + c] + (v[c] + bh[c]) * a.init_offset;
+                        a.scales[p * 3 + c] = fminf(expf(v[3 + c] + bh[3 + c]) * a.init_scale, a.max_scale);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
+}
+
+static int g_mlp_tc = 1;      // debug switch (dwg_avatar_mlp_set_tc): 0 = the fp32 SIMT forward
+
 static int g_sms = 0;
 static int num_sms() {
     if (!g_sms) {
@@ -518,6 +824,8 @@ using namespace dwg;
 using namespace dwg::mlp;
 
 extern "C" int64_t dwg_avatar_mlp_param_count(void) { return NPARAM; }
+/* Debug / A-B switch: 1 (default) = tensor-core kernels, 0 = the fp32 SIMT kernels. */
+extern "C" int dwg_avatar_mlp_set_tc(int on) { g_mlp_tc = on ? 1 : 0; return DWG_OK; }
 extern "C" int64_t dwg_avatar_mlp_scratch_bytes(void) { return (int64_t)sizeof(float) * NPARAM * num_sms(); }
 
 // Forward of both MLPs + activations for N Gaussians (the first Nu are unconstrained: both nets; the
@@ -538,6 +846,14 @@ extern "C" int dwg_avatar_mlp_fwd(const float* enc, const float* positions, cons
     a.colors = colors; a.opac = opac; a.pos_out = pos_out; a.scales = scales; a.acts_s = acts_s; a.acts_d = acts_d;
     a.N = N; a.Nu = Nu; a.Np = (N + 3) & ~(int64_t)3; a.Nup = (Nu + 3) & ~(int64_t)3;
     a.init_offset = init_offset; a.init_scale = init_scale; a.max_scale = max_scale;
+    if (g_mlp_tc) {
+        static bool attr_tc = false;
+        if (!attr_tc) { cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcFwdSmem); attr_tc = true; }
+        const int64_t npairs = ((N + PT - 1) / PT + 1) / 2;
+        const int grid = (int)(npairs < num_sms() ? npairs : num_sms());
+        mlp_fwd_tc_kernel<<<grid, 320, kTcFwdSmem, (cudaStream_t)stream>>>(a);
+        return check_launch("dwg_avatar_mlp_fwd");
+    }
     const int64_t ntiles = (N + P - 1) / P;
     const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
     mlp_fwd_kernel<<<grid, P, kFwdSmem, (cudaStream_t)stream>>>(a);

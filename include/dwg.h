@@ -207,6 +207,7 @@ int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
  *   params) and g_w_pose [64,63]; null output-gradient pointers mean zero; scratch =
  *   dwg_avatar_mlp_scratch_bytes() bytes. */
 int64_t dwg_avatar_mlp_param_count(void);
+int dwg_avatar_mlp_set_tc(int on);   /* debug / A-B switch: 1 (default) = tcgen05 kernels (fp16 hi+lo split, fp32 accuracy), 0 = fp32 SIMT kernels */
 int64_t dwg_avatar_mlp_scratch_bytes(void);
 int dwg_avatar_mlp_fwd(const float* enc, const float* positions, const float* params, const float* w_pose, const float* body_pose,
                        float* colors, float* opac, float* pos_out, float* scales, float* acts_s, float* acts_d,
