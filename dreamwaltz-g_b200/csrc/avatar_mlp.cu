@@ -509,8 +509,9 @@ mlp_reduce_kernel(const float* __restrict__ partial, int nparts, const float* __
 //     104 KB); a thread owns one point (= one TMEM lane): it reads its accumulator row with tcgen05.ld, applies bias +
 //     activation, stores the fp32 activations for the backward (same [layer][feature][point] layout as the SIMT kernel)
 //     and writes the split row straight into the swizzled A-operand tile of the next layer.
-//   * two independent 128-point tiles per CTA (warps 0-3 / 4-7, one issuing lane each in warps 8 / 9): while one tile is
-//     in its epilogue the tensor pipe works on the other.
+//   * two independent 128-point tiles per CTA (warps 0-3 / 4-7): while one tile is
+//     in its epilogue the tensor pipe works on the other.  No dedicated issuing warp: the first thread of a group issues
+//     its MMAs once all 128 rows of the A tile have arrived (256 threads per CTA: 255 registers per thread, no spills).
 constexpr int PT = 128;
 constexpr float kEncScale = 1024.0f, kEncInv = 1.0f / 1024.0f;
 constexpr uint32_t TC_TILE64 = 64 * 128, TC_TILE16 = 16 * 128, TC_ATILE = PT * 128;
@@ -615,7 +616,7 @@ __device__ __forceinline__ void tc_issue_layer(uint32_t tmem_d, uint32_t a_hi, u
     for (int ks = 0; ks < ksteps; ks++) tc_mma(tmem_d, dal + 2u * ks, dwh + 2u * ks, idesc, 1);
 }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(256, 1)
 mlp_fwd_tc_kernel(const FwdArgs a) {
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -630,15 +631,15 @@ mlp_fwd_tc_kernel(const FwdArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* W = a.params;
 
-    tc_fill_weight(Whi + TW_S1, Wlo + TW_S1, W + S1W, HID, ENC, 64, tid, 320);
-    tc_fill_weight(Whi + TW_S2, Wlo + TW_S2, W + S2W, HID, HID, 64, tid, 320);
-    tc_fill_weight(Whi + TW_S3, Wlo + TW_S3, W + S3W, 4, HID, 16, tid, 320);
-    tc_fill_weight(Whi + TW_D0, Wlo + TW_D0, W + D0W, HID, ENC, 64, tid, 320);
-    tc_fill_weight(Whi + TW_D1, Wlo + TW_D1, W + D1W, HID, HID, 64, tid, 320);
-    tc_fill_weight(Whi + TW_D2, Wlo + TW_D2, W + D2W, HID, HID, 64, tid, 320);
-    tc_fill_weight(Whi + TW_D3, Wlo + TW_D3, W + D3W, HID, HID, 64, tid, 320);
-    tc_fill_weight(Whi + TW_DH, Wlo + TW_DH, W + WPW, 3, HID, 3, tid, 320);                  // rows 0-2: warp head
-    for (int i = tid; i < 13 * 64; i += 320) {                                               // rows 3-5: scaling head, 6-15: zero
+    tc_fill_weight(Whi + TW_S1, Wlo + TW_S1, W + S1W, HID, ENC, 64, tid, 256);
+    tc_fill_weight(Whi + TW_S2, Wlo + TW_S2, W + S2W, HID, HID, 64, tid, 256);
+    tc_fill_weight(Whi + TW_S3, Wlo + TW_S3, W + S3W, 4, HID, 16, tid, 256);
+    tc_fill_weight(Whi + TW_D0, Wlo + TW_D0, W + D0W, HID, ENC, 64, tid, 256);
+    tc_fill_weight(Whi + TW_D1, Wlo + TW_D1, W + D1W, HID, HID, 64, tid, 256);
+    tc_fill_weight(Whi + TW_D2, Wlo + TW_D2, W + D2W, HID, HID, 64, tid, 256);
+    tc_fill_weight(Whi + TW_D3, Wlo + TW_D3, W + D3W, HID, HID, 64, tid, 256);
+    tc_fill_weight(Whi + TW_DH, Wlo + TW_DH, W + WPW, 3, HID, 3, tid, 256);                  // rows 0-2: warp head
+    for (int i = tid; i < 13 * 64; i += 256) {                                               // rows 3-5: scaling head, 6-15: zero
         const int o = 3 + (i >> 6), k = i & 63;
         const float w = o < 6 ? W[SCW + (o - 3) * HID + k] : 0.f;
         const __half h = __float2half_rn(w);
@@ -662,7 +663,7 @@ mlp_fwd_tc_kernel(const FwdArgs a) {
         tc_mbar_init(&a_ready[0], PT); tc_mbar_init(&a_ready[1], PT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(tmem_slot)), "n"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -673,38 +674,7 @@ mlp_fwd_tc_kernel(const FwdArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     const int64_t ntiles = (a.N + PT - 1) / PT;
-    if (warp >= 8) {
-        // ---------------- issuing lanes: warp 8 -> tile group 0, warp 9 -> tile group 1
-        const int g = warp - 8;
-        if (lane == 0) {
-            const uint32_t a_hi = tc_smem_u32(Abase + g * 2 * TC_ATILE), a_lo = a_hi + TC_ATILE;
-            const uint32_t whi = tc_smem_u32(Whi), wlo = tc_smem_u32(Wlo);
-            const uint32_t tm = tmem_base + (uint32_t)(g * 64);
-            uint32_t par = 0;
-            for (int64_t it = blockIdx.x; 2 * it + g < ntiles; it += gridDim.x) {
-                const int64_t p0 = (2 * it + g) * PT;
-                const int nl = p0 < a.Nu ? 8 : 3;
-                for (int l = 0; l < nl; l++) {
-                    tc_mbar_wait(&a_ready[g], par);
-                    par ^= 1u;
-                    tc_fence_after();
-                    uint32_t off; int ks, N;
-                    switch (l) {
-                        case 0: off = TW_S1; ks = 2; N = 64; break;
-                        case 1: off = TW_S2; ks = 4; N = 64; break;
-                        case 2: off = TW_S3; ks = 4; N = 16; break;
-                        case 3: off = TW_D0; ks = 2; N = 64; break;
-                        case 4: off = TW_D1; ks = 4; N = 64; break;
-                        case 5: off = TW_D2; ks = 4; N = 64; break;
-                        case 6: off = TW_D3; ks = 4; N = 64; break;
-                        default: off = TW_DH; ks = 4; N = 16; break;
-                    }
-                    tc_issue_layer(tm, a_hi, a_lo, whi + off, wlo + off, ks, N);
-                    tc_commit(&acc_full[g]);
-                }
-            }
-        }
-    } else {
+    {
         // ---------------- point threads: group g = warp / 4, TMEM lane = row = 32 * (warp % 4) + lane
         const int g = warp >> 2, r = ((warp & 3) << 5) + lane;
         uint8_t* Ahi = Abase + g * 2 * TC_ATILE;
@@ -712,10 +682,33 @@ mlp_fwd_tc_kernel(const FwdArgs a) {
         const uint32_t tm = tmem_base + (uint32_t)(g * 64) + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t par = 0;
         float v[64];
-        auto publish = [&]() {
+        // publish the A tile of layer l; the first thread of the group is also its issuing thread: once all 128 rows have
+        // arrived it issues the layer's MMAs and commits them to acc_full (every thread then waits on that barrier)
+        const uint32_t a_hi_s = tc_smem_u32(Ahi), a_lo_s = tc_smem_u32(Alo), w_hi_s = tc_smem_u32(Whi), w_lo_s = tc_smem_u32(Wlo);
+        const uint32_t tm_acc = tmem_base + (uint32_t)(g * 64);
+        uint32_t par_a = 0;
+        auto publish = [&](int l) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             tc_mbar_arrive(&a_ready[g]);
+            if (r == 0) {
+                tc_mbar_wait(&a_ready[g], par_a);
+                par_a ^= 1u;
+                tc_fence_after();
+                uint32_t off; int ks, N;
+                switch (l) {
+                    case 0: off = TW_S1; ks = 2; N = 64; break;
+                    case 1: off = TW_S2; ks = 4; N = 64; break;
+                    case 2: off = TW_S3; ks = 4; N = 16; break;
+                    case 3: off = TW_D0; ks = 2; N = 64; break;
+                    case 4: off = TW_D1; ks = 4; N = 64; break;
+                    case 5: off = TW_D2; ks = 4; N = 64; break;
+                    case 6: off = TW_D3; ks = 4; N = 64; break;
+                    default: off = TW_DH; ks = 4; N = 16; break;
+                }
+                tc_issue_layer(tm_acc, a_hi_s, a_lo_s, w_hi_s + off, w_lo_s + off, ks, N);
+                tc_commit(&acc_full[g]);
+            }
         };
         auto load_enc = [&](int64_t p, bool ok) {
             if (ok) {
@@ -746,26 +739,30 @@ mlp_fwd_tc_kernel(const FwdArgs a) {
             }
         };
         // hidden layer epilogue: v <- act(v * scale + b); save; write the next A tile
-        auto hidden = [&](const float* b, float scale, int act, float* gsave, int64_t Nrow, bool ok) {
+        // (the activation stores for the backward are issued AFTER the A tile is published: the proxy fence would otherwise
+        //  wait for them, and they overlap the next layer's MMAs instead)
+        auto hidden = [&](const float* b, float scale, int act, float* gsave, int64_t Nrow, bool ok, int next_layer) {
 #pragma unroll
             for (int o = 0; o < HID; o++) v[o] = act_fn(fmaf(v[o], scale, b[o]), act);
+            tc_store_row<HID>(Ahi, Alo, r, v);
+            publish(next_layer);
             if (gsave && ok) {
 #pragma unroll
                 for (int o = 0; o < HID; o++) gsave[o * Nrow] = v[o];
             }
-            tc_store_row<HID>(Ahi, Alo, r, v);
         };
         for (int64_t it = blockIdx.x; 2 * it + g < ntiles; it += gridDim.x) {
             const int64_t p0 = (2 * it + g) * PT, p = p0 + r;
             const bool valid = p < a.N;
+            // saved activations: tile-blocked [layer][tile][feature][128 points] (one contiguous 32 KB block per tile and layer)
+            const int64_t tile_off = (2 * it + g) * (int64_t)(HID * PT) + r;
+            const int64_t ngs = (a.N + PT - 1) / PT * PT, ngd = (a.Nu + PT - 1) / PT * PT;
             load_enc(p, valid);
-            publish();
+            publish(0);
             wait_acc(true);
-            hidden(bias, kEncInv, ACT_RELU, a.acts_s ? a.acts_s + p : nullptr, a.Np, valid);
-            publish();
+            hidden(bias, kEncInv, ACT_RELU, a.acts_s ? a.acts_s + tile_off : nullptr, PT, valid, 1);
             wait_acc(true);
-            hidden(bias + HID, 1.0f, ACT_RELU, a.acts_s ? a.acts_s + HID * a.Np + p : nullptr, a.Np, valid);
-            publish();
+            hidden(bias + HID, 1.0f, ACT_RELU, a.acts_s ? a.acts_s + HID * ngs + tile_off : nullptr, PT, valid, 2);
             wait_acc(false);
             if (valid) {
                 const float* b3 = bias + 6 * HID;
@@ -775,15 +772,13 @@ mlp_fwd_tc_kernel(const FwdArgs a) {
             if (p0 < a.Nu) {
                 const bool vu = p < a.Nu;
                 load_enc(p, vu);
-                publish();
+                publish(3);
                 wait_acc(true);
-                hidden(bias + 2 * HID, kEncInv, ACT_LRELU, a.acts_d ? a.acts_d + p : nullptr, a.Nup, vu);
-                publish();
+                hidden(bias + 2 * HID, kEncInv, ACT_LRELU, a.acts_d ? a.acts_d + tile_off : nullptr, PT, vu, 4);
 #pragma unroll 1
                 for (int l = 1; l <= 3; l++) {
                     wait_acc(true);
-                    hidden(bias + (2 + l) * HID, 1.0f, ACT_LRELU, a.acts_d ? a.acts_d + (int64_t)l * HID * a.Nup + p : nullptr, a.Nup, vu);
-                    publish();
+                    hidden(bias + (2 + l) * HID, 1.0f, ACT_LRELU, a.acts_d ? a.acts_d + (int64_t)l * HID * ngd + tile_off : nullptr, PT, vu, 4 + l);
                 }
                 wait_acc(false);
                 if (vu) {
@@ -799,7 +794,530 @@ mlp_fwd_tc_kernel(const FwdArgs a) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
+}
+
+// =====================================================================================================================
+// Tensor-core backward, two kernels.
+//   K1  mlp_bwd_tc_dgrad_kernel: the input-gradient chain, same structure as the forward (thread = point = TMEM lane,
+//       two tiles in flight): G_l = dL/dH_l * act'(H_l) is built per point, written (a) as the swizzled A operand of
+//       dL/dH_{l-1} = G_l W_l (B operand = W_l^T tiles resident in shared memory) and (b) to global memory as packed
+//       (hi, lo) fp16 pairs in [feature][point] layout for K2.  Ends with dL/denc.
+//   K2  mlp_bwd_tc_wgrad_kernel: dW_l = G_l^T X_{l-1}, a reduction over POINTS: both operands are K-major exactly as they
+//       lie in memory ([feature][point]); eight producer warps convert / split them into double-buffered swizzled tiles,
+//       one lane issues the MMAs, and every weight matrix keeps ONE accumulator in TMEM for the whole kernel (496 of the
+//       512 columns).  A row of ones appended to X^T yields the bias gradients in the same MMA; the two layers fed by
+//       the grid features (sigma layer 1, deform layer 0) share one 128-row A tile.  Per-CTA partials + the existing
+//       ordered reduction kernel: deterministic.
+constexpr int GR_S3 = 0, GR_S2 = 4, GR_S1 = 68, GR_DH = 132, GR_D3 = 138, GR_D2 = 202, GR_D1 = 266, GR_D0 = 330, GR_ROWS = 394;
+// W^T tiles ([in rows][out = K]) inside one precision half
+constexpr uint32_t TT_S3 = 0, TT_S2 = TT_S3 + TC_TILE64, TT_S1 = TT_S2 + TC_TILE64, TT_DH = TT_S1 + 32 * 128, TT_D3 = TT_DH + TC_TILE64,
+                   TT_D2 = TT_D3 + TC_TILE64, TT_D1 = TT_D2 + TC_TILE64, TT_D0 = TT_D1 + TC_TILE64, TT_HALF = TT_D0 + 32 * 128;
+constexpr size_t kTcDgradSmem = 1024 + 2 * (size_t)TT_HALF + 2 * 2 * (size_t)TC_ATILE + sizeof(float) * (256 * 10) + 64;
+
+struct BwdTcArgs {
+    BwdArgs b;
+    uint32_t* G;              // [GR_ROWS][Ng] packed half2 (hi, lo)
+    float* partial1;          // [gridDim.x][16]: db of the two head layers (S3: 0-3, warp: 4-6, scaling: 7-9)
+    int64_t Ng;
+};
+
+__device__ __forceinline__ uint32_t tc_split_pack(float x) {           // (hi, lo) of one value as half2
+    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    const __half l = __float2half_rn(x - __half2float(h));
+    return (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+}
+// B tile of W^T: rows = input feature i (rows_pad rows), K = output o: element (i, o) = W[o][i]
+__device__ __forceinline__ void tc_fill_weight_t(uint8_t* hi, uint8_t* lo, const float* __restrict__ W, int O, int K, int rows_pad, int o_off,
+                                                  int tid, int nthr) {
+    for (int idx = tid; idx < rows_pad * 64; idx += nthr) {
+        const int i = idx >> 6, o = idx & 63;
+        const float w = (i < K && o >= o_off && o < o_off + O) ? W[(o - o_off) * K + i] : 0.f;
+        const __half h = __float2half_rn(w);
+        const uint32_t off = tc_off(i, o);
+        *reinterpret_cast<__half*>(hi + off) = h;
+        *reinterpret_cast<__half*>(lo + off) = __float2half_rn(w - __half2float(h));
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+mlp_bwd_tc_dgrad_kernel(const BwdTcArgs t) {
+    const BwdArgs& a = t.b;
+    extern __shared__ uint8_t tc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* Whi = smem;
+    uint8_t* Wlo = Whi + TT_HALF;
+    uint8_t* Abase = Wlo + TT_HALF;
+    float* s_red = reinterpret_cast<float*>(Abase + 4 * TC_ATILE);   // [256][10]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 256 * 10);
+    uint64_t* acc_full = bars;
+    uint64_t* a_ready = bars + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* W = a.params;
+    tc_fill_weight_t(Whi + TT_S3, Wlo + TT_S3, W + S3W, 4, HID, 64, 0, tid, 256);
+    tc_fill_weight_t(Whi + TT_S2, Wlo + TT_S2, W + S2W, HID, HID, 64, 0, tid, 256);
+    tc_fill_weight_t(Whi + TT_S1, Wlo + TT_S1, W + S1W, HID, ENC, 32, 0, tid, 256);
+    // head tile: K columns 0-2 = warp head, 3-5 = scaling head
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        const int i = idx >> 6, o = idx & 63;
+        const float w = o < 3 ? W[WPW + o * HID + i] : (o < 6 ? W[SCW + (o - 3) * HID + i] : 0.f);
+        const __half h = __float2half_rn(w);
+        const uint32_t off = tc_off(i, o);
+        *reinterpret_cast<__half*>(Whi + TT_DH + off) = h;
+        *reinterpret_cast<__half*>(Wlo + TT_DH + off) = __float2half_rn(w - __half2float(h));
+    }
+    tc_fill_weight_t(Whi + TT_D3, Wlo + TT_D3, W + D3W, HID, HID, 64, 0, tid, 256);
+    tc_fill_weight_t(Whi + TT_D2, Wlo + TT_D2, W + D2W, HID, HID, 64, 0, tid, 256);
+    tc_fill_weight_t(Whi + TT_D1, Wlo + TT_D1, W + D1W, HID, HID, 64, 0, tid, 256);
+    tc_fill_weight_t(Whi + TT_D0, Wlo + TT_D0, W + D0W, HID, ENC, 32, 0, tid, 256);
+    if (tid == 0) {
+        tc_mbar_init(&acc_full[0], 1); tc_mbar_init(&acc_full[1], 1);
+        tc_mbar_init(&a_ready[0], PT); tc_mbar_init(&a_ready[1], PT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(tmem_slot)), "n"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t ntiles = (a.N + PT - 1) / PT;
+    float bsum[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) bsum[i] = 0.f;
+
+    {
+        const int g = warp >> 2, r = ((warp & 3) << 5) + lane;
+        uint8_t* Ahi = Abase + g * 2 * TC_ATILE;
+        uint8_t* Alo = Ahi + TC_ATILE;
+        const uint32_t tm = tmem_base + (uint32_t)(g * 64) + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t par = 0;
+        float v[64];
+        // publish the A tile of layer l; the first thread of the group is also its issuing thread: once all 128 rows have
+        // arrived it issues the layer's MMAs and commits them to acc_full (every thread then waits on that barrier)
+        const uint32_t a_hi_s = tc_smem_u32(Ahi), a_lo_s = tc_smem_u32(Alo), w_hi_s = tc_smem_u32(Whi), w_lo_s = tc_smem_u32(Wlo);
+        const uint32_t tm_acc = tmem_base + (uint32_t)(g * 64);
+        uint32_t par_a = 0;
+        auto publish = [&](int l) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            tc_mbar_arrive(&a_ready[g]);
+            if (r == 0) {
+                tc_mbar_wait(&a_ready[g], par_a);
+                par_a ^= 1u;
+                tc_fence_after();
+                uint32_t off; int ks, N;
+                switch (l) {
+                    case 0: off = TT_S3; ks = 1; N = 64; break;
+                    case 1: off = TT_S2; ks = 4; N = 64; break;
+                    case 2: off = TT_S1; ks = 4; N = 32; break;
+                    case 3: off = TT_DH; ks = 1; N = 64; break;
+                    case 4: off = TT_D3; ks = 4; N = 64; break;
+                    case 5: off = TT_D2; ks = 4; N = 64; break;
+                    case 6: off = TT_D1; ks = 4; N = 64; break;
+                    default: off = TT_D0; ks = 4; N = 32; break;
+                }
+                tc_issue_layer(tm_acc, a_hi_s, a_lo_s, w_hi_s + off, w_lo_s + off, ks, N);
+                tc_commit(&acc_full[g]);
+            }
+        };
+        auto wait_acc = [&](bool both) {
+            tc_mbar_wait(&acc_full[g], par);
+            par ^= 1u;
+            tc_fence_after();
+            float t0[32];
+            tc_ld32(tm, t0);
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = t0[j];
+            if (both) {
+                tc_ld32(tm + 32u, t0);
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[32 + j] = t0[j];
+            }
+        };
+        // v (dL/dH of a hidden layer) -> G = v * act'(H).  The 64 saved activations of the point are fetched BEFORE the wait
+        // for the accumulator (they do not depend on it), the A tile is published, and only then G goes to global memory
+        // (packed hi / lo, tile-blocked [tile][row][128 points]) for the weight-gradient kernel.
+        float hbuf[HID];
+        auto fetch_h = [&](const float* __restrict__ H, bool ok) {
+#pragma unroll
+            for (int i = 0; i < HID; i++) hbuf[i] = ok ? __ldg(H + i * PT) : 0.f;
+        };
+        auto hidden_bwd = [&](uint32_t* gp, bool ok, int act, int next_layer) {
+#pragma unroll
+            for (int i = 0; i < HID; i++) v[i] = ok ? v[i] * act_grad(hbuf[i], act) : 0.f;
+            tc_store_row<HID>(Ahi, Alo, r, v);
+            publish(next_layer);
+#pragma unroll
+            for (int i = 0; i < HID; i++) gp[i * PT] = tc_split_pack(v[i]);
+        };
+        for (int64_t it = blockIdx.x; 2 * it + g < ntiles; it += gridDim.x) {
+            const int64_t p0 = (2 * it + g) * PT, p = p0 + r;
+            const bool valid = p < a.N;
+            const int64_t tile_off = (2 * it + g) * (int64_t)(HID * PT) + r;
+            const int64_t ngs = (a.N + PT - 1) / PT * PT, ngd = (a.Nu + PT - 1) / PT * PT;
+            uint32_t* Gt = t.G + (2 * it + g) * (int64_t)(GR_ROWS * PT) + r;       // this tile's block of G, this point's column
+            // ---- opacity / colour net
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = 0.f;
+            if (valid) {
+                if (a.g_opac && p < a.Nu) { const float o = a.opac[p]; v[0] = a.g_opac[p] * o * (1.f - o); }
+                if (a.g_colors) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { const float x = a.colors[p * 3 + c]; v[1 + c] = a.g_colors[p * 3 + c] * x * (1.f - x); }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < 4; o++) { Gt[(GR_S3 + o) * PT] = tc_split_pack(v[o]); bsum[o] += v[o]; }
+            tc_store_row<16>(Ahi, Alo, r, v);
+            publish(0);
+            fetch_h(a.acts_s + HID * ngs + tile_off, valid);
+            wait_acc(true);
+            hidden_bwd(Gt + GR_S2 * PT, valid, ACT_RELU, 1);
+            fetch_h(a.acts_s + tile_off, valid);
+            wait_acc(true);
+            hidden_bwd(Gt + GR_S1 * PT, valid, ACT_RELU, 2);
+            wait_acc(false);                                          // dL/denc of the colour net (32 columns)
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(a.g_enc + p * ENC);
+#pragma unroll
+                for (int j = 0; j < ENC / 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            // ---- deformation net
+            if (p0 < a.Nu) {
+                const bool vu = p < a.Nu;
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = 0.f;
+                if (vu) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        if (a.g_pos) v[c] = a.g_pos[p * 3 + c] * a.init_offset;
+                        if (a.g_scales) { const float sc = a.scales[p * 3 + c]; v[3 + c] = sc < a.max_scale ? a.g_scales[p * 3 + c] * sc : 0.f; }
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < 6; o++) { Gt[(GR_DH + o) * PT] = tc_split_pack(v[o]); bsum[4 + o] += v[o]; }
+                tc_store_row<16>(Ahi, Alo, r, v);
+                publish(3);
+                fetch_h(a.acts_d + 3 * HID * ngd + tile_off, vu);
+                wait_acc(true);
+                hidden_bwd(Gt + GR_D3 * PT, vu, ACT_LRELU, 4);
+                fetch_h(a.acts_d + 2 * HID * ngd + tile_off, vu);
+                wait_acc(true);
+                hidden_bwd(Gt + GR_D2 * PT, vu, ACT_LRELU, 5);
+                fetch_h(a.acts_d + 1 * HID * ngd + tile_off, vu);
+                wait_acc(true);
+                hidden_bwd(Gt + GR_D1 * PT, vu, ACT_LRELU, 6);
+                fetch_h(a.acts_d + tile_off, vu);
+                wait_acc(true);
+                hidden_bwd(Gt + GR_D0 * PT, vu, ACT_LRELU, 7);
+                wait_acc(false);
+                if (vu) {                                             // same thread wrote these 128 bytes a few layers ago
+                    float4* dst = reinterpret_cast<float4*>(a.g_enc + p * ENC);
+#pragma unroll
+                    for (int j = 0; j < ENC / 4; j++) {
+                        float4 q = dst[j];
+                        q.x += v[4 * j]; q.y += v[4 * j + 1]; q.z += v[4 * j + 2]; q.w += v[4 * j + 3];
+                        dst[j] = q;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) s_red[tid * 10 + i] = bsum[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 10) {                                                   // fixed-order sum over the 256 point threads
+        float sacc = 0.f;
+        for (int k = 0; k < 256; k++) sacc += s_red[k * 10 + tid];
+        t.partial1[blockIdx.x * 16 + tid] = sacc;
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
+}
+
+// ---- K2: weight gradients.  Work item = (tile of 128 points, layer group); stage = 104 KB of operand tiles.
+constexpr uint32_t WG_AATOM = 128 * 128, WG_BATOM = 80 * 128;                 // [128 rows][64 pts], [80 rows][64 pts]
+constexpr uint32_t WG_A = 2 * WG_AATOM, WG_B = 2 * WG_BATOM;                   // one precision half (two 64-point atoms)
+constexpr uint32_t WG_STAGE = 2 * WG_A + 2 * WG_B;                             // hi + lo of both operands = 106496 B
+constexpr size_t kTcWgradSmem = 1024 + 2 * (size_t)WG_STAGE + 128;
+// TMEM columns of the seven accumulators
+constexpr int WC_L0 = 0, WC_S2 = 48, WC_S3 = 128, WC_D1 = 192, WC_D2 = 272, WC_D3 = 352, WC_DH = 432;
+
+struct WgItem { int a_row0, a_rows, a2_row0, b_kind, b_layer, n, col; };
+// b_kind: 0 = enc^T (32 rows + ones), 1 = acts_s[b_layer] (64 rows + ones), 2 = acts_d[b_layer] (+ ones), 3 / 4 = the same without the ones row
+__device__ __forceinline__ WgItem wg_item(int l) {
+    switch (l) {
+        case 0: return {GR_S1, 64, GR_D0, 0, 0, 48, WC_L0};
+        case 1: return {GR_S2, 64, -1, 1, 0, 80, WC_S2};
+        case 2: return {GR_S3, 4, -1, 3, 1, 64, WC_S3};
+        case 3: return {GR_D1, 64, -1, 2, 0, 80, WC_D1};
+        case 4: return {GR_D2, 64, -1, 2, 1, 80, WC_D2};
+        case 5: return {GR_D3, 64, -1, 2, 2, 80, WC_D3};
+        default: return {GR_DH, 6, -1, 4, 3, 64, WC_DH};
+    }
+}
+
+__global__ void __launch_bounds__(288, 1)
+mlp_bwd_tc_wgrad_kernel(const BwdTcArgs t, float* __restrict__ partial) {
+    const BwdArgs& a = t.b;
+    extern __shared__ uint8_t tc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * WG_STAGE);
+    uint64_t* full = bars;            // [2] producers -> issuer
+    uint64_t* empty = bars + 2;       // [2] tensor pipe -> producers
+    uint64_t* done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    int* s_used = reinterpret_cast<int*>(bars + 6);                 // [0]: this CTA had a tile, [1]: ... a deform tile
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc_mbar_init(&full[0], 256); tc_mbar_init(&full[1], 256);
+        tc_mbar_init(&empty[0], 1); tc_mbar_init(&empty[1], 1);
+        tc_mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_used[0] = 0; s_used[1] = 0;
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t ntiles = (a.N + PT - 1) / PT;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            uint32_t seen = 0;                                      // bit l: accumulator l already holds data
+            uint32_t n_item = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int nl = tile * PT < a.Nu ? 7 : 3;
+                for (int l = 0; l < nl; l++, n_item++) {
+                    const uint32_t st = n_item & 1u;
+                    tc_mbar_wait(&full[st], (n_item >> 1) & 1u);
+                    tc_fence_after();
+                    const WgItem w = wg_item(l);
+                    const uint32_t base = tc_smem_u32(smem + st * WG_STAGE);
+                    const uint32_t idesc = tc_idesc(w.n);
+                    const uint32_t d = tmem_base + (uint32_t)w.col;
+                    uint32_t acc = (seen >> l) & 1u;
+                    for (int at = 0; at < 2; at++) {
+                        const uint64_t ah = tc_desc(base + at * WG_AATOM), al = tc_desc(base + WG_A + at * WG_AATOM);
+                        const uint64_t bh = tc_desc(base + 2 * WG_A + at * WG_BATOM), bl = tc_desc(base + 2 * WG_A + WG_B + at * WG_BATOM);
+                        for (int ks = 0; ks < 4; ks++) { tc_mma(d, ah + 2u * ks, bh + 2u * ks, idesc, acc); acc = 1; }
+                        for (int ks = 0; ks < 4; ks++) tc_mma(d, ah + 2u * ks, bl + 2u * ks, idesc, 1);
+                        for (int ks = 0; ks < 4; ks++) tc_mma(d, al + 2u * ks, bh + 2u * ks, idesc, 1);
+                    }
+                    seen |= 1u << l;
+                    tc_commit(&empty[st]);
+                }
+            }
+            tc_commit(done);
+            s_used[0] = (seen & 1u) ? 1 : 0;
+            s_used[1] = (seen & 8u) ? 1 : 0;
+        }
+    } else {
+        // ---------------- producers: 256 threads fill the operand tiles of one item
+        uint32_t n_item = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t p0 = tile * PT;
+            const bool deform = p0 < a.Nu;
+            const int nl = deform ? 7 : 3;
+            for (int l = 0; l < nl; l++, n_item++) {
+                const uint32_t st = n_item & 1u;
+                tc_mbar_wait(&empty[st], ((n_item >> 1) & 1u) ^ 1u);
+                const WgItem w = wg_item(l);
+                uint8_t* Ah = smem + st * WG_STAGE;
+                uint8_t* Al = Ah + WG_A;
+                uint8_t* Bh = Ah + 2 * WG_A;
+                uint8_t* Bl = Bh + WG_B;
+                // ---- A = G^T: 128 rows x 16 groups of 8 points; 8 units per thread, every load issued before the first use
+                {
+                    uint4 u0[8], u1[8];
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int idx = tid + it * 256, f = idx >> 4, q = idx & 15;
+                        int grow = -1;
+                        if (f < w.a_rows) grow = w.a_row0 + f;
+                        else if (f >= 64 && w.a2_row0 >= 0 && deform) grow = w.a2_row0 + (f - 64);
+                        u0[it] = make_uint4(0, 0, 0, 0); u1[it] = u0[it];
+                        if (grow >= 0) {
+                            const uint4* src = reinterpret_cast<const uint4*>(t.G + tile * (int64_t)(GR_ROWS * PT) + grow * PT + 8 * q);
+                            u0[it] = __ldg(src); u1[it] = __ldg(src + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int idx = tid + it * 256, f = idx >> 4, q = idx & 15;
+                        uint4 hi, lo;
+                        hi.x = __byte_perm(u0[it].x, u0[it].y, 0x5410); hi.y = __byte_perm(u0[it].z, u0[it].w, 0x5410);
+                        hi.z = __byte_perm(u1[it].x, u1[it].y, 0x5410); hi.w = __byte_perm(u1[it].z, u1[it].w, 0x5410);
+                        lo.x = __byte_perm(u0[it].x, u0[it].y, 0x7632); lo.y = __byte_perm(u0[it].z, u0[it].w, 0x7632);
+                        lo.z = __byte_perm(u1[it].x, u1[it].y, 0x7632); lo.w = __byte_perm(u1[it].z, u1[it].w, 0x7632);
+                        const uint32_t off = (uint32_t)((q >> 3) * WG_AATOM + (f >> 3) * 1024 + (f & 7) * 128 + ((((q & 7) ^ (f & 7)) & 7) << 4));
+                        *reinterpret_cast<uint4*>(Ah + off) = hi;
+                        *reinterpret_cast<uint4*>(Al + off) = lo;
+                    }
+                }
+                // ---- B = X^T (+ a row of ones): 80 rows x 16 groups of 8 points
+                const int kin = w.b_kind == 0 ? ENC : HID;
+                const bool ones = w.b_kind <= 2;
+                if (w.b_kind == 0) {
+                    // grid features are point-major [N][32]: transposing scatter (2-byte stores)
+                    for (int idx = tid; idx < 128 * 8; idx += 256) {
+                        const int k = idx >> 3, j = idx & 7;                           // point k of the tile, features 4j .. 4j+3
+                        const int64_t p = p0 + k;
+                        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p < a.N) e = __ldg(reinterpret_cast<const float4*>(a.enc + p * ENC) + j);
+                        const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const int i = 4 * j + c;
+                            const uint32_t pk = tc_split_pack(ev[c] * kEncScale);
+                            const uint32_t off = (uint32_t)((k >> 6) * WG_BATOM + (i >> 3) * 1024 + (i & 7) * 128 + (((((k & 63) >> 3) ^ (i & 7)) & 7) << 4) + (k & 7) * 2);
+                            *reinterpret_cast<uint16_t*>(Bh + off) = (uint16_t)(pk & 0xffffu);
+                            *reinterpret_cast<uint16_t*>(Bl + off) = (uint16_t)(pk >> 16);
+                        }
+                    }
+                }
+                const int row_begin = w.b_kind == 0 ? ENC : 0;
+                const float* X = nullptr;
+                int64_t Nvalid = 0;
+                if (w.b_kind == 1 || w.b_kind == 3) { X = a.acts_s + (int64_t)w.b_layer * HID * ((a.N + PT - 1) / PT * PT) + tile * (int64_t)(HID * PT); Nvalid = a.N; }
+                if (w.b_kind == 2 || w.b_kind == 4) { X = a.acts_d + (int64_t)w.b_layer * HID * ((a.Nu + PT - 1) / PT * PT) + tile * (int64_t)(HID * PT); Nvalid = a.Nu; }
+                {
+                    // 80 rows x 16 groups = 1280 units, 5 per thread; loads first (rows below row_begin were written above)
+                    float4 x0[5], x1[5];
+#pragma unroll
+                    for (int it = 0; it < 5; it++) {
+                        const int idx = tid + it * 256, i = idx >> 4, q = idx & 15;
+                        x0[it] = make_float4(0.f, 0.f, 0.f, 0.f); x1[it] = x0[it];
+                        if (i >= row_begin && i < kin) {
+                            const int64_t p = p0 + 8 * q;
+                            const float* src = X + i * PT + 8 * q;
+                            if (p + 7 < Nvalid) { x0[it] = __ldg(reinterpret_cast<const float4*>(src)); x1[it] = __ldg(reinterpret_cast<const float4*>(src) + 1); }
+                            else {
+                                float x[8];
+#pragma unroll
+                                for (int c = 0; c < 8; c++) x[c] = (p + c < Nvalid) ? src[c] : 0.f;
+                                x0[it] = make_float4(x[0], x[1], x[2], x[3]); x1[it] = make_float4(x[4], x[5], x[6], x[7]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 5; it++) {
+                        const int idx = tid + it * 256, i = idx >> 4, q = idx & 15;
+                        if (i < row_begin) continue;
+                        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+                        if (i < kin) {
+                            const float x[8] = {x0[it].x, x0[it].y, x0[it].z, x0[it].w, x1[it].x, x1[it].y, x1[it].z, x1[it].w};
+                            uint32_t ph[4], pl[4];
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                ph[c] = pack_act2(x[2 * c], x[2 * c + 1]);
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&ph[c]));
+                                pl[c] = pack_act2(x[2 * c] - hf.x, x[2 * c + 1] - hf.y);
+                            }
+                            hi = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                            lo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        } else if (i == kin && ones) {
+                            hi = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);     // 1.0h x 8
+                        }
+                        const uint32_t off = (uint32_t)((q >> 3) * WG_BATOM + (i >> 3) * 1024 + (i & 7) * 128 + ((((q & 7) ^ (i & 7)) & 7) << 4));
+                        *reinterpret_cast<uint4*>(Bh + off) = hi;
+                        *reinterpret_cast<uint4*>(Bl + off) = lo;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tc_fence_before();
+                tc_mbar_arrive(&full[st]);
+            }
+        }
+    }
+    // ---------------- every accumulator -> this CTA's partial gradient vector
+    tc_mbar_wait(done, 0);
+    tc_fence_after();
+    __syncthreads();
+    float* out = partial + (int64_t)blockIdx.x * NPARAM;
+    const bool used = s_used[0] != 0, used_d = s_used[1] != 0;
+    if (warp < 4) {
+        const int o = (warp << 5) + lane;                            // TMEM lane = row of the accumulator
+        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float v[32];
+        // L0: lanes 0-63 sigma layer 1, lanes 64-127 deform layer 0; columns 0-31 weights (x 2^-10), column 32 bias
+        tc_ld32(tl + WC_L0, v);
+        {
+            const bool ok = o < 64 ? used : used_d;
+            float* wdst = out + (o < 64 ? S1W + o * ENC : D0W + (o - 64) * ENC);
+#pragma unroll
+            for (int i = 0; i < ENC; i++) wdst[i] = ok ? v[i] * kEncInv : 0.f;
+        }
+        float bcol[32];
+        tc_ld32(tl + WC_L0 + 32, bcol);
+        out[o < 64 ? S1B + o : D0B + (o - 64)] = (o < 64 ? used : used_d) ? bcol[0] : 0.f;
+        if (o < 64) {
+            auto dump64 = [&](int col, int wofs, int bofs, bool ok) {
+                tc_ld32(tl + col, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) out[wofs + o * HID + i] = ok ? v[i] : 0.f;
+                tc_ld32(tl + col + 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i++) out[wofs + o * HID + 32 + i] = ok ? v[i] : 0.f;
+                if (bofs >= 0) {
+                    tc_ld32(tl + col + 64, v);
+                    out[bofs + o] = ok ? v[0] : 0.f;
+                }
+            };
+            dump64(WC_S2, S2W, S2B, used);
+            dump64(WC_D1, D1W, D1B, used_d);
+            dump64(WC_D2, D2W, D2B, used_d);
+            dump64(WC_D3, D3W, D3B, used_d);
+        }
+        // head layers: a handful of rows (all lanes of the warp execute the collective loads)
+        {
+            float h0[32], h1[32];
+            tc_ld32(tl + WC_S3, h0); tc_ld32(tl + WC_S3 + 32, h1);
+            if (o < 4) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) { out[S3W + o * HID + i] = used ? h0[i] : 0.f; out[S3W + o * HID + 32 + i] = used ? h1[i] : 0.f; }
+            }
+            tc_ld32(tl + WC_DH, h0); tc_ld32(tl + WC_DH + 32, h1);
+            if (o < 6) {
+                float* wdst = out + (o < 3 ? WPW + o * HID : SCW + (o - 3) * HID);
+#pragma unroll
+                for (int i = 0; i < 32; i++) { wdst[i] = used_d ? h0[i] : 0.f; wdst[32 + i] = used_d ? h1[i] : 0.f; }
+            }
+        }
+    }
+    if (tid < 10) out[tid < 4 ? S3B + tid : (tid < 7 ? WPB + tid - 4 : SCB + tid - 7)] = 0.f;      // head biases come from K1 (partial1)
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512));
+}
+
+// g_params[j] = sum over CTAs of partial[c][j] (+ the head-bias partials of K1); g_w_pose[o][j] = g_bias0[o] * pose[j]
+__global__ void __launch_bounds__(256)
+mlp_reduce_tc_kernel(const float* __restrict__ partial, int nparts, const float* __restrict__ partial1, int nparts1,
+                     const float* __restrict__ pose, float* __restrict__ g_params, float* __restrict__ g_w_pose) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= NPARAM) return;
+    float s = 0.f;
+    for (int c = 0; c < nparts; c++) s += partial[(int64_t)c * NPARAM + j];
+    int hb = -1;
+    if (j >= S3B && j < S3B + 4) hb = j - S3B;
+    else if (j >= WPB && j < WPB + 3) hb = 4 + j - WPB;
+    else if (j >= SCB && j < SCB + 3) hb = 7 + j - SCB;
+    if (hb >= 0) for (int c = 0; c < nparts1; c++) s += partial1[c * 16 + hb];
+    g_params[j] = s;
+    if (g_w_pose && j >= D0B && j < D0B + HID) {
+        const int o = j - D0B;
+        for (int k = 0; k < POSE; k++) g_w_pose[o * POSE + k] = s * pose[k];
+    }
 }
 
 static int g_mlp_tc = 1;      // debug switch (dwg_avatar_mlp_set_tc): 0 = the fp32 SIMT forward
@@ -827,6 +1345,12 @@ extern "C" int64_t dwg_avatar_mlp_param_count(void) { return NPARAM; }
 /* Debug / A-B switch: 1 (default) = tensor-core kernels, 0 = the fp32 SIMT kernels. */
 extern "C" int dwg_avatar_mlp_set_tc(int on) { g_mlp_tc = on ? 1 : 0; return DWG_OK; }
 extern "C" int64_t dwg_avatar_mlp_scratch_bytes(void) { return (int64_t)sizeof(float) * NPARAM * num_sms(); }
+/* Scratch of dwg_avatar_mlp_bwd for N Gaussians: per-CTA partial gradient vectors + (tensor-core path) the packed
+ * per-layer gradients G [394][ceil(N / 128) * 128] that the input-gradient kernel hands to the weight-gradient kernel. */
+extern "C" int64_t dwg_avatar_mlp_bwd_scratch_bytes(int64_t N) {
+    const int64_t Ng = (N + PT - 1) / PT * PT;
+    return (int64_t)sizeof(float) * (NPARAM + 16) * num_sms() + (int64_t)sizeof(uint32_t) * GR_ROWS * Ng + 256;
+}
 
 // Forward of both MLPs + activations for N Gaussians (the first Nu are unconstrained: both nets; the
 // rest are mesh-bound: colour only, opacity 1).  acts_s [2][64][Np], acts_d [4][64][Nup] (Np, Nup =
@@ -851,7 +1375,7 @@ extern "C" int dwg_avatar_mlp_fwd(const float* enc, const float* positions, cons
         if (!attr_tc) { cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcFwdSmem); attr_tc = true; }
         const int64_t npairs = ((N + PT - 1) / PT + 1) / 2;
         const int grid = (int)(npairs < num_sms() ? npairs : num_sms());
-        mlp_fwd_tc_kernel<<<grid, 320, kTcFwdSmem, (cudaStream_t)stream>>>(a);
+        mlp_fwd_tc_kernel<<<grid, 256, kTcFwdSmem, (cudaStream_t)stream>>>(a);
         return check_launch("dwg_avatar_mlp_fwd");
     }
     const int64_t ntiles = (N + P - 1) / P;
@@ -880,9 +1404,31 @@ extern "C" int dwg_avatar_mlp_bwd(const float* enc, const float* params, const f
     a.g_enc = g_enc; a.partial = reinterpret_cast<float*>(scratch);
     a.N = N; a.Nu = Nu; a.Np = (N + 3) & ~(int64_t)3; a.Nup = (Nu + 3) & ~(int64_t)3;
     a.init_offset = init_offset; a.max_scale = max_scale;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_mlp_tc) {
+        static bool attr_tc = false;
+        if (!attr_tc) {
+            cudaFuncSetAttribute(mlp_bwd_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcDgradSmem);
+            cudaFuncSetAttribute(mlp_bwd_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcWgradSmem);
+            attr_tc = true;
+        }
+        const int sms = num_sms();
+        const int64_t nt = (N + PT - 1) / PT;
+        BwdTcArgs t;
+        t.b = a;
+        t.Ng = nt * PT;
+        float* partial2 = reinterpret_cast<float*>(scratch);
+        t.partial1 = partial2 + (int64_t)NPARAM * sms;
+        t.G = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(t.partial1 + 16 * (int64_t)sms) + 255) & ~(uintptr_t)255);
+        const int grid1 = (int)((nt + 1) / 2 < sms ? (nt + 1) / 2 : sms);
+        const int grid2 = (int)(nt < sms ? nt : sms);
+        mlp_bwd_tc_dgrad_kernel<<<grid1, 256, kTcDgradSmem, st>>>(t);
+        mlp_bwd_tc_wgrad_kernel<<<grid2, 288, kTcWgradSmem, st>>>(t, partial2);
+        mlp_reduce_tc_kernel<<<(NPARAM + 255) / 256, 256, 0, st>>>(partial2, grid2, t.partial1, grid1, body_pose, g_params, g_w_pose);
+        return check_launch("dwg_avatar_mlp_bwd");
+    }
     const int64_t ntiles = (N + P - 1) / P;
     const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
-    cudaStream_t st = (cudaStream_t)stream;
     mlp_bwd_kernel<<<grid, P, kBwdSmem, st>>>(a);
     mlp_reduce_kernel<<<(NPARAM + 255) / 256, 256, 0, st>>>(a.partial, grid, body_pose, g_params, g_w_pose);
     return check_launch("dwg_avatar_mlp_bwd");

@@ -58,6 +58,7 @@ SIGNATURES = {
                                 [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     'dwg_avatar_mlp_param_count': (c_int64, []),
     'dwg_avatar_mlp_set_tc': (c_int, [c_int]),
+    'dwg_avatar_mlp_bwd_scratch_bytes': (c_int64, [c_int64]),
     'dwg_avatar_mlp_scratch_bytes': (c_int64, []),
     'dwg_avatar_mlp_fwd': (c_int, [c_void_p] * 11 + [c_int64, c_int64, c_float, c_float, c_float, c_void_p]),
     'dwg_avatar_mlp_bwd': (c_int, [c_void_p] * 16 + [c_int64, c_int64, c_float, c_float, c_void_p]),

@@ -243,9 +243,9 @@ class _AvatarMLP(torch.autograd.Function):
         e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
         colors, opac, pos, scales = e(N, 3), e(N, 1), e(Nu, 3), e(Nu, 3)
         need_bwd = any(ctx.needs_input_grad)
-        Np, Nup = (N + 3) // 4 * 4, (Nu + 3) // 4 * 4
+        Np, Nup = (N + 127) // 128 * 128, (Nu + 127) // 128 * 128          # tile-blocked [layer][tile][64][128] (include/dwg.h)
         acts_s = e(2, 64, Np) if need_bwd else None
-        acts_d = e(4, 64, max(Nup, 4)) if need_bwd else None
+        acts_d = e(4, 64, max(Nup, 128)) if need_bwd else None
         check(L.dwg_avatar_mlp_fwd(ptr(enc), ptr(positions), ptr(flat), ptr(w_pose), ptr(pose), ptr(colors), ptr(opac), ptr(pos), ptr(scales),
                                    ptr(acts_s), ptr(acts_d), N, Nu, float(init_offset), float(init_scale), float(max_scale), stream()),
               'dwg_avatar_mlp_fwd')
@@ -264,7 +264,7 @@ class _AvatarMLP(torch.autograd.Function):
         g_enc = torch.empty_like(enc)
         g_flat = torch.empty_like(flat)
         g_w_pose = torch.empty(64, 63, device=enc.device, dtype=torch.float32)
-        scratch = torch.empty(int(L.dwg_avatar_mlp_scratch_bytes()), device=enc.device, dtype=torch.uint8)
+        scratch = torch.empty(int(L.dwg_avatar_mlp_bwd_scratch_bytes(N)), device=enc.device, dtype=torch.uint8)
         check(L.dwg_avatar_mlp_bwd(ptr(enc), ptr(flat), ptr(pose), ptr(colors), ptr(opac), ptr(scales), ptr(acts_s), ptr(acts_d),
                                    ptr(g_colors), ptr(g_opac), ptr(g_pos), ptr(g_scales), ptr(g_enc), ptr(g_flat), ptr(g_w_pose), ptr(scratch),
                                    N, Nu, init_offset, max_scale, stream()), 'dwg_avatar_mlp_bwd')

@@ -190,7 +190,9 @@ int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                   const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
                   float alpha, int act, void* stream);
 /* dwg_avatar_mlp_fwd / _bwd: the two per-Gaussian MLPs of DreamWaltzG.animate with their
- * activations, fused (fp32).  Replaces reference core/nerf/nerf_model.py:12-33 (MLP 32-64-64-4,
+ * activations, fused.  fp32 results on the tensor cores: every operand is split into an fp16 (hi, lo) pair and a layer is
+ * the three products hi*hi + hi*lo + lo*hi accumulated in fp32 (tcgen05, csrc/avatar_mlp.cu; dwg_avatar_mlp_set_tc(0)
+ * selects the plain fp32 SIMT kernels).  Replaces reference core/nerf/nerf_model.py:12-33 (MLP 32-64-64-4,
  * ReLU) as used by static_mlp_forward core/system/avatar.py:1283-1290, DeformNetwork.forward
  * core/deformation/deform_model.py:102-143 (D=4, W=64, leaky_relu; heads warp / scaling) as used by
  * dynamic_mlp_forward avatar.py:1292-1294, and non_rigid_transform avatar.py:1464-1498 with the
@@ -202,11 +204,12 @@ int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
  *     layers.0.weight[:, :32] layers.0.bias layers.{1,2,3}.{weight,bias}
  *     gaussian_warp.{weight[3,64],bias} gaussian_scaling.{weight[3,64],bias};
  *   w_pose = layers.0.weight[:, 32:95] [64,63], body_pose [63].
- *   acts_s [2][64][Np], acts_d [4][64][Nup] (Np/Nup = N/Nu rounded up to 4): hidden activations kept
- *   for the backward (null = inference).  Backward overwrites g_enc [N,32], g_params (same layout as
- *   params) and g_w_pose [64,63]; null output-gradient pointers mean zero; scratch =
- *   dwg_avatar_mlp_scratch_bytes() bytes. */
+ *   acts_s [2][64][Np], acts_d [4][64][Nup] (Np/Nup = N/Nu rounded up to 128): hidden activations kept
+ *   for the backward (null = inference); the tensor-core kernels lay them out tile-blocked, [layer][tile][64][128 points].
+ *   Backward overwrites g_enc [N,32], g_params (same layout as params) and g_w_pose [64,63]; null output-gradient
+ *   pointers mean zero; scratch = dwg_avatar_mlp_bwd_scratch_bytes(N) bytes. */
 int64_t dwg_avatar_mlp_param_count(void);
+int64_t dwg_avatar_mlp_bwd_scratch_bytes(int64_t N);   /* scratch of dwg_avatar_mlp_bwd for N Gaussians (supersedes dwg_avatar_mlp_scratch_bytes) */
 int dwg_avatar_mlp_set_tc(int on);   /* debug / A-B switch: 1 (default) = tcgen05 kernels (fp16 hi+lo split, fp32 accuracy), 0 = fp32 SIMT kernels */
 int64_t dwg_avatar_mlp_scratch_bytes(void);
 int dwg_avatar_mlp_fwd(const float* enc, const float* positions, const float* params, const float* w_pose, const float* body_pose,
