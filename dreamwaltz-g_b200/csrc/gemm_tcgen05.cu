@@ -82,6 +82,7 @@ struct Params {
     const float* bias2;             // [rows_b2][N] per-image bias (time embedding) or null
     int bias2_rows_per;
     int has_res;                    // residual fetched through tmR (bf16, same geometry as C)
+    int a_bcast1;                   // A has no batch-1 dimension (stride 0: one weight matrix for every batch entry)
     float alpha;
     int act;
     // slow path (unaligned output / residual strides): direct per-thread stores
@@ -396,7 +397,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     a_c3 = tn * p.BNI;
                 } else {
                     b1 = tc.z % p.nb1; b2 = tc.z / p.nb1;
-                    a_c1 = tc.m_tile * BM; a_c2 = b1; a_c3 = b2;
+                    a_c1 = tc.m_tile * BM; a_c2 = p.a_bcast1 ? 0 : b1; a_c3 = b2;
                 }
                 int it0, it1;
                 it_range(tc.ks, it0, it1);
@@ -1177,6 +1178,7 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
     DWG_REQUIRE(!(p.direct && act == ACT_GEGLU), "GEGLU epilogue needs 16-byte aligned output rows and N % 64 == 0");
     p.has_res = (residual && !p.direct) ? 1 : 0;
     p.M = M; p.N = N; p.K = K; p.taps_w = 1; p.taps_h = 1; p.k_chunks = (K + BK - 1) / BK; p.nb1 = nb1; p.conv_mode = 0;
+    p.a_bcast1 = (nb1 > 1 && a_b1 == 0) ? 1 : 0;
     p.a_bytes = A_BYTES;
     p.C = C; p.ldc = ldc; p.c_b1 = c_b1; p.c_b2 = c_b2;
     p.bias = bias; p.bias2 = bias2; p.bias2_rows_per = bias2_rows_per;
@@ -1196,8 +1198,10 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
     CUtensorMap tmA, tmB, tmC, tmR;
     const uint32_t ones[4] = {1, 1, 1, 1};
     {
-        const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)nb1, (uint64_t)nb2};
-        const uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)(nb1 > 1 ? a_b1 : lda * (int64_t)M) * 2, (uint64_t)(nb2 > 1 ? a_b2 : lda * (int64_t)M) * 2};
+        // a_b1 == 0 with nb1 > 1: A is broadcast over the first batch dimension (the producer then always loads batch 0)
+        const bool bc = nb1 > 1 && a_b1 == 0;
+        const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)(bc ? 1 : nb1), (uint64_t)nb2};
+        const uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)(nb1 > 1 && !bc ? a_b1 : lda * (int64_t)M) * 2, (uint64_t)(nb2 > 1 ? a_b2 : lda * (int64_t)M) * 2};
         const uint32_t box[4] = {BK, BM, 1, 1};
         rc = make_map_act(&tmA, A, dims, str, box, ones);
         if (rc) return rc;
@@ -1262,6 +1266,7 @@ static int conv_impl(const void* x, const void* w, void* y, int out_f16,
     p.has_res = (residual && !p.direct) ? 1 : 0;
     p.M = Nimg * Ho * Wo; p.N = Cout; p.K = Cin; p.taps_w = ksize; p.taps_h = ksize; p.k_chunks = (Cin + BK - 1) / BK;
     p.a_bytes = (uint32_t)(BW * BH * BNI * BK * 2);
+    p.a_bcast1 = 0;
     p.nb1 = 1; p.conv_mode = 1; p.Ho = Ho; p.Wo = Wo; p.BH = BH; p.BW = BW; p.BNI = BNI; p.Nimg = Nimg; p.tiles_w = tiles_w; p.tiles_h = tiles_h;
     p.stride = stride; p.pad_h = pad_h; p.pad_w = pad_w;
     p.ebw = BW < 32 ? BW : 32;

@@ -125,8 +125,9 @@ def attention(W, p, x, ctx, heads, residual, kv=None):
         if k3 is None:
             k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
         vT = torch.zeros(B, C, Tkp, device=x.device, dtype=F16) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=F16)
-        for b in range(B):
-            ops.gemm(W.w[p + '.to_v'], ctx[b], out=vT[b][:, :Tk] if Tkp != Tk else vT[b])
+        wv = W.w[p + '.to_v']
+        # ONE batched launch: the weight matrix is the (broadcast, batch stride 0) A operand, V^T[b] = Wv ctx[b]^T
+        ops.gemm(wv.unsqueeze(0).expand(B, -1, -1), ctx, out=vT[:, :, :Tk] if Tkp != Tk else vT)
         if (p + '.to_v') in W.b:
             vT += W.b[p + '.to_v'].to(F16)[None, :, None]
     if hd <= 128:
@@ -182,8 +183,7 @@ class DiffusionNet:
         S = self._xattn_total
         K_all = ops.gemm(ctx.reshape(B * Tk, Ck), self._xattn_wk).view(B, Tk, S)
         vT_all = torch.zeros(B, S, Tkp, device=ctx.device, dtype=F16)
-        for b in range(B):
-            ops.gemm(self._xattn_wv, ctx[b], out=vT_all[b][:, :Tk])
+        ops.gemm(self._xattn_wv.unsqueeze(0).expand(B, -1, -1), ctx, out=vT_all[:, :, :Tk])
         return {n: (K_all[:, :, a:c], vT_all[:, a:c, :]) for n, (a, c) in self._xattn_off.items()}
 
     def heads_at(self, level):

@@ -171,7 +171,9 @@ void* dwg_raster_view(int which, void* geom, void* bin, void* img, int64_t N, in
  * ONCE by the caller before its first use (the kernels leave the counters zero); launches that may run concurrently
  * (two streams) need different workspaces. */
 int64_t dwg_gemm_workspace_bytes(void);
-/* colstats (NULL = off): i64 [4, groups, N, 2] (4 slots that spread the atomics; the consumer adds them), PRE-ZEROED by the caller; the epilogue adds, per output column, the sum and
+/* Batches: nb1 x nb2 problems with element strides a_b1 / a_b2 (b_*, c_*, r_* likewise); a_b1 == 0 with nb1 > 1 broadcasts ONE A
+ * matrix over the first batch dimension (a weight matrix as the A operand of every batch entry).
+ * colstats (NULL = off): i64 [4, groups, N, 2] (4 slots that spread the atomics; the consumer adds them), PRE-ZEROED by the caller; the epilogue adds, per output column, the sum and
  * the sum of squares of the fp16 values it stores (2^-20 fixed point, integer atomics => deterministic), grouped by image
  * (conv: the image index; GEMM: global row / colstats_rows, a multiple of 32).  These are the GroupNorm statistics of the
  * layer that consumes the output: dwg_groupnorm_apply_cs folds them per group, so no statistics pass reads the tensor. */

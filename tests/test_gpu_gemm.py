@@ -270,3 +270,17 @@ def test_epilogue_column_statistics_feed_groupnorm(case):
     one_pass, st = ops.group_norm(y4.contiguous(), g, bta, 32, 1e-5, silu=True, return_stats=True, colstats=cs)
     assert (one_pass.float() - two_pass.float()).abs().max() <= 2e-3 * two_pass.float().abs().max()      # statistics agree to ~1e-7: a few fp16 ulps at most
     torch.testing.assert_close(st.double() / 2.0 ** 20, st_ref.double() / 2.0 ** 20, rtol=2e-6, atol=1e-2)
+
+
+def test_gemm_broadcast_a_over_batch():
+    """a_b1 == 0: one A matrix (a weight) for every batch entry -- V^T[b] = Wv ctx[b]^T of the attention layers in ONE launch."""
+    torch.manual_seed(3)
+    B, M, N, K = 2, 320, 1024, 320
+    w = (torch.randn(M, K, device=DEV) * 0.1).half()
+    x = torch.randn(B, N, K, device=DEV).half()
+    out = torch.zeros(B, M, N + 8, device=DEV, dtype=torch.float16)
+    ops.gemm(w.unsqueeze(0).expand(B, -1, -1), x, out=out[:, :, :N])
+    ref = torch.einsum('mk,bnk->bmn', w.float(), x.float())
+    err = (out[:, :, :N].float() - ref).abs().max() / ref.abs().max()
+    assert float(err) < 2e-3, float(err)
+    assert float(out[:, :, N:].abs().max()) == 0.0
