@@ -82,6 +82,14 @@ struct Params {
     const float* bias2;             // [rows_b2][N] per-image bias (time embedding) or null
     int bias2_rows_per;
     int has_res;                    // residual fetched through tmR (bf16, same geometry as C)
+    // LayerNorm folded into this GEMM (plain GEMM only).  The operand holds the UN-normalised activations and gamma is
+    // pre-multiplied into the weight (W' = W * gamma); with c1 = row sums of W' and c2 = W beta (+ bias, passed as the bias):
+    //   ln_mode 1 (activations = A rows):    out[m][n] = rstd_m * (acc - mean_m * c1[n]) + c2[n]
+    //   ln_mode 2 (activations = B rows):    out[m][n] = rstd_n * (acc - mean_n * c1[m]) + ln_rowbias[m]
+    // ln_stats = fixed-point (sum, sum of squares) per activation row, written by the producing GEMM (rowstats_out).
+    int ln_mode; float ln_inv_dim, ln_eps;
+    const unsigned long long* ln_stats; const float* ln_c1; const float* ln_rowbias;
+    unsigned long long* rowstats_out;   // [M][2]: per output row, sum / sum of squares of the stored fp16 values (2^-20 fixed point)
     int a_bcast1;                   // A has no batch-1 dimension (stride 0: one weight matrix for every batch entry)
     float alpha;
     int act;
@@ -308,7 +316,9 @@ __device__ __forceinline__ void cs_flush(const Params& p, const float* s_cs, con
 
 // Persistent, warp-specialised: the CTA walks tiles blockIdx.x, +gridDim.x, ...; the smem ring and
 // the two TMEM accumulator stages let the TMA / MMA of tile i+1 overlap the epilogue of tile i.
-template <int EPI, bool PAIR>
+// LNF: LayerNorm folding / row statistics compiled in (a separate instantiation: the ~350 launches of a step that use neither
+// run exactly the kernel they ran before)
+template <int EPI, bool PAIR, bool LNF>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -326,8 +336,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* sB = sA + (p.halo ? p.a_stages * HALO_BYTES : p.stages * A_BYTES);
     uint8_t* sStage = sB + p.stages * B_BYTES;                         // [kEpiWarps][2][STG_BYTES]
     uint8_t* sRes = sStage + kEpiWarps * 2 * STG_BYTES;                // [kEpiWarps][2][2048] (only when has_res)
-    float* s_bias = reinterpret_cast<float*>(sRes + (p.has_res ? kEpiWarps * 2 * 2048 : 0));      // [tile parity][image 0/1][256]
-    float* s_cs = s_bias + 2 * 2 * 256;                                // [tile parity][quadrant][256 columns][2]  (only when p.colstats)
+    float* s_bias = reinterpret_cast<float*>(sRes + (p.has_res ? kEpiWarps * 2 * 2048 : 0));      // [tile parity][image 0 / image 1 or LN c1 | mean / LN rstd][256]
+    float* s_cs = s_bias + 2 * 3 * 256;                                // [tile parity][quadrant][256 columns][2]  (only when p.colstats)
     int* s_csmeta = reinterpret_cast<int*>(s_cs + (p.colstats ? 2 * 4 * 256 * 2 : 0));      // [tile parity][8]: valid, slot, ntile0, -, grp[4]
     uint64_t* full = reinterpret_cast<uint64_t*>(s_csmeta + (p.colstats ? 16 : 0));
     uint64_t* empty = full + kMaxStages;
@@ -595,7 +605,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // ---- bias (+ per-image time-embedding bias) of the tile's columns -> shared memory, while the MMAs run.
             // Double-buffered by tile parity: the one barrier per tile also orders the reuse two tiles later.
             const bool stage_b2 = p.bias2 && p.conv_mode && p.BNI <= 2;
-            float* sb = s_bias + (tl & 1u) * 512;
+            float* sb = s_bias + (tl & 1u) * 768;
             {
                 const int img0 = p.conv_mode ? (tc.m_tile / (p.tiles_w * p.tiles_h)) * p.BNI : 0;
                 for (int cc = threadIdx.x - 128; cc < p.BN; cc += 32 * kEpiWarps) {
@@ -607,6 +617,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             v0 += p.bias2[(int64_t)img0 * p.N + n];
                             if (img0 + 1 < p.Nimg) v1 += p.bias2[(int64_t)(img0 + 1) * p.N + n];
                         }
+                    }
+                    if (LNF && p.ln_mode == 1) v1 = n < p.N ? p.ln_c1[n] : 0.f;
+                    if (LNF && p.ln_mode == 2) {
+                        float mean = 0.f, rstd = 0.f;
+                        if (n < p.N) {
+                            const double inv = (double)p.ln_inv_dim * (1.0 / 1048576.0);
+                            const int64_t sn = (int64_t)tc.z * p.N + n;
+                            const double mu = (double)(long long)p.ln_stats[2 * sn] * inv, qq = (double)(long long)p.ln_stats[2 * sn + 1] * inv;
+                            mean = (float)mu;
+                            rstd = rsqrtf((float)fmax(qq - mu * mu, 0.0) + p.ln_eps);
+                        }
+                        v1 = mean;
+                        sb[512 + cc] = rstd;
                     }
                     sb[cc] = v0; sb[256 + cc] = v1;
                 }
@@ -623,6 +646,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     meta[4 + q] = box_ok ? grp : -1;
                 }
                 if (e == 0 && lane == 0) { meta[0] = (p.ksplit == 1) ? 1 : 0; meta[1] = tc.m_tile & 3; meta[2] = ntile0; }
+            }
+            float ln_a = 0.f, ln_b = 0.f, ln_c = 0.f;                 // row mode: (mean, rstd) of this row; column mode: (c1, row bias)
+            if (LNF && p.ln_mode == 1 && row_ok) {
+                const int64_t m = (int64_t)tc.z * p.M + c1 + lane;
+                const double inv = (double)p.ln_inv_dim * (1.0 / 1048576.0);
+                const double mu = (double)(long long)p.ln_stats[2 * m] * inv, qq = (double)(long long)p.ln_stats[2 * m + 1] * inv;
+                ln_a = (float)mu;
+                ln_b = rsqrtf((float)fmax(qq - mu * mu, 0.0) + p.ln_eps);
+            } else if (LNF && p.ln_mode == 2 && row_ok) {
+                ln_a = p.ln_c1[c1 + lane];
+                ln_c = p.ln_rowbias ? p.ln_rowbias[c1 + lane] : 0.f;
             }
             const float* sbr = sb + ((stage_b2 && (r0 + lane) / (p.BW * p.BH) > 0) ? 256 : 0);
             const bool b2_global = p.bias2 && !stage_b2;                           // generic (plain GEMM / many images per tile) path
@@ -703,6 +737,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     float v[32], g[32];
                     tc_ld32(taddr_row + (uint32_t)acol0, v);
                     tc_ld32(taddr_row + (uint32_t)(acol0 + 32), g);
+                    if (LNF && p.ln_mode == 1) {
+                        const float* c1p = sb + 256 + acol0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) { v[j] = ln_b * (v[j] - ln_a * c1p[j]); g[j] = ln_b * (g[j] - ln_a * c1p[32 + j]); }
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const float4 b0 = bp[j], b1 = bp[8 + j];
@@ -755,6 +794,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         for (int j = 0; j < 32; j++) f[j] = nx[j];
                         reg_fence(f);                                   // the copy is complete before nx is handed to the next load
                         if (c + 2 < nchunks) tc_ld32_nowait(taddr_row + (uint32_t)((c + 2) * ACC_PER_CHUNK), nx);
+                    }
+                    if (LNF && p.ln_mode == 1) {
+                        const float* c1p = sb + 256 + acol0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = ln_b * (f[j] - ln_a * c1p[j]);
+                    } else if (LNF && p.ln_mode == 2) {
+                        const float* mp = sb + 256 + acol0;
+                        const float* rp = sb + 512 + acol0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = fmaf(rp[j], f[j] - mp[j] * ln_a, ln_c);
                     }
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
@@ -824,12 +873,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     for (int j = 0; j < 8; j++)
                         *reinterpret_cast<float4*>(srow + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 } else {
+                    float rs = 0.f, rq = 0.f;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         uint4 pk;
                         pk.x = pack_act(f[8 * j], f[8 * j + 1]); pk.y = pack_act(f[8 * j + 2], f[8 * j + 3]);
                         pk.z = pack_act(f[8 * j + 4], f[8 * j + 5]); pk.w = pack_act(f[8 * j + 6], f[8 * j + 7]);
                         *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = pk;
+                        if (LNF && p.rowstats_out) {
+                            const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const float2 t2 = act2_to_f2(*reinterpret_cast<const act2_t*>(&w4[k]));
+                                const bool k0 = ocol0 + 8 * j + 2 * k < p.N, k1 = ocol0 + 8 * j + 2 * k + 1 < p.N;
+                                if (k0) { rs += t2.x; rq = fmaf(t2.x, t2.x, rq); }
+                                if (k1) { rs += t2.y; rq = fmaf(t2.y, t2.y, rq); }
+                            }
+                        }
+                    }
+                    if (LNF && p.rowstats_out && row_ok) {
+                        // LayerNorm statistics of the consumer: one pair of fixed-point integer REDs per (row, 32-column chunk)
+                        unsigned long long* dst = p.rowstats_out + 2 * ((int64_t)tc.z * p.M + c1 + lane);
+                        atomicAdd(dst, (unsigned long long)__float2ll_rn(rs * 1048576.0f));
+                        atomicAdd(dst + 1, (unsigned long long)__float2ll_rn(rq * 1048576.0f));
                     }
                 }
                 if (tl == 0 && e == 0 && lane == 0 && c == 0) TRACE(10);
@@ -942,7 +1008,7 @@ constexpr size_t kSmemBudget = 232448 - 1024;       // opt-in maximum minus the 
 static int g_plan_cs = 0;                  // the launch being planned accumulates column statistics (16 KB + 64 B more shared memory)
 static size_t smem_fixed(int epi, int has_res) {
     const size_t stg = (epi == EPI_F32) ? 4096 : 2048;
-    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + 2 * 2 * 256 * 4 + (g_plan_cs ? 2 * 4 * 256 * 2 * 4 + 64 : 0) +
+    return (size_t)kEpiWarps * 2 * stg + (has_res ? (size_t)kEpiWarps * 2 * 2048 : 0) + 2 * 3 * 256 * 4 + (g_plan_cs ? 2 * 4 * 256 * 2 * 4 + 64 : 0) +
            (2 * kMaxStages + 4 + 2 * kEpiWarps + 2 * kMaxAStages) * 8 + 64;
 }
 
@@ -1052,15 +1118,15 @@ static Plan plan_tiles_auto(int m_tiles, int nz, int N, int iters, int epi, int 
     return best;
 }
 
-template <int EPI, bool PAIR>
+template <int EPI, bool PAIR, bool LNF>
 static cudaError_t launch_one(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                               const CUtensorMap& tmR, const Params& p) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(gemm_kernel<EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024));
+        cudaFuncSetAttribute(gemm_kernel<EPI, PAIR, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 1024));
         attr_done = true;
     }
-    if (!PAIR) return launch_pdl(gemm_kernel<EPI, PAIR>, grid, dim3(kThreads), smem, st, tmA, tmB, tmC, tmR, p);
+    if (!PAIR) return launch_pdl(gemm_kernel<EPI, PAIR, LNF>, grid, dim3(kThreads), smem, st, tmA, tmB, tmC, tmR, p);
     // CTA pair = cluster of 2 (same TPC) + programmatic dependent launch
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -1070,7 +1136,7 @@ static cudaError_t launch_one(dim3 grid, size_t smem, cudaStream_t st, const CUt
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, PAIR>, tmA, tmB, tmC, tmR, p);
+    return cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, PAIR, LNF>, tmA, tmB, tmC, tmR, p);
 }
 
 static int ensure_sms() {
@@ -1101,18 +1167,23 @@ static int launch(const CUtensorMap& tmA, CUtensorMap& tmB_out, const CUtensorMa
     const size_t b_bytes = (size_t)(pair ? p.BN / 2 : p.BN) * 128;
     const size_t smem = 1024 + (p.halo ? (size_t)p.a_stages * HALO_BYTES + (size_t)p.stages * b_bytes : (size_t)p.stages * (A_BYTES + b_bytes)) +
                         smem_fixed(epi, p.has_res);
-    if (pair) {
-        const int pairs = g_num_sms / 2;
-        const dim3 grid(2 * (p.total_tiles < pairs ? p.total_tiles : pairs));
-        if (epi == EPI_F16) launch_one<EPI_F16, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
-        else if (epi == EPI_F32) launch_one<EPI_F32, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
-        else launch_one<EPI_GEGLU, true>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+    const bool lnf = p.ln_mode != 0 || p.rowstats_out != nullptr;
+    const dim3 grid = pair ? dim3(2 * (p.total_tiles < g_num_sms / 2 ? p.total_tiles : g_num_sms / 2)) : dim3(p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms);
+#define DWG_LAUNCH(E, PR, LN) launch_one<E, PR, LN>(grid, smem, st, tmA, tmB_out, tmC, tmR, p)
+    if (lnf) {                                   // LayerNorm folding / row statistics: fp16-output epilogues only
+        if (epi == EPI_F16) { if (pair) DWG_LAUNCH(EPI_F16, true, true); else DWG_LAUNCH(EPI_F16, false, true); }
+        else if (epi == EPI_GEGLU) { if (pair) DWG_LAUNCH(EPI_GEGLU, true, true); else DWG_LAUNCH(EPI_GEGLU, false, true); }
+        else { set_error("LayerNorm folding needs an fp16 output"); return DWG_ERR_INVALID; }
+    } else if (pair) {
+        if (epi == EPI_F16) DWG_LAUNCH(EPI_F16, true, false);
+        else if (epi == EPI_F32) DWG_LAUNCH(EPI_F32, true, false);
+        else DWG_LAUNCH(EPI_GEGLU, true, false);
     } else {
-        const dim3 grid(p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms);
-        if (epi == EPI_F16) launch_one<EPI_F16, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
-        else if (epi == EPI_F32) launch_one<EPI_F32, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
-        else launch_one<EPI_GEGLU, false>(grid, smem, st, tmA, tmB_out, tmC, tmR, p);
+        if (epi == EPI_F16) DWG_LAUNCH(EPI_F16, false, false);
+        else if (epi == EPI_F32) DWG_LAUNCH(EPI_F32, false, false);
+        else DWG_LAUNCH(EPI_GEGLU, false, false);
     }
+#undef DWG_LAUNCH
     return check_launch("tcgen05 gemm");
 }
 
@@ -1148,13 +1219,17 @@ static int scratch_from_library(Scratch& s) {
     return DWG_OK;
 }
 
+struct LnFold {                      // optional LayerNorm folding / row statistics of one plain GEMM (see Params)
+    int mode = 0; const void* stats = nullptr; const float* c1 = nullptr; const float* rowbias = nullptr; int dim = 0; float eps = 0.f;
+    void* rowstats_out = nullptr;
+};
 static int gemm_impl(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
                              const void* B, int64_t ldb, int64_t b_b1, int64_t b_b2,
                              void* C, int64_t ldc, int64_t c_b1, int64_t c_b2, int out_f16,
                              int M, int N, int K, int nb1, int nb2,
                              const float* bias, const float* bias2, int bias2_rows_per,
                              const void* residual, int64_t ldr, int64_t r_b1, int64_t r_b2,
-                             float alpha, int act, const Scratch& ws, void* colstats, int cs_rows, void* stream) {
+                             float alpha, int act, const Scratch& ws, void* colstats, int cs_rows, void* stream, const LnFold& ln = LnFold()) {
     DWG_REQUIRE(A && B && C, "null pointer");
     DWG_REQUIRE(M > 0 && N > 0 && K > 0 && nb1 > 0 && nb2 > 0, "bad sizes");
     DWG_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && (a_b1 % 8) == 0 && (a_b2 % 8) == 0 && (b_b1 % 8) == 0 && (b_b2 % 8) == 0,
@@ -1192,6 +1267,14 @@ static int gemm_impl(const void* A, int64_t lda, int64_t a_b1, int64_t a_b2,
     p.total_tiles = p.m_sched * p.n_tiles * p.nz * p.ksplit;
     p.workspace = ws.data; p.counters = ws.counters; p.trace = g_trace;
     p.colstats = reinterpret_cast<unsigned long long*>(colstats); p.cs_rows = cs_rows;
+    p.ln_mode = ln.mode; p.ln_stats = reinterpret_cast<const unsigned long long*>(ln.stats); p.ln_c1 = ln.c1; p.ln_rowbias = ln.rowbias;
+    p.ln_inv_dim = ln.dim > 0 ? 1.0f / (float)ln.dim : 0.f; p.ln_eps = ln.eps;
+    p.rowstats_out = reinterpret_cast<unsigned long long*>(ln.rowstats_out);
+    DWG_REQUIRE(ln.mode >= 0 && ln.mode <= 2, "LayerNorm folding: mode must be 0, 1 or 2");
+    DWG_REQUIRE(ln.mode == 0 || (ln.stats && ln.c1 && ln.dim > 0), "LayerNorm folding: statistics, c1 and the feature count are required");
+    DWG_REQUIRE(ln.mode == 0 || nb2 == 1, "LayerNorm folding: at most one batch dimension");
+    DWG_REQUIRE(ln.mode == 0 || !p.direct, "LayerNorm folding needs the TMA-store epilogue (16-byte aligned output / residual rows and bias)");
+    DWG_REQUIRE(!ln.rowstats_out || (epi == EPI_F16 && nb2 == 1 && !p.direct), "row statistics need the fp16 TMA-store epilogue");
     DWG_REQUIRE(!colstats || (epi == EPI_F16 && !p.direct && cs_rows > 0 && (cs_rows % 32) == 0 && ((int64_t)M % cs_rows == 0 || nb1 * nb2 == 1)),
                 "column statistics need the fp16 TMA-store epilogue and statistics groups that are whole multiples of 32 rows");
 
@@ -1304,6 +1387,7 @@ static int conv_impl(const void* x, const void* w, void* y, int out_f16,
     p.total_tiles = p.m_sched * p.n_tiles * p.ksplit;
     p.workspace = ws.data; p.counters = ws.counters; p.trace = g_trace;
     p.colstats = reinterpret_cast<unsigned long long*>(colstats); p.cs_rows = 0;
+    p.ln_mode = 0; p.ln_stats = nullptr; p.ln_c1 = nullptr; p.ln_rowbias = nullptr; p.ln_inv_dim = 0.f; p.ln_eps = 0.f; p.rowstats_out = nullptr;
     DWG_REQUIRE(!colstats || (epi == EPI_F16 && !p.direct && (Wo % BW) == 0 && (Ho % BH) == 0 && (Nimg % BNI) == 0 && ((BW * BH) % 32) == 0),
                 "column statistics need the fp16 TMA-store epilogue and exactly tiled images with >= 32 pixels per tile image");
 
@@ -1368,6 +1452,20 @@ extern "C" int dwg_gemm_f16(const void* A, int64_t lda, int64_t a_b1, int64_t a_
     if (rc) return rc;
     return gemm_impl(A, lda, a_b1, a_b2, B, ldb, b_b1, b_b2, C, ldc, c_b1, c_b2, out_f16, M, N, K, nb1, nb2, bias, bias2, bias2_rows_per, residual, ldr,
                      r_b1, r_b2, alpha, act, s, nullptr, 0, stream);
+}
+/* dwg_gemm_f16_ws plus (a) LayerNorm of the activation operand folded into the epilogue and (b) LayerNorm statistics of the
+ * OUTPUT rows for the next consumer -- see include/dwg.h. */
+extern "C" int dwg_gemm_f16_ln(const void* A, int64_t lda, int64_t a_b, const void* B, int64_t ldb, int64_t b_b, void* C, int64_t ldc, int64_t c_b,
+                               int M, int N, int K, int nb, const float* bias, const void* residual, int64_t ldr, int64_t r_b, int act,
+                               int ln_mode, const void* ln_stats, const float* ln_c1, const float* ln_rowbias, int ln_dim, float ln_eps,
+                               void* rowstats_out, void* workspace, int64_t workspace_bytes, void* colstats, int colstats_rows, void* stream) {
+    Scratch s;
+    int rc = scratch_from_caller(workspace, workspace_bytes, s);
+    if (rc) return rc;
+    LnFold ln;
+    ln.mode = ln_mode; ln.stats = ln_stats; ln.c1 = ln_c1; ln.rowbias = ln_rowbias; ln.dim = ln_dim; ln.eps = ln_eps; ln.rowstats_out = rowstats_out;
+    return gemm_impl(A, lda, a_b, 0, B, ldb, b_b, 0, C, ldc, c_b, 0, 1, M, N, K, nb, 1, bias, nullptr, 0, residual, ldr, r_b, 0, 1.0f, act, s,
+                     colstats, colstats_rows, stream, ln);
 }
 extern "C" int dwg_conv2d_nhwc_f16_ws(const void* x, const void* w, void* y, int out_f16, int Nimg, int H, int W, int Cin, int Cout, int ksize,
                                       int stride, int pad_h, int pad_w, int Ho, int Wo, const float* bias, const float* bias2_per_image,

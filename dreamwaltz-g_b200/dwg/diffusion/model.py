@@ -67,15 +67,19 @@ class Weights:
 
 
 STATS_IN_EPILOGUE = os.environ.get('DWG_NO_EPILOGUE_STATS') != '1'      # GroupNorm statistics from the producing epilogue (A/B switch)
+# LayerNorms folded into the consuming GEMM epilogues (ops.gemm_ln).  Parity-neutral and 69 fewer launches per step, but MEASURED
+# 0.1 ms SLOWER than the three LayerNorm kernels per block at the benchmark's size (13.88 vs 13.77 ms/step, same box, DESIGN.md
+# section 6): off by default, DWG_LN_FOLD=1 enables it.
+LN_FOLD = os.environ.get('DWG_LN_FOLD') == '1'
 
 
-def conv(W, name, x, stride=1, padding=1, bias2=None, residual=None, out_dtype=F16, out_hw=None, use_bias=True, stats=False):
+def conv(W, name, x, stride=1, padding=1, bias2=None, residual=None, out_dtype=F16, out_hw=None, use_bias=True, stats=False, act=None):
     """stats=True: the output feeds a GroupNorm -- its epilogue accumulates that layer's statistics (y._cs)."""
     w = W.w[name]
     if x.shape[-1] != w.shape[-1]:
         x = _pad_c(x)
     return ops.conv2d_nhwc(x, w, bias=W.b.get(name) if use_bias else None, bias2=bias2, residual=residual, stride=stride,
-                           padding=padding, out_hw=out_hw, out_dtype=out_dtype, stats=stats and STATS_IN_EPILOGUE)
+                           padding=padding, out_hw=out_hw, out_dtype=out_dtype, stats=stats and STATS_IN_EPILOGUE, act=act)
 
 
 def linear(W, name, x2d, residual=None, act=None, out_dtype=F16, alpha=1.0, stats_rows=None):
@@ -130,16 +134,24 @@ def attention(W, p, x, ctx, heads, residual, kv=None):
         ops.gemm(wv.unsqueeze(0).expand(B, -1, -1), ctx, out=vT[:, :, :Tk] if Tkp != Tk else vT)
         if (p + '.to_v') in W.b:
             vT += W.b[p + '.to_v'].to(F16)[None, :, None]
-    if hd <= 128:
-        o = ops.attention(q3, k3, vT, heads, Tk)                       # fused: scores never reach HBM
-    else:
-        q, k = q3.view(B, T, heads, hd).permute(0, 2, 1, 3), k3.view(B, Tk, heads, hd).permute(0, 2, 1, 3)
-        S = torch.empty(B, heads, T, Tkp, device=x.device, dtype=F16)
-        ops.gemm(q, k, alpha=hd ** -0.5, out=S[..., :Tk] if Tkp != Tk else S)
-        ops.softmax_rows_(S, Tk)
-        o = torch.empty(B, T, C, device=x.device, dtype=F16)
-        ops.gemm(S, vT.unflatten(1, (heads, hd)), out=o.view(B, T, heads, hd).permute(0, 2, 1, 3))
+    o = attn_core(q3, k3, vT, heads, Tk)
     return linear(W, p + '.to_out.0', o.reshape(B * T, C), residual=residual.reshape(B * T, C)).view(B, T, C)
+
+
+def attn_core(q3, k3, vT, heads, Tk):
+    """softmax(Q K^T / sqrt(d)) V for q3 [B,T,C], k3 [B,Tk,C] (strided views allowed), vT [B,C,Tkp] -> [B,T,C]."""
+    B, T, C = q3.shape
+    hd = C // heads
+    Tkp = vT.shape[2]
+    if hd <= 128:
+        return ops.attention(q3, k3, vT, heads, Tk)                    # fused: scores never reach HBM
+    q, k = q3.unflatten(2, (heads, hd)).permute(0, 2, 1, 3), k3.unflatten(2, (heads, hd)).permute(0, 2, 1, 3)
+    S = torch.empty(B, heads, T, Tkp, device=q3.device, dtype=F16)
+    ops.gemm(q, k, alpha=hd ** -0.5, out=S[..., :Tk] if Tkp != Tk else S)
+    ops.softmax_rows_(S, Tk)
+    o = torch.empty(B, T, C, device=q3.device, dtype=F16)
+    ops.gemm(S, vT.unflatten(1, (heads, hd)), out=o.view(B, T, heads, hd).permute(0, 2, 1, 3))
+    return o
 
 
 class DiffusionNet:
@@ -171,6 +183,38 @@ class DiffusionNet:
             offs[n] = (o, o + c)
             o += c
         self._xattn_off, self._xattn_total = offs, o
+        # LayerNorm folding (ops.gemm_ln): per transformer block, gamma-scaled weights W' = W * gamma (fp16), c1 = row sums of W'
+        # (of the ROUNDED weights: exactly what the tensor cores multiply), c2 = W beta (+ bias)
+        self._lnf = {}
+        if LN_FOLD:
+            f32 = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+
+            def fold(wname, gamma, beta, bias=None, interleave=False):
+                w = f32(wname)
+                bv = f32(bias) if bias is not None and bias in sd else None
+                if interleave:                                            # GEGLU: (value_i, gate_i) rows interleaved, as Weights does
+                    inner = w.shape[0] // 2
+                    w = torch.stack([w[:inner], w[inner:]], dim=1).reshape(2 * inner, w.shape[1])
+                    if bv is not None:
+                        bv = torch.stack([bv[:inner], bv[inner:]], dim=1).reshape(2 * inner)
+                wp = (w * gamma[None, :]).to(F16).contiguous()
+                c1 = wp.float().sum(1).contiguous()
+                c2 = w @ beta
+                if bv is not None:
+                    c2 = c2 + bv
+                return wp, c1, c2.contiguous()
+            for blk in sorted(n[:-len('.norm1.weight')] for n in sd if n.endswith('.transformer_blocks.0.norm1.weight')):
+                g1, b1 = f32(blk + '.norm1.weight'), f32(blk + '.norm1.bias')
+                g2, b2 = f32(blk + '.norm2.weight'), f32(blk + '.norm2.bias')
+                g3, b3 = f32(blk + '.norm3.weight'), f32(blk + '.norm3.bias')
+                wq, c1q, c2q = fold(blk + '.attn1.to_q.weight', g1, b1, blk + '.attn1.to_q.bias')
+                wk, c1k, c2k = fold(blk + '.attn1.to_k.weight', g1, b1, blk + '.attn1.to_k.bias')
+                self._lnf[blk] = {
+                    'qk': (torch.cat([wq, wk], 0).contiguous(), torch.cat([c1q, c1k]).contiguous(), torch.cat([c2q, c2k]).contiguous()),
+                    'v': fold(blk + '.attn1.to_v.weight', g1, b1, blk + '.attn1.to_v.bias'),
+                    'q2': fold(blk + '.attn2.to_q.weight', g2, b2, blk + '.attn2.to_q.bias'),
+                    'ff': fold(blk + '.ff.net.0.proj.weight', g3, b3, blk + '.ff.net.0.proj.bias', interleave=True),
+                }
         # self-attention Q | K projection weights concatenated (bias-free in the public SD architectures)
         for n in sorted(n[:-len('.to_q')] for n in self.W.w if n.endswith('.attn1.to_q')):
             if (n + '.to_q') not in self.W.b and (n + '.to_k') not in self.W.b and os.environ.get('DWG_NO_QK') != '1':
@@ -221,11 +265,13 @@ class DiffusionNet:
         B, H, Wd, C = x.shape
         h = gn(W, p + '.norm', x, self.G, 1e-6, False)
         lin_proj = W.w[p + '.proj_in'].dim() == 2               # SD2.1 use_linear_projection: nn.Linear on the token layout (same memory)
+        b = p + '.transformer_blocks.0'
+        if b in self._lnf:
+            return self._transformer_folded(p, b, x, h, ctx, heads, lin_proj)
         if lin_proj:
             h = linear(W, p + '.proj_in', h.view(B * H * Wd, C)).view(B, H * Wd, C)
         else:
             h = conv(W, p + '.proj_in', h, padding=0).view(B, H * Wd, C)
-        b = p + '.transformer_blocks.0'
         n = ops.layer_norm(h, W.w[b + '.norm1'], W.b[b + '.norm1'])
         h = attention(W, b + '.attn1', n, n, heads, h)
         n = ops.layer_norm(h, W.w[b + '.norm2'], W.b[b + '.norm2'])
@@ -236,6 +282,42 @@ class DiffusionNet:
         if lin_proj:
             return _view_keep_stats(linear(W, p + '.proj_out', h.view(B * H * Wd, C), residual=x.view(B * H * Wd, C), stats_rows=H * Wd), B, H, Wd, C)
         return conv(W, p + '.proj_out', h, padding=0, residual=x, stats=True)
+
+    def _transformer_folded(self, p, b, x, hn, ctx, heads, lin_proj):
+        """The transformer block without LayerNorm kernels: every producer of a normalised tensor leaves the row statistics
+        (sum, sum of squares) in its epilogue, every consumer applies the normalisation algebraically in ITS epilogue
+        (ops.gemm_ln).  x = block input (residual of proj_out), hn = GroupNorm(x)."""
+        W, F = self.W, self._lnf[b]
+        B, H, Wd, C = x.shape
+        T = H * Wd
+        eps = 1e-5
+        w_in = W.w[p + '.proj_in']
+        h0 = ops.gemm_ln(hn.view(B * T, C), w_in.reshape(w_in.shape[0], -1)[:, :C] if w_in.dim() == 4 else w_in, bias=W.b.get(p + '.proj_in'), rowstats=True)
+        # ---- self-attention: Q | K (rows = tokens) and V^T (columns = tokens) straight from the un-normalised h0
+        wqk, c1qk, c2qk = F['qk']
+        qk = ops.gemm_ln(h0, wqk, bias=c2qk, ln=(h0._rs, c1qk, C, eps)).view(B, T, 2 * C)
+        wv, c1v, c2v = F['v']
+        Tp = (T + 7) // 8 * 8                                     # 16-byte rows for the TMA store (only the 2 x 2 test level pads)
+        vT = torch.empty(B, C, T, device=x.device, dtype=F16) if Tp == T else torch.zeros(B, C, Tp, device=x.device, dtype=F16)
+        ops.gemm_ln(wv.unsqueeze(0).expand(B, -1, -1), h0.view(B, T, C), ln_cols=(h0._rs, c1v, c2v, C, eps), out=vT if Tp == T else vT[:, :, :T])
+        o = attn_core(qk[:, :, :C], qk[:, :, C:], vT, heads, T)
+        h1 = ops.gemm_ln(o.reshape(B * T, C), W.w[b + '.attn1.to_out.0'], bias=W.b.get(b + '.attn1.to_out.0'), residual=h0, rowstats=True)
+        # ---- cross-attention (K / V^T of the text context come from prepare())
+        wq2, c1q2, c2q2 = F['q2']
+        q2 = ops.gemm_ln(h1, wq2, bias=c2q2, ln=(h1._rs, c1q2, C, eps)).view(B, T, C)
+        kv = self._ctx_kv.get(b + '.attn2') if self._ctx_kv else None
+        if kv is None:
+            kv = self.project_context(ctx.to(F16).contiguous())[b + '.attn2']
+        k2, vT2 = kv
+        o2 = attn_core(q2, k2, vT2, heads, ctx.shape[1])
+        h2 = ops.gemm_ln(o2.reshape(B * T, C), W.w[b + '.attn2.to_out.0'], bias=W.b.get(b + '.attn2.to_out.0'), residual=h1, rowstats=True)
+        # ---- feed-forward (GEGLU fused in the epilogue, after the folded LayerNorm)
+        wff, c1ff, c2ff = F['ff']
+        g = ops.gemm_ln(h2, wff, bias=c2ff, act='geglu', ln=(h2._rs, c1ff, C, eps))
+        h3 = linear(W, b + '.ff.net.2', g, residual=h2).view(B, H, Wd, C)
+        if lin_proj:
+            return _view_keep_stats(linear(W, p + '.proj_out', h3.view(B * T, C), residual=x.view(B * T, C), stats_rows=T), B, H, Wd, C)
+        return conv(W, p + '.proj_out', h3, padding=0, residual=x, stats=True)
 
     def down_path(self, h, tproj, ctx):
         cfg, nb = self.cfg, len(self.cfg['block_out'])
@@ -266,10 +348,10 @@ class ControlNet(DiffusionNet):
     def embed_condition(self, cond_nchw01):
         """controlnet_cond_embedding of the condition image(s) -> [Bc,h,w,C0] (before the residual add)."""
         W = self.W
-        c = ops.silu(conv(W, 'controlnet_cond_embedding.conv_in', to_nhwc_f16(cond_nchw01)))
+        c = conv(W, 'controlnet_cond_embedding.conv_in', to_nhwc_f16(cond_nchw01), act='silu')      # SiLU in the conv epilogue
         nblk = 2 * (len(self.cfg['cond_embed']) - 1)
         for k in range(nblk):
-            c = ops.silu(conv(W, f'controlnet_cond_embedding.blocks.{k}', c, stride=2 if k % 2 == 1 else 1))
+            c = conv(W, f'controlnet_cond_embedding.blocks.{k}', c, stride=2 if k % 2 == 1 else 1, act='silu')
         return conv(W, 'controlnet_cond_embedding.conv_out', c)
 
     @torch.no_grad()

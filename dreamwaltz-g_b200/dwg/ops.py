@@ -592,6 +592,65 @@ def gemm(a, b, *, bias=None, bias2=None, bias2_rows_per=0, residual=None, alpha=
     return out
 
 
+def take_rowstats(device, rows):
+    """Zero-initialised i64 [rows, 2] for an epilogue's LayerNorm row statistics (arena slice inside a step)."""
+    rs = STATS_ARENA.take(device, rows * 2)
+    if rs is None:
+        rs = torch.zeros(rows * 2, device=device, dtype=torch.int64)
+    return rs.view(rows, 2)
+
+
+def gemm_ln(a, b, *, bias=None, residual=None, act=None, ln=None, ln_cols=None, rowstats=False, colstats_rows=None, out=None):
+    """fp16 GEMM C = act(A B^T + bias) + residual ([M,K] x [N,K], or one batch dimension [nb,M,K] x [nb,N,K]; a batch stride of 0
+    broadcasts A) with a LayerNorm folded into the epilogue (dwg_gemm_f16_ln) and / or LayerNorm statistics of the output rows.
+      ln = (stats i64 [nb*M,2], c1 [N], dim, eps):                   the A rows are un-normalised activations, b = W * gamma, bias = W beta (+ bias)
+      ln_cols = (stats i64 [nb*N,2], c1 [M], rowbias [M], dim, eps):  the B rows are the activations (V^T = Wv' x^T), a = Wv * gamma
+      rowstats=True: out._rs = i64 [nb*M,2] (sum, sum of squares of the stored fp16 values, 2^-20 fixed point)."""
+    _chk_f16(a), _chk_f16(b)
+    assert a.dim() == b.dim() and a.dim() in (2, 3) and a.stride(-1) == 1 and b.stride(-1) == 1 and not (ln and ln_cols)
+    if a.dim() == 2:
+        a3, b3 = a.unsqueeze(0), b.unsqueeze(0)
+    else:
+        a3, b3 = a, b
+    nb, M, K = a3.shape
+    N = b3.shape[1]
+    assert b3.shape[0] == nb and b3.shape[2] == K
+    No = N // 2 if act == 'geglu' else N
+    if out is None:
+        out = torch.empty((nb, M, No) if a.dim() == 3 else (M, No), device=a.device, dtype=torch.float16)
+    o3 = out if out.dim() == 3 else out.unsqueeze(0)
+    assert o3.stride(-1) == 1
+    r3 = None
+    if residual is not None:
+        _chk_f16(residual)
+        r3 = residual if residual.dim() == 3 else residual.unsqueeze(0)
+        assert r3.stride(-1) == 1
+    mode, st, c1, rb, dim, eps = 0, None, None, None, 0, 0.0
+    if ln is not None:
+        mode, (st, c1, dim, eps) = 1, ln
+        assert st.shape == (nb * M, 2) and c1.numel() == N
+    if ln_cols is not None:
+        mode, (st, c1, rb, dim, eps) = 2, ln_cols
+        assert st.shape == (nb * N, 2) and c1.numel() == M
+    rs = take_rowstats(a.device, nb * M) if rowstats else None
+    cs = None
+    if colstats_rows is not None and act != 'geglu' and colstats_rows % 32 == 0 and (nb * M) % colstats_rows == 0 and N % 8 == 0:
+        cs = _take_colstats(a.device, (nb * M) // colstats_rows, N)
+    bias = None if bias is None else f32c(bias)
+    bs = lambda t: t.stride(0) if nb > 1 else 0
+    with _prof(2.0 * M * N * K * nb, f'gemm M{M} N{N} K{K} b{nb}', 2.0 * nb * (M * K + N * K + M * No)):
+        ws = _gemm_workspace(a.device)
+        check(lib().dwg_gemm_f16_ln(a3.data_ptr(), a3.stride(1), bs(a3), b3.data_ptr(), b3.stride(1), bs(b3), o3.data_ptr(), o3.stride(1), bs(o3),
+                                    M, N, K, nb, ptr(bias), None if r3 is None else r3.data_ptr(), 0 if r3 is None else r3.stride(1),
+                                    0 if r3 is None else bs(r3), ACT[act], mode, ptr(st), ptr(c1), ptr(rb), int(dim), float(eps), ptr(rs),
+                                    ws.data_ptr(), ws.numel(), ptr(cs), int(colstats_rows or 0) if cs is not None else 0, stream()), 'dwg_gemm_f16_ln')
+    if rs is not None:
+        out._rs = rs
+    if cs is not None:
+        out._cs = cs
+    return out
+
+
 def _conv_stats_ok(Nimg, Ho, Wo, Cout):
     """Mirror of the tile geometry of dwg_conv2d_nhwc_f16 (csrc/gemm_tcgen05.cu): column statistics need exactly tiled images
     whose share of a 128-row tile is a multiple of 32 pixels (true for every layer of the SD UNets / VAE)."""

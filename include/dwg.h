@@ -237,6 +237,20 @@ int dwg_gemm_tune_pair(int mode);
 int dwg_gemm_tune_halo(int mode, int base_offset_mode);
 int dwg_gemm_last_halo(void);
 int dwg_gemm_last_pair(void);
+/* dwg_gemm_f16_ln: GEMM (optionally batched) C[M,N] = act(A[M,K] B[N,K]^T ...) + residual (fp16 output) with
+ *  (a) a LayerNorm of the ACTIVATION operand folded into the epilogue -- the operand holds the un-normalised activations, gamma
+ *      is pre-multiplied into the weight (W' = W * gamma), c1 = row sums of W', beta enters through the bias (W beta + bias):
+ *        ln_mode 1 (activations = A rows): C[m][n] = rstd_m (acc - mean_m c1[n]) + bias[n]
+ *        ln_mode 2 (activations = B rows): C[m][n] = rstd_n (acc - mean_n c1[m]) + ln_rowbias[m]     (V^T = Wv' X^T)
+ *      ln_stats i64 [rows,2] = fixed-point (2^-20) sum and sum of squares of each activation row over ln_dim features;
+ *  (b) rowstats_out (NULL = off): i64 [M,2], PRE-ZEROED, receives the same statistics of the OUTPUT rows (of the fp16 values stored)
+ *      -- the LayerNorm statistics of the layer that consumes C.  No LayerNorm kernel and no normalised copy exist.
+ *  Replaces the three nn.LayerNorm of diffusers' BasicTransformerBlock behind core/guidance/controlnet.py:98-114. */
+int dwg_gemm_f16_ln(const void* A, int64_t lda, int64_t a_b, const void* B, int64_t ldb, int64_t b_b, void* C, int64_t ldc, int64_t c_b,
+                    int M, int N, int K, int nb /* batch count; a_b == 0 broadcasts A; statistics index = batch * rows + row */,
+                    const float* bias, const void* residual, int64_t ldr, int64_t r_b, int act,
+                    int ln_mode, const void* ln_stats, const float* ln_c1, const float* ln_rowbias, int ln_dim, float ln_eps,
+                    void* rowstats_out, void* workspace, int64_t workspace_bytes, void* colstats, int colstats_rows, void* stream);
 /* Split-K scratch lane (0 or 1) used by the launches that follow: GEMMs enqueued on two streams that may run
  * concurrently (ControlNet beside the UNet encoder, dwg/diffusion/guidance.py) must use different lanes. */
 int dwg_gemm_set_lane(int lane);

@@ -210,3 +210,23 @@ def test_sd21_style_unet_controlnet_match_oracle():
     assert rel_l2(mid.permute(0, 3, 1, 2), mid_r) < 5e-3
     eps = un.forward(x.to(DEV), t.to(DEV), ctx.to(DEV), down, mid)
     assert rel_l2(eps, eps_r) < 5e-3, rel_l2(eps, eps_r)
+
+
+def test_layernorm_folding_matches_layernorm_kernels(monkeypatch):
+    """The folded transformer block (row statistics from the producing epilogue, normalisation applied algebraically in the
+    consuming epilogue; off by default) against the LayerNorm-kernel path: same UNet, same inputs."""
+    from dwg.diffusion import model as M, weights as Wt
+    cfg = Wt.TINY
+    sd = Wt.make_unet(cfg)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 4, 16, 16, generator=g).to(DEV)
+    ctx = torch.randn(2, 77, cfg['ctx_dim'], generator=g).to(DEV)
+    t = torch.tensor([321], device=DEV)
+    outs = []
+    for fold in (False, True):
+        monkeypatch.setattr(M, 'LN_FOLD', fold)
+        net = M.UNet(sd, cfg, DEV)
+        assert bool(net._lnf) == fold
+        outs.append(net.forward(x, t, ctx, None, None).float())
+    rel = float((outs[1] - outs[0]).norm() / outs[0].norm())
+    assert rel < 5e-3, rel

@@ -284,3 +284,58 @@ def test_gemm_broadcast_a_over_batch():
     err = (out[:, :, :N].float() - ref).abs().max() / ref.abs().max()
     assert float(err) < 2e-3, float(err)
     assert float(out[:, :, N:].abs().max()) == 0.0
+
+
+def _ln_ref(x, g, b, eps=1e-5):
+    return F.layer_norm(x.float(), (x.shape[-1],), g, b, eps)
+
+
+@pytest.mark.parametrize('M,C,N', [(512, 320, 640), (8192, 320, 640), (300, 1280, 2560)])
+def test_gemm_layernorm_folded_rows_and_rowstats(M, C, N):
+    """LayerNorm folded into the consuming GEMM (ln_mode 1) from the row statistics the PRODUCING GEMM left in its epilogue,
+    against torch: y = LN(x) W^T + bias with x = fp16(A0 W0^T + r).  Also the GEGLU epilogue behind the folded LN."""
+    torch.manual_seed(M + C)
+    a0 = torch.randn(M, C, device=DEV).half()
+    w0 = (torch.randn(C, C, device=DEV) / C ** 0.5).half()
+    r = (torch.randn(M, C, device=DEV) + 0.7).half()                          # a mean offset: the cancellation the fold must survive
+    x = ops.gemm_ln(a0, w0, residual=r, rowstats=True)
+    xr = (a0.float() @ w0.float().t() + r.float()).half()
+    assert (x.float() - xr.float()).abs().max() < 2e-2
+    rs = x._rs.double() / 2 ** 20
+    assert torch.allclose(rs[:, 0], x.double().sum(1), atol=1e-3) and torch.allclose(rs[:, 1], (x.double() ** 2).sum(1), rtol=1e-5, atol=1e-3)
+    g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    W = torch.randn(N, C, device=DEV) / C ** 0.5
+    bias = torch.randn(N, device=DEV) * 0.1
+    wp = (W * g[None]).half()
+    c1, c2 = wp.float().sum(1), W @ b + bias
+    y = ops.gemm_ln(x, wp, bias=c2, ln=(x._rs, c1, C, 1e-5))
+    ref = _ln_ref(x, g, b) @ W.t() + bias
+    err = (y.float() - ref).abs().max() / ref.abs().max()
+    assert float(err) < 4e-3, float(err)
+    # GEGLU: interleaved (value, gate) rows
+    inner = N // 2
+    Wi = torch.stack([W[:inner], W[inner:]], 1).reshape(N, C)
+    bi = torch.stack([bias[:inner], bias[inner:]], 1).reshape(N)
+    wpi = (Wi * g[None]).half()
+    yg = ops.gemm_ln(x, wpi, bias=Wi @ b + bi, act='geglu', ln=(x._rs, wpi.float().sum(1), C, 1e-5))
+    refg = ref[:, :inner] * F.gelu(ref[:, inner:])
+    errg = (yg.float() - refg).abs().max() / refg.abs().max()
+    assert float(errg) < 6e-3, float(errg)
+
+
+def test_gemm_layernorm_folded_columns_batched():
+    """ln_mode 2: V^T[b] = Wv LN(x[b])^T with the tokens as the B rows (per-column statistics), A broadcast over the batch."""
+    torch.manual_seed(9)
+    B, T, C = 2, 1024, 320
+    x = (torch.randn(B * T, C, device=DEV) * 1.3 + 0.4).half()
+    ident = torch.eye(C, device=DEV).half()
+    xs = ops.gemm_ln(x, ident, rowstats=True)                                  # copy through the epilogue: row statistics of x
+    assert torch.equal(xs, x)
+    g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    Wv = torch.randn(C, C, device=DEV) / C ** 0.5
+    wp = (Wv * g[None]).half()
+    vT = torch.empty(B, C, T, device=DEV, dtype=torch.float16)
+    ops.gemm_ln(wp.unsqueeze(0).expand(B, -1, -1), x.view(B, T, C), ln_cols=(xs._rs, wp.float().sum(1), Wv @ b, C, 1e-5), out=vT)
+    ref = torch.einsum('ck,btk->bct', Wv, _ln_ref(x, g, b).view(B, T, C))
+    err = (vT.float() - ref).abs().max() / ref.abs().max()
+    assert float(err) < 4e-3, float(err)

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, 'gpurun_out')
-PROF = os.path.join(ROOT, 'profiles')
+PROF = os.environ.get('DWG_PROFILES_DIR', os.path.join(ROOT, 'profiles'))          # capture_profiles.sh summarises on the GPU box into gpurun_out/
 
 METRICS = [
     ('gpu__time_duration.sum', 'duration'),
