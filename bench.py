@@ -380,12 +380,12 @@ def run_dwg(args):
         except Exception as e:                       # reported, never fatal for the headline number
             roof_r = {'error': f'{type(e).__name__}: {e}'}
         if roof is not None:
-            tj = os.path.join(ROOT, 'profiles', 'r1c_gemm_traffic.json')
+            tj = os.path.join(ROOT, 'profiles', 'r2c_gemm_traffic.json')
             if os.path.exists(tj):
                 t = json.load(open(tj))
                 roof['traffic'] = round(t['gemm']['dram_bytes_per_launch'] / 1e6, 3)
                 roof['traffic_unit'] = 'MB of DRAM read+write per launch, mean over the %d gemm_kernel launches of one step (ncu, %s)' % (
-                    t['gemm']['launches'], 'profiles/r1c_gemm_traffic.json')
+                    t['gemm']['launches'], 'profiles/r2c_gemm_traffic.json')
                 n_gemm = sum(1 for _, _, _, kind in prof if not kind.startswith('attention'))
                 roof['algorithmic_MB_per_launch'] = round(ops.PROFILE_BYTES / 1e6 / max(n_gemm, 1), 3)
 

@@ -60,6 +60,7 @@ class ControlNetScoreDistillation:
         self.timestep = None
         self.two_streams = True                 # ControlNet beside the UNet encoder (_controlnet_unet)
         self._side = None
+        self._helpers = None
         self._prepared = None                   # results of prepare() waiting for the next __call__
 
     # ---- CUDA graphs: the diffusion blocks have static shapes; one capture each for
@@ -174,6 +175,7 @@ class ControlNetScoreDistillation:
         so the two chains fill each other's gaps; fork/join are graph edges under CUDA-graph capture."""
         B = x2.shape[0]
         if not self.two_streams:
+            self.unet.helper = self.controlnet.helper = None
             pre_c = self.controlnet.prepare(self.timestep, ctx, B, cond)
             skips_c, h_c = self.controlnet.features(x2, pre_c, cond)
             state = self.unet.encode(x2, self.timestep, ctx)
@@ -183,6 +185,11 @@ class ControlNetScoreDistillation:
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
         side = self._side
+        if self._helpers is None and os.environ.get('DWG_NO_HELPERS') != '1':
+            # one helper stream per network (own split-K lanes 2 / 3): ResNet shortcuts and V projections run beside their main chains
+            self._helpers = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        if self._helpers is not None:
+            self.unet.helper, self.controlnet.helper = (self._helpers[0], 2), (self._helpers[1], 3)
         prep, self._prepared = self._prepared, None
         pre_c = prep['controlnet'] if prep else None
         pre_u = prep['unet'] if prep else None

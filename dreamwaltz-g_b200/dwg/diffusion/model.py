@@ -106,7 +106,7 @@ def timestep_embedding(t, dim):
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
-def attention(W, p, x, ctx, heads, residual, kv=None):
+def attention(W, p, x, ctx, heads, residual, kv=None, helper=None):
     """x [B,T,C] fp16 (queries), ctx [B,Tk,Ck] fp16.  Returns to_out(softmax(QK^T/sqrt(d)) V) + residual.
     V is produced transposed ([B,C,Tk], the K-major operand of the PV matmul) by swapping the
     operands of its projection GEMM, so no transpose pass exists.  ``kv`` = precomputed (K, V^T)
@@ -115,25 +115,31 @@ def attention(W, p, x, ctx, heads, residual, kv=None):
     Tk = ctx.shape[1]
     hd = C // heads
     Tkp = (Tk + 7) // 8 * 8
-    k3 = None
-    if kv is None and ctx is x and (p + '.to_qk') in W.w:
-        # self-attention: Q and K projections of the same input as ONE GEMM (weights concatenated at load time);
-        # the attention kernel takes the two halves as strided views
-        qk = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_qk']).view(B, T, 2 * C)
-        q3, k3 = qk[:, :, :C], qk[:, :, C:]
-    else:
-        q3 = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_q'], bias=W.b.get(p + '.to_q')).view(B, T, C)
-    if kv is not None:
-        k3, vT = kv
-    else:
-        if k3 is None:
-            k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
+    def v_transposed():
         vT = torch.zeros(B, C, Tkp, device=x.device, dtype=F16) if Tkp != Tk else torch.empty(B, C, Tkp, device=x.device, dtype=F16)
         wv = W.w[p + '.to_v']
         # ONE batched launch: the weight matrix is the (broadcast, batch stride 0) A operand, V^T[b] = Wv ctx[b]^T
         ops.gemm(wv.unsqueeze(0).expand(B, -1, -1), ctx, out=vT[:, :, :Tk] if Tkp != Tk else vT)
         if (p + '.to_v') in W.b:
             vT += W.b[p + '.to_v'].to(F16)[None, :, None]
+        return vT
+    k3 = None
+    if kv is None and ctx is x and (p + '.to_qk') in W.w:
+        # self-attention.  V^T is independent of the Q | K projection: it is forked onto the helper stream first (when there is
+        # one), then Q and K projections of the same input run as ONE GEMM (weights concatenated at load time); the attention
+        # kernel takes the two halves as strided views
+        with ops.forked(helper) as fk:
+            vT = v_transposed()
+        qk = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_qk']).view(B, T, 2 * C)
+        q3, k3 = qk[:, :, :C], qk[:, :, C:]
+        fk.join(vT)
+    else:
+        q3 = ops.gemm(x.reshape(B * T, C), W.w[p + '.to_q'], bias=W.b.get(p + '.to_q')).view(B, T, C)
+        if kv is not None:
+            k3, vT = kv
+        else:
+            k3 = ops.gemm(ctx.reshape(B * Tk, -1), W.w[p + '.to_k'], bias=W.b.get(p + '.to_k')).view(B, Tk, C)
+            vT = v_transposed()
     o = attn_core(q3, k3, vT, heads, Tk)
     return linear(W, p + '.to_out.0', o.reshape(B * T, C), residual=residual.reshape(B * T, C)).view(B, T, C)
 
@@ -162,6 +168,7 @@ class DiffusionNet:
         self.W = Weights(sd, device)
         self.G = cfg['groups']
         self._ctx_kv = None
+        self.helper = None                      # (stream, split-K lane) for launches forked beside the main chain (set by the guidance object)
         # all time_emb_proj layers batched into ONE GEMM per step
         names = sorted(n[:-len('.time_emb_proj')] for n in self.W.w if n.endswith('.time_emb_proj'))
         self._tproj_names = names
@@ -254,10 +261,16 @@ class DiffusionNet:
 
     def resnet(self, p, x, tproj):
         W, G = self.W, self.G
+        sc, fk = x, None
+        if W.has(p + '.conv_shortcut'):
+            # the 1x1 shortcut only meets the main chain again in conv2's epilogue: forked onto the helper stream (if any)
+            with ops.forked(self.helper) as fk:
+                sc = conv(W, p + '.conv_shortcut', x, padding=0)
         h = gn(W, p + '.norm1', x, G, 1e-5, True)
         h = conv(W, p + '.conv1', h, bias2=tproj.get(p) if tproj else None, stats=True)
         h = gn(W, p + '.norm2', h, G, 1e-5, True)
-        sc = conv(W, p + '.conv_shortcut', x, padding=0) if W.has(p + '.conv_shortcut') else x
+        if fk is not None:
+            fk.join(sc)
         return conv(W, p + '.conv2', h, residual=sc, stats=True)
 
     def transformer(self, p, x, ctx, heads):
@@ -273,7 +286,7 @@ class DiffusionNet:
         else:
             h = conv(W, p + '.proj_in', h, padding=0).view(B, H * Wd, C)
         n = ops.layer_norm(h, W.w[b + '.norm1'], W.b[b + '.norm1'])
-        h = attention(W, b + '.attn1', n, n, heads, h)
+        h = attention(W, b + '.attn1', n, n, heads, h, helper=self.helper)
         n = ops.layer_norm(h, W.w[b + '.norm2'], W.b[b + '.norm2'])
         h = attention(W, b + '.attn2', n, ctx, heads, h, kv=self._ctx_kv.get(b + '.attn2') if self._ctx_kv else None)
         n = ops.layer_norm(h, W.w[b + '.norm3'], W.b[b + '.norm3'])

@@ -515,8 +515,41 @@ def gemm_lane(lane):
     possibly concurrent stream must use lane 1.  Host-side state of THIS wrapper: the C ABI receives the workspace as an
     argument (dwg_gemm_f16_ws / dwg_conv2d_nhwc_f16_ws), the library itself keeps none."""
     global _GEMM_LANE
-    assert lane in (0, 1)
+    assert lane in (0, 1, 2, 3)
     _GEMM_LANE = int(lane)
+
+
+class forked:
+    """`with ops.forked(helper) as f:` runs the enclosed launches on a helper stream (with its own split-K lane) beside the
+    current stream -- for a launch that is independent of the next few on the main chain (a ResNet's 1x1 shortcut, the V
+    projection of an attention layer); `f.join(*tensors)` makes the current stream wait before the results are used.
+    helper = (stream, lane) or None (then everything simply runs in line).  Fork / join are graph edges under capture."""
+
+    def __init__(self, helper):
+        self.helper = helper
+
+    def __enter__(self):
+        if self.helper is None:
+            return self
+        self.stream, lane = self.helper
+        self.cur = torch.cuda.current_stream()
+        self.stream.wait_stream(self.cur)
+        self.prev_lane = _GEMM_LANE
+        self.ctx = torch.cuda.stream(self.stream)
+        self.ctx.__enter__()
+        gemm_lane(lane)
+        return self
+
+    def __exit__(self, *a):
+        if self.helper is not None:
+            gemm_lane(self.prev_lane)
+            self.ctx.__exit__(*a)
+
+    def join(self, *tensors):
+        if self.helper is not None:
+            self.cur.wait_stream(self.stream)
+            for t in tensors:
+                t.record_stream(self.cur)
 
 
 def _gemm_workspace(device):
