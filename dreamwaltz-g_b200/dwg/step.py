@@ -114,6 +114,7 @@ class SDSTrainStep:
         # stream it was created on, and a node bound to the legacy default stream would break a later capture on another stream.
         self._stream = torch.cuda.Stream(device=self.dev)
         self._graph = None
+        self._result_dev, self._res_host, self._res_ev = None, None, None
         self.graph_launches = 0
         self.host_ms = {}
         self.fixed_draws = None         # tests: {'timestep', 'noise', 'vae_eps'} tensors instead of the guidance's own random draws
@@ -146,6 +147,33 @@ class SDSTrainStep:
         loss.backward()
         return loss, ro, so, text
 
+    # ---- the step's scalar results on the host, without stalling the pipeline
+    @staticmethod
+    def _result_vector(loss, so):
+        with torch.no_grad():
+            return torch.stack([loss.detach().float().reshape(()), so['gradients'].abs().mean().float(), so['timestep'].reshape(-1)[0].float()])
+
+    def _queue_result(self):
+        """Enqueue the asynchronous D2H copy of (loss, mean |SDS gradient|, timestep) of the step just enqueued into a pinned ring."""
+        if self._result_dev is None:
+            return
+        if self._res_host is None:
+            self._res_host = [torch.zeros(3).pin_memory() for _ in range(8)]
+            self._res_ev = [torch.cuda.Event() for _ in range(8)]
+        i = self.train_step % 8
+        self._res_host[i].copy_(self._result_dev, non_blocking=True)
+        self._res_ev[i].record()
+
+    def fetch_result(self, lag=0):
+        """(loss, mean |SDS gradient|, timestep) of the step issued ``lag`` steps ago (0 = the latest: waits for it).  Reading one
+        step late (lag=1) never stalls: host input preparation of the next step overlaps the device (trainer.py logs the loss
+        the same way, after the fact)."""
+        assert 0 <= lag < 8 and self._res_host is not None
+        i = (self.train_step - lag) % 8
+        self._res_ev[i].synchronize()
+        v = self._res_host[i]
+        return float(v[0]), float(v[1]), int(v[2])
+
     def _post(self):
         if self.allreduce:
             self.bucket.all_reduce()                            # ONE collective over the flat gradient buffer
@@ -162,7 +190,9 @@ class SDSTrainStep:
         self._stream.wait_stream(cur)
         with torch.cuda.stream(self._stream):
             out = self._body(data)
+            self._result_dev = self._result_vector(out[0], out[2])
         cur.wait_stream(self._stream)
+        self._queue_result()
         self._post()
         return out
 
@@ -193,6 +223,7 @@ class SDSTrainStep:
 
         def body():
             loss, ro, so, _ = self._body(sdata, cam_dev=st['cam'])
+            self._result_dev = self._result_vector(loss, so)     # captured: the step's scalars in one 12-byte device buffer
             return loss, ro, so
         side = self._stream
         side.wait_stream(torch.cuda.current_stream())
@@ -249,6 +280,7 @@ class SDSTrainStep:
         t2 = time.perf_counter()
         L = lib()
         object.__setattr__(L, 'launches', L.launches + self.graph_launches)
+        self._queue_result()
         self._post()
         self.host_ms = {'inputs': (t1 - t0) * 1e3, 'graph_launch': (t2 - t1) * 1e3, 'post': (time.perf_counter() - t2) * 1e3}
         loss, ro, so = self._out

@@ -93,7 +93,10 @@ def test_train_step_graph_replay_equals_eager_step():
     assert torch.equal(so['gradients'], eager_sds)
     assert rel(tr.bucket.flat, eager_flat) < 1e-4, rel(tr.bucket.flat, eager_flat)
     assert tr.graph_launches > 100 and set(tr.host_ms) == {'inputs', 'graph_launch', 'post'}
+    prev = (float(loss), float(so['gradients'].abs().mean()), 400)
+    assert tr.fetch_result(lag=0) == pytest.approx(prev, rel=1e-6)              # asynchronous 12-byte read-back of the step's scalars
     loss, ro, so, _ = tr.step(d0)                                               # and another view through the same graph
+    assert tr.fetch_result(lag=1) == pytest.approx(prev, rel=1e-6)              # one step late: no stall on the step just issued
     torch.cuda.synchronize()
     assert not torch.equal(ro['image'], eager_img)
 
