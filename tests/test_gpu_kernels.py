@@ -418,6 +418,42 @@ def test_avatar_mlp_fused_forward_backward_vs_oracle(N, Nu):
         assert err < 2e-4, (name, err)
 
 
+def test_avatar_mlp_tensor_core_kernels_match_fp32_simt():
+    """The tcgen05 kernels (fp16 hi + lo operand split, fp32 accumulation in TMEM) against the plain fp32 SIMT kernels of the
+    same ABI (dwg_avatar_mlp_set_tc): outputs to 2e-6, every gradient to 1e-4 of its largest entry -- at a size with a ragged
+    last tile, a tile that straddles the unconstrained / mesh-bound boundary and more tiles than SMs x 2."""
+    from dwg import _lib
+    L = _lib.lib()
+    torch.manual_seed(5)
+    N, Nu = 40000 + 77, 33000 + 5
+    shapes = [(64, 32), (64,), (64, 64), (64,), (4, 64), (4,), (64, 95), (64,), (64, 64), (64,), (64, 64), (64,), (64, 64), (64,),
+              (3, 64), (3,), (3, 64), (3,)]
+    params = [(torch.randn(*s) * 0.25).to(DEV).requires_grad_(True) for s in shapes]
+    enc = ((torch.rand(N, 32) - 0.5) * 1e-3).to(DEV).requires_grad_(True)          # grid features right after initialisation: ~1e-4
+    pos = torch.randn(Nu, 3).to(DEV).requires_grad_(True)
+    pose = (torch.randn(1, 63) * 0.5).to(DEV)
+    res = []
+    try:
+        for tc in (0, 1):
+            L.dwg_avatar_mlp_set_tc(tc)
+            out = ops.avatar_mlp(enc, pos, pose, params, Nu)
+            ws = [torch.full_like(o, 0.5 + 0.25 * i) for i, o in enumerate(out)]
+            g = torch.autograd.grad(out, [enc, pos] + params, ws)
+            res.append(([o.detach().clone() for o in out], [x.clone() for x in g]))
+    finally:
+        L.dwg_avatar_mlp_set_tc(1)
+    for a, b in zip(*[r[0] for r in res]):
+        assert float((a - b).abs().max()) < 2e-6
+    for i, (a, b) in enumerate(zip(*[r[1] for r in res])):
+        if i == 0:
+            continue          # dL/denc: a ReLU whose pre-activation is ~0 may flip between the two arithmetic orders (checked vs the oracle above)
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-12, i
+    # dL/denc: all but a handful of rows agree
+    ge0, ge1 = res[0][1][0], res[1][1][0]
+    bad = ((ge0 - ge1).abs().amax(1) > 1e-4 * float(ge0.abs().max())).sum()
+    assert int(bad) <= 8, int(bad)
+
+
 def test_raster_full_benchmark_size_bit_exact_and_psnr():
     """cfg2 size (150k Gaussians, 512x512): index state bit-exact with the oracle, render PSNR >= 40 dB (it is exact),
     gradients within the atomics-reorder tolerance -- the north-star parity gate at BASELINE.json's own size."""
