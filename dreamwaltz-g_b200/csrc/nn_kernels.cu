@@ -178,7 +178,7 @@ gn_apply_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ stats, co
 // sums, csrc/gemm_tcgen05.cu): no statistics pass and no memset -- the prologue folds the cpg column sums of each group
 // (integer adds: exact and order-free), the body is the apply pass.  CTA 0 of every image also writes the group statistics
 // for the backward.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colstats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, act_t* __restrict__ y, fix_t* __restrict__ stats_out, int HW, int C, int G, float eps,
                    int do_silu, int rows_per_cta) {
@@ -187,6 +187,27 @@ gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colsta
     __shared__ float s_mean[64], s_rstd[64];
     const int n = blockIdx.y;
     const int c8 = C / 8, cpg = C / G;
+    // The kernel is three dependent global round trips long (column statistics -> affine parameters -> first rows): the
+    // affine parameters and the first rows of this thread do not depend on the statistics, so their loads are issued
+    // BEFORE the fold and are in flight while it runs.
+    const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
+    const h8* xp = reinterpret_cast<const h8*>(x + (size_t)n * HW * C);
+    h8* yp = reinterpret_cast<h8*>(y + (size_t)n * HW * C);
+    const int rp = c8 <= 256 ? 256 / c8 : 1;
+    const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
+    const int cv0 = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x;
+    const bool first_ok = cv0 < c8 && rl < rp;
+    float gpre[8], bpre[8];
+    h8 vpre[4];
+    const bool pre_rows = first_ok && (row0 + rl + 3 * rp < row1);
+    if (first_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { gpre[i] = gamma[cv0 * 8 + i]; bpre[i] = beta[cv0 * 8 + i]; }
+    }
+    if (pre_rows) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) vpre[u] = xp[(size_t)(row0 + rl + u * rp) * c8 + cv0];
+    }
     {
         // 8 threads per group (G <= 32) fold the group's columns
         const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
@@ -208,24 +229,25 @@ gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colsta
         }
     }
     __syncthreads();
-    const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
-    const h8* xp = reinterpret_cast<const h8*>(x + (size_t)n * HW * C);
-    h8* yp = reinterpret_cast<h8*>(y + (size_t)n * HW * C);
-    const int rp = c8 <= 256 ? 256 / c8 : 1;
-    const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
-    for (int cv = c8 <= 256 ? threadIdx.x % c8 : threadIdx.x; cv < c8 && rl < rp; cv += 256) {
+    for (int cv = cv0; cv < c8 && rl < rp; cv += 256) {
         float a[8], b[8];
+        const bool first = cv == cv0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int c = cv * 8 + i, g = c / cpg;
-            a[i] = s_rstd[g] * gamma[c];
-            b[i] = beta[c] - s_mean[g] * a[i];
+            a[i] = s_rstd[g] * (first ? gpre[i] : gamma[c]);
+            b[i] = (first ? bpre[i] : beta[c]) - s_mean[g] * a[i];
         }
         int r = row0 + rl;
         for (; r + 3 * rp < row1; r += 4 * rp) {
             h8 v[4];
+            if (first && pre_rows && r == row0 + rl) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = xp[(size_t)(r + u * rp) * c8 + cv];
+                for (int u = 0; u < 4; u++) v[u] = vpre[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = xp[(size_t)(r + u * rp) * c8 + cv];
+            }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 float f[8];

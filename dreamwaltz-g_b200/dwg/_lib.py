@@ -10,7 +10,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SO_PATH = os.path.join(_PKG, 'libdwg_sm100.so')
+SO_PATH = os.environ.get('DWG_SO') or os.path.join(_PKG, 'libdwg_sm100.so')      # DWG_SO: A/B against another build of the same ABI (tools only)
 _lib = None
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
