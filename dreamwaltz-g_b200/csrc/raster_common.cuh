@@ -49,9 +49,14 @@ struct GeomView {
     }
 };
 
+// The per-tile histogram counters and scatter cursors are split into BIN_SUB sub-counters (sub = Gaussian index & 7): a
+// silhouette tile receives 5-9k same-address atomics, which serialise at the L2 (~45 us per pass); eight addresses per tile
+// cut that chain eight-fold.  Slots inside a tile come out in a different order -- the per-tile sort fixes the order anyway.
+constexpr int BIN_SUB = 8;
 struct BinView {
-    uint32_t* tile_count;    // [T]   instances per tile (atomic histogram)
-    uint32_t* tile_fill;     // [T]   scatter cursors
+    uint32_t* tile_count;    // [T][BIN_SUB] instances per (tile, sub-counter)  (atomic histogram)
+    uint32_t* tile_fill;     // [T][BIN_SUB] scatter cursors
+    uint32_t* sub_start;     // [T][BIN_SUB] first slot of each sub-counter's share of the tile segment
     uint32_t* tile_start;    // [T+1] exclusive scan
     uint2* ranges;           // [T]   [start,end) per tile (upstream identifyTileRanges)
     uint32_t* n_runs;        // [4]   {number of sort runs, ...}
@@ -64,7 +69,7 @@ struct BinView {
     Rec* recs;               // [P]
     __host__ __device__ static int64_t run_cap(int64_t P, int T) { return T + P / SORT_CHUNK + 1; }
     __host__ __device__ static size_t header_bytes(int T) {
-        return align256(sizeof(uint32_t) * T) * 2 + align256(sizeof(uint32_t) * (T + 1)) + align256(sizeof(uint2) * T) + 256;
+        return align256(sizeof(uint32_t) * T * BIN_SUB) * 3 + align256(sizeof(uint32_t) * (T + 1)) + align256(sizeof(uint2) * T) + 256;
     }
     __host__ __device__ static size_t bytes(int64_t P, int T) {
         return header_bytes(T) + align256(sizeof(uint2) * run_cap(P, T)) + align256(sizeof(uint64_t) * P) * 3 +
@@ -72,8 +77,9 @@ struct BinView {
     }
     __host__ __device__ BinView(void* base, int64_t P, int T) {
         char* p = (char*)base;
-        tile_count = (uint32_t*)p; p += align256(sizeof(uint32_t) * T);
-        tile_fill = (uint32_t*)p; p += align256(sizeof(uint32_t) * T);
+        tile_count = (uint32_t*)p; p += align256(sizeof(uint32_t) * T * BIN_SUB);
+        tile_fill = (uint32_t*)p; p += align256(sizeof(uint32_t) * T * BIN_SUB);
+        sub_start = (uint32_t*)p; p += align256(sizeof(uint32_t) * T * BIN_SUB);
         tile_start = (uint32_t*)p; p += align256(sizeof(uint32_t) * (T + 1));
         ranges = (uint2*)p; p += align256(sizeof(uint2) * T);
         n_runs = (uint32_t*)p; p += 256;

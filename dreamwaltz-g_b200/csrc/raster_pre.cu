@@ -124,11 +124,12 @@ preprocess_kernel(int64_t N, const float* __restrict__ means3D, const float* __r
     g.conic_opacity[i] = make_float4(conic[0], conic[1], conic[2], opacities[i]);
     g.rect[i] = make_int4(x0, y0, x1, y1);
     g.tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
+    const int sub = (int)(i & (BIN_SUB - 1));
     for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) atomicAdd(&tile_count[y * gx + x], 1u);
+        for (int x = x0; x < x1; x++) atomicAdd(&tile_count[(y * gx + x) * BIN_SUB + sub], 1u);
 }
 
-// One CTA: exclusive scan of the tile counts (T <= 1024*8), ranges, total P and overflow flag.
+// One CTA: exclusive scan of the tile counts (sum of the BIN_SUB sub-counters of each tile), ranges, total P and overflow flag.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int T, BinView b, int64_t P_cap, int32_t* __restrict__ status) {
     __shared__ uint32_t s_warp[32];
@@ -138,7 +139,10 @@ tile_scan_kernel(int T, BinView b, int64_t P_cap, int32_t* __restrict__ status) 
     uint32_t max_load = 0;
     for (int base = 0; base < T; base += 1024) {
         const int t = base + threadIdx.x;
-        const uint32_t v = t < T ? b.tile_count[t] : 0u;
+        uint32_t sc[BIN_SUB];
+        uint32_t v = 0u;
+#pragma unroll
+        for (int k = 0; k < BIN_SUB; k++) { sc[k] = t < T ? b.tile_count[t * BIN_SUB + k] : 0u; v += sc[k]; }
         max_load = max(max_load, v);
         uint32_t incl = v;
 #pragma unroll
@@ -163,6 +167,9 @@ tile_scan_kernel(int T, BinView b, int64_t P_cap, int32_t* __restrict__ status) 
         const uint32_t excl = carry + warp_off + incl - v;
         if (t < T) {
             b.tile_start[t] = excl;
+            uint32_t run = excl;
+#pragma unroll
+            for (int k = 0; k < BIN_SUB; k++) { b.sub_start[t * BIN_SUB + k] = run; run += sc[k]; }
             const uint32_t e = excl + v;
             // clamp to the granted capacity so later stages never touch memory beyond it
             const uint32_t cs = (uint32_t)min((int64_t)excl, P_cap), ce = (uint32_t)min((int64_t)e, P_cap);
@@ -236,7 +243,8 @@ scatter_kernel(int64_t N, int gx, GeomView g, BinView b, int64_t P_cap) {
     for (int y = rc.y; y < rc.w; y++)
         for (int x = rc.x; x < rc.z; x++) {
             const int t = y * gx + x;
-            const uint32_t slot = b.tile_start[t] + atomicAdd(&b.tile_fill[t], 1u);
+            const int ts = t * BIN_SUB + (int)(i & (BIN_SUB - 1));
+            const uint32_t slot = b.sub_start[ts] + atomicAdd(&b.tile_fill[ts], 1u);
             if ((int64_t)slot < P_cap) { b.inst_key[slot] = key; b.inst_tile[slot] = (uint32_t)t; }
         }
 }
