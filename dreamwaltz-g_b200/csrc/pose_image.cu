@@ -66,15 +66,56 @@ pose_draw_kernel(const float* __restrict__ kp2d, int H, int W, int flags, const 
         const bool draw = ok && ix > 0 && iy > 0;                                      // `x > eps and y > eps` on ints
         s_ix[k] = draw ? ix : -1; s_iy[k] = draw ? iy : -1;
     }
+    __shared__ int s_hit;
+    if (threadIdx.x == 0) s_hit = 0;
     __syncthreads();
     const int px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
-    if (px >= W || py >= H) return;
     // adaptive_draw_poses (open_pose.py:305-318)
     int body_r = 4, stick = 4, hand_r = 4, hand_th = 2, face_r = 3;
     if (H != 512 || W != 512) {
         const float r = (float)(H + W) / 2.f / 512.f;
         body_r = max((int)(body_r * r), 1); stick = max((int)(stick * r), 1); hand_r = max((int)(hand_r * r), 1);
         hand_th = max((int)(hand_th * r), 1); face_r = max((int)(face_r * r), 1);
+    }
+    {
+        // Per-tile early out: the skeleton covers a few per cent of the image.  A tile draws nothing unless the bounding box of
+        // some primitive (keypoint disc; limb ellipse and hand edge = box of their two end points), grown by the largest
+        // radius / half-thickness + 2 pixels, meets it -- conservative, so the drawn image is unchanged.
+        const float m = (float)(max(max(body_r, stick), max(max(hand_r, hand_th), face_r)) + 2);
+        const float tx0 = (float)(blockIdx.x * 16) - m, tx1 = (float)(blockIdx.x * 16 + 15) + m;
+        const float ty0 = (float)(blockIdx.y * 16) - m, ty1 = (float)(blockIdx.y * 16 + 15) + m;
+        auto seg_hits = [&](int k1, int k2) {
+            const float ax = s_x[k1], ay = s_y[k1], bx = s_x[k2], by = s_y[k2];
+            if (isnan(ax) || isnan(ay) || isnan(bx) || isnan(by)) return false;
+            return !(fmaxf(ax, bx) < tx0 || fminf(ax, bx) > tx1 || fmaxf(ay, by) < ty0 || fminf(ay, by) > ty1);
+        };
+        bool hit = false;
+        const int t = threadIdx.x;
+        if (t < NK) {
+            const float x = s_x[t], y = s_y[t];
+            hit = !(isnan(x) || isnan(y)) && x >= tx0 && x <= tx1 && y >= ty0 && y <= ty1;
+        } else if (t < NK + 17) {
+            const int limb[17][2] = {{2, 3}, {2, 6}, {3, 4}, {4, 5}, {6, 7}, {7, 8}, {2, 9}, {9, 10}, {10, 11}, {2, 12}, {12, 13}, {13, 14}, {2, 1},
+                                     {1, 15}, {15, 17}, {1, 16}, {16, 18}};
+            // both orientations (the flip map permutes body keypoints among themselves: test the limb's own and its mirror's box)
+            const int l = t - NK;
+            hit = seg_hits(limb[l][0] - 1, limb[l][1] - 1);
+            const int flipmap[18] = {0, 1, 5, 6, 7, 2, 3, 4, 11, 12, 13, 8, 9, 10, 15, 14, 17, 16};
+            hit |= seg_hits(flipmap[limb[l][0] - 1], flipmap[limb[l][1] - 1]);
+        } else if (t < NK + 17 + 40) {
+            const int edges[20][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {0, 5}, {5, 6}, {6, 7}, {7, 8}, {0, 9}, {9, 10}, {10, 11}, {11, 12}, {0, 13},
+                                      {13, 14}, {14, 15}, {15, 16}, {0, 17}, {17, 18}, {18, 19}, {19, 20}};
+            const int e = (t - NK - 17) % 20, base = 18 + 21 * ((t - NK - 17) / 20);
+            hit = seg_hits(base + edges[e][0], base + edges[e][1]);
+        }
+        if (hit) s_hit = 1;
+        __syncthreads();
+    }
+    if (px >= W || py >= H) return;
+    if (!s_hit) {
+        const size_t HW0 = (size_t)H * W, pix0 = (size_t)py * W + px;
+        out[pix0] = 0.f; out[HW0 + pix0] = 0.f; out[2 * HW0 + pix0] = 0.f;
+        return;
     }
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
     const int body_col[18][3] = {{255, 0, 0}, {255, 85, 0}, {255, 170, 0}, {255, 255, 0}, {170, 255, 0}, {85, 255, 0}, {0, 255, 0}, {0, 255, 85},
