@@ -11,7 +11,12 @@ the rasteriser and the avatar to every trainable parameter (optimiser excluded, 
 With N > 1 every rank takes its own view per step and the parameter gradients are summed with ONE
 NCCL all-reduce (weak scaling: 1 view per GPU per step); value = views (SDS steps) per second of
 the whole job.  `--impl reference` times the CPU oracle (the reference has no CPU path and
-cannot be installed here) on the host cores.
+cannot be installed here) on the host cores; `--impl reference-gpu` (also embedded
+in the default line as `ref_gpu`) times the reference-equivalent GPU step of BASELINE.md section 3.
+`--config cfg4|cfg5` run BASELINE.json's other single-GPU configurations (300k / 1024^2 / SD2.1
+shapes; 500-frame re-enactment, frames/s).  The e2e arm feeds every step from pinned HOST memory
+(camera + pose block, prompt embeddings) and reads every step's 12-byte result back through the
+step API's pinned ring, one step late (the last one inside the timed region).
 """
 import argparse
 import json
