@@ -181,7 +181,9 @@ gn_apply_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ stats, co
 __global__ void __launch_bounds__(256, 3)
 gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colstats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, act_t* __restrict__ y, fix_t* __restrict__ stats_out, int HW, int C, int G, float eps,
-                   int do_silu, int rows_per_cta) {
+                   int do_silu, int rows_per_cta, const act_t* __restrict__ x2, const fix_t* __restrict__ colstats2, int C1) {
+    // x2 != null: the input is the channel concatenation [x (C1 channels) | x2 (C - C1 channels)] of two tensors that are
+    // never materialised side by side (the UNet decoder's skip concat): columns < C1 come from x / colstats, the rest from x2.
     pdl_wait();
     pdl_trigger();
     __shared__ float s_mean[64], s_rstd[64];
@@ -191,7 +193,10 @@ gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colsta
     // affine parameters and the first rows of this thread do not depend on the statistics, so their loads are issued
     // BEFORE the fold and are in flight while it runs.
     const int row0 = blockIdx.x * rows_per_cta, row1 = min(HW, row0 + rows_per_cta);
-    const h8* xp = reinterpret_cast<const h8*>(x + (size_t)n * HW * C);
+    const int c8a = C1 / 8, c8b = c8 - c8a;
+    const h8* xpa = reinterpret_cast<const h8*>(x + (size_t)n * HW * C1);
+    const h8* xpb = x2 ? reinterpret_cast<const h8*>(x2 + (size_t)n * HW * (C - C1)) : nullptr;
+    auto load_x = [&](int r, int cv) { return cv < c8a ? xpa[(size_t)r * c8a + cv] : xpb[(size_t)r * c8b + (cv - c8a)]; };
     h8* yp = reinterpret_cast<h8*>(y + (size_t)n * HW * C);
     const int rp = c8 <= 256 ? 256 / c8 : 1;
     const int rl = c8 <= 256 ? threadIdx.x / c8 : 0;
@@ -206,16 +211,22 @@ gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colsta
     }
     if (pre_rows) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) vpre[u] = xp[(size_t)(row0 + rl + u * rp) * c8 + cv0];
+        for (int u = 0; u < 4; u++) vpre[u] = load_x(row0 + rl + u * rp, cv0);
     }
     {
         // 8 threads per group (G <= 32) fold the group's columns
         const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
         long long S = 0, Q = 0;
         if (g < G) {
+            const int Cb = C - C1;
             for (int slot = 0; slot < 4; slot++) {                // the producer spreads its atomics over 4 slots (m_tile & 3)
-                const fix_t* cs = colstats + (((size_t)slot * gridDim.y + n) * C + (size_t)g * cpg) * 2;
-                for (int k = sub; k < cpg; k += 8) { S += (long long)cs[2 * k]; Q += (long long)cs[2 * k + 1]; }
+                const fix_t* csa = colstats + (((size_t)slot * gridDim.y + n) * C1) * 2;
+                const fix_t* csb = colstats2 ? colstats2 + (((size_t)slot * gridDim.y + n) * Cb) * 2 : nullptr;
+                for (int k = sub; k < cpg; k += 8) {
+                    const int c = g * cpg + k;
+                    const fix_t* cs = c < C1 ? csa + 2 * (size_t)c : csb + 2 * (size_t)(c - C1);
+                    S += (long long)cs[0]; Q += (long long)cs[1];
+                }
             }
         }
 #pragma unroll
@@ -246,7 +257,7 @@ gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colsta
                 for (int u = 0; u < 4; u++) v[u] = vpre[u];
             } else {
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = xp[(size_t)(r + u * rp) * c8 + cv];
+                for (int u = 0; u < 4; u++) v[u] = load_x(r + u * rp, cv);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -262,7 +273,7 @@ gn_apply_cs_kernel(const act_t* __restrict__ x, const fix_t* __restrict__ colsta
         }
         for (; r < row1; r += rp) {
             float f[8];
-            unpack8(xp[(size_t)r * c8 + cv], f);
+            unpack8(load_x(r, cv), f);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 float o = fmaf(f[i], a[i], b[i]);
@@ -874,10 +885,11 @@ extern "C" int dwg_groupnorm_fwd(const void* x, const float* gamma, const float*
     return check_launch("dwg_groupnorm_fwd");
 }
 
-extern "C" int dwg_groupnorm_apply_cs(const void* x, const float* gamma, const float* beta, void* y, const void* colstats, void* stats_out,
-                                      int N, int HW, int C, int G, float eps, int do_silu, void* stream) {
+static int gn_apply_cs_impl(const void* x, const void* x2, int C1, const float* gamma, const float* beta, void* y, const void* colstats,
+                            const void* colstats2, void* stats_out, int N, int HW, int C, int G, float eps, int do_silu, void* stream, const char* what) {
     DWG_REQUIRE(x && gamma && beta && y && colstats, "null pointer");
     DWG_REQUIRE(C % 8 == 0 && C % G == 0 && G <= 32 && al16(x) && al16(y), "C must be a multiple of 8 and of G, G <= 32; 16-byte aligned tensors");
+    DWG_REQUIRE(!x2 || (colstats2 && C1 > 0 && C1 < C && C1 % 8 == 0 && al16(x2)), "two-source form: C1 in (0, C), a multiple of 8, second statistics given");
     cudaStream_t st = (cudaStream_t)stream;
     const int rp_ = (C / 8) <= 256 ? 256 / (C / 8) : 1;
     int rows_per_cta = (int)(((int64_t)N * HW + 4 * kNumSMs - 1) / (4 * kNumSMs));
@@ -885,8 +897,19 @@ extern "C" int dwg_groupnorm_apply_cs(const void* x, const float* gamma, const f
     if (rows_per_cta > 64 * rp_) rows_per_cta = 64 * rp_;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, N);
     launch_pdl(gn_apply_cs_kernel, grid, dim3(256), 0, st, (const h16*)x, (const fix_t*)colstats, gamma, beta, (h16*)y, (fix_t*)stats_out, HW, C, G, eps,
-               do_silu & 1, rows_per_cta);
-    return check_launch("dwg_groupnorm_apply_cs");
+               do_silu & 1, rows_per_cta, (const h16*)x2, (const fix_t*)colstats2, x2 ? C1 : C);
+    return check_launch(what);
+}
+extern "C" int dwg_groupnorm_apply_cs(const void* x, const float* gamma, const float* beta, void* y, const void* colstats, void* stats_out,
+                                      int N, int HW, int C, int G, float eps, int do_silu, void* stream) {
+    return gn_apply_cs_impl(x, nullptr, C, gamma, beta, y, colstats, nullptr, stats_out, N, HW, C, G, eps, do_silu, stream, "dwg_groupnorm_apply_cs");
+}
+/* GroupNorm(+SiLU) of the channel concatenation [x1 (C1 channels) | x2 (C - C1 channels)] without materialising it: each source comes
+ * with its own column statistics (see include/dwg.h). */
+extern "C" int dwg_groupnorm_apply_cs2(const void* x1, const void* x2, int C1, const float* gamma, const float* beta, void* y, const void* colstats1,
+                                       const void* colstats2, void* stats_out, int N, int HW, int C, int G, float eps, int do_silu, void* stream) {
+    DWG_REQUIRE(x2 && colstats2, "null pointer");
+    return gn_apply_cs_impl(x1, x2, C1, gamma, beta, y, colstats1, colstats2, stats_out, N, HW, C, G, eps, do_silu, stream, "dwg_groupnorm_apply_cs2");
 }
 
 extern "C" int dwg_groupnorm_bwd(const void* x, const void* dy, const void* stats_, const float* gamma, const float* beta,

@@ -67,6 +67,7 @@ class Weights:
 
 
 STATS_IN_EPILOGUE = os.environ.get('DWG_NO_EPILOGUE_STATS') != '1'      # GroupNorm statistics from the producing epilogue (A/B switch)
+CAT_FREE = os.environ.get('DWG_NO_CATFREE') != '1'                      # decoder skip concatenations never materialised (A/B switch)
 # LayerNorms folded into the consuming GEMM epilogues (ops.gemm_ln).  Parity-neutral and 69 fewer launches per step, but MEASURED
 # 0.1 ms SLOWER than the three LayerNorm kernels per block at the benchmark's size (13.88 vs 13.77 ms/step, same box, DESIGN.md
 # section 6): off by default, DWG_LN_FOLD=1 enables it.
@@ -168,6 +169,7 @@ class DiffusionNet:
         self.W = Weights(sd, device)
         self.G = cfg['groups']
         self._ctx_kv = None
+        self._sc_split = {}
         self.helper = None                      # (stream, split-K lane) for launches forked beside the main chain (set by the guidance object)
         # all time_emb_proj layers batched into ONE GEMM per step
         names = sorted(n[:-len('.time_emb_proj')] for n in self.W.w if n.endswith('.time_emb_proj'))
@@ -259,14 +261,27 @@ class DiffusionNet:
         ctx = ctx.to(F16).contiguous()
         return {'tproj': self.time_embed(t, B), 'ctx': ctx, 'ctx_kv': self.project_context(ctx)}
 
-    def resnet(self, p, x, tproj):
+    def resnet(self, p, x, tproj, x2=None):
+        """x2 (decoder): the ResNet input is the channel concatenation [x | x2] (skip connection), which is never built: norm1 reads
+        both tensors (ops.group_norm_cat) and the 1x1 shortcut is the sum of two convolutions over the two channel ranges."""
         W, G = self.W, self.G
+        if x2 is not None and not (CAT_FREE and STATS_IN_EPILOGUE and getattr(x, '_cs', None) is not None and getattr(x2, '_cs', None) is not None
+                                   and W.has(p + '.conv_shortcut')):
+            x, x2 = ops.cat_channels(x, x2), None
         sc, fk = x, None
         if W.has(p + '.conv_shortcut'):
             # the 1x1 shortcut only meets the main chain again in conv2's epilogue: forked onto the helper stream (if any)
             with ops.forked(self.helper) as fk:
-                sc = conv(W, p + '.conv_shortcut', x, padding=0)
-        h = gn(W, p + '.norm1', x, G, 1e-5, True)
+                if x2 is None:
+                    sc = conv(W, p + '.conv_shortcut', x, padding=0)
+                else:
+                    wa, wb = self._shortcut_halves(p + '.conv_shortcut', x.shape[-1])
+                    sc = ops.conv2d_nhwc(x2, wb, padding=0)
+                    sc = ops.conv2d_nhwc(x, wa, bias=W.b.get(p + '.conv_shortcut'), residual=sc, padding=0)
+        if x2 is None:
+            h = gn(W, p + '.norm1', x, G, 1e-5, True)
+        else:
+            h = ops.group_norm_cat(x, x2, W.w[p + '.norm1'], W.b[p + '.norm1'], G, 1e-5, True)
         h = conv(W, p + '.conv1', h, bias2=tproj.get(p) if tproj else None, stats=True)
         h = gn(W, p + '.norm2', h, G, 1e-5, True)
         if fk is not None:
@@ -295,6 +310,14 @@ class DiffusionNet:
         if lin_proj:
             return _view_keep_stats(linear(W, p + '.proj_out', h.view(B * H * Wd, C), residual=x.view(B * H * Wd, C), stats_rows=H * Wd), B, H, Wd, C)
         return conv(W, p + '.proj_out', h, padding=0, residual=x, stats=True)
+
+    def _shortcut_halves(self, name, C1):
+        """The 1x1 shortcut weight [Cout,1,1,C1+C2] split along its input channels (cached)."""
+        key = (name, C1)
+        if key not in self._sc_split:
+            w = self.W.w[name]
+            self._sc_split[key] = (w[..., :C1].contiguous(), w[..., C1:].contiguous())
+        return self._sc_split[key]
 
     def _transformer_folded(self, p, b, x, hn, ctx, heads, lin_proj):
         """The transformer block without LayerNorm kernels: every producer of a normalised tensor leaves the row statistics
@@ -464,8 +487,7 @@ class UNet(DiffusionNet):
         skips = list(skips)
         for i in range(nb):
             for j in range(cfg['layers_per_block'] + 1):
-                h = ops.cat_channels(h, skips.pop())
-                h = self.resnet(f'up_blocks.{i}.resnets.{j}', h, tproj)
+                h = self.resnet(f'up_blocks.{i}.resnets.{j}', h, tproj, x2=skips.pop())      # [h | skip] is never materialised
                 if i > 0:
                     h = self.transformer(f'up_blocks.{i}.attentions.{j}', h, ctx, self.heads_at(nb - 1 - i))
             if i < nb - 1:

@@ -796,6 +796,22 @@ def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, return_stats=Fal
     return (y, stats) if return_stats else y
 
 
+def group_norm_cat(x1, x2, gamma, beta, groups=32, eps=1e-5, silu=False):
+    """[SiLU](GroupNorm(cat([x1, x2], channel))) without the concatenation (dwg_groupnorm_apply_cs2): both inputs carry the column
+    statistics of their producing epilogues (x._cs).  Returns the normalised [N, ..., C1 + C2] tensor."""
+    _chk_f16(x1), _chk_f16(x2)
+    assert x1.is_contiguous() and x2.is_contiguous() and x1.shape[:-1] == x2.shape[:-1] and groups <= 32
+    N, C1, C2 = x1.shape[0], x1.shape[-1], x2.shape[-1]
+    C = C1 + C2
+    HW = x1.numel() // (N * C1)
+    cs1, cs2 = x1._cs, x2._cs
+    assert cs1.shape == (4, N, C1, 2) and cs2.shape == (4, N, C2, 2) and cs1.is_contiguous() and cs2.is_contiguous()
+    y = torch.empty(x1.shape[:-1] + (C,), device=x1.device, dtype=torch.float16)
+    check(lib().dwg_groupnorm_apply_cs2(ptr(x1), ptr(x2), C1, ptr(gamma), ptr(beta), ptr(y), ptr(cs1), ptr(cs2), None, N, HW, C, groups,
+                                        float(eps), int(silu), stream()), 'dwg_groupnorm_apply_cs2')
+    return y
+
+
 def cat_channels(a, b):
     """torch.cat([a, b], dim=-1) of two channels-last activations, carrying their column statistics along (the statistics of
     a channel concatenation are the concatenation of the statistics)."""

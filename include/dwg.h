@@ -297,6 +297,11 @@ int dwg_groupnorm_set_fused(int on);
  * stats_out i64 [N,G,2] (optional) receives the group statistics in the format dwg_groupnorm_bwd consumes. */
 int dwg_groupnorm_apply_cs(const void* x, const float* gamma, const float* beta, void* y, const void* colstats, void* stats_out,
                            int N, int HW, int C, int G, float eps, int do_silu, void* stream);
+/* The same for the channel concatenation [x1 (C1 channels) | x2 (C - C1)] of two tensors that are never stored side by side (the UNet
+ * decoder's skip connections, diffusers UNet2DConditionModel up blocks behind core/guidance/controlnet.py:98-114): every source
+ * brings its own column statistics; y [N,HW,C] is the normalised concatenation. */
+int dwg_groupnorm_apply_cs2(const void* x1, const void* x2, int C1, const float* gamma, const float* beta, void* y, const void* colstats1,
+                            const void* colstats2, void* stats_out, int N, int HW, int C, int G, float eps, int do_silu, void* stream);
 /* dx = d/dx [SiLU](GroupNorm(x)) . dy  (+ dx_add if given);  bstats [N,G,2] i64 workspace (2^-36 fixed point) */
 int dwg_groupnorm_bwd(const void* x, const void* dy, const void* stats, const float* gamma, const float* beta,
                       const void* dx_add, void* dx, void* bstats, int N, int HW, int C, int G, float eps,

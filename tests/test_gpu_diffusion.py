@@ -230,3 +230,22 @@ def test_layernorm_folding_matches_layernorm_kernels(monkeypatch):
         outs.append(net.forward(x, t, ctx, None, None).float())
     rel = float((outs[1] - outs[0]).norm() / outs[0].norm())
     assert rel < 5e-3, rel
+
+
+def test_group_norm_of_a_concatenation_without_the_concatenation():
+    """dwg_groupnorm_apply_cs2: GroupNorm(+SiLU) of cat([x1, x2], channels) from the two tensors and their epilogue statistics,
+    against the one-tensor path on the materialised concatenation (bitwise: same statistics, same arithmetic)."""
+    from dwg import ops
+    torch.manual_seed(11)
+    for C1, C2 in ((640, 320), (1280, 640), (320, 320)):
+        xin = torch.randn(2, 32, 32, 64, device=DEV).half()
+        w1 = (torch.randn(C1, 3, 3, 64, device=DEV) * 0.05).half()
+        w2 = (torch.randn(C2, 3, 3, 64, device=DEV) * 0.05).half()
+        x1, x2 = ops.conv2d_nhwc(xin, w1, stats=True), ops.conv2d_nhwc(xin, w2, stats=True)
+        g, b = torch.rand(C1 + C2, device=DEV) + 0.5, torch.randn(C1 + C2, device=DEV) * 0.1
+        y = ops.group_norm_cat(x1, x2, g, b, 32, 1e-5, True)
+        xc = ops.cat_channels(x1, x2)
+        ref = ops.group_norm(xc, g, b, 32, 1e-5, True, colstats=xc._cs)
+        assert torch.equal(y, ref)
+        ref32 = torch.nn.functional.silu(torch.nn.functional.group_norm(xc.float().permute(0, 3, 1, 2), 32, g, b, 1e-5)).permute(0, 2, 3, 1)
+        assert float((y.float() - ref32).abs().max()) < 2e-2
