@@ -960,6 +960,56 @@ extern "C" int dwg_geglu(const void* x, void* y, int64_t rows, int inner, void* 
     return check_launch("dwg_geglu");
 }
 
+// ---------------------------------------------------------------------------- layout boundary kernels
+// The network boundaries of the diffusion path change layout AND type: planar fp32 (images, latents: the reference's NCHW tensors)
+// <-> channels-last fp16 padded to 8 channels (the tcgen05 convolutions' operand).  One kernel each way instead of
+// permute + pad + cast (+ scale) as three or four torch kernels.
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc8_kernel(const float* __restrict__ src, act_t* __restrict__ dst, int C, int64_t HW, int Cp, float scale, float shift, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = one pixel's 8-channel vector
+    if (i >= total) return;
+    const int v8 = Cp / 8;
+    const int64_t pix = i / v8;
+    const int cv = (int)(i - pix * v8);
+    const int64_t n = pix / HW, p = pix - n * HW;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = cv * 8 + k;
+        f[k] = c < C ? fmaf(src[(n * C + c) * HW + p], scale, shift) : 0.f;
+    }
+    reinterpret_cast<h8*>(dst)[i] = pack8(f);
+}
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const act_t* __restrict__ src, float* __restrict__ dst, int C, int64_t HW, int Cp, float scale, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = one pixel (C <= 8 valid channels of the first vector)
+    if (i >= total) return;
+    const int64_t n = i / HW, p = i - n * HW;
+    if ((Cp & 7) == 0) {
+        float f[8];
+        unpack8(reinterpret_cast<const h8*>(src + i * Cp)[0], f);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < C) dst[(n * C + k) * HW + p] = f[k] * scale;
+    } else {                                                     // unpadded rows (a 3-channel dgrad output): scalar reads
+        for (int k = 0; k < C; k++) dst[(n * C + k) * HW + p] = act_to_f(src[i * Cp + k]) * scale;
+    }
+}
+/* dst [N,H,W,Cp] fp16 (Cp = C rounded up to 8, padding channels zero) = scale * src [N,C,H,W] fp32 + shift */
+extern "C" int dwg_nchw_f32_to_nhwc_f16(const float* src, void* dst, int N, int C, int64_t HW, int Cp, float scale, float shift, void* stream) {
+    DWG_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0 && Cp % 8 == 0 && Cp >= C && al16(dst), "bad arguments");
+    const int64_t total = (int64_t)N * HW * (Cp / 8);
+    nchw_to_nhwc8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (h16*)dst, C, HW, Cp, scale, shift, total);
+    return check_launch("dwg_nchw_f32_to_nhwc_f16");
+}
+/* dst [N,C,H,W] fp32 = scale * src [N,H,W,Cp][..., :C] (C <= 8) */
+extern "C" int dwg_nhwc_f16_to_nchw_f32(const void* src, float* dst, int N, int C, int64_t HW, int Cp, float scale, void* stream) {
+    DWG_REQUIRE(src && dst && N > 0 && C > 0 && C <= 8 && HW > 0 && Cp >= C && (Cp % 8 != 0 || al16(src)), "bad arguments");
+    const int64_t total = (int64_t)N * HW;
+    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const h16*)src, dst, C, HW, Cp, scale, total);
+    return check_launch("dwg_nhwc_f16_to_nchw_f32");
+}
+
 extern "C" int dwg_eltwise_f16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream) {
     DWG_REQUIRE(x && y && n % 8 == 0 && mode >= 0 && mode <= 2 && (mode == 0 || a), "bad arguments");
     launch_pdl(eltwise_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, (const h16*)x, (const h16*)a, (h16*)y, n / 8, mode);

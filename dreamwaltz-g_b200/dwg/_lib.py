@@ -82,6 +82,8 @@ SIGNATURES = {
     'dwg_groupnorm_set_fused': (c_int, [c_int]),
     'dwg_groupnorm_fwd': (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     'dwg_groupnorm_apply_cs': (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    'dwg_nchw_f32_to_nhwc_f16': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, c_float, c_void_p]),
+    'dwg_nhwc_f16_to_nchw_f32': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, c_void_p]),
     'dwg_groupnorm_apply_cs2': (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     'dwg_groupnorm_bwd': (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     'dwg_layernorm_fwd': (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),
@@ -124,7 +126,7 @@ def lib():
 KERNELS_PER_CALL = {
     'dwg_lbs_skin_fwd': 1, 'dwg_lbs_skin_bwd': 1, 'dwg_sh_eval_fwd': 1, 'dwg_sh_eval_bwd': 1,
     'dwg_grid_encode_fwd': 1, 'dwg_grid_encode_bwd': 1, 'dwg_avatar_mlp_fwd': 1, 'dwg_avatar_mlp_bwd': 2, 'dwg_raster_forward': 12, 'dwg_raster_backward': 2,
-    'dwg_gemm_f16': 1, 'dwg_conv2d_nhwc_f16': 1, 'dwg_gemm_f16_ws': 1, 'dwg_gemm_f16_ln': 1, 'dwg_conv2d_nhwc_f16_ws': 1, 'dwg_groupnorm_fwd': 2, 'dwg_groupnorm_bwd': 2, 'dwg_groupnorm_apply_cs': 1, 'dwg_groupnorm_apply_cs2': 1,
+    'dwg_gemm_f16': 1, 'dwg_conv2d_nhwc_f16': 1, 'dwg_gemm_f16_ws': 1, 'dwg_gemm_f16_ln': 1, 'dwg_conv2d_nhwc_f16_ws': 1, 'dwg_groupnorm_fwd': 2, 'dwg_groupnorm_bwd': 2, 'dwg_groupnorm_apply_cs': 1, 'dwg_groupnorm_apply_cs2': 1, 'dwg_nchw_f32_to_nhwc_f16': 1, 'dwg_nhwc_f16_to_nchw_f32': 1,
     'dwg_layernorm_fwd': 1, 'dwg_softmax_rows': 1, 'dwg_softmax_rows_bwd': 1, 'dwg_geglu': 1,
     'dwg_eltwise_f16': 1, 'dwg_sds_grad': 1, 'dwg_attention_fwd': 1, 'dwg_adam_step': 2, 'dwg_grid_level_table': 1, 'dwg_frame_pack': 1, 'dwg_glbs_joints': 1, 'dwg_glbs_vertices': 1,
     'dwg_mesh_gaussians_fwd': 2, 'dwg_mesh_gaussians_bwd': 1, 'dwg_pose_keypoints_2d': 1, 'dwg_pose_image': 1,

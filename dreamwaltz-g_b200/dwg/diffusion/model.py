@@ -375,8 +375,11 @@ class DiffusionNet:
         return self.resnet('mid_block.resnets.1', h, tproj)
 
 
-def to_nhwc_f16(x_nchw):
-    return _pad_c(x_nchw.permute(0, 2, 3, 1)).to(F16).contiguous()
+def to_nhwc_f16(x_nchw, scale=1.0, shift=0.0):
+    """[N,C,H,W] -> channels-last fp16, channels zero-padded to a multiple of 8 (one kernel: dwg_nchw_f32_to_nhwc_f16)."""
+    if x_nchw.is_cuda and x_nchw.dtype == torch.float32:
+        return ops.nchw_to_nhwc_f16(x_nchw, scale, shift)
+    return _pad_c((x_nchw * scale + shift).permute(0, 2, 3, 1)).to(F16).contiguous()
 
 
 class ControlNet(DiffusionNet):
@@ -540,7 +543,7 @@ class VAEEncoder:
         W, cfg, G = self.W, self.cfg, self.G
         tape = [] if tape is None else tape
         nb = len(cfg['block_out'])
-        x = to_nhwc_f16(2.0 * images01_nchw - 1.0)
+        x = to_nhwc_f16(images01_nchw, 2.0, -1.0)                          # [0,1] -> [-1,1] in the same kernel
         h = conv(W, 'encoder.conv_in', x, stats=True)
         for i in range(nb):
             for j in range(cfg['layers_per_block']):
@@ -624,7 +627,7 @@ class VAEEncoder:
                 up[:, ::2, ::2] = g                                       # zero-insertion (data movement)
                 g = ops.conv2d_nhwc(up, W.dg[name], stride=1, padding=(2, 2), out_hw=(Hh, Ww))
         g = self._dgrad('encoder.conv_in', g)                               # [B,H,W,8] (3 valid channels)
-        return 2.0 * g[..., :3].float().permute(0, 3, 1, 2).contiguous()
+        return ops.nhwc_f16_to_nchw(g, 3, 2.0)                              # d(2x - 1)/dx = 2, layout + type change in one kernel
 
 
 class _VaeEncodeFn(torch.autograd.Function):

@@ -812,6 +812,26 @@ def group_norm_cat(x1, x2, gamma, beta, groups=32, eps=1e-5, silu=False):
     return y
 
 
+def nchw_to_nhwc_f16(x, scale=1.0, shift=0.0):
+    """[N,C,H,W] fp32 -> [N,H,W,C8] fp16 (C padded to a multiple of 8 with zeros) = scale * x + shift, one kernel."""
+    x = f32c(x)
+    N, C, H, W = x.shape
+    Cp = (C + 7) // 8 * 8
+    y = torch.empty(N, H, W, Cp, device=x.device, dtype=torch.float16)
+    check(lib().dwg_nchw_f32_to_nhwc_f16(ptr(x), ptr(y), N, C, H * W, Cp, float(scale), float(shift), stream()), 'dwg_nchw_f32_to_nhwc_f16')
+    return y
+
+
+def nhwc_f16_to_nchw(x, C, scale=1.0):
+    """[N,H,W,Cp] fp16 (Cp >= C, padded or not) -> [N,C,H,W] fp32 = scale * x[..., :C] (C <= 8), one kernel."""
+    _chk_f16(x)
+    assert x.is_contiguous() and x.dim() == 4 and C <= 8
+    N, H, W, Cp = x.shape
+    y = torch.empty(N, C, H, W, device=x.device, dtype=torch.float32)
+    check(lib().dwg_nhwc_f16_to_nchw_f32(ptr(x), ptr(y), N, C, H * W, Cp, float(scale), stream()), 'dwg_nhwc_f16_to_nchw_f32')
+    return y
+
+
 def cat_channels(a, b):
     """torch.cat([a, b], dim=-1) of two channels-last activations, carrying their column statistics along (the statistics of
     a channel concatenation are the concatenation of the statistics)."""

@@ -315,6 +315,11 @@ int dwg_softmax_rows_bwd(const void* p, void* dp, int64_t rows, int cols_pad, vo
 int dwg_geglu(const void* x, void* y, int64_t rows, int inner, void* stream);
 /* mode 0: y = silu(x); 1: y = x + a; 2: y = a * silu'(x)   (n bf16 elements, n % 8 == 0) */
 int dwg_eltwise_f16(const void* x, const void* a, void* y, int64_t n, int mode, void* stream);
+/* Layout / type boundary of the diffusion path: the reference's planar fp32 tensors (images core/guidance/vae.py:34-40, latents
+ * basic.py:595-603) <-> channels-last fp16 padded to 8 channels.  dst = scale * src + shift (padding channels zero); and back:
+  * dst [N,C,H,W] fp32 = scale * src[..., :C], C <= 8 (rows of Cp elements; Cp need not be padded). */
+int dwg_nchw_f32_to_nhwc_f16(const float* src, void* dst, int N, int C, int64_t HW, int Cp, float scale, float shift, void* stream);
+int dwg_nhwc_f16_to_nchw_f32(const void* src, float* dst, int N, int C, int64_t HW, int Cp, float scale, void* stream);
 /* noise_pred = eps_u + s (eps_c - eps_u);  grad = weight * (noise_pred - noise)   (fp32) */
 int dwg_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float* grad, float* noise_pred,
                  float guidance_scale, float weight, int64_t n, void* stream);
