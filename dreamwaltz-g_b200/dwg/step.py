@@ -166,8 +166,8 @@ class SDSTrainStep:
 
     def fetch_result(self, lag=0):
         """(loss, mean |SDS gradient|, timestep) of the step issued ``lag`` steps ago (0 = the latest: waits for it).  Reading one
-        step late (lag=1) never stalls: host input preparation of the next step overlaps the device (trainer.py logs the loss
-        the same way, after the fact)."""
+        step late (lag=1) never stalls: host input preparation of the next step overlaps the device (the reference's loop,
+        core/trainer.py:856-891, does not read the loss back inside a step either)."""
         assert 0 <= lag < 8 and self._res_host is not None
         i = (self.train_step - lag) % 8
         self._res_ev[i].synchronize()
