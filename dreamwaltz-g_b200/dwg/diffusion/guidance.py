@@ -239,6 +239,24 @@ class ControlNetScoreDistillation:
             return 7.5 + (train_step - 1) * delta
         raise NotImplementedError(self.guidance_adjust)
 
+    def prepare_image(self, image, width=None, height=None):
+        """core/guidance/controlnet.py:33-55 (prepare_image): the reference hands the ControlNet condition over as a PIL image (or a
+        list of them) and resizes it on the host with LANCZOS every step; tensors / lists of tensors pass through.  Returns a
+        [B,3,height,width] fp32 tensor in [0,1] on this object's device.  The device-side producer (dwg.condition) never comes
+        through here -- it writes the tensor directly."""
+        width = width or self.default_image_size
+        height = height or self.default_image_size
+        if isinstance(image, torch.Tensor):
+            return image.to(device=self.device, dtype=torch.float32)
+        if not isinstance(image, (list, tuple)):
+            image = [image]
+        if isinstance(image[0], torch.Tensor):
+            return torch.cat([i if i.dim() == 4 else i.unsqueeze(0) for i in image], dim=0).to(device=self.device, dtype=torch.float32)
+        from PIL import Image
+        arrs = [np.array(i.convert('RGB').resize((width, height), resample=Image.Resampling.LANCZOS))[None] for i in image]
+        x = np.concatenate(arrs, axis=0).astype(np.float32) / 255.0
+        return torch.from_numpy(x.transpose(0, 3, 1, 2).copy()).to(self.device)
+
     def prepare_latents(self, inputs):
         """basic.py:354-383: a 3-channel render that is not default_image_size^2 is resized bilinearly
         (align_corners=False, differentiable) before the VAE; cfg4 renders 1024^2 and feeds SD2.1 at 768^2."""
@@ -253,6 +271,8 @@ class ControlNetScoreDistillation:
         """inputs [1,3,H,W] in [0,1] (autograd-connected); cond_inputs [1,3,S,S] in [0,1] (device tensor).
         Returns the reference's dict: latents, timestep, sources, targets, gradients, diffusion_loss."""
         assert inputs.dim() == 4 and inputs.shape[1] == 3, 'inputs must be [B,3,H,W]'
+        if cond_inputs is not None and not isinstance(cond_inputs, torch.Tensor):
+            cond_inputs = self.prepare_image(cond_inputs)       # PIL image(s) / list of tensors, as the reference passes them
         inputs = self.prepare_latents(inputs)
         if not getattr(self, '_g', None):
             ops.STATS_ARENA.reset(inputs.device)               # ONE memset serves every GroupNorm statistic of this step
