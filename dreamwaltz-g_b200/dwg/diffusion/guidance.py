@@ -42,7 +42,7 @@ class ControlNetScoreDistillation:
 
     def __init__(self, unet_sd, controlnet_sd, vae_sd, cfg=Wt.SD15, vae_cfg=Wt.VAE15, device='cuda', guidance_scale=50.0,
                  conditioning_scale=1.0, min_timestep=0.02, max_timestep=0.98, seed=0, default_image_size=512, input_interpolate=True,
-                 guidance_adjust='constant'):
+                 guidance_adjust='constant', time_sampling='uniform', time_annealing='linear'):
         self.device = device
         self.unet = M.UNet(unet_sd, cfg, device)
         self.controlnet = M.ControlNet(controlnet_sd, cfg, device)
@@ -51,6 +51,8 @@ class ControlNetScoreDistillation:
         self.initial_guidance_scale, self.guidance_adjust = guidance_scale, guidance_adjust
         self.acp = alphas_cumprod(device)
         self.t_lo, self.t_hi = int(min_timestep * 1000), int(max_timestep * 1000)
+        # guide.time_sampling / time_annealing (configs/__init__.py:261-262, core/guidance/time_prior.py:322-351); the shipped scripts use 'uniform'
+        self.time_sampling, self.time_annealing = time_sampling, time_annealing
         self.default_image_size = default_image_size     # 512 (SD1.5) / 768 (SD2.1), basic.py:296-300
         self.input_interpolate = input_interpolate       # basic.py:360-362
         self.vae_scale_factor = 8
@@ -217,8 +219,45 @@ class ControlNetScoreDistillation:
         down, mid = self.controlnet.residuals(skips_c, h_c, self.conditioning_scale, add_to=(state[1], state[0]))
         return self.unet.decode(state, down, mid, summed=True)
 
-    def get_timestep(self, batch_size):
-        return torch.randint(self.t_lo, self.t_hi + 1, (batch_size,), device=self.device,
+    def scheduled_timestep(self, train_step, max_iteration):
+        """The deterministic timestep modes of TimePrioritizedScheduler.get_timestep (time_prior.py:329-347) as a host integer,
+        None for the random ones ('uniform', 'stage').  'annealed' covers the prior-free annealing functions ('linear': p = 1,
+        'hifa': p = 0.5, optional ',t_begin,t_end[,p]' arguments; impulse window) -- time_prior.py:199-224."""
+        lo, hi = self.t_lo, self.t_hi
+        if self.time_sampling == 'constant':
+            return (lo + hi) // 2
+        if self.time_sampling == 'linear':
+            return int(hi - (train_step - 1) * ((hi - lo) / (max_iteration - 1)))
+        if self.time_sampling == 'annealed':
+            kind, *args = self.time_annealing.split(',')
+            if kind not in ('linear', 'hifa'):
+                raise NotImplementedError(f'time_annealing {kind!r}: prior-weighted annealing (dreamtime / ddpm / p2) is not part of the hot path')
+            p = 1.0 if kind == 'linear' else 0.5
+            t_begin, t_end = hi, lo
+            if len(args) >= 2:
+                t_begin, t_end = int(args[0]), int(args[1])
+            if len(args) == 3:
+                p = float(args[2])
+            assert t_begin >= t_end and hi >= t_begin and lo <= t_end
+            return int(t_begin - (t_begin - t_end) * (train_step / max_iteration) ** p)
+        return None
+
+    def get_timestep(self, batch_size, train_step=0, max_iteration=1):
+        """time_prior.py:322-351.  'uniform' (the shipped setting) and 'stage-K' draw on the device; the other modes are a host
+        integer broadcast to the batch."""
+        t = self.scheduled_timestep(train_step, max_iteration)
+        if t is not None:
+            return torch.full((batch_size,), int(t), dtype=torch.long, device=self.device)
+        lo, hi = self.t_lo, self.t_hi
+        if self.time_sampling.startswith('stage'):
+            _, *a = self.time_sampling.split('-')
+            n_stage = int(a[0]) if a else 2
+            per = (hi - lo) // n_stage
+            i_stage = min(train_step // max(max_iteration // n_stage, 1), n_stage - 1)
+            hi = lo + per * (n_stage - i_stage)                  # stage_intervals[i_stage][1]; the lower end stays t_lo ("Important!")
+        elif self.time_sampling != 'uniform':
+            raise NotImplementedError(self.time_sampling)
+        return torch.randint(lo, hi + 1, (batch_size,), device=self.device,
                              generator=None if self.use_default_generator else self.gen)
 
     def add_noise(self, latents, noise, t):
@@ -289,7 +328,7 @@ class ControlNetScoreDistillation:
             if prep is not None and self._side is not None:
                 torch.cuda.current_stream().wait_stream(self._side)      # discard: join the side stream so nothing stays in flight
             self._prepared = None
-            self.timestep = timestep if timestep is not None else self.get_timestep(inputs.shape[0])
+            self.timestep = timestep if timestep is not None else self.get_timestep(inputs.shape[0], train_step, max_iteration)
         with torch.no_grad():
             if noise is None:
                 noise = torch.randn(latents.shape, device=latents.device, generator=None if self.use_default_generator else self.gen)

@@ -200,6 +200,9 @@ class SDSTrainStep:
     def capture(self, data, warmup=3):
         """Capture the whole step (on the private stream the eager steps use as well)."""
         g = self.guidance
+        if getattr(g, 'time_sampling', 'uniform') != 'uniform' and not self.fixed_draws:
+            raise NotImplementedError("whole-step capture draws the timestep inside the graph: only time_sampling='uniform' (the shipped "
+                                      "setting) can be captured; the iteration-dependent modes run through the eager step")
         g._g = None
         g.use_default_generator = True                          # graph-safe philox state
         dev = self.dev

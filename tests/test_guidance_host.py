@@ -47,3 +47,31 @@ def test_guidance_scale_schedules():
     np.random.seed(0)
     s = [cls.get_guidance_scale(me, 1, 100) for _ in range(50)]
     assert min(s) >= 7.5 and max(s) <= 50.0
+
+
+def test_timestep_sampling_modes_follow_the_reference_formulas():
+    """TimePrioritizedScheduler.get_timestep (core/guidance/time_prior.py:322-351) for min / max timestep 0.02 / 0.98."""
+    cls = _guidance_cls()
+    me = types.SimpleNamespace(t_lo=20, t_hi=980, time_sampling='constant', time_annealing='linear', device='cpu', use_default_generator=True, gen=None)
+    me.scheduled_timestep = lambda a, b: cls.scheduled_timestep(me, a, b)
+    assert cls.get_timestep(me, 2, 5, 100).tolist() == [500, 500]
+    me.time_sampling = 'linear'
+    delta = (980 - 20) / 99
+    for step in (1, 2, 50, 100):
+        assert cls.get_timestep(me, 1, step, 100).item() == int(980 - (step - 1) * delta)
+    me.time_sampling = 'annealed'
+    for step in (0, 10, 100):
+        assert cls.get_timestep(me, 1, step, 100).item() == int(980 - 960 * (step / 100) ** 1.0)
+    me.time_annealing = 'hifa,900,100'
+    assert cls.get_timestep(me, 1, 25, 100).item() == int(900 - 800 * 0.25 ** 0.5)
+    me.time_annealing = 'linear,900,100,2.0'
+    assert cls.get_timestep(me, 1, 50, 100).item() == int(900 - 800 * 0.5 ** 2.0)
+    me.time_sampling = 'stage-3'
+    torch.manual_seed(0)
+    per = (980 - 20) // 3
+    for step, top in ((0, 20 + 3 * per), (40, 20 + 2 * per), (99, 20 + per)):
+        t = cls.get_timestep(me, 512, step, 100)
+        assert int(t.min()) >= 20 and int(t.max()) <= top and int(t.max()) > top - per // 4
+    me.time_sampling = 'uniform'
+    t = cls.get_timestep(me, 2048, 7, 100)
+    assert int(t.min()) >= 20 and int(t.max()) <= 980 and int(t.max()) > 900 and int(t.min()) < 100
